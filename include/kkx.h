@@ -1,0 +1,128 @@
+/*
+ * kkx.h -- C ABI of the B200-native Kokoro-82M inference backend.
+ *
+ * Drop-in boundary for the ONNX-Runtime session wrapper of byteowlz/kokorox
+ * (/root/reference/kokorox/src/onn/).  Each entry point names the reference interface it
+ * replaces.  Plain pointers and sizes only; every function is callable from Rust FFI
+ * (`extern "C"`), cgo, or ctypes.  No function aborts or throws across the ABI: all failures
+ * are a negative return code plus a message retrievable with kkx_last_error().
+ *
+ * Thread safety: a kkx_ctx may be shared between threads (the reference shares one
+ * `Arc<OrtKoko>` between tokio workers, ort_koko.rs:13-18, koko.rs:36-45); calls on one ctx
+ * are serialised internally, exactly like the reference's `Mutex<Session>` (ort_koko.rs:77-78).
+ * Use one ctx per GPU for multi-GPU request sharding.
+ */
+#ifndef KKX_H_
+#define KKX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kkx_ctx kkx_ctx;
+
+#if defined(__GNUC__)
+#define KKX_API __attribute__((visibility("default")))
+#else
+#define KKX_API
+#endif
+
+#define KKX_OK 0
+#define KKX_ERR_ARG (-1)      /* bad argument (null pointer, token id out of 0..177, n_tokens > 512) */
+#define KKX_ERR_IO (-2)       /* weight file missing / malformed / tensor missing              */
+#define KKX_ERR_CUDA (-3)     /* CUDA runtime error (message has the cudaError string)          */
+#define KKX_ERR_NO_DEVICE (-4)/* no CUDA device / device ordinal out of range -- there is NO CPU fallback */
+#define KKX_ERR_STATE (-5)    /* ctx not initialised ("Session is not initialized.", ort_koko.rs:88-90) */
+
+#define KKX_STYLE_DIM 256     /* ort_koko.rs:61-65: style tensor [B,256]                        */
+#define KKX_MAX_TOKENS 512    /* ALBERT max_position_embeddings; koko.rs:781-783 chunks to <=500 */
+#define KKX_SAMPLE_RATE 24000 /* koko.rs:59                                                     */
+
+/* Replaces kokorox::onn::init_ort(dylib_path) (onn/mod.rs:19-49): process-wide one-time init.
+ * Checks that a CUDA driver and at least one sm_100 device are present.  Optional: kkx_create
+ * performs the same check.  Returns KKX_OK or KKX_ERR_NO_DEVICE. */
+KKX_API int kkx_init(void);
+
+/* Replaces OrtKoko::new(model_path) -> OrtBase::load_model (ort_koko.rs:31-35,
+ * ort_base.rs:14-39): loads a KKXW weight file onto GPU `device_ordinal` and builds every
+ * derived weight layout.  On failure *out is NULL and kkx_last_error(NULL) has the reason. */
+KKX_API int kkx_create(const char* weights_path, int device_ordinal, kkx_ctx** out);
+
+/* Drop of OrtKoko (koko.rs:1338-1375 `cleanup`): frees all device and pinned host memory. */
+KKX_API void kkx_destroy(kkx_ctx* ctx);
+
+/* Error string of the last failed call on this ctx (ctx == NULL: last failed kkx_create /
+ * kkx_init on this thread).  The Rust shim turns rc<0 into Err(kkx_last_error()), matching
+ * the Result<_, String> / Box<dyn Error> returns of ort_koko.rs:31,42. */
+KKX_API const char* kkx_last_error(const kkx_ctx* ctx);
+
+/* Replaces OrtKoko::infer(tokens, styles, speed) at B=1 (ort_koko.rs:37-91; call site
+ * koko.rs:1168-1177).
+ *   tokens     [n_tokens] i64, INCLUDING the leading and trailing 0 pad (koko.rs:1168-1173);
+ *              2 <= n_tokens <= 512, ids in 0..177 (tts/vocab.rs:5-20)   -- "input_ids"
+ *   style256   [256] f32 (koko.rs:1255-1306 mix_styles row)             -- "style"
+ *   speed      > 0                                                        -- "speed"
+ *   out_audio  receives a library-owned pinned host buffer of *out_samples f32 (24 kHz mono,
+ *              = 600 * sum(pred_dur)); valid until kkx_release(ctx, ptr) -- outputs[0]
+ *   out_pred_dur  nullable; [n_tokens] predicted integer frame durations (not observable
+ *              through the reference graph; exposed for parity tests). */
+KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
+              float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur);
+
+/* Ragged batch of independent utterances (new capability; the reference only ever calls infer
+ * with B=1, koko.rs:1175, and serialises callers on a mutex).  Item b uses
+ * tokens[tok_offsets[b] .. tok_offsets[b+1]), styles[b*256 ..], speeds[b]; result b is
+ * (*out_audio)[out_sample_offsets[b] .. out_sample_offsets[b+1]) and equals what kkx_infer
+ * returns for that item alone.  out_pred_dur (nullable) is indexed like tokens. */
+KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                    const float* styles, const float* speeds, float** out_audio,
+                    int64_t* out_sample_offsets, int32_t* out_pred_dur);
+
+/* Returns an audio buffer obtained from kkx_infer / kkx_infer_batch to the library. */
+KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
+/* ---- device-resident variant (bench.py `value`: inputs already in HBM, output stays in HBM).
+ * Stages the batch on the device once; kkx_run_staged() then runs the whole forward with no
+ * host<->device payload traffic (only the per-item frame counts cross, 4 bytes per item).
+ * Returns total samples in *out_total_samples and kernel launches in *out_launches
+ * (either may be NULL). */
+KKX_API int kkx_stage_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                    const float* styles, const float* speeds);
+KKX_API int kkx_run_staged(kkx_ctx* ctx, int64_t* out_total_samples, int64_t* out_launches);
+/* Copies the result of the last kkx_run_staged to host memory. */
+KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, int64_t* out_sample_offsets,
+                     int32_t* out_pred_dur);
+
+/* ---- options.  Known keys:
+ *   "precision"   0 = fp32 SIMT everywhere, 1 = bf16 tensor-core (tcgen05) decoder+generator
+ *   "noise_seed"  seed of the on-device Philox N(0,1) generator for the SineGen noise
+ *   "max_frames"  frame budget per frame-phase group (memory control for large batches)
+ *   "stft_replicate" 0 = reflect edge padding (upstream STFT), 1 = replicate (conv-STFT export)  */
+KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value);
+KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key); /* "launches", "last_frames", "gpu_us" ... */
+
+/* ---- test-only hooks (parity harness; not used by the Rust shim) -------------------------
+ * kkx_set_noise: explicit SineGen noise, element (sample t, harmonic h) of batch item 0 at
+ *   noise[t*9+h]; n = number of floats; n == 0 returns to the on-device generator.  With a
+ *   batch, item b reads the same buffer (each item from offset 0).
+ * kkx_set_inject: teacher-force an intermediate for item 0 of the next call.  name is
+ *   "pred_dur" (int32 data), "F0" or "N" (f32 data); count = elements; count == 0 clears.
+ * kkx_debug_stage: after a call, copy a named stage tensor of the LAST frame group to host.
+ *   Returns the number of floats the stage holds (rows*cols) or <0; rows/cols are written if
+ *   non-NULL; at most `capacity` floats are copied (dst may be NULL to query the size).
+ *   Stage names match oracle/kokoro_ref.py (`bert`, `d`, `dur_logits`, `F0`, `har`, ...). */
+KKX_API int kkx_set_noise(kkx_ctx* ctx, const float* noise, int64_t n);
+KKX_API int kkx_set_inject(kkx_ctx* ctx, const char* name, const void* data, int64_t count);
+KKX_API int64_t kkx_debug_stage(kkx_ctx* ctx, const char* name, int32_t item, float* dst, int64_t capacity,
+                        int64_t* rows, int64_t* cols);
+KKX_API int kkx_debug_enable(kkx_ctx* ctx, int enable); /* keep stage tensors alive for kkx_debug_stage */
+
+/* Library / build identification, e.g. "kkx 0.1 sm_100a". */
+KKX_API const char* kkx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KKX_H_ */

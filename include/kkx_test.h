@@ -1,0 +1,35 @@
+/*
+ * kkx_test.h -- op-level test hooks of libkkx.so (parity harness only; the Rust shim binds
+ * nothing from this header).  Host pointers in, host pointers out, one ragged item; each call
+ * allocates device scratch, runs ONE hand-written kernel and copies the result back, so that
+ * tests/ can compare a kernel against the matching torch op in isolation.
+ */
+#ifndef KKX_TEST_H_
+#define KKX_TEST_H_
+#include "kkx.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Generic shifted-GEMM kernel (Conv1d / ConvTranspose1d phase / Linear), see kernels.h ConvArgs.
+ * in [rows_in, ldi]; w [ks][Ci][Co]; out [out_rows, Co] (pre-filled by the caller; rows not
+ * written keep their value); res [ceil(out_rows >> res_shift), Co] or NULL. */
+KKX_API int kkx_test_conv(int device, const float* in, int rows_in, int ldi, int Ci, const float* w,
+                          const float* bias, int Co, int ks, int dil, int pad, int stride,
+                          const float* pscale, const float* pshift, int pact, float pslope,
+                          const float* palpha, int m_len, int ors, int oro, int out_rows,
+                          const float* res, int res_rows, int res_shift, float oscale, int eact,
+                          int accumulate, float* out);
+/* xproj [N,2048], whhT [2][256][1024] -> out [N,512] */
+KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out);
+/* qkv [N,2304] -> ctx [N,768] */
+KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
+/* x [L,C] + style row (gamma|beta, 2C) -> scale [C], shift [C] (InstanceNorm stats + AdaIN) */
+KKX_API int kkx_test_adain_coef(int device, const float* x, int L, int C, const float* gamma_beta,
+                                float* scale, float* shift);
+KKX_API const char* kkx_test_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+// kernels.h -- launchers for the hand-written sm_100a kernels of the Kokoro-82M forward pass.
+// Activations are time-major [rows, C] fp32 ("NLC"), ragged items packed along rows (Level).
+#pragma once
+#include "common.h"
+
+namespace kkx {
+
+enum Act : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_SNAKE = 2, ACT_GELU_NEW = 3 };
+
+// Generic fp32 "shifted GEMM": Conv1d / ConvTranspose1d phase / Linear, with a fused
+// normalise+activate prologue on the input operand and a fused bias/activation/residual/scale
+// epilogue.  For item b and m in [0, m_len[b]):
+//   out[out_off[b] + m*ors + oro, ocol + n] (+)= oscale * ( eact( bias[n] +
+//        sum_{tap<ks} sum_{c<Ci} A(in_off[b] + m*stride + tap*dil - pad, c) * w[tap][c][n] )
+//        + res[res_off[b] + ((m*ors+oro) >> res_shift), rcol + n] )
+//   A(r, c) = pact( in[r, c] * pscale[b, c] + pshift[b, c] ) for 0 <= r - in_off[b] < in_len[b], else 0
+struct ConvArgs {
+  const float* in = nullptr; int ldi = 0;
+  const int* in_off = nullptr; const int* in_len = nullptr;
+  const int* m_len = nullptr; int max_m = 0; int B = 1;
+  const float* w = nullptr; const float* bias = nullptr;
+  int Ci = 0, Co = 0, ks = 1, dil = 1, pad = 0, stride = 1;
+  const float* pscale = nullptr; const float* pshift = nullptr; int pld = 0;
+  int pact = ACT_NONE; float pslope = 0.f; const float* palpha = nullptr;
+  float* out = nullptr; int ldo = 0; int ocol = 0; const int* out_off = nullptr;
+  int ors = 1, oro = 0;
+  int eact = ACT_NONE;
+  const float* res = nullptr; int ldr = 0; int rcol = 0; const int* res_off = nullptr;
+  int res_shift = 0;
+  float oscale = 1.f; int accumulate = 0;
+};
+void launch_conv_f32(const ConvArgs& a, cudaStream_t st);
+
+// y = act( LN(x (+res)) [* w + b] [(1+gamma_b) * . + beta_b] ), one row at a time.
+struct LnArgs {
+  const float* x = nullptr; int ldx = 0;
+  const float* res = nullptr; int ldr = 0;
+  const float* w = nullptr; const float* b = nullptr;         // affine [C] (nullable)
+  const float* ada = nullptr; int ada_ld = 0; int ada_off = 0; // per-item gamma at ada_off, beta at ada_off+C
+  float eps = 1e-5f; float slope = 1.f;                        // slope != 1 -> LeakyReLU
+  float* out = nullptr; int ldo = 0; int ocol = 0;
+  const int* off = nullptr; const int* len = nullptr; int B = 1; int max_len = 0; int C = 0;
+};
+void launch_layernorm(const LnArgs& a, cudaStream_t st);
+
+// ALBERT embeddings: word[id] + pos[t] + type[0] -> LayerNorm(128, eps 1e-12).  out [rows,128]
+void launch_albert_embed(const int* ids, const float* word, const float* pos, const float* type,
+                         const float* lnw, const float* lnb, float* out, const int* off,
+                         const int* len, int B, int max_len, cudaStream_t st);
+// out[row, 0:C] = table[ids[row], :]
+void launch_embed_rows(const int* ids, const float* table, int C, float* out, int ldo,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st);
+// out[row, ocol + c] = vec[b*ldv + voff + c]  (broadcast a per-item vector over the item's rows)
+void launch_bcast_cols(const float* vec, int ldv, int voff, int C, float* out, int ldo, int ocol,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st);
+// dst[row, dcol + c] = src[row, scol + c]
+void launch_copy_cols(const float* src, int lds, int scol, float* dst, int ldd, int dcol, int C,
+                      const int* off, const int* len, int B, int max_len, cudaStream_t st);
+// out = a + b over the items' rows, C columns (all ld = C)
+void launch_add_rows(const float* a, const float* b, float* out, int C, const int* off,
+                     const int* len, int B, int max_len, cudaStream_t st);
+// u[off[b] + dst_row] = u[off[b] + src_row] (ReflectionPad1d((1,0)) fix-up)
+void launch_copy_row(float* u, int C, int dst_row, int src_row, const int* off, int B,
+                     cudaStream_t st);
+
+// softmax(QK^T/8)V per item and head; qkv [rows, 2304] (q|k|v, head h at h*64); ctx [rows,768]
+void launch_attention(const float* qkv, float* ctx, const int* off, const int* len, int B,
+                      int max_len, cudaStream_t st);
+
+// Bidirectional LSTM recurrence, H=256.  xproj [rows, 2048] = x W_ih^T + b_ih + b_hh for
+// (fwd i,f,g,o | bwd i,f,g,o); whhT [2][256][1024] (k-major); out [rows, ldo] cols ocol..+512.
+void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
+                 const int* off, const int* len, int B, cudaStream_t st);
+
+// InstanceNorm statistics -> AdaIN coefficients.
+//   partial sums over row chunks, then scale[b,c] = rstd*(1+gamma), shift[b,c] = beta - mean*scale
+//   with gamma = sty[b*sld + soff + c], beta = sty[b*sld + soff + C + c].
+constexpr int kStatRows = 128;
+void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
+                     int B, int max_len, cudaStream_t st);  // part [B][nchunk_max][2][C]
+void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
+                       int sld, int soff, float eps, float* scale, float* shift, int B,
+                       cudaStream_t st);
+
+// Depthwise ConvTranspose1d(k3,s2,p1,op1) on lrelu(x*scale+shift): in [T,C] -> out [2T,C]
+void launch_pool_up(const float* in, int ldi, const float* scale, const float* shift, float slope,
+                    const float* w /*[C][3]*/, const float* bias, int C, float* out, int ldo,
+                    const int* in_off, const int* in_len, const int* out_off, int B, int max_len,
+                    cudaStream_t st);
+
+// Duration head (K4): dur = sum_k sigmoid(logits[row,k]) / speed_b -> rintf -> max(.,1)
+void launch_duration(const float* logits, int K, const float* speeds, int* pred_dur,
+                     float* dur_float, const int* off, const int* len, int B, int max_len,
+                     cudaStream_t st);
+// cum[b, n] = exclusive prefix sum of pred_dur over the item's tokens; total[b] = T_b
+void launch_dur_scan(const int* pred_dur, int* cum, int cum_ld, int* total, const int* off,
+                     const int* len, int B, cudaStream_t st);
+// idx[fr_off[b] + j] = token n with cum[b,n] <= j < cum[b,n] + dur[n]
+void launch_expand_idx(const int* cum, int cum_ld, const int* tok_len, int* idx, const int* fr_off,
+                       const int* fr_len, int B, int max_len, cudaStream_t st);
+// K5: out[out_off[b] + j, ocol + c] = in[in_off[b] + idx[idx_off[b] + j], c]
+void launch_gather_rows(const float* in, int ldi, const int* in_off, const int* idx,
+                        const int* fr_off, const int* fr_len, int C, float* out, int ldo, int ocol,
+                        int B, int max_len, cudaStream_t st);
+
+// Conv1d(1,1,k3,s2,p1) on a curve: x [2T] -> out[t, ocol] (ld ldo), t < T
+void launch_curve_conv(const float* x, const int* x_off, const int* x_len, const float* w3,
+                       const float* bias, float* out, int ldo, int ocol, const int* out_off,
+                       const int* out_len, int B, int max_len, cudaStream_t st);
+
+// K9 SineGen + SourceModuleHnNSF.
+//   phase: per (item, harmonic) fp64 inclusive scan of frac(f0*h/24000) over 2T coarse steps,
+//          stored as fp32 ((c*2)*pi)*300
+//   source: per sample linear x300 interpolation of the coarse phase, sin, uv gating, noise,
+//          Linear(9->1), tanh -> har_source [samples]
+void launch_sine_phase(const float* f0, const int* f0_off, const int* f0_len, float* phase,
+                       const int* ph_off /*per item, in floats*/, int B, cudaStream_t st);
+void launch_sine_source(const float* f0, const int* f0_off, const int* f0_len, const float* phase,
+                        const int* ph_off, const float* noise /*nullable, [t*9+h]*/,
+                        unsigned long long seed, const float* lin_w, const float* lin_b,
+                        float* out, const long long* s_off, int B, long long max_samples,
+                        cudaStream_t st);
+// K10 STFT (n_fft 20, hop 5, periodic hann, center): x [600T] -> har[row, 0:11]=|X|, [11:22]=angle
+void launch_stft(const float* x, const long long* s_off, float* har, int ldh, const int* h_off,
+                 const int* h_len, int replicate_pad, int B, int max_len, cudaStream_t st);
+// K11 head: mag = exp(cp[:, :11]), ph = sin(cp[:, 11:]) -> iSTFT -> audio [600T]
+void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio,
+                  const long long* s_off, int B, int max_len, cudaStream_t st);
+
+}  // namespace kkx

@@ -1,0 +1,457 @@
+// kernels_dense.cu -- fp32 SIMT shifted-GEMM (Conv1d / Linear), LayerNorm, attention, LSTM.
+// These carry the precision-critical predictor path (ALBERT -> durations -> F0/N), where the
+// integer frame durations must match the oracle bit for bit, and serve as the fp32 reference
+// configuration ("precision"=0) for the decoder/generator.
+#include "kernels.h"
+#include <math.h>
+
+namespace kkx {
+
+thread_local LaunchStats* g_launch_stats = nullptr;
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope, float alpha) {
+  if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == ACT_SNAKE) {
+    float s = sinf(alpha * v);
+    return v + (1.0f / alpha) * (s * s);
+  }
+  if (act == ACT_GELU_NEW) {
+    // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+    float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+    return 0.5f * v * (1.0f + tanhf(u));
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shifted GEMM.  256 threads, BMxBN output tile, BK=16; thread (ty,tx) owns rows ty+16*i and
+// columns tx+16*j so that smem reads are conflict-free/broadcast and global stores coalesce.
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) conv_f32_kernel(ConvArgs a) {
+  constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN];
+  const int b = blockIdx.z;
+  const int mlen = a.m_len[b];
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= mlen) return;
+  const int n0 = blockIdx.y * BN;
+  const int in_off = a.in_off[b], in_len = a.in_len[b];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* psc = a.pscale ? a.pscale + (size_t)b * a.pld : nullptr;
+  const float* psh = a.pshift ? a.pshift + (size_t)b * a.pld : nullptr;
+  const bool prologue = (psc != nullptr) || (a.pact != ACT_NONE);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+
+  for (int tap = 0; tap < a.ks; tap++) {
+    const int shift = tap * a.dil - a.pad;
+    for (int c0 = 0; c0 < a.Ci; c0 += BK) {
+      // A tile: BM x BK, channel index fastest across threads
+      for (int i = tid; i < BM * BK; i += 256) {
+        const int kk = i & (BK - 1), m = i >> 4;
+        const int c = c0 + kk, mm = m0 + m;
+        float v = 0.f;
+        if (c < a.Ci && mm < mlen) {
+          const int r = mm * a.stride + shift;
+          if (r >= 0 && r < in_len) {
+            v = a.in[(size_t)(in_off + r) * a.ldi + c];
+            if (prologue) {
+              if (psc) v = v * psc[c] + psh[c];
+              v = act_apply(v, a.pact, a.pslope, a.palpha ? a.palpha[c] : 1.f);
+            }
+          }
+        }
+        As[kk][m] = v;
+      }
+      // B tile: BK x BN, output channel fastest
+      for (int i = tid; i < BK * BN; i += 256) {
+        const int nn = i % BN, kk = i / BN;
+        const int c = c0 + kk, n = n0 + nn;
+        Bs[kk][nn] = (c < a.Ci && n < a.Co) ? a.w[((size_t)tap * a.Ci + c) * a.Co + n] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; kk++) {
+        float ar[TM], br[TN];
+#pragma unroll
+        for (int i = 0; i < TM; i++) ar[i] = As[kk][ty + 16 * i];
+#pragma unroll
+        for (int j = 0; j < TN; j++) br[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < TM; i++)
+#pragma unroll
+          for (int j = 0; j < TN; j++) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  const int out_off = a.out_off[b];
+  const int res_off = a.res ? a.res_off[b] : 0;
+#pragma unroll
+  for (int i = 0; i < TM; i++) {
+    const int mm = m0 + ty + 16 * i;
+    if (mm >= mlen) continue;
+    const int orow = mm * a.ors + a.oro;
+    float* op = a.out + (size_t)(out_off + orow) * a.ldo + a.ocol;
+    const float* rp = a.res ? a.res + (size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol : nullptr;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= a.Co) continue;
+      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      v = act_apply(v, a.eact, 0.f, 1.f);
+      if (rp) v += rp[n];
+      v *= a.oscale;
+      if (a.accumulate) v += op[n];
+      op[n] = v;
+    }
+  }
+}
+
+void launch_conv_f32(const ConvArgs& a, cudaStream_t st) {
+  if (g_dry_run) return;
+  if (a.max_m <= 0 || a.B <= 0) return;
+  // tile choice: big tiles when there is enough work to fill 148 SMs, small ones otherwise
+  const long long tiles128 = (long long)((a.max_m + 127) / 128) * ((a.Co + 127) / 128) * a.B;
+  if (a.Co >= 128 && tiles128 >= 148) {
+    dim3 g((a.max_m + 127) / 128, (a.Co + 127) / 128, a.B);
+    conv_f32_kernel<128, 128><<<g, 256, 0, st>>>(a);
+  } else if (a.Co > 32) {
+    dim3 g((a.max_m + 63) / 64, (a.Co + 63) / 64, a.B);
+    conv_f32_kernel<64, 64><<<g, 256, 0, st>>>(a);
+  } else {
+    dim3 g((a.max_m + 127) / 128, (a.Co + 31) / 32, a.B);
+    conv_f32_kernel<128, 32><<<g, 256, 0, st>>>(a);
+  }
+  post_launch("conv_f32", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the channel axis: one warp per row, two-pass (mean, then centred variance).
+__global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= a.len[b]) return;
+  const size_t row = (size_t)a.off[b] + t;
+  const float* x = a.x + row * a.ldx;
+  const float* r = a.res ? a.res + row * a.ldr : nullptr;
+  const int C = a.C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += x[c] + (r ? r[c] : 0.f);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = x[c] + (r ? r[c] : 0.f) - mean;
+    q = fmaf(d, d, q);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)C + a.eps);
+  const float* ada = a.ada ? a.ada + (size_t)b * a.ada_ld + a.ada_off : nullptr;
+  float* o = a.out + row * a.ldo + a.ocol;
+  for (int c = lane; c < C; c += 32) {
+    float v = (x[c] + (r ? r[c] : 0.f) - mean) * rstd;
+    if (a.w) v = v * a.w[c] + a.b[c];
+    if (ada) v = (1.0f + ada[c]) * v + ada[C + c];
+    if (a.slope != 1.f) v = v > 0.f ? v : v * a.slope;
+    o[c] = v;
+  }
+}
+
+void launch_layernorm(const LnArgs& a, cudaStream_t st) {
+  if (g_dry_run) return;
+  if (a.max_len <= 0) return;
+  dim3 g((a.max_len + 7) / 8, a.B);
+  layernorm_kernel<<<g, 256, 0, st>>>(a);
+  post_launch("layernorm", st);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) albert_embed_kernel(const int* ids, const float* word,
+                                                           const float* pos, const float* type,
+                                                           const float* lnw, const float* lnb,
+                                                           float* out, const int* off,
+                                                           const int* len) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= len[b]) return;
+  const size_t row = (size_t)off[b] + t;
+  const int id = ids[row];
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = lane + 32 * i;
+    v[i] = word[id * 128 + c] + type[c] + pos[t * 128 + c];
+    s += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 128.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 128.f) + 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = lane + 32 * i;
+    out[row * 128 + c] = (v[i] - mean) * rstd * lnw[c] + lnb[c];
+  }
+}
+
+void launch_albert_embed(const int* ids, const float* word, const float* pos, const float* type,
+                         const float* lnw, const float* lnb, float* out, const int* off,
+                         const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 7) / 8, B);
+  albert_embed_kernel<<<g, 256, 0, st>>>(ids, word, pos, type, lnw, lnb, out, off, len);
+  post_launch("albert_embed", st);
+}
+
+__global__ void __launch_bounds__(256) embed_rows_kernel(const int* ids, const float* table, int C,
+                                                         float* out, int ldo, const int* off,
+                                                         const int* len) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  if (t >= len[b]) return;
+  const size_t row = (size_t)off[b] + t;
+  const int id = ids[row];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[row * ldo + c] = table[(size_t)id * C + c];
+}
+void launch_embed_rows(const int* ids, const float* table, int C, float* out, int ldo,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g(max_len, B);
+  embed_rows_kernel<<<g, 256, 0, st>>>(ids, table, C, out, ldo, off, len);
+  post_launch("embed_rows", st);
+}
+
+__global__ void __launch_bounds__(256) bcast_cols_kernel(const float* vec, int ldv, int voff, int C,
+                                                         float* out, int ldo, int ocol,
+                                                         const int* off, const int* len) {
+  const int b = blockIdx.y;
+  const int rows_per_block = 256 / 32;
+  const int t = blockIdx.x * rows_per_block + (threadIdx.x >> 5);
+  if (t >= len[b]) return;
+  const size_t row = (size_t)off[b] + t;
+  for (int c = threadIdx.x & 31; c < C; c += 32) out[row * ldo + ocol + c] = vec[(size_t)b * ldv + voff + c];
+}
+void launch_bcast_cols(const float* vec, int ldv, int voff, int C, float* out, int ldo, int ocol,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 7) / 8, B);
+  bcast_cols_kernel<<<g, 256, 0, st>>>(vec, ldv, voff, C, out, ldo, ocol, off, len);
+  post_launch("bcast_cols", st);
+}
+
+__global__ void __launch_bounds__(256) copy_cols_kernel(const float* src, int lds, int scol,
+                                                        float* dst, int ldd, int dcol, int C,
+                                                        const int* off, const int* len) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= len[b]) return;
+  const size_t row = (size_t)off[b] + t;
+  for (int c = threadIdx.x & 31; c < C; c += 32) dst[row * ldd + dcol + c] = src[row * lds + scol + c];
+}
+void launch_copy_cols(const float* src, int lds, int scol, float* dst, int ldd, int dcol, int C,
+                      const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 7) / 8, B);
+  copy_cols_kernel<<<g, 256, 0, st>>>(src, lds, scol, dst, ldd, dcol, C, off, len);
+  post_launch("copy_cols", st);
+}
+
+__global__ void __launch_bounds__(256) add_rows_kernel(const float* a, const float* b2, float* out,
+                                                       int C, const int* off, const int* len) {
+  const int b = blockIdx.y;
+  const size_t n = (size_t)len[b] * C;
+  const size_t base = (size_t)off[b] * C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    out[base + i] = a[base + i] + b2[base + i];
+}
+void launch_add_rows(const float* a, const float* b, float* out, int C, const int* off,
+                     const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  long long blocks = ((long long)max_len * C + 256 * 8 - 1) / (256 * 8);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  dim3 g((unsigned)blocks, B);
+  add_rows_kernel<<<g, 256, 0, st>>>(a, b, out, C, off, len);
+  post_launch("add_rows", st);
+}
+
+__global__ void copy_row_kernel(float* u, int C, int dst_row, int src_row, const int* off) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    u[(size_t)(off[b] + dst_row) * C + c] = u[(size_t)(off[b] + src_row) * C + c];
+}
+void launch_copy_row(float* u, int C, int dst_row, int src_row, const int* off, int B,
+                     cudaStream_t st) {
+  if (g_dry_run) return;
+  copy_row_kernel<<<B, 128, 0, st>>>(u, C, dst_row, src_row, off);
+  post_launch("copy_row", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// ALBERT self-attention (12 heads x 64), flash-style online softmax in fp32.
+// Block = 8 warps, 32 query rows (4 per warp); keys/values streamed in chunks of 64 via smem.
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv,
+                                                        float* __restrict__ ctx, const int* off,
+                                                        const int* len) {
+  __shared__ float Ks[64][65];
+  __shared__ float Vs[64][64];
+  __shared__ float Qs[32][64];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int N = len[b];
+  const int q0 = blockIdx.x * 32;
+  if (q0 >= N) return;
+  const size_t base = (size_t)off[b];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 32 * 64; i += 256) {
+    const int r = i >> 6, d = i & 63;
+    Qs[r][d] = (q0 + r < N) ? qkv[(base + q0 + r) * 2304 + h * 64 + d] : 0.f;
+  }
+  float m[4], l[4], o0[4], o1[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) { m[r] = -INFINITY; l[r] = 0.f; o0[r] = 0.f; o1[r] = 0.f; }
+
+  for (int k0 = 0; k0 < N; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int j = i >> 6, d = i & 63;
+      const bool ok = k0 + j < N;
+      Ks[j][d] = ok ? qkv[(base + k0 + j) * 2304 + 768 + h * 64 + d] : 0.f;
+      Vs[j][d] = ok ? qkv[(base + k0 + j) * 2304 + 1536 + h * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int d = 0; d < 64; d++) {
+      const float ka = Ks[lane][d], kb = Ks[lane + 32][d];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const float qv = Qs[warp * 4 + r][d];
+        s0[r] = fmaf(qv, ka, s0[r]);
+        s1[r] = fmaf(qv, kb, s1[r]);
+      }
+    }
+    const bool v0 = k0 + lane < N, v1 = k0 + lane + 32 < N;
+    float pr0[4], pr1[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const float a0 = v0 ? s0[r] * 0.125f : -INFINITY;
+      const float a1 = v1 ? s1[r] * 0.125f : -INFINITY;
+      float cm = fmaxf(a0, a1);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+      const float mn = fmaxf(m[r], cm);
+      const float p0 = expf(a0 - mn), p1 = expf(a1 - mn);
+      float ps = p0 + p1;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      const float corr = expf(m[r] - mn);
+      l[r] = l[r] * corr + ps;
+      o0[r] *= corr; o1[r] *= corr;
+      m[r] = mn;
+      pr0[r] = p0;
+      pr1[r] = p1;
+    }
+#pragma unroll 4
+    for (int j = 0; j < 32; j++) {
+      const float va = Vs[j][lane], vb = Vs[j][lane + 32];
+      const float vc = Vs[j + 32][lane], vd = Vs[j + 32][lane + 32];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const float pa = __shfl_sync(0xffffffffu, pr0[r], j);
+        const float pb = __shfl_sync(0xffffffffu, pr1[r], j);
+        o0[r] = fmaf(pa, va, o0[r]);
+        o1[r] = fmaf(pa, vb, o1[r]);
+        o0[r] = fmaf(pb, vc, o0[r]);
+        o1[r] = fmaf(pb, vd, o1[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int q = q0 + warp * 4 + r;
+    if (q < N) {
+      const float inv = 1.0f / l[r];
+      ctx[(base + q) * 768 + h * 64 + lane] = o0[r] * inv;
+      ctx[(base + q) * 768 + h * 64 + lane + 32] = o1[r] * inv;
+    }
+  }
+}
+
+void launch_attention(const float* qkv, float* ctx, const int* off, const int* len, int B,
+                      int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 31) / 32, 12, B);
+  attention_kernel<<<g, 256, 0, st>>>(qkv, ctx, off, len);
+  post_launch("attention", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bidirectional LSTM recurrence (H = 256).  One CTA per (item, direction); thread r owns gate
+// row r (i,f,g,o blocks of 256).  W_hh^T is k-major so each k step is one coalesced 4 KB read
+// that stays L2-resident (1 MB per direction); h lives in shared memory, c in registers.
+__global__ void __launch_bounds__(1024) lstm_kernel(const float* __restrict__ xproj,
+                                                    const float* __restrict__ whhT,
+                                                    float* __restrict__ out, int ldo, int ocol,
+                                                    const int* off, const int* len) {
+  __shared__ float h[256];
+  __shared__ float g[1024];
+  const int b = blockIdx.x, dir = blockIdx.y;
+  const int N = len[b];
+  const size_t base = (size_t)off[b];
+  const int r = threadIdx.x;
+  const float* W = whhT + (size_t)dir * 256 * 1024 + r;
+  if (r < 256) h[r] = 0.f;
+  float c = 0.f;
+  __syncthreads();
+  for (int s = 0; s < N; s++) {
+    const int t = dir == 0 ? s : N - 1 - s;
+    float acc0 = xproj[(base + t) * 2048 + dir * 1024 + r];
+    float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 256; k += 4) {
+      acc0 = fmaf(W[(size_t)(k + 0) * 1024], h[k + 0], acc0);
+      acc1 = fmaf(W[(size_t)(k + 1) * 1024], h[k + 1], acc1);
+      acc2 = fmaf(W[(size_t)(k + 2) * 1024], h[k + 2], acc2);
+      acc3 = fmaf(W[(size_t)(k + 3) * 1024], h[k + 3], acc3);
+    }
+    g[r] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (r < 256) {
+      const float ig = 1.0f / (1.0f + expf(-g[r]));
+      const float fg = 1.0f / (1.0f + expf(-g[256 + r]));
+      const float gg = tanhf(g[512 + r]);
+      const float og = 1.0f / (1.0f + expf(-g[768 + r]));
+      c = fg * c + ig * gg;
+      const float hv = og * tanhf(c);
+      h[r] = hv;
+      out[(base + t) * ldo + ocol + dir * 256 + r] = hv;
+    }
+    __syncthreads();
+  }
+}
+
+void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
+                 const int* off, const int* len, int B, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g(B, 2);
+  lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);
+  post_launch("lstm", st);
+}
+
+}  // namespace kkx

@@ -1,0 +1,538 @@
+// kernels_signal.cu -- HBM-bound kernels: instance-norm statistics, duration head + exact
+// integer length regulation (K4/K5), harmonic source (K9), STFT (K10), iSTFT head (K11).
+#include "kernels.h"
+#include <math.h>
+
+namespace kkx {
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm statistics: per (item, chunk of kStatRows rows) column sums and sums of squares.
+// part layout: [B][nchunk][2][C] with nchunk = ceil(max_len / kStatRows)
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, int ldx, int C,
+                                                       float* __restrict__ part, int nchunk,
+                                                       const int* off, const int* len) {
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int L = len[b];
+  const int r0 = ch * kStatRows;
+  if (r0 >= L) return;
+  const int r1 = min(L, r0 + kStatRows);
+  const float* xp = x + (size_t)(off[b] + r0) * ldx;
+  float* pp = part + ((size_t)b * nchunk + ch) * 2 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f, q = 0.f;
+    const float* p = xp + c;
+    for (int r = r0; r < r1; r++, p += ldx) {
+      const float v = *p;
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    pp[c] = s;
+    pp[C + c] = q;
+  }
+}
+void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
+                     int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  const int nchunk = (max_len + kStatRows - 1) / kStatRows;
+  dim3 g(nchunk, B);
+  colstats_kernel<<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
+  post_launch("colstats", st);
+}
+
+__global__ void __launch_bounds__(128) adain_coef_kernel(const float* __restrict__ part, int C,
+                                                         int nchunk, const int* len,
+                                                         const float* __restrict__ sty, int sld,
+                                                         int soff, float eps, float* scale,
+                                                         float* shift) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const int L = len[b];
+  const int nc = (L + kStatRows - 1) / kStatRows;
+  double S = 0.0, Q = 0.0;
+  const float* pp = part + (size_t)b * nchunk * 2 * C;
+  for (int k = 0; k < nc; k++) {
+    S += (double)pp[(size_t)k * 2 * C + c];
+    Q += (double)pp[(size_t)k * 2 * C + C + c];
+  }
+  const double mean = S / (double)L;
+  double var = Q / (double)L - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = 1.0f / sqrtf((float)var + eps);
+  const float gamma = sty[(size_t)b * sld + soff + c];
+  const float beta = sty[(size_t)b * sld + soff + C + c];
+  const float sc = rstd * (1.0f + gamma);
+  scale[(size_t)b * C + c] = sc;
+  shift[(size_t)b * C + c] = beta - (float)mean * sc;
+}
+void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
+                       int sld, int soff, float eps, float* scale, float* shift, int B,
+                       cudaStream_t st) {
+  if (g_dry_run) return;
+  const int nchunk = (max_len + kStatRows - 1) / kStatRows;
+  dim3 g((C + 127) / 128, B);
+  adain_coef_kernel<<<g, 128, 0, st>>>(part, C, nchunk, len, sty, sld, soff, eps, scale, shift);
+  post_launch("adain_coef", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Depthwise ConvTranspose1d(k3, s2, p1, op1) applied to lrelu(x*scale+shift):
+//   y[2t]   = w[1]*a[t] + bias
+//   y[2t+1] = w[2]*a[t] + w[0]*a[t+1] + bias           (a[T] = 0)
+__global__ void __launch_bounds__(256) pool_up_kernel(const float* __restrict__ in, int ldi,
+                                                      const float* scale, const float* shift,
+                                                      float slope, const float* w, const float* bias,
+                                                      int C, float* out, int ldo, const int* in_off,
+                                                      const int* in_len, const int* out_off) {
+  const int b = blockIdx.z;
+  const int T = in_len[b];
+  const int t = blockIdx.x;
+  if (t >= T) return;
+  const float* sc = scale + (size_t)b * C;
+  const float* sh = shift + (size_t)b * C;
+  const float* x0 = in + (size_t)(in_off[b] + t) * ldi;
+  float* y0 = out + (size_t)(out_off[b] + 2 * t) * ldo;
+  for (int c = blockIdx.y * 256 + threadIdx.x; c < C; c += gridDim.y * 256) {
+    float a0 = x0[c] * sc[c] + sh[c];
+    a0 = a0 > 0.f ? a0 : a0 * slope;
+    float a1 = 0.f;
+    if (t + 1 < T) {
+      a1 = x0[ldi + c] * sc[c] + sh[c];
+      a1 = a1 > 0.f ? a1 : a1 * slope;
+    }
+    const float w0 = w[c * 3 + 0], w1 = w[c * 3 + 1], w2 = w[c * 3 + 2], bb = bias[c];
+    y0[c] = w1 * a0 + bb;
+    y0[ldo + c] = w2 * a0 + w0 * a1 + bb;
+  }
+}
+void launch_pool_up(const float* in, int ldi, const float* scale, const float* shift, float slope,
+                    const float* w, const float* bias, int C, float* out, int ldo,
+                    const int* in_off, const int* in_len, const int* out_off, int B, int max_len,
+                    cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g(max_len, (C + 255) / 256, B);
+  pool_up_kernel<<<g, 256, 0, st>>>(in, ldi, scale, shift, slope, w, bias, C, out, ldo, in_off,
+                                    in_len, out_off);
+  post_launch("pool_up", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 duration head.  sigmoid in fp32, 50-way sum accumulated in fp64 and rounded once, divide
+// by speed, round-half-even (rintf), clamp >= 1.
+__global__ void __launch_bounds__(128) duration_kernel(const float* __restrict__ logits, int K,
+                                                       const float* speeds, int* pred_dur,
+                                                       float* dur_float, const int* off,
+                                                       const int* len) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= len[b]) return;
+  const size_t row = (size_t)off[b] + t;
+  double s = 0.0;
+  for (int k = 0; k < K; k++) {
+    const float sg = 1.0f / (1.0f + expf(-logits[row * K + k]));
+    s += (double)sg;
+  }
+  const float d = __fdiv_rn((float)s, speeds[b]);
+  dur_float[row] = d;
+  float r = rintf(d);
+  if (!(r >= 1.0f)) r = 1.0f;
+  pred_dur[row] = (int)r;
+}
+void launch_duration(const float* logits, int K, const float* speeds, int* pred_dur,
+                     float* dur_float, const int* off, const int* len, int B, int max_len,
+                     cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 127) / 128, B);
+  duration_kernel<<<g, 128, 0, st>>>(logits, K, speeds, pred_dur, dur_float, off, len);
+  post_launch("duration", st);
+}
+
+// Exclusive integer prefix sum over one item's tokens (N <= 512): one CTA of 512 threads.
+__global__ void __launch_bounds__(512) dur_scan_kernel(const int* __restrict__ pred_dur, int* cum,
+                                                       int cum_ld, int* total, const int* off,
+                                                       const int* len) {
+  __shared__ int wsum[16];
+  const int b = blockIdx.x;
+  const int N = len[b];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int v = t < N ? pred_dur[off[b] + t] : 0;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < 16 ? wsum[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    if (lane < 16) wsum[lane] = w;
+  }
+  __syncthreads();
+  const int incl = x + (warp ? wsum[warp - 1] : 0);
+  if (t < N) cum[(size_t)b * cum_ld + t] = incl - v;
+  if (t == N - 1) total[b] = incl;
+}
+void launch_dur_scan(const int* pred_dur, int* cum, int cum_ld, int* total, const int* off,
+                     const int* len, int B, cudaStream_t st) {
+  if (g_dry_run) return;
+  dur_scan_kernel<<<B, 512, 0, st>>>(pred_dur, cum, cum_ld, total, off, len);
+  post_launch("dur_scan", st);
+}
+
+// idx[j] = the token n whose frame interval [cum[n], cum[n+1]) contains j (binary search).
+__global__ void __launch_bounds__(256) expand_idx_kernel(const int* __restrict__ cum, int cum_ld,
+                                                         const int* tok_len, int* idx,
+                                                         const int* fr_off, const int* fr_len) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= fr_len[b]) return;
+  const int* c = cum + (size_t)b * cum_ld;
+  int lo = 0, hi = tok_len[b] - 1;  // largest n with c[n] <= j
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (c[mid] <= j) lo = mid; else hi = mid - 1;
+  }
+  idx[fr_off[b] + j] = lo;
+}
+void launch_expand_idx(const int* cum, int cum_ld, const int* tok_len, int* idx, const int* fr_off,
+                       const int* fr_len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 255) / 256, B);
+  expand_idx_kernel<<<g, 256, 0, st>>>(cum, cum_ld, tok_len, idx, fr_off, fr_len);
+  post_launch("expand_idx", st);
+}
+
+// K5 length regulation: exact row gather.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ in, int ldi,
+                                                          const int* in_off, const int* idx,
+                                                          const int* fr_off, const int* fr_len,
+                                                          int C, float* out, int ldo, int ocol) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= fr_len[b]) return;
+  const int n = idx[fr_off[b] + j];
+  const float* src = in + (size_t)(in_off[b] + n) * ldi;
+  float* dst = out + (size_t)(fr_off[b] + j) * ldo + ocol;
+  for (int c = threadIdx.x & 31; c < C; c += 32) dst[c] = src[c];
+}
+void launch_gather_rows(const float* in, int ldi, const int* in_off, const int* idx,
+                        const int* fr_off, const int* fr_len, int C, float* out, int ldo, int ocol,
+                        int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 7) / 8, B);
+  gather_rows_kernel<<<g, 256, 0, st>>>(in, ldi, in_off, idx, fr_off, fr_len, C, out, ldo, ocol);
+  post_launch("gather_rows", st);
+}
+
+// Conv1d(1,1,k3,s2,p1) on the F0 / N curves.
+__global__ void __launch_bounds__(256) curve_conv_kernel(const float* __restrict__ x,
+                                                         const int* x_off, const int* x_len,
+                                                         const float* w3, const float* bias,
+                                                         float* out, int ldo, int ocol,
+                                                         const int* out_off, const int* out_len) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= out_len[b]) return;
+  const int L = x_len[b];
+  const float* xp = x + x_off[b];
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int r = 2 * t - 1 + k;
+    if (r >= 0 && r < L) acc = fmaf(w3[k], xp[r], acc);
+  }
+  out[(size_t)(out_off[b] + t) * ldo + ocol] = acc + bias[0];
+}
+void launch_curve_conv(const float* x, const int* x_off, const int* x_len, const float* w3,
+                       const float* bias, float* out, int ldo, int ocol, const int* out_off,
+                       const int* out_len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((max_len + 255) / 256, B);
+  curve_conv_kernel<<<g, 256, 0, st>>>(x, x_off, x_len, w3, bias, out, ldo, ocol, out_off, out_len);
+  post_launch("curve_conv", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// K9 harmonic source.
+// Coarse phase: rad_h[i] = frac(f0[i]*h/24000) (the x1/300 linear down-sampling of the
+// nearest-upsampled curve reads two taps of the same 300-sample plateau, so it reproduces the
+// plateau value), inclusive cumsum in fp64 rounded to fp32 per element (matches the CPU
+// reference's cumsum, which accumulates in double), then ((c*2)*pi)*300 in fp32.
+__global__ void __launch_bounds__(256) sine_phase_kernel(const float* __restrict__ f0,
+                                                         const int* f0_off, const int* f0_len,
+                                                         float* phase, const int* ph_off) {
+  __shared__ double wsum[8];
+  __shared__ double carry_s;
+  const int b = blockIdx.x, hm = blockIdx.y;  // harmonic index 0..8
+  const int L = f0_len[b];
+  const float* fp = f0 + f0_off[b];
+  float* pp = phase + ph_off[b] + (size_t)hm * L;
+  const float mult = (float)(hm + 1);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) carry_s = 0.0;
+  __syncthreads();
+  for (int base = 0; base < L; base += 256) {
+    const int i = base + t;
+    double v = 0.0;
+    if (i < L) {
+      const float fn = __fmul_rn(fp[i], mult);
+      const float q = __fdiv_rn(fn, 24000.0f);
+      const float r = q - floorf(q);          // python-style % 1
+      v = (double)r;
+    }
+    double x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    double pre = carry_s;
+    for (int w = 0; w < warp; w++) pre += wsum[w];
+    const double incl = pre + x;
+    if (i < L) {
+      const float c = (float)incl;
+      pp[i] = __fmul_rn(__fmul_rn(__fmul_rn(c, 2.0f), 3.14159265358979323846f), 300.0f);
+    }
+    __syncthreads();
+    if (t == 255) carry_s = incl;
+    __syncthreads();
+  }
+}
+void launch_sine_phase(const float* f0, const int* f0_off, const int* f0_len, float* phase,
+                       const int* ph_off, int B, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g(B, 9);
+  sine_phase_kernel<<<g, 256, 0, st>>>(f0, f0_off, f0_len, phase, ph_off);
+  post_launch("sine_phase", st);
+}
+
+// Philox4x32-10 counter RNG + Box-Muller for the production noise path (tests inject noise).
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                              unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+    const unsigned n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    const unsigned n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Per sample: x300 linear interpolation (align_corners=False) of the coarse phase exactly as the
+// CPU reference evaluates it -- src = fma(1/300, n+0.5, -0.5) clamped at 0, lambda = src - i0,
+// value = fma(p[i0], 1-lambda, p[i1]*lambda) -- then sin, *0.1, uv gating, noise, Linear(9->1),
+// tanh.
+__global__ void __launch_bounds__(256) sine_source_kernel(
+    const float* __restrict__ f0, const int* f0_off, const int* f0_len,
+    const float* __restrict__ phase, const int* ph_off, const float* __restrict__ noise,
+    unsigned long long seed, const float* lin_w, const float* lin_b, float* out,
+    const long long* s_off) {
+  const int b = blockIdx.y;
+  const int L = f0_len[b];
+  const long long S = (long long)L * 300;
+  const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (n >= S) return;
+  const float f = f0[f0_off[b] + (int)(n / 300)];
+  const float uv = f > 10.0f ? 1.0f : 0.0f;
+  const float scale = 0.0033333334f;  // (float)(1.0/300.0)
+  float src = __fmaf_rn(scale, (float)n + 0.5f, -0.5f);
+  if (src < 0.f) src = 0.f;
+  const int i0 = (int)src;
+  const int i1 = i0 + (i0 < L - 1 ? 1 : 0);
+  float lam = src - (float)i0;
+  lam = fminf(fmaxf(lam, 0.f), 1.f);
+  const float w0 = 1.0f - lam;
+  const float namp = __fadd_rn(__fmul_rn(uv, 0.003f), __fdiv_rn(__fmul_rn(1.0f - uv, 0.1f), 3.0f));
+  float nz[9];
+  if (noise) {
+#pragma unroll
+    for (int h = 0; h < 9; h++) nz[h] = noise[n * 9 + h];
+  } else {
+    unsigned r[12];
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 1u, (unsigned)seed, (unsigned)(seed >> 32), r + 4);
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 2u, (unsigned)seed, (unsigned)(seed >> 32), r + 8);
+#pragma unroll
+    for (int h = 0; h < 5; h++) {
+      const float u1 = u01(r[2 * h]), u2 = u01(r[2 * h + 1]);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincosf(6.283185307179586f * u2, &sn, &cs);
+      nz[2 * h] = rad * cs;
+      if (2 * h + 1 < 9) nz[2 * h + 1] = rad * sn;
+    }
+  }
+  const float* pp = phase + ph_off[b];
+  float acc = lin_b[0];
+#pragma unroll
+  for (int h = 0; h < 9; h++) {
+    const float p0 = pp[(size_t)h * L + i0], p1 = pp[(size_t)h * L + i1];
+    const float ph = __fmaf_rn(p0, w0, __fmul_rn(p1, lam));
+    const float sw = __fmul_rn(sinf(ph), 0.1f);
+    const float v = __fadd_rn(__fmul_rn(sw, uv), __fmul_rn(namp, nz[h]));
+    acc = fmaf(lin_w[h], v, acc);
+  }
+  out[s_off[b] + n] = tanhf(acc);
+}
+void launch_sine_source(const float* f0, const int* f0_off, const int* f0_len, const float* phase,
+                        const int* ph_off, const float* noise, unsigned long long seed,
+                        const float* lin_w, const float* lin_b, float* out, const long long* s_off,
+                        int B, long long max_samples, cudaStream_t st) {
+  if (g_dry_run) return;
+  dim3 g((unsigned)((max_samples + 255) / 256), B);
+  sine_source_kernel<<<g, 256, 0, st>>>(f0, f0_off, f0_len, phase, ph_off, noise, seed, lin_w,
+                                        lin_b, out, s_off);
+  post_launch("sine_source", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// K10 STFT of the source: n_fft 20, hop 5, periodic hann, center=True.  One thread per frame.
+__constant__ float c_cos20[20];
+__constant__ float c_sin20[20];
+__constant__ float c_hann20[20];
+static bool g_tables_ready[64] = {false};
+
+static void ensure_tables() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && g_tables_ready[dev]) return;
+  float cs[20], sn[20], hw[20];
+  for (int j = 0; j < 20; j++) {
+    cs[j] = (float)cos(2.0 * M_PI * j / 20.0);
+    sn[j] = (float)sin(2.0 * M_PI * j / 20.0);
+    hw[j] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * j / 20.0));
+  }
+  sn[0] = 0.f; sn[10] = 0.f; cs[5] = 0.f; cs[15] = 0.f;
+  KKX_CUDA(cudaMemcpyToSymbol(c_cos20, cs, sizeof cs));
+  KKX_CUDA(cudaMemcpyToSymbol(c_sin20, sn, sizeof sn));
+  KKX_CUDA(cudaMemcpyToSymbol(c_hann20, hw, sizeof hw));
+  if (dev < 64) g_tables_ready[dev] = true;
+}
+
+__global__ void __launch_bounds__(128) stft_kernel(const float* __restrict__ x,
+                                                   const long long* s_off, float* har, int ldh,
+                                                   const int* h_off, const int* h_len,
+                                                   int replicate_pad) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * 128 + threadIdx.x;
+  const int F = h_len[b];
+  if (f >= F) return;
+  const long long S = (long long)(F - 1) * 5;
+  const float* xp = x + s_off[b];
+  float xw[20];
+#pragma unroll
+  for (int j = 0; j < 20; j++) {
+    long long i = (long long)f * 5 - 10 + j;
+    if (replicate_pad) {
+      i = i < 0 ? 0 : (i >= S ? S - 1 : i);
+    } else {
+      if (i < 0) i = -i;
+      if (i >= S) i = 2 * (S - 1) - i;
+    }
+    xw[j] = xp[i] * c_hann20[j];
+  }
+  float* o = har + (size_t)(h_off[b] + f) * ldh;
+#pragma unroll
+  for (int k = 0; k <= 10; k++) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int j = 0; j < 20; j++) {
+      const int m = (j * k) % 20;
+      re = fmaf(xw[j], c_cos20[m], re);
+      im = fmaf(-xw[j], c_sin20[m], im);
+    }
+    if (k == 0 || k == 10) im = 0.f;   // real input: DC / Nyquist are exactly real (+0)
+    o[k] = hypotf(re, im);
+    o[11 + k] = atan2f(im, re);
+  }
+}
+void launch_stft(const float* x, const long long* s_off, float* har, int ldh, const int* h_off,
+                 const int* h_len, int replicate_pad, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  ensure_tables();
+  dim3 g((max_len + 127) / 128, B);
+  stft_kernel<<<g, 128, 0, st>>>(x, s_off, har, ldh, h_off, h_len, replicate_pad);
+  post_launch("stft", st);
+}
+
+// K11 head + iSTFT.  CTA = 128 frames (+3 frames of left halo): each frame's spectrum
+// (mag*cos(ph), mag*sin(ph)) is inverse-transformed (one-sided irfft, n=20) and windowed into
+// shared memory, then 640 output samples are overlap-added, divided by the window envelope and
+// stored coalesced.  Output sample n (after the n_fft/2 trim) sits at untrimmed position n+10.
+__global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int ldc,
+                                                    const int* h_off, const int* h_len,
+                                                    float* audio, const long long* s_off) {
+  constexpr int FR = 128, HALO = 3;
+  __shared__ float fr[FR + HALO + 2][20];  // windowed time frames f0-3 .. f0+129
+  const int b = blockIdx.y;
+  const int F = h_len[b];
+  const int f0 = blockIdx.x * FR;
+  if (f0 >= F) return;
+  const long long S = (long long)(F - 1) * 5;
+  // phase 1: inverse DFT of frames f0-3 .. f0+FR+1  (133 frames x 20 samples)
+  for (int i = threadIdx.x; i < (FR + HALO + 2) * 20; i += 256) {
+    const int lf = i / 20, j = i % 20;
+    const int f = f0 - HALO + lf;
+    float v = 0.f;
+    if (f >= 0 && f < F) {
+      const float* c = cp + (size_t)(h_off[b] + f) * ldc;
+      // bins 0 and 10: real part only
+      float acc = expf(c[0]) * cosf(sinf(c[11]));
+      const float x10 = expf(c[10]) * cosf(sinf(c[21]));
+      acc += (j & 1) ? -x10 : x10;
+#pragma unroll
+      for (int k = 1; k < 10; k++) {
+        const float mag = expf(c[k]);
+        float sn, cs;
+        sincosf(sinf(c[11 + k]), &sn, &cs);
+        const int m = (j * k) % 20;
+        acc += 2.0f * (mag * cs * c_cos20[m] - mag * sn * c_sin20[m]);
+      }
+      v = acc * (1.0f / 20.0f) * c_hann20[j];
+    }
+    fr[lf][j] = v;
+  }
+  __syncthreads();
+  // phase 2: overlap-add.  Sample n covers untrimmed position p = n + 10; frames f with
+  // 5f <= p < 5f+20.
+  for (int i = threadIdx.x; i < FR * 5; i += 256) {
+    const long long n = (long long)f0 * 5 + i;
+    if (n >= S) break;
+    const long long p = n + 10;
+    const int fhi = (int)(p / 5);
+    float acc = 0.f, env = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      const int f = fhi - d;
+      if (f < 0 || f >= F) continue;
+      const int j = (int)(p - (long long)f * 5);
+      acc += fr[f - (f0 - HALO)][j];
+      env += c_hann20[j] * c_hann20[j];
+    }
+    audio[s_off[b] + n] = acc / env;
+  }
+}
+void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio,
+                  const long long* s_off, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  ensure_tables();
+  dim3 g((max_len + 127) / 128, B);
+  istft_kernel<<<g, 256, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off);
+  post_launch("istft", st);
+}
+
+}  // namespace kkx

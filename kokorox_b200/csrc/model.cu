@@ -1,0 +1,480 @@
+// model.cu -- Kokoro-82M forward pass on one B200: weight preparation + kernel orchestration.
+// Replaces `sess.run` of /root/reference/kokorox/src/onn/ort_koko.rs:79 (the ONNX graph
+// kokoro-v1.0.onnx); the architecture follows SURVEY.md Appendix A (A.1 - A.10).
+#include "model.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+
+namespace kkx {
+
+thread_local bool g_dry_run = false;
+
+// ============================================================================ weight file
+WeightFile::WeightFile(const std::string& path) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) throw IoError("cannot open weight file: " + path);
+  const std::streamsize sz = f.tellg();
+  f.seekg(0);
+  buf_.resize((size_t)sz);
+  if (!f.read(buf_.data(), sz)) throw IoError("short read: " + path);
+  if (sz < 16 || memcmp(buf_.data(), "KKXW0001", 8) != 0)
+    throw IoError(path + ": not a KKXW0001 weight file");
+  uint32_t n, hb;
+  memcpy(&n, buf_.data() + 8, 4);
+  memcpy(&hb, buf_.data() + 12, 4);
+  size_t p = 16;
+  auto need = [&](size_t k) { if (p + k > (size_t)sz) throw IoError(path + ": truncated header"); };
+  for (uint32_t i = 0; i < n; i++) {
+    need(2);
+    uint16_t ln; memcpy(&ln, buf_.data() + p, 2); p += 2;
+    need(ln);
+    std::string name(buf_.data() + p, ln); p += ln;
+    need(8);
+    uint32_t dtype, ndim; memcpy(&dtype, buf_.data() + p, 4); memcpy(&ndim, buf_.data() + p + 4, 4); p += 8;
+    if (dtype != 0 || ndim > 8) throw IoError(name + ": unsupported dtype/rank");
+    HostTensor t;
+    need(4 * ndim + 16);
+    size_t numel = 1;
+    for (uint32_t d = 0; d < ndim; d++) {
+      uint32_t v; memcpy(&v, buf_.data() + p, 4); p += 4;
+      t.shape.push_back((int)v); numel *= v;
+    }
+    uint64_t off, nb; memcpy(&off, buf_.data() + p, 8); memcpy(&nb, buf_.data() + p + 8, 8); p += 16;
+    if (nb != numel * 4 || (size_t)hb + off + nb > (size_t)sz) throw IoError(name + ": bad extent");
+    t.data = reinterpret_cast<const float*>(buf_.data() + hb + off);
+    t.numel = numel;
+    t_[name] = t;
+  }
+}
+
+const HostTensor& WeightFile::get(const std::string& name) const {
+  auto it = t_.find(name);
+  if (it == t_.end()) throw IoError("weight tensor missing: " + name);
+  return it->second;
+}
+
+// ============================================================================ construction
+Model::Model(const std::string& weights_path, int device) : device_(device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    throw CudaError("no CUDA device available (this backend has no CPU fallback)");
+  if (device < 0 || device >= ndev) throw CudaError("device ordinal out of range");
+  KKX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KKX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+             prop.major, prop.minor);
+    throw CudaError(b);
+  }
+  KKX_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  KKX_CUDA(cudaEventCreate(&ev0_));
+  KKX_CUDA(cudaEventCreate(&ev1_));
+  const char* dbg = getenv("KKX_DEBUG_SYNC");
+  stats.check_each = dbg && dbg[0] == '1';
+  WeightFile wf(weights_path);
+  load_weights(wf);
+}
+
+Model::~Model() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (void* p : owned_) cudaFree(p);
+  if (d_audio_) cudaFree(d_audio_);
+  if (d_noise_) cudaFree(d_noise_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+float* Model::up(const std::vector<float>& v) {
+  float* d = nullptr;
+  KKX_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  owned_.push_back(d);
+  KKX_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return d;
+}
+
+namespace {
+std::vector<float> raw(const WeightFile& wf, const std::string& n) {
+  const HostTensor& t = wf.get(n);
+  return std::vector<float>(t.data, t.data + t.numel);
+}
+void expect(const HostTensor& t, std::initializer_list<int> shp, const std::string& n) {
+  if (t.shape != std::vector<int>(shp)) throw IoError("unexpected shape for " + n);
+}
+// torch Linear [N][K] -> [K][N]
+std::vector<float> linT(const WeightFile& wf, const std::string& n, int N, int K) {
+  const HostTensor& t = wf.get(n);
+  if ((int)t.numel != N * K) throw IoError("unexpected size for " + n);
+  std::vector<float> o((size_t)N * K);
+  for (int i = 0; i < N; i++)
+    for (int k = 0; k < K; k++) o[(size_t)k * N + i] = t.data[(size_t)i * K + k];
+  return o;
+}
+// Conv1d [Co][Ci][k] -> [k][Ci][Co]
+std::vector<float> convW(const WeightFile& wf, const std::string& n, int Co, int Ci, int k) {
+  const HostTensor& t = wf.get(n);
+  expect(t, {Co, Ci, k}, n);
+  std::vector<float> o((size_t)Co * Ci * k);
+  for (int oc = 0; oc < Co; oc++)
+    for (int c = 0; c < Ci; c++)
+      for (int tt = 0; tt < k; tt++)
+        o[((size_t)tt * Ci + c) * Co + oc] = t.data[((size_t)oc * Ci + c) * k + tt];
+  return o;
+}
+}  // namespace
+
+void Model::load_weights(const WeightFile& wf) {
+  auto U = [&](const std::string& n) { return up(raw(wf, n)); };
+  auto LT = [&](const std::string& n, int N, int K) { return up(linT(wf, n, N, K)); };
+  auto CW = [&](const std::string& n, int Co, int Ci, int k) { return up(convW(wf, n, Co, Ci, k)); };
+
+  // ---- ALBERT (A.2)
+  const std::string E = "bert.embeddings.", L = "bert.encoder.albert_layer_groups.0.albert_layers.0.";
+  W.word = U(E + "word_embeddings.weight");
+  W.pos = U(E + "position_embeddings.weight");
+  W.type = U(E + "token_type_embeddings.weight");
+  W.emb_lnw = U(E + "LayerNorm.weight"); W.emb_lnb = U(E + "LayerNorm.bias");
+  W.map_w = LT("bert.encoder.embedding_hidden_mapping_in.weight", 768, 128);
+  W.map_b = U("bert.encoder.embedding_hidden_mapping_in.bias");
+  {
+    std::vector<float> qkv((size_t)768 * 2304), qb(2304);
+    const char* nm[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; j++) {
+      const HostTensor& t = wf.get(L + "attention." + nm[j] + ".weight");
+      const HostTensor& bb = wf.get(L + "attention." + nm[j] + ".bias");
+      expect(t, {768, 768}, nm[j]);
+      for (int n = 0; n < 768; n++) {
+        qb[j * 768 + n] = bb.data[n];
+        for (int k = 0; k < 768; k++) qkv[(size_t)k * 2304 + j * 768 + n] = t.data[(size_t)n * 768 + k];
+      }
+    }
+    W.qkv_w = up(qkv); W.qkv_b = up(qb);
+  }
+  W.dense_w = LT(L + "attention.dense.weight", 768, 768); W.dense_b = U(L + "attention.dense.bias");
+  W.attn_lnw = U(L + "attention.LayerNorm.weight"); W.attn_lnb = U(L + "attention.LayerNorm.bias");
+  W.ffn_w = LT(L + "ffn.weight", 2048, 768); W.ffn_b = U(L + "ffn.bias");
+  W.ffo_w = LT(L + "ffn_output.weight", 768, 2048); W.ffo_b = U(L + "ffn_output.bias");
+  W.full_lnw = U(L + "full_layer_layer_norm.weight"); W.full_lnb = U(L + "full_layer_layer_norm.bias");
+  W.benc_w = LT("bert_encoder.weight", 512, 768); W.benc_b = U("bert_encoder.bias");
+
+  // ---- LSTMs (A.11 gate order i,f,g,o)
+  auto LSTM = [&](const std::string& p, int in) {
+    LstmW l; l.in = in;
+    std::vector<float> wih((size_t)in * 2048), bias(2048), whh((size_t)2 * 256 * 1024);
+    const char* sfx[2] = {"", "_reverse"};
+    for (int d = 0; d < 2; d++) {
+      const HostTensor& a = wf.get(p + ".weight_ih_l0" + sfx[d]);
+      const HostTensor& h = wf.get(p + ".weight_hh_l0" + sfx[d]);
+      const HostTensor& bi = wf.get(p + ".bias_ih_l0" + sfx[d]);
+      const HostTensor& bh = wf.get(p + ".bias_hh_l0" + sfx[d]);
+      expect(a, {1024, in}, p); expect(h, {1024, 256}, p);
+      for (int g = 0; g < 1024; g++) {
+        bias[d * 1024 + g] = bi.data[g] + bh.data[g];
+        for (int k = 0; k < in; k++) wih[(size_t)k * 2048 + d * 1024 + g] = a.data[(size_t)g * in + k];
+        for (int k = 0; k < 256; k++) whh[((size_t)d * 256 + k) * 1024 + g] = h.data[(size_t)g * 256 + k];
+      }
+    }
+    l.wih = up(wih); l.bias = up(bias); l.whhT = up(whh);
+    return l;
+  };
+
+  // ---- style FC tables
+  std::vector<float> pro_w, pro_b, dec_w, dec_b;
+  std::vector<std::pair<std::string, int>> pro_list, dec_list;  // (fc prefix, outputs)
+  auto add_sty = [&](std::vector<std::pair<std::string, int>>& lst, int& total, const std::string& fc, int nout) {
+    const int off = total;
+    lst.push_back({fc, nout});
+    total += nout;
+    return off;
+  };
+  int npro = 0, ndec = 0;
+
+  for (int i = 0; i < 3; i++) {
+    W.dur_lstm[i] = LSTM("predictor.text_encoder.lstms." + std::to_string(2 * i), 640);
+    W.dur_ada[i] = add_sty(pro_list, npro, "predictor.text_encoder.lstms." + std::to_string(2 * i + 1) + ".fc", 1024);
+  }
+  W.pred_lstm = LSTM("predictor.lstm", 640);
+  W.shared_lstm = LSTM("predictor.shared", 640);
+  W.te_lstm = LSTM("text_encoder.lstm", 512);
+  W.durp_w = LT("predictor.duration_proj.linear_layer.weight", 50, 512);
+  W.durp_b = U("predictor.duration_proj.linear_layer.bias");
+
+  auto BLK = [&](const std::string& p, int ci, int co, bool upf, bool pro) {
+    AdaBlkW b; b.ci = ci; b.co = co; b.up = upf;
+    b.w1 = CW(p + ".conv1.weight", co, ci, 3); b.b1 = U(p + ".conv1.bias");
+    b.w2 = CW(p + ".conv2.weight", co, co, 3); b.b2 = U(p + ".conv2.bias");
+    if (ci != co) b.w1x1 = CW(p + ".conv1x1.weight", co, ci, 1);
+    if (upf) { b.poolw = U(p + ".pool.weight"); b.poolb = U(p + ".pool.bias"); }
+    auto& lst = pro ? pro_list : dec_list; int& tot = pro ? npro : ndec;
+    b.sty1 = add_sty(lst, tot, p + ".norm1.fc", 2 * ci);
+    b.sty2 = add_sty(lst, tot, p + ".norm2.fc", 2 * co);
+    return b;
+  };
+  const char* br[2] = {"F0", "N"};
+  for (int k = 0; k < 2; k++) {
+    AdaBlkW* dst = k == 0 ? W.f0blk : W.nblk;
+    const std::string p = std::string("predictor.") + br[k];
+    dst[0] = BLK(p + ".0", 512, 512, false, true);
+    dst[1] = BLK(p + ".1", 512, 256, true, true);
+    dst[2] = BLK(p + ".2", 256, 256, false, true);
+  }
+  W.f0proj_w = LT("predictor.F0_proj.weight", 1, 256); W.f0proj_b = U("predictor.F0_proj.bias");
+  W.nproj_w = LT("predictor.N_proj.weight", 1, 256); W.nproj_b = U("predictor.N_proj.bias");
+
+  // ---- text encoder (A.4)
+  W.temb = U("text_encoder.embedding.weight");
+  for (int i = 0; i < 3; i++) {
+    const std::string p = "text_encoder.cnn." + std::to_string(i);
+    W.tcnn_w[i] = CW(p + ".0.weight", 512, 512, 5); W.tcnn_b[i] = U(p + ".0.bias");
+    W.tln_g[i] = U(p + ".1.gamma"); W.tln_b[i] = U(p + ".1.beta");
+  }
+
+  // ---- decoder (A.8)
+  W.enc = BLK("decoder.encode", 514, 1024, false, false);
+  for (int i = 0; i < 3; i++) W.dec[i] = BLK("decoder.decode." + std::to_string(i), 1090, 1024, false, false);
+  W.dec[3] = BLK("decoder.decode.3", 1090, 512, true, false);
+  W.f0conv_w = U("decoder.F0_conv.weight"); W.f0conv_b = U("decoder.F0_conv.bias");
+  W.nconv_w = U("decoder.N_conv.weight"); W.nconv_b = U("decoder.N_conv.bias");
+  W.asr_w = CW("decoder.asr_res.0.weight", 64, 512, 1); W.asr_b = U("decoder.asr_res.0.bias");
+
+  // ---- generator (A.9)
+  const std::string G = "decoder.generator.";
+  W.lin_w = U(G + "m_source.l_linear.weight"); W.lin_b = U(G + "m_source.l_linear.bias");
+  W.nc0_w = CW(G + "noise_convs.0.weight", 256, 22, 12); W.nc0_b = U(G + "noise_convs.0.bias");
+  W.nc1_w = CW(G + "noise_convs.1.weight", 128, 22, 1); W.nc1_b = U(G + "noise_convs.1.bias");
+  auto ARB = [&](const std::string& p, int c, int k) {
+    ArbW a; a.c = c; a.k = k;
+    for (int j = 0; j < 3; j++) {
+      const std::string sj = std::to_string(j);
+      a.w1[j] = CW(p + ".convs1." + sj + ".weight", c, c, k); a.b1[j] = U(p + ".convs1." + sj + ".bias");
+      a.w2[j] = CW(p + ".convs2." + sj + ".weight", c, c, k); a.b2[j] = U(p + ".convs2." + sj + ".bias");
+      a.a1[j] = U(p + ".alpha1." + sj); a.a2[j] = U(p + ".alpha2." + sj);
+      a.s1[j] = add_sty(dec_list, ndec, p + ".adain1." + sj + ".fc", 2 * c);
+      a.s2[j] = add_sty(dec_list, ndec, p + ".adain2." + sj + ".fc", 2 * c);
+    }
+    return a;
+  };
+  W.nres[0] = ARB(G + "noise_res.0", 256, 7);
+  W.nres[1] = ARB(G + "noise_res.1", 128, 11);
+  const int rk[3] = {3, 7, 11};
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 3; j++) W.res[i * 3 + j] = ARB(G + "resblocks." + std::to_string(i * 3 + j), i == 0 ? 256 : 128, rk[j]);
+  auto UPS = [&](const std::string& n, int Ci, int Co, int k, int s, std::vector<float*>& out) {
+    const HostTensor& t = wf.get(n);
+    expect(t, {Ci, Co, k}, n);
+    for (int r = 0; r < s; r++) {
+      std::vector<float> ph((size_t)2 * Ci * Co);
+      for (int j = 0; j < 2; j++)
+        for (int c = 0; c < Ci; c++)
+          for (int o = 0; o < Co; o++)
+            ph[((size_t)j * Ci + c) * Co + o] = t.data[((size_t)c * Co + o) * k + r + j * s];
+      out.push_back(up(ph));
+    }
+  };
+  UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0); W.ups0_b = U(G + "ups.0.bias");
+  UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1); W.ups1_b = U(G + "ups.1.bias");
+  W.post_w = CW(G + "conv_post.weight", 22, 128, 7); W.post_b = U(G + "conv_post.bias");
+
+  // ---- build the two style FC tables: W^T [128][n], bias [n]
+  auto build = [&](const std::vector<std::pair<std::string, int>>& lst, int total, float*& dw, float*& db) {
+    std::vector<float> w((size_t)128 * total), b(total);
+    int off = 0;
+    for (auto& e : lst) {
+      const HostTensor& t = wf.get(e.first + ".weight");
+      const HostTensor& bb = wf.get(e.first + ".bias");
+      expect(t, {e.second, 128}, e.first);
+      for (int o = 0; o < e.second; o++) {
+        b[off + o] = bb.data[o];
+        for (int k = 0; k < 128; k++) w[(size_t)k * total + off + o] = t.data[(size_t)o * 128 + k];
+      }
+      off += e.second;
+    }
+    dw = up(w); db = up(b);
+  };
+  build(pro_list, npro, W.sty_pro_w, W.sty_pro_b);
+  build(dec_list, ndec, W.sty_dec_w, W.sty_dec_b);
+  W.sty_pro_n = npro; W.sty_dec_n = ndec;
+}
+
+// ============================================================================ helpers
+Level Model::make_level(const std::vector<int>& lens, Arena& A) {
+  Level L;
+  L.B = (int)lens.size();
+  L.len = lens;
+  L.off.resize(L.B);
+  int o = kGapRows;
+  for (int b = 0; b < L.B; b++) {
+    L.off[b] = o;
+    o = (o + lens[b] + kGapRows + 7) & ~7;
+    L.max_len = std::max(L.max_len, lens[b]);
+    L.sum_len += lens[b];
+  }
+  L.rows = o;
+  L.d_off = A.alloc<int>(L.B);
+  L.d_len = A.alloc<int>(L.B);
+  if (!g_dry_run) {
+    KKX_CUDA(cudaMemcpyAsync(L.d_off, L.off.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    KKX_CUDA(cudaMemcpyAsync(L.d_len, L.len.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    KKX_CUDA(cudaStreamSynchronize(stream_));  // L.off / L.len are locals of the caller's frame
+  }
+  return L;
+}
+
+void Model::capture(const char* name, const float* p, int ld, int col, int cols, const Level& L,
+                    int item0) {
+  if (!debug_ || g_dry_run) return;
+  KKX_CUDA(cudaStreamSynchronize(stream_));
+  for (int b = 0; b < L.B; b++) {
+    DebugStage s;
+    s.rows = L.len[b]; s.cols = cols;
+    s.data.resize((size_t)s.rows * cols);
+    if (s.rows > 0)
+      KKX_CUDA(cudaMemcpy2D(s.data.data(), cols * sizeof(float), p + (size_t)L.off[b] * ld + col,
+                            ld * sizeof(float), cols * sizeof(float), s.rows, cudaMemcpyDeviceToHost));
+    dbg_[std::string(name) + "#" + std::to_string(item0 + b)] = std::move(s);
+  }
+}
+
+const DebugStage* Model::debug_stage(const std::string& name, int item) const {
+  auto it = dbg_.find(name + "#" + std::to_string(item));
+  return it == dbg_.end() ? nullptr : &it->second;
+}
+
+void Model::set_noise(const float* noise, long long n) {
+  KKX_CUDA(cudaSetDevice(device_));
+  if (d_noise_) { cudaFree(d_noise_); d_noise_ = nullptr; }
+  noise_n_ = 0;
+  if (noise && n > 0) {
+    KKX_CUDA(cudaMalloc(&d_noise_, n * sizeof(float)));
+    KKX_CUDA(cudaMemcpy(d_noise_, noise, n * sizeof(float), cudaMemcpyHostToDevice));
+    noise_n_ = n;
+  }
+}
+
+void Model::set_inject(const std::string& name, const void* data, long long count) {
+  if (name == "pred_dur") {
+    inj_dur_.assign((const int*)data, (const int*)data + (data ? count : 0));
+  } else if (name == "F0") {
+    inj_f0_.assign((const float*)data, (const float*)data + (data ? count : 0));
+  } else if (name == "N") {
+    inj_n_.assign((const float*)data, (const float*)data + (data ? count : 0));
+  } else {
+    throw ArgError("unknown inject name: " + name);
+  }
+}
+
+
+// ============================================================================ staging / IO
+void Model::stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
+                  const float* speeds) {
+  if (B <= 0) throw ArgError("batch must be >= 1");
+  if (!tokens || !tok_offsets || !styles || !speeds) throw ArgError("null input pointer");
+  KKX_CUDA(cudaSetDevice(device_));
+  std::vector<int> lens(B);
+  for (int b = 0; b < B; b++) {
+    const int n = tok_offsets[b + 1] - tok_offsets[b];
+    if (n < 1 || n > 512) throw ArgError("n_tokens must be in 1..512 (got " + std::to_string(n) + ")");
+    if (!(speeds[b] > 0.f)) throw ArgError("speed must be > 0");
+    lens[b] = n;
+  }
+  ioA_.reserve((size_t)B * (560 * 4 + 1024 + 64) + (1 << 20));
+  ioA_.reset();
+  g_dry_run = false;
+  tokL_ = make_level(lens, ioA_);
+  std::vector<int> ids((size_t)tokL_.rows, 0);
+  for (int b = 0; b < B; b++)
+    for (int t = 0; t < lens[b]; t++) {
+      const int64_t id = tokens[tok_offsets[b] + t];
+      if (id < 0 || id > 177) throw ArgError("token id out of range 0..177: " + std::to_string(id));
+      ids[tokL_.off[b] + t] = (int)id;
+    }
+  d_ids_ = ioA_.alloc<int>(tokL_.rows);
+  d_styles_ = ioA_.alloc<float>((size_t)B * 256);
+  d_speeds_ = ioA_.alloc<float>(B);
+  KKX_CUDA(cudaMemcpyAsync(d_ids_, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(d_styles_, styles, (size_t)B * 256 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(d_speeds_, speeds, B * sizeof(float), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaStreamSynchronize(stream_));
+  B_ = B;
+  tok_len_ = lens;
+}
+
+void Model::fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur) {
+  KKX_CUDA(cudaSetDevice(device_));
+  if (sample_offsets)
+    for (int b = 0; b <= B_; b++) sample_offsets[b] = sample_off_[b];
+  if (pred_dur) {
+    size_t k = 0;
+    for (int b = 0; b < B_; b++)
+      for (int t = 0; t < tok_len_[b]; t++) pred_dur[k++] = pred_dur_h_[tokL_.off[b] + t];
+  }
+  if (dst) {
+    if (capacity < total_samples_) throw ArgError("audio buffer too small");
+    KKX_CUDA(cudaMemcpyAsync(dst, d_audio_, total_samples_ * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+  }
+}
+
+// ============================================================================ forward
+void Model::run() {
+  if (B_ <= 0) throw ArgError("no batch staged");
+  KKX_CUDA(cudaSetDevice(device_));
+  g_launch_stats = &stats;
+  stats.launches = 0;
+  dbg_.clear();
+  KKX_CUDA(cudaEventRecord(ev0_, stream_));
+  Run r;
+  token_phase(r);
+
+  // frame-phase groups under the frame budget
+  sample_off_.assign(B_ + 1, 0);
+  long long tot = 0;
+  for (int b = 0; b < B_; b++) { sample_off_[b] = tot * 600; tot += r.T[b]; }
+  sample_off_[B_] = tot * 600;
+  total_samples_ = tot * 600;
+  last_frames = tot;
+  if ((size_t)total_samples_ > audio_cap_) {
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    if (d_audio_) cudaFree(d_audio_);
+    audio_cap_ = (size_t)total_samples_ + (size_t)total_samples_ / 4;
+    KKX_CUDA(cudaMalloc(&d_audio_, audio_cap_ * sizeof(float)));
+  }
+  int b0 = 0;
+  while (b0 < B_) {
+    int b1 = b0; long long fr = 0;
+    while (b1 < B_ && (b1 == b0 || fr + r.T[b1] <= opt.max_frames)) { fr += r.T[b1]; b1++; }
+    // size the arena with a dry run of the same allocation sequence (no launches, no copies)
+    frA_.reset();
+    frA_.set_virtual(true);
+    g_dry_run = true;
+    try {
+      frame_phase(r, b0, b1, true);
+    } catch (...) {
+      g_dry_run = false; frA_.set_virtual(false);
+      throw;
+    }
+    g_dry_run = false;
+    frA_.set_virtual(false);
+    const size_t need = frA_.used();
+    if (need + (1 << 20) > frA_.capacity()) {
+      KKX_CUDA(cudaStreamSynchronize(stream_));
+      frA_.reserve(need + need / 8 + (1 << 20));
+    }
+    frA_.reset();
+    frame_phase(r, b0, b1, false);
+    b0 = b1;
+  }
+  KKX_CUDA(cudaEventRecord(ev1_, stream_));
+  KKX_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0_, ev1_);
+  last_gpu_us = ms * 1e3;
+  g_launch_stats = nullptr;
+}
+
+}  // namespace kkx

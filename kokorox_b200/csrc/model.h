@@ -1,0 +1,152 @@
+// model.h -- weight set + forward pass orchestration of Kokoro-82M on one B200.
+#pragma once
+#include "common.h"
+#include "kernels.h"
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace kkx {
+
+struct HostTensor {
+  std::vector<int> shape;
+  const float* data = nullptr;
+  size_t numel = 0;
+};
+
+// Reads a KKXW0001 file (kokorox_b200/weightfile.py) into host memory.
+class WeightFile {
+ public:
+  explicit WeightFile(const std::string& path);
+  const HostTensor& get(const std::string& name) const;
+  bool has(const std::string& name) const { return t_.count(name) != 0; }
+
+ private:
+  std::vector<char> buf_;
+  std::map<std::string, HostTensor> t_;
+};
+
+struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; };
+struct AdaBlkW {  // AdainResBlk1d
+  int ci = 0, co = 0; bool up = false;
+  float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *w1x1 = nullptr;
+  float *poolw = nullptr, *poolb = nullptr;
+  int sty1 = 0, sty2 = 0;  // offsets into the per-item style-parameter table
+};
+struct ArbW {  // AdaINResBlock1
+  int c = 0, k = 0;
+  float *w1[3], *b1[3], *w2[3], *b2[3], *a1[3], *a2[3];
+  int s1[3], s2[3];
+};
+
+struct Weights {
+  // ALBERT
+  float *word, *pos, *type, *emb_lnw, *emb_lnb, *map_w, *map_b;
+  float *qkv_w, *qkv_b, *dense_w, *dense_b, *attn_lnw, *attn_lnb;
+  float *ffn_w, *ffn_b, *ffo_w, *ffo_b, *full_lnw, *full_lnb;
+  float *benc_w, *benc_b;
+  // predictor
+  LstmW dur_lstm[3]; int dur_ada[3];
+  LstmW pred_lstm, shared_lstm;
+  float *durp_w, *durp_b;
+  AdaBlkW f0blk[3], nblk[3];
+  float *f0proj_w, *f0proj_b, *nproj_w, *nproj_b;
+  // text encoder
+  float* temb; float *tcnn_w[3], *tcnn_b[3], *tln_g[3], *tln_b[3]; LstmW te_lstm;
+  // decoder
+  AdaBlkW enc, dec[4];
+  float *f0conv_w, *f0conv_b, *nconv_w, *nconv_b, *asr_w, *asr_b;
+  // generator
+  float *lin_w, *lin_b, *nc0_w, *nc0_b, *nc1_w, *nc1_b;
+  ArbW nres[2], res[6];
+  std::vector<float*> ups0, ups1;  // per-phase [2][Ci][Co]
+  float *ups0_b, *ups1_b, *post_w, *post_b;
+  // style FC tables (all AdaIN / AdaLN fcs of one style half concatenated)
+  float *sty_pro_w, *sty_pro_b, *sty_dec_w, *sty_dec_b;
+  int sty_pro_n = 0, sty_dec_n = 0;
+};
+
+struct DebugStage { std::vector<float> data; long long rows = 0, cols = 0; };
+
+struct Options {
+  int precision = 0;
+  unsigned long long noise_seed = 0x5eed;
+  int max_frames = 49152;
+  int stft_replicate = 0;
+};
+
+class Model {
+ public:
+  Model(const std::string& weights_path, int device);
+  ~Model();
+
+  // Stage inputs on the device (H2D), run the forward pass, fetch results (D2H).
+  void stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
+             const float* speeds);
+  void run();
+  long long total_samples() const { return total_samples_; }
+  void fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
+
+  void set_noise(const float* noise, long long n);
+  void set_inject(const std::string& name, const void* data, long long count);
+  void set_debug(bool on) { debug_ = on; }
+  const DebugStage* debug_stage(const std::string& name, int item) const;
+
+  Options opt;
+  LaunchStats stats;
+  long long last_frames = 0;
+  double last_gpu_us = 0;
+  int device() const { return device_; }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  struct Run {  // per-call state
+    float* d = nullptr;        // [R,640]  DurationEncoder output (A.3)
+    float* t_en = nullptr;     // [R,512]  TextEncoder output (A.4)
+    float* sty_pro = nullptr;  // [B, sty_pro_n] predictor-side AdaIN/AdaLN parameters
+    float* sty_dec = nullptr;  // [B, sty_dec_n] decoder-side AdaIN parameters
+    int* pred_dur = nullptr;   // [R]
+    int* cum = nullptr;        // [B,512] exclusive prefix sums of pred_dur
+    int* total = nullptr;      // [B]     T_b
+    std::vector<int> T;        // frames per item (host)
+    Level styL;                // one item of B rows (style FC GEMMs)
+  };
+  void load_weights(const WeightFile& wf);
+  float* up(const std::vector<float>& v);
+  void token_phase(Run& r);
+  void frame_phase(Run& r, int b0, int b1, bool dry);
+  void adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ldx, const Level& Lin,
+                 const Level& Lout, const float* sty, int sld, float* out, int ldo, int ocol,
+                 bool dry);
+  void arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
+           int sld, float* xw, float* t1, float* out, float oscale, bool accumulate);
+  Level make_level(const std::vector<int>& lens, Arena& A);
+  void capture(const char* name, const float* p, int ld, int col, int cols, const Level& L,
+               int item0);
+
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  std::vector<void*> owned_;  // device weight allocations
+  Weights W;
+  Arena tokA_, frA_, ioA_;
+  bool debug_ = false;
+  std::map<std::string, DebugStage> dbg_;
+  // staged inputs
+  int B_ = 0;
+  std::vector<int> tok_len_;
+  int* d_ids_ = nullptr; float* d_styles_ = nullptr; float* d_speeds_ = nullptr;
+  Level tokL_;
+  // outputs
+  float* d_audio_ = nullptr; size_t audio_cap_ = 0;
+  std::vector<long long> sample_off_;
+  std::vector<int> pred_dur_h_;
+  long long total_samples_ = 0;
+  // test hooks
+  float* d_noise_ = nullptr; long long noise_n_ = 0;
+  std::vector<int> inj_dur_; std::vector<float> inj_f0_, inj_n_;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+};
+
+}  // namespace kkx

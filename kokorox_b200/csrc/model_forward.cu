@@ -1,0 +1,439 @@
+// model_forward.cu -- the forward pass proper: token phase (ALBERT, DurationEncoder, duration
+// head, TextEncoder) and frame phase (length regulation, F0/N predictor, Decoder, Generator,
+// iSTFT).  SURVEY.md Appendix A.1 - A.10; replaces ort_koko.rs:79 `sess.run`.
+#include "model.h"
+#include <algorithm>
+#include <cmath>
+
+namespace kkx {
+
+namespace {
+ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float* w, const float* bias,
+                   int N, float* out, int ldo, int ocol) {
+  ConvArgs a;
+  a.in = in; a.ldi = ldi; a.in_off = L.d_off; a.in_len = L.d_len;
+  a.m_len = L.d_len; a.max_m = L.max_len; a.B = L.B;
+  a.w = w; a.bias = bias; a.Ci = K; a.Co = N;
+  a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = L.d_off;
+  return a;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Token phase: everything at phoneme-token rate, for the whole batch.
+void Model::token_phase(Run& r) {
+  cudaStream_t st = stream_;
+  const Level& L = tokL_;
+  const size_t R = (size_t)L.rows;
+  const int B = B_;
+  const size_t need = R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16) * sizeof(float) +
+                      (size_t)B * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20);
+  if (need > tokA_.capacity()) {
+    KKX_CUDA(cudaStreamSynchronize(st));
+    tokA_.reserve(need);
+  }
+  tokA_.reset();
+  Arena& A = tokA_;
+
+  // style-parameter tables for every AdaIN / AdaLN of the model: two GEMMs over the batch
+  r.styL = make_level(std::vector<int>{B}, A);
+  // make_level puts the single item at row kGapRows; style rows live at [0,B) -> use explicit offsets
+  {
+    int zero = 0;
+    KKX_CUDA(cudaMemcpyAsync(r.styL.d_off, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    KKX_CUDA(cudaStreamSynchronize(st));
+    r.styL.off[0] = 0;
+  }
+  r.sty_pro = A.alloc<float>((size_t)B * W.sty_pro_n);
+  r.sty_dec = A.alloc<float>((size_t)B * W.sty_dec_n);
+  launch_conv_f32(gemm_args(r.styL, d_styles_ + 128, 256, 128, W.sty_pro_w, W.sty_pro_b, W.sty_pro_n,
+                            r.sty_pro, W.sty_pro_n, 0), st);
+  launch_conv_f32(gemm_args(r.styL, d_styles_, 256, 128, W.sty_dec_w, W.sty_dec_b, W.sty_dec_n,
+                            r.sty_dec, W.sty_dec_n, 0), st);
+
+  // ---- ALBERT (A.2)
+  float* e = A.alloc<float>(R * 128);
+  float* h = A.alloc<float>(R * 768);
+  float* h1 = A.alloc<float>(R * 768);
+  float* ctx = A.alloc<float>(R * 768);
+  float* tmp = A.alloc<float>(R * 768);
+  float* qkv = A.alloc<float>(R * 2304);
+  float* ff = A.alloc<float>(R * 2048);
+  launch_albert_embed(d_ids_, W.word, W.pos, W.type, W.emb_lnw, W.emb_lnb, e, L.d_off, L.d_len, B,
+                      L.max_len, st);
+  launch_conv_f32(gemm_args(L, e, 128, 128, W.map_w, W.map_b, 768, h, 768, 0), st);
+  for (int layer = 0; layer < 12; layer++) {
+    launch_conv_f32(gemm_args(L, h, 768, 768, W.qkv_w, W.qkv_b, 2304, qkv, 2304, 0), st);
+    launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
+    launch_conv_f32(gemm_args(L, ctx, 768, 768, W.dense_w, W.dense_b, 768, tmp, 768, 0), st);
+    LnArgs ln;
+    ln.x = h; ln.ldx = 768; ln.res = tmp; ln.ldr = 768; ln.w = W.attn_lnw; ln.b = W.attn_lnb;
+    ln.eps = 1e-12f; ln.out = h1; ln.ldo = 768; ln.off = L.d_off; ln.len = L.d_len; ln.B = B;
+    ln.max_len = L.max_len; ln.C = 768;
+    launch_layernorm(ln, st);
+    ConvArgs f1 = gemm_args(L, h1, 768, 768, W.ffn_w, W.ffn_b, 2048, ff, 2048, 0);
+    f1.eact = ACT_GELU_NEW;
+    launch_conv_f32(f1, st);
+    launch_conv_f32(gemm_args(L, ff, 2048, 2048, W.ffo_w, W.ffo_b, 768, tmp, 768, 0), st);
+    ln.x = tmp; ln.res = h1; ln.w = W.full_lnw; ln.b = W.full_lnb; ln.out = h;
+    launch_layernorm(ln, st);
+  }
+  capture("bert", h, 768, 0, 768, L, 0);
+
+  // ---- bert_encoder + DurationEncoder (A.3)
+  float* xa = A.alloc<float>(R * 640);
+  float* xb = A.alloc<float>(R * 640);
+  float* xp = A.alloc<float>(R * 2048);
+  float* lo = A.alloc<float>(R * 512);
+  launch_conv_f32(gemm_args(L, h, 768, 768, W.benc_w, W.benc_b, 512, xa, 640, 0), st);
+  capture("d_en", xa, 640, 0, 512, L, 0);
+  launch_bcast_cols(d_styles_, 256, 128, 128, xa, 640, 512, L.d_off, L.d_len, B, L.max_len, st);
+  launch_bcast_cols(d_styles_, 256, 128, 128, xb, 640, 512, L.d_off, L.d_len, B, L.max_len, st);
+  float* cur = xa; float* nxt = xb;
+  for (int i = 0; i < 3; i++) {
+    launch_conv_f32(gemm_args(L, cur, 640, 640, W.dur_lstm[i].wih, W.dur_lstm[i].bias, 2048, xp, 2048, 0), st);
+    launch_lstm(xp, W.dur_lstm[i].whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
+    LnArgs ln;
+    ln.x = lo; ln.ldx = 512; ln.ada = r.sty_pro; ln.ada_ld = W.sty_pro_n; ln.ada_off = W.dur_ada[i];
+    ln.eps = 1e-5f; ln.out = nxt; ln.ldo = 640; ln.ocol = 0; ln.off = L.d_off; ln.len = L.d_len;
+    ln.B = B; ln.max_len = L.max_len; ln.C = 512;
+    launch_layernorm(ln, st);
+    std::swap(cur, nxt);
+  }
+  r.d = cur;
+  capture("d", r.d, 640, 0, 640, L, 0);
+
+  // ---- duration head (A.1, K4)
+  launch_conv_f32(gemm_args(L, r.d, 640, 640, W.pred_lstm.wih, W.pred_lstm.bias, 2048, xp, 2048, 0), st);
+  launch_lstm(xp, W.pred_lstm.whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
+  capture("dur_lstm", lo, 512, 0, 512, L, 0);
+  float* logits = A.alloc<float>(R * 50);
+  launch_conv_f32(gemm_args(L, lo, 512, 512, W.durp_w, W.durp_b, 50, logits, 50, 0), st);
+  capture("dur_logits", logits, 50, 0, 50, L, 0);
+  r.pred_dur = A.alloc<int>(R);
+  float* durf = A.alloc<float>(R);
+  r.cum = A.alloc<int>((size_t)B * 512);
+  r.total = A.alloc<int>(B);
+  launch_duration(logits, 50, d_speeds_, r.pred_dur, durf, L.d_off, L.d_len, B, L.max_len, st);
+  capture("dur_float", durf, 1, 0, 1, L, 0);
+  if (!inj_dur_.empty()) {
+    if ((int)inj_dur_.size() != L.len[0]) throw ArgError("inject pred_dur: length != n_tokens of item 0");
+    KKX_CUDA(cudaMemcpyAsync(r.pred_dur + L.off[0], inj_dur_.data(), inj_dur_.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, st));
+  }
+  launch_dur_scan(r.pred_dur, r.cum, 512, r.total, L.d_off, L.d_len, B, st);
+
+  // ---- TextEncoder (A.4) -- independent of the duration path; issued before the host sync
+  float* ta = A.alloc<float>(R * 512);
+  float* tb = A.alloc<float>(R * 512);
+  r.t_en = A.alloc<float>(R * 512);
+  launch_embed_rows(d_ids_, W.temb, 512, ta, 512, L.d_off, L.d_len, B, L.max_len, st);
+  for (int i = 0; i < 3; i++) {
+    ConvArgs c = gemm_args(L, ta, 512, 512, W.tcnn_w[i], W.tcnn_b[i], 512, tb, 512, 0);
+    c.ks = 5; c.pad = 2;
+    launch_conv_f32(c, st);
+    LnArgs ln;
+    ln.x = tb; ln.ldx = 512; ln.w = W.tln_g[i]; ln.b = W.tln_b[i]; ln.eps = 1e-5f; ln.slope = 0.2f;
+    ln.out = ta; ln.ldo = 512; ln.off = L.d_off; ln.len = L.d_len; ln.B = B; ln.max_len = L.max_len;
+    ln.C = 512;
+    launch_layernorm(ln, st);
+  }
+  launch_conv_f32(gemm_args(L, ta, 512, 512, W.te_lstm.wih, W.te_lstm.bias, 2048, xp, 2048, 0), st);
+  launch_lstm(xp, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, st);
+  capture("t_en", r.t_en, 512, 0, 512, L, 0);
+
+  // ---- the one mid-pipeline host sync: frame counts decide every later launch shape
+  r.T.resize(B);
+  pred_dur_h_.resize(R);
+  KKX_CUDA(cudaMemcpyAsync(r.T.data(), r.total, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  KKX_CUDA(cudaMemcpyAsync(pred_dur_h_.data(), r.pred_dur, R * sizeof(int), cudaMemcpyDeviceToHost, st));
+  KKX_CUDA(cudaStreamSynchronize(st));
+}
+
+// ------------------------------------------------------------------------------------------
+// AdainResBlk1d (A.6).  x [Lin rows, ci] -> out [Lout rows, co] (Lout = 2*Lin when upsampling).
+void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ldx, const Level& Lin,
+                      const Level& Lout, const float* sty, int sld, float* out, int ldo, int ocol,
+                      bool dry) {
+  (void)r; (void)dry;
+  cudaStream_t st = stream_;
+  const int B = Lin.B;
+  const int nch_in = (Lin.max_len + kStatRows - 1) / kStatRows;
+  const int nch_out = (Lout.max_len + kStatRows - 1) / kStatRows;
+  float* part = A.alloc<float>((size_t)B * std::max(nch_in, nch_out) * 2 * std::max(w.ci, w.co));
+  float* sc1 = A.alloc<float>((size_t)B * w.ci);
+  float* sh1 = A.alloc<float>((size_t)B * w.ci);
+  float* sc2 = A.alloc<float>((size_t)B * w.co);
+  float* sh2 = A.alloc<float>((size_t)B * w.co);
+  float* t = A.alloc<float>((size_t)Lout.rows * w.co);
+
+  launch_colstats(x, ldx, w.ci, part, Lin.d_off, Lin.d_len, B, Lin.max_len, st);
+  launch_adain_coef(part, w.ci, Lin.max_len, Lin.d_len, sty, sld, w.sty1, 1e-5f, sc1, sh1, B, st);
+  if (w.up) {
+    float* p = A.alloc<float>((size_t)Lout.rows * w.ci);
+    launch_pool_up(x, ldx, sc1, sh1, 0.2f, w.poolw, w.poolb, w.ci, p, w.ci, Lin.d_off, Lin.d_len,
+                   Lout.d_off, B, Lin.max_len, st);
+    ConvArgs c = gemm_args(Lout, p, w.ci, w.ci, w.w1, w.b1, w.co, t, w.co, 0);
+    c.ks = 3; c.pad = 1;
+    launch_conv_f32(c, st);
+  } else {
+    ConvArgs c = gemm_args(Lin, x, ldx, w.ci, w.w1, w.b1, w.co, t, w.co, 0);
+    c.ks = 3; c.pad = 1;
+    c.pscale = sc1; c.pshift = sh1; c.pld = w.ci; c.pact = ACT_LRELU; c.pslope = 0.2f;
+    launch_conv_f32(c, st);
+  }
+  launch_colstats(t, w.co, w.co, part, Lout.d_off, Lout.d_len, B, Lout.max_len, st);
+  launch_adain_coef(part, w.co, Lout.max_len, Lout.d_len, sty, sld, w.sty2, 1e-5f, sc2, sh2, B, st);
+
+  const float* sc = x; int ldsc = ldx;
+  if (w.w1x1) {
+    float* s = A.alloc<float>((size_t)Lin.rows * w.co);
+    launch_conv_f32(gemm_args(Lin, x, ldx, w.ci, w.w1x1, nullptr, w.co, s, w.co, 0), st);
+    sc = s; ldsc = w.co;
+  }
+  ConvArgs c2 = gemm_args(Lout, t, w.co, w.co, w.w2, w.b2, w.co, out, ldo, ocol);
+  c2.ks = 3; c2.pad = 1;
+  c2.pscale = sc2; c2.pshift = sh2; c2.pld = w.co; c2.pact = ACT_LRELU; c2.pslope = 0.2f;
+  c2.res = sc; c2.ldr = ldsc; c2.rcol = 0; c2.res_off = Lin.d_off; c2.res_shift = w.up ? 1 : 0;
+  c2.oscale = 0.70710678118654752440f;
+  launch_conv_f32(c2, st);
+}
+
+// AdaINResBlock1 (A.9): three (AdaIN -> Snake -> dilated conv -> AdaIN -> Snake -> conv) + residual
+// iterations.  Reads x, uses xw/t1 as work buffers, writes (or accumulates) oscale * result to out.
+void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
+                int sld, float* xw, float* t1, float* out, float oscale, bool accumulate) {
+  (void)r;
+  cudaStream_t st = stream_;
+  const int B = L.B, C = w.c, k = w.k;
+  const int nch = (L.max_len + kStatRows - 1) / kStatRows;
+  float* part = A.alloc<float>((size_t)B * nch * 2 * C);
+  float* sc = A.alloc<float>((size_t)B * C);
+  float* sh = A.alloc<float>((size_t)B * C);
+  const int dil[3] = {1, 3, 5};
+  const float* cur = x;
+  for (int j = 0; j < 3; j++) {
+    launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
+    ConvArgs c1 = gemm_args(L, cur, C, C, w.w1[j], w.b1[j], C, t1, C, 0);
+    c1.ks = k; c1.dil = dil[j]; c1.pad = dil[j] * (k - 1) / 2;
+    c1.pscale = sc; c1.pshift = sh; c1.pld = C; c1.pact = ACT_SNAKE; c1.palpha = w.a1[j];
+    launch_conv_f32(c1, st);
+    launch_colstats(t1, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s2[j], 1e-5f, sc, sh, B, st);
+    float* dst = (j == 2) ? out : xw;
+    ConvArgs c2 = gemm_args(L, t1, C, C, w.w2[j], w.b2[j], C, dst, C, 0);
+    c2.ks = k; c2.dil = 1; c2.pad = (k - 1) / 2;
+    c2.pscale = sc; c2.pshift = sh; c2.pld = C; c2.pact = ACT_SNAKE; c2.palpha = w.a2[j];
+    c2.res = cur; c2.ldr = C; c2.res_off = L.d_off;
+    if (j == 2) { c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; }
+    launch_conv_f32(c2, st);
+    cur = dst;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Frame phase for items [b0, b1): length regulation, F0/N, decoder, generator, iSTFT.
+void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
+  cudaStream_t st = stream_;
+  Arena& A = frA_;
+  const int B = b1 - b0;
+  std::vector<int> T(r.T.begin() + b0, r.T.begin() + b1), T2(B), T20(B), T120(B), one(B, 1);
+  long long maxS = 0;
+  for (int b = 0; b < B; b++) {
+    T2[b] = 2 * T[b]; T20[b] = 20 * T[b]; T120[b] = 120 * T[b] + 1;
+    maxS = std::max(maxS, 600LL * T[b]);
+  }
+  Level FR = make_level(T, A), FR2 = make_level(T2, A), G20 = make_level(T20, A), G120 = make_level(T120, A);
+  // per-item views into batch-level (token-phase) arrays
+  const int* tok_off = tokL_.d_off + b0;
+  const int* tok_len = tokL_.d_len + b0;
+  const int* cum = r.cum + (size_t)b0 * 512;
+  const float* sty_pro = r.sty_pro + (size_t)b0 * W.sty_pro_n;
+  const float* sty_dec = r.sty_dec + (size_t)b0 * W.sty_dec_n;
+  // curve (F0 / N) offsets: element offsets == FR2 row offsets (ld 1); phase offsets; sample offsets
+  std::vector<int> ph_off(B);
+  std::vector<long long> s_loc(B), s_glob(B);
+  {
+    int po = 0; long long so = 0;
+    for (int b = 0; b < B; b++) {
+      ph_off[b] = po; po += 9 * T2[b];
+      s_loc[b] = so; so += 600LL * T[b];
+      s_glob[b] = sample_off_[b0 + b];
+    }
+  }
+  int* d_ph_off = A.alloc<int>(B);
+  long long* d_s_loc = A.alloc<long long>(B);
+  long long* d_s_glob = A.alloc<long long>(B);
+  if (!dry) {
+    KKX_CUDA(cudaMemcpyAsync(d_ph_off, ph_off.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    KKX_CUDA(cudaMemcpyAsync(d_s_loc, s_loc.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+    KKX_CUDA(cudaMemcpyAsync(d_s_glob, s_glob.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+    KKX_CUDA(cudaStreamSynchronize(st));
+  }
+
+  // ---- length regulation (K4/K5)
+  int* idx = A.alloc<int>(FR.rows);
+  float* en = A.alloc<float>((size_t)FR.rows * 640);
+  float* x514 = A.alloc<float>((size_t)FR.rows * 520);
+  launch_expand_idx(cum, 512, tok_len, idx, FR.d_off, FR.d_len, B, FR.max_len, st);
+  launch_gather_rows(r.d, 640, tok_off, idx, FR.d_off, FR.d_len, 640, en, 640, 0, B, FR.max_len, st);
+  launch_gather_rows(r.t_en, 512, tok_off, idx, FR.d_off, FR.d_len, 512, x514, 520, 0, B, FR.max_len, st);
+  if (debug_ && !dry) {
+    // idx as float for the debug channel
+    KKX_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> hi(FR.rows);
+    KKX_CUDA(cudaMemcpy(hi.data(), idx, FR.rows * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; b++) {
+      DebugStage s; s.rows = FR.len[b]; s.cols = 1; s.data.resize(FR.len[b]);
+      for (int j = 0; j < FR.len[b]; j++) s.data[j] = (float)hi[FR.off[b] + j];
+      dbg_["idx#" + std::to_string(b0 + b)] = std::move(s);
+    }
+  }
+  capture("en", en, 640, 0, 640, FR, b0);
+  capture("asr", x514, 520, 0, 512, FR, b0);
+
+  // ---- F0 / N predictor (A.7)
+  float* xp = A.alloc<float>((size_t)FR.rows * 2048);
+  float* shd = A.alloc<float>((size_t)FR.rows * 512);
+  launch_conv_f32(gemm_args(FR, en, 640, 640, W.shared_lstm.wih, W.shared_lstm.bias, 2048, xp, 2048, 0), st);
+  launch_lstm(xp, W.shared_lstm.whhT, shd, 512, 0, FR.d_off, FR.d_len, B, st);
+  capture("shared_lstm", shd, 512, 0, 512, FR, b0);
+  float* curves[2];
+  for (int k = 0; k < 2; k++) {
+    const AdaBlkW* blk = k == 0 ? W.f0blk : W.nblk;
+    const size_t mark = A.used();
+    float* y0 = A.alloc<float>((size_t)FR.rows * 512);
+    float* y1 = A.alloc<float>((size_t)FR2.rows * 256);
+    float* y2 = A.alloc<float>((size_t)FR2.rows * 256);
+    adain_blk(r, A, blk[0], shd, 512, FR, FR, sty_pro, W.sty_pro_n, y0, 512, 0, dry);
+    adain_blk(r, A, blk[1], y0, 512, FR, FR2, sty_pro, W.sty_pro_n, y1, 256, 0, dry);
+    adain_blk(r, A, blk[2], y1, 256, FR2, FR2, sty_pro, W.sty_pro_n, y2, 256, 0, dry);
+    (void)mark;
+    curves[k] = A.alloc<float>(FR2.rows);
+    launch_conv_f32(gemm_args(FR2, y2, 256, 256, k == 0 ? W.f0proj_w : W.nproj_w,
+                              k == 0 ? W.f0proj_b : W.nproj_b, 1, curves[k], 1, 0), st);
+  }
+  float* f0 = curves[0]; float* nc = curves[1];
+  if (!dry && b0 == 0) {
+    if (!inj_f0_.empty()) {
+      if ((int)inj_f0_.size() != FR2.len[0]) throw ArgError("inject F0: length != 2T of item 0");
+      KKX_CUDA(cudaMemcpyAsync(f0 + FR2.off[0], inj_f0_.data(), inj_f0_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (!inj_n_.empty()) {
+      if ((int)inj_n_.size() != FR2.len[0]) throw ArgError("inject N: length != 2T of item 0");
+      KKX_CUDA(cudaMemcpyAsync(nc + FR2.off[0], inj_n_.data(), inj_n_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+  }
+  capture("F0", f0, 1, 0, 1, FR2, b0);
+  capture("N", nc, 1, 0, 1, FR2, b0);
+
+  // ---- decoder (A.8)
+  float* xA = A.alloc<float>((size_t)FR.rows * 1096);
+  float* xB = A.alloc<float>((size_t)FR.rows * 1096);
+  launch_curve_conv(f0, FR2.d_off, FR2.d_len, W.f0conv_w, W.f0conv_b, x514, 520, 512, FR.d_off, FR.d_len, B, FR.max_len, st);
+  launch_curve_conv(nc, FR2.d_off, FR2.d_len, W.nconv_w, W.nconv_b, x514, 520, 513, FR.d_off, FR.d_len, B, FR.max_len, st);
+  adain_blk(r, A, W.enc, x514, 520, FR, FR, sty_dec, W.sty_dec_n, xA, 1096, 0, dry);
+  capture("dec.encode", xA, 1096, 0, 1024, FR, b0);
+  launch_conv_f32(gemm_args(FR, x514, 520, 512, W.asr_w, W.asr_b, 64, xA, 1096, 1024), st);
+  launch_copy_cols(x514, 520, 512, xA, 1096, 1088, 2, FR.d_off, FR.d_len, B, FR.max_len, st);
+  launch_copy_cols(xA, 1096, 1024, xB, 1096, 1024, 66, FR.d_off, FR.d_len, B, FR.max_len, st);
+  float* dcur = xA; float* dnxt = xB;
+  for (int i = 0; i < 3; i++) {
+    adain_blk(r, A, W.dec[i], dcur, 1096, FR, FR, sty_dec, W.sty_dec_n, dnxt, 1096, 0, dry);
+    std::swap(dcur, dnxt);
+    capture(("dec.decode." + std::to_string(i)).c_str(), dcur, 1096, 0, 1024, FR, b0);
+  }
+  float* y = A.alloc<float>((size_t)FR2.rows * 512);
+  adain_blk(r, A, W.dec[3], dcur, 1096, FR, FR2, sty_dec, W.sty_dec_n, y, 512, 0, dry);
+  capture("dec.decode.3", y, 512, 0, 512, FR2, b0);
+
+  // ---- generator: harmonic source + STFT (A.9, K9/K10)
+  float* phase = A.alloc<float>((size_t)9 * FR2.sum_len + 16);
+  float* src = A.alloc<float>((size_t)600 * FR.sum_len + 16);
+  float* har = A.alloc<float>((size_t)G120.rows * 24);
+  launch_sine_phase(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, B, st);
+  if (!dry && d_noise_) {
+    for (int b = 0; b < B; b++)
+      if (600LL * T[b] * 9 > noise_n_) throw ArgError("noise buffer smaller than 600*T*9");
+  }
+  launch_sine_source(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, d_noise_, opt.noise_seed, W.lin_w,
+                     W.lin_b, src, d_s_loc, B, maxS, st);
+  if (debug_ && !dry) {
+    KKX_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; b++) {
+      DebugStage s; s.rows = 600LL * T[b]; s.cols = 1; s.data.resize(s.rows);
+      KKX_CUDA(cudaMemcpy(s.data.data(), src + s_loc[b], s.rows * sizeof(float), cudaMemcpyDeviceToHost));
+      dbg_["har_source#" + std::to_string(b0 + b)] = std::move(s);
+    }
+  }
+  launch_stft(src, d_s_loc, har, 24, G120.d_off, G120.d_len, opt.stft_replicate, B, G120.max_len, st);
+  capture("har", har, 24, 0, 22, G120, b0);
+
+  // ---- generator stage 0 (20T rows, 256 ch)
+  const size_t n20 = (size_t)G20.rows * 256, n120 = (size_t)G120.rows * 128;
+  float* xs0 = A.alloc<float>(n20);
+  float* x0 = A.alloc<float>(n20);
+  float* w0 = A.alloc<float>(n20);
+  float* t0 = A.alloc<float>(n20);
+  float* acc0 = A.alloc<float>(n20);
+  {
+    ConvArgs c = gemm_args(G20, har, 24, 22, W.nc0_w, W.nc0_b, 256, xs0, 256, 0);
+    c.in_off = G120.d_off; c.in_len = G120.d_len;
+    c.ks = 12; c.stride = 6; c.pad = 3;
+    launch_conv_f32(c, st);
+  }
+  arb(r, A, W.nres[0], xs0, G20, sty_dec, W.sty_dec_n, w0, t0, xs0, 1.f, false);
+  capture("gen.x_source.0", xs0, 256, 0, 256, G20, b0);
+  for (int ph = 0; ph < 10; ph++) {  // ConvTranspose1d(512,256,k20,s10,p5) as 10 two-tap phase convs
+    const int q0 = ph < 5 ? 1 : 0;
+    ConvArgs c = gemm_args(FR2, y, 512, 512, W.ups0[ph], W.ups0_b, 256, x0, 256, 0);
+    c.out_off = G20.d_off;
+    c.ks = 2; c.dil = -1; c.pad = -q0; c.stride = 1;
+    c.ors = 10; c.oro = q0 * 10 + ph - 5;
+    c.pact = ACT_LRELU; c.pslope = 0.1f;
+    launch_conv_f32(c, st);
+  }
+  capture("gen.ups.0", x0, 256, 0, 256, G20, b0);
+  launch_add_rows(x0, xs0, x0, 256, G20.d_off, G20.d_len, B, G20.max_len, st);
+  for (int j = 0; j < 3; j++)
+    arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0);
+  capture("gen.stage.0", acc0, 256, 0, 256, G20, b0);
+
+  // ---- generator stage 1 (120T+1 rows, 128 ch)
+  float* xs1 = A.alloc<float>(n120);
+  float* x1 = A.alloc<float>(n120);
+  float* w1 = A.alloc<float>(n120);
+  float* t1 = A.alloc<float>(n120);
+  float* acc1 = A.alloc<float>(n120);
+  launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st);
+  arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
+  capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
+  for (int ph = 0; ph < 6; ph++) {  // ConvTranspose1d(256,128,k12,s6,p3) + ReflectionPad1d((1,0))
+    const int q0 = ph < 3 ? 1 : 0;
+    ConvArgs c = gemm_args(G20, acc0, 256, 256, W.ups1[ph], W.ups1_b, 128, x1, 128, 0);
+    c.out_off = G120.d_off;
+    c.ks = 2; c.dil = -1; c.pad = -q0; c.stride = 1;
+    c.ors = 6; c.oro = q0 * 6 + ph - 3 + 1;
+    c.pact = ACT_LRELU; c.pslope = 0.1f;
+    launch_conv_f32(c, st);
+  }
+  launch_copy_row(x1, 128, 0, 2, G120.d_off, B, st);
+  capture("gen.ups.1", x1, 128, 0, 128, G120, b0);
+  launch_add_rows(x1, xs1, x1, 128, G120.d_off, G120.d_len, B, G120.max_len, st);
+  for (int j = 0; j < 3; j++)
+    arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0);
+  capture("gen.stage.1", acc1, 128, 0, 128, G120, b0);
+
+  // ---- head (K11)
+  float* cp = A.alloc<float>((size_t)G120.rows * 24);
+  {
+    ConvArgs c = gemm_args(G120, acc1, 128, 128, W.post_w, W.post_b, 22, cp, 24, 0);
+    c.ks = 7; c.pad = 3; c.pact = ACT_LRELU; c.pslope = 0.01f;
+    launch_conv_f32(c, st);
+  }
+  capture("conv_post", cp, 24, 0, 22, G120, b0);
+  launch_istft(cp, 24, G120.d_off, G120.d_len, d_audio_, d_s_glob, B, G120.max_len, st);
+}
+
+}  // namespace kkx

@@ -1,0 +1,108 @@
+// testapi.cu -- op-level test hooks (include/kkx_test.h).  Parity harness only.
+#include "../../include/kkx_test.h"
+#include "kernels.h"
+#include <string>
+#include <vector>
+
+using namespace kkx;
+static thread_local std::string t_err;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  DevBuf(const void* host, size_t bytes) {
+    KKX_CUDA(cudaMalloc(&p, bytes ? bytes : 4));
+    if (host && bytes) KKX_CUDA(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+template <class F> int run(int device, F&& f) {
+  try {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) throw CudaError("no CUDA device (no CPU fallback)");
+    KKX_CUDA(cudaSetDevice(device));
+    f();
+    KKX_CUDA(cudaDeviceSynchronize());
+    return KKX_OK;
+  } catch (const std::exception& e) {
+    t_err = e.what();
+    cudaGetLastError();
+    return KKX_ERR_CUDA;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+KKX_API const char* kkx_test_last_error(void) { return t_err.c_str(); }
+
+KKX_API int kkx_test_conv(int device, const float* in, int rows_in, int ldi, int Ci, const float* w,
+                          const float* bias, int Co, int ks, int dil, int pad, int stride,
+                          const float* pscale, const float* pshift, int pact, float pslope,
+                          const float* palpha, int m_len, int ors, int oro, int out_rows,
+                          const float* res, int res_rows, int res_shift, float oscale, int eact,
+                          int accumulate, float* out) {
+  return run(device, [&] {
+    DevBuf din(in, (size_t)rows_in * ldi * 4), dw(w, (size_t)ks * Ci * Co * 4), db(bias, bias ? Co * 4 : 0);
+    DevBuf dps(pscale, pscale ? Ci * 4 : 0), dph(pshift, pshift ? Ci * 4 : 0), dal(palpha, palpha ? Ci * 4 : 0);
+    DevBuf dres(res, res ? (size_t)res_rows * Co * 4 : 0), dout(out, (size_t)out_rows * Co * 4);
+    int meta[4] = {0, rows_in, m_len, 0};
+    DevBuf dm(meta, sizeof meta);
+    ConvArgs a;
+    a.in = din.as<float>(); a.ldi = ldi; a.in_off = dm.as<int>(); a.in_len = dm.as<int>() + 1;
+    a.m_len = dm.as<int>() + 2; a.max_m = m_len; a.B = 1;
+    a.w = dw.as<float>(); a.bias = bias ? db.as<float>() : nullptr;
+    a.Ci = Ci; a.Co = Co; a.ks = ks; a.dil = dil; a.pad = pad; a.stride = stride;
+    a.pscale = pscale ? dps.as<float>() : nullptr; a.pshift = pshift ? dph.as<float>() : nullptr; a.pld = Ci;
+    a.pact = pact; a.pslope = pslope; a.palpha = palpha ? dal.as<float>() : nullptr;
+    a.out = dout.as<float>(); a.ldo = Co; a.ocol = 0; a.out_off = dm.as<int>(); a.ors = ors; a.oro = oro;
+    a.eact = eact;
+    a.res = res ? dres.as<float>() : nullptr; a.ldr = Co; a.rcol = 0; a.res_off = dm.as<int>() + 3;
+    a.res_shift = res_shift; a.oscale = oscale; a.accumulate = accumulate;
+    launch_conv_f32(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)out_rows * Co * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out) {
+  return run(device, [&] {
+    DevBuf dx(xproj, (size_t)N * 2048 * 4), dw(whhT, (size_t)2 * 256 * 1024 * 4), dout(nullptr, (size_t)N * 512 * 4);
+    int meta[2] = {0, N};
+    DevBuf dm(meta, sizeof meta);
+    launch_lstm(dx.as<float>(), dw.as<float>(), dout.as<float>(), 512, 0, dm.as<int>(), dm.as<int>() + 1, 1, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)N * 512 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) {
+  return run(device, [&] {
+    DevBuf dq(qkv, (size_t)N * 2304 * 4), dout(nullptr, (size_t)N * 768 * 4);
+    int meta[2] = {0, N};
+    DevBuf dm(meta, sizeof meta);
+    launch_attention(dq.as<float>(), dout.as<float>(), dm.as<int>(), dm.as<int>() + 1, 1, N, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(ctx, dout.p, (size_t)N * 768 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_adain_coef(int device, const float* x, int L, int C, const float* gamma_beta,
+                                float* scale, float* shift) {
+  return run(device, [&] {
+    const int nch = (L + kStatRows - 1) / kStatRows;
+    DevBuf dx(x, (size_t)L * C * 4), dgb(gamma_beta, (size_t)2 * C * 4), dpart(nullptr, (size_t)nch * 2 * C * 4);
+    DevBuf dsc(nullptr, C * 4), dsh(nullptr, C * 4);
+    int meta[2] = {0, L};
+    DevBuf dm(meta, sizeof meta);
+    launch_colstats(dx.as<float>(), C, C, dpart.as<float>(), dm.as<int>(), dm.as<int>() + 1, 1, L, 0);
+    launch_adain_coef(dpart.as<float>(), C, L, dm.as<int>() + 1, dgb.as<float>(), 2 * C, 0, 1e-5f,
+                      dsc.as<float>(), dsh.as<float>(), 1, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(scale, dsc.p, C * 4, cudaMemcpyDeviceToHost));
+    KKX_CUDA(cudaMemcpy(shift, dsh.p, C * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

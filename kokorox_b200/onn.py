@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference's inference seam, over the C ABI of ``include/kkx.h``.
+
+Reference interface mirrored (same names, argument meaning and error behaviour):
+
+* ``kokorox::onn::init_ort(dylib_path)``        /root/reference/kokorox/src/onn/mod.rs:19-49
+* ``OrtKoko::new(model_path) -> Result<_, String>``          .../onn/ort_koko.rs:31-35
+* ``OrtKoko::infer(tokens: Vec<Vec<i64>>, styles: Vec<Vec<f32>>, speed: f32)
+      -> Result<ArrayD<f32>, Box<dyn Error>>``               .../onn/ort_koko.rs:37-91
+
+The host language of the reference is Rust, which this image does not have; the Rust shim a
+maintainer would add is in INTEGRATION.md, and this module is the same shim in Python (ctypes).
+There is no CPU fallback: if ``libkkx.so`` is missing or no B200 is visible every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libkkx.so")
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class KkxError(RuntimeError):
+    """Err(String) of the reference API (ort_koko.rs:31,42)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kkx error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libkkx.so and declare the prototypes of include/kkx.h (and kkx_test.h)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or os.environ.get("KKX_LIB", LIB_PATH)
+        if not os.path.exists(p):
+            raise KkxError(-4, f"{p} not found: build it with `python -m kokorox_b200.build` "
+                               "(there is no CPU fallback)")
+        lib = C.CDLL(p)
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        P = C.POINTER
+        lib.kkx_version.restype = C.c_char_p
+        lib.kkx_init.restype = C.c_int
+        lib.kkx_create.argtypes = [C.c_char_p, C.c_int, P(vp)]
+        lib.kkx_destroy.argtypes = [vp]
+        lib.kkx_destroy.restype = None
+        lib.kkx_last_error.argtypes = [vp]
+        lib.kkx_last_error.restype = C.c_char_p
+        lib.kkx_infer.argtypes = [vp, P(i64), i32, P(f32), f32, P(P(f32)), P(i64), P(i32)]
+        lib.kkx_infer_batch.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32), P(P(f32)), P(i64), P(i32)]
+        lib.kkx_release.argtypes = [vp, P(f32)]
+        lib.kkx_release.restype = None
+        lib.kkx_stage_batch.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32)]
+        lib.kkx_run_staged.argtypes = [vp, P(i64), P(i64)]
+        lib.kkx_fetch_staged.argtypes = [vp, P(f32), i64, P(i64), P(i32)]
+        lib.kkx_set_option.argtypes = [vp, C.c_char_p, i64]
+        lib.kkx_get_stat.argtypes = [vp, C.c_char_p]
+        lib.kkx_get_stat.restype = i64
+        lib.kkx_set_noise.argtypes = [vp, P(f32), i64]
+        lib.kkx_set_inject.argtypes = [vp, C.c_char_p, vp, i64]
+        lib.kkx_debug_stage.argtypes = [vp, C.c_char_p, i32, P(f32), i64, P(i64), P(i64)]
+        lib.kkx_debug_stage.restype = i64
+        lib.kkx_debug_enable.argtypes = [vp, C.c_int]
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def init_ort(dylib_path: Optional[str] = None) -> None:
+    """mod.rs:19-49.  ``dylib_path`` optionally names libkkx.so (the reference's ORT_DYLIB_PATH)."""
+    lib = load_library(dylib_path)
+    rc = lib.kkx_init()
+    if rc != 0:
+        raise KkxError(rc, (lib.kkx_last_error(None) or b"").decode())
+
+
+class B200Koko:
+    """Drop-in for ``OrtKoko`` (ort_koko.rs:13-91): ``new(model_path)`` then ``infer(...)``.
+
+    Send + Sync like the reference type (ort_koko.rs:17-18): one instance may be shared between
+    threads; calls serialise inside the library.
+    """
+
+    def __init__(self, model_path: str, device: int = 0):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.kkx_create(os.fsencode(model_path), int(device), C.byref(self._ctx))
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise KkxError(rc, (self._lib.kkx_last_error(None) or b"").decode())
+        self.device = device
+
+    @classmethod
+    def new(cls, model_path: str, device: int = 0) -> "B200Koko":
+        return cls(model_path, device)
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.kkx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise KkxError(rc, (self._lib.kkx_last_error(self._ctx) or b"").decode())
+
+    def _require(self):
+        if not self._ctx.value:
+            raise KkxError(-5, "Session is not initialized.")  # ort_koko.rs:88-90
+
+    # -- the reference entry point --------------------------------------------------------
+    def infer(self, tokens: Sequence[Sequence[int]], styles: Sequence[Sequence[float]],
+              speed: float) -> np.ndarray:
+        """ort_koko.rs:37-91.  tokens [B][N] (rectangular, incl. the 0 pads), styles [B][256],
+        one speed.  Returns the waveform(s) as one flat f32 array -- the caller flattens the
+        reference's output the same way (koko.rs:1179)."""
+        outs = self.infer_batch([list(t) for t in tokens], styles, [speed] * len(tokens))
+        return outs[0] if len(outs) == 1 else np.concatenate(outs)
+
+    def infer_batch(self, tokens: Sequence[Sequence[int]], styles, speeds: Sequence[float],
+                    return_durations: bool = False):
+        """Ragged batch of independent utterances (kkx_infer_batch).  Returns a list of 1-D f32
+        arrays (and the per-item integer frame durations if asked)."""
+        self._require()
+        B = len(tokens)
+        if B == 0:
+            raise KkxError(-1, "empty batch")
+        lens = [len(t) for t in tokens]
+        offs = np.zeros(B + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(lens)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tokens]))
+        st = np.ascontiguousarray(np.asarray(styles, dtype=np.float32).reshape(B, -1))
+        if st.shape[1] != 256:
+            raise KkxError(-1, f"style must have 256 values, got {st.shape[1]}")
+        sp = np.ascontiguousarray(np.asarray(speeds, dtype=np.float32).reshape(B))
+        audio = C.POINTER(C.c_float)()
+        soff = np.zeros(B + 1, dtype=np.int64)
+        dur = np.zeros(int(offs[-1]), dtype=np.int32)
+        rc = self._lib.kkx_infer_batch(
+            self._ctx, B, flat.ctypes.data_as(C.POINTER(C.c_int64)),
+            offs.ctypes.data_as(C.POINTER(C.c_int32)), _fp(st), _fp(sp), C.byref(audio),
+            soff.ctypes.data_as(C.POINTER(C.c_int64)), dur.ctypes.data_as(C.POINTER(C.c_int32)))
+        self._check(rc)
+        try:
+            total = int(soff[-1])
+            buf = np.ctypeslib.as_array(audio, shape=(max(total, 1),))[:total]
+            outs = [buf[int(soff[b]):int(soff[b + 1])].copy() for b in range(B)]
+        finally:
+            self._lib.kkx_release(self._ctx, audio)
+        if return_durations:
+            return outs, [dur[int(offs[b]):int(offs[b + 1])].copy() for b in range(B)]
+        return outs
+
+    # -- device-resident path (bench `value`) ---------------------------------------------
+    def stage(self, tokens, styles, speeds) -> None:
+        self._require()
+        B = len(tokens)
+        offs = np.zeros(B + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(t) for t in tokens])
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tokens]))
+        st = np.ascontiguousarray(np.asarray(styles, dtype=np.float32).reshape(B, 256))
+        sp = np.ascontiguousarray(np.asarray(speeds, dtype=np.float32).reshape(B))
+        self._check(self._lib.kkx_stage_batch(self._ctx, B, flat.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              offs.ctypes.data_as(C.POINTER(C.c_int32)), _fp(st), _fp(sp)))
+        self._staged = (B, int(offs[-1]))
+
+    def run_staged(self):
+        """Returns (total_samples, kernel_launches)."""
+        self._require()
+        n, l = C.c_int64(), C.c_int64()
+        self._check(self._lib.kkx_run_staged(self._ctx, C.byref(n), C.byref(l)))
+        return int(n.value), int(l.value)
+
+    def fetch_staged(self, total_samples: int):
+        B, ntok = self._staged
+        out = np.empty(max(total_samples, 1), dtype=np.float32)
+        soff = np.zeros(B + 1, dtype=np.int64)
+        dur = np.zeros(ntok, dtype=np.int32)
+        self._check(self._lib.kkx_fetch_staged(self._ctx, _fp(out), total_samples,
+                                               soff.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               dur.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out[:total_samples], soff, dur
+
+    # -- options / test hooks -------------------------------------------------------------
+    def set_option(self, key: str, value: int) -> None:
+        self._require()
+        self._check(self._lib.kkx_set_option(self._ctx, key.encode(), int(value)))
+
+    def get_stat(self, key: str) -> int:
+        self._require()
+        return int(self._lib.kkx_get_stat(self._ctx, key.encode()))
+
+    def set_noise(self, noise: Optional[np.ndarray]) -> None:
+        self._require()
+        if noise is None:
+            self._check(self._lib.kkx_set_noise(self._ctx, None, 0))
+        else:
+            a = np.ascontiguousarray(noise, dtype=np.float32).reshape(-1)
+            self._check(self._lib.kkx_set_noise(self._ctx, _fp(a), a.size))
+
+    def set_inject(self, name: str, data: Optional[np.ndarray]) -> None:
+        self._require()
+        if data is None:
+            self._check(self._lib.kkx_set_inject(self._ctx, name.encode(), None, 0))
+            return
+        a = np.ascontiguousarray(data, dtype=np.int32 if name == "pred_dur" else np.float32).reshape(-1)
+        self._check(self._lib.kkx_set_inject(self._ctx, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+
+    def debug_enable(self, on: bool = True) -> None:
+        self._require()
+        self._check(self._lib.kkx_debug_enable(self._ctx, 1 if on else 0))
+
+    def debug_stage(self, name: str, item: int = 0) -> Optional[np.ndarray]:
+        self._require()
+        rows, cols = C.c_int64(), C.c_int64()
+        n = self._lib.kkx_debug_stage(self._ctx, name.encode(), item, None, 0, C.byref(rows), C.byref(cols))
+        if n < 0:
+            return None
+        out = np.empty(max(int(n), 1), dtype=np.float32)
+        self._lib.kkx_debug_stage(self._ctx, name.encode(), item, _fp(out), n, None, None)
+        out = out[:n].reshape(int(rows.value), int(cols.value))
+        return out[:, 0] if cols.value == 1 else out

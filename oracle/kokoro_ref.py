@@ -41,7 +41,12 @@ HOP = 5
 
 
 def _t(a) -> torch.Tensor:
-    return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    if isinstance(a, torch.Tensor):
+        return a
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
+    return torch.from_numpy(a)
 
 
 class KokoroOracle:

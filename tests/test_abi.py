@@ -1,0 +1,70 @@
+"""CPU tests: the C-ABI library builds, loads, exports every symbol include/*.h declares, and
+fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from kokorox_b200 import build
+    path = build.build()
+    return ctypes.CDLL(path)
+
+
+def declared_symbols():
+    syms = []
+    for h in ("kkx.h", "kkx_test.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        syms += re.findall(r"KKX_API[^;(]*?\b(kkx_\w+)\s*\(", src)
+    return sorted(set(syms))
+
+
+def test_header_declares_the_boundary():
+    syms = declared_symbols()
+    for s in ("kkx_init", "kkx_create", "kkx_destroy", "kkx_last_error", "kkx_infer", "kkx_infer_batch",
+              "kkx_release", "kkx_stage_batch", "kkx_run_staged", "kkx_fetch_staged"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"libkkx.so does not export {s}"
+
+
+def test_no_torch_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "kkx.h")).read()
+    assert "torch" not in src and "at::" not in src and "std::" not in src
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(lib, tmp_path):
+    lib.kkx_last_error.restype = ctypes.c_char_p
+    lib.kkx_last_error.argtypes = [ctypes.c_void_p]
+    assert lib.kkx_init() == -4
+    ctx = ctypes.c_void_p()
+    rc = lib.kkx_create(b"/nonexistent.kkxw", 0, ctypes.byref(ctx))
+    assert rc == -4 and not ctx.value
+    assert b"no CPU fallback" in lib.kkx_last_error(None)
+    from kokorox_b200.onn import B200Koko, KkxError
+    with pytest.raises(KkxError):
+        B200Koko.new("/nonexistent.kkxw")
+
+
+def test_python_shim_mirrors_reference_names():
+    # OrtKoko::new / OrtKoko::infer / init_ort (ort_koko.rs:31-42, mod.rs:19-49)
+    from kokorox_b200 import onn
+    assert callable(onn.init_ort) and hasattr(onn.B200Koko, "new") and hasattr(onn.B200Koko, "infer")
