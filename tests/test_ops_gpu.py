@@ -1,0 +1,149 @@
+"""GPU tests (-m gpu): each hand-written kernel in isolation against the matching torch op,
+through the op-level hooks of include/kkx_test.h."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from kokorox_b200.onn import load_library
+    lib = load_library()
+    lib.kkx_test_last_error.restype = C.c_char_p
+    return lib
+
+
+def fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def run_conv(lib, x, w_kic, bias, ks, dil, pad, stride, m_len, out_rows, ors=1, oro=0, pscale=None, pshift=None,
+             pact=0, pslope=0.0, palpha=None, res=None, res_shift=0, oscale=1.0, eact=0, accumulate=0, out_init=None):
+    rows_in, Ci = x.shape
+    Co = w_kic.shape[2]
+    out = np.zeros((out_rows, Co), np.float32) if out_init is None else out_init.copy()
+    rc = lib.kkx_test_conv(0, fp(x), rows_in, Ci, Ci, fp(w_kic), fp(bias), Co, ks, dil, pad, stride, fp(pscale),
+                           fp(pshift), pact, C.c_float(pslope), fp(palpha), m_len, ors, oro, out_rows, fp(res),
+                           0 if res is None else res.shape[0], res_shift, C.c_float(oscale), eact, accumulate, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    return out
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("L,Ci,Co,k,dil", [(300, 128, 128, 3, 1), (777, 256, 256, 7, 3), (513, 128, 128, 11, 5),
+                                           (130, 514, 1024, 3, 1), (1000, 128, 22, 7, 1), (40, 768, 2304, 1, 1)])
+def test_conv1d_matches_torch(lib, L, Ci, Co, k, dil):
+    x, w, b = rnd(L, Ci, seed=1), rnd(Co, Ci, k, seed=2, scale=1 / np.sqrt(Ci * k)), rnd(Co, seed=3)
+    pad = dil * (k - 1) // 2
+    ref = F.conv1d(torch.from_numpy(x.T)[None], torch.from_numpy(w), torch.from_numpy(b), padding=pad, dilation=dil)[0].T.numpy()
+    got = run_conv(lib, x, np.ascontiguousarray(w.transpose(2, 1, 0)), b, k, dil, pad, 1, L, L)
+    np.testing.assert_allclose(got, ref, atol=2e-4, rtol=1e-4)
+
+
+def test_conv_strided_noise_conv(lib):
+    # noise_convs[0]: Conv1d(22,256,k12,s6,p3) on 120T+1 rows -> 20T rows
+    T = 7
+    x, w, b = rnd(120 * T + 1, 22, seed=4), rnd(256, 22, 12, seed=5, scale=0.1), rnd(256, seed=6)
+    ref = F.conv1d(torch.from_numpy(x.T)[None], torch.from_numpy(w), torch.from_numpy(b), stride=6, padding=3)[0].T.numpy()
+    assert ref.shape[0] == 20 * T
+    got = run_conv(lib, x, np.ascontiguousarray(w.transpose(2, 1, 0)), b, 12, 1, 3, 6, 20 * T, 20 * T)
+    np.testing.assert_allclose(got, ref, atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("Ci,Co,k,s", [(512, 256, 20, 10), (256, 128, 12, 6)])
+def test_conv_transpose_as_phase_convs(lib, Ci, Co, k, s):
+    # generator ups: ConvTranspose1d(k=2s, stride s, padding s/2) as s two-tap phase convs, with the
+    # LeakyReLU(0.1) prologue the generator applies first
+    L, p = 37, (k - s) // 2
+    x, w, b = rnd(L, Ci, seed=7), rnd(Ci, Co, k, seed=8, scale=0.05), rnd(Co, seed=9)
+    xin = F.leaky_relu(torch.from_numpy(x.T)[None], 0.1)
+    ref = F.conv_transpose1d(xin, torch.from_numpy(w), torch.from_numpy(b), stride=s, padding=p)[0].T.numpy()
+    out = np.full((L * s, Co), np.nan, np.float32)
+    for r in range(s):
+        q0 = 1 if r < p else 0
+        ph = np.stack([w[:, :, r], w[:, :, r + s]])  # [2][Ci][Co]
+        out = run_conv(lib, x, np.ascontiguousarray(ph), b, 2, -1, -q0, 1, L, L * s, ors=s, oro=q0 * s + r - p,
+                       pact=1, pslope=0.1, out_init=out)
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(out, ref, atol=2e-4, rtol=1e-4)
+
+
+def test_conv_prologue_epilogue_fusions(lib):
+    # AdaIN scale/shift + Snake on the operand, bias + residual(row>>1) + scale + accumulate on the result
+    L, Cc, k = 200, 128, 3
+    x, w, b = rnd(L, Cc, seed=10), rnd(Cc, Cc, k, seed=11, scale=0.05), rnd(Cc, seed=12)
+    sc, sh = (1 + 0.3 * rnd(Cc, seed=13)), 0.2 * rnd(Cc, seed=14)
+    alpha = np.clip(1 + 0.3 * rnd(Cc, seed=15), 0.3, 2).astype(np.float32)
+    res = rnd(L // 2, Cc, seed=16)
+    init = rnd(L, Cc, seed=17)
+    xt = torch.from_numpy(x) * torch.from_numpy(sc) + torch.from_numpy(sh)
+    a = torch.from_numpy(alpha)
+    xt = xt + (1 / a) * torch.sin(a * xt) ** 2
+    y = F.conv1d(xt.T[None], torch.from_numpy(w), torch.from_numpy(b), padding=1)[0].T
+    ref = (torch.from_numpy(init) + 0.5 * (y + torch.from_numpy(res).repeat_interleave(2, 0))).numpy()
+    got = run_conv(lib, x, np.ascontiguousarray(w.transpose(2, 1, 0)), b, k, 1, 1, 1, L, L, pscale=sc.astype(np.float32),
+                   pshift=sh.astype(np.float32), pact=2, palpha=alpha, res=res, res_shift=1, oscale=0.5, accumulate=1,
+                   out_init=init)
+    np.testing.assert_allclose(got, ref, atol=3e-4, rtol=1e-4)
+
+
+def test_gemm_gelu_new_epilogue(lib):
+    x, w, b = rnd(100, 768, seed=18), rnd(2048, 768, seed=19, scale=0.03), rnd(2048, seed=20)
+    f = torch.from_numpy(x) @ torch.from_numpy(w).T + torch.from_numpy(b)
+    ref = (0.5 * f * (1 + torch.tanh(np.sqrt(2 / np.pi) * (f + 0.044715 * f ** 3)))).numpy()
+    got = run_conv(lib, x, np.ascontiguousarray(w.T[None]), b, 1, 1, 0, 1, 100, 100, eact=3)
+    np.testing.assert_allclose(got, ref, atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N", [1, 5, 64, 200])
+def test_lstm_matches_torch(lib, N):
+    torch.manual_seed(N)
+    m = torch.nn.LSTM(640, 256, 1, batch_first=True, bidirectional=True).eval()
+    x = torch.randn(1, N, 640)
+    with torch.no_grad():
+        ref = m(x)[0][0].numpy()
+        xp = []
+        whh = np.zeros((2, 256, 1024), np.float32)
+        for d, sfx in enumerate(("", "_reverse")):
+            wih, b = getattr(m, "weight_ih_l0" + sfx), getattr(m, "bias_ih_l0" + sfx) + getattr(m, "bias_hh_l0" + sfx)
+            xp.append((x[0] @ wih.T + b).numpy())
+            whh[d] = getattr(m, "weight_hh_l0" + sfx).numpy().T
+    xproj = np.ascontiguousarray(np.concatenate(xp, axis=1), dtype=np.float32)
+    out = np.zeros((N, 512), np.float32)
+    rc = lib.kkx_test_lstm(0, fp(xproj), fp(whh), N, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("N", [3, 52, 130, 512])
+def test_attention_matches_torch(lib, N):
+    qkv = rnd(N, 2304, seed=N)
+    t = torch.from_numpy(qkv)
+    q, k, v = (t[:, i * 768:(i + 1) * 768].view(N, 12, 64).transpose(0, 1) for i in range(3))
+    p = torch.softmax(q @ k.transpose(1, 2) / 8.0, -1)
+    ref = (p @ v).transpose(0, 1).reshape(N, 768).numpy()
+    out = np.zeros((N, 768), np.float32)
+    rc = lib.kkx_test_attention(0, fp(qkv), N, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("L,Cc", [(50, 128), (1000, 256), (20001, 128)])
+def test_instance_norm_adain_coefficients(lib, L, Cc):
+    x = (rnd(L, Cc, seed=L) * 2 + 3 * rnd(1, Cc, seed=L + 1)).astype(np.float32)
+    gb = rnd(2 * Cc, seed=L + 2, scale=0.3)
+    sc, sh = np.zeros(Cc, np.float32), np.zeros(Cc, np.float32)
+    rc = lib.kkx_test_adain_coef(0, fp(x), L, Cc, fp(gb), fp(sc), fp(sh))
+    assert rc == 0, lib.kkx_test_last_error()
+    ref = (1 + torch.from_numpy(gb[:Cc]))[None, :, None] * F.instance_norm(torch.from_numpy(x.T.copy())[None], eps=1e-5) \
+        + torch.from_numpy(gb[Cc:])[None, :, None]
+    got = x * sc + sh
+    np.testing.assert_allclose(got, ref[0].T.numpy(), atol=3e-4, rtol=1e-4)
