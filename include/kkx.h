@@ -103,6 +103,12 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
 KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value);
 KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key); /* "launches", "last_frames", "gpu_us" ... */
 
+/* Per-kernel device timing of the last run (CUDA events on the library's stream, one after every
+ * launch).  kkx_profile_json writes {"conv_flops": F, "gpu_us": T, "kernels": {name: [launches,
+ * total_us]}} and returns the full length of the text. */
+KKX_API int kkx_profile_enable(kkx_ctx* ctx, int enable);
+KKX_API int64_t kkx_profile_json(kkx_ctx* ctx, char* buf, int64_t capacity);
+
 /* ---- test-only hooks (parity harness; not used by the Rust shim) -------------------------
  * kkx_set_noise: explicit SineGen noise, element (sample t, harmonic h) of batch item 0 at
  *   noise[t*9+h]; n = number of floats; n == 0 returns to the on-device generator.  With a

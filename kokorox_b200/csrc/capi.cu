@@ -6,7 +6,9 @@
 #include "model.h"
 #include <cstring>
 #include <mutex>
+#include <map>
 #include <set>
+#include <sstream>
 
 using namespace kkx;
 
@@ -14,7 +16,8 @@ struct kkx_ctx {
   std::unique_ptr<Model> model;
   std::mutex mu;  // single-flight like the reference's Mutex<Session> (ort_koko.rs:14,77-78)
   std::string err;
-  std::set<float*> pinned;  // audio buffers handed out
+  std::map<float*, size_t> pinned;       // audio buffers handed out -> capacity (floats)
+  std::vector<std::pair<float*, size_t>> pinned_free;  // returned buffers kept for reuse
 };
 
 static thread_local std::string g_err;
@@ -71,7 +74,8 @@ KKX_API void kkx_destroy(kkx_ctx* ctx) {
   if (!ctx) return;
   try {
     if (ctx->model) cudaSetDevice(ctx->model->device());
-    for (float* p : ctx->pinned) cudaFreeHost(p);
+    for (auto& p : ctx->pinned) cudaFreeHost(p.first);
+    for (auto& p : ctx->pinned_free) cudaFreeHost(p.first);
     ctx->model.reset();
   } catch (...) {}
   delete ctx;
@@ -99,11 +103,21 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
     m.run();
     float* host = nullptr;
     const long long n = m.total_samples();
-    KKX_CUDA(cudaMallocHost(&host, std::max<long long>(n, 1) * sizeof(float)));
+    size_t cap = 0;
+    for (size_t i = 0; i < ctx->pinned_free.size(); i++)
+      if (ctx->pinned_free[i].second >= (size_t)n) {
+        host = ctx->pinned_free[i].first; cap = ctx->pinned_free[i].second;
+        ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
+        break;
+      }
+    if (!host) {
+      cap = (size_t)std::max<long long>(n + n / 8, 1024);
+      KKX_CUDA(cudaMallocHost(&host, cap * sizeof(float)));
+    }
     try {
       m.fetch(host, n, out_sample_offsets, out_pred_dur);
     } catch (...) { cudaFreeHost(host); throw; }
-    ctx->pinned.insert(host);
+    ctx->pinned[host] = cap;
     *out_audio = host;
   });
 }
@@ -123,8 +137,12 @@ KKX_API void kkx_release(kkx_ctx* ctx, float* audio) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->pinned.find(audio);
   if (it != ctx->pinned.end()) {
-    if (ctx->model) cudaSetDevice(ctx->model->device());
-    cudaFreeHost(audio);
+    if (ctx->pinned_free.size() < 4) {
+      ctx->pinned_free.push_back({it->first, it->second});
+    } else {
+      if (ctx->model) cudaSetDevice(ctx->model->device());
+      cudaFreeHost(audio);
+    }
     ctx->pinned.erase(it);
   }
 }
@@ -181,6 +199,36 @@ KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key) {
   if (k == "gpu_us") return (int64_t)ctx->model->last_gpu_us;
   if (k == "precision") return ctx->model->opt.precision;
   return -1;
+}
+
+KKX_API int kkx_profile_enable(kkx_ctx* ctx, int enable) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->model->stats.profile = enable != 0;
+  return KKX_OK;
+}
+
+KKX_API int64_t kkx_profile_json(kkx_ctx* ctx, char* buf, int64_t capacity) {
+  if (check_ctx(ctx)) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  std::ostringstream os;
+  os << "{\"conv_flops\": " << ctx->model->stats.conv_flops << ", \"gpu_us\": " << ctx->model->last_gpu_us
+     << ", \"kernels\": {";
+  bool first = true;
+  for (auto& kv : ctx->model->prof_) {
+    if (!first) os << ", ";
+    first = false;
+    os << "\"" << kv.first << "\": [" << kv.second.first << ", " << kv.second.second << "]";
+  }
+  os << "}}";
+  const std::string s = os.str();
+  if (buf && capacity > 0) {
+    const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
 }
 
 KKX_API int kkx_set_noise(kkx_ctx* ctx, const float* noise, int64_t n) {

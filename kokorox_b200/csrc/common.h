@@ -34,12 +34,31 @@ struct IoError : std::runtime_error {
 struct LaunchStats {
   int64_t launches = 0;
   bool check_each = false;  // KKX_DEBUG_SYNC=1: synchronize + check after every launch
+  // per-kernel timing (kkx_profile_enable): one event after every launch on the in-order stream;
+  // the gap between consecutive events is attributed to the launch in between
+  bool profile = false;
+  std::vector<cudaEvent_t> events;       // pool, events[0] = start of run
+  std::vector<const char*> names;        // names[i] = kernel launched before events[i+1]
+  size_t n_events = 0;
+  double conv_flops = 0;                 // algorithmic FLOPs issued through the shifted-GEMM kernels
+  cudaEvent_t next_event() {
+    if (n_events == events.size()) {
+      cudaEvent_t e; cudaEventCreate(&e); events.push_back(e);
+    }
+    return events[n_events++];
+  }
 };
 extern thread_local LaunchStats* g_launch_stats;
 extern thread_local bool g_dry_run;  // true while sizing arenas: launchers return immediately
 
 inline void post_launch(const char* name, cudaStream_t st) {
-  if (g_launch_stats) g_launch_stats->launches++;
+  if (g_launch_stats) {
+    g_launch_stats->launches++;
+    if (g_launch_stats->profile) {
+      cudaEventRecord(g_launch_stats->next_event(), st);
+      g_launch_stats->names.push_back(name);
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && g_launch_stats && g_launch_stats->check_each) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {

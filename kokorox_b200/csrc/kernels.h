@@ -18,6 +18,7 @@ struct ConvArgs {
   const float* in = nullptr; int ldi = 0;
   const int* in_off = nullptr; const int* in_len = nullptr;
   const int* m_len = nullptr; int max_m = 0; int B = 1;
+  long long sum_m = 0;  // sum of m_len over items (host copy; FLOP accounting only)
   const float* w = nullptr; const float* bias = nullptr;
   int Ci = 0, Co = 0, ks = 1, dil = 1, pad = 0, stride = 1;
   const float* pscale = nullptr; const float* pshift = nullptr; int pld = 0;

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(ConvArgs a) {
 void launch_conv_f32(const ConvArgs& a, cudaStream_t st) {
   if (g_dry_run) return;
   if (a.max_m <= 0 || a.B <= 0) return;
+  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
   // tile choice: big tiles when there is enough work to fill 148 SMs, small ones otherwise
   const long long tiles128 = (long long)((a.max_m + 127) / 128) * ((a.Co + 127) / 128) * a.B;
   if (a.Co >= 128 && tiles128 >= 148) {

@@ -426,8 +426,12 @@ void Model::run() {
   KKX_CUDA(cudaSetDevice(device_));
   g_launch_stats = &stats;
   stats.launches = 0;
+  stats.conv_flops = 0;
+  stats.n_events = 0;
+  stats.names.clear();
   dbg_.clear();
   KKX_CUDA(cudaEventRecord(ev0_, stream_));
+  if (stats.profile) cudaEventRecord(stats.next_event(), stream_);
   Run r;
   token_phase(r);
 
@@ -474,6 +478,15 @@ void Model::run() {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0_, ev1_);
   last_gpu_us = ms * 1e3;
+  if (stats.profile) {
+    prof_.clear();
+    for (size_t i = 0; i + 1 < stats.n_events && i < stats.names.size(); i++) {
+      float dt = 0.f;
+      cudaEventElapsedTime(&dt, stats.events[i], stats.events[i + 1]);
+      auto& e = prof_[stats.names[i]];
+      e.first += 1; e.second += dt * 1e3;
+    }
+  }
   g_launch_stats = nullptr;
 }
 

@@ -98,6 +98,7 @@ class Model {
   LaunchStats stats;
   long long last_frames = 0;
   double last_gpu_us = 0;
+  std::map<std::string, std::pair<long long, double>> prof_;  // kernel -> (launches, total us)
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
 

@@ -12,7 +12,7 @@ ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float*
                    int N, float* out, int ldo, int ocol) {
   ConvArgs a;
   a.in = in; a.ldi = ldi; a.in_off = L.d_off; a.in_len = L.d_len;
-  a.m_len = L.d_len; a.max_m = L.max_len; a.B = L.B;
+  a.m_len = L.d_len; a.max_m = L.max_len; a.B = L.B; a.sum_m = L.sum_len;
   a.w = w; a.bias = bias; a.Ci = K; a.Co = N;
   a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = L.d_off;
   return a;

@@ -70,6 +70,9 @@ def load_library(path: Optional[str] = None):
         lib.kkx_debug_stage.argtypes = [vp, C.c_char_p, i32, P(f32), i64, P(i64), P(i64)]
         lib.kkx_debug_stage.restype = i64
         lib.kkx_debug_enable.argtypes = [vp, C.c_int]
+        lib.kkx_profile_enable.argtypes = [vp, C.c_int]
+        lib.kkx_profile_json.argtypes = [vp, C.c_char_p, i64]
+        lib.kkx_profile_json.restype = i64
         if path is None:
             _lib = lib
         return lib
@@ -224,6 +227,19 @@ class B200Koko:
             return
         a = np.ascontiguousarray(data, dtype=np.int32 if name == "pred_dur" else np.float32).reshape(-1)
         self._check(self._lib.kkx_set_inject(self._ctx, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+
+    def profile_enable(self, on: bool = True) -> None:
+        self._require()
+        self._check(self._lib.kkx_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile(self) -> dict:
+        """Per-kernel device time of the last run: {"conv_flops", "gpu_us", "kernels": {name: [n, us]}}."""
+        import json
+        self._require()
+        n = self._lib.kkx_profile_json(self._ctx, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        self._lib.kkx_profile_json(self._ctx, buf, n + 1)
+        return json.loads(buf.value.decode())
 
     def debug_enable(self, on: bool = True) -> None:
         self._require()
