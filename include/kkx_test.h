@@ -27,6 +27,14 @@ KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* x [L,C] + style row (gamma|beta, 2C) -> scale [C], shift [C] (InstanceNorm stats + AdaIN) */
 KKX_API int kkx_test_adain_coef(int device, const float* x, int L, int C, const float* gamma_beta,
                                 float* scale, float* shift);
+/* Tensor-core (tcgen05/TMEM/TMA) shifted GEMM, stride 1: x [L, Ci] fp32 is rounded to bf16 by the
+ * operand-producer kernel (optional per-channel scale/shift + activation), w [Co][ks][Ci] fp32 is
+ * rounded to bf16 on the host; fp32 accumulation and epilogue.  out [out_rows, Co] pre-filled. */
+KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                             int Co, int ks, int dil, int pad, const float* pscale, const float* pshift,
+                             int pact, float pslope, const float* palpha, int m_len, int ors, int oro,
+                             int out_rows, const float* res, int res_rows, int res_shift, float oscale,
+                             int accumulate, float* out);
 KKX_API const char* kkx_test_last_error(void);
 
 #ifdef __cplusplus

@@ -32,6 +32,33 @@ struct ConvArgs {
 };
 void launch_conv_f32(const ConvArgs& a, cudaStream_t st);
 
+// Tensor-core (tcgen05) variant of the shifted GEMM, stride 1 only: bf16 operands fetched by TMA
+// (A = activations [rows_total, Cpad] with zero gap rows / pad columns, B = weights
+// [Co, ks*Cpad]), fp32 accumulation in TMEM, fp32 epilogue (bias, residual, scale, accumulate).
+struct TcConvArgs {
+  const void* tmA = nullptr;  // host pointers to CUtensorMap objects (copied into kernel params)
+  const void* tmB = nullptr;
+  int Cpad = 0, Ci = 0, Co = 0, ks = 1, dil = 1, pad = 0;
+  const int* in_off = nullptr; const int* m_len = nullptr; int max_m = 0; int B = 1; long long sum_m = 0;
+  const float* bias = nullptr;
+  float* out = nullptr; int ldo = 0; int ocol = 0; const int* out_off = nullptr; int ors = 1, oro = 0;
+  const float* res = nullptr; int ldr = 0; int rcol = 0; const int* res_off = nullptr; int res_shift = 0;
+  float oscale = 1.f; int accumulate = 0; int vec4 = 0;
+};
+void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);
+// out_map: 128-byte CUtensorMap storage (64-byte aligned).  bf16 [outer, inner], box [box_outer, 64].
+void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
+                    long long pitch_elems, int box_outer);
+inline int tc_box_n(int Co) { return Co > 128 ? 256 : (Co > 64 ? 128 : 64); }
+// bf16 operand producers (AdaIN scale/shift + activation fused; zero halo rows and pad columns)
+void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                       float slope, const float* alpha, void* out, int Cpad, int rows_total,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st);
+void launch_pool_up_bf16(const float* in, int ldi, const float* scale, const float* shift, float slope,
+                         const float* w, const float* bias, int C, void* out, int Cpad, int rows_total,
+                         const int* in_off, const int* in_len, const int* out_off, int B, int max_len,
+                         cudaStream_t st);
+
 // y = act( LN(x (+res)) [* w + b] [(1+gamma_b) * . + beta_b] ), one row at a time.
 struct LnArgs {
   const float* x = nullptr; int ldx = 0;

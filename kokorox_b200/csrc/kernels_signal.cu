@@ -445,6 +445,10 @@ __global__ void __launch_bounds__(128) stft_kernel(const float* __restrict__ x,
     }
     xw[j] = xp[i] * c_hann20[j];
   }
+  float l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 20; j++) l1 += fabsf(xw[j]);
+  const float cut_tol = 4e-6f * l1;  // fp32 rounding floor of the 20-term sums
   float* o = har + (size_t)(h_off[b] + f) * ldh;
 #pragma unroll
   for (int k = 0; k <= 10; k++) {
@@ -457,7 +461,9 @@ __global__ void __launch_bounds__(128) stft_kernel(const float* __restrict__ x,
     }
     if (k == 0 || k == 10) im = 0.f;   // real input: DC / Nyquist are exactly real (+0)
     o[k] = hypotf(re, im);
-    o[11 + k] = atan2f(im, re);
+    // branch-cut canonicalisation shared with the oracle: (re<0, |im| inside the rounding floor) -> +pi
+    const bool cut = re < 0.f && fabsf(im) <= cut_tol;
+    o[11 + k] = cut ? 3.14159265358979323846f : atan2f(im, re);
   }
 }
 void launch_stft(const float* x, const long long* s_off, float* har, int ldh, const int* h_off,

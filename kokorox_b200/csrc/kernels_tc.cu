@@ -1,0 +1,370 @@
+// kernels_tc.cu -- Blackwell tensor-core path: bf16 implicit-GEMM Conv1d / ConvTranspose1d-phase /
+// Linear on tcgen05.mma with TMEM accumulators, operands staged by TMA (cp.async.bulk.tensor,
+// 128B swizzle) through an mbarrier ring; plus the HBM-bound "apply" kernels that produce the
+// bf16 operand (AdaIN scale/shift + LeakyReLU/Snake fused, zero halo rows maintained).
+//
+// A conv is a sum of row-shifted GEMMs over the time-major activation matrix:
+//   D[t, co] = sum_tap sum_c A[t + tap*dil - pad, c] * W[co, tap, c]
+// so the A tile of tap `tap` is the same 2-D TMA box shifted by tap*dil - pad rows; rows outside
+// the tensor are zero-filled by TMA and rows between ragged items are zero gap rows (kGapRows).
+#include "kernels.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace kkx {
+
+// ------------------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  if (!fn) throw CudaError("cuTensorMapEncodeTiled entry point not available");
+  return fn;
+}
+
+// bf16 row-major [outer, inner] with row pitch `pitch_elems`; box = [box_outer, 64] elements,
+// 128-byte swizzle (one box row = 128 B = one swizzle span).
+void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
+                    long long pitch_elems, int box_outer) {
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode()((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                            dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[160];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld", (int)r, inner, outer, pitch_elems);
+    throw CudaError(b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers (raw PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SM100 shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(1)<<16 | SBO(1024B>>4)<<32 |
+// version 1 <<46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::f16: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel.  One 128 x BN output tile per CTA.  6 warps:
+//   warp 0  TMA producer (one elected lane)        warp 1  TMEM alloc + MMA issuer (one lane)
+//   warps 2..5  epilogue: tcgen05.ld of the warp's 32-lane TMEM quadrant -> bias / residual /
+//               scale / accumulate -> global
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB,
+                                                      TcConvArgs a) {
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;        // full[S], empty[S], tmem_full
+  const uint32_t tmem_slot = bar_base + (2 * STAGES + 1) * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
+  const uint32_t tfull_bar = bar_base + 2 * STAGES * 8;
+
+  const int b = blockIdx.z;
+  const int mlen = a.m_len[b];
+  const int m0 = blockIdx.x * 128;
+  if (m0 >= mlen) return;  // CTA-uniform
+  const int n0 = blockIdx.y * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.Cpad >> 6;
+  const int num_k = a.ks * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int row0 = a.in_off[b] + m0 - a.pad;
+      for (int it = 0; it < num_k; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+        const uint32_t sa = base + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
+        tma_load_2d(sa + A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      for (int it = 0; it < num_k; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
+          umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+      }
+      umma_commit(tfull_bar);       // accumulator complete
+    }
+  } else {
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int mm = m0 + q * 32 + lane;      // output row of this thread
+    const bool row_ok = mm < mlen;
+    const int orow = mm * a.ors + a.oro;
+    float* op = a.out + ((size_t)(a.out_off[b] + orow) * a.ldo + a.ocol);
+    const float* rp = a.res ? a.res + ((size_t)(a.res_off[b] + (orow >> a.res_shift)) * a.ldr + a.rcol) : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c + j;
+          if (n + 3 < a.Co && a.vec4) {
+            float4 o;
+            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
+            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+            if (a.bias) { const float4 bb = *reinterpret_cast<const float4*>(a.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+            if (rp) { const float4 r = *reinterpret_cast<const float4*>(rp + n); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
+            if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(op + n); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            *reinterpret_cast<float4*>(op + n) = o;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              if (n + e < a.Co) {
+                float o = __uint_as_float(v[j + e]);
+                if (a.bias) o += a.bias[n + e];
+                if (rp) o += rp[n + e];
+                o *= a.oscale;
+                if (a.accumulate) o += op[n + e];
+                op[n + e] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
+  constexpr int smem = STAGES * (128 * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev] = true;
+  }
+  dim3 g((a.max_m + 127) / 128, (a.Co + BN - 1) / BN, a.B);
+  conv_tc_kernel<BN, STAGES><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
+                                                   *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+}
+
+void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
+  if (g_dry_run) return;
+  if (a0.max_m <= 0 || a0.B <= 0) return;
+  TcConvArgs a = a0;
+  a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
+  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
+  if (a.Co > 128) launch_tc<256, 4>(a, st);
+  else if (a.Co > 64) launch_tc<128, 3>(a, st);
+  else launch_tc<64, 4>(a, st);
+  post_launch("conv_tc", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Operand producer: out_bf16[r, c] = act(x[r, c] * scale[b, c] + shift[b, c]) for rows of item b,
+// 0 for halo/gap rows and for pad columns c >= C.  Covers rows [off-gap, off+len+gap_after).
+__global__ void __launch_bounds__(256) apply_bf16_kernel(const float* __restrict__ x, int ldx, int C,
+                                                         const float* scale, const float* shift,
+                                                         int act, float slope, const float* alpha,
+                                                         __nv_bfloat16* out, int Cpad, int rows_total,
+                                                         const int* off, const int* len) {
+  const int b = blockIdx.y;
+  const int L = len[b], o = off[b];
+  const int r_begin = o - kGapRows, r_end = min(rows_total, o + L + kGapRows + 8);
+  const float* sc = scale ? scale + (size_t)b * C : nullptr;
+  const float* sh = shift ? shift + (size_t)b * C : nullptr;
+  const int cp2 = Cpad >> 1;  // column pairs
+  const long long total = (long long)(r_end - r_begin) * cp2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int r = r_begin + (int)(i / cp2);
+    const int c = (int)(i % cp2) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (r >= o && r < o + L) {
+      const float* xp = x + (size_t)r * ldx;
+      if (c < C) {
+        v0 = xp[c];
+        if (sc) v0 = v0 * sc[c] + sh[c];
+        if (act == ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * slope;
+        else if (act == ACT_SNAKE) { const float al = alpha[c]; const float s = sinf(al * v0); v0 = v0 + (1.0f / al) * (s * s); }
+      }
+      if (c + 1 < C) {
+        v1 = xp[c + 1];
+        if (sc) v1 = v1 * sc[c + 1] + sh[c + 1];
+        if (act == ACT_LRELU) v1 = v1 > 0.f ? v1 : v1 * slope;
+        else if (act == ACT_SNAKE) { const float al = alpha[c + 1]; const float s = sinf(al * v1); v1 = v1 + (1.0f / al) * (s * s); }
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)r * Cpad + c) = __floats2bfloat162_rn(v0, v1);
+  }
+}
+
+void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                       float slope, const float* alpha, void* out, int Cpad, int rows_total,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  long long work = (long long)(max_len + 2 * kGapRows + 8) * (Cpad / 2);
+  long long blocks = (work + 256 * 4 - 1) / (256 * 4);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 g((unsigned)blocks, B);
+  apply_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, alpha, (__nv_bfloat16*)out, Cpad,
+                                       rows_total, off, len);
+  post_launch("apply_bf16", st);
+}
+
+// Depthwise ConvTranspose1d(k3,s2,p1,op1) on lrelu(x*scale+shift) -> bf16 operand [2T rows, Cpad]
+__global__ void __launch_bounds__(256) pool_up_bf16_kernel(const float* __restrict__ in, int ldi,
+                                                           const float* scale, const float* shift,
+                                                           float slope, const float* w, const float* bias,
+                                                           int C, __nv_bfloat16* out, int Cpad,
+                                                           int rows_total, const int* in_off,
+                                                           const int* in_len, const int* out_off) {
+  const int b = blockIdx.y;
+  const int T = in_len[b], oo = out_off[b];
+  const int r_begin = oo - kGapRows, r_end = min(rows_total, oo + 2 * T + kGapRows + 8);
+  const float* sc = scale + (size_t)b * C;
+  const float* sh = shift + (size_t)b * C;
+  const long long total = (long long)(r_end - r_begin) * Cpad;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int r = r_begin + (int)(i / Cpad);
+    const int c = (int)(i % Cpad);
+    float v = 0.f;
+    const int j = r - oo;
+    if (j >= 0 && j < 2 * T && c < C) {
+      const int t = j >> 1;
+      const float* x0 = in + (size_t)(in_off[b] + t) * ldi;
+      float a0 = x0[c] * sc[c] + sh[c];
+      a0 = a0 > 0.f ? a0 : a0 * slope;
+      if ((j & 1) == 0) {
+        v = w[c * 3 + 1] * a0 + bias[c];
+      } else {
+        float a1 = 0.f;
+        if (t + 1 < T) { a1 = x0[ldi + c] * sc[c] + sh[c]; a1 = a1 > 0.f ? a1 : a1 * slope; }
+        v = w[c * 3 + 2] * a0 + w[c * 3 + 0] * a1 + bias[c];
+      }
+    }
+    out[(size_t)r * Cpad + c] = __float2bfloat16_rn(v);
+  }
+}
+
+void launch_pool_up_bf16(const float* in, int ldi, const float* scale, const float* shift, float slope,
+                         const float* w, const float* bias, int C, void* out, int Cpad, int rows_total,
+                         const int* in_off, const int* in_len, const int* out_off, int B, int max_len,
+                         cudaStream_t st) {
+  if (g_dry_run) return;
+  long long work = (long long)(2 * max_len + 2 * kGapRows + 8) * Cpad;
+  long long blocks = (work + 256 * 4 - 1) / (256 * 4);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 g((unsigned)blocks, B);
+  pool_up_bf16_kernel<<<g, 256, 0, st>>>(in, ldi, scale, shift, slope, w, bias, C, (__nv_bfloat16*)out, Cpad,
+                                         rows_total, in_off, in_len, out_off);
+  post_launch("pool_up_bf16", st);
+}
+
+}  // namespace kkx

@@ -126,7 +126,39 @@ std::vector<float> convW(const WeightFile& wf, const std::string& n, int Co, int
         o[((size_t)tt * Ci + c) * Co + oc] = t.data[((size_t)oc * Ci + c) * k + tt];
   return o;
 }
+// Conv1d [Co][Ci][k] -> [Co][k][Ci] (tensor-core weight layout before padding / bf16 rounding)
+std::vector<float> convCoKsCi(const WeightFile& wf, const std::string& n, int Co, int Ci, int k) {
+  const HostTensor& t = wf.get(n);
+  expect(t, {Co, Ci, k}, n);
+  std::vector<float> o((size_t)Co * Ci * k);
+  for (int oc = 0; oc < Co; oc++)
+    for (int c = 0; c < Ci; c++)
+      for (int tt = 0; tt < k; tt++)
+        o[((size_t)oc * k + tt) * Ci + c] = t.data[((size_t)oc * Ci + c) * k + tt];
+  return o;
+}
+uint16_t f2bf(float f) {  // round-to-nearest-even fp32 -> bf16
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(r >> 16);
+}
 }  // namespace
+
+TcW Model::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
+  TcW t;
+  t.Ci = Ci; t.Co = Co; t.ks = ks; t.Cpad = (Ci + 63) & ~63;
+  std::vector<uint16_t> h((size_t)Co * ks * t.Cpad, 0);
+  for (int o = 0; o < Co; o++)
+    for (int k = 0; k < ks; k++)
+      for (int c = 0; c < Ci; c++)
+        h[((size_t)o * ks + k) * t.Cpad + c] = f2bf(w[((size_t)o * ks + k) * Ci + c]);
+  KKX_CUDA(cudaMalloc(&t.w, h.size() * 2));
+  owned_.push_back(t.w);
+  KKX_CUDA(cudaMemcpy(t.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  make_tmap_bf16(t.tmap, t.w, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n(Co));
+  return t;
+}
 
 void Model::load_weights(const WeightFile& wf) {
   auto U = [&](const std::string& n) { return up(raw(wf, n)); };
@@ -210,6 +242,11 @@ void Model::load_weights(const WeightFile& wf) {
     b.w2 = CW(p + ".conv2.weight", co, co, 3); b.b2 = U(p + ".conv2.bias");
     if (ci != co) b.w1x1 = CW(p + ".conv1x1.weight", co, ci, 1);
     if (upf) { b.poolw = U(p + ".pool.weight"); b.poolb = U(p + ".pool.bias"); }
+    if (!pro) {  // decoder blocks also get tensor-core weights; the F0/N predictor stays fp32
+      b.t1 = make_tc(convCoKsCi(wf, p + ".conv1.weight", co, ci, 3), co, 3, ci);
+      b.t2 = make_tc(convCoKsCi(wf, p + ".conv2.weight", co, co, 3), co, 3, co);
+      if (ci != co) b.t1x1 = make_tc(convCoKsCi(wf, p + ".conv1x1.weight", co, ci, 1), co, 1, ci);
+    }
     auto& lst = pro ? pro_list : dec_list; int& tot = pro ? npro : ndec;
     b.sty1 = add_sty(lst, tot, p + ".norm1.fc", 2 * ci);
     b.sty2 = add_sty(lst, tot, p + ".norm2.fc", 2 * co);
@@ -254,6 +291,8 @@ void Model::load_weights(const WeightFile& wf) {
       a.w1[j] = CW(p + ".convs1." + sj + ".weight", c, c, k); a.b1[j] = U(p + ".convs1." + sj + ".bias");
       a.w2[j] = CW(p + ".convs2." + sj + ".weight", c, c, k); a.b2[j] = U(p + ".convs2." + sj + ".bias");
       a.a1[j] = U(p + ".alpha1." + sj); a.a2[j] = U(p + ".alpha2." + sj);
+      a.t1[j] = make_tc(convCoKsCi(wf, p + ".convs1." + sj + ".weight", c, c, k), c, k, c);
+      a.t2[j] = make_tc(convCoKsCi(wf, p + ".convs2." + sj + ".weight", c, c, k), c, k, c);
       a.s1[j] = add_sty(dec_list, ndec, p + ".adain1." + sj + ".fc", 2 * c);
       a.s2[j] = add_sty(dec_list, ndec, p + ".adain2." + sj + ".fc", 2 * c);
     }
@@ -264,10 +303,16 @@ void Model::load_weights(const WeightFile& wf) {
   const int rk[3] = {3, 7, 11};
   for (int i = 0; i < 2; i++)
     for (int j = 0; j < 3; j++) W.res[i * 3 + j] = ARB(G + "resblocks." + std::to_string(i * 3 + j), i == 0 ? 256 : 128, rk[j]);
-  auto UPS = [&](const std::string& n, int Ci, int Co, int k, int s, std::vector<float*>& out) {
+  auto UPS = [&](const std::string& n, int Ci, int Co, int k, int s, std::vector<float*>& out, std::vector<TcW>& tout) {
     const HostTensor& t = wf.get(n);
     expect(t, {Ci, Co, k}, n);
     for (int r = 0; r < s; r++) {
+      std::vector<float> tw((size_t)Co * 2 * Ci);
+      for (int o = 0; o < Co; o++)
+        for (int j = 0; j < 2; j++)
+          for (int c = 0; c < Ci; c++)
+            tw[((size_t)o * 2 + j) * Ci + c] = t.data[((size_t)c * Co + o) * k + r + j * s];
+      tout.push_back(make_tc(tw, Co, 2, Ci));
       std::vector<float> ph((size_t)2 * Ci * Co);
       for (int j = 0; j < 2; j++)
         for (int c = 0; c < Ci; c++)
@@ -276,8 +321,8 @@ void Model::load_weights(const WeightFile& wf) {
       out.push_back(up(ph));
     }
   };
-  UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0); W.ups0_b = U(G + "ups.0.bias");
-  UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1); W.ups1_b = U(G + "ups.1.bias");
+  UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0, W.tups0); W.ups0_b = U(G + "ups.0.bias");
+  UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1, W.tups1); W.ups1_b = U(G + "ups.1.bias");
   W.post_w = CW(G + "conv_post.weight", 22, 128, 7); W.post_b = U(G + "conv_post.bias");
 
   // ---- build the two style FC tables: W^T [128][n], bias [n]

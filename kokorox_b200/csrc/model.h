@@ -28,17 +28,25 @@ class WeightFile {
   std::map<std::string, HostTensor> t_;
 };
 
+// bf16 weight [Co][ks][Cpad] + its TMA descriptor (tensor-core path)
+struct TcW {
+  void* w = nullptr;
+  alignas(64) unsigned char tmap[128];
+  int Cpad = 0, Ci = 0, Co = 0, ks = 0;
+};
 struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; };
 struct AdaBlkW {  // AdainResBlk1d
   int ci = 0, co = 0; bool up = false;
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *w1x1 = nullptr;
   float *poolw = nullptr, *poolb = nullptr;
   int sty1 = 0, sty2 = 0;  // offsets into the per-item style-parameter table
+  TcW t1, t2, t1x1;
 };
 struct ArbW {  // AdaINResBlock1
   int c = 0, k = 0;
   float *w1[3], *b1[3], *w2[3], *b2[3], *a1[3], *a2[3];
   int s1[3], s2[3];
+  TcW t1[3], t2[3];
 };
 
 struct Weights {
@@ -62,6 +70,7 @@ struct Weights {
   float *lin_w, *lin_b, *nc0_w, *nc0_b, *nc1_w, *nc1_b;
   ArbW nres[2], res[6];
   std::vector<float*> ups0, ups1;  // per-phase [2][Ci][Co]
+  std::vector<TcW> tups0, tups1;   // per-phase bf16 [Co][2][Ci]
   float *ups0_b, *ups1_b, *post_w, *post_b;
   // style FC tables (all AdaIN / AdaLN fcs of one style half concatenated)
   float *sty_pro_w, *sty_pro_b, *sty_dec_w, *sty_dec_b;
@@ -116,6 +125,11 @@ class Model {
   };
   void load_weights(const WeightFile& wf);
   float* up(const std::vector<float>& v);
+  TcW make_tc(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
+  void tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, int dil, int pad, const Level& Lin,
+               const Level& Lm, const float* bias, float* out, int ldo, int ocol, const Level& Lout, int ors,
+               int oro, const float* res, int ldr, const Level* Lres, int res_shift, float oscale,
+               bool accumulate);
   void token_phase(Run& r);
   void frame_phase(Run& r, int b0, int b1, bool dry);
   void adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ldx, const Level& Lin,

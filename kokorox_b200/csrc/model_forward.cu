@@ -19,6 +19,24 @@ ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float*
 }
 }  // namespace
 
+void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, int dil, int pad, const Level& Lin,
+                    const Level& Lm, const float* bias, float* out, int ldo, int ocol, const Level& Lout, int ors,
+                    int oro, const float* res, int ldr, const Level* Lres, int res_shift, float oscale,
+                    bool accumulate) {
+  (void)A;
+  alignas(64) unsigned char tmA[128];
+  if (g_dry_run) return;
+  make_tmap_bf16(tmA, abuf, w.Cpad, rows_total, w.Cpad, 128);
+  TcConvArgs a;
+  a.tmA = tmA; a.tmB = w.tmap;
+  a.Cpad = w.Cpad; a.Ci = w.Ci; a.Co = w.Co; a.ks = w.ks; a.dil = dil; a.pad = pad;
+  a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
+  a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lout.d_off; a.ors = ors; a.oro = oro;
+  a.res = res; a.ldr = ldr; a.rcol = 0; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift;
+  a.oscale = oscale; a.accumulate = accumulate ? 1 : 0;
+  launch_conv_tc(a, stream_);
+}
+
 // ------------------------------------------------------------------------------------------
 // Token phase: everything at phoneme-token rate, for the whole batch.
 void Model::token_phase(Run& r) {
@@ -169,6 +187,35 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
 
   launch_colstats(x, ldx, w.ci, part, Lin.d_off, Lin.d_len, B, Lin.max_len, st);
   launch_adain_coef(part, w.ci, Lin.max_len, Lin.d_len, sty, sld, w.sty1, 1e-5f, sc1, sh1, B, st);
+  if (opt.precision == 1 && w.t1.w) {
+    // tensor-core path: bf16 operands produced by the apply kernels, tcgen05 convs, fp32 results
+    const int cpi = w.t1.Cpad, cpo = w.t2.Cpad;
+    void* a1 = A.alloc_bytes((size_t)Lout.rows * cpi * 2);
+    if (w.up)
+      launch_pool_up_bf16(x, ldx, sc1, sh1, 0.2f, w.poolw, w.poolb, w.ci, a1, cpi, Lout.rows, Lin.d_off,
+                          Lin.d_len, Lout.d_off, B, Lin.max_len, st);
+    else
+      launch_apply_bf16(x, ldx, w.ci, sc1, sh1, ACT_LRELU, 0.2f, nullptr, a1, cpi, Lin.rows, Lin.d_off,
+                        Lin.d_len, B, Lin.max_len, st);
+    tc_conv(A, a1, Lout.rows, w.t1, 1, 1, Lout, Lout, w.b1, t, w.co, 0, Lout, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+    launch_colstats(t, w.co, w.co, part, Lout.d_off, Lout.d_len, B, Lout.max_len, st);
+    launch_adain_coef(part, w.co, Lout.max_len, Lout.d_len, sty, sld, w.sty2, 1e-5f, sc2, sh2, B, st);
+    void* a2 = A.alloc_bytes((size_t)Lout.rows * cpo * 2);
+    launch_apply_bf16(t, w.co, w.co, sc2, sh2, ACT_LRELU, 0.2f, nullptr, a2, cpo, Lout.rows, Lout.d_off,
+                      Lout.d_len, B, Lout.max_len, st);
+    const float* scp = x; int ldsc = ldx;
+    if (w.w1x1) {
+      void* a3 = A.alloc_bytes((size_t)Lin.rows * cpi * 2);
+      float* s = A.alloc<float>((size_t)Lin.rows * w.co);
+      launch_apply_bf16(x, ldx, w.ci, nullptr, nullptr, ACT_NONE, 0.f, nullptr, a3, cpi, Lin.rows, Lin.d_off,
+                        Lin.d_len, B, Lin.max_len, st);
+      tc_conv(A, a3, Lin.rows, w.t1x1, 1, 0, Lin, Lin, nullptr, s, w.co, 0, Lin, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+      scp = s; ldsc = w.co;
+    }
+    tc_conv(A, a2, Lout.rows, w.t2, 1, 1, Lout, Lout, w.b2, out, ldo, ocol, Lout, 1, 0, scp, ldsc, &Lin,
+            w.up ? 1 : 0, 0.70710678118654752440f, false);
+    return;
+  }
   if (w.up) {
     float* p = A.alloc<float>((size_t)Lout.rows * w.ci);
     launch_pool_up(x, ldx, sc1, sh1, 0.2f, w.poolw, w.poolb, w.ci, p, w.ci, Lin.d_off, Lin.d_len,
@@ -212,9 +259,25 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
   float* sh = A.alloc<float>((size_t)B * C);
   const int dil[3] = {1, 3, 5};
   const float* cur = x;
+  const bool tc = opt.precision == 1;
+  void* abuf = tc ? A.alloc_bytes((size_t)L.rows * w.t1[0].Cpad * 2) : nullptr;
   for (int j = 0; j < 3; j++) {
     launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
     launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
+    if (tc) {
+      const int cp = w.t1[j].Cpad;
+      launch_apply_bf16(cur, C, C, sc, sh, ACT_SNAKE, 0.f, w.a1[j], abuf, cp, L.rows, L.d_off, L.d_len, B, L.max_len, st);
+      tc_conv(A, abuf, L.rows, w.t1[j], dil[j], dil[j] * (k - 1) / 2, L, L, w.b1[j], t1, C, 0, L, 1, 0, nullptr, 0,
+              nullptr, 0, 1.f, false);
+      launch_colstats(t1, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+      launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s2[j], 1e-5f, sc, sh, B, st);
+      launch_apply_bf16(t1, C, C, sc, sh, ACT_SNAKE, 0.f, w.a2[j], abuf, cp, L.rows, L.d_off, L.d_len, B, L.max_len, st);
+      float* dst = (j == 2) ? out : xw;
+      tc_conv(A, abuf, L.rows, w.t2[j], 1, (k - 1) / 2, L, L, w.b2[j], dst, C, 0, L, 1, 0, cur, C, &L, 0,
+              j == 2 ? oscale : 1.f, j == 2 && accumulate);
+      cur = dst;
+      continue;
+    }
     ConvArgs c1 = gemm_args(L, cur, C, C, w.w1[j], w.b1[j], C, t1, C, 0);
     c1.ks = k; c1.dil = dil[j]; c1.pad = dil[j] * (k - 1) / 2;
     c1.pscale = sc; c1.pshift = sh; c1.pld = C; c1.pact = ACT_SNAKE; c1.palpha = w.a1[j];
@@ -385,8 +448,19 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   }
   arb(r, A, W.nres[0], xs0, G20, sty_dec, W.sty_dec_n, w0, t0, xs0, 1.f, false);
   capture("gen.x_source.0", xs0, 256, 0, 256, G20, b0);
+  void* ybf = nullptr;
+  if (opt.precision == 1) {
+    ybf = A.alloc_bytes((size_t)FR2.rows * 512 * 2);
+    launch_apply_bf16(y, 512, 512, nullptr, nullptr, ACT_LRELU, 0.1f, nullptr, ybf, 512, FR2.rows, FR2.d_off,
+                      FR2.d_len, B, FR2.max_len, st);
+  }
   for (int ph = 0; ph < 10; ph++) {  // ConvTranspose1d(512,256,k20,s10,p5) as 10 two-tap phase convs
     const int q0 = ph < 5 ? 1 : 0;
+    if (opt.precision == 1) {
+      tc_conv(A, ybf, FR2.rows, W.tups0[ph], -1, -q0, FR2, FR2, W.ups0_b, x0, 256, 0, G20, 10, q0 * 10 + ph - 5,
+              nullptr, 0, nullptr, 0, 1.f, false);
+      continue;
+    }
     ConvArgs c = gemm_args(FR2, y, 512, 512, W.ups0[ph], W.ups0_b, 256, x0, 256, 0);
     c.out_off = G20.d_off;
     c.ks = 2; c.dil = -1; c.pad = -q0; c.stride = 1;
@@ -409,8 +483,19 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st);
   arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
   capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
+  void* abf = nullptr;
+  if (opt.precision == 1) {
+    abf = A.alloc_bytes((size_t)G20.rows * 256 * 2);
+    launch_apply_bf16(acc0, 256, 256, nullptr, nullptr, ACT_LRELU, 0.1f, nullptr, abf, 256, G20.rows, G20.d_off,
+                      G20.d_len, B, G20.max_len, st);
+  }
   for (int ph = 0; ph < 6; ph++) {  // ConvTranspose1d(256,128,k12,s6,p3) + ReflectionPad1d((1,0))
     const int q0 = ph < 3 ? 1 : 0;
+    if (opt.precision == 1) {
+      tc_conv(A, abf, G20.rows, W.tups1[ph], -1, -q0, G20, G20, W.ups1_b, x1, 128, 0, G120, 6, q0 * 6 + ph - 3 + 1,
+              nullptr, 0, nullptr, 0, 1.f, false);
+      continue;
+    }
     ConvArgs c = gemm_args(G20, acc0, 256, 256, W.ups1[ph], W.ups1_b, 128, x1, 128, 0);
     c.out_off = G120.d_off;
     c.ks = 2; c.dil = -1; c.pad = -q0; c.stride = 1;

@@ -1,6 +1,7 @@
 // testapi.cu -- op-level test hooks (include/kkx_test.h).  Parity harness only.
 #include "../../include/kkx_test.h"
 #include "kernels.h"
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,50 @@ KKX_API int kkx_test_conv(int device, const float* in, int rows_in, int ldi, int
     a.res = res ? dres.as<float>() : nullptr; a.ldr = Co; a.rcol = 0; a.res_off = dm.as<int>() + 3;
     a.res_shift = res_shift; a.oscale = oscale; a.accumulate = accumulate;
     launch_conv_f32(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)out_rows * Co * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                             int Co, int ks, int dil, int pad, const float* pscale, const float* pshift,
+                             int pact, float pslope, const float* palpha, int m_len, int ors, int oro,
+                             int out_rows, const float* res, int res_rows, int res_shift, float oscale,
+                             int accumulate, float* out) {
+  return run(device, [&] {
+    const int Cpad = (Ci + 63) & ~63;
+    const int off = kGapRows, rows_total = (off + L + kGapRows + 7) & ~7;
+    std::vector<uint16_t> hw((size_t)Co * ks * Cpad, 0);
+    for (int o = 0; o < Co; o++)
+      for (int k = 0; k < ks; k++)
+        for (int c = 0; c < Ci; c++) {
+          float f = w[((size_t)o * ks + k) * Ci + c];
+          uint32_t u; memcpy(&u, &f, 4);
+          hw[((size_t)o * ks + k) * Cpad + c] = (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+        }
+    std::vector<float> xin((size_t)rows_total * Ci, 0.f);
+    memcpy(xin.data() + (size_t)off * Ci, x, (size_t)L * Ci * 4);
+    DevBuf dx(xin.data(), xin.size() * 4), dw(hw.data(), hw.size() * 2), db(bias, bias ? Co * 4 : 0);
+    DevBuf dps(pscale, pscale ? Ci * 4 : 0), dph(pshift, pshift ? Ci * 4 : 0), dal(palpha, palpha ? Ci * 4 : 0);
+    DevBuf dres(res, res ? (size_t)res_rows * Co * 4 : 0), dout(out, (size_t)out_rows * Co * 4);
+    DevBuf dab(nullptr, (size_t)rows_total * Cpad * 2);
+    KKX_CUDA(cudaMemset(dab.p, 0xFF, (size_t)rows_total * Cpad * 2));  // NaN-fill: the producer must zero halos
+    int meta[5] = {off, L, m_len, 0, 0};
+    DevBuf dm(meta, sizeof meta);
+    launch_apply_bf16(dx.as<float>(), Ci, Ci, pscale ? dps.as<float>() : nullptr, pshift ? dph.as<float>() : nullptr,
+                      pact, pslope, palpha ? dal.as<float>() : nullptr, dab.p, Cpad, rows_total, dm.as<int>(),
+                      dm.as<int>() + 1, 1, L, 0);
+    alignas(64) unsigned char tmA[128], tmB[128];
+    make_tmap_bf16(tmA, dab.p, Cpad, rows_total, Cpad, 128);
+    make_tmap_bf16(tmB, dw.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, tc_box_n(Co));
+    TcConvArgs a;
+    a.tmA = tmA; a.tmB = tmB; a.Cpad = Cpad; a.Ci = Ci; a.Co = Co; a.ks = ks; a.dil = dil; a.pad = pad;
+    a.in_off = dm.as<int>(); a.m_len = dm.as<int>() + 2; a.max_m = m_len; a.B = 1; a.sum_m = m_len;
+    a.bias = bias ? db.as<float>() : nullptr;
+    a.out = dout.as<float>(); a.ldo = Co; a.ocol = 0; a.out_off = dm.as<int>() + 3; a.ors = ors; a.oro = oro;
+    a.res = res ? dres.as<float>() : nullptr; a.ldr = Co; a.rcol = 0; a.res_off = dm.as<int>() + 4;
+    a.res_shift = res_shift; a.oscale = oscale; a.accumulate = accumulate;
+    launch_conv_tc(a, 0);
     KKX_CUDA(cudaDeviceSynchronize());
     KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)out_rows * Co * 4, cudaMemcpyDeviceToHost));
   });

@@ -210,10 +210,22 @@ class KokoroOracle:
         return har[0, :, 0]
 
     def stft(self, x: torch.Tensor):
-        """A.9 STFT: n_fft 20, hop 5, periodic hann, center.  x [S] -> mag, phase [11, S/5+1]."""
+        """A.9 STFT: n_fft 20, hop 5, periodic hann, center.  x [S] -> mag, phase [11, S/5+1].
+
+        Branch-cut canonicalisation: angle() is discontinuous at (re<0, im=0).  Frame 0 is
+        even-symmetric about its centre (reflect padding about sample 0 + symmetric window), so every
+        bin has im == 0 up to rounding and upstream's +pi / -pi there is decided by FFT rounding
+        noise.  Both this oracle and the CUDA kernel map (re<0, |im| <= 4e-6 * sum_j |x_j w_j|), i.e.
+        an imaginary part inside the fp32 rounding floor of the 20-term sum, to +pi;
+        e^{i pi} = e^{-i pi}, so both choices denote the same spectrum."""
         X = torch.stft(x.unsqueeze(0), N_FFT, HOP, N_FFT, window=self.window, center=True,
                        pad_mode=self.stft_pad_mode, return_complex=True)[0]
-        return torch.abs(X), torch.angle(X)
+        xp = F.pad(x.view(1, 1, -1), (N_FFT // 2, N_FFT // 2), mode=self.stft_pad_mode)[0, 0]
+        l1 = (xp.unfold(0, N_FFT, HOP) * self.window).abs().sum(dim=1)          # [frames]
+        ph = torch.angle(X)
+        cut = (X.real < 0) & (X.imag.abs() <= 4e-6 * l1.unsqueeze(0))
+        ph = torch.where(cut, torch.full_like(ph, math.pi), ph)
+        return torch.abs(X), ph
 
     def istft(self, mag: torch.Tensor, ph: torch.Tensor) -> torch.Tensor:
         """A.9 head: torch.istft semantics (window OLA / envelope, trim n_fft/2)."""

@@ -147,3 +147,65 @@ def test_instance_norm_adain_coefficients(lib, L, Cc):
         + torch.from_numpy(gb[Cc:])[None, :, None]
     got = x * sc + sh
     np.testing.assert_allclose(got, ref[0].T.numpy(), atol=3e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------- tensor-core path
+def bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32)
+
+
+def run_conv_tc(lib, x, w_co_ks_ci, bias, dil, pad, m_len, out_rows, ors=1, oro=0, pscale=None, pshift=None, pact=0,
+                pslope=0.0, palpha=None, res=None, res_shift=0, oscale=1.0, accumulate=0, out_init=None):
+    L, Ci = x.shape
+    Co, ks, _ = w_co_ks_ci.shape
+    out = np.zeros((out_rows, Co), np.float32) if out_init is None else out_init.copy()
+    rc = lib.kkx_test_conv_tc(0, fp(x), L, Ci, fp(w_co_ks_ci), fp(bias), Co, ks, dil, pad, fp(pscale), fp(pshift), pact,
+                              C.c_float(pslope), fp(palpha), m_len, ors, oro, out_rows, fp(res),
+                              0 if res is None else res.shape[0], res_shift, C.c_float(oscale), accumulate, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    return out
+
+
+@pytest.mark.parametrize("L,Ci,Co,k,dil", [(300, 128, 128, 3, 1), (1000, 256, 256, 7, 3), (513, 128, 128, 11, 5),
+                                           (130, 514, 1024, 3, 1), (77, 1090, 512, 3, 1), (260, 1090, 1024, 1, 1),
+                                           (129, 64, 64, 3, 1)])
+def test_tc_conv_matches_torch_on_bf16_operands(lib, L, Ci, Co, k, dil):
+    x, w, b = rnd(L, Ci, seed=1), rnd(Co, Ci, k, seed=2, scale=1 / np.sqrt(Ci * k)), rnd(Co, seed=3)
+    pad = dil * (k - 1) // 2
+    ref = F.conv1d(bf16_round(x).T[None], bf16_round(w), torch.from_numpy(b), padding=pad, dilation=dil)[0].T.numpy()
+    got = run_conv_tc(lib, x, np.ascontiguousarray(w.transpose(0, 2, 1)), b, dil, pad, L, L)
+    np.testing.assert_allclose(got, ref, atol=3e-4, rtol=1e-4)
+    # and against the fp32 conv: the stated bf16-operand tolerance
+    ref32 = F.conv1d(torch.from_numpy(x.T)[None], torch.from_numpy(w), torch.from_numpy(b), padding=pad, dilation=dil)[0].T.numpy()
+    assert np.sqrt(((got - ref32) ** 2).sum() / (ref32 ** 2).sum()) < 6e-3
+
+
+@pytest.mark.parametrize("Ci,Co,k,s", [(512, 256, 20, 10), (256, 128, 12, 6)])
+def test_tc_conv_transpose_phases(lib, Ci, Co, k, s):
+    L, p = 141, (k - s) // 2
+    x, w, b = rnd(L, Ci, seed=7), rnd(Ci, Co, k, seed=8, scale=0.05), rnd(Co, seed=9)
+    xin = bf16_round(F.leaky_relu(torch.from_numpy(x), 0.1).numpy()).T[None]
+    ref = F.conv_transpose1d(xin, bf16_round(w), torch.from_numpy(b), stride=s, padding=p)[0].T.numpy()
+    out = np.full((L * s, Co), np.nan, np.float32)
+    for r in range(s):
+        q0 = 1 if r < p else 0
+        ph = np.ascontiguousarray(np.stack([w[:, :, r], w[:, :, r + s]], axis=0).transpose(2, 0, 1))  # [Co][2][Ci]
+        out = run_conv_tc(lib, x, ph, b, -1, -q0, L, L * s, ors=s, oro=q0 * s + r - p, pact=1, pslope=0.1, out_init=out)
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(out, ref, atol=3e-4, rtol=1e-4)
+
+
+def test_tc_conv_fused_prologue_epilogue(lib):
+    L, Cc, k = 700, 128, 7
+    x, w, b = rnd(L, Cc, seed=10), rnd(Cc, Cc, k, seed=11, scale=0.04), rnd(Cc, seed=12)
+    sc, sh = (1 + 0.3 * rnd(Cc, seed=13)).astype(np.float32), (0.2 * rnd(Cc, seed=14)).astype(np.float32)
+    alpha = np.clip(1 + 0.3 * rnd(Cc, seed=15), 0.3, 2).astype(np.float32)
+    res, init = rnd(L, Cc, seed=16), rnd(L, Cc, seed=17)
+    xt = torch.from_numpy(x) * torch.from_numpy(sc) + torch.from_numpy(sh)
+    a = torch.from_numpy(alpha)
+    xt = xt + (1 / a) * torch.sin(a * xt) ** 2
+    y = F.conv1d(bf16_round(xt.numpy()).T[None], bf16_round(w), torch.from_numpy(b), padding=3)[0].T
+    ref = (torch.from_numpy(init) + (1 / 3) * (y + torch.from_numpy(res))).numpy()
+    got = run_conv_tc(lib, x, np.ascontiguousarray(w.transpose(0, 2, 1)), b, 1, 3, L, L, pscale=sc, pshift=sh, pact=2,
+                      palpha=alpha, res=res, oscale=1 / 3, accumulate=1, out_init=init)
+    np.testing.assert_allclose(got, ref, atol=2e-3, rtol=1e-3)
