@@ -248,14 +248,12 @@ def main():
         lat = lat[2:]
 
     # ---------------- reductions over ranks (max time, summed work)
+    from kokorox_b200.sharding import reduce_step
     step_s = dev_s / args.steps
-    vals = torch.tensor([step_s, wall / args.steps, e2e_wall / args.steps], device="cuda", dtype=torch.float64)
-    work = torch.tensor([audio_s_step, e2e_audio / args.steps, float(frames), float(sum_n)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    step_s, wall_step_s, e2e_step_s = vals.tolist()
-    audio_all, e2e_audio_all, frames_all, tokens_all = work.tolist()
+    dev = torch.device("cuda", local_rank)
+    step_s, (audio_all, frames_all, tokens_all) = reduce_step(step_s, [audio_s_step, float(frames), float(sum_n)], dev)
+    wall_step_s, _ = reduce_step(wall / args.steps, [0.0], dev)
+    e2e_step_s, (e2e_audio_all,) = reduce_step(e2e_wall / args.steps, [e2e_audio / args.steps], dev)
 
     if rank == 0:
         peaks, peaks_src = load_peaks()

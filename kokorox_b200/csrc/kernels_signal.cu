@@ -7,27 +7,57 @@ namespace kkx {
 
 // ------------------------------------------------------------------------------------------
 // InstanceNorm statistics: per (item, chunk of kStatRows rows) column sums and sums of squares.
-// part layout: [B][nchunk][2][C] with nchunk = ceil(max_len / kStatRows)
+// part layout: [B][nchunk][2][C] with nchunk = ceil(max_len / kStatRows).
+// Block = 256 threads = XT column-quads x YT row slices (float4 loads when C % 4 == 0); the row
+// slices are combined through shared memory in a fixed order (deterministic).
+template <int VEC>
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, int ldx, int C,
                                                        float* __restrict__ part, int nchunk,
                                                        const int* off, const int* len) {
+  __shared__ float red[2][256 * VEC];
   const int b = blockIdx.y, ch = blockIdx.x;
   const int L = len[b];
   const int r0 = ch * kStatRows;
   if (r0 >= L) return;
   const int r1 = min(L, r0 + kStatRows);
-  const float* xp = x + (size_t)(off[b] + r0) * ldx;
+  const int CV = (C + VEC - 1) / VEC;           // column groups
+  const int XT = CV < 256 ? CV : 256;           // threads along columns (CV is 32 / 64 / 128+ here)
+  const int YT = 256 / XT;                      // row slices
+  const int tx = threadIdx.x % XT, ty = threadIdx.x / XT;
   float* pp = part + ((size_t)b * nchunk + ch) * 2 * C;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f, q = 0.f;
-    const float* p = xp + c;
-    for (int r = r0; r < r1; r++, p += ldx) {
-      const float v = *p;
-      s += v;
-      q = fmaf(v, v, q);
+  for (int cg0 = 0; cg0 < CV; cg0 += XT) {
+    const int cg = cg0 + tx;
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) { s[v] = 0.f; q[v] = 0.f; }
+    if (cg < CV && ty < YT) {
+      const float* p = x + (size_t)(off[b] + r0 + ty) * ldx + cg * VEC;
+      for (int r = r0 + ty; r < r1; r += YT, p += (size_t)YT * ldx) {
+        if (VEC == 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(p);
+          s[0] += v4.x; q[0] = fmaf(v4.x, v4.x, q[0]);
+          s[1 % VEC] += v4.y; q[1 % VEC] = fmaf(v4.y, v4.y, q[1 % VEC]);
+          s[2 % VEC] += v4.z; q[2 % VEC] = fmaf(v4.z, v4.z, q[2 % VEC]);
+          s[3 % VEC] += v4.w; q[3 % VEC] = fmaf(v4.w, v4.w, q[3 % VEC]);
+        } else {
+          const float v1 = *p;
+          s[0] += v1; q[0] = fmaf(v1, v1, q[0]);
+        }
+      }
     }
-    pp[c] = s;
-    pp[C + c] = q;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VEC; v++) { red[0][threadIdx.x * VEC + v] = s[v]; red[1][threadIdx.x * VEC + v] = q[v]; }
+    __syncthreads();
+    if (ty == 0 && cg < CV) {
+#pragma unroll
+      for (int v = 0; v < VEC; v++) {
+        float ss = 0.f, qq = 0.f;
+        for (int y = 0; y < YT; y++) { ss += red[0][(y * XT + tx) * VEC + v]; qq += red[1][(y * XT + tx) * VEC + v]; }
+        const int c = cg * VEC + v;
+        if (c < C) { pp[c] = ss; pp[C + c] = qq; }
+      }
+    }
   }
 }
 void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
@@ -35,43 +65,58 @@ void launch_colstats(const float* x, int ldx, int C, float* part, const int* off
   if (g_dry_run) return;
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
   dim3 g(nchunk, B);
-  colstats_kernel<<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
+  if ((C % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0))
+    colstats_kernel<4><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
+  else
+    colstats_kernel<1><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
   post_launch("colstats", st);
 }
 
-__global__ void __launch_bounds__(128) adain_coef_kernel(const float* __restrict__ part, int C,
+// Combine the chunk partials (fp64, fixed order) -> AdaIN coefficients.  Block = 32 channels x 8
+// chunk slices.
+__global__ void __launch_bounds__(256) adain_coef_kernel(const float* __restrict__ part, int C,
                                                          int nchunk, const int* len,
                                                          const float* __restrict__ sty, int sld,
                                                          int soff, float eps, float* scale,
                                                          float* shift) {
+  __shared__ double rs[8][32], rq[8][32];
   const int b = blockIdx.y;
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   const int L = len[b];
   const int nc = (L + kStatRows - 1) / kStatRows;
   double S = 0.0, Q = 0.0;
-  const float* pp = part + (size_t)b * nchunk * 2 * C;
-  for (int k = 0; k < nc; k++) {
-    S += (double)pp[(size_t)k * 2 * C + c];
-    Q += (double)pp[(size_t)k * 2 * C + C + c];
+  if (c < C) {
+    const float* pp = part + (size_t)b * nchunk * 2 * C + c;
+    for (int k = ty; k < nc; k += 8) {
+      S += (double)pp[(size_t)k * 2 * C];
+      Q += (double)pp[(size_t)k * 2 * C + C];
+    }
   }
-  const double mean = S / (double)L;
-  double var = Q / (double)L - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = 1.0f / sqrtf((float)var + eps);
-  const float gamma = sty[(size_t)b * sld + soff + c];
-  const float beta = sty[(size_t)b * sld + soff + C + c];
-  const float sc = rstd * (1.0f + gamma);
-  scale[(size_t)b * C + c] = sc;
-  shift[(size_t)b * C + c] = beta - (float)mean * sc;
+  rs[ty][tx] = S; rq[ty][tx] = Q;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    S = 0.0; Q = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) { S += rs[y][tx]; Q += rq[y][tx]; }
+    const double mean = S / (double)L;
+    double var = Q / (double)L - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = 1.0f / sqrtf((float)var + eps);
+    const float gamma = sty[(size_t)b * sld + soff + c];
+    const float beta = sty[(size_t)b * sld + soff + C + c];
+    const float sc = rstd * (1.0f + gamma);
+    scale[(size_t)b * C + c] = sc;
+    shift[(size_t)b * C + c] = beta - (float)mean * sc;
+  }
 }
 void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
                        int sld, int soff, float eps, float* scale, float* shift, int B,
                        cudaStream_t st) {
   if (g_dry_run) return;
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
-  dim3 g((C + 127) / 128, B);
-  adain_coef_kernel<<<g, 128, 0, st>>>(part, C, nchunk, len, sty, sld, soff, eps, scale, shift);
+  dim3 g((C + 31) / 32, B);
+  adain_coef_kernel<<<g, 256, 0, st>>>(part, C, nchunk, len, sty, sld, soff, eps, scale, shift);
   post_launch("adain_coef", st);
 }
 
@@ -363,9 +408,11 @@ __global__ void __launch_bounds__(256) sine_source_kernel(
     for (int h = 0; h < 9; h++) nz[h] = noise[n * 9 + h];
   } else {
     unsigned r[12];
-    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
-    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 1u, (unsigned)seed, (unsigned)(seed >> 32), r + 4);
-    philox4x32_10((unsigned)n, (unsigned)(n >> 32), (unsigned)b, 2u, (unsigned)seed, (unsigned)(seed >> 32), r + 8);
+    // keyed by (seed, sample index) only, NOT by the batch slot: an utterance gets the same noise
+    // whether it runs alone or inside a batch (kkx_infer_batch == per-item kkx_infer)
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), 0u, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), 0u, 1u, (unsigned)seed, (unsigned)(seed >> 32), r + 4);
+    philox4x32_10((unsigned)n, (unsigned)(n >> 32), 0u, 2u, (unsigned)seed, (unsigned)(seed >> 32), r + 8);
 #pragma unroll
     for (int h = 0; h < 5; h++) {
       const float u1 = u01(r[2 * h]), u2 = u01(r[2 * h + 1]);

@@ -188,41 +188,58 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       umma_commit(tfull_bar);       // accumulator complete
     }
   } else {
+    // ---- epilogue (4 warps).  All MMAs have completed when tfull_bar flips, so the pipeline
+    // stages are idle and stage memory is reused as a transpose buffer: each thread drops its
+    // 32-column strip of one accumulator row into padded smem (conflict-free), then the 128
+    // threads write whole 128-byte row segments to global (8 lanes per row -> full-line stores,
+    // coalesced residual / accumulate reads).
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int mm = m0 + q * 32 + lane;      // output row of this thread
-    const bool row_ok = mm < mlen;
-    const int orow = mm * a.ors + a.oro;
-    float* op = a.out + ((size_t)(a.out_off[b] + orow) * a.ldo + a.ocol);
-    const float* rp = a.res ? a.res + ((size_t)(a.res_off[b] + (orow >> a.res_shift)) * a.ldr + a.rcol) : nullptr;
+    const int et = q * 32 + lane;           // accumulator row held by this thread
+    constexpr int PITCH = 36;               // floats per staged row (32 + 4 pad)
+    float* stage_f = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
+    const int out_off = a.out_off[b];
+    const int res_off = a.res ? a.res_off[b] : 0;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (row_ok) {
+      float* buf = stage_f + ((c >> 5) & 1) * (128 * PITCH);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c + j;
-          if (n + 3 < a.Co && a.vec4) {
-            float4 o;
-            o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]);
-            o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-            if (a.bias) { const float4 bb = *reinterpret_cast<const float4*>(a.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-            if (rp) { const float4 r = *reinterpret_cast<const float4*>(rp + n); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-            o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
-            if (a.accumulate) { const float4 p = *reinterpret_cast<const float4*>(op + n); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-            *reinterpret_cast<float4*>(op + n) = o;
-          } else {
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(buf + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (n0 + c < a.Co) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-              if (n + e < a.Co) {
-                float o = __uint_as_float(v[j + e]);
-                if (a.bias) o += a.bias[n + e];
-                if (rp) o += rp[n + e];
-                o *= a.oscale;
-                if (a.accumulate) o += op[n + e];
-                op[n + e] = o;
+        for (int i = 0; i < 8; i++) {
+          const int idx = i * 128 + (threadIdx.x - 64);
+          const int row = idx >> 3, c4 = (idx & 7) << 2;
+          const int mm = m0 + row;
+          const int n = n0 + c + c4;
+          if (mm < mlen && n < a.Co) {
+            float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
+            const int orow = mm * a.ors + a.oro;
+            float* op = a.out + ((size_t)(out_off + orow) * a.ldo + a.ocol + n);
+            const float* rp = a.res ? a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n) : nullptr;
+            if (a.vec4 && n + 3 < a.Co) {
+              if (a.bias) { const float4 bb = *reinterpret_cast<const float4*>(a.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+              if (rp) { const float4 r = *reinterpret_cast<const float4*>(rp); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+              o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
+              if (a.accumulate) { const float4 pv = *reinterpret_cast<const float4*>(op); o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
+              *reinterpret_cast<float4*>(op) = o;
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                if (n + e < a.Co) {
+                  float t = ov[e];
+                  if (a.bias) t += a.bias[n + e];
+                  if (rp) t += rp[e];
+                  t *= a.oscale;
+                  if (a.accumulate) t += op[e];
+                  op[e] = t;
+                }
               }
             }
           }
@@ -259,7 +276,9 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   TcConvArgs a = a0;
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
-  if (a.Co > 128) launch_tc<256, 4>(a, st);
+  // smem per CTA ~97 KB in every configuration -> two CTAs per SM, so one tile's epilogue overlaps
+  // the other's TMA/MMA main loop (TMEM: 2 x 256 columns = the whole 512-column file)
+  if (a.Co > 128) launch_tc<256, 2>(a, st);
   else if (a.Co > 64) launch_tc<128, 3>(a, st);
   else launch_tc<64, 4>(a, st);
   post_launch("conv_tc", st);
@@ -268,38 +287,59 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // Operand producer: out_bf16[r, c] = act(x[r, c] * scale[b, c] + shift[b, c]) for rows of item b,
 // 0 for halo/gap rows and for pad columns c >= C.  Covers rows [off-gap, off+len+gap_after).
+// Each thread produces 4 consecutive channels (float4 load when aligned, one 8-byte store); the
+// bf16 result absorbs the error of the fast sin / division intrinsics used for Snake.
+__device__ __forceinline__ float apply_act(float v, int act, float slope, float al) {
+  if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == ACT_SNAKE) { const float s = __sinf(al * v); return v + __fdividef(s * s, al); }
+  return v;
+}
+constexpr int kApplyRows = 16;  // rows per CTA
 __global__ void __launch_bounds__(256) apply_bf16_kernel(const float* __restrict__ x, int ldx, int C,
                                                          const float* scale, const float* shift,
                                                          int act, float slope, const float* alpha,
                                                          __nv_bfloat16* out, int Cpad, int rows_total,
-                                                         const int* off, const int* len) {
+                                                         const int* off, const int* len, int vec_ok) {
   const int b = blockIdx.y;
   const int L = len[b], o = off[b];
-  const int r_begin = o - kGapRows, r_end = min(rows_total, o + L + kGapRows + 8);
+  // item b zeroes its leading gap and kGapRows rows after its end (never reaching the next item,
+  // whose own leading gap covers the alignment slack); the last item zeroes up to rows_total
+  const int r_begin = o - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : o + L + kGapRows;
+  const int rb = r_begin + blockIdx.x * kApplyRows;
+  if (rb >= r_end) return;
+  const int re = min(r_end, rb + kApplyRows);
   const float* sc = scale ? scale + (size_t)b * C : nullptr;
   const float* sh = shift ? shift + (size_t)b * C : nullptr;
-  const int cp2 = Cpad >> 1;  // column pairs
-  const long long total = (long long)(r_end - r_begin) * cp2;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int r = r_begin + (int)(i / cp2);
-    const int c = (int)(i % cp2) * 2;
-    float v0 = 0.f, v1 = 0.f;
-    if (r >= o && r < o + L) {
-      const float* xp = x + (size_t)r * ldx;
-      if (c < C) {
-        v0 = xp[c];
-        if (sc) v0 = v0 * sc[c] + sh[c];
-        if (act == ACT_LRELU) v0 = v0 > 0.f ? v0 : v0 * slope;
-        else if (act == ACT_SNAKE) { const float al = alpha[c]; const float s = sinf(al * v0); v0 = v0 + (1.0f / al) * (s * s); }
+  const int cq = Cpad >> 2;  // column quads
+  const int total = (re - rb) * cq;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = rb + i / cq;
+    const int c = (i % cq) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r >= o && r < o + L && c < C) {
+      const float* xp = x + (size_t)r * ldx + c;
+      if (vec_ok && c + 3 < C) {
+        const float4 t = *reinterpret_cast<const float4*>(xp);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (c + e < C) v[e] = xp[e];
       }
-      if (c + 1 < C) {
-        v1 = xp[c + 1];
-        if (sc) v1 = v1 * sc[c + 1] + sh[c + 1];
-        if (act == ACT_LRELU) v1 = v1 > 0.f ? v1 : v1 * slope;
-        else if (act == ACT_SNAKE) { const float al = alpha[c + 1]; const float s = sinf(al * v1); v1 = v1 + (1.0f / al) * (s * s); }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (c + e < C) {
+          float t = v[e];
+          if (sc) t = fmaf(t, sc[c + e], sh[c + e]);
+          v[e] = apply_act(t, act, slope, alpha ? alpha[c + e] : 1.f);
+        }
       }
     }
-    *reinterpret_cast<__nv_bfloat162*>(out + (size_t)r * Cpad + c) = __floats2bfloat162_rn(v0, v1);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + (size_t)r * Cpad + c) = pk;
   }
 }
 
@@ -307,13 +347,11 @@ void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const
                        float slope, const float* alpha, void* out, int Cpad, int rows_total,
                        const int* off, const int* len, int B, int max_len, cudaStream_t st) {
   if (g_dry_run) return;
-  long long work = (long long)(max_len + 2 * kGapRows + 8) * (Cpad / 2);
-  long long blocks = (work + 256 * 4 - 1) / (256 * 4);
-  if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  dim3 g((unsigned)blocks, B);
+  const int rows = max_len + 2 * kGapRows + 8;
+  dim3 g((rows + kApplyRows - 1) / kApplyRows, B);
+  const int vec_ok = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
   apply_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, alpha, (__nv_bfloat16*)out, Cpad,
-                                       rows_total, off, len);
+                                       rows_total, off, len, vec_ok);
   post_launch("apply_bf16", st);
 }
 
@@ -326,7 +364,8 @@ __global__ void __launch_bounds__(256) pool_up_bf16_kernel(const float* __restri
                                                            const int* in_len, const int* out_off) {
   const int b = blockIdx.y;
   const int T = in_len[b], oo = out_off[b];
-  const int r_begin = oo - kGapRows, r_end = min(rows_total, oo + 2 * T + kGapRows + 8);
+  const int r_begin = oo - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : oo + 2 * T + kGapRows;
   const float* sc = scale + (size_t)b * C;
   const float* sh = shift + (size_t)b * C;
   const long long total = (long long)(r_end - r_begin) * Cpad;

