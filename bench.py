@@ -157,7 +157,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--tokens", type=int, default=510)
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("KKX_PRECISION", "0")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("KKX_PRECISION", "1")),
+                    help="1 = bf16 tensor-core decoder+generator (default), 0 = fp32 SIMT everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel timing table of one step here")
     args = ap.parse_args()

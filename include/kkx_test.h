@@ -22,6 +22,9 @@ KKX_API int kkx_test_conv(int device, const float* in, int rows_in, int ldi, int
                           int accumulate, float* out);
 /* xproj [N,2048], whhT [2][256][1024] -> out [N,512] */
 KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out);
+/* ragged batch: xproj [rows,2048], items at off[b] with len[b] rows -> out [rows,512] (pre-zeroed) */
+KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whhT, int B, const int* off,
+                                const int* len, int rows, float* out);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* x [L,C] + style row (gamma|beta, 2C) -> scale [C], shift [C] (InstanceNorm stats + AdaIN) */
@@ -35,6 +38,10 @@ KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const fl
                              int pact, float pslope, const float* palpha, int m_len, int ors, int oro,
                              int out_rows, const float* res, int res_rows, int res_shift, float oscale,
                              int accumulate, float* out);
+/* Split-TF32 tensor-core GEMM/conv (fp32-grade accuracy on tcgen05 kind::tf32): x [L,Ci], w [Co][ks][Ci]
+ * fp32, nprod = 3 or 4 partial products, eact 0 / 3 (gelu_new).  out [L, Co]. */
+KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                               int Co, int ks, int dil, int pad, int nprod, int eact, float* out);
 KKX_API const char* kkx_test_last_error(void);
 
 #ifdef __cplusplus

@@ -38,6 +38,11 @@ void launch_conv_f32(const ConvArgs& a, cudaStream_t st);
 struct TcConvArgs {
   const void* tmA = nullptr;  // host pointers to CUtensorMap objects (copied into kernel params)
   const void* tmB = nullptr;
+  const void* tmA2 = nullptr; // split-TF32 mode: the "lo" planes
+  const void* tmB2 = nullptr;
+  int tf32 = 0;               // 1 = split-TF32 operands (fp32 containers), nprod products (3 or 4)
+  int nprod = 3;
+  int eact = ACT_NONE;
   int Cpad = 0, Ci = 0, Co = 0, ks = 1, dil = 1, pad = 0;
   const int* in_off = nullptr; const int* m_len = nullptr; int max_m = 0; int B = 1; long long sum_m = 0;
   const float* bias = nullptr;
@@ -49,7 +54,13 @@ void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);
 // out_map: 128-byte CUtensorMap storage (64-byte aligned).  bf16 [outer, inner], box [box_outer, 64].
 void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
                     long long pitch_elems, int box_outer);
+void make_tmap_f32(void* out_map, const void* ptr, long long inner, long long outer,
+                   long long pitch_elems, int box_outer);
 inline int tc_box_n(int Co) { return Co > 128 ? 256 : (Co > 64 ? 128 : 64); }
+inline int tc_box_n_tf32(int Co) { return Co > 64 ? 128 : 64; }
+void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                       float slope, float* out_hi, float* out_lo, int Cpad, int rows_total,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st);
 // bf16 operand producers (AdaIN scale/shift + activation fused; zero halo rows and pad columns)
 void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
                        float slope, const float* alpha, void* out, int Cpad, int rows_total,

@@ -447,11 +447,155 @@ __global__ void __launch_bounds__(1024) lstm_kernel(const float* __restrict__ xp
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent weight-stationary bi-LSTM (K3).  One thread-block CLUSTER of 8 CTAs per (direction,
+// group of G items).  CTA r of the cluster keeps the W_hh rows of hidden units [32r, 32r+32) (all
+// four gates: 128 rows x 256 k fp32 = 128 KB) resident in shared memory for the whole sequence;
+// every step it computes those 128 gate pre-activations for the G items of its group (weights read
+// once per step and reused across items), updates its 32 cell/hidden values per item, and
+// broadcasts the new h slice into the next-step h buffer of all 8 CTAs through distributed shared
+// memory, followed by one cluster barrier.  Gate dot products are split over two half-warps and
+// combined with a warp shuffle.
+}  // namespace kkx
+#include <cooperative_groups.h>
+namespace kkx {
+namespace cg = cooperative_groups;
+
+template <int G>
+__global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __restrict__ xproj,
+                                                              const float* __restrict__ whhT,
+                                                              float* __restrict__ out, int ldo, int ocol,
+                                                              const int* off, const int* len, int B) {
+  extern __shared__ float4 lsm4[];
+  float* Ws = reinterpret_cast<float*>(lsm4);          // [64 k4][128 rows][4]
+  float* hbuf = Ws + 256 * 128;                        // [2][G][256]
+  float* gates = hbuf + 2 * G * 256;                   // [G][128]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = (int)cluster.block_rank();             // 0..7: hidden-unit slice
+  const int group = blockIdx.x >> 3, dir = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = lane >> 4, rloc = warp * 16 + (lane & 15);   // gate row (local) of this thread
+  const int gate = rloc >> 5, jl = rloc & 31;
+  const int grow = gate * 256 + r * 32 + jl;                    // global gate row
+
+  // stage this CTA's 128 KB weight slice: Ws[(k>>2)][rloc][k&3] = W_hh^T[dir][k][grow(rloc)]
+  const float* Wg = whhT + (size_t)dir * 256 * 1024;
+  for (int i = tid; i < 256 * 128; i += 256) {
+    const int k = i >> 7, rl = i & 127;
+    const int gr = (rl >> 5) * 256 + r * 32 + (rl & 31);
+    Ws[((k >> 2) * 128 + rl) * 4 + (k & 3)] = Wg[(size_t)k * 1024 + gr];
+  }
+  for (int i = tid; i < 2 * G * 256; i += 256) hbuf[i] = 0.f;
+
+  int ioff[G], ilen[G];
+  int maxN = 0;
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const int item = group * G + g;
+    ioff[g] = item < B ? off[item] : 0;
+    ilen[g] = item < B ? len[item] : 0;
+    maxN = max(maxN, ilen[g]);
+  }
+  float c = 0.f;                                         // cell state of (item tid>>5, unit tid&31)
+  cluster.sync();
+
+  for (int s = 0; s < maxN; s++) {
+    const float* hc = hbuf + (s & 1) * G * 256;
+    float* hn_local = hbuf + ((s + 1) & 1) * G * 256;
+    // prefetch this step's input projections (consumed after the dot loop)
+    float xp[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      xp[g] = 0.f;
+      if (half == 0 && s < ilen[g]) {
+        const int t = dir == 0 ? s : ilen[g] - 1 - s;
+        xp[g] = xproj[(size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow];
+      }
+    }
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(Ws) + (half * 32) * 128 + rloc;
+    const float4* h4 = reinterpret_cast<const float4*>(hc) + half * 32;
+#pragma unroll 4
+    for (int kk = 0; kk < 32; kk++) {
+      const float4 w = w4[kk * 128];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const float4 h = h4[g * 64 + kk];
+        acc[g] = fmaf(w.x, h.x, acc[g]);
+        acc[g] = fmaf(w.y, h.y, acc[g]);
+        acc[g] = fmaf(w.z, h.z, acc[g]);
+        acc[g] = fmaf(w.w, h.w, acc[g]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 16);
+      if (half == 0) gates[g * 128 + rloc] = acc[g] + xp[g];
+    }
+    __syncthreads();
+    if (tid < 32 * G) {
+      const int g = tid >> 5, j = tid & 31;
+      const float* gp = gates + g * 128;
+      const float ig = 1.0f / (1.0f + expf(-gp[j]));
+      const float fg = 1.0f / (1.0f + expf(-gp[32 + j]));
+      const float gg = tanhf(gp[64 + j]);
+      const float og = 1.0f / (1.0f + expf(-gp[96 + j]));
+      c = fg * c + ig * gg;
+      const float hv = og * tanhf(c);
+      if (s < ilen[g]) {
+        const int t = dir == 0 ? s : ilen[g] - 1 - s;
+        out[(size_t)(ioff[g] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
+      }
+      float* dst_local = hn_local + g * 256 + r * 32 + j;
+#pragma unroll
+      for (int d = 0; d < 8; d++) *cluster.map_shared_rank(dst_local, d) = hv;
+    }
+    cluster.sync();   // new h visible cluster-wide; everyone is done with the old h and the gates
+  }
+}
+
+template <int G>
+static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
+                                const int* off, const int* len, int B, cudaStream_t st) {
+  const size_t smem = (size_t)(256 * 128 + 2 * G * 256 + G * 128) * sizeof(float);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[dev] = true;
+  }
+  const int groups = (B + G - 1) / G;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(8 * groups, 2, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  KKX_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<G>, xproj, whhT, out, ldo, ocol, off, len, B));
+}
+
 void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                  const int* off, const int* len, int B, cudaStream_t st) {
   if (g_dry_run) return;
-  dim3 g(B, 2);
-  lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);
+  static const bool simple = [] { const char* e = getenv("KKX_LSTM_SIMPLE"); return e && e[0] == '1'; }();
+  if (simple) {
+    dim3 g(B, 2);
+    lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);
+  } else if (B <= 8) {
+    launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st);    // 2B clusters <= 16
+  } else if (B <= 16) {
+    launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+  } else if (B <= 32) {
+    launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+  } else {
+    launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);    // 64 items -> 16 clusters
+  }
   post_launch("lstm", st);
 }
 

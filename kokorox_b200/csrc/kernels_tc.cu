@@ -36,13 +36,14 @@ static EncodeTiledFn get_encode() {
 
 // bf16 row-major [outer, inner] with row pitch `pitch_elems`; box = [box_outer, 64] elements,
 // 128-byte swizzle (one box row = 128 B = one swizzle span).
-void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
-                    long long pitch_elems, int box_outer) {
+static void make_tmap(void* out_map, const void* ptr, long long inner, long long outer,
+                      long long pitch_elems, int box_outer, bool f32) {
+  const int esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+  CUresult r = get_encode()((CUtensorMap*)out_map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -50,6 +51,15 @@ void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long o
     snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld pitch=%lld", (int)r, inner, outer, pitch_elems);
     throw CudaError(b);
   }
+}
+void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
+                    long long pitch_elems, int box_outer) {
+  make_tmap(out_map, ptr, inner, outer, pitch_elems, box_outer, false);
+}
+// fp32 container (tf32 operands): box = [box_outer, 32] elements = 128 B rows
+void make_tmap_f32(void* out_map, const void* ptr, long long inner, long long outer,
+                   long long pitch_elems, int box_outer) {
+  make_tmap(out_map, ptr, inner, outer, pitch_elems, box_outer, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -95,6 +105,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// kind::tf32: A/B format 2 (TF32), fp32 accumulate; K = 8 per instruction
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -111,23 +131,44 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float gelu_new_f(float v) {
+  const float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+  return 0.5f * v * (1.0f + tanhf(u));
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel.  One 128 x BN output tile per CTA.  6 warps:
 //   warp 0  TMA producer (one elected lane)        warp 1  TMEM alloc + MMA issuer (one lane)
 //   warps 2..5  epilogue: tcgen05.ld of the warp's 32-lane TMEM quadrant -> bias / residual /
 //               scale / accumulate -> global
-template <int BN, int STAGES>
+// MODE 0: bf16 operands, one product.  MODE 1: split-TF32 ("3xTF32"/"4xTF32"): every operand is a
+// pair of tf32-exact fp32 planes (hi, lo = a - hi), D += Ahi*Bhi + Alo*Bhi + Ahi*Blo [+ Alo*Blo] on
+// kind::tf32, which recovers ~fp32 accuracy on the tensor cores for the precision-critical
+// predictor path (ALBERT -> durations, F0/N).
+template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
+                                                      const __grid_constant__ CUtensorMap tmA2,
+                                                      const __grid_constant__ CUtensorMap tmB2,
                                                       TcConvArgs a) {
-  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t PLANES = MODE ? 2 : 1;
+  constexpr int KE = MODE ? 32 : 64;   // K elements per pipeline stage (one 128-byte swizzle span)
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;        // full[S], empty[S], tmem_full
-  const uint32_t tmem_slot = bar_base + (2 * STAGES + 1) * 8;
+  // MODE 1 keeps 4 accumulators in TMEM: [0] all small cross terms, [1..3] a ring for the hi*hi
+  // term, which is accumulated in chains of only 64 K-elements: the tensor core adds with
+  // round-toward-zero once per MMA (measured: error grows linearly, ~0.5 ulp per K=8 step), so long
+  // chains would lose fp32-grade accuracy; the epilogue warps drain each finished chain and add it
+  // into registers with IEEE round-to-nearest while the next chain runs.
+  constexpr uint32_t TMEM_COLS = MODE ? 4 * BN : BN;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;        // full[S], empty[S], tmem_full, bfull[3], bempty[3]
+  const uint32_t tmem_slot = bar_base + (2 * STAGES + 1 + 6) * 8;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
   const uint32_t tfull_bar = bar_base + 2 * STAGES * 8;
+  auto bfull_bar = [&](int j) { return bar_base + (2 * STAGES + 1 + j) * 8; };
+  auto bempty_bar = [&](int j) { return bar_base + (2 * STAGES + 4 + j) * 8; };
 
   const int b = blockIdx.z;
   const int mlen = a.m_len[b];
@@ -135,19 +176,24 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   if (m0 >= mlen) return;  // CTA-uniform
   const int n0 = blockIdx.y * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kchunks = a.Cpad >> 6;
+  const int kchunks = a.Cpad / KE;
   const int num_k = a.ks * kchunks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (MODE) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    }
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tfull_bar, 1);
+    if (MODE) for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -163,26 +209,51 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+        const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
         const uint32_t sa = base + s * STAGE_BYTES;
         mbar_expect_tx(full_bar(s), STAGE_BYTES);
         tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
-        tma_load_2d(sa + A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+        tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+        if (MODE) {
+          tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
+          tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = MODE ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sa = base + s * STAGE_BYTES;
-        const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
+        if (MODE == 0) {
+          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
-          umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
+            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        } else {
+          const int chain = it >> 1, j = chain % 3;
+          const bool chain_start = (it & 1) == 0;
+          if (chain_start && chain >= 3) {       // ring slot j must have been drained by the epilogue
+            mbar_wait(bempty_bar(j), (uint32_t)(chain / 3 - 1) & 1u);
+            tc_fence_after();
+          }
+          const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+          const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
+            const uint64_t o = (uint64_t)(2 * k);
+            if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
+            umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
+            umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
+            umma_tf32(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u);
+          }
+          if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
+        }
         umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
       }
       umma_commit(tfull_bar);       // accumulator complete
@@ -193,18 +264,42 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     // 32-column strip of one accumulator row into padded smem (conflict-free), then the 128
     // threads write whole 128-byte row segments to global (8 lanes per row -> full-line stores,
     // coalesced residual / accumulate reads).
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int et = q * 32 + lane;           // accumulator row held by this thread
+    float racc[MODE ? BN : 1];              // MODE 1: fp32 (round-to-nearest) sum of the drained hi*hi chains
+    if (MODE) {
+#pragma unroll
+      for (int e = 0; e < (MODE ? BN : 1); e++) racc[e] = 0.f;
+      const int nchains = (num_k + 1) >> 1;
+      for (int ch = 0; ch < nchains; ch++) {
+        const int j = ch % 3;
+        mbar_wait(bfull_bar(j), (uint32_t)(ch / 3) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
+#pragma unroll
+          for (int e = 0; e < 32; e++) racc[(MODE ? c : 0) + (MODE ? e : 0)] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
+      }
+    }
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
     constexpr int PITCH = 36;               // floats per staged row (32 + 4 pad)
     float* stage_f = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
     const int out_off = a.out_off[b];
     const int res_off = a.res ? a.res_off[b] : 0;
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (MODE) {
+#pragma unroll
+        for (int e = 0; e < 32; e++) v[e] = __float_as_uint(__uint_as_float(v[e]) + racc[(MODE ? c : 0) + (MODE ? e : 0)]);
+      }
       float* buf = stage_f + ((c >> 5) & 1) * (128 * PITCH);
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -224,6 +319,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
             const float* rp = a.res ? a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n) : nullptr;
             if (a.vec4 && n + 3 < a.Co) {
               if (a.bias) { const float4 bb = *reinterpret_cast<const float4*>(a.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
+              if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
               if (rp) { const float4 r = *reinterpret_cast<const float4*>(rp); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
               o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
               if (a.accumulate) { const float4 pv = *reinterpret_cast<const float4*>(op); o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
@@ -235,6 +331,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
                 if (n + e < a.Co) {
                   float t = ov[e];
                   if (a.bias) t += a.bias[n + e];
+                  if (a.eact == ACT_GELU_NEW) t = gelu_new_f(t);
                   if (rp) t += rp[e];
                   t *= a.oscale;
                   if (a.accumulate) t += op[e];
@@ -251,23 +348,27 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MODE>
 static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
-  constexpr int smem = STAGES * (128 * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int PLANES = MODE ? 2 : 1;
+  constexpr int smem = STAGES * PLANES * (128 * 128 + BN * 128) + (2 * STAGES + 7) * 8 + 16 + 1024;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set[dev] = true;
   }
   dim3 g((a.max_m + 127) / 128, (a.Co + BN - 1) / BN, a.B);
-  conv_tc_kernel<BN, STAGES><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
-                                                   *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  const CUtensorMap* mA = reinterpret_cast<const CUtensorMap*>(a.tmA);
+  const CUtensorMap* mB = reinterpret_cast<const CUtensorMap*>(a.tmB);
+  const CUtensorMap* mA2 = reinterpret_cast<const CUtensorMap*>(a.tmA2 ? a.tmA2 : a.tmA);
+  const CUtensorMap* mB2 = reinterpret_cast<const CUtensorMap*>(a.tmB2 ? a.tmB2 : a.tmB);
+  conv_tc_kernel<BN, STAGES, MODE><<<g, 192, smem, st>>>(*mA, *mB, *mA2, *mB2, a);
 }
 
 void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
@@ -276,11 +377,18 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   TcConvArgs a = a0;
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
+  if (a.tf32) {
+    // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
+    if (a.Co > 64) launch_tc<128, 3, 1>(a, st);
+    else launch_tc<64, 4, 1>(a, st);
+    post_launch("conv_tc_tf32x3", st);
+    return;
+  }
   // smem per CTA ~97 KB in every configuration -> two CTAs per SM, so one tile's epilogue overlaps
   // the other's TMA/MMA main loop (TMEM: 2 x 256 columns = the whole 512-column file)
-  if (a.Co > 128) launch_tc<256, 2>(a, st);
-  else if (a.Co > 64) launch_tc<128, 3>(a, st);
-  else launch_tc<64, 4>(a, st);
+  if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
+  else if (a.Co > 64) launch_tc<128, 3, 0>(a, st);
+  else launch_tc<64, 4, 0>(a, st);
   post_launch("conv_tc", st);
 }
 
@@ -353,6 +461,52 @@ void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const
   apply_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, alpha, (__nv_bfloat16*)out, Cpad,
                                        rows_total, off, len, vec_ok);
   post_launch("apply_bf16", st);
+}
+
+// Split-TF32 operand producer: hi = rna_tf32(v), lo = rna_tf32(v - hi), two fp32 planes
+// [rows_total, Cpad]; same prologue fusion and halo zeroing as apply_bf16.
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__global__ void __launch_bounds__(256) apply_tf32_kernel(const float* __restrict__ x, int ldx, int C,
+                                                         const float* scale, const float* shift,
+                                                         int act, float slope, float* out_hi, float* out_lo,
+                                                         int Cpad, int rows_total, const int* off,
+                                                         const int* len) {
+  const int b = blockIdx.y;
+  const int L = len[b], o = off[b];
+  const int r_begin = o - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : o + L + kGapRows;
+  const int rb = r_begin + blockIdx.x * kApplyRows;
+  if (rb >= r_end) return;
+  const int re = min(r_end, rb + kApplyRows);
+  const float* sc = scale ? scale + (size_t)b * C : nullptr;
+  const float* sh = shift ? shift + (size_t)b * C : nullptr;
+  const int total = (re - rb) * Cpad;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = rb + i / Cpad;
+    const int c = i % Cpad;
+    float v = 0.f;
+    if (r >= o && r < o + L && c < C) {
+      v = x[(size_t)r * ldx + c];
+      if (sc) v = v * sc[c] + sh[c];            // same arithmetic as the fp32 SIMT prologue
+      if (act == ACT_LRELU) v = v > 0.f ? v : v * slope;
+    }
+    const float hi = to_tf32(v);
+    out_hi[(size_t)r * Cpad + c] = hi;
+    out_lo[(size_t)r * Cpad + c] = to_tf32(v - hi);
+  }
+}
+void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                       float slope, float* out_hi, float* out_lo, int Cpad, int rows_total,
+                       const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  const int rows = max_len + 2 * kGapRows + 8;
+  dim3 g((rows + kApplyRows - 1) / kApplyRows, B);
+  apply_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, out_hi, out_lo, Cpad, rows_total, off, len);
+  post_launch("apply_tf32", st);
 }
 
 // Depthwise ConvTranspose1d(k3,s2,p1,op1) on lrelu(x*scale+shift) -> bf16 operand [2T rows, Cpad]

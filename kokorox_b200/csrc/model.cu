@@ -160,6 +160,40 @@ TcW Model::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
   return t;
 }
 
+namespace {
+float host_tf32(float f) {  // cvt.rna.tf32.f32
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u = (u + 0x1000u) & ~0x1FFFu;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+std::vector<float> concat(std::initializer_list<const HostTensor*> ts) {
+  std::vector<float> o;
+  for (auto t : ts) o.insert(o.end(), t->data, t->data + t->numel);
+  return o;
+}
+}  // namespace
+
+TcW32 Model::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) {
+  TcW32 t;
+  t.Ci = Ci; t.Co = Co; t.ks = ks; t.Cpad = (Ci + 63) & ~63;
+  std::vector<float> hi((size_t)Co * ks * t.Cpad, 0.f), lo((size_t)Co * ks * t.Cpad, 0.f);
+  for (int o = 0; o < Co; o++)
+    for (int k = 0; k < ks; k++)
+      for (int c = 0; c < Ci; c++) {
+        const float f = w[((size_t)o * ks + k) * Ci + c];
+        const float h = host_tf32(f);
+        hi[((size_t)o * ks + k) * t.Cpad + c] = h;
+        lo[((size_t)o * ks + k) * t.Cpad + c] = host_tf32(f - h);
+      }
+  t.hi = up(hi); t.lo = up(lo);
+  make_tmap_f32(t.tm_hi, t.hi, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
+  make_tmap_f32(t.tm_lo, t.lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
+  return t;
+}
+
 void Model::load_weights(const WeightFile& wf) {
   auto U = [&](const std::string& n) { return up(raw(wf, n)); };
   auto LT = [&](const std::string& n, int N, int K) { return up(linT(wf, n, N, K)); };
@@ -193,6 +227,14 @@ void Model::load_weights(const WeightFile& wf) {
   W.ffo_w = LT(L + "ffn_output.weight", 768, 2048); W.ffo_b = U(L + "ffn_output.bias");
   W.full_lnw = U(L + "full_layer_layer_norm.weight"); W.full_lnb = U(L + "full_layer_layer_norm.bias");
   W.benc_w = LT("bert_encoder.weight", 512, 768); W.benc_b = U("bert_encoder.bias");
+  // split-TF32 copies (torch Linear [N][K] is already [Co][1][Ci])
+  W.t_map = make_tc32(raw(wf, "bert.encoder.embedding_hidden_mapping_in.weight"), 768, 1, 128);
+  W.t_qkv = make_tc32(concat({&wf.get(L + "attention.query.weight"), &wf.get(L + "attention.key.weight"),
+                              &wf.get(L + "attention.value.weight")}), 2304, 1, 768);
+  W.t_dense = make_tc32(raw(wf, L + "attention.dense.weight"), 768, 1, 768);
+  W.t_ffn = make_tc32(raw(wf, L + "ffn.weight"), 2048, 1, 768);
+  W.t_ffo = make_tc32(raw(wf, L + "ffn_output.weight"), 768, 1, 2048);
+  W.t_benc = make_tc32(raw(wf, "bert_encoder.weight"), 512, 1, 768);
 
   // ---- LSTMs (A.11 gate order i,f,g,o)
   auto LSTM = [&](const std::string& p, int in) {
@@ -212,6 +254,7 @@ void Model::load_weights(const WeightFile& wf) {
       }
     }
     l.wih = up(wih); l.bias = up(bias); l.whhT = up(whh);
+    l.t_ih = make_tc32(concat({&wf.get(p + ".weight_ih_l0"), &wf.get(p + ".weight_ih_l0_reverse")}), 2048, 1, in);
     return l;
   };
 
@@ -235,6 +278,7 @@ void Model::load_weights(const WeightFile& wf) {
   W.te_lstm = LSTM("text_encoder.lstm", 512);
   W.durp_w = LT("predictor.duration_proj.linear_layer.weight", 50, 512);
   W.durp_b = U("predictor.duration_proj.linear_layer.bias");
+  W.t_durp = make_tc32(raw(wf, "predictor.duration_proj.linear_layer.weight"), 50, 1, 512);
 
   auto BLK = [&](const std::string& p, int ci, int co, bool upf, bool pro) {
     AdaBlkW b; b.ci = ci; b.co = co; b.up = upf;
@@ -242,7 +286,12 @@ void Model::load_weights(const WeightFile& wf) {
     b.w2 = CW(p + ".conv2.weight", co, co, 3); b.b2 = U(p + ".conv2.bias");
     if (ci != co) b.w1x1 = CW(p + ".conv1x1.weight", co, ci, 1);
     if (upf) { b.poolw = U(p + ".pool.weight"); b.poolb = U(p + ".pool.bias"); }
-    if (!pro) {  // decoder blocks also get tensor-core weights; the F0/N predictor stays fp32
+    if (pro) {   // F0/N predictor blocks: split-TF32 (fp32-grade) tensor-core weights
+      b.s1 = make_tc32(convCoKsCi(wf, p + ".conv1.weight", co, ci, 3), co, 3, ci);
+      b.s2 = make_tc32(convCoKsCi(wf, p + ".conv2.weight", co, co, 3), co, 3, co);
+      if (ci != co) b.s1x1 = make_tc32(convCoKsCi(wf, p + ".conv1x1.weight", co, ci, 1), co, 1, ci);
+    }
+    if (!pro) {  // decoder blocks: bf16 tensor-core weights
       b.t1 = make_tc(convCoKsCi(wf, p + ".conv1.weight", co, ci, 3), co, 3, ci);
       b.t2 = make_tc(convCoKsCi(wf, p + ".conv2.weight", co, co, 3), co, 3, co);
       if (ci != co) b.t1x1 = make_tc(convCoKsCi(wf, p + ".conv1x1.weight", co, ci, 1), co, 1, ci);
@@ -268,6 +317,7 @@ void Model::load_weights(const WeightFile& wf) {
   for (int i = 0; i < 3; i++) {
     const std::string p = "text_encoder.cnn." + std::to_string(i);
     W.tcnn_w[i] = CW(p + ".0.weight", 512, 512, 5); W.tcnn_b[i] = U(p + ".0.bias");
+    W.t_tcnn[i] = make_tc32(convCoKsCi(wf, p + ".0.weight", 512, 512, 5), 512, 5, 512);
     W.tln_g[i] = U(p + ".1.gamma"); W.tln_b[i] = U(p + ".1.beta");
   }
 

@@ -34,13 +34,21 @@ struct TcW {
   alignas(64) unsigned char tmap[128];
   int Cpad = 0, Ci = 0, Co = 0, ks = 0;
 };
-struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; };
+// split-TF32 weight: tf32-exact hi / lo fp32 planes [Co][ks][Cpad] + TMA descriptors
+struct TcW32 {
+  float* hi = nullptr; float* lo = nullptr;
+  alignas(64) unsigned char tm_hi[128];
+  alignas(64) unsigned char tm_lo[128];
+  int Cpad = 0, Ci = 0, Co = 0, ks = 0;
+};
+struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; TcW32 t_ih; };
 struct AdaBlkW {  // AdainResBlk1d
   int ci = 0, co = 0; bool up = false;
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr, *w1x1 = nullptr;
   float *poolw = nullptr, *poolb = nullptr;
   int sty1 = 0, sty2 = 0;  // offsets into the per-item style-parameter table
   TcW t1, t2, t1x1;
+  TcW32 s1, s2, s1x1;   // split-TF32 variants (predictor F0/N blocks)
 };
 struct ArbW {  // AdaINResBlock1
   int c = 0, k = 0;
@@ -55,6 +63,7 @@ struct Weights {
   float *qkv_w, *qkv_b, *dense_w, *dense_b, *attn_lnw, *attn_lnb;
   float *ffn_w, *ffn_b, *ffo_w, *ffo_b, *full_lnw, *full_lnb;
   float *benc_w, *benc_b;
+  TcW32 t_map, t_qkv, t_dense, t_ffn, t_ffo, t_benc, t_durp, t_tcnn[3];
   // predictor
   LstmW dur_lstm[3]; int dur_ada[3];
   LstmW pred_lstm, shared_lstm;
@@ -126,6 +135,15 @@ class Model {
   void load_weights(const WeightFile& wf);
   float* up(const std::vector<float>& v);
   TcW make_tc(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
+  TcW32 make_tc32(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
+  // Linear / Conv1d on the precision-critical path: split-TF32 tensor cores when precision==1 and
+  // the weight has a TcW32, fp32 SIMT otherwise.
+  void gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
+            const float* bias, int N, float* out, int ldo, int ocol, int eact = ACT_NONE, int ks = 1,
+            int pad = 0, const float* pscale = nullptr, const float* pshift = nullptr, int pact = ACT_NONE,
+            float pslope = 0.f, const float* res = nullptr, int ldr = 0, const Level* Lres = nullptr,
+            int res_shift = 0, float oscale = 1.f);
+  float* split_hi_ = nullptr; float* split_lo_ = nullptr; size_t split_cap_ = 0;  // scratch planes (floats)
   void tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, int dil, int pad, const Level& Lin,
                const Level& Lm, const float* bias, float* out, int ldo, int ocol, const Level& Lout, int ors,
                int oro, const float* res, int ldr, const Level* Lres, int res_shift, float oscale,

@@ -37,6 +37,35 @@ void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, in
   launch_conv_tc(a, stream_);
 }
 
+void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
+                 const float* bias, int N, float* out, int ldo, int ocol, int eact, int ks, int pad,
+                 const float* pscale, const float* pshift, int pact, float pslope, const float* res, int ldr,
+                 const Level* Lres, int res_shift, float oscale) {
+  cudaStream_t st = stream_;
+  if (opt.precision == 1 && w32 && w32->hi && split_hi_ && (size_t)Lin.rows * w32->Cpad <= split_cap_) {
+    if (g_dry_run) return;
+    launch_apply_tf32(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
+                      Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
+    alignas(64) unsigned char tA[128], tA2[128];
+    make_tmap_f32(tA, split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+    make_tmap_f32(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+    TcConvArgs a;
+    a.tmA = tA; a.tmA2 = tA2; a.tmB = w32->tm_hi; a.tmB2 = w32->tm_lo; a.tf32 = 1; a.nprod = 3; a.eact = eact;
+    a.Cpad = w32->Cpad; a.Ci = K; a.Co = N; a.ks = ks; a.dil = 1; a.pad = pad;
+    a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
+    a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lm.d_off;
+    a.res = res; a.ldr = ldr; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift; a.oscale = oscale;
+    launch_conv_tc(a, st);
+    return;
+  }
+  ConvArgs c = gemm_args(Lm, in, ldi, K, w, bias, N, out, ldo, ocol);
+  c.in_off = Lin.d_off; c.in_len = Lin.d_len;
+  c.ks = ks; c.pad = pad; c.eact = eact;
+  c.pscale = pscale; c.pshift = pshift; c.pld = K; c.pact = pact; c.pslope = pslope;
+  c.res = res; c.ldr = ldr; c.res_off = Lres ? Lres->d_off : nullptr; c.res_shift = res_shift; c.oscale = oscale;
+  launch_conv_f32(c, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // Token phase: everything at phoneme-token rate, for the whole batch.
 void Model::token_phase(Run& r) {
@@ -44,7 +73,7 @@ void Model::token_phase(Run& r) {
   const Level& L = tokL_;
   const size_t R = (size_t)L.rows;
   const int B = B_;
-  const size_t need = R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16) * sizeof(float) +
+  const size_t need = R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048) * sizeof(float) +
                       (size_t)B * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20);
   if (need > tokA_.capacity()) {
     KKX_CUDA(cudaStreamSynchronize(st));
@@ -69,6 +98,11 @@ void Model::token_phase(Run& r) {
   launch_conv_f32(gemm_args(r.styL, d_styles_, 256, 128, W.sty_dec_w, W.sty_dec_b, W.sty_dec_n,
                             r.sty_dec, W.sty_dec_n, 0), st);
 
+  // scratch planes for the split-TF32 operand producer (largest K on this path: 2048)
+  split_cap_ = R * 2048;
+  split_hi_ = A.alloc<float>(split_cap_);
+  split_lo_ = A.alloc<float>(split_cap_);
+
   // ---- ALBERT (A.2)
   float* e = A.alloc<float>(R * 128);
   float* h = A.alloc<float>(R * 768);
@@ -79,20 +113,18 @@ void Model::token_phase(Run& r) {
   float* ff = A.alloc<float>(R * 2048);
   launch_albert_embed(d_ids_, W.word, W.pos, W.type, W.emb_lnw, W.emb_lnb, e, L.d_off, L.d_len, B,
                       L.max_len, st);
-  launch_conv_f32(gemm_args(L, e, 128, 128, W.map_w, W.map_b, 768, h, 768, 0), st);
+  gemm(L, L, e, 128, 128, W.map_w, &W.t_map, W.map_b, 768, h, 768, 0);
   for (int layer = 0; layer < 12; layer++) {
-    launch_conv_f32(gemm_args(L, h, 768, 768, W.qkv_w, W.qkv_b, 2304, qkv, 2304, 0), st);
+    gemm(L, L, h, 768, 768, W.qkv_w, &W.t_qkv, W.qkv_b, 2304, qkv, 2304, 0);
     launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
-    launch_conv_f32(gemm_args(L, ctx, 768, 768, W.dense_w, W.dense_b, 768, tmp, 768, 0), st);
+    gemm(L, L, ctx, 768, 768, W.dense_w, &W.t_dense, W.dense_b, 768, tmp, 768, 0);
     LnArgs ln;
     ln.x = h; ln.ldx = 768; ln.res = tmp; ln.ldr = 768; ln.w = W.attn_lnw; ln.b = W.attn_lnb;
     ln.eps = 1e-12f; ln.out = h1; ln.ldo = 768; ln.off = L.d_off; ln.len = L.d_len; ln.B = B;
     ln.max_len = L.max_len; ln.C = 768;
     launch_layernorm(ln, st);
-    ConvArgs f1 = gemm_args(L, h1, 768, 768, W.ffn_w, W.ffn_b, 2048, ff, 2048, 0);
-    f1.eact = ACT_GELU_NEW;
-    launch_conv_f32(f1, st);
-    launch_conv_f32(gemm_args(L, ff, 2048, 2048, W.ffo_w, W.ffo_b, 768, tmp, 768, 0), st);
+    gemm(L, L, h1, 768, 768, W.ffn_w, &W.t_ffn, W.ffn_b, 2048, ff, 2048, 0, ACT_GELU_NEW);
+    gemm(L, L, ff, 2048, 2048, W.ffo_w, &W.t_ffo, W.ffo_b, 768, tmp, 768, 0);
     ln.x = tmp; ln.res = h1; ln.w = W.full_lnw; ln.b = W.full_lnb; ln.out = h;
     launch_layernorm(ln, st);
   }
@@ -103,13 +135,13 @@ void Model::token_phase(Run& r) {
   float* xb = A.alloc<float>(R * 640);
   float* xp = A.alloc<float>(R * 2048);
   float* lo = A.alloc<float>(R * 512);
-  launch_conv_f32(gemm_args(L, h, 768, 768, W.benc_w, W.benc_b, 512, xa, 640, 0), st);
+  gemm(L, L, h, 768, 768, W.benc_w, &W.t_benc, W.benc_b, 512, xa, 640, 0);
   capture("d_en", xa, 640, 0, 512, L, 0);
   launch_bcast_cols(d_styles_, 256, 128, 128, xa, 640, 512, L.d_off, L.d_len, B, L.max_len, st);
   launch_bcast_cols(d_styles_, 256, 128, 128, xb, 640, 512, L.d_off, L.d_len, B, L.max_len, st);
   float* cur = xa; float* nxt = xb;
   for (int i = 0; i < 3; i++) {
-    launch_conv_f32(gemm_args(L, cur, 640, 640, W.dur_lstm[i].wih, W.dur_lstm[i].bias, 2048, xp, 2048, 0), st);
+    gemm(L, L, cur, 640, 640, W.dur_lstm[i].wih, &W.dur_lstm[i].t_ih, W.dur_lstm[i].bias, 2048, xp, 2048, 0);
     launch_lstm(xp, W.dur_lstm[i].whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
     LnArgs ln;
     ln.x = lo; ln.ldx = 512; ln.ada = r.sty_pro; ln.ada_ld = W.sty_pro_n; ln.ada_off = W.dur_ada[i];
@@ -122,11 +154,11 @@ void Model::token_phase(Run& r) {
   capture("d", r.d, 640, 0, 640, L, 0);
 
   // ---- duration head (A.1, K4)
-  launch_conv_f32(gemm_args(L, r.d, 640, 640, W.pred_lstm.wih, W.pred_lstm.bias, 2048, xp, 2048, 0), st);
+  gemm(L, L, r.d, 640, 640, W.pred_lstm.wih, &W.pred_lstm.t_ih, W.pred_lstm.bias, 2048, xp, 2048, 0);
   launch_lstm(xp, W.pred_lstm.whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
   capture("dur_lstm", lo, 512, 0, 512, L, 0);
   float* logits = A.alloc<float>(R * 50);
-  launch_conv_f32(gemm_args(L, lo, 512, 512, W.durp_w, W.durp_b, 50, logits, 50, 0), st);
+  gemm(L, L, lo, 512, 512, W.durp_w, &W.t_durp, W.durp_b, 50, logits, 50, 0);
   capture("dur_logits", logits, 50, 0, 50, L, 0);
   r.pred_dur = A.alloc<int>(R);
   float* durf = A.alloc<float>(R);
@@ -147,19 +179,18 @@ void Model::token_phase(Run& r) {
   r.t_en = A.alloc<float>(R * 512);
   launch_embed_rows(d_ids_, W.temb, 512, ta, 512, L.d_off, L.d_len, B, L.max_len, st);
   for (int i = 0; i < 3; i++) {
-    ConvArgs c = gemm_args(L, ta, 512, 512, W.tcnn_w[i], W.tcnn_b[i], 512, tb, 512, 0);
-    c.ks = 5; c.pad = 2;
-    launch_conv_f32(c, st);
+    gemm(L, L, ta, 512, 512, W.tcnn_w[i], &W.t_tcnn[i], W.tcnn_b[i], 512, tb, 512, 0, ACT_NONE, 5, 2);
     LnArgs ln;
     ln.x = tb; ln.ldx = 512; ln.w = W.tln_g[i]; ln.b = W.tln_b[i]; ln.eps = 1e-5f; ln.slope = 0.2f;
     ln.out = ta; ln.ldo = 512; ln.off = L.d_off; ln.len = L.d_len; ln.B = B; ln.max_len = L.max_len;
     ln.C = 512;
     launch_layernorm(ln, st);
   }
-  launch_conv_f32(gemm_args(L, ta, 512, 512, W.te_lstm.wih, W.te_lstm.bias, 2048, xp, 2048, 0), st);
+  gemm(L, L, ta, 512, 512, W.te_lstm.wih, &W.te_lstm.t_ih, W.te_lstm.bias, 2048, xp, 2048, 0);
   launch_lstm(xp, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, st);
   capture("t_en", r.t_en, 512, 0, 512, L, 0);
 
+  split_hi_ = split_lo_ = nullptr; split_cap_ = 0;
   // ---- the one mid-pipeline host sync: frame counts decide every later launch shape
   r.T.resize(B);
   pred_dur_h_.resize(R);
@@ -216,18 +247,14 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
             w.up ? 1 : 0, 0.70710678118654752440f, false);
     return;
   }
+  // fp32-grade path (SIMT fp32, or split-TF32 tensor cores for the F0/N predictor blocks)
   if (w.up) {
     float* p = A.alloc<float>((size_t)Lout.rows * w.ci);
     launch_pool_up(x, ldx, sc1, sh1, 0.2f, w.poolw, w.poolb, w.ci, p, w.ci, Lin.d_off, Lin.d_len,
                    Lout.d_off, B, Lin.max_len, st);
-    ConvArgs c = gemm_args(Lout, p, w.ci, w.ci, w.w1, w.b1, w.co, t, w.co, 0);
-    c.ks = 3; c.pad = 1;
-    launch_conv_f32(c, st);
+    gemm(Lout, Lout, p, w.ci, w.ci, w.w1, &w.s1, w.b1, w.co, t, w.co, 0, ACT_NONE, 3, 1);
   } else {
-    ConvArgs c = gemm_args(Lin, x, ldx, w.ci, w.w1, w.b1, w.co, t, w.co, 0);
-    c.ks = 3; c.pad = 1;
-    c.pscale = sc1; c.pshift = sh1; c.pld = w.ci; c.pact = ACT_LRELU; c.pslope = 0.2f;
-    launch_conv_f32(c, st);
+    gemm(Lin, Lin, x, ldx, w.ci, w.w1, &w.s1, w.b1, w.co, t, w.co, 0, ACT_NONE, 3, 1, sc1, sh1, ACT_LRELU, 0.2f);
   }
   launch_colstats(t, w.co, w.co, part, Lout.d_off, Lout.d_len, B, Lout.max_len, st);
   launch_adain_coef(part, w.co, Lout.max_len, Lout.d_len, sty, sld, w.sty2, 1e-5f, sc2, sh2, B, st);
@@ -235,15 +262,11 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
   const float* sc = x; int ldsc = ldx;
   if (w.w1x1) {
     float* s = A.alloc<float>((size_t)Lin.rows * w.co);
-    launch_conv_f32(gemm_args(Lin, x, ldx, w.ci, w.w1x1, nullptr, w.co, s, w.co, 0), st);
+    gemm(Lin, Lin, x, ldx, w.ci, w.w1x1, &w.s1x1, nullptr, w.co, s, w.co, 0);
     sc = s; ldsc = w.co;
   }
-  ConvArgs c2 = gemm_args(Lout, t, w.co, w.co, w.w2, w.b2, w.co, out, ldo, ocol);
-  c2.ks = 3; c2.pad = 1;
-  c2.pscale = sc2; c2.pshift = sh2; c2.pld = w.co; c2.pact = ACT_LRELU; c2.pslope = 0.2f;
-  c2.res = sc; c2.ldr = ldsc; c2.rcol = 0; c2.res_off = Lin.d_off; c2.res_shift = w.up ? 1 : 0;
-  c2.oscale = 0.70710678118654752440f;
-  launch_conv_f32(c2, st);
+  gemm(Lout, Lout, t, w.co, w.co, w.w2, &w.s2, w.b2, w.co, out, ldo, ocol, ACT_NONE, 3, 1, sc2, sh2, ACT_LRELU, 0.2f,
+       sc, ldsc, &Lin, w.up ? 1 : 0, 0.70710678118654752440f);
 }
 
 // AdaINResBlock1 (A.9): three (AdaIN -> Snake -> dilated conv -> AdaIN -> Snake -> conv) + residual
@@ -359,7 +382,10 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   // ---- F0 / N predictor (A.7)
   float* xp = A.alloc<float>((size_t)FR.rows * 2048);
   float* shd = A.alloc<float>((size_t)FR.rows * 512);
-  launch_conv_f32(gemm_args(FR, en, 640, 640, W.shared_lstm.wih, W.shared_lstm.bias, 2048, xp, 2048, 0), st);
+  split_cap_ = std::max((size_t)FR.rows * 640, (size_t)FR2.rows * 512);
+  split_hi_ = A.alloc<float>(split_cap_);
+  split_lo_ = A.alloc<float>(split_cap_);
+  gemm(FR, FR, en, 640, 640, W.shared_lstm.wih, &W.shared_lstm.t_ih, W.shared_lstm.bias, 2048, xp, 2048, 0);
   launch_lstm(xp, W.shared_lstm.whhT, shd, 512, 0, FR.d_off, FR.d_len, B, st);
   capture("shared_lstm", shd, 512, 0, 512, FR, b0);
   float* curves[2];
@@ -378,6 +404,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
                               k == 0 ? W.f0proj_b : W.nproj_b, 1, curves[k], 1, 0), st);
   }
   float* f0 = curves[0]; float* nc = curves[1];
+  split_hi_ = split_lo_ = nullptr; split_cap_ = 0;   // decoder / generator use the bf16 operand path
   if (!dry && b0 == 0) {
     if (!inj_f0_.empty()) {
       if ((int)inj_f0_.size() != FR2.len[0]) throw ArgError("inject F0: length != 2T of item 0");

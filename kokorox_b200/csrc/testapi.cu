@@ -111,6 +111,55 @@ KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const fl
   });
 }
 
+static inline float host_tf32(float f) {   // cvt.rna.tf32.f32
+  uint32_t u; memcpy(&u, &f, 4);
+  u = (u + 0x1000u) & ~0x1FFFu;
+  float r; memcpy(&r, &u, 4);
+  return r;
+}
+
+KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                               int Co, int ks, int dil, int pad, int nprod, int eact, float* out) {
+  return run(device, [&] {
+    const int Cpad = (Ci + 63) & ~63;
+    const int off = kGapRows, rows_total = (off + L + kGapRows + 7) & ~7;
+    std::vector<float> whi((size_t)Co * ks * Cpad, 0.f), wlo((size_t)Co * ks * Cpad, 0.f);
+    for (int o = 0; o < Co; o++)
+      for (int k = 0; k < ks; k++)
+        for (int c = 0; c < Ci; c++) {
+          const float f = w[((size_t)o * ks + k) * Ci + c];
+          const float hi = host_tf32(f);
+          whi[((size_t)o * ks + k) * Cpad + c] = hi;
+          wlo[((size_t)o * ks + k) * Cpad + c] = host_tf32(f - hi);
+        }
+    std::vector<float> xin((size_t)rows_total * Ci, 0.f);
+    memcpy(xin.data() + (size_t)off * Ci, x, (size_t)L * Ci * 4);
+    DevBuf dx(xin.data(), xin.size() * 4), dwh(whi.data(), whi.size() * 4), dwl(wlo.data(), wlo.size() * 4);
+    DevBuf db(bias, bias ? Co * 4 : 0), dout(nullptr, (size_t)L * Co * 4);
+    DevBuf dah(nullptr, (size_t)rows_total * Cpad * 4), dal(nullptr, (size_t)rows_total * Cpad * 4);
+    KKX_CUDA(cudaMemset(dah.p, 0xFF, (size_t)rows_total * Cpad * 4));
+    KKX_CUDA(cudaMemset(dal.p, 0xFF, (size_t)rows_total * Cpad * 4));
+    int meta[4] = {off, L, 0, 0};
+    DevBuf dm(meta, sizeof meta);
+    launch_apply_tf32(dx.as<float>(), Ci, Ci, nullptr, nullptr, ACT_NONE, 0.f, dah.as<float>(), dal.as<float>(), Cpad,
+                      rows_total, dm.as<int>(), dm.as<int>() + 1, 1, L, 0);
+    alignas(64) unsigned char tA[128], tA2[128], tB[128], tB2[128];
+    make_tmap_f32(tA, dah.p, Cpad, rows_total, Cpad, 128);
+    make_tmap_f32(tA2, dal.p, Cpad, rows_total, Cpad, 128);
+    make_tmap_f32(tB, dwh.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, tc_box_n_tf32(Co));
+    make_tmap_f32(tB2, dwl.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, tc_box_n_tf32(Co));
+    TcConvArgs a;
+    a.tmA = tA; a.tmA2 = tA2; a.tmB = tB; a.tmB2 = tB2; a.tf32 = 1; a.nprod = nprod; a.eact = eact;
+    a.Cpad = Cpad; a.Ci = Ci; a.Co = Co; a.ks = ks; a.dil = dil; a.pad = pad;
+    a.in_off = dm.as<int>(); a.m_len = dm.as<int>() + 1; a.max_m = L; a.B = 1; a.sum_m = L;
+    a.bias = bias ? db.as<float>() : nullptr;
+    a.out = dout.as<float>(); a.ldo = Co; a.ocol = 0; a.out_off = dm.as<int>() + 2; a.ors = 1; a.oro = 0;
+    launch_conv_tc(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)L * Co * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out) {
   return run(device, [&] {
     DevBuf dx(xproj, (size_t)N * 2048 * 4), dw(whhT, (size_t)2 * 256 * 1024 * 4), dout(nullptr, (size_t)N * 512 * 4);
@@ -119,6 +168,17 @@ KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int
     launch_lstm(dx.as<float>(), dw.as<float>(), dout.as<float>(), 512, 0, dm.as<int>(), dm.as<int>() + 1, 1, 0);
     KKX_CUDA(cudaDeviceSynchronize());
     KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)N * 512 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whhT, int B, const int* off,
+                                const int* len, int rows, float* out) {
+  return run(device, [&] {
+    DevBuf dx(xproj, (size_t)rows * 2048 * 4), dw(whhT, (size_t)2 * 256 * 1024 * 4), dout(out, (size_t)rows * 512 * 4);
+    DevBuf doff(off, B * 4), dlen(len, B * 4);
+    launch_lstm(dx.as<float>(), dw.as<float>(), dout.as<float>(), 512, 0, doff.as<int>(), dlen.as<int>(), B, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)rows * 512 * 4, cudaMemcpyDeviceToHost));
   });
 }
 

@@ -123,6 +123,38 @@ def test_lstm_matches_torch(lib, N):
     np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B", [2, 9, 20, 40, 64])
+def test_lstm_ragged_batch_groups(lib, B):
+    # the persistent cluster kernel processes G = 1/2/4/8 items per cluster; ragged lengths
+    torch.manual_seed(B)
+    m = torch.nn.LSTM(512, 256, 1, batch_first=True, bidirectional=True).eval()
+    rng = np.random.default_rng(B)
+    lens = rng.integers(1, 90, B).astype(np.int32)
+    offs = np.zeros(B, np.int32)
+    o = 3
+    for b in range(B):
+        offs[b] = o
+        o += int(lens[b]) + 5
+    rows = o
+    xproj = np.zeros((rows, 2048), np.float32)
+    ref = np.zeros((rows, 512), np.float32)
+    whh = np.zeros((2, 256, 1024), np.float32)
+    with torch.no_grad():
+        for d, sfx in enumerate(("", "_reverse")):
+            whh[d] = getattr(m, "weight_hh_l0" + sfx).numpy().T
+        for b in range(B):
+            x = torch.randn(1, int(lens[b]), 512)
+            ref[offs[b]:offs[b] + lens[b]] = m(x)[0][0].numpy()
+            for d, sfx in enumerate(("", "_reverse")):
+                wih, bb = getattr(m, "weight_ih_l0" + sfx), getattr(m, "bias_ih_l0" + sfx) + getattr(m, "bias_hh_l0" + sfx)
+                xproj[offs[b]:offs[b] + lens[b], d * 1024:(d + 1) * 1024] = (x[0] @ wih.T + bb).numpy()
+    out = np.zeros((rows, 512), np.float32)
+    rc = lib.kkx_test_lstm_batch(0, fp(xproj), fp(whh), B, offs.ctypes.data_as(C.POINTER(C.c_int)),
+                                 lens.ctypes.data_as(C.POINTER(C.c_int)), rows, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
+
+
 @pytest.mark.parametrize("N", [3, 52, 130, 512])
 def test_attention_matches_torch(lib, N):
     qkv = rnd(N, 2304, seed=N)
@@ -209,3 +241,25 @@ def test_tc_conv_fused_prologue_epilogue(lib):
     got = run_conv_tc(lib, x, np.ascontiguousarray(w.transpose(0, 2, 1)), b, 1, 3, L, L, pscale=sc, pshift=sh, pact=2,
                       palpha=alpha, res=res, oscale=1 / 3, accumulate=1, out_init=init)
     np.testing.assert_allclose(got, ref, atol=2e-3, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------- split-TF32 tensor-core GEMM
+@pytest.mark.parametrize("L,Ci,Co,k", [(512, 768, 2304, 1), (300, 2048, 768, 1), (200, 128, 768, 1), (140, 640, 2048, 1),
+                                       (333, 512, 512, 5), (77, 512, 50, 1), (260, 256, 256, 3)])
+@pytest.mark.parametrize("nprod", [3, 4])
+def test_split_tf32_gemm_is_fp32_grade(lib, L, Ci, Co, k, nprod):
+    x, w, b = rnd(L, Ci, seed=21), rnd(Co, Ci, k, seed=22, scale=1 / np.sqrt(Ci * k)), rnd(Co, seed=23)
+    pad = (k - 1) // 2
+    ref64 = F.conv1d(torch.from_numpy(x.T.astype(np.float64))[None], torch.from_numpy(w.astype(np.float64)),
+                     torch.from_numpy(b.astype(np.float64)), padding=pad)[0].T.numpy()
+    ref32 = F.conv1d(torch.from_numpy(x.T)[None], torch.from_numpy(w), torch.from_numpy(b), padding=pad)[0].T.numpy()
+    out = np.zeros((L, Co), np.float32)
+    rc = lib.kkx_test_conv_tf32(0, fp(x), L, Ci, fp(np.ascontiguousarray(w.transpose(0, 2, 1))), fp(b), Co, k, 1, pad,
+                                nprod, 0, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    e_tc = np.abs(out - ref64).max()
+    e_32 = np.abs(ref32 - ref64).max()
+    rms_tc = np.sqrt(((out - ref64) ** 2).mean())
+    rms_32 = np.sqrt(((ref32 - ref64) ** 2).mean())
+    print(f"split-TF32 x{nprod}: max err {e_tc:.3e} (torch fp32 {e_32:.3e}), rms err {rms_tc:.3e} (fp32 {rms_32:.3e})")
+    assert e_tc < 2e-5 and rms_tc < 8 * max(rms_32, 1e-8)
