@@ -37,8 +37,9 @@ struct LaunchStats {
   // per-kernel timing (kkx_profile_enable): one event after every launch on the in-order stream;
   // the gap between consecutive events is attributed to the launch in between
   bool profile = false;
+  bool detail = false;                   // per-shape kernel names (KKX_PROFILE_DETAIL=1)
   std::vector<cudaEvent_t> events;       // pool, events[0] = start of run
-  std::vector<const char*> names;        // names[i] = kernel launched before events[i+1]
+  std::vector<std::string> names;        // names[i] = kernel launched before events[i+1]
   size_t n_events = 0;
   double conv_flops = 0;                 // algorithmic FLOPs issued through the shifted-GEMM kernels
   cudaEvent_t next_event() {

@@ -130,7 +130,10 @@ void launch_conv_f32(const ConvArgs& a, cudaStream_t st) {
     dim3 g((a.max_m + 127) / 128, (a.Co + 31) / 32, a.B);
     conv_f32_kernel<128, 32><<<g, 256, 0, st>>>(a);
   }
-  post_launch("conv_f32", st);
+  if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
+    char nm[96]; snprintf(nm, sizeof nm, "conv_f32[ci%d co%d k%d s%d m%lld]", a.Ci, a.Co, a.ks, a.stride, a.sum_m);
+    post_launch(nm, st);
+  } else post_launch("conv_f32", st);
 }
 
 // ------------------------------------------------------------------------------------------

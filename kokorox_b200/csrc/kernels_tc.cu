@@ -306,39 +306,61 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         *reinterpret_cast<uint4*>(buf + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (n0 + c < a.Co) {
+        // thread t writes columns c4..c4+3 (c4 = 4*(t&7), fixed) of rows (t>>3) + 16*i, i = 0..7.
+        // Loads are issued as one batch (8 residual + 8 accumulate float4 in flight) before any
+        // arithmetic so the epilogue is bandwidth- rather than latency-bound.
+        const int t = threadIdx.x - 64;
+        const int c4 = (t & 7) << 2;
+        const int n = n0 + c + c4;
+        const bool col_ok = n < a.Co;
+        const bool vec = a.vec4 && (n + 3 < a.Co);
+        float4 ov[8], rv[8], pv[8];
+        float* opp[8];
+        bool ok[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const int idx = i * 128 + (threadIdx.x - 64);
-          const int row = idx >> 3, c4 = (idx & 7) << 2;
+          const int row = (t >> 3) + 16 * i;
           const int mm = m0 + row;
-          const int n = n0 + c + c4;
-          if (mm < mlen && n < a.Co) {
-            float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-            const int orow = mm * a.ors + a.oro;
-            float* op = a.out + ((size_t)(out_off + orow) * a.ldo + a.ocol + n);
-            const float* rp = a.res ? a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n) : nullptr;
-            if (a.vec4 && n + 3 < a.Co) {
-              if (a.bias) { const float4 bb = *reinterpret_cast<const float4*>(a.bias + n); o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w; }
-              if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
-              if (rp) { const float4 r = *reinterpret_cast<const float4*>(rp); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-              o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
-              if (a.accumulate) { const float4 pv = *reinterpret_cast<const float4*>(op); o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w; }
-              *reinterpret_cast<float4*>(op) = o;
-            } else {
-              const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                if (n + e < a.Co) {
-                  float t = ov[e];
-                  if (a.bias) t += a.bias[n + e];
-                  if (a.eact == ACT_GELU_NEW) t = gelu_new_f(t);
-                  if (rp) t += rp[e];
-                  t *= a.oscale;
-                  if (a.accumulate) t += op[e];
-                  op[e] = t;
-                }
-              }
+          ok[i] = col_ok && mm < mlen;
+          ov[i] = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
+          const int orow = mm * a.ors + a.oro;
+          opp[i] = a.out + ((size_t)(out_off + orow) * a.ldo + a.ocol + n);
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[i]) {
+            if (a.res) {
+              const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
+              if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+              else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
             }
+            if (a.accumulate) {
+              if (vec) pv[i] = *reinterpret_cast<const float4*>(opp[i]);
+              else { pv[i].x = opp[i][0]; if (n + 1 < a.Co) pv[i].y = opp[i][1]; if (n + 2 < a.Co) pv[i].z = opp[i][2]; if (n + 3 < a.Co) pv[i].w = opp[i][3]; }
+            }
+          }
+        }
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias && col_ok) {
+          if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+          else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (!ok[i]) continue;
+          float4 o = ov[i];
+          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+          o.x = (o.x + rv[i].x) * a.oscale + pv[i].x;
+          o.y = (o.y + rv[i].y) * a.oscale + pv[i].y;
+          o.z = (o.z + rv[i].z) * a.oscale + pv[i].z;
+          o.w = (o.w + rv[i].w) * a.oscale + pv[i].w;
+          if (vec) {
+            *reinterpret_cast<float4*>(opp[i]) = o;
+          } else {
+            opp[i][0] = o.x;
+            if (n + 1 < a.Co) opp[i][1] = o.y;
+            if (n + 2 < a.Co) opp[i][2] = o.z;
+            if (n + 3 < a.Co) opp[i][3] = o.w;
           }
         }
       }
@@ -381,7 +403,10 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
     if (a.Co > 64) launch_tc<128, 3, 1>(a, st);
     else launch_tc<64, 4, 1>(a, st);
-    post_launch("conv_tc_tf32x3", st);
+    if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
+      char nm[96]; snprintf(nm, sizeof nm, "conv_tc_tf32x3[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);
+      post_launch(nm, st);
+    } else post_launch("conv_tc_tf32x3", st);
     return;
   }
   // smem per CTA ~97 KB in every configuration -> two CTAs per SM, so one tile's epilogue overlaps
@@ -389,7 +414,10 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
   else if (a.Co > 64) launch_tc<128, 3, 0>(a, st);
   else launch_tc<64, 4, 0>(a, st);
-  post_launch("conv_tc", st);
+  if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
+    char nm[96]; snprintf(nm, sizeof nm, "conv_tc[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);
+    post_launch(nm, st);
+  } else post_launch("conv_tc", st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -402,7 +430,8 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope, float 
   if (act == ACT_SNAKE) { const float s = __sinf(al * v); return v + __fdividef(s * s, al); }
   return v;
 }
-constexpr int kApplyRows = 16;  // rows per CTA
+constexpr int kApplyRows = 16;  // rows per CTA (tf32 producer)
+constexpr int kApplyRowsB = 64; // rows per CTA (bf16 producer)
 __global__ void __launch_bounds__(256) apply_bf16_kernel(const float* __restrict__ x, int ldx, int C,
                                                          const float* scale, const float* shift,
                                                          int act, float slope, const float* alpha,
@@ -414,40 +443,46 @@ __global__ void __launch_bounds__(256) apply_bf16_kernel(const float* __restrict
   // whose own leading gap covers the alignment slack); the last item zeroes up to rows_total
   const int r_begin = o - kGapRows;
   const int r_end = (b == (int)gridDim.y - 1) ? rows_total : o + L + kGapRows;
-  const int rb = r_begin + blockIdx.x * kApplyRows;
+  const int rb = r_begin + blockIdx.x * kApplyRowsB;
   if (rb >= r_end) return;
-  const int re = min(r_end, rb + kApplyRows);
-  const float* sc = scale ? scale + (size_t)b * C : nullptr;
-  const float* sh = shift ? shift + (size_t)b * C : nullptr;
-  const int cq = Cpad >> 2;  // column quads
-  const int total = (re - rb) * cq;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int r = rb + i / cq;
-    const int c = (i % cq) << 2;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (r >= o && r < o + L && c < C) {
-      const float* xp = x + (size_t)r * ldx + c;
-      if (vec_ok && c + 3 < C) {
-        const float4 t = *reinterpret_cast<const float4*>(xp);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else {
+  const int re = min(r_end, rb + kApplyRowsB);
+  const int cq = Cpad >> 2;                 // column quads per row
+  // thread -> (column quad, row lane); a thread keeps its quad's coefficients in registers
+  const int lanes = cq >= 256 ? 1 : 256 / cq;
+  for (int q0 = 0; q0 < cq; q0 += 256) {
+    const int qi = q0 + (cq >= 256 ? threadIdx.x : threadIdx.x % cq);
+    const int rl = cq >= 256 ? 0 : threadIdx.x / cq;
+    if (qi >= cq || rl >= lanes) continue;
+    const int c = qi << 2;
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f}, al[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
-        for (int e = 0; e < 4; e++) if (c + e < C) v[e] = xp[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        if (c + e < C) {
-          float t = v[e];
-          if (sc) t = fmaf(t, sc[c + e], sh[c + e]);
-          v[e] = apply_act(t, act, slope, alpha ? alpha[c + e] : 1.f);
-        }
+    for (int e = 0; e < 4; e++) {
+      if (c + e < C) {
+        if (scale) { sc[e] = scale[(size_t)b * C + c + e]; sh[e] = shift[(size_t)b * C + c + e]; }
+        if (alpha) al[e] = alpha[c + e];
       }
     }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(out + (size_t)r * Cpad + c) = pk;
+    for (int r = rb + rl; r < re; r += lanes) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r >= o && r < o + L && c < C) {
+        const float* xp = x + (size_t)r * ldx + c;
+        if (vec_ok && c + 3 < C) {
+          const float4 t = *reinterpret_cast<const float4*>(xp);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; e++) if (c + e < C) v[e] = xp[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          v[e] = (c + e < C) ? apply_act(fmaf(v[e], sc[e], sh[e]), act, slope, al[e]) : 0.f;
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out + (size_t)r * Cpad + c) = pk;
+    }
   }
 }
 
@@ -456,11 +491,48 @@ void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const
                        const int* off, const int* len, int B, int max_len, cudaStream_t st) {
   if (g_dry_run) return;
   const int rows = max_len + 2 * kGapRows + 8;
-  dim3 g((rows + kApplyRows - 1) / kApplyRows, B);
+  dim3 g((rows + kApplyRowsB - 1) / kApplyRowsB, B);
   const int vec_ok = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
   apply_bf16_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, alpha, (__nv_bfloat16*)out, Cpad,
                                        rows_total, off, len, vec_ok);
   post_launch("apply_bf16", st);
+}
+
+// im2col operand producer for strided convs with few channels (noise_convs[0]: 22 ch, k12, s6, p3):
+// out[m, tap*C + c] = in[m*stride + tap - pad, c] (0 outside the item), bf16 [rows_out_total, Cpad].
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restrict__ in, int ldi, int C, int ks,
+                                                          int stride, int pad, __nv_bfloat16* out, int Cpad,
+                                                          int rows_total, const int* in_off, const int* in_len,
+                                                          const int* out_off, const int* out_len) {
+  const int b = blockIdx.y;
+  const int Lo = out_len[b], oo = out_off[b], Li = in_len[b], io = in_off[b];
+  const int r_begin = oo - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : oo + Lo + kGapRows;
+  const int rb = r_begin + blockIdx.x * 8;
+  if (rb >= r_end) return;
+  const int re = min(r_end, rb + 8);
+  const int total = (re - rb) * Cpad;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = rb + i / Cpad, k = i % Cpad;
+    float v = 0.f;
+    const int m = r - oo;
+    if (m >= 0 && m < Lo && k < ks * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int ir = m * stride + tap - pad;
+      if (ir >= 0 && ir < Li) v = in[(size_t)(io + ir) * ldi + c];
+    }
+    out[(size_t)r * Cpad + k] = __float2bfloat16_rn(v);
+  }
+}
+void launch_im2col_bf16(const float* in, int ldi, int C, int ks, int stride, int pad, void* out, int Cpad,
+                        int rows_total, const int* in_off, const int* in_len, const int* out_off,
+                        const int* out_len, int B, int max_out_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  const int rows = max_out_len + 2 * kGapRows + 8;
+  dim3 g((rows + 7) / 8, B);
+  im2col_bf16_kernel<<<g, 256, 0, st>>>(in, ldi, C, ks, stride, pad, (__nv_bfloat16*)out, Cpad, rows_total,
+                                        in_off, in_len, out_off, out_len);
+  post_launch("im2col_bf16", st);
 }
 
 // Split-TF32 operand producer: hi = rna_tf32(v), lo = rna_tf32(v - hi), two fp32 planes

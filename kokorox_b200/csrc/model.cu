@@ -75,6 +75,8 @@ Model::Model(const std::string& weights_path, int device) : device_(device) {
   KKX_CUDA(cudaEventCreate(&ev1_));
   const char* dbg = getenv("KKX_DEBUG_SYNC");
   stats.check_each = dbg && dbg[0] == '1';
+  const char* det = getenv("KKX_PROFILE_DETAIL");
+  stats.detail = det && det[0] == '1';
   WeightFile wf(weights_path);
   load_weights(wf);
 }
@@ -374,6 +376,11 @@ void Model::load_weights(const WeightFile& wf) {
   UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0, W.tups0); W.ups0_b = U(G + "ups.0.bias");
   UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1, W.tups1); W.ups1_b = U(G + "ups.1.bias");
   W.post_w = CW(G + "conv_post.weight", 22, 128, 7); W.post_b = U(G + "conv_post.bias");
+  W.t_post = make_tc(convCoKsCi(wf, G + "conv_post.weight", 22, 128, 7), 22, 7, 128);
+  W.t_nc1 = make_tc(convCoKsCi(wf, G + "noise_convs.1.weight", 128, 22, 1), 128, 1, 22);
+  // noise_convs[0] as a 1-tap GEMM over the im2col operand: K index = tap*22 + c
+  W.t_nc0 = make_tc(convCoKsCi(wf, G + "noise_convs.0.weight", 256, 22, 12), 256, 1, 12 * 22);
+  W.t_asr = make_tc(convCoKsCi(wf, "decoder.asr_res.0.weight", 64, 512, 1), 64, 1, 512);
 
   // ---- build the two style FC tables: W^T [128][n], bias [n]
   auto build = [&](const std::vector<std::pair<std::string, int>>& lst, int total, float*& dw, float*& db) {

@@ -80,6 +80,7 @@ struct Weights {
   ArbW nres[2], res[6];
   std::vector<float*> ups0, ups1;  // per-phase [2][Ci][Co]
   std::vector<TcW> tups0, tups1;   // per-phase bf16 [Co][2][Ci]
+  TcW t_post, t_nc0, t_nc1, t_asr; // conv_post, noise_convs (nc0 as an im2col GEMM, K = 12*22), asr_res
   float *ups0_b, *ups1_b, *post_w, *post_b;
   // style FC tables (all AdaIN / AdaLN fcs of one style half concatenated)
   float *sty_pro_w, *sty_pro_b, *sty_dec_w, *sty_dec_b;

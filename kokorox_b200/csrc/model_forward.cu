@@ -467,7 +467,12 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   float* w0 = A.alloc<float>(n20);
   float* t0 = A.alloc<float>(n20);
   float* acc0 = A.alloc<float>(n20);
-  {
+  if (opt.precision == 1) {
+    void* col = A.alloc_bytes((size_t)G20.rows * W.t_nc0.Cpad * 2);
+    launch_im2col_bf16(har, 24, 22, 12, 6, 3, col, W.t_nc0.Cpad, G20.rows, G120.d_off, G120.d_len, G20.d_off,
+                       G20.d_len, B, G20.max_len, st);
+    tc_conv(A, col, G20.rows, W.t_nc0, 1, 0, G20, G20, W.nc0_b, xs0, 256, 0, G20, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+  } else {
     ConvArgs c = gemm_args(G20, har, 24, 22, W.nc0_w, W.nc0_b, 256, xs0, 256, 0);
     c.in_off = G120.d_off; c.in_len = G120.d_len;
     c.ks = 12; c.stride = 6; c.pad = 3;
@@ -507,7 +512,14 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   float* w1 = A.alloc<float>(n120);
   float* t1 = A.alloc<float>(n120);
   float* acc1 = A.alloc<float>(n120);
-  launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st);
+  if (opt.precision == 1) {
+    void* hb = A.alloc_bytes((size_t)G120.rows * W.t_nc1.Cpad * 2);
+    launch_apply_bf16(har, 24, 22, nullptr, nullptr, ACT_NONE, 0.f, nullptr, hb, W.t_nc1.Cpad, G120.rows, G120.d_off,
+                      G120.d_len, B, G120.max_len, st);
+    tc_conv(A, hb, G120.rows, W.t_nc1, 1, 0, G120, G120, W.nc1_b, xs1, 128, 0, G120, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+  } else {
+    launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st);
+  }
   arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
   capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
   void* abf = nullptr;
@@ -539,7 +551,12 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
 
   // ---- head (K11)
   float* cp = A.alloc<float>((size_t)G120.rows * 24);
-  {
+  if (opt.precision == 1) {
+    void* pb = A.alloc_bytes((size_t)G120.rows * 128 * 2);
+    launch_apply_bf16(acc1, 128, 128, nullptr, nullptr, ACT_LRELU, 0.01f, nullptr, pb, 128, G120.rows, G120.d_off,
+                      G120.d_len, B, G120.max_len, st);
+    tc_conv(A, pb, G120.rows, W.t_post, 1, 3, G120, G120, W.post_b, cp, 24, 0, G120, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+  } else {
     ConvArgs c = gemm_args(G120, acc1, 128, 128, W.post_w, W.post_b, 22, cp, 24, 0);
     c.ks = 7; c.pad = 3; c.pact = ACT_LRELU; c.pslope = 0.01f;
     launch_conv_f32(c, st);
