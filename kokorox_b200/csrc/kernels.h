@@ -49,6 +49,7 @@ struct TcConvArgs {
   float* out = nullptr; int ldo = 0; int ocol = 0; const int* out_off = nullptr; int ors = 1, oro = 0;
   const float* res = nullptr; int ldr = 0; int rcol = 0; const int* res_off = nullptr; int res_shift = 0;
   float oscale = 1.f; int accumulate = 0; int vec4 = 0;
+  int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);
 // out_map: 128-byte CUtensorMap storage (64-byte aligned).  bf16 [outer, inner], box [box_outer, 64].

@@ -529,35 +529,50 @@ void launch_stft(const float* x, const long long* s_off, float* har, int ldh, co
 __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int ldc,
                                                     const int* h_off, const int* h_len,
                                                     float* audio, const long long* s_off) {
-  constexpr int FR = 128, HALO = 3;
-  __shared__ float fr[FR + HALO + 2][20];  // windowed time frames f0-3 .. f0+129
+  constexpr int FR = 128, HALO = 3, NF = FR + HALO + 2;
+  __shared__ float spec[NF][22];           // (re, im) of the 11 bins of frames f0-3 .. f0+129
+  __shared__ float fr[NF][20];             // windowed time frames
+  // twiddles / window in shared memory: the lookups below are indexed per lane (j varies across a
+  // warp), which would serialise on the constant cache
+  __shared__ float s_cos[20], s_sin[20], s_win[20];
+  if (threadIdx.x < 20) {
+    s_cos[threadIdx.x] = c_cos20[threadIdx.x];
+    s_sin[threadIdx.x] = c_sin20[threadIdx.x];
+    s_win[threadIdx.x] = c_hann20[threadIdx.x];
+  }
   const int b = blockIdx.y;
   const int F = h_len[b];
   const int f0 = blockIdx.x * FR;
   if (f0 >= F) return;
   const long long S = (long long)(F - 1) * 5;
-  // phase 1: inverse DFT of frames f0-3 .. f0+FR+1  (133 frames x 20 samples)
-  for (int i = threadIdx.x; i < (FR + HALO + 2) * 20; i += 256) {
-    const int lf = i / 20, j = i % 20;
+  // phase 0: spectrum of each (frame, bin) once: mag = exp(x), phase = sin(x') -> mag*(cos, sin)
+  for (int i = threadIdx.x; i < NF * 11; i += 256) {
+    const int lf = i / 11, k = i % 11;
     const int f = f0 - HALO + lf;
-    float v = 0.f;
+    float re = 0.f, im = 0.f;
     if (f >= 0 && f < F) {
       const float* c = cp + (size_t)(h_off[b] + f) * ldc;
-      // bins 0 and 10: real part only
-      float acc = expf(c[0]) * cosf(sinf(c[11]));
-      const float x10 = expf(c[10]) * cosf(sinf(c[21]));
-      acc += (j & 1) ? -x10 : x10;
-#pragma unroll
-      for (int k = 1; k < 10; k++) {
-        const float mag = expf(c[k]);
-        float sn, cs;
-        sincosf(sinf(c[11 + k]), &sn, &cs);
-        const int m = (j * k) % 20;
-        acc += 2.0f * (mag * cs * c_cos20[m] - mag * sn * c_sin20[m]);
-      }
-      v = acc * (1.0f / 20.0f) * c_hann20[j];
+      const float mag = expf(c[k]);
+      float sn, cs;
+      sincosf(sinf(c[11 + k]), &sn, &cs);
+      re = mag * cs;
+      im = mag * sn;
     }
-    fr[lf][j] = v;
+    spec[lf][k] = re;
+    spec[lf][11 + k] = im;
+  }
+  __syncthreads();
+  // phase 1: one-sided inverse DFT (n = 20) + synthesis window
+  for (int i = threadIdx.x; i < NF * 20; i += 256) {
+    const int lf = i / 20, j = i % 20;
+    const float* sp = spec[lf];
+    float acc = sp[0] + ((j & 1) ? -sp[10] : sp[10]);   // bins 0 and 10: real part only
+#pragma unroll
+    for (int k = 1; k < 10; k++) {
+      const int m = (j * k) % 20;
+      acc += 2.0f * (sp[k] * s_cos[m] - sp[11 + k] * s_sin[m]);
+    }
+    fr[lf][j] = acc * (1.0f / 20.0f) * s_win[j];
   }
   __syncthreads();
   // phase 2: overlap-add.  Sample n covers untrimmed position p = n + 10; frames f with
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
       if (f < 0 || f >= F) continue;
       const int j = (int)(p - (long long)f * 5);
       acc += fr[f - (f0 - HALO)][j];
-      env += c_hann20[j] * c_hann20[j];
+      env += s_win[j] * s_win[j];
     }
     audio[s_off[b] + n] = acc / env;
   }

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
-            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+            if (!(a.debug & 2)) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
         } else {
           const int chain = it >> 1, j = chain % 3;
           const bool chain_start = (it & 1) == 0;
@@ -286,12 +286,35 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
       }
     }
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
     constexpr int PITCH = 36;               // floats per staged row (32 + 4 pad)
     float* stage_f = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)));
     const int out_off = a.out_off[b];
     const int res_off = a.res ? a.res_off[b] : 0;
+    // thread t writes columns c4..c4+3 (c4 = 4*(t&7), fixed) of rows (t>>3) + 16*i, i = 0..7, of
+    // every 32-column chunk.  Residual / accumulate operands of chunk c+1 are fetched while chunk c
+    // is processed, and those of chunk 0 before the accumulator is even complete, so their HBM
+    // latency hides behind the MMA main loop.
+    const int t = threadIdx.x - 64;
+    const int c4 = (t & 7) << 2;
+    auto fetch = [&](int c, float4* rv) {   // residual operand of chunk c for this thread's 8 rows
+      const int n = n0 + c + c4;
+      const bool vec = a.vec4 && (n + 3 < a.Co);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int mm = m0 + (t >> 3) + 16 * i;
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.res && n < a.Co && mm < mlen) {
+          const int orow = mm * a.ors + a.oro;
+          const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
+          if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+          else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+        }
+      }
+    };
+    float4 rv[8];
+    if (MODE == 0) fetch(0, rv);            // overlaps the whole MMA main loop
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
 #pragma unroll
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
@@ -304,66 +327,40 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(buf + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      if (MODE) fetch(c, rv);               // MODE 1 has no registers to spare for an early fetch
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (n0 + c < a.Co) {
-        // thread t writes columns c4..c4+3 (c4 = 4*(t&7), fixed) of rows (t>>3) + 16*i, i = 0..7.
-        // Loads are issued as one batch (8 residual + 8 accumulate float4 in flight) before any
-        // arithmetic so the epilogue is bandwidth- rather than latency-bound.
-        const int t = threadIdx.x - 64;
-        const int c4 = (t & 7) << 2;
-        const int n = n0 + c + c4;
-        const bool col_ok = n < a.Co;
+      const int n = n0 + c + c4;
+      if (n < a.Co) {
         const bool vec = a.vec4 && (n + 3 < a.Co);
-        float4 ov[8], rv[8], pv[8];
-        float* opp[8];
-        bool ok[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = (t >> 3) + 16 * i;
-          const int mm = m0 + row;
-          ok[i] = col_ok && mm < mlen;
-          ov[i] = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-          const int orow = mm * a.ors + a.oro;
-          opp[i] = a.out + ((size_t)(out_off + orow) * a.ldo + a.ocol + n);
-          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[i]) {
-            if (a.res) {
-              const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
-              if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
-              else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
-            }
-            if (a.accumulate) {
-              if (vec) pv[i] = *reinterpret_cast<const float4*>(opp[i]);
-              else { pv[i].x = opp[i][0]; if (n + 1 < a.Co) pv[i].y = opp[i][1]; if (n + 2 < a.Co) pv[i].z = opp[i][2]; if (n + 3 < a.Co) pv[i].w = opp[i][3]; }
-            }
-          }
-        }
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias && col_ok) {
+        if (a.bias) {
           if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
           else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          if (!ok[i]) continue;
-          float4 o = ov[i];
+          const int row = (t >> 3) + 16 * i;
+          const int mm = m0 + row;
+          if (mm >= mlen || (a.debug & 1)) continue;
+          float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
-          o.x = (o.x + rv[i].x) * a.oscale + pv[i].x;
-          o.y = (o.y + rv[i].y) * a.oscale + pv[i].y;
-          o.z = (o.z + rv[i].z) * a.oscale + pv[i].z;
-          o.w = (o.w + rv[i].w) * a.oscale + pv[i].w;
+          o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+          o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+          float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
           if (vec) {
-            *reinterpret_cast<float4*>(opp[i]) = o;
+            if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+            *reinterpret_cast<float4*>(op) = o;
           } else {
-            opp[i][0] = o.x;
-            if (n + 1 < a.Co) opp[i][1] = o.y;
-            if (n + 2 < a.Co) opp[i][2] = o.z;
-            if (n + 3 < a.Co) opp[i][3] = o.w;
+            if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+            op[0] = o.x;
+            if (n + 1 < a.Co) op[1] = o.y;
+            if (n + 2 < a.Co) op[2] = o.z;
+            if (n + 3 < a.Co) op[3] = o.w;
           }
         }
       }
+      if (MODE == 0 && c + 32 < BN) fetch(c + 32, rv);   // in flight during the next chunk's TMEM->smem hop
     }
   }
   tc_fence_before();
@@ -372,6 +369,200 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-tile variant (bf16): one CTA walks TPC consecutive 128-row tiles of one item.  The TMA/MMA
+// pipeline runs straight across tile boundaries and alternates between two TMEM accumulators, so
+// the epilogue of tile i (TMEM -> smem transpose -> global) overlaps the main loop of tile i+1, and
+// barrier init / TMEM allocation / descriptor prefetch are paid once per TPC tiles.
+template <int BN, int STAGES, int TPC>
+__global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            TcConvArgs a) {
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int PITCH = 36;
+  constexpr uint32_t STG_BYTES = 2 * 128 * PITCH * 4;  // two transpose buffers
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = stg_base + STG_BYTES;       // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t tmem_slot = bar_base + (2 * STAGES + 4) * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
+  auto tfull_bar = [&](int j) { return bar_base + (2 * STAGES + j) * 8; };
+  auto tempty_bar = [&](int j) { return bar_base + (2 * STAGES + 2 + j) * 8; };
+
+  const int b = blockIdx.z;
+  const int mlen = a.m_len[b];
+  const int m_base = blockIdx.x * (128 * TPC);
+  if (m_base >= mlen) return;  // CTA-uniform
+  const int ntiles = min(TPC, (mlen - m_base + 127) >> 7);
+  const int n0 = blockIdx.y * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.Cpad >> 6;
+  const int num_k = a.ks * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int j = 0; j < 2; j++) { mbar_init(tfull_bar(j), 1); mbar_init(tempty_bar(j), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int ti = 0; ti < ntiles; ti++) {
+        const int row0 = a.in_off[b] + m_base + ti * 128 - a.pad;
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+          const uint32_t sa = base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
+          tma_load_2d(sa + A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int g = 0;
+      for (int ti = 0; ti < ntiles; ti++) {
+        const int acc = ti & 1;
+        mbar_wait(tempty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // accumulator drained?
+        tc_fence_after();
+        const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (!(a.debug & 2)) umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = q * 32 + lane;
+    float* stage_f = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+    const int out_off = a.out_off[b];
+    const int res_off = a.res ? a.res_off[b] : 0;
+    const int t = threadIdx.x - 64;
+    const int c4 = (t & 7) << 2;
+    int chunk_ctr = 0;
+    for (int ti = 0; ti < ntiles; ti++) {
+      const int m0 = m_base + ti * 128;
+      const int acc = ti & 1;
+      auto fetch = [&](int c, float4* rv) {
+        const int n = n0 + c + c4;
+        const bool vec = a.vec4 && (n + 3 < a.Co);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int mm = m0 + (t >> 3) + 16 * i;
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.res && n < a.Co && mm < mlen) {
+            const int orow = mm * a.ors + a.oro;
+            const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
+            if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+            else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+          }
+        }
+      };
+      float4 rv[8];
+      fetch(0, rv);
+      mbar_wait(tfull_bar(acc), (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        if (c + 32 >= BN) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
+        }
+        float* buf = stage_f + (chunk_ctr & 1) * (128 * PITCH);
+        chunk_ctr++;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(buf + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int n = n0 + c + c4;
+        if (n < a.Co) {
+          const bool vec = a.vec4 && (n + 3 < a.Co);
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) {
+            if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+            else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int row = (t >> 3) + 16 * i;
+            const int mm = m0 + row;
+            if (mm >= mlen || (a.debug & 1)) continue;
+            float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+            o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+            o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+            float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
+            if (vec) {
+              if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+              *reinterpret_cast<float4*>(op) = o;
+            } else {
+              if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+              op[0] = o.x;
+              if (n + 1 < a.Co) op[1] = o.y;
+              if (n + 2 < a.Co) op[2] = o.z;
+              if (n + 3 < a.Co) op[3] = o.w;
+            }
+          }
+        }
+        if (c + 32 < BN) fetch(c + 32, rv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
+template <int BN, int STAGES, int TPC>
+static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
+  constexpr int smem = STAGES * (128 * 128 + BN * 128) + 2 * 128 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    KKX_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel<BN, STAGES, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[dev] = true;
+  }
+  dim3 g((a.max_m + 128 * TPC - 1) / (128 * TPC), (a.Co + BN - 1) / BN, a.B);
+  conv_tc_multi_kernel<BN, STAGES, TPC><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
+                                                             *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 template <int BN, int STAGES, int MODE>
@@ -397,6 +588,8 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (g_dry_run) return;
   if (a0.max_m <= 0 || a0.B <= 0) return;
   TcConvArgs a = a0;
+  static const int dbg = [] { const char* e = getenv("KKX_TC_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = a.tf32 ? 0 : dbg;
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
   if (a.tf32) {
@@ -409,10 +602,26 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
     } else post_launch("conv_tc_tf32x3", st);
     return;
   }
+  // Multi-tile CTAs (pipeline runs across tiles, double-buffered TMEM accumulators).  Measured on
+  // B200: NOT faster than 2-3 co-resident single-tile CTAs (202 vs 182 ms per B=64 step) -- the
+  // kernel is bound by L2->SM operand traffic (A re-fetched per tap, B per tile), not by prologue /
+  // epilogue serialisation (KKX_TC_DEBUG experiments, profiles/r1_conv_tc_experiments.txt).  Kept
+  // opt-in (KKX_TC_MULTI=1) as the base for the halo-reuse kernel.
+  static const bool multi_ok = [] { const char* e = getenv("KKX_TC_MULTI"); return e && e[0] == '1'; }();
+  const long long tiles = (a.sum_m + 127) / 128 * ((a.Co + 127) / 128);
+  if (multi_ok && tiles >= 4 * 2 * 148 && a.Co > 64) {
+    if (a.Co > 128) launch_tc_multi<256, 2, 4>(a, st);   // 96 + 37 KB smem, 512 TMEM cols: 1 CTA/SM
+    else launch_tc_multi<128, 2, 4>(a, st);              // 64 + 37 KB smem, 256 TMEM cols: 2 CTAs/SM
+    if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
+      char nm[96]; snprintf(nm, sizeof nm, "conv_tc[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);
+      post_launch(nm, st);
+    } else post_launch("conv_tc", st);
+    return;
+  }
   // smem per CTA ~97 KB in every configuration -> two CTAs per SM, so one tile's epilogue overlaps
   // the other's TMA/MMA main loop (TMEM: 2 x 256 columns = the whole 512-column file)
   if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
-  else if (a.Co > 64) launch_tc<128, 3, 0>(a, st);
+  else if (a.Co > 64) launch_tc<128, 2, 0>(a, st);   // 65 KB smem -> three CTAs per SM
   else launch_tc<64, 4, 0>(a, st);
   if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
     char nm[96]; snprintf(nm, sizeof nm, "conv_tc[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);

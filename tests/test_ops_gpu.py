@@ -263,3 +263,18 @@ def test_split_tf32_gemm_is_fp32_grade(lib, L, Ci, Co, k, nprod):
     rms_32 = np.sqrt(((ref32 - ref64) ** 2).mean())
     print(f"split-TF32 x{nprod}: max err {e_tc:.3e} (torch fp32 {e_32:.3e}), rms err {rms_tc:.3e} (fp32 {rms_32:.3e})")
     assert e_tc < 2e-5 and rms_tc < 8 * max(rms_32, 1e-8)
+
+
+@pytest.mark.parametrize("Cc,k,dil", [(128, 3, 1), (128, 11, 5), (256, 7, 3)])
+def test_tc_conv_multi_tile_kernel(lib, Cc, k, dil):
+    # large enough (>= 1184 tiles) to take the multi-tile / double-buffered-TMEM kernel, with a ragged
+    # tail (L not a multiple of 128*4), residual, scale and accumulate fused in the epilogue
+    L = 128 * 4 * 300 + 77 if Cc == 128 else 128 * 4 * 150 + 205
+    x, w, b = rnd(L, Cc, seed=31), rnd(Cc, Cc, k, seed=32, scale=1 / np.sqrt(Cc * k)), rnd(Cc, seed=33)
+    res, init = rnd(L, Cc, seed=34), rnd(L, Cc, seed=35)
+    pad = dil * (k - 1) // 2
+    y = F.conv1d(bf16_round(x).T[None], bf16_round(w), torch.from_numpy(b), padding=pad, dilation=dil)[0].T
+    ref = (torch.from_numpy(init) + (1 / 3) * (y + torch.from_numpy(res))).numpy()
+    got = run_conv_tc(lib, x, np.ascontiguousarray(w.transpose(0, 2, 1)), b, dil, pad, L, L, res=res, oscale=1 / 3,
+                      accumulate=1, out_init=init)
+    np.testing.assert_allclose(got, ref, atol=5e-4, rtol=1e-4)
