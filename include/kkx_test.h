@@ -42,6 +42,15 @@ KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const fl
  * fp32, nprod = 3 or 4 partial products, eact 0 / 3 (gelu_new).  out [L, Co]. */
 KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const float* w, const float* bias,
                                int Co, int ks, int dil, int pad, int nprod, int eact, float* out);
+/* Fused generator res-block conv (kernels_arb.cu): out = (conv1d(snake(x*scale_b+shift_b), w, dilation) + bias + res)
+ * * oscale (+ out when accumulate); B ragged items packed along rows (x, res, out: [sum lens, C]); C in
+ * {128, 256}; w [C][ks][C]; x optionally rounded to bf16 first (in_bf16); result as fp32 or, want_bf16, the
+ * unscaled bf16 output widened to fp32.  sums (nullable) [B][2][C] = column sums of (conv+bias+res) and of
+ * its square.  desc_mode selects the UMMA base-offset convention for row-shifted operand views. */
+KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens, int C, int in_bf16,
+                              const float* scale, const float* shift, const float* alpha, const float* w,
+                              const float* bias, int ks, int dil, const float* res, float oscale,
+                              int accumulate, int want_bf16, float* out, float* sums, int desc_mode);
 KKX_API const char* kkx_test_last_error(void);
 
 #ifdef __cplusplus

@@ -2,6 +2,7 @@
 // Activations are time-major [rows, C] fp32 ("NLC"), ragged items packed along rows (Level).
 #pragma once
 #include "common.h"
+#include <cuda_bf16.h>
 
 namespace kkx {
 
@@ -73,6 +74,30 @@ void launch_pool_up_bf16(const float* in, int ldi, const float* scale, const flo
                          const float* w, const float* bias, int C, void* out, int Cpad, int rows_total,
                          const int* in_off, const int* in_len, const int* out_off, int B, int max_len,
                          cudaStream_t st);
+
+// Fused generator res-block conv (kernels_arb.cu): AdaIN scale/shift + Snake applied to the raw
+// activations inside the kernel, every tap a row-shifted view of one smem halo tile, epilogue with
+// bias / residual / scale / accumulate, fp32 and/or bf16 outputs and per-128-row column sums for
+// the next AdaIN.  C = Ci = Co in {128, 256}; all tensors [rows, C] with the Level's row offsets.
+struct ArbConvArgs {
+  const void* x = nullptr; int in_bf16 = 0;           // raw input: fp32 or bf16 [rows, C]
+  const float* scale = nullptr; const float* shift = nullptr;  // AdaIN coefficients [B][C]
+  const float* alpha = nullptr;                        // Snake alpha [C]
+  const void* tmB = nullptr;                           // host pointer to the weight CUtensorMap (bf16 [C][ks*C], box [C,64])
+  int C = 0, ks = 1, dil = 1, pad = 0;
+  const int* off = nullptr; const int* len = nullptr;  // Level (device)
+  const int* tile_start = nullptr;                     // [B+1] prefix sum of ceil(len/arb_tile_rows(C))
+  int B = 1; int total_tiles = 0; long long sum_m = 0;
+  const float* bias = nullptr;
+  __nv_bfloat16* out_bf16 = nullptr;                   // y (+res) as bf16, unscaled (nullable)
+  float* out_f32 = nullptr;                            // (y + res) * oscale (+ previous value) (nullable)
+  const float* res = nullptr; float oscale = 1.f; int accumulate = 0;
+  float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
+  int desc_mode = 0;                                   // UMMA descriptor base-offset convention for row-shifted views
+};
+int arb_tile_rows(int C);
+bool arb_conv_supported(int C, int ks, int dil, int B);
+void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st);
 
 // y = act( LN(x (+res)) [* w + b] [(1+gamma_b) * . + beta_b] ), one row at a time.
 struct LnArgs {

@@ -419,9 +419,19 @@ Level Model::make_level(const std::vector<int>& lens, Arena& A) {
   L.rows = o;
   L.d_off = A.alloc<int>(L.B);
   L.d_len = A.alloc<int>(L.B);
+  L.d_tiles128 = A.alloc<int>(L.B + 1);
+  L.d_tiles256 = A.alloc<int>(L.B + 1);
+  std::vector<int> t128(L.B + 1, 0), t256(L.B + 1, 0);
+  for (int b = 0; b < L.B; b++) {
+    t128[b + 1] = t128[b] + (lens[b] + 127) / 128;
+    t256[b + 1] = t256[b] + (lens[b] + 255) / 256;
+  }
+  L.ntiles128 = t128[L.B]; L.ntiles256 = t256[L.B];
   if (!g_dry_run) {
     KKX_CUDA(cudaMemcpyAsync(L.d_off, L.off.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaMemcpyAsync(L.d_len, L.len.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    KKX_CUDA(cudaMemcpyAsync(L.d_tiles128, t128.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    KKX_CUDA(cudaMemcpyAsync(L.d_tiles256, t256.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaStreamSynchronize(stream_));  // L.off / L.len are locals of the caller's frame
   }
   return L;

@@ -4,6 +4,7 @@
 #include "model.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace kkx {
 
@@ -284,6 +285,35 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
   const float* cur = x;
   const bool tc = opt.precision == 1;
   void* abuf = tc ? A.alloc_bytes((size_t)L.rows * w.t1[0].Cpad * 2) : nullptr;
+  static const bool fused_ok = [] { const char* e = getenv("KKX_ARB_FUSED"); return !e || e[0] != '0'; }();
+  static const int desc_mode = [] { const char* e = getenv("KKX_ARB_DESC"); return e ? atoi(e) : 0; }();
+  if (tc && fused_ok && arb_conv_supported(C, k, 5, B)) {
+    // fused path (kernels_arb.cu): AdaIN + Snake inside the conv kernel, bf16 intermediate, column
+    // statistics for the next AdaIN from the conv epilogues -- one colstats pass per res-block
+    ArbConvArgs base;
+    base.C = C; base.ks = k; base.off = L.d_off; base.len = L.d_len; base.B = B; base.sum_m = L.sum_len;
+    base.tile_start = C == 128 ? L.d_tiles256 : L.d_tiles128;
+    base.total_tiles = C == 128 ? L.ntiles256 : L.ntiles128;
+    base.scale = sc; base.shift = sh; base.nchunk = nch; base.desc_mode = desc_mode;
+    launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    for (int j = 0; j < 3; j++) {
+      launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
+      ArbConvArgs c1 = base;
+      c1.x = cur; c1.in_bf16 = 0; c1.alpha = w.a1[j]; c1.tmB = w.t1[j].tmap; c1.dil = dil[j];
+      c1.pad = dil[j] * (k - 1) / 2; c1.bias = w.b1[j];
+      c1.out_bf16 = static_cast<__nv_bfloat16*>(abuf); c1.part = part;
+      launch_arb_conv(c1, st);
+      launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s2[j], 1e-5f, sc, sh, B, st);
+      float* dst = (j == 2) ? out : xw;
+      ArbConvArgs c2 = base;
+      c2.x = abuf; c2.in_bf16 = 1; c2.alpha = w.a2[j]; c2.tmB = w.t2[j].tmap; c2.dil = 1; c2.pad = (k - 1) / 2;
+      c2.bias = w.b2[j]; c2.out_f32 = dst; c2.res = cur;
+      if (j == 2) { c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; } else c2.part = part;
+      launch_arb_conv(c2, st);
+      cur = dst;
+    }
+    return;
+  }
   for (int j = 0; j < 3; j++) {
     launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
     launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);

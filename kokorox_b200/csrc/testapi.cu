@@ -1,7 +1,9 @@
 // testapi.cu -- op-level test hooks (include/kkx_test.h).  Parity harness only.
 #include "../../include/kkx_test.h"
 #include "kernels.h"
+#include <algorithm>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -207,6 +209,88 @@ KKX_API int kkx_test_adain_coef(int device, const float* x, int L, int C, const 
     KKX_CUDA(cudaDeviceSynchronize());
     KKX_CUDA(cudaMemcpy(scale, dsc.p, C * 4, cudaMemcpyDeviceToHost));
     KKX_CUDA(cudaMemcpy(shift, dsh.p, C * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+static inline uint16_t host_bf16(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+}
+
+KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens, int C, int in_bf16,
+                              const float* scale, const float* shift, const float* alpha, const float* w,
+                              const float* bias, int ks, int dil, const float* res, float oscale,
+                              int accumulate, int want_bf16, float* out, float* sums, int desc_mode) {
+  return run(device, [&] {
+    if (!arb_conv_supported(C, ks, dil, B)) throw ArgError("kkx_test_arb_conv: unsupported shape");
+    // ragged Level layout with NaN-filled gap rows: the kernel must never consume a gap row
+    std::vector<int> off(B), tiles(B + 1, 0);
+    const int MT = arb_tile_rows(C);
+    int o = kGapRows, maxL = 0; long long sumL = 0;
+    for (int b = 0; b < B; b++) {
+      off[b] = o; o = (o + lens[b] + kGapRows + 7) & ~7;
+      tiles[b + 1] = tiles[b] + (lens[b] + MT - 1) / MT;
+      maxL = std::max(maxL, lens[b]); sumL += lens[b];
+    }
+    const int rows = o;
+    const float qnan = std::numeric_limits<float>::quiet_NaN();
+    std::vector<float> hx((size_t)rows * C, qnan), hres((size_t)rows * C, qnan), hout((size_t)rows * C, qnan);
+    size_t src = 0;
+    for (int b = 0; b < B; b++) {
+      memcpy(hx.data() + (size_t)off[b] * C, x + src * C, (size_t)lens[b] * C * 4);
+      if (res) memcpy(hres.data() + (size_t)off[b] * C, res + src * C, (size_t)lens[b] * C * 4);
+      memcpy(hout.data() + (size_t)off[b] * C, out + src * C, (size_t)lens[b] * C * 4);
+      src += lens[b];
+    }
+    std::vector<uint16_t> hxb;
+    if (in_bf16) { hxb.resize(hx.size()); for (size_t i = 0; i < hx.size(); i++) hxb[i] = host_bf16(hx[i]); }
+    std::vector<uint16_t> hw((size_t)C * ks * C);
+    for (size_t i = 0; i < hw.size(); i++) hw[i] = host_bf16(w[i]);
+    DevBuf dx(in_bf16 ? (const void*)hxb.data() : (const void*)hx.data(), hx.size() * (in_bf16 ? 2 : 4));
+    DevBuf dw(hw.data(), hw.size() * 2), db(bias, C * 4), dsc(scale, (size_t)B * C * 4), dsh(shift, (size_t)B * C * 4);
+    DevBuf dal(alpha, C * 4), dres(res ? hres.data() : nullptr, res ? hres.size() * 4 : 0);
+    DevBuf dout(hout.data(), hout.size() * 4), doutb(nullptr, hout.size() * 2);
+    KKX_CUDA(cudaMemset(doutb.p, 0xFF, hout.size() * 2));
+    const int nchunk = (maxL + 127) / 128;
+    DevBuf dpart(nullptr, (size_t)B * nchunk * 2 * C * 4);
+    KKX_CUDA(cudaMemset(dpart.p, 0, (size_t)B * nchunk * 2 * C * 4));
+    DevBuf doff(off.data(), B * 4), dlen(lens, B * 4), dts(tiles.data(), (B + 1) * 4);
+    alignas(64) unsigned char tmB[128];
+    make_tmap_bf16(tmB, dw.p, (long long)ks * C, C, (long long)ks * C, tc_box_n(C));
+    ArbConvArgs a;
+    a.x = dx.p; a.in_bf16 = in_bf16; a.scale = dsc.as<float>(); a.shift = dsh.as<float>(); a.alpha = dal.as<float>();
+    a.tmB = tmB; a.C = C; a.ks = ks; a.dil = dil; a.pad = dil * (ks - 1) / 2;
+    a.off = doff.as<int>(); a.len = dlen.as<int>(); a.tile_start = dts.as<int>(); a.B = B; a.total_tiles = tiles[B];
+    a.sum_m = sumL; a.bias = db.as<float>();
+    a.out_bf16 = want_bf16 ? doutb.as<__nv_bfloat16>() : nullptr;
+    a.out_f32 = want_bf16 ? nullptr : dout.as<float>();
+    a.res = res ? dres.as<float>() : nullptr; a.oscale = oscale; a.accumulate = accumulate;
+    a.part = sums ? dpart.as<float>() : nullptr; a.nchunk = nchunk; a.desc_mode = desc_mode;
+    launch_arb_conv(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    if (want_bf16) {
+      std::vector<uint16_t> hb(hout.size());
+      KKX_CUDA(cudaMemcpy(hb.data(), doutb.p, hb.size() * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < hb.size(); i++) { uint32_t u = (uint32_t)hb[i] << 16; memcpy(&hout[i], &u, 4); }
+    } else {
+      KKX_CUDA(cudaMemcpy(hout.data(), dout.p, hout.size() * 4, cudaMemcpyDeviceToHost));
+    }
+    src = 0;
+    for (int b = 0; b < B; b++) {
+      memcpy(out + src * C, hout.data() + (size_t)off[b] * C, (size_t)lens[b] * C * 4);
+      src += lens[b];
+    }
+    if (sums) {
+      std::vector<float> hp((size_t)B * nchunk * 2 * C);
+      KKX_CUDA(cudaMemcpy(hp.data(), dpart.p, hp.size() * 4, cudaMemcpyDeviceToHost));
+      for (int b = 0; b < B; b++)
+        for (int k = 0; k < 2; k++)
+          for (int c = 0; c < C; c++) {
+            double acc = 0.0;
+            for (int ch = 0; ch < (lens[b] + 127) / 128; ch++) acc += hp[(((size_t)b * nchunk + ch) * 2 + k) * C + c];
+            sums[((size_t)b * 2 + k) * C + c] = (float)acc;
+          }
+    }
   });
 }
 

@@ -278,3 +278,24 @@ def test_tc_conv_multi_tile_kernel(lib, Cc, k, dil):
     got = run_conv_tc(lib, x, np.ascontiguousarray(w.transpose(0, 2, 1)), b, dil, pad, L, L, res=res, oscale=1 / 3,
                       accumulate=1, out_init=init)
     np.testing.assert_allclose(got, ref, atol=5e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("Cc,k,dil,lens", [(128, 3, 1, [300]), (128, 11, 5, [700, 13, 257]), (128, 7, 3, [256, 512, 1]),
+                                            (256, 7, 1, [333]), (256, 11, 5, [129, 640]), (256, 3, 3, [128, 127])])
+@pytest.mark.parametrize("variant", ["conv1_f32_to_bf16_stats", "conv2_bf16_res_accumulate"])
+def test_fused_arb_conv(lib, Cc, k, dil, lens, variant):
+    # kernels_arb.cu: AdaIN scale/shift + Snake inside the conv, row-shifted smem views per tap, ragged items
+    # separated by NaN gap rows (the hook fills them), epilogue statistics.  Reference: float64 conv of the
+    # same bf16-rounded operands (tools/arb_probe.py).
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from arb_probe import run_case
+    if variant == "conv1_f32_to_bf16_stats":
+        out, ref, sums, rs = run_case(lib, Cc, k, dil, lens, 0, 1, 0, 1.0, 0, 0)
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=1e-3)      # one bf16 ulp of the stored value
+    else:
+        out, ref, sums, rs = run_case(lib, Cc, k, dil, lens, 1, 0, 1, 1.0 / 3.0, 1, 0)
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-3)         # fast-sin + bf16 re-rounding flips
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(sums, rs, rtol=1e-3, atol=1e-2 * float(np.abs(rs).max()) * 1e-2)

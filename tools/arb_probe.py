@@ -1,0 +1,96 @@
+"""Probe of the fused res-block conv kernel (kernels_arb.cu) against a float64 reference with the same
+bf16 operand rounding.  Prints max-abs / rel-L2 errors for both UMMA base-offset conventions.
+
+    python tools/arb_probe.py
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def bf16_round(a):
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32) << 16
+    return r.view(np.float32)
+
+
+def reference(x, lens, sc, sh, al, w, bias, k, dil, res, in_bf16):
+    """float64 conv of the bf16-rounded operands; x, res packed [sum L, C]; w [C][k][C] (co, tap, ci)."""
+    Cc = x.shape[1]
+    xx = bf16_round(x) if in_bf16 else x
+    wb = bf16_round(w).astype(np.float64)
+    out = np.zeros((x.shape[0], Cc), np.float64)
+    pad = dil * (k - 1) // 2
+    o = 0
+    for b, L in enumerate(lens):
+        v = xx[o:o + L].astype(np.float32) * sc[b][None, :] + sh[b][None, :]
+        a = v + (np.sin(al[None, :] * v) ** 2) / al[None, :]
+        a = bf16_round(a.astype(np.float32)).astype(np.float64)
+        ap = np.zeros((L + 2 * pad, Cc))
+        ap[pad:pad + L] = a
+        y = np.zeros((L, Cc))
+        for t in range(k):
+            y += ap[t * dil:t * dil + L] @ wb[:, t, :].T
+        out[o:o + L] = y + bias[None, :]
+        if res is not None:
+            out[o:o + L] += res[o:o + L]
+        o += L
+    return out
+
+
+def run_case(lib, Cc, k, dil, lens, in_bf16, want_bf16, use_res, oscale, accumulate, desc_mode, seed=0):
+    rng = np.random.default_rng(seed)
+    n = int(sum(lens))
+    B = len(lens)
+    x = rng.standard_normal((n, Cc)).astype(np.float32)
+    sc = (1.0 + 0.3 * rng.standard_normal((B, Cc))).astype(np.float32)
+    sh = (0.3 * rng.standard_normal((B, Cc))).astype(np.float32)
+    al = (0.5 + rng.random(Cc)).astype(np.float32)
+    w = (rng.standard_normal((Cc, k, Cc)) / np.sqrt(Cc * k)).astype(np.float32)
+    bias = rng.standard_normal(Cc).astype(np.float32)
+    res = rng.standard_normal((n, Cc)).astype(np.float32) if use_res else None
+    prev = rng.standard_normal((n, Cc)).astype(np.float32)
+    out = prev.copy()
+    sums = np.zeros((B, 2, Cc), np.float32)
+    fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+    li = np.asarray(lens, np.int32)
+    rc = lib.kkx_test_arb_conv(0, fp(x), B, li.ctypes.data_as(C.POINTER(C.c_int)), Cc, int(in_bf16), fp(sc), fp(sh),
+                               fp(al), fp(w), fp(bias), k, dil, fp(res), C.c_float(oscale), int(accumulate),
+                               int(want_bf16), fp(out), fp(sums), desc_mode)
+    assert rc == 0, lib.kkx_test_last_error()
+    y = reference(x, lens, sc, sh, al, w, bias, k, dil, res, in_bf16)
+    ref = y.copy() if want_bf16 else y * oscale + (prev if accumulate else 0.0)
+    ref_sums = np.zeros((B, 2, Cc))
+    o = 0
+    for b, L in enumerate(lens):
+        ref_sums[b, 0] = y[o:o + L].sum(0)
+        ref_sums[b, 1] = (y[o:o + L] ** 2).sum(0)
+        o += L
+    return out, ref, sums, ref_sums
+
+
+def main():
+    from kokorox_b200.onn import load_library
+    lib = load_library()
+    lib.kkx_test_last_error.restype = C.c_char_p
+    cases = [(128, 3, 1, [300]), (128, 11, 5, [700, 13, 257]), (128, 7, 3, [256, 512, 1]), (256, 7, 1, [333]),
+             (256, 11, 5, [129, 640]), (256, 3, 3, [128, 127])]
+    for mode in (0, 1):
+        for (Cc, k, dil, lens) in cases:
+            for (in_bf16, want_bf16, use_res, osc, acc) in [(0, 1, 0, 1.0, 0), (1, 0, 1, 1.0 / 3, 1)]:
+                out, ref, sums, rs = run_case(lib, Cc, k, dil, lens, in_bf16, want_bf16, use_res, osc, acc, mode)
+                bad = int(np.isnan(out).sum())
+                err = np.nan_to_num(out - ref, nan=1e9)
+                rel = np.sqrt((err ** 2).sum() / (ref ** 2).sum())
+                srel = np.abs(sums - rs).max() / np.abs(rs).max()
+                print(f"mode={mode} C={Cc} k={k} dil={dil} lens={lens} in_bf16={in_bf16} out_bf16={want_bf16} "
+                      f"max_abs={np.abs(err).max():.3e} rel_l2={rel:.3e} sums_rel={srel:.2e} nan={bad}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
