@@ -20,6 +20,7 @@ LIB = os.path.join(OUT_DIR, "libkkx.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("KKX_NVCC_EXTRA", "").split()   # e.g. -DKKX_ARB_TIMING for the diagnostic build
 
 
 def _sources():

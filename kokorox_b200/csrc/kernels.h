@@ -93,7 +93,7 @@ struct ArbConvArgs {
   float* out_f32 = nullptr;                            // (y + res) * oscale (+ previous value) (nullable)
   const float* res = nullptr; float oscale = 1.f; int accumulate = 0;
   float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
-  int desc_mode = 0;                                   // UMMA descriptor base-offset convention for row-shifted views
+  long long* timing = nullptr;                         // diagnostics (-DKKX_ARB_TIMING builds): per-role phase cycle counters
 };
 int arb_tile_rows(int C);
 bool arb_conv_supported(int C, int ks, int dil, int B);

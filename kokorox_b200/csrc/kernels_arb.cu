@@ -18,18 +18,33 @@
 // TMEM holds two accumulator sets (2 x MSUB x BN = 512 columns): the epilogue of tile i overlaps the
 // MMAs of tile i+1; the operand producers run one channel chunk ahead of the MMA warp.
 //
-// Warp roles (448 threads, 1 CTA/SM, persistent over tiles blockIdx.x + i*gridDim.x):
-//   warp 0      weight-tile TMA producer          warp 1      TMEM alloc + tcgen05.mma issuer
-//   warps 2-5   epilogue                          warps 6-13  operand producers (transform)
+// Warp roles (512 threads, 1 CTA/SM, persistent over a contiguous range of tiles):
+//   warp 0      weight-tile TMA producer          warp 1        TMEM alloc + tcgen05.mma issuer
+//   warps 2-9   epilogue (two groups of 4)        warps 10-15   operand producers (transform)
 #include "kernels.h"
 #include "tc_ptx.cuh"
+#include <type_traits>
 
 namespace kkx {
 
 namespace {
 
-constexpr int kArbThreads = 448;
-constexpr int kArbMaxB = 1024;
+// Optional per-role phase timing (-DKKX_ARB_TIMING, diagnostics only): designated threads of CTA 0 attribute
+// the cycles between consecutive TICKs to a slot and add their totals to a.timing[] at kernel end.
+#ifdef KKX_ARB_TIMING
+#define TIM_DECL(n) long long tim_acc[n] = {0}; long long tim_last = clock64(); const bool tim_on = a.timing && blockIdx.x == 0
+#define TICK(slot) do { if (tim_on) { const long long now_ = clock64(); tim_acc[slot] += now_ - tim_last; tim_last = now_; } } while (0)
+#define TIM_FLUSH(base, n) do { if (tim_on) for (int i_ = 0; i_ < (n); i_++) atomicAdd(reinterpret_cast<unsigned long long*>(a.timing) + (base) + i_, (unsigned long long)tim_acc[i_]); } while (0)
+#else
+#define TIM_DECL(n)
+#define TICK(slot)
+#define TIM_FLUSH(base, n)
+#endif
+
+constexpr int kArbThreads = 512;   // 16 warps: TMA, MMA, 8 epilogue, 6 operand producers (128 regs/thread)
+constexpr int kProdThreads = 192;
+constexpr int kProdRows = kProdThreads / 8;   // rows per producer pass
+constexpr int kArbMaxB = 512;
 
 template <int BN, int MSUB>
 struct ArbCfg {
@@ -38,41 +53,45 @@ struct ArbCfg {
   static constexpr uint32_t A_SLOT = RA * 128;              // bytes (multiple of 1024)
   static constexpr int NA = (BN == 128) ? 2 : 3;            // A slots
   static constexpr uint32_t B_STAGE = BN * 128;             // bytes
-  static constexpr int NB = (BN == 128) ? 4 : 3;            // B stages
+  static constexpr int NB = (BN == 128) ? 6 : 3;            // B stages
   static constexpr int PITCH = 36;                          // floats per staged epilogue row
-  static constexpr uint32_t STG = 2 * 128 * PITCH * 4;      // two transpose buffers
-  static constexpr uint32_t STAT = 4 * BN * 2 * 4;          // per-warp column sums
+  static constexpr uint32_t STG = 2 * 128 * PITCH * 4;      // one transpose buffer per epilogue group
+  static constexpr uint32_t STAT = 4 * BN * 2 * 4;          // per-quadrant column sums
+  static constexpr uint32_t COEF = 3 * BN * 4;              // per-item operand-transform coefficients
   static constexpr int NBAR = 2 * NA + 2 * NB + 4;
-  static constexpr uint32_t SMEM = NA * A_SLOT + NB * B_STAGE + STG + STAT + NBAR * 8 + 16 + (kArbMaxB + 1) * 4 + 1024;
+  static constexpr uint32_t SMEM = NA * A_SLOT + NB * B_STAGE + STG + STAT + COEF + NBAR * 8 + 16 + (3 * kArbMaxB + 2) * 4 + 1024;
   static_assert(A_SLOT % 1024 == 0, "A slot must keep the 1024-byte swizzle alignment");
 };
-
-__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t saddr, int mode) {
-  uint64_t d = umma_desc_sw128(saddr);
-  if (mode == 1) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // matrix base offset = row phase inside the 1024 B swizzle pattern
-  return d;
-}
-
-__device__ __forceinline__ float snake_f(float v, float al, float ial) {
-  const float s = __sinf(al * v);
-  return fmaf(s * s, ial, v);
-}
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-__device__ __forceinline__ void tile_decode(const int* ts, int B, int tile, int& b, int& mt) {
-  int lo = 0, hi = B;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (ts[mid] <= tile) lo = mid; else hi = mid;
+// tile cursor: walks the (item, tile-in-item) pairs in item-major order
+struct TileCur {
+  int b, mt;
+  __device__ __forceinline__ void init(const int* ts, int B, int tile) {
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ts[mid] <= tile) lo = mid; else hi = mid;
+    }
+    b = lo; mt = tile - ts[lo];
   }
-  b = lo; mt = tile - ts[lo];
-}
+  __device__ __forceinline__ void next(const int* ts) {
+    mt++;
+    while (ts[b] + mt >= ts[b + 1]) { b++; mt = 0; if (ts[b] < 0) break; }   // ts[B+1] = -1 sentinel
+  }
+};
 
-template <int BN, int MSUB, bool IN_BF16>
+// CONV2 = false: "conv1" of a res-block iteration -- fp32 input (residual stream), bf16 output, statistics.
+// CONV2 = true : "conv2" -- bf16 input, fp32 output = (y + residual) * oscale (stored, or added to the
+//                previous value with one reduction per element), optional statistics.
+// The two roles are separate instantiations so that each carries only its own epilogue / producer code:
+// with 16 warps in four different roles the hot code of all roles has to stay inside the instruction cache
+// (an earlier, more generic version of this kernel lost ~40 % of its time to instruction-fetch stalls).
+template <int BN, int MSUB, bool CONV2>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
   using Cfg = ArbCfg<BN, MSUB>;
   constexpr int KCH = Cfg::KCH, NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
@@ -84,7 +103,8 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   const uint32_t b_base = a_base + NA * Cfg::A_SLOT;
   const uint32_t stg_base = b_base + NB * Cfg::B_STAGE;
   const uint32_t stat_base = stg_base + Cfg::STG;
-  const uint32_t bar_base = stat_base + Cfg::STAT;
+  const uint32_t coef_base = stat_base + Cfg::STAT;
+  const uint32_t bar_base = coef_base + Cfg::COEF;
   const uint32_t tmem_slot = bar_base + Cfg::NBAR * 8;
   const uint32_t ts_base = tmem_slot + 16;
   auto fullA = [&](int s) { return bar_base + s * 8; };
@@ -94,16 +114,21 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   auto tfull = [&](int j) { return bar_base + (2 * NA + 2 * NB + j) * 8; };
   auto tempty = [&](int j) { return bar_base + (2 * NA + 2 * NB + 2 + j) * 8; };
   int* const s_ts = reinterpret_cast<int*>(gbase + (ts_base - base));
+  int* const s_len = s_ts + (kArbMaxB + 2);
+  int* const s_off = s_len + kArbMaxB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B = a.B;
-  for (int i = threadIdx.x; i <= B; i += kArbThreads) s_ts[i] = a.tile_start[i];
+#pragma unroll 1
+  for (int i = threadIdx.x; i <= B + 1; i += kArbThreads) s_ts[i] = i <= B ? a.tile_start[i] : -1;
+#pragma unroll 1
+  for (int i = threadIdx.x; i < B; i += kArbThreads) { s_len[i] = a.len[i]; s_off[i] = a.off[i]; }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < NA; s++) { mbar_init(fullA(s), 8); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < NA; s++) { mbar_init(fullA(s), kProdThreads / 32); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < NB; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int j = 0; j < 2; j++) { mbar_init(tfull(j), 1); mbar_init(tempty(j), 4); }
+    for (int j = 0; j < 2; j++) { mbar_init(tfull(j), 1); mbar_init(tempty(j), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -117,251 +142,382 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int ntiles = a.total_tiles;
+  // contiguous tile range of this CTA (neighbouring tiles share halo rows and, mostly, the item)
+  const int t_begin = (int)(((long long)a.total_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)a.total_tiles * (blockIdx.x + 1)) / gridDim.x);
   const int ks = a.ks, dil = a.dil, pad = a.pad;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight tiles (TMA)
-    if (lane == 0) {
+    if (lane == 0 && t_begin < t_end) {
       int g = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      TIM_DECL(2);
+      // k=3 at C=128: the whole weight set (KCH*ks tiles) fits the ring -> load it once, keep it resident
+      const bool resident = KCH * ks <= NB;
+#pragma unroll 1
+      for (int tile = t_begin; tile < (resident ? t_begin + 1 : t_end); tile++) {
+#pragma unroll 1
         for (int c = 0; c < KCH; c++)
+#pragma unroll 1
           for (int tap = 0; tap < ks; tap++, g++) {
             const int s = g % NB;
             mbar_wait(emptyB(s), (((uint32_t)(g / NB)) & 1u) ^ 1u);
+            TICK(0);
             mbar_expect_tx(fullB(s), Cfg::B_STAGE);
             tma_load_2d(b_base + s * Cfg::B_STAGE, &tmB, tap * BN + c * 64, 0, fullB(s));
+            TICK(1);
           }
       }
+      TIM_FLUSH(0, 2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issue
-    if (lane == 0) {
+    if (lane == 0 && t_begin < t_end) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int gA = 0, gB = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
-        int b, mt;
-        tile_decode(s_ts, B, tile, b, mt);
-        const int rem = a.len[b] - mt * MT;                 // rows of this item left from the tile start
+      TileCur cur;
+      cur.init(s_ts, B, t_begin);
+      const bool resident = KCH * ks <= NB;
+      TIM_DECL(4);
+#pragma unroll 1
+      for (int tile = t_begin; tile < t_end; tile++, ti++) {
+        const int rem = s_len[cur.b] - cur.mt * MT;         // rows of this item left from the tile start
         const int buf = ti & 1;
         mbar_wait(tempty(buf), (((uint32_t)(ti >> 1)) & 1u) ^ 1u);
         tc_fence_after();
+        TICK(0);
+#pragma unroll 1
         for (int c = 0; c < KCH; c++, gA++) {
           const int sa = gA % NA;
           mbar_wait(fullA(sa), ((uint32_t)(gA / NA)) & 1u);
           tc_fence_after();
+          TICK(1);
           const uint32_t slot = a_base + sa * Cfg::A_SLOT;
+#pragma unroll 1
           for (int tap = 0; tap < ks; tap++, gB++) {
-            const int sb = gB % NB;
-            mbar_wait(fullB(sb), ((uint32_t)(gB / NB)) & 1u);
-            tc_fence_after();
+            const int sb = resident ? c * ks + tap : gB % NB;
+            if (!resident || ti == 0) {
+              mbar_wait(fullB(sb), resident ? 0u : ((uint32_t)(gB / NB)) & 1u);
+              tc_fence_after();
+            }
+            TICK(2);
             const uint64_t bd = umma_desc_sw128(b_base + sb * Cfg::B_STAGE);
 #pragma unroll
             for (int sub = 0; sub < MSUB; sub++) {
               if (sub * 128 >= rem) continue;
-              const uint64_t ad = umma_desc_sw128_bo(slot + (uint32_t)(sub * 128 + tap * dil) * 128u, a.desc_mode);
+              // row-shifted view of the halo tile: start address moves by whole 128-byte rows; the
+              // 128B swizzle is a function of the absolute smem address, so the view stays consistent
+              // with how the producers (and TMA) lay rows out (verified on B200, tools/arb_probe.py)
+              const uint64_t ad = umma_desc_sw128(slot + (uint32_t)(sub * 128 + tap * dil) * 128u);
               const uint32_t td = tmem_base + (uint32_t)((buf * MSUB + sub) * BN);
 #pragma unroll
               for (int k = 0; k < 4; k++)
                 umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
             }
-            umma_commit(emptyB(sb));
+            if (!resident) umma_commit(emptyB(sb));
+            TICK(3);
           }
           umma_commit(emptyA(sa));
         }
         umma_commit(tfull(buf));
+        cur.next(s_ts);
       }
+      TIM_FLUSH(4, 4);
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ epilogue
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ epilogue (2 groups of 4 warps)
+    // group eg owns the 32-column chunks of parity eg; inside a group, thread `et` drops its accumulator
+    // row into padded smem, then thread t handles columns c4..c4+3 of rows (t>>3) + 16*i (full 128-byte
+    // row segments per 8 lanes -> coalesced residual reads and stores).
+    const int eg = (warp - 2) >> 2;
     const int q = warp & 3;                 // TMEM lane quadrant of this warp
     const int et = q * 32 + lane;           // accumulator row held by this thread
-    const int t = threadIdx.x - 64;         // 0..127
+    const int t = (threadIdx.x - 64) & 127; // 0..127 inside the group
+    const int tr = t >> 3;                  // first row handled after the transpose
     const int c4 = (t & 7) << 2;
-    float* const stage_f = reinterpret_cast<float*>(gbase + (stg_base - base));
+    const int bar_id = 1 + eg;
+    float* const buf_f = reinterpret_cast<float*>(gbase + (stg_base - base)) + eg * (128 * PITCH);
     float* const stat_f = reinterpret_cast<float*>(gbase + (stat_base - base));   // [4][BN][2]
-    int chunk_ctr = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ti++) {
-      int b, mt;
-      tile_decode(s_ts, B, tile, b, mt);
-      const int L = a.len[b], off = a.off[b];
-      const int m0 = mt * MT;
-      const int nsub = min(MSUB, (L - m0 + 127) >> 7);
-      const int buf = ti & 1;
-      auto fetch = [&](int sub, int c, float4* rv) {   // residual operand of (sub, 32-col chunk c)
-        const int n = c + c4;
+    const float* const st_rd = buf_f + tr * PITCH + c4;
+    float* const st_wr = buf_f + et * PITCH;
+    constexpr int NCH = BN / 64;            // 32-column chunks per group and sub-tile (2 or 4)
+    constexpr int RS = 16 * BN;             // elements between the rows one thread handles
+    const float2 os2 = make_float2(a.oscale, a.oscale);
+    const bool accum = a.accumulate != 0;
+    // Residual operands are prefetched TWO chunk iterations ahead (two register buffers), across sub-tile
+    // and tile boundaries: with ~2 us of HBM latency under load, one iteration of lead is not enough.
+    auto fetch = [&](int L, int off, int m0, int e, float4 (&rv)[8]) {   // iteration e of a tile: (sub, chunk)
+      if (!CONV2) return;
+      const int sub = e / NCH, ci = e & (NCH - 1);
+      const int row = m0 + sub * 128 + tr;
+      const float* rp = a.res + (size_t)(off + row) * BN + ((2 * ci + eg) * 32 + c4);
+      const int left = L - row;            // row i valid iff 16*i < left
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int mm = m0 + sub * 128 + (t >> 3) + 16 * i;
-          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.res && mm < L) rv[i] = *reinterpret_cast<const float4*>(a.res + (size_t)(off + mm) * BN + n);
-        }
-      };
-      float4 rv[8];
-      fetch(0, 0, rv);
+      for (int i = 0; i < 8; i++)
+        if (16 * i < left) rv[i] = *reinterpret_cast<const float4*>(rp + i * RS);
+    };
+    int ti = 0;
+    TileCur cur;
+    float4 rv0[8], rv1[8];
+#ifdef KKX_ARB_TIMING
+    long long tim_acc[9] = {0}; long long tim_last = clock64();
+    const bool tim_on = a.timing && blockIdx.x == 0 && warp == 2 && lane == 0;
+#endif
+    if (t_begin < t_end) {
+      cur.init(s_ts, B, t_begin);
+      fetch(s_len[cur.b], s_off[cur.b], cur.mt * MT, 0, rv0);
+      fetch(s_len[cur.b], s_off[cur.b], cur.mt * MT, 1, rv1);
+    }
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; tile++, ti++) {
+      const int b = cur.b;
+      const int L = s_len[b], off = s_off[b];
+      const int m0 = cur.mt * MT;
+      const int nsub = min(MSUB, (L - m0 + 127) >> 7);
+      const int E = nsub * NCH;
+      const int buf = ti & 1;
+      cur.next(s_ts);                       // cur now names the NEXT tile (prefetch target)
+      const bool has_next = tile + 1 < t_end;
+      const int nL = has_next ? s_len[cur.b] : 0, noff = has_next ? s_off[cur.b] : 0, nm0 = cur.mt * MT;
+      TICK(8);
       mbar_wait(tfull(buf), ((uint32_t)(ti >> 1)) & 1u);
       tc_fence_after();
-      for (int sub = 0; sub < nsub; sub++) {
-        const int sm0 = m0 + sub * 128;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+      TICK(0);
+      auto body = [&](int e, float4 (&rv)[8], auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;   // every row of the sub-tile is inside the item
+        const int sub = e / NCH, ci = e & (NCH - 1);
+        const int row = m0 + sub * 128 + tr;
+        const int n = (2 * ci + eg) * 32 + c4;
+        {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MSUB + sub) * BN + c), v);
-          if (sub == nsub - 1 && c + 32 >= BN) {   // last TMEM read of this tile: hand the accumulators back
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * MSUB + sub) * BN + n - c4), v);
+          if (e == E - 1) {   // last TMEM read of this tile: hand the accumulators back
             tc_fence_before();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
           }
-          float* buf_f = stage_f + (chunk_ctr & 1) * (128 * PITCH);
-          chunk_ctr++;
+          TICK(1);
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // staging buffer drained by the previous iteration
+          TICK(2);
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(buf_f + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const int n = c + c4;
-          const float4 bb = *reinterpret_cast<const float4*>(a.bias + n);
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            *reinterpret_cast<uint4*>(st_wr + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          TICK(3);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        TICK(4);
+        const float4 bb = *reinterpret_cast<const float4*>(a.bias + n);
+        const float2 b01 = make_float2(bb.x, bb.y), b23 = make_float2(bb.z, bb.w);
+        const int left = L - row;
+        const size_t g0 = (size_t)(off + row) * BN + n;
+        float2 s01 = make_float2(0.f, 0.f), s23 = s01, q01 = s01, q23 = s01;
+        // packed fp32 (FADD2 / FFMA2 / FMUL2): the epilogue is issue-bound, this halves its math instructions
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int row = (t >> 3) + 16 * i;
-            const int mm = sm0 + row;
-            if (mm >= L) continue;
-            float4 o = *reinterpret_cast<const float4*>(buf_f + row * PITCH + c4);
-            o.x += bb.x + rv[i].x; o.y += bb.y + rv[i].y; o.z += bb.z + rv[i].z; o.w += bb.w + rv[i].w;
-            s0 += o.x; s1 += o.y; s2 += o.z; s3 += o.w;
-            q0 = fmaf(o.x, o.x, q0); q1 = fmaf(o.y, o.y, q1); q2 = fmaf(o.z, o.z, q2); q3 = fmaf(o.w, o.w, q3);
-            const size_t gi = (size_t)(off + mm) * BN + n;
-            if (a.out_bf16) {
-              uint2 pk;
-              pk.x = pack_bf16(o.x, o.y); pk.y = pack_bf16(o.z, o.w);
-              *reinterpret_cast<uint2*>(a.out_bf16 + gi) = pk;
-            }
-            if (a.out_f32) {
-              o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
-              if (a.accumulate) {
-                const float4 pv = *reinterpret_cast<const float4*>(a.out_f32 + gi);
-                o.x += pv.x; o.y += pv.y; o.z += pv.z; o.w += pv.w;
-              }
-              *reinterpret_cast<float4*>(a.out_f32 + gi) = o;
-            }
-          }
-          // next chunk's residual operand in flight during the next TMEM -> smem hop
-          if (c + 32 < BN) fetch(sub, c + 32, rv);
-          else if (sub + 1 < nsub) fetch(sub + 1, 0, rv);
-          if (a.part) {
-            // rows of one column quad live in lanes l, l+8, l+16, l+24
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 8); s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 8);
-            q0 += __shfl_xor_sync(0xffffffffu, q0, 8); q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
-            q2 += __shfl_xor_sync(0xffffffffu, q2, 8); q3 += __shfl_xor_sync(0xffffffffu, q3, 8);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 16); s3 += __shfl_xor_sync(0xffffffffu, s3, 16);
-            q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-            q2 += __shfl_xor_sync(0xffffffffu, q2, 16); q3 += __shfl_xor_sync(0xffffffffu, q3, 16);
-            if (lane < 8) {
-              float* sp = stat_f + ((size_t)(warp - 2) * BN + n) * 2;
-              *reinterpret_cast<float4*>(sp) = make_float4(s0, q0, s1, q1);
-              *reinterpret_cast<float4*>(sp + 4) = make_float4(s2, q2, s3, q3);
+        for (int i = 0; i < 8; i++) {
+          const bool ok = FULL || 16 * i < left;
+          const float4 ov = *reinterpret_cast<const float4*>(st_rd + i * 16 * PITCH);
+          float2 o01 = make_float2(ov.x, ov.y), o23 = make_float2(ov.z, ov.w);
+          if (CONV2) { o01 = __fadd2_rn(o01, make_float2(rv[i].x, rv[i].y)); o23 = __fadd2_rn(o23, make_float2(rv[i].z, rv[i].w)); }
+          o01 = __fadd2_rn(o01, b01); o23 = __fadd2_rn(o23, b23);
+          if (!FULL) { o01.x = ok ? o01.x : 0.f; o01.y = ok ? o01.y : 0.f; o23.x = ok ? o23.x : 0.f; o23.y = ok ? o23.y : 0.f; }
+          s01 = __fadd2_rn(s01, o01); s23 = __fadd2_rn(s23, o23);
+          q01 = __ffma2_rn(o01, o01, q01); q23 = __ffma2_rn(o23, o23, q23);
+          if (!CONV2) {
+            uint2 pk;
+            pk.x = pack_bf16(o01.x, o01.y); pk.y = pack_bf16(o23.x, o23.y);
+            if (ok) *reinterpret_cast<uint2*>(a.out_bf16 + g0 + i * RS) = pk;
+          } else {
+            o01 = __fmul2_rn(o01, os2); o23 = __fmul2_rn(o23, os2);
+            float* op = a.out_f32 + g0 + i * RS;
+            if (ok) {
+              if (accum)   // exactly one add per element and launch -> order-independent, no load round trip
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(o01.x), "f"(o01.y), "f"(o23.x), "f"(o23.y) : "memory");
+              else
+                *reinterpret_cast<float4*>(op) = make_float4(o01.x, o01.y, o23.x, o23.y);
             }
           }
         }
+        TICK(5);
+        // refill this register buffer with the operand of iteration e+2 (possibly of the next tile)
+        if (e + 2 < E) fetch(L, off, m0, e + 2, rv);
+        else if (has_next) fetch(nL, noff, nm0, e + 2 - E, rv);
+        TICK(6);
         if (a.part) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          float* pp = a.part + ((size_t)b * a.nchunk + (size_t)(sm0 >> 7)) * 2 * BN;
-          for (int n = t; n < BN; n += 128) {
-            float S = 0.f, Q = 0.f;
+          // rows of one column quad live in lanes l, l+8, l+16, l+24
 #pragma unroll
-            for (int w = 0; w < 4; w++) { S += stat_f[((size_t)w * BN + n) * 2]; Q += stat_f[((size_t)w * BN + n) * 2 + 1]; }
-            pp[n] = S; pp[BN + n] = Q;
+          for (int d = 8; d <= 16; d <<= 1) {
+            float2 t0, t1, t2, t3;
+            t0.x = __shfl_xor_sync(0xffffffffu, s01.x, d); t0.y = __shfl_xor_sync(0xffffffffu, s01.y, d);
+            t1.x = __shfl_xor_sync(0xffffffffu, s23.x, d); t1.y = __shfl_xor_sync(0xffffffffu, s23.y, d);
+            t2.x = __shfl_xor_sync(0xffffffffu, q01.x, d); t2.y = __shfl_xor_sync(0xffffffffu, q01.y, d);
+            t3.x = __shfl_xor_sync(0xffffffffu, q23.x, d); t3.y = __shfl_xor_sync(0xffffffffu, q23.y, d);
+            s01 = __fadd2_rn(s01, t0); s23 = __fadd2_rn(s23, t1); q01 = __fadd2_rn(q01, t2); q23 = __fadd2_rn(q23, t3);
           }
-          // the next sub-tile's first statistic write happens after its own bar.sync
+          if (lane < 8) {
+            // warp w of the group covers rows 2w, 2w+1 (+16i) of the transposed tile: slot (t >> 5)
+            float* sp = stat_f + ((size_t)(t >> 5) * BN + n) * 2;
+            *reinterpret_cast<float4*>(sp) = make_float4(s01.x, q01.x, s01.y, q01.y);
+            *reinterpret_cast<float4*>(sp + 4) = make_float4(s23.x, q23.x, s23.y, q23.y);
+          }
+          if (ci == NCH - 1) {   // sub-tile complete: combine the four warps' sums in a fixed order
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (t < BN / 2) {
+              const int nn = ((t >> 5) * 2 + eg) * 32 + (t & 31);
+              float* pp = a.part + ((size_t)b * a.nchunk + (size_t)((m0 >> 7) + sub)) * 2 * BN + nn;
+              const float* sf = stat_f + 2 * nn;
+              pp[0] = (sf[0] + sf[2 * BN]) + (sf[4 * BN] + sf[6 * BN]);
+              pp[BN] = (sf[1] + sf[2 * BN + 1]) + (sf[4 * BN + 1] + sf[6 * BN + 1]);
+            }
+            // the next statistic write happens after two more group barriers
+          }
         }
+        TICK(7);
+      };
+      if (L - m0 >= MT) {   // hot path: full tile, no row predicates
+#pragma unroll 1
+        for (int e = 0; e < E; e += 2) {
+          body(e, rv0, std::true_type{});
+          body(e + 1, rv1, std::true_type{});
+        }
+        continue;
       }
-      if (nsub <= 0) {   // cannot happen (tiles only cover rows < len); keep the pipeline protocol intact anyway
-        tc_fence_before();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
+#pragma unroll 1
+      for (int e = 0; e < E; e += 2) {   // last tile of an item
+        body(e, rv0, std::false_type{});
+        body(e + 1, rv1, std::false_type{});
       }
     }
+    TIM_FLUSH(8, 9);
   } else {
     // ------------------------------------------------------------------ operand producers
-    const int pt = threadIdx.x - 192;       // 0..255
+    // y = snake(x*sc + sh) = ial * (u + sin(u)^2), u = x*(al*sc) + al*sh: three per-channel coefficients,
+    // cached in smem per item.  Loads run one group (4 passes of 24 rows) ahead of the transform through
+    // two register buffers, across chunk and tile boundaries, so HBM/L2 latency stays hidden.
+    const int pt = threadIdx.x - 320;       // 0..191
     const int cg = pt & 7;                  // 8-channel group inside the 64-channel chunk
-    const int rl = pt >> 3;                 // row lane 0..31
-    constexpr int GP = (MSUB == 2) ? 5 : 3; // passes (of 32 rows) per load group
-    constexpr int NG = 2;
+    const int rl = pt >> 3;                 // row lane 0..23
+    constexpr int GP = 4;
+    constexpr int GR = GP * kProdRows;      // rows per load group (96: a multiple of 8 -> constant swizzle phase)
     const int ra_used = MT + 2 * pad;       // <= Cfg::RA
-    int gA = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int b, mt;
-      tile_decode(s_ts, B, tile, b, mt);
-      const int L = a.len[b], off = a.off[b];
-      const int r0 = mt * MT - pad;         // item-relative row of A-slot row 0
-      for (int c = 0; c < KCH; c++, gA++) {
-        const int sa = gA % NA;
-        const int ch0 = c * 64 + cg * 8;
-        float sc[8], sh[8], al[8], ial[8];
-        {
-          const float4 t0 = *reinterpret_cast<const float4*>(a.scale + (size_t)b * BN + ch0);
-          const float4 t1 = *reinterpret_cast<const float4*>(a.scale + (size_t)b * BN + ch0 + 4);
-          sc[0] = t0.x; sc[1] = t0.y; sc[2] = t0.z; sc[3] = t0.w; sc[4] = t1.x; sc[5] = t1.y; sc[6] = t1.z; sc[7] = t1.w;
-          const float4 u0 = *reinterpret_cast<const float4*>(a.shift + (size_t)b * BN + ch0);
-          const float4 u1 = *reinterpret_cast<const float4*>(a.shift + (size_t)b * BN + ch0 + 4);
-          sh[0] = u0.x; sh[1] = u0.y; sh[2] = u0.z; sh[3] = u0.w; sh[4] = u1.x; sh[5] = u1.y; sh[6] = u1.z; sh[7] = u1.w;
-          const float4 v0 = *reinterpret_cast<const float4*>(a.alpha + ch0);
-          const float4 v1 = *reinterpret_cast<const float4*>(a.alpha + ch0 + 4);
-          al[0] = v0.x; al[1] = v0.y; al[2] = v0.z; al[3] = v0.w; al[4] = v1.x; al[5] = v1.y; al[6] = v1.z; al[7] = v1.w;
+    const int ngc = (ra_used + GR - 1) / GR;                 // load groups per chunk
+    float* const coef = reinterpret_cast<float*>(gbase + (coef_base - base));   // [3][BN]: al*sc, al*sh, 1/al
+    const int F = (t_end - t_begin) * KCH * ngc;
+    using Raw = typename std::conditional<CONV2, uint4, float4>::type;
+    constexpr int RPP = CONV2 ? 1 : 2;      // raw vectors per pass (8 channels)
+    constexpr int XE = CONV2 ? 2 : 4;       // bytes per input element
+    // this thread's byte offset inside an A slot, minus the row part: 16-byte chunk cg of row r sits at
+    // chunk position cg ^ (r & 7); all rows this thread writes have r = rl (mod 8)
+    const uint32_t sw = (uint32_t)rl * 128u + (uint32_t)((cg ^ (rl & 7)) << 4);
+
+    TileCur lc; int l_c = 0, l_g = 0;                                  // load stream
+    TileCur sc_; int s_c = 0, s_g = 0, gA = 0, coef_b = -1;             // transform stream
+    if (F > 0) { lc.init(s_ts, B, t_begin); sc_ = lc; }
+    float2 cA[4], cB[4], cI[4];
+#ifdef KKX_ARB_TIMING
+    long long tim_acc[5] = {0}; long long tim_last = clock64();
+    const bool tim_on = a.timing && blockIdx.x == 0 && warp == 10 && lane == 0;
+#endif
+
+    auto issue = [&](Raw (&rb)[GP][RPP]) {
+      const int L = s_len[lc.b];
+      const int row = lc.mt * MT - pad + l_g * GR + rl;     // item-relative row of pass 0
+      const int rloc = l_g * GR + rl;
+      const char* xp = reinterpret_cast<const char*>(a.x) + ((size_t)(s_off[lc.b] + row) * BN + (l_c * 64 + cg * 8)) * XE;
 #pragma unroll
-          for (int e = 0; e < 8; e++) ial[e] = __fdividef(1.f, al[e]);
+      for (int p = 0; p < GP; p++) {
+        if ((unsigned)(row + p * kProdRows) < (unsigned)L && rloc + p * kProdRows < ra_used) {
+#pragma unroll
+          for (int v = 0; v < RPP; v++)
+            rb[p][v] = *reinterpret_cast<const Raw*>(xp + (size_t)p * kProdRows * BN * XE + v * 16);
         }
-        uint8_t* const slot = gbase + (a_base - base) + (size_t)sa * Cfg::A_SLOT;
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-          float xv[GP][8];
-          // issue this group's loads first (they overlap the slot wait and the previous group's math)
-#pragma unroll
-          for (int p = 0; p < GP; p++) {
-            const int rloc = (g * GP + p) * 32 + rl;
-            const int gr = r0 + rloc;
-            const bool ok = rloc < ra_used && gr >= 0 && gr < L;
-            if (IN_BF16) {
-              uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-              if (ok) raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.x) + (size_t)(off + gr) * BN + ch0);
-              xv[p][0] = __uint_as_float(raw.x << 16); xv[p][1] = __uint_as_float(raw.x & 0xFFFF0000u);
-              xv[p][2] = __uint_as_float(raw.y << 16); xv[p][3] = __uint_as_float(raw.y & 0xFFFF0000u);
-              xv[p][4] = __uint_as_float(raw.z << 16); xv[p][5] = __uint_as_float(raw.z & 0xFFFF0000u);
-              xv[p][6] = __uint_as_float(raw.w << 16); xv[p][7] = __uint_as_float(raw.w & 0xFFFF0000u);
-            } else {
-              float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
-              if (ok) {
-                const float* xp = reinterpret_cast<const float*>(a.x) + (size_t)(off + gr) * BN + ch0;
-                f0 = *reinterpret_cast<const float4*>(xp);
-                f1 = *reinterpret_cast<const float4*>(xp + 4);
-              }
-              xv[p][0] = f0.x; xv[p][1] = f0.y; xv[p][2] = f0.z; xv[p][3] = f0.w;
-              xv[p][4] = f1.x; xv[p][5] = f1.y; xv[p][6] = f1.z; xv[p][7] = f1.w;
-            }
+      }
+      if (++l_g == ngc) { l_g = 0; if (++l_c == KCH) { l_c = 0; lc.next(s_ts); } }
+    };
+    auto process = [&](Raw (&rb)[GP][RPP]) {
+      const int b = sc_.b;
+      const int sa = gA % NA;
+      if (s_g == 0) {
+        if (b != coef_b) {   // new item: rebuild the coefficient table (all producer threads take this branch together)
+          asm volatile("bar.sync 3, 192;" ::: "memory");
+          for (int ch = pt; ch < BN; ch += kProdThreads) {
+            const float al = a.alpha[ch], s = a.scale[(size_t)b * BN + ch], h = a.shift[(size_t)b * BN + ch];
+            coef[ch] = al * s; coef[BN + ch] = al * h; coef[2 * BN + ch] = 1.0f / al;
           }
-          if (g == 0) mbar_wait(emptyA(sa), (((uint32_t)(gA / NA)) & 1u) ^ 1u);
-#pragma unroll
-          for (int p = 0; p < GP; p++) {
-            const int rloc = (g * GP + p) * 32 + rl;
-            if (rloc >= ra_used) continue;
-            const int gr = r0 + rloc;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (gr >= 0 && gr < L) {
-              float y[8];
-#pragma unroll
-              for (int e = 0; e < 8; e++) y[e] = snake_f(fmaf(xv[p][e], sc[e], sh[e]), al[e], ial[e]);
-              pk.x = pack_bf16(y[0], y[1]); pk.y = pack_bf16(y[2], y[3]);
-              pk.z = pack_bf16(y[4], y[5]); pk.w = pack_bf16(y[6], y[7]);
-            }
-            *reinterpret_cast<uint4*>(slot + (size_t)rloc * 128 + ((cg ^ (rloc & 7)) << 4)) = pk;
-          }
+          asm volatile("bar.sync 3, 192;" ::: "memory");
+          coef_b = b;
         }
+        const float* cp = coef + s_c * 64 + cg * 8;
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const float4 t0 = *reinterpret_cast<const float4*>(cp + 2 * e);
+          const float4 t1 = *reinterpret_cast<const float4*>(cp + BN + 2 * e);
+          const float4 t2 = *reinterpret_cast<const float4*>(cp + 2 * BN + 2 * e);
+          cA[e] = make_float2(t0.x, t0.y); cA[e + 1] = make_float2(t0.z, t0.w);
+          cB[e] = make_float2(t1.x, t1.y); cB[e + 1] = make_float2(t1.z, t1.w);
+          cI[e] = make_float2(t2.x, t2.y); cI[e + 1] = make_float2(t2.z, t2.w);
+        }
+        TICK(1);
+        mbar_wait(emptyA(sa), (((uint32_t)(gA / NA)) & 1u) ^ 1u);
+        TICK(2);
+      }
+      const int L = s_len[b];
+      const int row = sc_.mt * MT - pad + s_g * GR + rl;
+      const int rloc = s_g * GR + rl;
+      uint8_t* const sp = gbase + (a_base - base) + (size_t)sa * Cfg::A_SLOT + (size_t)(s_g * GR) * 128 + sw;
+#pragma unroll
+      for (int p = 0; p < GP; p++) {
+        // straight-line: rows outside the item produce zeros through a select, only the store is predicated
+        const bool inside = (unsigned)(row + p * kProdRows) < (unsigned)L;
+        float2 xv[4];
+        if (CONV2) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(&rb[p][0]);
+          xv[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
+          xv[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+          xv[2] = make_float2(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xFFFF0000u));
+          xv[3] = make_float2(__uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xFFFF0000u));
+        } else {
+          const float4 f0 = *reinterpret_cast<const float4*>(&rb[p][0]);
+          const float4 f1 = *reinterpret_cast<const float4*>(&rb[p][RPP - 1]);
+          xv[0] = make_float2(f0.x, f0.y); xv[1] = make_float2(f0.z, f0.w);
+          xv[2] = make_float2(f1.x, f1.y); xv[3] = make_float2(f1.z, f1.w);
+        }
+        uint32_t pw[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {   // packed fp32 math around the two scalar MUFU.SIN
+          const float2 u = __ffma2_rn(xv[e], cA[e], cB[e]);
+          const float2 sn = make_float2(__sinf(u.x), __sinf(u.y));
+          const float2 y = __fmul2_rn(__ffma2_rn(sn, sn, u), cI[e]);
+          pw[e] = inside ? pack_bf16(y.x, y.y) : 0u;
+        }
+        const uint4 pk = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        if (rloc + p * kProdRows < ra_used) *reinterpret_cast<uint4*>(sp + p * kProdRows * 128) = pk;
+      }
+      TICK(3);
+      if (++s_g == ngc) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fullA(sa)) : "memory");
+        s_g = 0; gA++;
+        if (++s_c == KCH) { s_c = 0; sc_.next(s_ts); }
       }
+    };
+
+    Raw bufA[GP][RPP], bufB[GP][RPP];
+#pragma unroll
+    for (int p = 0; p < GP; p++)
+#pragma unroll
+      for (int v = 0; v < RPP; v++) { bufA[p][v] = Raw(); bufB[p][v] = Raw(); }
+    if (F > 0) issue(bufA);
+#pragma unroll 1
+    for (int f = 0; f < F; f += 2) {
+      if (f + 1 < F) issue(bufB);
+      TICK(0);
+      process(bufA);
+      if (f + 1 >= F) break;
+      if (f + 2 < F) issue(bufA);
+      TICK(0);
+      process(bufB);
     }
+    TIM_FLUSH(20, 5);
   }
   tc_fence_before();
   __syncthreads();
@@ -371,7 +527,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   }
 }
 
-template <int BN, int MSUB, bool IN_BF16>
+template <int BN, int MSUB, bool CONV2>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   using Cfg = ArbCfg<BN, MSUB>;
   static bool attr_set[64] = {false};
@@ -379,13 +535,13 @@ void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, IN_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
   const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
-  arb_conv_kernel<BN, MSUB, IN_BF16><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  arb_conv_kernel<BN, MSUB, CONV2><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 }  // namespace
@@ -400,6 +556,9 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
   if (g_dry_run) return;
   if (a.total_tiles <= 0 || a.B <= 0) return;
   if (!arb_conv_supported(a.C, a.ks, a.dil, a.B)) throw ArgError("launch_arb_conv: unsupported shape");
+  // two roles: fp32 in -> bf16 out (+statistics), or bf16 in + fp32 residual -> fp32 out
+  if (a.in_bf16 ? (!a.out_f32 || a.out_bf16 || !a.res) : (!a.out_bf16 || a.out_f32 || a.res || a.accumulate))
+    throw ArgError("launch_arb_conv: unsupported input/output combination");
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.C * a.C * a.ks;
   if (a.C == 128) {
     if (a.in_bf16) launch_arb_t<128, 2, true>(a, st); else launch_arb_t<128, 2, false>(a, st);

@@ -587,6 +587,7 @@ void Model::run() {
   }
   KKX_CUDA(cudaEventRecord(ev1_, stream_));
   KKX_CUDA(cudaStreamSynchronize(stream_));
+  arb_timing_dump();
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0_, ev1_);
   last_gpu_us = ms * 1e3;

@@ -87,6 +87,8 @@ struct Weights {
   int sty_pro_n = 0, sty_dec_n = 0;
 };
 
+void arb_timing_dump();  // diagnostics (model_forward.cu); no-op unless KKX_ARB_TIMING=1
+
 struct DebugStage { std::vector<float> data; long long rows = 0, cols = 0; };
 
 struct Options {

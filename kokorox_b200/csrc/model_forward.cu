@@ -9,6 +9,18 @@
 namespace kkx {
 
 namespace {
+// diagnostics: per-role phase cycle counters of the fused res-block conv (KKX_ARB_TIMING=1 on a
+// -DKKX_ARB_TIMING build); 4 variants (conv1/conv2 x C128/C256) x 32 slots
+long long* g_arb_timing = nullptr;
+long long* arb_timing_buf() {
+  static const bool on = [] { const char* e = getenv("KKX_ARB_TIMING"); return e && e[0] == '1'; }();
+  if (!on) return nullptr;
+  if (!g_arb_timing) {
+    KKX_CUDA(cudaMalloc(&g_arb_timing, 128 * sizeof(long long)));
+    KKX_CUDA(cudaMemset(g_arb_timing, 0, 128 * sizeof(long long)));
+  }
+  return g_arb_timing;
+}
 ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float* w, const float* bias,
                    int N, float* out, int ldo, int ocol) {
   ConvArgs a;
@@ -19,6 +31,23 @@ ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float*
   return a;
 }
 }  // namespace
+
+void arb_timing_dump() {
+  if (!g_arb_timing) return;
+  long long h[128];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, g_arb_timing, sizeof h, cudaMemcpyDeviceToHost);
+  cudaMemset(g_arb_timing, 0, sizeof h);
+  const char* nm[4] = {"conv1 C128", "conv2 C128", "conv1 C256", "conv2 C256"};
+  for (int v = 0; v < 4; v++) {
+    const long long* t = h + v * 32;
+    fprintf(stderr, "[arb timing %s] (Mcycles)  TMA wait %.2f issue %.2f | MMA wait_tempty %.2f wait_fullA %.2f wait_fullB %.2f issue %.2f |"
+            " EPI wait_tfull %.2f tmem_ld %.2f barA %.2f sts %.2f barB %.2f compute+store %.2f fetch %.2f stats %.2f tile %.2f |"
+            " PROD issue %.2f coef %.2f wait_emptyA %.2f transform %.2f mov+arrive %.2f\n", nm[v],
+            t[0] / 1e6, t[1] / 1e6, t[4] / 1e6, t[5] / 1e6, t[6] / 1e6, t[7] / 1e6, t[8] / 1e6, t[9] / 1e6, t[10] / 1e6, t[11] / 1e6,
+            t[12] / 1e6, t[13] / 1e6, t[14] / 1e6, t[15] / 1e6, t[16] / 1e6, t[20] / 1e6, t[21] / 1e6, t[22] / 1e6, t[23] / 1e6, t[24] / 1e6);
+  }
+}
 
 void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, int dil, int pad, const Level& Lin,
                     const Level& Lm, const float* bias, float* out, int ldo, int ocol, const Level& Lout, int ors,
@@ -286,7 +315,6 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
   const bool tc = opt.precision == 1;
   void* abuf = tc ? A.alloc_bytes((size_t)L.rows * w.t1[0].Cpad * 2) : nullptr;
   static const bool fused_ok = [] { const char* e = getenv("KKX_ARB_FUSED"); return !e || e[0] != '0'; }();
-  static const int desc_mode = [] { const char* e = getenv("KKX_ARB_DESC"); return e ? atoi(e) : 0; }();
   if (tc && fused_ok && arb_conv_supported(C, k, 5, B)) {
     // fused path (kernels_arb.cu): AdaIN + Snake inside the conv kernel, bf16 intermediate, column
     // statistics for the next AdaIN from the conv epilogues -- one colstats pass per res-block
@@ -294,11 +322,13 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
     base.C = C; base.ks = k; base.off = L.d_off; base.len = L.d_len; base.B = B; base.sum_m = L.sum_len;
     base.tile_start = C == 128 ? L.d_tiles256 : L.d_tiles128;
     base.total_tiles = C == 128 ? L.ntiles256 : L.ntiles128;
-    base.scale = sc; base.shift = sh; base.nchunk = nch; base.desc_mode = desc_mode;
+    base.scale = sc; base.shift = sh; base.nchunk = nch;
     launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    long long* tim = arb_timing_buf();
     for (int j = 0; j < 3; j++) {
       launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
       ArbConvArgs c1 = base;
+      if (tim) c1.timing = tim + (C == 128 ? 0 : 64);
       c1.x = cur; c1.in_bf16 = 0; c1.alpha = w.a1[j]; c1.tmB = w.t1[j].tmap; c1.dil = dil[j];
       c1.pad = dil[j] * (k - 1) / 2; c1.bias = w.b1[j];
       c1.out_bf16 = static_cast<__nv_bfloat16*>(abuf); c1.part = part;
@@ -306,6 +336,7 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
       launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s2[j], 1e-5f, sc, sh, B, st);
       float* dst = (j == 2) ? out : xw;
       ArbConvArgs c2 = base;
+      if (tim) c2.timing = tim + (C == 128 ? 32 : 96);
       c2.x = abuf; c2.in_bf16 = 1; c2.alpha = w.a2[j]; c2.tmB = w.t2[j].tmap; c2.dil = 1; c2.pad = (k - 1) / 2;
       c2.bias = w.b2[j]; c2.out_f32 = dst; c2.res = cur;
       if (j == 2) { c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; } else c2.part = part;

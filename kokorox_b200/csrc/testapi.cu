@@ -265,7 +265,7 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
     a.out_bf16 = want_bf16 ? doutb.as<__nv_bfloat16>() : nullptr;
     a.out_f32 = want_bf16 ? nullptr : dout.as<float>();
     a.res = res ? dres.as<float>() : nullptr; a.oscale = oscale; a.accumulate = accumulate;
-    a.part = sums ? dpart.as<float>() : nullptr; a.nchunk = nchunk; a.desc_mode = desc_mode;
+    a.part = sums ? dpart.as<float>() : nullptr; a.nchunk = nchunk; (void)desc_mode;
     launch_arb_conv(a, 0);
     KKX_CUDA(cudaDeviceSynchronize());
     if (want_bf16) {
