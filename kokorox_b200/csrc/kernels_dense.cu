@@ -464,31 +464,70 @@ __global__ void __launch_bounds__(1024) lstm_kernel(const float* __restrict__ xp
 namespace kkx {
 namespace cg = cooperative_groups;
 
+// Step hand-off without a cluster barrier: every CTA pushes its new h slice (vectorised, 16 bytes per
+// store) into the next-step h buffer of all 8 CTAs with st.async, which completes transaction bytes on the
+// DESTINATION CTA's mbarrier; a CTA starts step s+1 as soon as its own barrier has seen all 8 slices.
+// Two h buffers / two barriers (step parity) make the scheme race-free: a CTA can only be one step ahead
+// of the slowest one, because it needs that CTA's slice to proceed.
+__device__ __forceinline__ uint32_t lstm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lstm_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void lstm_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LD_%=;\n\t"
+      "bra LW_%=;\n\t"
+      "LD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// Register blocking of the per-step dot products (the kernel is bound by shared-memory wavefronts, not by
+// FMAs): a thread owns TWO gate rows and one QUARTER of the k range for all G items, so every h vector
+// fetched from smem feeds 8 FMAs and every weight vector G*4.  Layouts are chosen so that each LDS.128 is
+// served in the minimum number of wavefronts: weights [k/4][row parity][row pair] (8 lanes = 128 contiguous
+// bytes), h [item][quarter][64 + 4 pad] (the 4 quarters of a warp hit 4 different bank groups, lanes of
+// a quarter broadcast).
+constexpr int kHQ = 68;                 // floats per h quarter (64 + 4 pad)
+constexpr int kHItem = 4 * kHQ;         // floats per item in an h buffer
+
 template <int G>
 __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __restrict__ xproj,
                                                               const float* __restrict__ whhT,
                                                               float* __restrict__ out, int ldo, int ocol,
                                                               const int* off, const int* len, int B) {
   extern __shared__ float4 lsm4[];
-  float* Ws = reinterpret_cast<float*>(lsm4);          // [64 k4][128 rows][4]
-  float* hbuf = Ws + 256 * 128;                        // [2][G][256]
-  float* gates = hbuf + 2 * G * 256;                   // [G][128]
+  float* Ws = reinterpret_cast<float*>(lsm4);          // [64 k4][2 parity][64 row pairs][4]
+  float* hbuf = Ws + 256 * 128;                        // [2][G][4][68]
+  float* gates = hbuf + 2 * G * kHItem;                // [G][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gates + G * 128);   // [2] h-buffer "full" barriers
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();             // 0..7: hidden-unit slice
   const int group = blockIdx.x >> 3, dir = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int half = lane >> 4, rloc = warp * 16 + (lane & 15);   // gate row (local) of this thread
-  const int gate = rloc >> 5, jl = rloc & 31;
-  const int grow = gate * 256 + r * 32 + jl;                    // global gate row
+  const int q = lane >> 3;                             // k quarter [64q, 64q+64)
+  const int rp = warp * 8 + (lane & 7);                // row pair: local gate rows 2rp, 2rp+1
+  constexpr uint32_t kStepBytes = G * 256 * 4;         // bytes every CTA receives per step
 
-  // stage this CTA's 128 KB weight slice: Ws[(k>>2)][rloc][k&3] = W_hh^T[dir][k][grow(rloc)]
+  // stage this CTA's 128 KB weight slice; local row rl = gate*32 + j  <->  W_hh row gate*256 + r*32 + j
   const float* Wg = whhT + (size_t)dir * 256 * 1024;
   for (int i = tid; i < 256 * 128; i += 256) {
     const int k = i >> 7, rl = i & 127;
     const int gr = (rl >> 5) * 256 + r * 32 + (rl & 31);
-    Ws[((k >> 2) * 128 + rl) * 4 + (k & 3)] = Wg[(size_t)k * 1024 + gr];
+    Ws[(((k >> 2) * 2 + (rl & 1)) * 64 + (rl >> 1)) * 4 + (k & 3)] = Wg[(size_t)k * 1024 + gr];
   }
-  for (int i = tid; i < 2 * G * 256; i += 256) hbuf[i] = 0.f;
+  for (int i = tid; i < 2 * G * kHItem; i += 256) hbuf[i] = 0.f;
+  const uint32_t bar0 = lstm_smem_u32(bars), bar1 = bar0 + 8;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // buffer 1 receives h_1 during step 0
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar1), "r"(kStepBytes) : "memory");
+  }
 
   int ioff[G], ilen[G];
   int maxN = 0;
@@ -499,43 +538,63 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
     ilen[g] = item < B ? len[item] : 0;
     maxN = max(maxN, ilen[g]);
   }
+  // global gate rows of this thread's row pair (same gate block: 2rp and 2rp+1 never straddle 32)
+  const int grow0 = ((2 * rp) >> 5) * 256 + r * 32 + ((2 * rp) & 31);
   float c = 0.f;                                         // cell state of (item tid>>5, unit tid&31)
+  float2 xpn[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    xpn[g] = make_float2(0.f, 0.f);
+    if ((g & 3) == q && ilen[g] > 0) {
+      const int t = dir == 0 ? 0 : ilen[g] - 1;
+      xpn[g] = *reinterpret_cast<const float2*>(xproj + (size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow0);
+    }
+  }
   cluster.sync();
 
   for (int s = 0; s < maxN; s++) {
-    const float* hc = hbuf + (s & 1) * G * 256;
-    float* hn_local = hbuf + ((s + 1) & 1) * G * 256;
-    // prefetch this step's input projections (consumed after the dot loop)
-    float xp[G];
+    const uint32_t bcur = (s & 1) ? bar1 : bar0;
+    if (s > 0) lstm_mbar_wait(bcur, (uint32_t)((s - 1) >> 1) & 1u);   // h_s complete in hbuf[s&1]
+    // re-arm this buffer's barrier for its next use (h_{s+2}); no slice of h_{s+2} can be complete before
+    // this CTA has sent h_{s+1}, and early bytes only drive the (signed) tx-count of the new phase
+    if (tid == 0 && s + 2 < maxN)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bcur), "r"(kStepBytes) : "memory");
+    const float* hc = hbuf + (s & 1) * G * kHItem;
+    float* hn_local = hbuf + ((s + 1) & 1) * G * kHItem;
+    // input projections were fetched one step ahead (xpn); fetch the next step's now so that the global
+    // latency hides behind a whole step.  Lane quarter q finishes the items g with (g & 3) == q.
+    float2 xp[G];
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      xp[g] = 0.f;
-      if (half == 0 && s < ilen[g]) {
-        const int t = dir == 0 ? s : ilen[g] - 1 - s;
-        xp[g] = xproj[(size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow];
+      xp[g] = xpn[g];
+      if ((g & 3) == q && s + 1 < ilen[g]) {
+        const int t = dir == 0 ? s + 1 : ilen[g] - 2 - s;
+        xpn[g] = *reinterpret_cast<const float2*>(xproj + (size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow0);
       }
     }
-    float acc[G];
+    float acc0[G], acc1[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) acc[g] = 0.f;
-    const float4* w4 = reinterpret_cast<const float4*>(Ws) + (half * 32) * 128 + rloc;
-    const float4* h4 = reinterpret_cast<const float4*>(hc) + half * 32;
+    for (int g = 0; g < G; g++) { acc0[g] = 0.f; acc1[g] = 0.f; }
+    const float4* w4 = reinterpret_cast<const float4*>(Ws) + (size_t)(q * 16) * 128 + rp;
+    const float4* h4 = reinterpret_cast<const float4*>(hc + q * kHQ);
 #pragma unroll 4
-    for (int kk = 0; kk < 32; kk++) {
-      const float4 w = w4[kk * 128];
+    for (int kk = 0; kk < 16; kk++) {
+      const float4 wa = w4[kk * 128], wb = w4[kk * 128 + 64];
 #pragma unroll
       for (int g = 0; g < G; g++) {
-        const float4 h = h4[g * 64 + kk];
-        acc[g] = fmaf(w.x, h.x, acc[g]);
-        acc[g] = fmaf(w.y, h.y, acc[g]);
-        acc[g] = fmaf(w.z, h.z, acc[g]);
-        acc[g] = fmaf(w.w, h.w, acc[g]);
+        const float4 h = h4[g * (kHItem / 4) + kk];
+        acc0[g] = fmaf(wa.x, h.x, acc0[g]); acc1[g] = fmaf(wb.x, h.x, acc1[g]);
+        acc0[g] = fmaf(wa.y, h.y, acc0[g]); acc1[g] = fmaf(wb.y, h.y, acc1[g]);
+        acc0[g] = fmaf(wa.z, h.z, acc0[g]); acc1[g] = fmaf(wb.z, h.z, acc1[g]);
+        acc0[g] = fmaf(wa.w, h.w, acc0[g]); acc1[g] = fmaf(wb.w, h.w, acc1[g]);
       }
     }
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], 16);
-      if (half == 0) gates[g * 128 + rloc] = acc[g] + xp[g];
+      acc0[g] += __shfl_xor_sync(0xffffffffu, acc0[g], 8);  acc1[g] += __shfl_xor_sync(0xffffffffu, acc1[g], 8);
+      acc0[g] += __shfl_xor_sync(0xffffffffu, acc0[g], 16); acc1[g] += __shfl_xor_sync(0xffffffffu, acc1[g], 16);
+      if ((g & 3) == q)
+        *reinterpret_cast<float2*>(gates + g * 128 + 2 * rp) = make_float2(acc0[g] + xp[g].x, acc1[g] + xp[g].y);
     }
     __syncthreads();
     if (tid < 32 * G) {
@@ -551,18 +610,31 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
         const int t = dir == 0 ? s : ilen[g] - 1 - s;
         out[(size_t)(ioff[g] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
       }
-      float* dst_local = hn_local + g * 256 + r * 32 + j;
+      // gather 4 consecutive hidden units into one lane, push 16 bytes to every CTA of the cluster
+      const float h1 = __shfl_down_sync(0xffffffffu, hv, 1);
+      const float h2 = __shfl_down_sync(0xffffffffu, hv, 2);
+      const float h3 = __shfl_down_sync(0xffffffffu, hv, 3);
+      if ((j & 3) == 0 && s + 1 < maxN) {
+        const int u = r * 32 + j;                        // hidden unit -> padded quarter layout
+        const uint32_t dst = lstm_smem_u32(hn_local + g * kHItem + (u >> 6) * kHQ + (u & 63));
+        const uint32_t bnext = (s & 1) ? bar0 : bar1;
 #pragma unroll
-      for (int d = 0; d < 8; d++) *cluster.map_shared_rank(dst_local, d) = hv;
+        for (int d = 0; d < 8; d++) {
+          const uint32_t ra = lstm_mapa(dst, (uint32_t)d), rb = lstm_mapa(bnext, (uint32_t)d);
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                       ::"r"(ra), "f"(hv), "f"(h1), "f"(h2), "f"(h3), "r"(rb) : "memory");
+        }
+      }
     }
-    cluster.sync();   // new h visible cluster-wide; everyone is done with the old h and the gates
+    __syncthreads();   // gates[] is rewritten by the next step's dot loop
   }
+  cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
 
 template <int G>
 static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                                 const int* off, const int* len, int B, cudaStream_t st) {
-  const size_t smem = (size_t)(256 * 128 + 2 * G * 256 + G * 128) * sizeof(float);
+  const size_t smem = (size_t)(256 * 128 + 2 * G * kHItem + G * 128) * sizeof(float) + 16;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
