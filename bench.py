@@ -225,8 +225,9 @@ def main():
             json.dump(prof, f, indent=1)
 
     # ---------------- e2e: host buffers through the public call, copies inside the timed region
-    for _ in range(min(args.warmup, 2)):
-        m.infer_batch(toks, styles, speeds)
+    outs = None
+    for _ in range(max(args.warmup, 3)):   # same call pattern as the timed loop: the previous result is still alive
+        outs = m.infer_batch(toks, styles, speeds)   # during the next call, so the library cycles two pinned buffers
     barrier()
     t1 = time.perf_counter()
     e2e_audio = 0.0
@@ -264,18 +265,34 @@ def main():
         kern = prof.get("kernels", {})
         top = max(kern.items(), key=lambda kv: kv[1][1]) if kern else ("none", [0, 0.0])
         total_us = sum(v[1] for v in kern.values()) or 1.0
-        conv_names = [k for k in kern if k.startswith("conv")]
+        # roofline of the dominant kernel family.  The generator res-block convs (kernels_arb.cu, "arb_conv")
+        # dominate the step; they are tensor-pipe work whose activations (GBs per launch) stream through HBM, so
+        # both fractions are reported: algorithmic FLOPs and algorithmic bytes (every tensor once) over the summed,
+        # event-timed launch durations of that kernel.
+        conv_names = [k for k in kern if k.startswith("conv") or k == "arb_conv"]
         conv_us = sum(kern[k][1] for k in conv_names) or 1.0
-        conv_n = sum(kern[k][0] for k in conv_names) or 1
-        achieved_tf = prof.get("conv_flops", 0.0) / (conv_us * 1e-6) / 1e12
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_gbs = peaks.get("hbm_gbs", 6650.0)
+        dom = "arb_conv" if "arb_conv" in kern else (top[0] if top[0].startswith("conv") else "conv")
+        if dom == "arb_conv":
+            dn, dus = kern[dom]
+            dflops, dbytes = prof.get("arb_flops", 0.0), prof.get("arb_bytes", 0.0)
+        else:
+            dn = sum(kern[k][0] for k in conv_names) or 1
+            dus, dflops, dbytes = conv_us, prof.get("conv_flops", 0.0), 0.0
+        achieved_tf = dflops / (dus * 1e-6) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "+".join(sorted(conv_names)) or "none",
+            "bound": "tensor", "kernel": dom,
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
             "traffic": None, "peak_source": f"{peaks_src} (sustained bf16; kernel timed inside a long step)",
-            "launches_per_step": conv_n, "avg_launch_us": conv_us / conv_n,
-            "alg_flops_per_launch": prof.get("conv_flops", 0.0) / conv_n,
-            "share_of_step": conv_us / total_us, "top_kernel": top[0], "top_kernel_share": top[1][1] / total_us,
+            "launches_per_step": dn, "avg_launch_us": dus / max(dn, 1),
+            "alg_flops_per_launch": dflops / max(dn, 1),
+            "alg_bytes_per_launch": dbytes / max(dn, 1),
+            "hbm_achieved_gbs": dbytes / (dus * 1e-6) / 1e9, "hbm_peak_gbs": peak_gbs,
+            "hbm_frac": dbytes / (dus * 1e-6) / 1e9 / peak_gbs,
+            "share_of_step": dus / total_us, "top_kernel": top[0], "top_kernel_share": top[1][1] / total_us,
+            "all_conv_share_of_step": conv_us / total_us,
+            "all_conv_tflops": prof.get("conv_flops", 0.0) / (conv_us * 1e-6) / 1e12,
             "step_alg_tflops": flops_step / step_s / 1e12,
         }
         line = {

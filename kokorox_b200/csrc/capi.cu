@@ -213,7 +213,8 @@ KKX_API int64_t kkx_profile_json(kkx_ctx* ctx, char* buf, int64_t capacity) {
   if (check_ctx(ctx)) return -1;
   std::lock_guard<std::mutex> lk(ctx->mu);
   std::ostringstream os;
-  os << "{\"conv_flops\": " << ctx->model->stats.conv_flops << ", \"gpu_us\": " << ctx->model->last_gpu_us
+  os << "{\"conv_flops\": " << ctx->model->stats.conv_flops << ", \"arb_flops\": " << ctx->model->stats.arb_flops
+     << ", \"arb_bytes\": " << ctx->model->stats.arb_bytes << ", \"gpu_us\": " << ctx->model->last_gpu_us
      << ", \"kernels\": {";
   bool first = true;
   for (auto& kv : ctx->model->prof_) {

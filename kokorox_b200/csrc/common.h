@@ -41,7 +41,8 @@ struct LaunchStats {
   std::vector<cudaEvent_t> events;       // pool, events[0] = start of run
   std::vector<std::string> names;        // names[i] = kernel launched before events[i+1]
   size_t n_events = 0;
-  double conv_flops = 0;                 // algorithmic FLOPs issued through the shifted-GEMM kernels
+  double conv_flops = 0;                 // algorithmic FLOPs issued through the shifted-GEMM kernels (all of them)
+  double arb_flops = 0, arb_bytes = 0;   // share of the fused res-block conv (kernels_arb.cu) + its algorithmic HBM bytes
   cudaEvent_t next_event() {
     if (n_events == events.size()) {
       cudaEvent_t e; cudaEventCreate(&e); events.push_back(e);

@@ -559,7 +559,13 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
   // two roles: fp32 in -> bf16 out (+statistics), or bf16 in + fp32 residual -> fp32 out
   if (a.in_bf16 ? (!a.out_f32 || a.out_bf16 || !a.res) : (!a.out_bf16 || a.out_f32 || a.res || a.accumulate))
     throw ArgError("launch_arb_conv: unsupported input/output combination");
-  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.C * a.C * a.ks;
+  if (g_launch_stats) {
+    const double fl = 2.0 * (double)a.sum_m * a.C * a.C * a.ks;
+    g_launch_stats->conv_flops += fl;
+    g_launch_stats->arb_flops += fl;
+    // every tensor once: conv1 reads fp32, writes bf16; conv2 reads bf16 + fp32 residual, writes fp32
+    g_launch_stats->arb_bytes += (double)a.sum_m * a.C * (a.in_bf16 ? 10.0 : 6.0);
+  }
   if (a.C == 128) {
     if (a.in_bf16) launch_arb_t<128, 2, true>(a, st); else launch_arb_t<128, 2, false>(a, st);
   } else {

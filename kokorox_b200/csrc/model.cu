@@ -539,6 +539,7 @@ void Model::run() {
   g_launch_stats = &stats;
   stats.launches = 0;
   stats.conv_flops = 0;
+  stats.arb_flops = 0; stats.arb_bytes = 0;
   stats.n_events = 0;
   stats.names.clear();
   dbg_.clear();

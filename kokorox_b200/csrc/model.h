@@ -157,7 +157,8 @@ class Model {
                  const Level& Lout, const float* sty, int sld, float* out, int ldo, int ocol,
                  bool dry);
   void arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
-           int sld, float* xw, float* t1, float* out, float oscale, bool accumulate);
+           int sld, float* xw, float* t1, float* out, float oscale, bool accumulate,
+           const float* part_x = nullptr);
   Level make_level(const std::vector<int>& lens, Arena& A);
   void capture(const char* name, const float* p, int ld, int col, int cols, const Level& L,
                int item0);

@@ -302,7 +302,7 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
 // AdaINResBlock1 (A.9): three (AdaIN -> Snake -> dilated conv -> AdaIN -> Snake -> conv) + residual
 // iterations.  Reads x, uses xw/t1 as work buffers, writes (or accumulates) oscale * result to out.
 void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
-                int sld, float* xw, float* t1, float* out, float oscale, bool accumulate) {
+                int sld, float* xw, float* t1, float* out, float oscale, bool accumulate, const float* part_x) {
   (void)r;
   cudaStream_t st = stream_;
   const int B = L.B, C = w.c, k = w.k;
@@ -323,10 +323,11 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
     base.tile_start = C == 128 ? L.d_tiles256 : L.d_tiles128;
     base.total_tiles = C == 128 ? L.ntiles256 : L.ntiles128;
     base.scale = sc; base.shift = sh; base.nchunk = nch;
-    launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    // statistics of the block input: shared by the three res-blocks of a stage (computed once by the caller)
+    if (!part_x) launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
     long long* tim = arb_timing_buf();
     for (int j = 0; j < 3; j++) {
-      launch_adain_coef(part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
+      launch_adain_coef(j == 0 && part_x ? part_x : part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
       ArbConvArgs c1 = base;
       if (tim) c1.timing = tim + (C == 128 ? 0 : 64);
       c1.x = cur; c1.in_bf16 = 0; c1.alpha = w.a1[j]; c1.tmB = w.t1[j].tmap; c1.dil = dil[j];
@@ -563,8 +564,15 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   }
   capture("gen.ups.0", x0, 256, 0, 256, G20, b0);
   launch_add_rows(x0, xs0, x0, 256, G20.d_off, G20.d_len, B, G20.max_len, st);
-  for (int j = 0; j < 3; j++)
-    arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0);
+  {
+    float* px = nullptr;
+    if (opt.precision == 1) {
+      px = A.alloc<float>((size_t)B * ((G20.max_len + kStatRows - 1) / kStatRows) * 2 * 256);
+      launch_colstats(x0, 256, 256, px, G20.d_off, G20.d_len, B, G20.max_len, st);
+    }
+    for (int j = 0; j < 3; j++)
+      arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0, px);
+  }
   capture("gen.stage.0", acc0, 256, 0, 256, G20, b0);
 
   // ---- generator stage 1 (120T+1 rows, 128 ch)
@@ -606,8 +614,15 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   launch_copy_row(x1, 128, 0, 2, G120.d_off, B, st);
   capture("gen.ups.1", x1, 128, 0, 128, G120, b0);
   launch_add_rows(x1, xs1, x1, 128, G120.d_off, G120.d_len, B, G120.max_len, st);
-  for (int j = 0; j < 3; j++)
-    arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0);
+  {
+    float* px = nullptr;
+    if (opt.precision == 1) {
+      px = A.alloc<float>((size_t)B * ((G120.max_len + kStatRows - 1) / kStatRows) * 2 * 128);
+      launch_colstats(x1, 128, 128, px, G120.d_off, G120.d_len, B, G120.max_len, st);
+    }
+    for (int j = 0; j < 3; j++)
+      arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0, px);
+  }
   capture("gen.stage.1", acc1, 128, 0, 128, G120, b0);
 
   // ---- head (K11)

@@ -14,6 +14,7 @@ There is no CPU fallback: if ``libkkx.so`` is missing or no B200 is visible ever
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 import threading
 from typing import List, Optional, Sequence
@@ -105,6 +106,8 @@ class B200Koko:
             self._ctx = C.c_void_p()
             raise KkxError(rc, (self._lib.kkx_last_error(None) or b"").decode())
         self.device = device
+        self._outstanding = 0
+        self._closing = False
 
     @classmethod
     def new(cls, model_path: str, device: int = 0) -> "B200Koko":
@@ -112,9 +115,27 @@ class B200Koko:
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self) -> None:
-        if getattr(self, "_ctx", None) is not None and self._ctx.value:
-            self._lib.kkx_destroy(self._ctx)
-            self._ctx = C.c_void_p()
+        """Destroy the session.  If waveforms returned by infer_batch are still alive (they are views into
+        library-owned pinned memory), destruction is deferred until the last of them is released."""
+        if getattr(self, "_ctx", None) is None or not self._ctx.value:
+            return
+        if getattr(self, "_outstanding", 0) > 0:
+            self._closing = True
+            return
+        self._lib.kkx_destroy(self._ctx)
+        self._ctx = C.c_void_p()
+
+    @staticmethod
+    def _release_buffer(session: "B200Koko", addr: int) -> None:
+        try:
+            if session._ctx.value:
+                session._lib.kkx_release(session._ctx, C.cast(C.c_void_p(addr), C.POINTER(C.c_float)))
+            session._outstanding -= 1
+            if session._closing and session._outstanding <= 0:
+                session._closing = False
+                session.close()
+        except Exception:
+            pass
 
     def __del__(self):
         try:
@@ -163,12 +184,16 @@ class B200Koko:
             offs.ctypes.data_as(C.POINTER(C.c_int32)), _fp(st), _fp(sp), C.byref(audio),
             soff.ctypes.data_as(C.POINTER(C.c_int64)), dur.ctypes.data_as(C.POINTER(C.c_int32)))
         self._check(rc)
-        try:
-            total = int(soff[-1])
-            buf = np.ctypeslib.as_array(audio, shape=(max(total, 1),))[:total]
-            outs = [buf[int(soff[b]):int(soff[b + 1])].copy() for b in range(B)]
-        finally:
-            self._lib.kkx_release(self._ctx, audio)
+        total = int(soff[-1])
+        # Zero-copy: the waveforms are views into the library-owned pinned buffer the D2H copy landed in
+        # (the reference copies its output twice, ort_koko.rs:85 + koko.rs:1179).  The buffer goes back to
+        # the library's pool (kkx_release) when the last view is garbage-collected; the views keep this
+        # session alive until then.
+        base = np.ctypeslib.as_array(audio, shape=(max(total, 1),))
+        self._outstanding += 1
+        weakref.finalize(base, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
+        outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
+        del base
         if return_durations:
             return outs, [dur[int(offs[b]):int(offs[b + 1])].copy() for b in range(B)]
         return outs
