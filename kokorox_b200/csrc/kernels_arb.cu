@@ -24,6 +24,7 @@
 #include "kernels.h"
 #include "tc_ptx.cuh"
 #include <type_traits>
+#include <cstdlib>
 
 namespace kkx {
 
@@ -46,16 +47,24 @@ constexpr int kProdThreads = 192;
 constexpr int kProdRows = kProdThreads / 8;   // rows per producer pass
 constexpr int kArbMaxB = 512;
 
-template <int BN, int MSUB>
+// T ("transposed", C = 128 only): the WEIGHT tile is the M operand (128 output channels) and the 256
+// activation rows are the N operand of one 128x256 MMA, so the accumulator is [channel][row]:
+//   * a weight tile is read from smem once per 256 rows instead of once per 128 (the tensor pipe's own
+//     operand reads saturate the 128 B/clk smem port at M = N = 128; 75 % with N = 256);
+//   * after tcgen05.ld a thread owns ONE channel and 32 consecutive rows: global accesses are already
+//     coalesced across the warp (32 channels = 128 contiguous bytes per row), so the epilogue needs no smem
+//     transpose and no barrier, the bias is a per-thread scalar, and the AdaIN statistics are plain
+//     per-thread sums (no shuffles); the freed smem holds a third operand slot.
+template <int BN, int MSUB, bool T>
 struct ArbCfg {
   static constexpr int KCH = BN / 64;                       // 64-channel chunks
   static constexpr int RA = MSUB * 128 + 56;                // rows per A slot (halo <= 2*25, 8-row granule)
   static constexpr uint32_t A_SLOT = RA * 128;              // bytes (multiple of 1024)
-  static constexpr int NA = (BN == 128) ? 2 : 3;            // A slots
+  static constexpr int NA = (BN == 128 && !T) ? 2 : 3;      // A slots
   static constexpr uint32_t B_STAGE = BN * 128;             // bytes
   static constexpr int NB = (BN == 128) ? 6 : 3;            // B stages
   static constexpr int PITCH = 36;                          // floats per staged epilogue row
-  static constexpr uint32_t STG = 2 * 128 * PITCH * 4;      // one transpose buffer per epilogue group
+  static constexpr uint32_t STG = T ? 0 : 2 * 128 * PITCH * 4;   // one transpose buffer per epilogue group
   static constexpr uint32_t STAT = 4 * BN * 2 * 4;          // per-quadrant column sums
   static constexpr uint32_t COEF = 3 * BN * 4;              // per-item operand-transform coefficients
   static constexpr int NBAR = 2 * NA + 2 * NB + 4;
@@ -91,9 +100,10 @@ struct TileCur {
 // The two roles are separate instantiations so that each carries only its own epilogue / producer code:
 // with 16 warps in four different roles the hot code of all roles has to stay inside the instruction cache
 // (an earlier, more generic version of this kernel lost ~40 % of its time to instruction-fetch stalls).
-template <int BN, int MSUB, bool CONV2>
+template <int BN, int MSUB, bool CONV2, bool T>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
-  using Cfg = ArbCfg<BN, MSUB>;
+  static_assert(!T || (BN == 128 && MSUB == 2), "transposed mode: C = 128, 256-row tiles");
+  using Cfg = ArbCfg<BN, MSUB, T>;
   constexpr int KCH = Cfg::KCH, NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   constexpr int MT = MSUB * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -182,6 +192,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
 #pragma unroll 1
       for (int tile = t_begin; tile < t_end; tile++, ti++) {
         const int rem = s_len[cur.b] - cur.mt * MT;         // rows of this item left from the tile start
+        (void)rem;
         const int buf = ti & 1;
         mbar_wait(tempty(buf), (((uint32_t)(ti >> 1)) & 1u) ^ 1u);
         tc_fence_after();
@@ -202,17 +213,28 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
             }
             TICK(2);
             const uint64_t bd = umma_desc_sw128(b_base + sb * Cfg::B_STAGE);
-#pragma unroll
-            for (int sub = 0; sub < MSUB; sub++) {
-              if (sub * 128 >= rem) continue;
-              // row-shifted view of the halo tile: start address moves by whole 128-byte rows; the
-              // 128B swizzle is a function of the absolute smem address, so the view stays consistent
-              // with how the producers (and TMA) lay rows out (verified on B200, tools/arb_probe.py)
-              const uint64_t ad = umma_desc_sw128(slot + (uint32_t)(sub * 128 + tap * dil) * 128u);
-              const uint32_t td = tmem_base + (uint32_t)((buf * MSUB + sub) * BN);
+            if (T) {
+              // D[co, row] += W[co, k] * Act[row + tap*dil, k]: weights = M operand, 256 rows = N operand
+              constexpr uint32_t idescT = umma_idesc_bf16(128, 256);
+              const uint64_t wd = bd;
+              const uint64_t xd = umma_desc_sw128(slot + (uint32_t)(tap * dil) * 128u);
+              const uint32_t td = tmem_base + (uint32_t)(buf * 256);
 #pragma unroll
               for (int k = 0; k < 4; k++)
-                umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
+                umma_bf16(td, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idescT, (c | tap | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int sub = 0; sub < MSUB; sub++) {
+                if (sub * 128 >= rem) continue;
+                // row-shifted view of the halo tile: start address moves by whole 128-byte rows; the
+                // 128B swizzle is a function of the absolute smem address, so the view stays consistent
+                // with how the producers (and TMA) lay rows out (verified on B200, tools/arb_probe.py)
+                const uint64_t ad = umma_desc_sw128(slot + (uint32_t)(sub * 128 + tap * dil) * 128u);
+                const uint32_t td = tmem_base + (uint32_t)((buf * MSUB + sub) * BN);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (c | tap | k) ? 1u : 0u);
+              }
             }
             if (!resident) umma_commit(emptyB(sb));
             TICK(3);
@@ -224,6 +246,121 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       }
       TIM_FLUSH(4, 4);
     }
+  } else if (T && warp < 10) {
+    // ------------------------------------------------------------------ epilogue, transposed accumulator
+    // warp: 32 channels (TMEM lane quadrant q) x 128 rows (row half eg); thread: one channel.  Register j of
+    // a 32-column tcgen05.ld is row j of the chunk, so a warp-wide access to row j covers 32 consecutive
+    // channels = 128 contiguous bytes.  No smem, no barrier; statistics are per-thread sums.
+    const int eg = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int co = q * 32 + lane;
+    const float bias_c = a.bias[co];
+    const float2 bias2 = make_float2(bias_c, bias_c);
+    const float2 os2 = make_float2(a.oscale, a.oscale);
+    const bool accum = a.accumulate != 0;
+    // residual rows are prefetched two 32-row chunks ahead (two register buffers), across tile boundaries
+    auto fetchT = [&](int L, int off, int m0, int ch, float (&rv)[32]) {
+      if (!CONV2) return;
+      const int row = m0 + eg * 128 + ch * 32;
+      const float* rp = a.res + (size_t)(off + row) * 128 + co;
+      const int left = L - row;
+#pragma unroll
+      for (int j = 0; j < 32; j++)
+        if (j < left) rv[j] = rp[j * 128];
+    };
+    int ti = 0;
+    TileCur cur;
+    float rv0[32], rv1[32];
+    if (t_begin < t_end) {
+      cur.init(s_ts, B, t_begin);
+      fetchT(s_len[cur.b], s_off[cur.b], cur.mt * MT, 0, rv0);
+      fetchT(s_len[cur.b], s_off[cur.b], cur.mt * MT, 1, rv1);
+    }
+#ifdef KKX_ARB_TIMING
+    long long tim_acc[9] = {0}; long long tim_last = clock64();
+    const bool tim_on = a.timing && blockIdx.x == 0 && warp == 2 && lane == 0;
+#endif
+#pragma unroll 1
+    for (int tile = t_begin; tile < t_end; tile++, ti++) {
+      const int b = cur.b;
+      const int L = s_len[b], off = s_off[b];
+      const int m0 = cur.mt * MT;
+      const int buf = ti & 1;
+      cur.next(s_ts);                       // cur now names the NEXT tile (prefetch target)
+      const bool has_next = tile + 1 < t_end;
+      const int nL = has_next ? s_len[cur.b] : 0, noff = has_next ? s_off[cur.b] : 0, nm0 = cur.mt * MT;
+      TICK(8);
+      mbar_wait(tfull(buf), ((uint32_t)(ti >> 1)) & 1u);
+      tc_fence_after();
+      TICK(0);
+      float2 s2 = make_float2(0.f, 0.f), q2 = s2;
+      auto bodyT = [&](int ch, float (&rv)[32], auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const int row = m0 + eg * 128 + ch * 32;
+        const int left = L - row;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + eg * 128 + ch * 32), v);
+        if (ch == 3) {      // last TMEM read of this tile by this warp
+          tc_fence_before();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
+        }
+        TICK(1);
+        if (CONV2) {
+          float* op = a.out_f32 + (size_t)(off + row) * 128 + co;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 o = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            o = __fadd2_rn(__fadd2_rn(o, make_float2(rv[j], rv[j + 1])), bias2);
+            if (!FULL) { o.x = j < left ? o.x : 0.f; o.y = j + 1 < left ? o.y : 0.f; }
+            s2 = __fadd2_rn(s2, o);
+            q2 = __ffma2_rn(o, o, q2);
+            o = __fmul2_rn(o, os2);
+            if (accum) {      // exactly one add per element and launch -> order-independent
+              if (FULL || j < left) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(op + j * 128), "f"(o.x) : "memory");
+              if (FULL || j + 1 < left) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(op + (j + 1) * 128), "f"(o.y) : "memory");
+            } else {
+              if (FULL || j < left) op[j * 128] = o.x;
+              if (FULL || j + 1 < left) op[(j + 1) * 128] = o.y;
+            }
+          }
+        } else {
+          // bf16 output: lanes 2i / 2i+1 exchange so that each lane stores one 4-byte word (two channels):
+          // even lanes the word of row j, odd lanes the word of row j+1
+          const int odd = lane & 1;
+          __nv_bfloat16* op = a.out_bf16 + (size_t)(off + row + odd) * 128 + (co & ~1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 o = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), bias2);
+            if (!FULL) { o.x = j < left ? o.x : 0.f; o.y = j + 1 < left ? o.y : 0.f; }
+            s2 = __fadd2_rn(s2, o);
+            q2 = __ffma2_rn(o, o, q2);
+            const float send = odd ? o.x : o.y;
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            const uint32_t w = odd ? pack_bf16(recv, o.y) : pack_bf16(o.x, recv);
+            if (FULL || j + odd < left) *reinterpret_cast<uint32_t*>(op + j * 128) = w;
+          }
+        }
+        TICK(5);
+        // refill this register buffer with the rows of chunk ch+2 (possibly of the next tile)
+        if (ch + 2 < 4) fetchT(L, off, m0, ch + 2, rv);
+        else if (has_next) fetchT(nL, noff, nm0, ch - 2, rv);
+        TICK(6);
+      };
+      if (L - m0 >= MT) {
+        bodyT(0, rv0, std::true_type{}); bodyT(1, rv1, std::true_type{});
+        bodyT(2, rv0, std::true_type{}); bodyT(3, rv1, std::true_type{});
+      } else {
+        bodyT(0, rv0, std::false_type{}); bodyT(1, rv1, std::false_type{});
+        bodyT(2, rv0, std::false_type{}); bodyT(3, rv1, std::false_type{});
+      }
+      if (a.part && m0 + eg * 128 < L) {   // one thread per channel and 128-row statistics chunk
+        float* pp = a.part + ((size_t)b * a.nchunk + (size_t)((m0 >> 7) + eg)) * 2 * 128 + co;
+        pp[0] = s2.x + s2.y;
+        pp[128] = q2.x + q2.y;
+      }
+      TICK(7);
+    }
+    TIM_FLUSH(8, 9);
   } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue (2 groups of 4 warps)
     // group eg owns the 32-column chunks of parity eg; inside a group, thread `et` drops its accumulator
@@ -466,7 +603,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
 #pragma unroll
       for (int p = 0; p < GP; p++) {
         // straight-line: rows outside the item produce zeros through a select, only the store is predicated
-        const bool inside = (unsigned)(row + p * kProdRows) < (unsigned)L;
+        const uint32_t inmask = (unsigned)(row + p * kProdRows) < (unsigned)L ? 0xFFFFFFFFu : 0u;
         float2 xv[4];
         if (CONV2) {
           const uint4 raw = *reinterpret_cast<const uint4*>(&rb[p][0]);
@@ -486,7 +623,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
           const float2 u = __ffma2_rn(xv[e], cA[e], cB[e]);
           const float2 sn = make_float2(__sinf(u.x), __sinf(u.y));
           const float2 y = __fmul2_rn(__ffma2_rn(sn, sn, u), cI[e]);
-          pw[e] = inside ? pack_bf16(y.x, y.y) : 0u;
+          pw[e] = pack_bf16(y.x, y.y) & inmask;   // mask, not select: keeps the 16 chains of a group branch-free
         }
         const uint4 pk = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         if (rloc + p * kProdRows < ra_used) *reinterpret_cast<uint4*>(sp + p * kProdRows * 128) = pk;
@@ -527,21 +664,21 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   }
 }
 
-template <int BN, int MSUB, bool CONV2>
+template <int BN, int MSUB, bool CONV2, bool T>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
-  using Cfg = ArbCfg<BN, MSUB>;
+  using Cfg = ArbCfg<BN, MSUB, T>;
   static bool attr_set[64] = {false};
   static int sms[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
   const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
-  arb_conv_kernel<BN, MSUB, CONV2><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  arb_conv_kernel<BN, MSUB, CONV2, T><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 }  // namespace
@@ -566,10 +703,13 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
     // every tensor once: conv1 reads fp32, writes bf16; conv2 reads bf16 + fp32 residual, writes fp32
     g_launch_stats->arb_bytes += (double)a.sum_m * a.C * (a.in_bf16 ? 10.0 : 6.0);
   }
-  if (a.C == 128) {
-    if (a.in_bf16) launch_arb_t<128, 2, true>(a, st); else launch_arb_t<128, 2, false>(a, st);
+  static const bool no_t = [] { const char* e = getenv("KKX_ARB_NOT"); return e && e[0] == '1'; }();
+  if (a.C == 128 && !no_t) {
+    if (a.in_bf16) launch_arb_t<128, 2, true, true>(a, st); else launch_arb_t<128, 2, false, true>(a, st);
+  } else if (a.C == 128) {
+    if (a.in_bf16) launch_arb_t<128, 2, true, false>(a, st); else launch_arb_t<128, 2, false, false>(a, st);
   } else {
-    if (a.in_bf16) launch_arb_t<256, 1, true>(a, st); else launch_arb_t<256, 1, false>(a, st);
+    if (a.in_bf16) launch_arb_t<256, 1, true, false>(a, st); else launch_arb_t<256, 1, false, false>(a, st);
   }
   if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
     char nm[96]; snprintf(nm, sizeof nm, "arb_conv[c%d k%d d%d %s m%lld]", a.C, a.ks, a.dil, a.in_bf16 ? "bf16" : "f32", a.sum_m);
