@@ -397,11 +397,185 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant: flash attention with split-TF32 ("3xTF32") products on mma.sync m16n8k8, which
+// keeps fp32-grade accuracy (this path feeds the duration predictor, whose integer durations must match
+// the fp32 oracle bit-exactly) at several times the fp32 SIMT rate.  Attention is ~0.5 % of the model's
+// FLOPs, with d = 64 and N <= 512: the warp-level MMA with register fragments fits it better than a
+// TMEM pipeline.  CTA = 4 warps x 16 query rows; keys/values stream through smem in tiles of 64 as
+// tf32 hi/lo planes; every product is hi*hi + hi*lo + lo*hi.
+//   S = (Q/8) K^T : A = Q fragments (registers, split once), B[k=d][n=key] = K[key][d]
+//   O += P V      : A = P in the accumulator layout with the key order (2t, 2t+1) taken as k = (t, t+4),
+//                   so no shuffles are needed; B[k=key][n=d] = V[key][d] with the same key permutation.
+__device__ __forceinline__ uint32_t att_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void att_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int kAttLd = 68;   // smem row stride (floats): conflict-free B-fragment loads for both products
+
+__global__ void __launch_bounds__(128) attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+                                                           const int* off, const int* len) {
+  extern __shared__ uint32_t att_sm[];
+  uint32_t* Kh = att_sm;                       // [64][68] tf32 hi
+  uint32_t* Kl = Kh + 64 * kAttLd;
+  uint32_t* Vh = Kl + 64 * kAttLd;
+  uint32_t* Vl = Vh + 64 * kAttLd;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int N = len[b];
+  const int q0 = blockIdx.x * 64;
+  if (q0 >= N) return;
+  const size_t base = (size_t)off[b];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;       // the two query rows of this thread's fragments
+
+  // Q fragments (scaled by 1/8, exact), split into tf32 hi / lo once
+  uint32_t qh[8][4], ql[8][4];
+#pragma unroll
+  for (int kk = 0; kk < 8; kk++) {
+    const int d = kk * 8 + t;
+    const float* p0 = qkv + (base + r0) * 2304 + h * 64 + d;
+    const float* p1 = qkv + (base + r1) * 2304 + h * 64 + d;
+    float v[4];
+    v[0] = r0 < N ? p0[0] * 0.125f : 0.f;
+    v[1] = r1 < N ? p1[0] * 0.125f : 0.f;
+    v[2] = r0 < N ? p0[4] * 0.125f : 0.f;
+    v[3] = r1 < N ? p1[4] * 0.125f : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      qh[kk][e] = att_tf32(v[e]);
+      ql[kk][e] = att_tf32(v[e] - __uint_as_float(qh[kk][e]));
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int k0 = 0; k0 < N; k0 += 64) {
+    __syncthreads();
+    // stage K and V tiles as hi/lo planes (float4 global loads, 16 rows x 8 column quads per pass)
+    for (int i = tid; i < 64 * 16; i += 128) {
+      const int j = i >> 4, c4 = (i & 15) << 2;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + j < N) {
+        const float* rp = qkv + (base + k0 + j) * 2304 + h * 64 + c4;
+        kv = *reinterpret_cast<const float4*>(rp + 768);
+        vv = *reinterpret_cast<const float4*>(rp + 1536);
+      }
+      const float kx[4] = {kv.x, kv.y, kv.z, kv.w}, vx[4] = {vv.x, vv.y, vv.z, vv.w};
+      uint32_t a[4], bq[4], c[4], dq[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        a[e] = att_tf32(kx[e]); bq[e] = att_tf32(kx[e] - __uint_as_float(a[e]));
+        c[e] = att_tf32(vx[e]); dq[e] = att_tf32(vx[e] - __uint_as_float(c[e]));
+      }
+      *reinterpret_cast<uint4*>(Kh + j * kAttLd + c4) = make_uint4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<uint4*>(Kl + j * kAttLd + c4) = make_uint4(bq[0], bq[1], bq[2], bq[3]);
+      *reinterpret_cast<uint4*>(Vh + j * kAttLd + c4) = make_uint4(c[0], c[1], c[2], c[3]);
+      *reinterpret_cast<uint4*>(Vl + j * kAttLd + c4) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
+    }
+    __syncthreads();
+
+    // S = Q K^T for 16 rows x 64 keys
+    float sc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+      const uint32_t* kh = Kh + (n * 8 + g) * kAttLd + t;
+      const uint32_t* kl = Kl + (n * 8 + g) * kAttLd + t;
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        const uint32_t bh0 = kh[kk * 8], bh1 = kh[kk * 8 + 4], bl0 = kl[kk * 8], bl1 = kl[kk * 8 + 4];
+        att_mma(sc[n], ql[kk], bh0, bh1);     // small terms first
+        att_mma(sc[n], qh[kk], bl0, bl1);
+        att_mma(sc[n], qh[kk], bh0, bh1);
+      }
+    }
+    // online softmax (rows r0: elements 0,1; rows r1: elements 2,3); keys beyond N masked out
+    float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      const int key = k0 + n * 8 + 2 * t;
+      if (key >= N) { sc[n][0] = -INFINITY; sc[n][2] = -INFINITY; }
+      if (key + 1 >= N) { sc[n][1] = -INFINITY; sc[n][3] = -INFINITY; }
+      cm0 = fmaxf(cm0, fmaxf(sc[n][0], sc[n][1]));
+      cm1 = fmaxf(cm1, fmaxf(sc[n][2], sc[n][3]));
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);   // finite: every tile holds at least one valid key
+    const float corr0 = expf(m0 - mn0), corr1 = expf(m1 - mn1);
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      sc[n][0] = expf(sc[n][0] - mn0); sc[n][1] = expf(sc[n][1] - mn0);
+      sc[n][2] = expf(sc[n][2] - mn1); sc[n][3] = expf(sc[n][3] - mn1);
+      ps0 += sc[n][0] + sc[n][1];
+      ps1 += sc[n][2] + sc[n][3];
+    }
+    ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1); ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+    ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1); ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+    l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;
+    m0 = mn0; m1 = mn1;
+#pragma unroll
+    for (int n = 0; n < 8; n++) { o[n][0] *= corr0; o[n][1] *= corr0; o[n][2] *= corr1; o[n][3] *= corr1; }
+
+    // O += P V: k-step kk covers keys kk*8 .. +7; fragment column t <-> key 2t, column t+4 <-> key 2t+1
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      uint32_t ph[4], pl[4];
+      const float pv[4] = {sc[kk][0], sc[kk][2], sc[kk][1], sc[kk][3]};   // a0 (g,t) a1 (g+8,t) a2 (g,t+4) a3 (g+8,t+4)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        ph[e] = att_tf32(pv[e]);
+        pl[e] = att_tf32(pv[e] - __uint_as_float(ph[e]));
+      }
+      const uint32_t* vh = Vh + (kk * 8 + 2 * t) * kAttLd + g;
+      const uint32_t* vl = Vl + (kk * 8 + 2 * t) * kAttLd + g;
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        const uint32_t bh0 = vh[n * 8], bh1 = vh[kAttLd + n * 8], bl0 = vl[n * 8], bl1 = vl[kAttLd + n * 8];
+        att_mma(o[n], pl, bh0, bh1);
+        att_mma(o[n], ph, bl0, bl1);
+        att_mma(o[n], ph, bh0, bh1);
+      }
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int n = 0; n < 8; n++) {
+    const int d = n * 8 + 2 * t;
+    if (r0 < N) *reinterpret_cast<float2*>(ctx + (base + r0) * 768 + h * 64 + d) = make_float2(o[n][0] * i0, o[n][1] * i0);
+    if (r1 < N) *reinterpret_cast<float2*>(ctx + (base + r1) * 768 + h * 64 + d) = make_float2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
 void launch_attention(const float* qkv, float* ctx, const int* off, const int* len, int B,
                       int max_len, cudaStream_t st) {
   if (g_dry_run) return;
-  dim3 g((max_len + 31) / 32, 12, B);
-  attention_kernel<<<g, 256, 0, st>>>(qkv, ctx, off, len);
+  static const bool simt = [] { const char* e = getenv("KKX_ATT_SIMT"); return e && e[0] == '1'; }();
+  if (simt) {
+    dim3 g((max_len + 31) / 32, 12, B);
+    attention_kernel<<<g, 256, 0, st>>>(qkv, ctx, off, len);
+  } else {
+    constexpr int smem = 4 * 64 * kAttLd * 4;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+      KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set[dev] = true;
+    }
+    dim3 g((max_len + 63) / 64, 12, B);
+    attention_tc_kernel<<<g, 128, smem, st>>>(qkv, ctx, off, len);
+  }
   post_launch("attention", st);
 }
 
