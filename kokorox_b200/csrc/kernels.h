@@ -41,6 +41,9 @@ struct TcConvArgs {
   const void* tmB = nullptr;
   const void* tmA2 = nullptr; // split-TF32 mode: the "lo" planes
   const void* tmB2 = nullptr;
+  const void* tmB_c = nullptr;   // split-TF32 cluster mode: weight maps with half-height boxes (BN/2 rows)
+  const void* tmB2_c = nullptr;
+  int cluster = 1;               // CTAs per cluster along M sharing each weight tile by TMA multicast (1 or 2)
   int tf32 = 0;               // 1 = split-TF32 operands (fp32 containers), nprod products (3 or 4)
   int nprod = 3;
   int eact = ACT_NONE;

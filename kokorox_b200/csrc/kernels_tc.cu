@@ -77,7 +77,10 @@ __device__ __forceinline__ float gelu_new_f(float v) {
 // pair of tf32-exact fp32 planes (hi, lo = a - hi), D += Ahi*Bhi + Alo*Bhi + Ahi*Blo [+ Alo*Blo] on
 // kind::tf32, which recovers ~fp32 accuracy on the tensor cores for the precision-critical
 // predictor path (ALBERT -> durations, F0/N).
-template <int BN, int STAGES, int MODE>
+// CL > 1 (split-TF32 GEMMs): a cluster of CL CTAs along M shares every weight (B) tile -- each CTA fetches
+// 1/CL of its rows and multicasts them to all CTAs of the cluster, which cuts the L2->SM operand traffic
+// these GEMMs are bound by (4 fp32 planes per stage) by 25 % at CL = 2.
+template <int BN, int STAGES, int MODE, int CL>
 __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB,
                                                       const __grid_constant__ CUtensorMap tmA2,
@@ -105,7 +108,13 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   const int b = blockIdx.z;
   const int mlen = a.m_len[b];
   const int m0 = blockIdx.x * 128;
-  if (m0 >= mlen) return;  // CTA-uniform
+  if (CL == 1) {
+    if (m0 >= mlen) return;  // CTA-uniform
+  } else {
+    if ((int)(blockIdx.x / CL) * CL * 128 >= mlen) return;  // cluster-uniform: a CTA past the end still feeds its peers
+  }
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
   const int n0 = blockIdx.y * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.Cpad / KE;
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
     }
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     mbar_init(tfull_bar, 1);
     if (MODE) for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers exist before any multicast / remote arrive can land
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -140,15 +150,22 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_wait(empty_bar(s), ph ^ 1u);   // CL > 1: every CTA of the cluster has drained this stage
         const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
         const uint32_t sa = base + s * STAGE_BYTES;
         mbar_expect_tx(full_bar(s), STAGE_BYTES);
         tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
-        tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
-        if (MODE) {
-          tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
-          tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+        if (MODE) tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
+        if (CL == 1) {
+          tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+          if (MODE) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+        } else {
+          // this CTA's 1/CL of the weight rows (tmB / tmB2 have BN/CL-row boxes), multicast to the whole cluster
+          constexpr uint32_t SUB = (BN / CL) * 128;
+          tma_load_2d_mc(sa + PLANES * A_BYTES + crank * SUB, &tmB, tap * a.Cpad + c0, n0 + (int)crank * (BN / CL),
+                         full_bar(s), cmask);
+          if (MODE) tma_load_2d_mc(sa + 2 * A_BYTES + B_BYTES + crank * SUB, &tmB2, tap * a.Cpad + c0,
+                                   n0 + (int)crank * (BN / CL), full_bar(s), cmask);
         }
       }
     }
@@ -186,7 +203,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           }
           if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
         }
-        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+        if (CL == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
+        else umma_commit_mc(empty_bar(s), cmask);   // ... in every CTA of the cluster (they all write into it)
       }
       umma_commit(tfull_bar);       // accumulator complete
     }
@@ -297,6 +315,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA exits while a peer can still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -497,7 +516,7 @@ static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
                                                              *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, int CL = 1>
 static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
   constexpr int PLANES = MODE ? 2 : 1;
   constexpr int smem = STAGES * PLANES * (128 * 128 + BN * 128) + (2 * STAGES + 7) * 8 + 16 + 1024;
@@ -505,15 +524,26 @@ static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set[dev] = true;
   }
-  dim3 g((a.max_m + 127) / 128, (a.Co + BN - 1) / BN, a.B);
+  const unsigned gx = (unsigned)(((a.max_m + 127) / 128 + CL - 1) / CL * CL);
+  dim3 g(gx, (a.Co + BN - 1) / BN, a.B);
   const CUtensorMap* mA = reinterpret_cast<const CUtensorMap*>(a.tmA);
-  const CUtensorMap* mB = reinterpret_cast<const CUtensorMap*>(a.tmB);
+  const CUtensorMap* mB = reinterpret_cast<const CUtensorMap*>(CL > 1 ? a.tmB_c : a.tmB);
   const CUtensorMap* mA2 = reinterpret_cast<const CUtensorMap*>(a.tmA2 ? a.tmA2 : a.tmA);
-  const CUtensorMap* mB2 = reinterpret_cast<const CUtensorMap*>(a.tmB2 ? a.tmB2 : a.tmB);
-  conv_tc_kernel<BN, STAGES, MODE><<<g, 192, smem, st>>>(*mA, *mB, *mA2, *mB2, a);
+  const CUtensorMap* mB2 = reinterpret_cast<const CUtensorMap*>(CL > 1 ? a.tmB2_c : (a.tmB2 ? a.tmB2 : a.tmB));
+  if (CL == 1) {
+    conv_tc_kernel<BN, STAGES, MODE, CL><<<g, 192, smem, st>>>(*mA, *mB, *mA2, *mB2, a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = dim3(192, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    KKX_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, MODE, CL>, *mA, *mB, *mA2, *mB2, a));
+  }
 }
 
 void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
@@ -526,7 +556,8 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
   if (a.tf32) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
-    if (a.Co > 64) launch_tc<128, 3, 1>(a, st);
+    if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);
+    else if (a.Co > 64) launch_tc<128, 3, 1>(a, st);
     else launch_tc<64, 4, 1>(a, st);
     if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
       char nm[96]; snprintf(nm, sizeof nm, "conv_tc_tf32x3[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);

@@ -193,6 +193,11 @@ TcW32 Model::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) {
   t.hi = up(hi); t.lo = up(lo);
   make_tmap_f32(t.tm_hi, t.hi, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
   make_tmap_f32(t.tm_lo, t.lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
+  if (tc_box_n_tf32(Co) == 128) {
+    make_tmap_f32(t.tm_hi_c, t.hi, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 64);
+    make_tmap_f32(t.tm_lo_c, t.lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 64);
+    t.has_c = true;
+  }
   return t;
 }
 

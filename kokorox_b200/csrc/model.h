@@ -39,6 +39,9 @@ struct TcW32 {
   float* hi = nullptr; float* lo = nullptr;
   alignas(64) unsigned char tm_hi[128];
   alignas(64) unsigned char tm_lo[128];
+  alignas(64) unsigned char tm_hi_c[128];   // half-height boxes for the 2-CTA multicast GEMM (Co > 64 only)
+  alignas(64) unsigned char tm_lo_c[128];
+  bool has_c = false;
   int Cpad = 0, Ci = 0, Co = 0, ks = 0;
 };
 struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; TcW32 t_ih; };

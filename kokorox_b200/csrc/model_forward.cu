@@ -81,6 +81,11 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
     make_tmap_f32(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
     TcConvArgs a;
     a.tmA = tA; a.tmA2 = tA2; a.tmB = w32->tm_hi; a.tmB2 = w32->tm_lo; a.tf32 = 1; a.nprod = 3; a.eact = eact;
+    // 2-CTA clusters with TMA-multicast weight tiles: measured on B200 NOT faster (13.9 vs 12.4 ms for the 12 qkv
+    // GEMMs): these GEMMs are bound by what each SM can ingest (~28 B/clk: 64 KB of hi/lo planes per 128x128x32
+    // step), which multicast does not change.  Opt-in (KKX_TC_CLUSTER=1).
+    static const bool cl_ok = [] { const char* e = getenv("KKX_TC_CLUSTER"); return e && e[0] == '1'; }();
+    if (cl_ok && w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = 2; }
     a.Cpad = w32->Cpad; a.Ci = K; a.Co = N; a.ks = ks; a.dil = 1; a.pad = pad;
     a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
     a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lm.d_off;
