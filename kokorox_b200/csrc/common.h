@@ -119,8 +119,8 @@ struct Level {
   int* d_off = nullptr;  // device copies
   int* d_len = nullptr;
   // prefix sums (B+1) of the per-item tile counts for 128- and 256-row tiles (persistent kernels)
-  int* d_tiles128 = nullptr; int* d_tiles256 = nullptr;
-  int ntiles128 = 0, ntiles256 = 0;
+  int* d_tiles128 = nullptr; int* d_tiles256 = nullptr; int* d_tiles512 = nullptr;
+  int ntiles128 = 0, ntiles256 = 0, ntiles512 = 0;
 };
 
 constexpr int kGapRows = 32;  // >= largest conv halo (k=11, dil=5 -> 25)

@@ -89,7 +89,7 @@ struct ArbConvArgs {
   const void* tmB = nullptr;                           // host pointer to the weight CUtensorMap (bf16 [C][ks*C], box [C,64])
   int C = 0, ks = 1, dil = 1, pad = 0;
   const int* off = nullptr; const int* len = nullptr;  // Level (device)
-  const int* tile_start = nullptr;                     // [B+1] prefix sum of ceil(len/arb_tile_rows(C))
+  const int* tile_start = nullptr;                     // [B+1] prefix sum of ceil(len/arb_tile_rows(C, ks))
   int B = 1; int total_tiles = 0; long long sum_m = 0;
   const float* bias = nullptr;
   __nv_bfloat16* out_bf16 = nullptr;                   // y (+res) as bf16, unscaled (nullable)
@@ -98,7 +98,7 @@ struct ArbConvArgs {
   float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
   long long* timing = nullptr;                         // diagnostics (-DKKX_ARB_TIMING builds): per-role phase cycle counters
 };
-int arb_tile_rows(int C);
+int arb_tile_rows(int C, int ks);   // rows per persistent-kernel tile for this shape (128, 256 or 512)
 bool arb_conv_supported(int C, int ks, int dil, int B);
 void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st);
 

@@ -60,9 +60,9 @@ struct ArbCfg {
   static constexpr int KCH = BN / 64;                       // 64-channel chunks
   static constexpr int RA = MSUB * 128 + 56;                // rows per A slot (halo <= 2*25, 8-row granule)
   static constexpr uint32_t A_SLOT = RA * 128;              // bytes (multiple of 1024)
-  static constexpr int NA = (BN == 128 && !T) ? 2 : 3;      // A slots
+  static constexpr int NA = (BN == 128 && (!T || MSUB == 4)) ? 2 : 3;   // A slots
   static constexpr uint32_t B_STAGE = BN * 128;             // bytes
-  static constexpr int NB = (BN == 128) ? 6 : 3;            // B stages
+  static constexpr int NB = (T && MSUB == 4) ? 4 : (BN == 128) ? 6 : 3;   // B stages
   static constexpr int PITCH = 36;                          // floats per staged epilogue row
   static constexpr uint32_t STG = T ? 0 : 2 * 128 * PITCH * 4;   // one transpose buffer per epilogue group
   static constexpr uint32_t STAT = 4 * BN * 2 * 4;          // per-quadrant column sums
@@ -102,7 +102,13 @@ struct TileCur {
 // (an earlier, more generic version of this kernel lost ~40 % of its time to instruction-fetch stalls).
 template <int BN, int MSUB, bool CONV2, bool T>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
-  static_assert(!T || (BN == 128 && MSUB == 2), "transposed mode: C = 128, 256-row tiles");
+  static_assert(!T || (BN == 128 && (MSUB == 2 || MSUB == 4)), "transposed mode: C = 128, 256- or 512-row tiles");
+  // T with MSUB = 4 (k >= 7): 512-row tiles, i.e. TWO 128x256 MMAs per weight tile.  The k = 7 / 11 convs are
+  // bound by what an SM can ingest from L2 (the weight set is re-streamed for every tile: 352 KB per tile at
+  // k = 11); doubling the rows per weight tile halves that.  The two accumulators fill TMEM, so the epilogue
+  // of tile i no longer overlaps the MMAs of tile i+1 (the producers still run ahead) -- measured: not a net win
+  // (see arb_variant), kept as an opt-in variant.
+  constexpr int NBUF = (T && MSUB == 4) ? 1 : 2;
   using Cfg = ArbCfg<BN, MSUB, T>;
   constexpr int KCH = Cfg::KCH, NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   constexpr int MT = MSUB * 128;
@@ -193,8 +199,8 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       for (int tile = t_begin; tile < t_end; tile++, ti++) {
         const int rem = s_len[cur.b] - cur.mt * MT;         // rows of this item left from the tile start
         (void)rem;
-        const int buf = ti & 1;
-        mbar_wait(tempty(buf), (((uint32_t)(ti >> 1)) & 1u) ^ 1u);
+        const int buf = NBUF == 2 ? (ti & 1) : 0;
+        mbar_wait(tempty(buf), (NBUF == 2 ? (((uint32_t)(ti >> 1)) & 1u) : ((uint32_t)ti & 1u)) ^ 1u);
         tc_fence_after();
         TICK(0);
 #pragma unroll 1
@@ -217,11 +223,14 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
               // D[co, row] += W[co, k] * Act[row + tap*dil, k]: weights = M operand, 256 rows = N operand
               constexpr uint32_t idescT = umma_idesc_bf16(128, 256);
               const uint64_t wd = bd;
-              const uint64_t xd = umma_desc_sw128(slot + (uint32_t)(tap * dil) * 128u);
-              const uint32_t td = tmem_base + (uint32_t)(buf * 256);
 #pragma unroll
-              for (int k = 0; k < 4; k++)
-                umma_bf16(td, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idescT, (c | tap | k) ? 1u : 0u);
+              for (int s2 = 0; s2 < MSUB / 2; s2++) {
+                const uint64_t xd = umma_desc_sw128(slot + (uint32_t)(s2 * 256 + tap * dil) * 128u);
+                const uint32_t td = tmem_base + (uint32_t)(buf * 256 + s2 * 256);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                  umma_bf16(td, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idescT, (c | tap | k) ? 1u : 0u);
+              }
             } else {
 #pragma unroll
               for (int sub = 0; sub < MSUB; sub++) {
@@ -259,9 +268,11 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     const float2 os2 = make_float2(a.oscale, a.oscale);
     const bool accum = a.accumulate != 0;
     // residual rows are prefetched two 32-row chunks ahead (two register buffers), across tile boundaries
+    constexpr int RW = MSUB * 64;            // rows per epilogue warp (row half eg of the tile)
+    constexpr int NCHK = RW / 32;            // 32-row chunks per warp and tile (4 or 8)
     auto fetchT = [&](int L, int off, int m0, int ch, float (&rv)[32]) {
       if (!CONV2) return;
-      const int row = m0 + eg * 128 + ch * 32;
+      const int row = m0 + eg * RW + ch * 32;
       const float* rp = a.res + (size_t)(off + row) * 128 + co;
       const int left = L - row;
 #pragma unroll
@@ -285,22 +296,22 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       const int b = cur.b;
       const int L = s_len[b], off = s_off[b];
       const int m0 = cur.mt * MT;
-      const int buf = ti & 1;
+      const int buf = NBUF == 2 ? (ti & 1) : 0;
       cur.next(s_ts);                       // cur now names the NEXT tile (prefetch target)
       const bool has_next = tile + 1 < t_end;
       const int nL = has_next ? s_len[cur.b] : 0, noff = has_next ? s_off[cur.b] : 0, nm0 = cur.mt * MT;
       TICK(8);
-      mbar_wait(tfull(buf), ((uint32_t)(ti >> 1)) & 1u);
+      mbar_wait(tfull(buf), NBUF == 2 ? (((uint32_t)(ti >> 1)) & 1u) : ((uint32_t)ti & 1u));
       tc_fence_after();
       TICK(0);
       float2 s2 = make_float2(0.f, 0.f), q2 = s2;
       auto bodyT = [&](int ch, float (&rv)[32], auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        const int row = m0 + eg * 128 + ch * 32;
+        const int row = m0 + eg * RW + ch * 32;
         const int left = L - row;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + eg * 128 + ch * 32), v);
-        if (ch == 3) {      // last TMEM read of this tile by this warp
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + eg * RW + ch * 32), v);
+        if (ch == NCHK - 1) {      // last TMEM read of this tile by this warp
           tc_fence_before();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
         }
@@ -342,21 +353,24 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
         }
         TICK(5);
         // refill this register buffer with the rows of chunk ch+2 (possibly of the next tile)
-        if (ch + 2 < 4) fetchT(L, off, m0, ch + 2, rv);
-        else if (has_next) fetchT(nL, noff, nm0, ch - 2, rv);
+        if (ch + 2 < NCHK) fetchT(L, off, m0, ch + 2, rv);
+        else if (has_next) fetchT(nL, noff, nm0, ch + 2 - NCHK, rv);
         TICK(6);
+        if ((ch & 3) == 3) {   // 128 rows done: one thread per channel and statistics chunk
+          if (a.part && row - 96 < L) {
+            float* pp = a.part + ((size_t)b * a.nchunk + (size_t)((row - 96) >> 7)) * 2 * 128 + co;
+            pp[0] = s2.x + s2.y;
+            pp[128] = q2.x + q2.y;
+          }
+          s2 = make_float2(0.f, 0.f); q2 = s2;
+        }
       };
       if (L - m0 >= MT) {
-        bodyT(0, rv0, std::true_type{}); bodyT(1, rv1, std::true_type{});
-        bodyT(2, rv0, std::true_type{}); bodyT(3, rv1, std::true_type{});
+#pragma unroll
+        for (int ch = 0; ch < NCHK; ch += 2) { bodyT(ch, rv0, std::true_type{}); bodyT(ch + 1, rv1, std::true_type{}); }
       } else {
-        bodyT(0, rv0, std::false_type{}); bodyT(1, rv1, std::false_type{});
-        bodyT(2, rv0, std::false_type{}); bodyT(3, rv1, std::false_type{});
-      }
-      if (a.part && m0 + eg * 128 < L) {   // one thread per channel and 128-row statistics chunk
-        float* pp = a.part + ((size_t)b * a.nchunk + (size_t)((m0 >> 7) + eg)) * 2 * 128 + co;
-        pp[0] = s2.x + s2.y;
-        pp[128] = q2.x + q2.y;
+#pragma unroll
+        for (int ch = 0; ch < NCHK; ch += 2) { bodyT(ch, rv0, std::false_type{}); bodyT(ch + 1, rv1, std::false_type{}); }
       }
       TICK(7);
     }
@@ -683,7 +697,18 @@ void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-int arb_tile_rows(int C) { return C == 128 ? 256 : 128; }
+// kernel variant per shape: 0 = rows as M (C = 256, or C = 128 with KKX_ARB_NOT=1), 1 = transposed with 256-row
+// tiles, 2 = transposed with 512-row tiles (k >= 7: halves the weight re-streaming the k = 7/11 convs are bound by)
+static int arb_variant(int C, int ks) {
+  static const bool no_t = [] { const char* e = getenv("KKX_ARB_NOT"); return e && e[0] == '1'; }();
+  // 512-row tiles measured on B200 (5.7 M rows): conv1 k7 1.40 -> 1.25 ms, conv1 k11 unchanged, conv2 k7 / k11
+  // 1.65 -> 1.81 / 1.81 -> 2.19 ms (losing the epilogue/MMA overlap costs more than the halved weight stream
+  // saves; ncu shows the tensor pipe already 75 % active at k = 11).  Opt-in: KKX_ARB_512=1.
+  static const bool use_512 = [] { const char* e = getenv("KKX_ARB_512"); return e && e[0] == '1'; }();
+  if (C != 128 || no_t) return 0;
+  return (ks >= 7 && use_512) ? 2 : 1;
+}
+int arb_tile_rows(int C, int ks) { return C == 128 ? (arb_variant(C, ks) == 2 ? 512 : 256) : 128; }
 
 bool arb_conv_supported(int C, int ks, int dil, int B) {
   return (C == 128 || C == 256) && ks >= 1 && dil >= 1 && dil * (ks - 1) <= 50 && (ks & 1) && B <= kArbMaxB;
@@ -703,8 +728,10 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
     // every tensor once: conv1 reads fp32, writes bf16; conv2 reads bf16 + fp32 residual, writes fp32
     g_launch_stats->arb_bytes += (double)a.sum_m * a.C * (a.in_bf16 ? 10.0 : 6.0);
   }
-  static const bool no_t = [] { const char* e = getenv("KKX_ARB_NOT"); return e && e[0] == '1'; }();
-  if (a.C == 128 && !no_t) {
+  const int variant = arb_variant(a.C, a.ks);
+  if (variant == 2) {
+    if (a.in_bf16) launch_arb_t<128, 4, true, true>(a, st); else launch_arb_t<128, 4, false, true>(a, st);
+  } else if (variant == 1) {
     if (a.in_bf16) launch_arb_t<128, 2, true, true>(a, st); else launch_arb_t<128, 2, false, true>(a, st);
   } else if (a.C == 128) {
     if (a.in_bf16) launch_arb_t<128, 2, true, false>(a, st); else launch_arb_t<128, 2, false, false>(a, st);

@@ -426,17 +426,20 @@ Level Model::make_level(const std::vector<int>& lens, Arena& A) {
   L.d_len = A.alloc<int>(L.B);
   L.d_tiles128 = A.alloc<int>(L.B + 1);
   L.d_tiles256 = A.alloc<int>(L.B + 1);
-  std::vector<int> t128(L.B + 1, 0), t256(L.B + 1, 0);
+  L.d_tiles512 = A.alloc<int>(L.B + 1);
+  std::vector<int> t128(L.B + 1, 0), t256(L.B + 1, 0), t512(L.B + 1, 0);
   for (int b = 0; b < L.B; b++) {
     t128[b + 1] = t128[b] + (lens[b] + 127) / 128;
     t256[b + 1] = t256[b] + (lens[b] + 255) / 256;
+    t512[b + 1] = t512[b] + (lens[b] + 511) / 512;
   }
-  L.ntiles128 = t128[L.B]; L.ntiles256 = t256[L.B];
+  L.ntiles128 = t128[L.B]; L.ntiles256 = t256[L.B]; L.ntiles512 = t512[L.B];
   if (!g_dry_run) {
     KKX_CUDA(cudaMemcpyAsync(L.d_off, L.off.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaMemcpyAsync(L.d_len, L.len.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaMemcpyAsync(L.d_tiles128, t128.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaMemcpyAsync(L.d_tiles256, t256.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    KKX_CUDA(cudaMemcpyAsync(L.d_tiles512, t512.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
     KKX_CUDA(cudaStreamSynchronize(stream_));  // L.off / L.len are locals of the caller's frame
   }
   return L;

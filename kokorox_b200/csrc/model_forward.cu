@@ -325,8 +325,9 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
     // statistics for the next AdaIN from the conv epilogues -- one colstats pass per res-block
     ArbConvArgs base;
     base.C = C; base.ks = k; base.off = L.d_off; base.len = L.d_len; base.B = B; base.sum_m = L.sum_len;
-    base.tile_start = C == 128 ? L.d_tiles256 : L.d_tiles128;
-    base.total_tiles = C == 128 ? L.ntiles256 : L.ntiles128;
+    const int trows = arb_tile_rows(C, k);
+    base.tile_start = trows == 512 ? L.d_tiles512 : trows == 256 ? L.d_tiles256 : L.d_tiles128;
+    base.total_tiles = trows == 512 ? L.ntiles512 : trows == 256 ? L.ntiles256 : L.ntiles128;
     base.scale = sc; base.shift = sh; base.nchunk = nch;
     // statistics of the block input: shared by the three res-blocks of a stage (computed once by the caller)
     if (!part_x) launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
