@@ -659,12 +659,11 @@ __device__ __forceinline__ void lstm_mbar_wait(uint32_t bar, uint32_t parity) {
       "LD_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// Register blocking of the per-step dot products (the kernel is bound by shared-memory wavefronts, not by
-// FMAs): a thread owns TWO gate rows and one QUARTER of the k range for all G items, so every h vector
-// fetched from smem feeds 8 FMAs and every weight vector G*4.  Layouts are chosen so that each LDS.128 is
-// served in the minimum number of wavefronts: weights [k/4][row parity][row pair] (8 lanes = 128 contiguous
-// bytes), h [item][quarter][64 + 4 pad] (the 4 quarters of a warp hit 4 different bank groups, lanes of
-// a quarter broadcast).
+// Register-stationary weights: a thread owns TWO gate rows and one QUARTER of the k range for all G items and
+// keeps those 2 x 64 weights in registers for the whole sequence (the 8 CTAs x 256 threads of a cluster hold
+// the full 1 MB W_hh of one direction), so the per-step dot products read only h from shared memory: one
+// broadcast LDS.128 feeds 8 FMAs, issued as packed FFMA2 over consecutive k.  h layout [item][quarter]
+// [64 + 4 pad]: the 4 quarters of a warp hit 4 different bank groups, lanes of a quarter broadcast.
 constexpr int kHQ = 68;                 // floats per h quarter (64 + 4 pad)
 constexpr int kHItem = 4 * kHQ;         // floats per item in an h buffer
 
@@ -674,8 +673,7 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
                                                               float* __restrict__ out, int ldo, int ocol,
                                                               const int* off, const int* len, int B) {
   extern __shared__ float4 lsm4[];
-  float* Ws = reinterpret_cast<float*>(lsm4);          // [64 k4][2 parity][64 row pairs][4]
-  float* hbuf = Ws + 256 * 128;                        // [2][G][4][68]
+  float* hbuf = reinterpret_cast<float*>(lsm4);        // [2][G][4][68]
   float* gates = hbuf + 2 * G * kHItem;                // [G][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gates + G * 128);   // [2] h-buffer "full" barriers
   cg::cluster_group cluster = cg::this_cluster();
@@ -686,13 +684,6 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
   const int rp = warp * 8 + (lane & 7);                // row pair: local gate rows 2rp, 2rp+1
   constexpr uint32_t kStepBytes = G * 256 * 4;         // bytes every CTA receives per step
 
-  // stage this CTA's 128 KB weight slice; local row rl = gate*32 + j  <->  W_hh row gate*256 + r*32 + j
-  const float* Wg = whhT + (size_t)dir * 256 * 1024;
-  for (int i = tid; i < 256 * 128; i += 256) {
-    const int k = i >> 7, rl = i & 127;
-    const int gr = (rl >> 5) * 256 + r * 32 + (rl & 31);
-    Ws[(((k >> 2) * 2 + (rl & 1)) * 64 + (rl >> 1)) * 4 + (k & 3)] = Wg[(size_t)k * 1024 + gr];
-  }
   for (int i = tid; i < 2 * G * kHItem; i += 256) hbuf[i] = 0.f;
   const uint32_t bar0 = lstm_smem_u32(bars), bar1 = bar0 + 8;
   if (tid == 0) {
@@ -712,8 +703,21 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
     ilen[g] = item < B ? len[item] : 0;
     maxN = max(maxN, ilen[g]);
   }
-  // global gate rows of this thread's row pair (same gate block: 2rp and 2rp+1 never straddle 32)
+  // global gate rows of this thread's row pair (same gate block: 2rp and 2rp+1 never straddle 32);
+  // local row rl = gate*32 + j  <->  W_hh row gate*256 + r*32 + j
   const int grow0 = ((2 * rp) >> 5) * 256 + r * 32 + ((2 * rp) & 31);
+  // this thread's weights, k in [64q, 64q+64), as pairs over consecutive k (FFMA2 operands)
+  float2 w0[32], w1[32];
+  {
+    const float* Wg = whhT + (size_t)dir * 256 * 1024 + (size_t)(64 * q) * 1024 + grow0;
+#pragma unroll
+    for (int kk = 0; kk < 32; kk++) {
+      const float2 a = *reinterpret_cast<const float2*>(Wg + (size_t)(2 * kk) * 1024);       // rows (2rp, 2rp+1) at k
+      const float2 b2 = *reinterpret_cast<const float2*>(Wg + (size_t)(2 * kk + 1) * 1024);  // ... at k+1
+      w0[kk] = make_float2(a.x, b2.x);
+      w1[kk] = make_float2(a.y, b2.y);
+    }
+  }
   float c = 0.f;                                         // cell state of (item tid>>5, unit tid&31)
   float2 xpn[G];
 #pragma unroll
@@ -746,29 +750,27 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
         xpn[g] = *reinterpret_cast<const float2*>(xproj + (size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow0);
       }
     }
-    float acc0[G], acc1[G];
+    float2 acc0[G], acc1[G];               // (even-k, odd-k) partial sums of the two rows
 #pragma unroll
-    for (int g = 0; g < G; g++) { acc0[g] = 0.f; acc1[g] = 0.f; }
-    const float4* w4 = reinterpret_cast<const float4*>(Ws) + (size_t)(q * 16) * 128 + rp;
+    for (int g = 0; g < G; g++) { acc0[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
     const float4* h4 = reinterpret_cast<const float4*>(hc + q * kHQ);
-#pragma unroll 4
+#pragma unroll
     for (int kk = 0; kk < 16; kk++) {
-      const float4 wa = w4[kk * 128], wb = w4[kk * 128 + 64];
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const float4 h = h4[g * (kHItem / 4) + kk];
-        acc0[g] = fmaf(wa.x, h.x, acc0[g]); acc1[g] = fmaf(wb.x, h.x, acc1[g]);
-        acc0[g] = fmaf(wa.y, h.y, acc0[g]); acc1[g] = fmaf(wb.y, h.y, acc1[g]);
-        acc0[g] = fmaf(wa.z, h.z, acc0[g]); acc1[g] = fmaf(wb.z, h.z, acc1[g]);
-        acc0[g] = fmaf(wa.w, h.w, acc0[g]); acc1[g] = fmaf(wb.w, h.w, acc1[g]);
+        const float2 h01 = make_float2(h.x, h.y), h23 = make_float2(h.z, h.w);
+        acc0[g] = __ffma2_rn(w0[2 * kk], h01, acc0[g]); acc1[g] = __ffma2_rn(w1[2 * kk], h01, acc1[g]);
+        acc0[g] = __ffma2_rn(w0[2 * kk + 1], h23, acc0[g]); acc1[g] = __ffma2_rn(w1[2 * kk + 1], h23, acc1[g]);
       }
     }
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      acc0[g] += __shfl_xor_sync(0xffffffffu, acc0[g], 8);  acc1[g] += __shfl_xor_sync(0xffffffffu, acc1[g], 8);
-      acc0[g] += __shfl_xor_sync(0xffffffffu, acc0[g], 16); acc1[g] += __shfl_xor_sync(0xffffffffu, acc1[g], 16);
+      float a0 = acc0[g].x + acc0[g].y, a1 = acc1[g].x + acc1[g].y;
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 8);  a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
       if ((g & 3) == q)
-        *reinterpret_cast<float2*>(gates + g * 128 + 2 * rp) = make_float2(acc0[g] + xp[g].x, acc1[g] + xp[g].y);
+        *reinterpret_cast<float2*>(gates + g * 128 + 2 * rp) = make_float2(a0 + xp[g].x, a1 + xp[g].y);
     }
     __syncthreads();
     if (tid < 32 * G) {
@@ -808,7 +810,7 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
 template <int G>
 static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                                 const int* off, const int* len, int B, cudaStream_t st) {
-  const size_t smem = (size_t)(256 * 128 + 2 * G * kHItem + G * 128) * sizeof(float) + 16;
+  const size_t smem = (size_t)(2 * G * kHItem + G * 128) * sizeof(float) + 16;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
