@@ -149,6 +149,9 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
 constexpr int kStatRows = 128;
 void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
                      int B, int max_len, cudaStream_t st);  // part [B][nchunk_max][2][C]
+// out = a + b (all [rows, C], row pitch C) and the chunk statistics of the sum, in one pass
+void launch_add_rows_stats(const float* a, const float* b, float* out, int C, float* part, const int* off,
+                           const int* len, int B, int max_len, cudaStream_t st);
 void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
                        int sld, int soff, float eps, float* scale, float* shift, int B,
                        cudaStream_t st);

@@ -10,10 +10,13 @@ namespace kkx {
 // part layout: [B][nchunk][2][C] with nchunk = ceil(max_len / kStatRows).
 // Block = 256 threads = XT column-quads x YT row slices (float4 loads when C % 4 == 0); the row
 // slices are combined through shared memory in a fixed order (deterministic).
-template <int VEC>
+// ADD: the statistics are those of x + y, and the sum is also stored to `out` (same row pitch): the generator's
+// `x = ups(x) + x_source` add and the first AdaIN's statistics pass in one sweep.
+template <int VEC, bool ADD>
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, int ldx, int C,
                                                        float* __restrict__ part, int nchunk,
-                                                       const int* off, const int* len) {
+                                                       const int* off, const int* len,
+                                                       const float* __restrict__ y, float* __restrict__ out) {
   __shared__ float red[2][256 * VEC];
   const int b = blockIdx.y, ch = blockIdx.x;
   const int L = len[b];
@@ -34,7 +37,13 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
       const float* p = x + (size_t)(off[b] + r0 + ty) * ldx + cg * VEC;
       for (int r = r0 + ty; r < r1; r += YT, p += (size_t)YT * ldx) {
         if (VEC == 4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(p);
+          float4 v4 = *reinterpret_cast<const float4*>(p);
+          if (ADD) {
+            const size_t o = (size_t)(p - x);
+            const float4 w4 = *reinterpret_cast<const float4*>(y + o);
+            v4.x += w4.x; v4.y += w4.y; v4.z += w4.z; v4.w += w4.w;
+            *reinterpret_cast<float4*>(out + o) = v4;
+          }
           s[0] += v4.x; q[0] = fmaf(v4.x, v4.x, q[0]);
           s[1 % VEC] += v4.y; q[1 % VEC] = fmaf(v4.y, v4.y, q[1 % VEC]);
           s[2 % VEC] += v4.z; q[2 % VEC] = fmaf(v4.z, v4.z, q[2 % VEC]);
@@ -66,10 +75,20 @@ void launch_colstats(const float* x, int ldx, int C, float* part, const int* off
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
   dim3 g(nchunk, B);
   if ((C % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0))
-    colstats_kernel<4><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
+    colstats_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr);
   else
-    colstats_kernel<1><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len);
+    colstats_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr);
   post_launch("colstats", st);
+}
+void launch_add_rows_stats(const float* a, const float* b, float* out, int C, float* part, const int* off,
+                           const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  if (C % 4 != 0 || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15))
+    throw ArgError("launch_add_rows_stats: needs C % 4 == 0 and 16-byte aligned tensors");
+  const int nchunk = (max_len + kStatRows - 1) / kStatRows;
+  dim3 g(nchunk, B);
+  colstats_kernel<4, true><<<g, 256, 0, st>>>(a, C, C, part, nchunk, off, len, b, out);
+  post_launch("add_rows_stats", st);
 }
 
 // Combine the chunk partials (fp64, fixed order) -> AdaIN coefficients.  Block = 32 channels x 8
@@ -88,7 +107,20 @@ __global__ void __launch_bounds__(256) adain_coef_kernel(const float* __restrict
   double S = 0.0, Q = 0.0;
   if (c < C) {
     const float* pp = part + (size_t)b * nchunk * 2 * C + c;
-    for (int k = ty; k < nc; k += 8) {
+    int k = ty;
+    // 8 chunks (16 independent loads) in flight per thread: the kernel is pure L2/HBM latency otherwise;
+    // the additions keep their fixed order
+    for (; k + 56 < nc; k += 64) {
+      float sv[8], qv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        sv[u] = pp[(size_t)(k + 8 * u) * 2 * C];
+        qv[u] = pp[(size_t)(k + 8 * u) * 2 * C + C];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { S += (double)sv[u]; Q += (double)qv[u]; }
+    }
+    for (; k < nc; k += 8) {
       S += (double)pp[(size_t)k * 2 * C];
       Q += (double)pp[(size_t)k * 2 * C + C];
     }

@@ -569,12 +569,13 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     launch_conv_f32(c, st);
   }
   capture("gen.ups.0", x0, 256, 0, 256, G20, b0);
-  launch_add_rows(x0, xs0, x0, 256, G20.d_off, G20.d_len, B, G20.max_len, st);
   {
     float* px = nullptr;
-    if (opt.precision == 1) {
+    if (opt.precision == 1) {   // x0 += x_source and the statistics of the sum (input of three res-blocks) in one pass
       px = A.alloc<float>((size_t)B * ((G20.max_len + kStatRows - 1) / kStatRows) * 2 * 256);
-      launch_colstats(x0, 256, 256, px, G20.d_off, G20.d_len, B, G20.max_len, st);
+      launch_add_rows_stats(x0, xs0, x0, 256, px, G20.d_off, G20.d_len, B, G20.max_len, st);
+    } else {
+      launch_add_rows(x0, xs0, x0, 256, G20.d_off, G20.d_len, B, G20.max_len, st);
     }
     for (int j = 0; j < 3; j++)
       arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0, px);
@@ -619,12 +620,13 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   }
   launch_copy_row(x1, 128, 0, 2, G120.d_off, B, st);
   capture("gen.ups.1", x1, 128, 0, 128, G120, b0);
-  launch_add_rows(x1, xs1, x1, 128, G120.d_off, G120.d_len, B, G120.max_len, st);
   {
     float* px = nullptr;
     if (opt.precision == 1) {
       px = A.alloc<float>((size_t)B * ((G120.max_len + kStatRows - 1) / kStatRows) * 2 * 128);
-      launch_colstats(x1, 128, 128, px, G120.d_off, G120.d_len, B, G120.max_len, st);
+      launch_add_rows_stats(x1, xs1, x1, 128, px, G120.d_off, G120.d_len, B, G120.max_len, st);
+    } else {
+      launch_add_rows(x1, xs1, x1, 128, G120.d_off, G120.d_len, B, G120.max_len, st);
     }
     for (int j = 0; j < 3; j++)
       arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0, px);
