@@ -53,6 +53,8 @@ struct TcConvArgs {
   float* out = nullptr; int ldo = 0; int ocol = 0; const int* out_off = nullptr; int ors = 1, oro = 0;
   const float* res = nullptr; int ldr = 0; int rcol = 0; const int* res_off = nullptr; int res_shift = 0;
   float oscale = 1.f; int accumulate = 0; int vec4 = 0;
+  long long* timing = nullptr;   // diagnostics (-DKKX_TC_TIMING builds)
+  const int* tile_start = nullptr; int ntiles_m = 0;   // persistent split-TF32 GEMM: prefix sum of ceil(m_len/128) per item
   int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);

@@ -15,6 +15,16 @@
 
 namespace kkx {
 
+#ifdef KKX_TC_TIMING
+#define TCT_DECL(n) long long tct_acc[n] = {0}; long long tct_last = clock64(); const bool tct_on = a.timing && blockIdx.x == gridDim.x - 2 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1
+#define TCT(slot) do { if (tct_on) { const long long now_ = clock64(); tct_acc[slot] += now_ - tct_last; tct_last = now_; } } while (0)
+#define TCT_FLUSH(base, n) do { if (tct_on) for (int i_ = 0; i_ < (n); i_++) atomicAdd(reinterpret_cast<unsigned long long*>(a.timing) + (base) + i_, (unsigned long long)tct_acc[i_]); } while (0)
+#else
+#define TCT_DECL(n)
+#define TCT(slot)
+#define TCT_FLUSH(base, n)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // host: tensor-map encoding through the driver entry point (no libcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -147,18 +157,22 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       const int row0 = a.in_off[b] + m0 - a.pad;
+      TCT_DECL(2);
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);   // CL > 1: every CTA of the cluster has drained this stage
+        TCT(0);
         const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
         const uint32_t sa = base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const bool skipA2 = MODE && (a.debug & 8);     // perf experiment: pretend the A lo plane needs no L2 traffic
+        const bool skipB2 = MODE && (a.debug & 16);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES - (skipA2 ? A_BYTES : 0) - (skipB2 ? B_BYTES : 0));
         tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
-        if (MODE) tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
+        if (MODE && !skipA2) tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
         if (CL == 1) {
           tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
-          if (MODE) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+          if (MODE && !skipB2) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
         } else {
           // this CTA's 1/CL of the weight rows (tmB / tmB2 have BN/CL-row boxes), multicast to the whole cluster
           constexpr uint32_t SUB = (BN / CL) * 128;
@@ -167,16 +181,20 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           if (MODE) tma_load_2d_mc(sa + 2 * A_BYTES + B_BYTES + crank * SUB, &tmB2, tap * a.Cpad + c0,
                                    n0 + (int)crank * (BN / CL), full_bar(s), cmask);
         }
+        TCT(1);
       }
+      TCT_FLUSH(0, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = MODE ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
+      TCT_DECL(3);
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        TCT(0);
         const uint32_t sa = base + s * STAGE_BYTES;
         if (MODE == 0) {
           const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
@@ -189,6 +207,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           if (chain_start && chain >= 3) {       // ring slot j must have been drained by the epilogue
             mbar_wait(bempty_bar(j), (uint32_t)(chain / 3 - 1) & 1u);
             tc_fence_after();
+            TCT(1);
           }
           const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + A_BYTES);
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
@@ -196,17 +215,22 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
             const uint64_t o = (uint64_t)(2 * k);
+            if (a.debug & 2) continue;                 // perf experiment: no MMAs
             if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
-            umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
-            umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
+            if (!(a.debug & 32)) {                     // perf experiment: hi*hi only
+              umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
+              umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
+            }
             umma_tf32(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u);
           }
           if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
         }
         if (CL == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
         else umma_commit_mc(empty_bar(s), cmask);   // ... in every CTA of the cluster (they all write into it)
+        TCT(2);
       }
       umma_commit(tfull_bar);       // accumulator complete
+      TCT_FLUSH(4, 3);
     }
   } else {
     // ---- epilogue (4 warps).  All MMAs have completed when tfull_bar flips, so the pipeline
@@ -217,6 +241,10 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     const int q = warp & 3;                 // TMEM lane quadrant this warp may access
     const int et = q * 32 + lane;           // accumulator row held by this thread
     float racc[MODE ? BN : 1];              // MODE 1: fp32 (round-to-nearest) sum of the drained hi*hi chains
+#ifdef KKX_TC_TIMING
+    long long tct_acc[4] = {0}; long long tct_last = clock64();
+    const bool tct_on = a.timing && blockIdx.x == gridDim.x - 2 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1 && threadIdx.x == 64;
+#endif
     if (MODE) {
 #pragma unroll
       for (int e = 0; e < (MODE ? BN : 1); e++) racc[e] = 0.f;
@@ -225,8 +253,10 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int j = ch % 3;
         mbar_wait(bfull_bar(j), (uint32_t)(ch / 3) & 1u);
         tc_fence_after();
+        TCT(0);
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
+          if (a.debug & 4) continue;                   // perf experiment: chains are not drained
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
 #pragma unroll
@@ -234,6 +264,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         }
         tc_fence_before();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
+        TCT(1);
       }
     }
     constexpr int PITCH = 36;               // floats per staged row (32 + 4 pad)
@@ -265,6 +296,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     if (MODE == 0) fetch(0, rv);            // overlaps the whole MMA main loop
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
+    TCT(2);
 #pragma unroll
     for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
@@ -312,6 +344,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
       }
       if (MODE == 0 && c + 32 < BN) fetch(c + 32, rv);   // in flight during the next chunk's TMEM->smem hop
     }
+    TCT(3);
+    TCT_FLUSH(8, 4);
   }
   tc_fence_before();
   __syncthreads();
@@ -501,6 +535,253 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent split-TF32 GEMM / conv (BN = 128, 3 stages of 4 x 16 KB operand planes).  One CTA per SM
+// walks tiles t = blockIdx.x + i*gridDim.x of the (n-tile, item, m-tile) space, m fastest.  Same arithmetic
+// and chain-split accumulation as conv_tc_kernel<128,3,1> (bit-identical results), but the TMA / MMA pipeline
+// runs straight across tile boundaries: measured on the single-tile kernel, only ~46 % of a tile's time was
+// MMA work -- the rest was launch + TMEM allocation + pipeline ramp (~14 %) and the final epilogue (~20 %),
+// neither overlapped with anything at one CTA per SM.  Here the epilogue pulls the small-terms accumulator
+// into registers right after the last chain, hands all of TMEM back, and finishes (smem transpose, bias,
+// activation, residual, stores) from registers while the next tile's operands stream in and its MMAs run.
+__global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB,
+                                                         const __grid_constant__ CUtensorMap tmA2,
+                                                         const __grid_constant__ CUtensorMap tmB2,
+                                                         TcConvArgs a) {
+  constexpr int BN = 128, STAGES = 3, KE = 32;
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  constexpr int PITCH = 36;
+  constexpr uint32_t STG_BYTES = 128 * PITCH * 4;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = stg_base + STG_BYTES;       // full[3], empty[3], bfull[3], bempty[3], sfull, sfree
+  const uint32_t tmem_slot = bar_base + 14 * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
+  auto bfull_bar = [&](int j) { return bar_base + (6 + j) * 8; };
+  auto bempty_bar = [&](int j) { return bar_base + (9 + j) * 8; };
+  const uint32_t sfull_bar = bar_base + 12 * 8, sfree_bar = bar_base + 13 * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.Cpad / KE;
+  const int num_k = a.ks * kchunks;
+  const int nchains = (num_k + 1) >> 1;
+  const int ntm = a.ntiles_m;
+  const int total = ntm * ((a.Co + BN - 1) / BN);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 4); }
+    mbar_init(sfull_bar, 1); mbar_init(sfree_bar, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // tile -> (n-tile, item, m-tile); tile_start is the prefix sum of ceil(m_len / 128) over the items
+  auto decode = [&](int t, int& b, int& m0, int& n0) {
+    const int nt = t / ntm, mg = t - nt * ntm;
+    int lo = 0, hi = a.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.tile_start[mid] <= mg) lo = mid; else hi = mid;
+    }
+    b = lo; m0 = (mg - a.tile_start[lo]) * 128; n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int b, m0, n0;
+        decode(t, b, m0, n0);
+        const int row0 = a.in_off[b] + m0 - a.pad;
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          mbar_wait(empty_bar(s), (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
+          const uint32_t sa = base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
+          tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
+          tma_load_2d(sa + 2 * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+          tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+      int g = 0, gc = 0, ti = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
+        // the small-terms accumulator of the previous tile must have been pulled into registers
+        if (ti > 0) { mbar_wait(sfree_bar, (uint32_t)(ti - 1) & 1u); tc_fence_after(); }
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const int G = gc + (it >> 1), j = G % 3;
+          const bool chain_start = (it & 1) == 0;
+          if (chain_start && G >= 3) {           // ring slot j must have been drained by the epilogue
+            mbar_wait(bempty_bar(j), (uint32_t)(G / 3 - 1) & 1u);
+            tc_fence_after();
+          }
+          const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
+          const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
+            const uint64_t o = (uint64_t)(2 * k);
+            if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
+            umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
+            umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
+            umma_tf32(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u);
+          }
+          if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(sfull_bar);
+        gc += nchains;
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int et = q * 32 + lane;           // accumulator row held by this thread
+    const int t128 = threadIdx.x - 64;
+    const int c4 = (t128 & 7) << 2;
+    float* const buf = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+    int gc = 0, ti = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
+      int b, m0, n0;
+      decode(t, b, m0, n0);
+      const int mlen = a.m_len[b];
+      float racc[BN];
+#pragma unroll
+      for (int e = 0; e < BN; e++) racc[e] = 0.f;
+      for (int ch = 0; ch < nchains; ch++) {
+        const int G = gc + ch, j = G % 3;
+        mbar_wait(bfull_bar(j), (uint32_t)(G / 3) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
+#pragma unroll
+          for (int e = 0; e < 32; e++) racc[c + e] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
+      }
+      gc += nchains;
+      mbar_wait(sfull_bar, (uint32_t)ti & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) racc[c + e] = __uint_as_float(v[e]) + racc[c + e];   // same order as the single-tile kernel
+      }
+      tc_fence_before();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sfree_bar) : "memory");   // TMEM is free again
+
+      // ---- the rest runs from registers while the next tile's pipeline is already going
+      const int out_off = a.out_off[b];
+      const int res_off = a.res ? a.res_off[b] : 0;
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        const int n = n0 + c + c4;
+        const bool vec = a.vec4 && (n + 3 < a.Co);
+        float4 rv[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {           // residual operand of this chunk (in flight across the two barriers)
+          const int mm = m0 + (t128 >> 3) + 16 * i;
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.res && n < a.Co && mm < mlen) {
+            const int orow = mm * a.ors + a.oro;
+            const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
+            if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+            else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer drained by the previous chunk
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(buf + et * PITCH + j) = make_float4(racc[c + j], racc[c + j + 1], racc[c + j + 2], racc[c + j + 3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (n < a.Co) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) {
+            if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+            else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int row = (t128 >> 3) + 16 * i;
+            const int mm = m0 + row;
+            if (mm >= mlen) continue;
+            float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+            o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+            o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+            float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
+            if (vec) {
+              if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+              *reinterpret_cast<float4*>(op) = o;
+            } else {
+              if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+              op[0] = o.x;
+              if (n + 1 < a.Co) op[1] = o.y;
+              if (n + 2 < a.Co) op[2] = o.z;
+              if (n + 3 < a.Co) op[3] = o.w;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
+  constexpr int smem = 3 * 4 * 128 * 128 + 128 * 36 * 4 + 14 * 8 + 16 + 1024;
+  static bool attr_set[64] = {false};
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    KKX_CUDA(cudaFuncSetAttribute(gemm32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    attr_set[dev] = true;
+  }
+  const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
+  const int total = a.ntiles_m * ((a.Co + 127) / 128);
+  const int grid = total < nsm ? total : nsm;
+  gemm32p_kernel<<<grid, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB),
+                                          *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2), a);
+}
+
 template <int BN, int STAGES, int TPC>
 static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (128 * 128 + BN * 128) + 2 * 128 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -551,14 +832,20 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (a0.max_m <= 0 || a0.B <= 0) return;
   TcConvArgs a = a0;
   static const int dbg = [] { const char* e = getenv("KKX_TC_DEBUG"); return e ? atoi(e) : 0; }();
-  a.debug = a.tf32 ? 0 : dbg;
+  a.debug = dbg;
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
   if (a.tf32) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
-    if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);
-    else if (a.Co > 64) launch_tc<128, 3, 1>(a, st);
-    else launch_tc<64, 4, 1>(a, st);
+    static const bool bn64 = [] { const char* e = getenv("KKX_TC_BN64"); return e && e[0] == '1'; }();
+    static const bool persist = [] { const char* e = getenv("KKX_TC_PERSIST"); return !e || e[0] != '0'; }();
+    if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) launch_gemm32p(a, st);
+    else if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);
+    else if (a.Co > 64 && !(bn64 && a.tmB_c)) launch_tc<128, 3, 1>(a, st);
+    else if (a.Co > 64) {   // experiment: 64-wide tiles (4 stages of 48 KB) with the half-height weight boxes
+      TcConvArgs b = a; b.tmB = a.tmB_c; b.tmB2 = a.tmB2_c;
+      launch_tc<64, 4, 1>(b, st);
+    } else launch_tc<64, 4, 1>(a, st);
     if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
       char nm[96]; snprintf(nm, sizeof nm, "conv_tc_tf32x3[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);
       post_launch(nm, st);

@@ -38,8 +38,11 @@ void arb_timing_dump() {
   cudaDeviceSynchronize();
   cudaMemcpy(h, g_arb_timing, sizeof h, cudaMemcpyDeviceToHost);
   cudaMemset(g_arb_timing, 0, sizeof h);
+  fprintf(stderr, "[tf32x3 timing, CTA 0 of every launch] (Mcycles) TMA wait_empty %.2f issue %.2f | MMA wait_full %.2f wait_ring %.2f issue %.2f |"
+          " EPI wait_chain %.2f drain %.2f wait_final %.2f final %.2f\n", h[100] / 1e6, h[101] / 1e6, h[104] / 1e6, h[105] / 1e6, h[106] / 1e6,
+          h[108] / 1e6, h[109] / 1e6, h[110] / 1e6, h[111] / 1e6);
   const char* nm[4] = {"conv1 C128", "conv2 C128", "conv1 C256", "conv2 C256"};
-  for (int v = 0; v < 4; v++) {
+  for (int v = 0; v < 3; v++) {
     const long long* t = h + v * 32;
     fprintf(stderr, "[arb timing %s] (Mcycles)  TMA wait %.2f issue %.2f | MMA wait_tempty %.2f wait_fullA %.2f wait_fullB %.2f issue %.2f |"
             " EPI wait_tfull %.2f tmem_ld %.2f barA %.2f sts %.2f barB %.2f compute+store %.2f fetch %.2f stats %.2f tile %.2f |"
@@ -85,11 +88,13 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
     // GEMMs): these GEMMs are bound by what each SM can ingest (~28 B/clk: 64 KB of hi/lo planes per 128x128x32
     // step), which multicast does not change.  Opt-in (KKX_TC_CLUSTER=1).
     static const bool cl_ok = [] { const char* e = getenv("KKX_TC_CLUSTER"); return e && e[0] == '1'; }();
-    if (cl_ok && w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = 2; }
+    if (w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = cl_ok ? 2 : 1; }
     a.Cpad = w32->Cpad; a.Ci = K; a.Co = N; a.ks = ks; a.dil = 1; a.pad = pad;
     a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
     a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lm.d_off;
     a.res = res; a.ldr = ldr; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift; a.oscale = oscale;
+    if (long long* tim = arb_timing_buf()) a.timing = tim + 100;   // diagnostics: slots 100..111
+    a.tile_start = Lm.d_tiles128; a.ntiles_m = Lm.ntiles128;
     launch_conv_tc(a, st);
     return;
   }
