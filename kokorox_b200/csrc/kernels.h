@@ -55,6 +55,7 @@ struct TcConvArgs {
   float oscale = 1.f; int accumulate = 0; int vec4 = 0;
   long long* timing = nullptr;   // diagnostics (-DKKX_TC_TIMING builds)
   const int* tile_start = nullptr; int ntiles_m = 0;   // persistent split-TF32 GEMM: prefix sum of ceil(m_len/128) per item
+  int group_m = 1;               // (set by the launcher) m-tiles per L2-resident group
   int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);

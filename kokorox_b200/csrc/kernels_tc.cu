@@ -593,8 +593,15 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   // tile -> (n-tile, item, m-tile); tile_start is the prefix sum of ceil(m_len / 128) over the items
+  // Order: groups of `gm` consecutive m-tiles whose operand planes (~48 MB) stay L2-resident while all the
+  // n-tiles of the group are computed (n outer, m inner inside a group) -- the activation planes of a whole
+  // GEMM (200 MB at M = 32768, K = 768) do not fit the 126 MB L2.
+  const int NT = (a.Co + BN - 1) / BN;
+  const int gm = a.group_m;
   auto decode = [&](int t, int& b, int& m0, int& n0) {
-    const int nt = t / ntm, mg = t - nt * ntm;
+    const int g = t / (gm * NT), r = t - g * gm * NT;
+    const int gsz = min(gm, ntm - g * gm);
+    const int nt = r / gsz, mg = g * gm + (r - nt * gsz);
     int lo = 0, hi = a.B;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -778,8 +785,15 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
   const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
   const int total = a.ntiles_m * ((a.Co + 127) / 128);
   const int grid = total < nsm ? total : nsm;
+  TcConvArgs b = a;
+  static const int l2mb = [] { const char* e = getenv("KKX_TC_GROUP_MB"); return e ? atoi(e) : 24; }();
+  const long long per_tile = 128LL * a.Cpad * 8;       // bytes of hi+lo planes of one m-tile
+  long long gm = (long long)l2mb * 1000000LL / (per_tile > 0 ? per_tile : 1);
+  if (gm < 8) gm = 8;
+  if (gm > a.ntiles_m) gm = a.ntiles_m;
+  b.group_m = (int)gm;
   gemm32p_kernel<<<grid, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB),
-                                          *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2), a);
+                                          *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2), b);
 }
 
 template <int BN, int STAGES, int TPC>
