@@ -281,10 +281,22 @@ def main():
             dn = sum(kern[k][0] for k in conv_names) or 1
             dus, dflops, dbytes = conv_us, prof.get("conv_flops", 0.0), 0.0
         achieved_tf = dflops / (dus * 1e-6) / 1e12
+        # DRAM traffic per launch: the ncu --set full capture of this kernel (profiles/) measured
+        # dram read+write = 1.00 x the algorithmic bytes; scale this run's per-launch algorithmic bytes by that ratio
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_arb_conv_traffic.json")) as f:
+                tj = json.load(f)
+            if dom == "arb_conv" and dbytes > 0:
+                traffic = tj["traffic_over_algorithmic"] * dbytes / max(dn, 1)
+                traffic_src = "ncu dram__bytes_read+write / algorithmic bytes = %.4f (%s)" % (tj["traffic_over_algorithmic"], "profiles/r1_arb_conv_traffic.json")
+        except Exception:
+            pass
         roofline = {
             "bound": "tensor", "kernel": dom,
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-            "traffic": None, "peak_source": f"{peaks_src} (sustained bf16; kernel timed inside a long step)",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": f"{peaks_src} (sustained bf16; kernel timed inside a long step)",
             "launches_per_step": dn, "avg_launch_us": dus / max(dn, 1),
             "alg_flops_per_launch": dflops / max(dn, 1),
             "alg_bytes_per_launch": dbytes / max(dn, 1),
