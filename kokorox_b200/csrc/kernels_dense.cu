@@ -419,8 +419,9 @@ __device__ __forceinline__ void att_mma(float (&c)[4], const uint32_t (&a)[4], u
 }
 constexpr int kAttLd = 68;   // smem row stride (floats): conflict-free B-fragment loads for both products
 
-__global__ void __launch_bounds__(128) attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
-                                                           const int* off, const int* len) {
+template <int NW>   // warps per CTA: NW*16 query rows share every staged K/V tile
+__global__ void __launch_bounds__(NW * 32) attention_tc_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+                                                               const int* off, const int* len) {
   extern __shared__ uint32_t att_sm[];
   uint32_t* Kh = att_sm;                       // [64][68] tf32 hi
   uint32_t* Kl = Kh + 64 * kAttLd;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const float* __restri
   uint32_t* Vl = Vh + 64 * kAttLd;
   const int b = blockIdx.z, h = blockIdx.y;
   const int N = len[b];
-  const int q0 = blockIdx.x * 64;
+  const int q0 = blockIdx.x * (NW * 16);
   if (q0 >= N) return;
   const size_t base = (size_t)off[b];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const float* __restri
   for (int k0 = 0; k0 < N; k0 += 64) {
     __syncthreads();
     // stage K and V tiles as hi/lo planes (float4 global loads, 16 rows x 8 column quads per pass)
-    for (int i = tid; i < 64 * 16; i += 128) {
+    for (int i = tid; i < 64 * 16; i += NW * 32) {
       const int j = i >> 4, c4 = (i & 15) << 2;
       float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
       if (k0 + j < N) {
@@ -570,11 +571,17 @@ void launch_attention(const float* qkv, float* ctx, const int* off, const int* l
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
-      KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set[dev] = true;
     }
-    dim3 g((max_len + 63) / 64, 12, B);
-    attention_tc_kernel<<<g, 128, smem, st>>>(qkv, ctx, off, len);
+    if (max_len > 64) {   // 128 query rows per CTA: the K/V staging (load + tf32 split) is amortised over twice the MMAs
+      dim3 g((max_len + 127) / 128, 12, B);
+      attention_tc_kernel<8><<<g, 256, smem, st>>>(qkv, ctx, off, len);
+    } else {
+      dim3 g((max_len + 63) / 64, 12, B);
+      attention_tc_kernel<4><<<g, 128, smem, st>>>(qkv, ctx, off, len);
+    }
   }
   post_launch("attention", st);
 }

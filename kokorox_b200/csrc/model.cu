@@ -572,7 +572,9 @@ void Model::run() {
   int b0 = 0;
   while (b0 < B_) {
     int b1 = b0; long long fr = 0;
-    while (b1 < B_ && (b1 == b0 || fr + r.T[b1] <= opt.max_frames)) { fr += r.T[b1]; b1++; }
+    // at most 512 items per group: the fused generator kernels keep per-item tables in shared memory, and a
+    // batch must take the same code path as a single call (results are bit-identical either way)
+    while (b1 < B_ && b1 - b0 < 512 && (b1 == b0 || fr + r.T[b1] <= opt.max_frames)) { fr += r.T[b1]; b1++; }
     // size the arena with a dry run of the same allocation sequence (no launches, no copies)
     frA_.reset();
     frA_.set_virtual(true);

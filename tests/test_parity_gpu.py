@@ -219,3 +219,27 @@ def test_bf16_batch_equals_single(model):
             assert np.array_equal(outs[b], singles[b][0])
     finally:
         model.set_option("precision", 0)
+
+
+def test_many_short_requests_bf16(model):
+    # BASELINE configs[3]/[4] flavour: hundreds of short, mixed-length, mixed-speed requests in one call (more items
+    # than one frame group may hold).  Every item must equal its own B=1 call bit for bit, and lengths must follow
+    # the integer durations.
+    rng = np.random.default_rng(4)
+    B = 600
+    lens = rng.integers(3, 41, size=B)
+    cases = [synth_case(int(n), 5000 + i, 6000 + (i % 54)) for i, n in enumerate(lens)]
+    speeds = rng.uniform(0.8, 1.3, size=B).astype(np.float32).tolist()
+    model.set_option("precision", 1)
+    try:
+        model.set_noise(None)
+        outs, durs = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds, return_durations=True)
+        assert len(outs) == B
+        for b in range(B):
+            assert len(outs[b]) == 600 * int(durs[b].sum()) and np.isfinite(outs[b]).all()
+        for b in (0, 17, 311, 599):
+            one, d1 = model.infer_batch([cases[b][0]], [cases[b][1]], [speeds[b]], return_durations=True)
+            assert np.array_equal(d1[0], durs[b])
+            assert np.array_equal(one[0], outs[b]), f"item {b}: batched result differs from the B=1 call"
+    finally:
+        model.set_option("precision", 0)
