@@ -83,6 +83,31 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
 /* Returns an audio buffer obtained from kkx_infer / kkx_infer_batch to the library. */
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
 
+/* ---- "next" rows of the hot-path scope: the host work either side of the call.
+ *
+ * kkx_load_voices replaces TTSKoko::load_voices (koko.rs:1308-1334): uploads the voice table once,
+ *   table [n_voices][511][256] f32 (row = un-padded token count, koko.rs:1262).
+ * kkx_infer_batch_voices replaces TTSKoko::mix_styles + OrtKoko::infer (koko.rs:1161-1180, 1255-1306): like
+ *   kkx_infer_batch, but the style of item b is mixed ON THE DEVICE from the table:
+ *     style_b[j] = sum over i in [mix_offsets[b], mix_offsets[b+1]) of table[voice_ids[i]][style_rows[b]][j] * voice_portions[i]
+ *   in that order with separate multiply and add, i.e. bit-identical to the reference loop (koko.rs:1296-1302).
+ *   A single voice ("af_sky") is one entry with portion 1.0; a mix "af_sky.4+af_nicole.5" is two entries with
+ *   portions 0.4, 0.5 (portion = weight * 0.1, NOT renormalised, koko.rs:1283). */
+KKX_API int kkx_load_voices(kkx_ctx* ctx, const float* table, int32_t n_voices);
+KKX_API int kkx_infer_batch_voices(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                           const int32_t* mix_offsets, const int32_t* voice_ids, const float* voice_portions,
+                           const int32_t* style_rows, const float* speeds, float** out_audio,
+                           int64_t* out_sample_offsets, int32_t* out_pred_dur);
+
+/* kkx_infer_batch_pcm16: like kkx_infer_batch, but the waveform comes back as 16-bit PCM,
+ *   pcm = trunc(clamp(s, -1, 1) * 32767) -- the f32 -> i16 conversion of the reference's WebSocket server
+ *   (kokorox-websocket/src/lib.rs:699-703) fused into the iSTFT kernel; half the device->host bytes.
+ *   Release the buffer with kkx_release_pcm16. */
+KKX_API int kkx_infer_batch_pcm16(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                          const float* styles, const float* speeds, int16_t** out_pcm,
+                          int64_t* out_sample_offsets, int32_t* out_pred_dur);
+KKX_API void kkx_release_pcm16(kkx_ctx* ctx, int16_t* pcm);
+
 /* ---- device-resident variant (bench.py `value`: inputs already in HBM, output stays in HBM).
  * Stages the batch on the device once; kkx_run_staged() then runs the whole forward with no
  * host<->device payload traffic (only the per-item frame counts cross, 4 bytes per item).

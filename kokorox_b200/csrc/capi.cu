@@ -89,6 +89,8 @@ static int check_ctx(kkx_ctx* ctx) {
   return KKX_OK;
 }
 
+KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
 KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
                     const float* styles, const float* speeds, float** out_audio,
                     int64_t* out_sample_offsets, int32_t* out_pred_dur) {
@@ -121,6 +123,82 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
     *out_audio = host;
   });
 }
+
+// shared tail of the infer entry points: run the staged batch and hand out a pooled pinned buffer
+static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
+  float* host = nullptr;
+  size_t cap = 0;
+  for (size_t i = 0; i < ctx->pinned_free.size(); i++)
+    if (ctx->pinned_free[i].second >= need_floats) {
+      host = ctx->pinned_free[i].first; cap = ctx->pinned_free[i].second;
+      ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
+      break;
+    }
+  if (!host) {
+    cap = std::max<size_t>(need_floats + need_floats / 8, 1024);
+    KKX_CUDA(cudaMallocHost(&host, cap * sizeof(float)));
+  }
+  *cap_out = cap;
+  return host;
+}
+
+KKX_API int kkx_load_voices(kkx_ctx* ctx, const float* table, int32_t n_voices) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded(ctx, [&] { ctx->model->load_voices(table, n_voices); });
+}
+
+KKX_API int kkx_infer_batch_voices(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                           const int32_t* mix_offsets, const int32_t* voice_ids, const float* voice_portions,
+                           const int32_t* style_rows, const float* speeds, float** out_audio,
+                           int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (out_audio) *out_audio = nullptr;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded(ctx, [&] {
+    if (!out_audio) throw ArgError("out_audio is null");
+    Model& m = *ctx->model;
+    m.stage_voices(batch, tokens, tok_offsets, mix_offsets, voice_ids, voice_portions, style_rows, speeds);
+    m.run();
+    const long long n = m.total_samples();
+    size_t cap = 0;
+    float* host = take_pinned(ctx, (size_t)n, &cap);
+    try {
+      m.fetch(host, n, out_sample_offsets, out_pred_dur);
+    } catch (...) { cudaFreeHost(host); throw; }
+    ctx->pinned[host] = cap;
+    *out_audio = host;
+  });
+}
+
+KKX_API int kkx_infer_batch_pcm16(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                          const float* styles, const float* speeds, int16_t** out_pcm,
+                          int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (out_pcm) *out_pcm = nullptr;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded(ctx, [&] {
+    if (!out_pcm) throw ArgError("out_pcm is null");
+    Model& m = *ctx->model;
+    m.stage(batch, tokens, tok_offsets, styles, speeds);
+    m.set_pcm16(true);
+    try { m.run(); } catch (...) { m.set_pcm16(false); throw; }
+    m.set_pcm16(false);
+    const long long n = m.total_samples();
+    size_t cap = 0;
+    float* host = take_pinned(ctx, (size_t)(n + 1) / 2, &cap);   // n int16 = n/2 floats of the same pool
+    try {
+      m.fetch_pcm16(reinterpret_cast<short*>(host), n, out_sample_offsets, out_pred_dur);
+    } catch (...) { cudaFreeHost(host); throw; }
+    ctx->pinned[host] = cap;
+    *out_pcm = reinterpret_cast<int16_t*>(host);
+  });
+}
+
+KKX_API void kkx_release_pcm16(kkx_ctx* ctx, int16_t* pcm) { kkx_release(ctx, reinterpret_cast<float*>(pcm)); }
 
 KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {

@@ -560,7 +560,7 @@ void launch_stft(const float* x, const long long* s_off, float* har, int ldh, co
 // stored coalesced.  Output sample n (after the n_fft/2 trim) sits at untrimmed position n+10.
 __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int ldc,
                                                     const int* h_off, const int* h_len,
-                                                    float* audio, const long long* s_off) {
+                                                    float* audio, const long long* s_off, short* pcm) {
   constexpr int FR = 128, HALO = 3, NF = FR + HALO + 2;
   __shared__ float spec[NF][22];           // (re, im) of the 11 bins of frames f0-3 .. f0+129
   __shared__ float fr[NF][20];             // windowed time frames
@@ -623,16 +623,40 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
       acc += fr[f - (f0 - HALO)][j];
       env += s_win[j] * s_win[j];
     }
-    audio[s_off[b] + n] = acc / env;
+    const float smp = acc / env;
+    audio[s_off[b] + n] = smp;
+    // optional 16-bit PCM: trunc(clamp(s, -1, 1) * 32767), the f32 -> i16 conversion of the reference's WebSocket
+    // server (kokorox-websocket/src/lib.rs:699-703; Rust `as i16` truncates toward zero, NaN -> 0)
+    if (pcm) pcm[s_off[b] + n] = (short)__float2int_rz(fminf(fmaxf(smp, -1.0f), 1.0f) * 32767.0f);
   }
 }
-void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio,
+void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio, short* pcm,
                   const long long* s_off, int B, int max_len, cudaStream_t st) {
   if (g_dry_run) return;
   ensure_tables();
   dim3 g((max_len + 127) / 128, B);
-  istft_kernel<<<g, 256, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off);
+  istft_kernel<<<g, 256, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off, pcm);
   post_launch("istft", st);
+}
+
+// ------------------------------------------------------------------------------------------
+// TTSKoko::mix_styles on the device (koko.rs:1255-1306): style_b[j] = sum_i table[voice_i][row_b][j] * portion_i,
+// accumulated in the reference's order with separate multiply and add (no FMA contraction), so the result is
+// bit-identical to the Rust loop; a single voice is portion 1.0 and therefore an exact copy.
+__global__ void __launch_bounds__(256) mix_styles_kernel(const float* __restrict__ table, const int* mix_off,
+                                                         const int* voice_ids, const float* portions,
+                                                         const int* rows, float* styles) {
+  const int b = blockIdx.x, j = threadIdx.x;
+  float acc = 0.0f;
+  for (int i = mix_off[b]; i < mix_off[b + 1]; i++)
+    acc = __fadd_rn(acc, __fmul_rn(table[((size_t)voice_ids[i] * 511 + rows[b]) * 256 + j], portions[i]));
+  styles[(size_t)b * 256 + j] = acc;
+}
+void launch_mix_styles(const float* table, const int* mix_off, const int* voice_ids, const float* portions,
+                       const int* rows, float* styles, int B, cudaStream_t st) {
+  if (g_dry_run) return;
+  mix_styles_kernel<<<B, 256, 0, st>>>(table, mix_off, voice_ids, portions, rows, styles);
+  post_launch("mix_styles", st);
 }
 
 }  // namespace kkx

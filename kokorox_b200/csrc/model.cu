@@ -86,6 +86,8 @@ Model::~Model() {
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : owned_) cudaFree(p);
   if (d_audio_) cudaFree(d_audio_);
+  if (d_pcm_) cudaFree(d_pcm_);
+  if (d_voices_) cudaFree(d_voices_);
   if (d_noise_) cudaFree(d_noise_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -493,7 +495,7 @@ void Model::set_inject(const std::string& name, const void* data, long long coun
 void Model::stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
                   const float* speeds) {
   if (B <= 0) throw ArgError("batch must be >= 1");
-  if (!tokens || !tok_offsets || !styles || !speeds) throw ArgError("null input pointer");
+  if (!tokens || !tok_offsets || !speeds) throw ArgError("null input pointer");   // styles == nullptr: filled by stage_voices
   KKX_CUDA(cudaSetDevice(device_));
   std::vector<int> lens(B);
   for (int b = 0; b < B; b++) {
@@ -517,11 +519,58 @@ void Model::stage(int B, const int64_t* tokens, const int32_t* tok_offsets, cons
   d_styles_ = ioA_.alloc<float>((size_t)B * 256);
   d_speeds_ = ioA_.alloc<float>(B);
   KKX_CUDA(cudaMemcpyAsync(d_ids_, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaMemcpyAsync(d_styles_, styles, (size_t)B * 256 * sizeof(float), cudaMemcpyHostToDevice, stream_));
+  if (styles) KKX_CUDA(cudaMemcpyAsync(d_styles_, styles, (size_t)B * 256 * sizeof(float), cudaMemcpyHostToDevice, stream_));
   KKX_CUDA(cudaMemcpyAsync(d_speeds_, speeds, B * sizeof(float), cudaMemcpyHostToDevice, stream_));
   KKX_CUDA(cudaStreamSynchronize(stream_));
   B_ = B;
   tok_len_ = lens;
+}
+
+void Model::load_voices(const float* table, int n_voices) {
+  if (!table || n_voices < 1) throw ArgError("load_voices: null table or n_voices < 1");
+  KKX_CUDA(cudaSetDevice(device_));
+  KKX_CUDA(cudaStreamSynchronize(stream_));
+  if (d_voices_) { cudaFree(d_voices_); d_voices_ = nullptr; n_voices_ = 0; }
+  const size_t bytes = (size_t)n_voices * 511 * 256 * sizeof(float);
+  KKX_CUDA(cudaMalloc(&d_voices_, bytes));
+  KKX_CUDA(cudaMemcpy(d_voices_, table, bytes, cudaMemcpyHostToDevice));
+  n_voices_ = n_voices;
+}
+
+void Model::stage_voices(int B, const int64_t* tokens, const int32_t* tok_offsets, const int32_t* mix_offsets,
+                         const int32_t* voice_ids, const float* portions, const int32_t* style_rows,
+                         const float* speeds) {
+  if (!d_voices_) throw ArgError("no voice table loaded (kkx_load_voices)");
+  if (B <= 0 || !mix_offsets || !voice_ids || !portions || !style_rows) throw ArgError("null input pointer");
+  for (int b = 0; b < B; b++) {
+    if (mix_offsets[b + 1] <= mix_offsets[b]) throw ArgError("every item needs at least one voice");
+    if (style_rows[b] < 0 || style_rows[b] > 510) throw ArgError("style row must be in 0..510 (koko.rs:1262 indexes a 511-row table)");
+    for (int i = mix_offsets[b]; i < mix_offsets[b + 1]; i++)
+      if (voice_ids[i] < 0 || voice_ids[i] >= n_voices_) throw ArgError("voice id out of range");
+  }
+  stage(B, tokens, tok_offsets, nullptr, speeds);
+  const int nmix = mix_offsets[B];
+  int* d_mo = ioA_.alloc<int>(B + 1);
+  int* d_vi = ioA_.alloc<int>(nmix);
+  float* d_po = ioA_.alloc<float>(nmix);
+  int* d_rows = ioA_.alloc<int>(B);
+  KKX_CUDA(cudaMemcpyAsync(d_mo, mix_offsets, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(d_vi, voice_ids, nmix * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(d_po, portions, nmix * sizeof(float), cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(d_rows, style_rows, B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  g_launch_stats = nullptr;
+  launch_mix_styles(d_voices_, d_mo, d_vi, d_po, d_rows, d_styles_, B, stream_);
+  KKX_CUDA(cudaStreamSynchronize(stream_));   // the index arrays are the caller's
+}
+
+void Model::fetch_pcm16(short* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur) {
+  if (!d_pcm_ || !pcm_valid_) throw ArgError("the last run did not produce 16-bit PCM");
+  fetch(nullptr, 0, sample_offsets, pred_dur);
+  if (dst) {
+    if (capacity < total_samples_) throw ArgError("pcm buffer too small");
+    KKX_CUDA(cudaMemcpyAsync(dst, d_pcm_, total_samples_ * sizeof(short), cudaMemcpyDeviceToHost, stream_));
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+  }
 }
 
 void Model::fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur) {
@@ -569,6 +618,13 @@ void Model::run() {
     audio_cap_ = (size_t)total_samples_ + (size_t)total_samples_ / 4;
     KKX_CUDA(cudaMalloc(&d_audio_, audio_cap_ * sizeof(float)));
   }
+  if (want_pcm_ && (size_t)total_samples_ > pcm_cap_) {
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    if (d_pcm_) cudaFree(d_pcm_);
+    pcm_cap_ = (size_t)total_samples_ + (size_t)total_samples_ / 4;
+    KKX_CUDA(cudaMalloc(&d_pcm_, pcm_cap_ * sizeof(short)));
+  }
+  pcm_valid_ = want_pcm_;
   int b0 = 0;
   while (b0 < B_) {
     int b1 = b0; long long fr = 0;

@@ -109,6 +109,12 @@ class Model {
   // Stage inputs on the device (H2D), run the forward pass, fetch results (D2H).
   void stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
              const float* speeds);
+  // styles taken from the device-resident voice table (load_voices) instead of host vectors
+  void load_voices(const float* table, int n_voices);
+  void stage_voices(int B, const int64_t* tokens, const int32_t* tok_offsets, const int32_t* mix_offsets,
+                    const int32_t* voice_ids, const float* portions, const int32_t* style_rows, const float* speeds);
+  void set_pcm16(bool on) { want_pcm_ = on; }
+  void fetch_pcm16(short* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
   void run();
   long long total_samples() const { return total_samples_; }
   void fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
@@ -180,6 +186,8 @@ class Model {
   Level tokL_;
   // outputs
   float* d_audio_ = nullptr; size_t audio_cap_ = 0;
+  short* d_pcm_ = nullptr; size_t pcm_cap_ = 0; bool want_pcm_ = false, pcm_valid_ = false;   // optional 16-bit PCM twin of d_audio_
+  float* d_voices_ = nullptr; int n_voices_ = 0;                           // [V][511][256] voice table
   std::vector<long long> sample_off_;
   std::vector<int> pred_dur_h_;
   long long total_samples_ = 0;

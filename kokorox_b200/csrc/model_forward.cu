@@ -651,7 +651,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     launch_conv_f32(c, st);
   }
   capture("conv_post", cp, 24, 0, 22, G120, b0);
-  launch_istft(cp, 24, G120.d_off, G120.d_len, d_audio_, d_s_glob, B, G120.max_len, st);
+  launch_istft(cp, 24, G120.d_off, G120.d_len, d_audio_, want_pcm_ ? d_pcm_ : nullptr, d_s_glob, B, G120.max_len, st);
 }
 
 }  // namespace kkx

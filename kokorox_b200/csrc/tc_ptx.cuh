@@ -19,10 +19,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend-time hint: the warp sleeps in
+      "@p bra DONE_%=;\n\t"                                            // hardware instead of spinning on issue slots
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(

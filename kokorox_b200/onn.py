@@ -60,6 +60,13 @@ def load_library(path: Optional[str] = None):
         lib.kkx_infer_batch.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32), P(P(f32)), P(i64), P(i32)]
         lib.kkx_release.argtypes = [vp, P(f32)]
         lib.kkx_release.restype = None
+        i16 = C.c_int16
+        lib.kkx_load_voices.argtypes = [vp, P(f32), i32]
+        lib.kkx_infer_batch_voices.argtypes = [vp, i32, P(i64), P(i32), P(i32), P(i32), P(f32), P(i32), P(f32),
+                                               P(P(f32)), P(i64), P(i32)]
+        lib.kkx_infer_batch_pcm16.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32), P(P(i16)), P(i64), P(i32)]
+        lib.kkx_release_pcm16.argtypes = [vp, P(i16)]
+        lib.kkx_release_pcm16.restype = None
         lib.kkx_stage_batch.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32)]
         lib.kkx_run_staged.argtypes = [vp, P(i64), P(i64)]
         lib.kkx_fetch_staged.argtypes = [vp, P(f32), i64, P(i64), P(i32)]
@@ -196,6 +203,119 @@ class B200Koko:
         del base
         if return_durations:
             return outs, [dur[int(offs[b]):int(offs[b + 1])].copy() for b in range(B)]
+        return outs
+
+    # -- "next" rows: voice table + mix_styles on the device, 16-bit PCM output ------------
+    def load_voices(self, voices) -> None:
+        """TTSKoko::load_voices (koko.rs:1308-1334): ``voices`` maps name -> array [511,1,256] (or [511,256]);
+        the table is uploaded once and addressed by name afterwards."""
+        self._require()
+        names = sorted(voices)
+        table = np.zeros((len(names), 511, 256), dtype=np.float32)
+        for i, n in enumerate(names):
+            v = np.asarray(voices[n], dtype=np.float32).reshape(-1, 256)
+            table[i, :min(511, v.shape[0])] = v[:511]      # koko.rs:1315-1321 copies into a fixed 511-row tensor
+        self._check(self._lib.kkx_load_voices(self._ctx, _fp(table), len(names)))
+        self._voice_ids = {n: i for i, n in enumerate(names)}
+        self._voice_table = table
+
+    def _parse_style(self, style_name: str):
+        """The parsing half of TTSKoko::mix_styles (koko.rs:1255-1306): -> ([voice ids], [f32 portions])."""
+        ids = getattr(self, "_voice_ids", None)
+        if ids is None:
+            raise KkxError(-5, "no voices loaded")
+        if "+" not in style_name:
+            if style_name not in ids:
+                raise KkxError(-1, f"can not found from styles_map: {style_name}")
+            return [ids[style_name]], [np.float32(1.0)]
+        vs, ps = [], []
+        for part in style_name.split("+"):
+            if "." in part:
+                name, portion = part.split(".", 1)
+                try:
+                    w = np.float32(float(portion))
+                except ValueError:
+                    continue
+                if name not in ids:
+                    raise KkxError(-1, f"Voice '{name}' not found in available voices")
+                vs.append(ids[name])
+                ps.append(np.float32(w * np.float32(0.1)))
+        if not vs:
+            raise KkxError(-1, f"Invalid voice mix format '{style_name}'. Use format: voice1.weight+voice2.weight "
+                               "(e.g., jf_alpha.4+am_echo.6)")
+        return vs, ps
+
+    def mix_styles(self, style_name: str, tokens_len: int) -> np.ndarray:
+        """Host mirror of TTSKoko::mix_styles (same f32 arithmetic and order) -> [1,256]; the device path of
+        ``infer_batch_voices`` must agree with it bit for bit."""
+        vs, ps = self._parse_style(style_name)
+        if "+" not in style_name:
+            return self._voice_table[vs[0], tokens_len][None, :].copy()
+        out = np.zeros(256, dtype=np.float32)
+        for v, p in zip(vs, ps):
+            out = (out + self._voice_table[v, tokens_len] * p).astype(np.float32)
+        return out[None, :]
+
+    def infer_batch_voices(self, tokens: Sequence[Sequence[int]], style_names: Sequence[str],
+                           speeds: Sequence[float], return_durations: bool = False):
+        """koko.rs:1161-1180 for a ragged batch: item b uses voice / mix ``style_names[b]`` at table row
+        ``len(tokens[b]) - 2`` (the un-padded token count); styles are mixed on the device."""
+        self._require()
+        B = len(tokens)
+        lens = [len(t) for t in tokens]
+        offs = np.zeros(B + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(lens)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tokens]))
+        moff = np.zeros(B + 1, dtype=np.int32)
+        vids, pors = [], []
+        for b, name in enumerate(style_names):
+            v, p = self._parse_style(name)
+            vids += v
+            pors += p
+            moff[b + 1] = len(vids)
+        vids = np.asarray(vids, dtype=np.int32)
+        pors = np.asarray(pors, dtype=np.float32)
+        rows = np.asarray([n - 2 for n in lens], dtype=np.int32)
+        sp = np.ascontiguousarray(np.asarray(speeds, dtype=np.float32).reshape(B))
+        audio = C.POINTER(C.c_float)()
+        soff = np.zeros(B + 1, dtype=np.int64)
+        dur = np.zeros(int(offs[-1]), dtype=np.int32)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        self._check(self._lib.kkx_infer_batch_voices(
+            self._ctx, B, flat.ctypes.data_as(C.POINTER(C.c_int64)), ip(offs), ip(moff), ip(vids), _fp(pors),
+            ip(rows), _fp(sp), C.byref(audio), soff.ctypes.data_as(C.POINTER(C.c_int64)), ip(dur)))
+        total = int(soff[-1])
+        base = np.ctypeslib.as_array(audio, shape=(max(total, 1),))
+        self._outstanding += 1
+        weakref.finalize(base, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
+        outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
+        del base
+        if return_durations:
+            return outs, [dur[int(offs[b]):int(offs[b + 1])].copy() for b in range(B)]
+        return outs
+
+    def infer_batch_pcm16(self, tokens: Sequence[Sequence[int]], styles, speeds: Sequence[float]):
+        """Like infer_batch, but returns int16 PCM (trunc(clamp(s,-1,1)*32767), kokorox-websocket lib.rs:699-703),
+        converted inside the iSTFT kernel; the device->host copy is half the size."""
+        self._require()
+        B = len(tokens)
+        lens = [len(t) for t in tokens]
+        offs = np.zeros(B + 1, dtype=np.int32)
+        offs[1:] = np.cumsum(lens)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tokens]))
+        st = np.ascontiguousarray(np.asarray(styles, dtype=np.float32).reshape(B, 256))
+        sp = np.ascontiguousarray(np.asarray(speeds, dtype=np.float32).reshape(B))
+        pcm = C.POINTER(C.c_int16)()
+        soff = np.zeros(B + 1, dtype=np.int64)
+        self._check(self._lib.kkx_infer_batch_pcm16(
+            self._ctx, B, flat.ctypes.data_as(C.POINTER(C.c_int64)), offs.ctypes.data_as(C.POINTER(C.c_int32)),
+            _fp(st), _fp(sp), C.byref(pcm), soff.ctypes.data_as(C.POINTER(C.c_int64)), None))
+        total = int(soff[-1])
+        base = np.ctypeslib.as_array(pcm, shape=(max(total, 1),))
+        self._outstanding += 1
+        weakref.finalize(base, B200Koko._release_buffer, self, C.cast(pcm, C.c_void_p).value)
+        outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
+        del base
         return outs
 
     # -- device-resident path (bench `value`) ---------------------------------------------

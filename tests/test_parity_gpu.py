@@ -243,3 +243,52 @@ def test_many_short_requests_bf16(model):
             assert np.array_equal(one[0], outs[b]), f"item {b}: batched result differs from the B=1 call"
     finally:
         model.set_option("precision", 0)
+
+
+# ---------------------------------------------------------------------------- "next" rows
+def _voices(n=5, seed=77):
+    rng = np.random.default_rng(seed)
+    names = ["af_sky", "af_nicole", "am_echo", "jf_alpha", "zf_xiaoxiao"][:n]
+    return {nm: (rng.standard_normal((511, 1, 256)) * 0.15).astype(np.float32) for nm in names}
+
+
+def test_device_voice_table_and_mix_styles(model):
+    # TTSKoko::load_voices + mix_styles (koko.rs:1255-1334) on the device: the device-mixed style must equal the
+    # reference loop (f32, un-normalised portions = weight * 0.1, row = un-padded token count) bit for bit, so the
+    # audio equals the host-mixed call exactly.
+    from kokorox_b200.onn import KkxError
+    model.load_voices(_voices())
+    toks = [synth_case(n, 900 + n, 1)[0] for n in (30, 77, 12)]
+    names = ["af_sky", "af_sky.4+af_nicole.5", "jf_alpha.3+am_echo.3+zf_xiaoxiao.4"]
+    speeds = [1.0, 0.9, 1.1]
+    model.set_noise(None)
+    host_styles = [model.mix_styles(nm, len(t) - 2)[0] for nm, t in zip(names, toks)]
+    # the reference arithmetic, spelled out for the two-voice mix (koko.rs:1296-1302)
+    tab = model._voice_table
+    ids = model._voice_ids
+    row = len(toks[1]) - 2
+    want = np.zeros(256, np.float32)
+    want = want + tab[ids["af_sky"], row] * np.float32(np.float32(4.0) * np.float32(0.1))
+    want = want + tab[ids["af_nicole"], row] * np.float32(np.float32(5.0) * np.float32(0.1))
+    assert np.array_equal(want.astype(np.float32), host_styles[1])
+    ref, rd = model.infer_batch(toks, host_styles, speeds, return_durations=True)
+    got, gd = model.infer_batch_voices(toks, names, speeds, return_durations=True)
+    for b in range(3):
+        assert np.array_equal(rd[b], gd[b])
+        assert np.array_equal(ref[b], got[b]), f"item {b}: device-mixed style differs from the host-mixed one"
+    with pytest.raises(KkxError):
+        model.infer_batch_voices(toks[:1], ["no_such_voice"], [1.0])
+    with pytest.raises(KkxError):
+        model.infer_batch_voices(toks[:1], ["af_sky.x"], [1.0])
+
+
+def test_pcm16_output_fused_into_istft(model):
+    # f32 -> i16 like kokorox-websocket/src/lib.rs:699-703: (s.clamp(-1, 1) * 32767) as i16 (truncation)
+    cases = [synth_case(n, 40 + n, 41 + n) for n in (25, 140)]
+    model.set_noise(None)
+    f = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], [1.0, 1.2])
+    p = model.infer_batch_pcm16([c[0] for c in cases], [c[1] for c in cases], [1.0, 1.2])
+    for a, b in zip(f, p):
+        assert b.dtype == np.int16 and len(a) == len(b)
+        want = np.trunc(np.clip(a, -1.0, 1.0).astype(np.float32) * np.float32(32767.0)).astype(np.int16)
+        assert np.array_equal(want, b)
