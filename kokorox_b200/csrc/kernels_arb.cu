@@ -43,8 +43,6 @@ namespace {
 #endif
 
 constexpr int kArbThreads = 512;   // 16 warps: TMA, MMA, 8 epilogue, 6 operand producers (128 regs/thread)
-constexpr int kProdThreads = 192;
-constexpr int kProdRows = kProdThreads / 8;   // rows per producer pass
 constexpr int kArbMaxB = 512;
 
 // T ("transposed", C = 128 only): the WEIGHT tile is the M operand (128 output channels) and the 256
@@ -109,6 +107,14 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   // of tile i no longer overlaps the MMAs of tile i+1 (the producers still run ahead) -- measured: not a net win
   // (see arb_variant), kept as an opt-in variant.
   constexpr int NBUF = (T && MSUB == 4) ? 1 : 2;
+  // Warp split between epilogue and operand producers (14 warps besides TMA and MMA): 8 + 6.  A 4 + 10 split for
+  // conv1 in transposed mode (trivial epilogue, producer-bound) was measured: no gain (1.14 / 1.35 / 1.61 ms vs
+  // 1.20 / 1.29 / 1.63 ms at k = 3 / 7 / 11) -- the producers are limited by the shared-memory port they share
+  // with the tensor pipe's operand reads, not by their thread count.
+  constexpr int NEW = 8;                                    // epilogue warps (4 is supported by the transposed epilogue)
+  constexpr int NPW = 14 - NEW;                             // producer warps
+  constexpr int kProdThreads = NPW * 32;
+  constexpr int kProdRows = kProdThreads / 8;               // rows per producer pass (24 or 40: multiples of 8)
   using Cfg = ArbCfg<BN, MSUB, T>;
   constexpr int KCH = Cfg::KCH, NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   constexpr int MT = MSUB * 128;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < NA; s++) { mbar_init(fullA(s), kProdThreads / 32); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < NB; s++) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int j = 0; j < 2; j++) { mbar_init(tfull(j), 1); mbar_init(tempty(j), 8); }
+    for (int j = 0; j < 2; j++) { mbar_init(tfull(j), 1); mbar_init(tempty(j), NEW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -255,12 +261,12 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       }
       TIM_FLUSH(4, 4);
     }
-  } else if (T && warp < 10) {
+  } else if (T && warp < 2 + NEW) {
     // ------------------------------------------------------------------ epilogue, transposed accumulator
     // warp: 32 channels (TMEM lane quadrant q) x 128 rows (row half eg); thread: one channel.  Register j of
     // a 32-column tcgen05.ld is row j of the chunk, so a warp-wide access to row j covers 32 consecutive
     // channels = 128 contiguous bytes.  No smem, no barrier; statistics are per-thread sums.
-    const int eg = (warp - 2) >> 2;
+    const int eg = (warp - 2) >> 2;          // row group (NEW / 4 groups share the tile's rows)
     const int q = warp & 3;
     const int co = q * 32 + lane;
     const float bias_c = a.bias[co];
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     const float2 os2 = make_float2(a.oscale, a.oscale);
     const bool accum = a.accumulate != 0;
     // residual rows are prefetched two 32-row chunks ahead (two register buffers), across tile boundaries
-    constexpr int RW = MSUB * 64;            // rows per epilogue warp (row half eg of the tile)
+    constexpr int RW = MSUB * 128 / (NEW / 4);   // rows per epilogue warp (row group eg of the tile)
     constexpr int NCHK = RW / 32;            // 32-row chunks per warp and tile (4 or 8)
     auto fetchT = [&](int L, int off, int m0, int ch, float (&rv)[32]) {
       if (!CONV2) return;
@@ -375,7 +381,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       TICK(7);
     }
     TIM_FLUSH(8, 9);
-  } else if (warp < 10) {
+  } else if (!T && warp < 10) {
     // ------------------------------------------------------------------ epilogue (2 groups of 4 warps)
     // group eg owns the 32-column chunks of parity eg; inside a group, thread `et` drops its accumulator
     // row into padded smem, then thread t handles columns c4..c4+3 of rows (t>>3) + 16*i (full 128-byte
@@ -543,11 +549,11 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     // y = snake(x*sc + sh) = ial * (u + sin(u)^2), u = x*(al*sc) + al*sh: three per-channel coefficients,
     // cached in smem per item.  Loads run one group (4 passes of 24 rows) ahead of the transform through
     // two register buffers, across chunk and tile boundaries, so HBM/L2 latency stays hidden.
-    const int pt = threadIdx.x - 320;       // 0..191
+    const int pt = threadIdx.x - (2 + NEW) * 32;   // 0..kProdThreads-1
     const int cg = pt & 7;                  // 8-channel group inside the 64-channel chunk
     const int rl = pt >> 3;                 // row lane 0..23
     constexpr int GP = 4;
-    constexpr int GR = GP * kProdRows;      // rows per load group (96: a multiple of 8 -> constant swizzle phase)
+    constexpr int GR = GP * kProdRows;      // rows per load group (96 or 160: multiples of 8 -> constant swizzle phase)
     const int ra_used = MT + 2 * pad;       // <= Cfg::RA
     const int ngc = (ra_used + GR - 1) / GR;                 // load groups per chunk
     float* const coef = reinterpret_cast<float*>(gbase + (coef_base - base));   // [3][BN]: al*sc, al*sh, 1/al
@@ -588,12 +594,12 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       const int sa = gA % NA;
       if (s_g == 0) {
         if (b != coef_b) {   // new item: rebuild the coefficient table (all producer threads take this branch together)
-          asm volatile("bar.sync 3, 192;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");
           for (int ch = pt; ch < BN; ch += kProdThreads) {
             const float al = a.alpha[ch], s = a.scale[(size_t)b * BN + ch], h = a.shift[(size_t)b * BN + ch];
             coef[ch] = al * s; coef[BN + ch] = al * h; coef[2 * BN + ch] = 1.0f / al;
           }
-          asm volatile("bar.sync 3, 192;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");
           coef_b = b;
         }
         const float* cp = coef + s_c * 64 + cg * 8;
