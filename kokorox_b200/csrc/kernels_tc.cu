@@ -1019,7 +1019,7 @@ __global__ void __launch_bounds__(256) apply_tf32_kernel(const float* __restrict
                                                          const float* scale, const float* shift,
                                                          int act, float slope, float* out_hi, float* out_lo,
                                                          int Cpad, int rows_total, const int* off,
-                                                         const int* len) {
+                                                         const int* len, int vec_ok) {
   const int b = blockIdx.y;
   const int L = len[b], o = off[b];
   const int r_begin = o - kGapRows;
@@ -1029,19 +1029,36 @@ __global__ void __launch_bounds__(256) apply_tf32_kernel(const float* __restrict
   const int re = min(r_end, rb + kApplyRows);
   const float* sc = scale ? scale + (size_t)b * C : nullptr;
   const float* sh = shift ? shift + (size_t)b * C : nullptr;
-  const int total = (re - rb) * Cpad;
+  // one column quad per thread: float4 load, two float4 stores (the kernel is a pure HBM stream:
+  // 4 B read + 8 B written per element)
+  const int cq = Cpad >> 2;
+  const int total = (re - rb) * cq;
   for (int i = threadIdx.x; i < total; i += 256) {
-    const int r = rb + i / Cpad;
-    const int c = i % Cpad;
-    float v = 0.f;
+    const int r = rb + i / cq;
+    const int c = (i % cq) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (r >= o && r < o + L && c < C) {
-      v = x[(size_t)r * ldx + c];
-      if (sc) v = v * sc[c] + sh[c];            // same arithmetic as the fp32 SIMT prologue
-      if (act == ACT_LRELU) v = v > 0.f ? v : v * slope;
+      const float* xp = x + (size_t)r * ldx + c;
+      if (vec_ok && c + 3 < C) {
+        const float4 t = *reinterpret_cast<const float4*>(xp);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (c + e < C) v[e] = xp[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (c + e < C) {
+          if (sc) v[e] = v[e] * sc[c + e] + sh[c + e];            // same arithmetic as the fp32 SIMT prologue
+          if (act == ACT_LRELU) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+        } else v[e] = 0.f;
+      }
     }
-    const float hi = to_tf32(v);
-    out_hi[(size_t)r * Cpad + c] = hi;
-    out_lo[(size_t)r * Cpad + c] = to_tf32(v - hi);
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) { hi[e] = to_tf32(v[e]); lo[e] = to_tf32(v[e] - hi[e]); }
+    *reinterpret_cast<float4*>(out_hi + (size_t)r * Cpad + c) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(out_lo + (size_t)r * Cpad + c) = make_float4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
@@ -1050,7 +1067,8 @@ void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const
   if (g_dry_run) return;
   const int rows = max_len + 2 * kGapRows + 8;
   dim3 g((rows + kApplyRows - 1) / kApplyRows, B);
-  apply_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, out_hi, out_lo, Cpad, rows_total, off, len);
+  const int vec_ok = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  apply_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, out_hi, out_lo, Cpad, rows_total, off, len, vec_ok);
   post_launch("apply_tf32", st);
 }
 
