@@ -459,18 +459,31 @@ __global__ void __launch_bounds__(NW * 32) attention_tc_kernel(const float* __re
   for (int n = 0; n < 8; n++) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int k0 = 0; k0 < N; k0 += 64) {
-    __syncthreads();
-    // stage K and V tiles as hi/lo planes (float4 global loads, 16 rows x 8 column quads per pass)
-    for (int i = tid; i < 64 * 16; i += NW * 32) {
+  // K/V tiles are fetched one tile ahead into registers (the loads fly during the MMAs of the current tile),
+  // then split into tf32 hi/lo planes and stored to smem
+  constexpr int NLD = 1024 / (NW * 32);        // float4 per thread, matrix and tile
+  float4 kreg[NLD], vreg[NLD];
+  auto prefetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < NLD; u++) {
+      const int i = tid + u * (NW * 32);
       const int j = i >> 4, c4 = (i & 15) << 2;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      kreg[u] = make_float4(0.f, 0.f, 0.f, 0.f); vreg[u] = kreg[u];
       if (k0 + j < N) {
         const float* rp = qkv + (base + k0 + j) * 2304 + h * 64 + c4;
-        kv = *reinterpret_cast<const float4*>(rp + 768);
-        vv = *reinterpret_cast<const float4*>(rp + 1536);
+        kreg[u] = *reinterpret_cast<const float4*>(rp + 768);
+        vreg[u] = *reinterpret_cast<const float4*>(rp + 1536);
       }
-      const float kx[4] = {kv.x, kv.y, kv.z, kv.w}, vx[4] = {vv.x, vv.y, vv.z, vv.w};
+    }
+  };
+  prefetch(0);
+  for (int k0 = 0; k0 < N; k0 += 64) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < NLD; u++) {
+      const int i = tid + u * (NW * 32);
+      const int j = i >> 4, c4 = (i & 15) << 2;
+      const float kx[4] = {kreg[u].x, kreg[u].y, kreg[u].z, kreg[u].w}, vx[4] = {vreg[u].x, vreg[u].y, vreg[u].z, vreg[u].w};
       uint32_t a[4], bq[4], c[4], dq[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
@@ -483,6 +496,7 @@ __global__ void __launch_bounds__(NW * 32) attention_tc_kernel(const float* __re
       *reinterpret_cast<uint4*>(Vl + j * kAttLd + c4) = make_uint4(dq[0], dq[1], dq[2], dq[3]);
     }
     __syncthreads();
+    if (k0 + 64 < N) prefetch(k0 + 64);
 
     // S = Q K^T for 16 rows x 64 keys
     float sc[8][4];
