@@ -89,41 +89,6 @@ static int check_ctx(kkx_ctx* ctx) {
   return KKX_OK;
 }
 
-KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
-
-KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
-                    const float* styles, const float* speeds, float** out_audio,
-                    int64_t* out_sample_offsets, int32_t* out_pred_dur) {
-  int rc = check_ctx(ctx);
-  if (rc) return rc;
-  if (out_audio) *out_audio = nullptr;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  return guarded(ctx, [&] {
-    if (!out_audio) throw ArgError("out_audio is null");
-    Model& m = *ctx->model;
-    m.stage(batch, tokens, tok_offsets, styles, speeds);
-    m.run();
-    float* host = nullptr;
-    const long long n = m.total_samples();
-    size_t cap = 0;
-    for (size_t i = 0; i < ctx->pinned_free.size(); i++)
-      if (ctx->pinned_free[i].second >= (size_t)n) {
-        host = ctx->pinned_free[i].first; cap = ctx->pinned_free[i].second;
-        ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
-        break;
-      }
-    if (!host) {
-      cap = (size_t)std::max<long long>(n + n / 8, 1024);
-      KKX_CUDA(cudaMallocHost(&host, cap * sizeof(float)));
-    }
-    try {
-      m.fetch(host, n, out_sample_offsets, out_pred_dur);
-    } catch (...) { cudaFreeHost(host); throw; }
-    ctx->pinned[host] = cap;
-    *out_audio = host;
-  });
-}
-
 // shared tail of the infer entry points: run the staged batch and hand out a pooled pinned buffer
 static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
   float* host = nullptr;
@@ -140,6 +105,36 @@ static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
   }
   *cap_out = cap;
   return host;
+}
+
+KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
+KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                    const float* styles, const float* speeds, float** out_audio,
+                    int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (out_audio) *out_audio = nullptr;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return guarded(ctx, [&] {
+    if (!out_audio) throw ArgError("out_audio is null");
+    Model& m = *ctx->model;
+    m.stage(batch, tokens, tok_offsets, styles, speeds);
+    // the pinned result buffer is handed to the model as a sink: every frame group's audio is copied out on a
+    // second stream while the next group computes
+    float* host = nullptr;
+    size_t cap = 0;
+    m.host_sink = [&](long long n) { host = take_pinned(ctx, (size_t)n, &cap); return host; };
+    try {
+      m.run();
+      m.host_sink = nullptr;
+      const long long n = m.total_samples();
+      if (!host) host = take_pinned(ctx, (size_t)n, &cap);
+      m.fetch(m.sink_filled() ? nullptr : host, n, out_sample_offsets, out_pred_dur);
+    } catch (...) { m.host_sink = nullptr; if (host) cudaFreeHost(host); throw; }
+    ctx->pinned[host] = cap;
+    *out_audio = host;
+  });
 }
 
 KKX_API int kkx_load_voices(kkx_ctx* ctx, const float* table, int32_t n_voices) {

@@ -73,6 +73,8 @@ Model::Model(const std::string& weights_path, int device) : device_(device) {
   KKX_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   KKX_CUDA(cudaEventCreate(&ev0_));
   KKX_CUDA(cudaEventCreate(&ev1_));
+  KKX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+  KKX_CUDA(cudaEventCreateWithFlags(&ev_grp_, cudaEventDisableTiming));
   const char* dbg = getenv("KKX_DEBUG_SYNC");
   stats.check_each = dbg && dbg[0] == '1';
   const char* det = getenv("KKX_PROFILE_DETAIL");
@@ -91,6 +93,8 @@ Model::~Model() {
   if (d_noise_) cudaFree(d_noise_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
+  if (ev_grp_) cudaEventDestroy(ev_grp_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -625,6 +629,9 @@ void Model::run() {
     KKX_CUDA(cudaMalloc(&d_pcm_, pcm_cap_ * sizeof(short)));
   }
   pcm_valid_ = want_pcm_;
+  sink_filled_ = false;
+  float* sink = (host_sink && !debug_) ? host_sink(total_samples_) : nullptr;
+  // (both streams are idle here: the previous run synchronised them, and d_audio_ was sized above)
   int b0 = 0;
   while (b0 < B_) {
     int b1 = b0; long long fr = 0;
@@ -650,10 +657,18 @@ void Model::run() {
     }
     frA_.reset();
     frame_phase(r, b0, b1, false);
+    if (sink) {   // this group's audio goes to the host while the next group computes
+      const long long s0 = sample_off_[b0], s1 = sample_off_[b1];
+      KKX_CUDA(cudaEventRecord(ev_grp_, stream_));
+      KKX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_grp_, 0));
+      if (s1 > s0)
+        KKX_CUDA(cudaMemcpyAsync(sink + s0, d_audio_ + s0, (size_t)(s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, copy_stream_));
+    }
     b0 = b1;
   }
   KKX_CUDA(cudaEventRecord(ev1_, stream_));
   KKX_CUDA(cudaStreamSynchronize(stream_));
+  if (sink) { KKX_CUDA(cudaStreamSynchronize(copy_stream_)); sink_filled_ = true; }
   arb_timing_dump();
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0_, ev1_);

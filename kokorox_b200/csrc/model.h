@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "kernels.h"
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -115,6 +116,11 @@ class Model {
                     const int32_t* voice_ids, const float* portions, const int32_t* style_rows, const float* speeds);
   void set_pcm16(bool on) { want_pcm_ = on; }
   void fetch_pcm16(short* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
+  // Optional host sink for the waveform: called once the total sample count is known (after the token phase);
+  // returns a pinned buffer of >= n floats.  Each frame group's audio is then copied to it on a second stream as
+  // soon as the group's iSTFT is done, overlapping the device->host copy with the next group's kernels.
+  std::function<float*(long long)> host_sink;
+  bool sink_filled() const { return sink_filled_; }
   void run();
   long long total_samples() const { return total_samples_; }
   void fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
@@ -195,6 +201,7 @@ class Model {
   float* d_noise_ = nullptr; long long noise_n_ = 0;
   std::vector<int> inj_dur_; std::vector<float> inj_f0_, inj_n_;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr; cudaEvent_t ev_grp_ = nullptr; bool sink_filled_ = false;
 };
 
 }  // namespace kkx
