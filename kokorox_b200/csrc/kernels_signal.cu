@@ -91,14 +91,17 @@ void launch_add_rows_stats(const float* a, const float* b, float* out, int C, fl
   post_launch("add_rows_stats", st);
 }
 
-// Combine the chunk partials (fp64, fixed order) -> AdaIN coefficients.  Block = 32 channels x 8
-// chunk slices.
-__global__ void __launch_bounds__(256) adain_coef_kernel(const float* __restrict__ part, int C,
-                                                         int nchunk, const int* len,
-                                                         const float* __restrict__ sty, int sld,
-                                                         int soff, float eps, float* scale,
-                                                         float* shift) {
-  __shared__ double rs[8][32], rq[8][32];
+// Combine the chunk partials (fp64, fixed order) -> AdaIN coefficients.  Block = 32 channels x 32 chunk
+// slices (1024 threads): the grid is tiny (C/32 x B blocks), so the kernel is pure load latency -- every thread
+// keeps 4 chunks (8 independent loads) in flight; the additions keep a fixed order, so the result depends only
+// on the data, not on how a batch was composed.
+constexpr int kCoefSlices = 32;
+__global__ void __launch_bounds__(32 * kCoefSlices) adain_coef_kernel(const float* __restrict__ part, int C,
+                                                                      int nchunk, const int* len,
+                                                                      const float* __restrict__ sty, int sld,
+                                                                      int soff, float eps, float* scale,
+                                                                      float* shift) {
+  __shared__ double rs[kCoefSlices][32], rq[kCoefSlices][32];
   const int b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -108,19 +111,17 @@ __global__ void __launch_bounds__(256) adain_coef_kernel(const float* __restrict
   if (c < C) {
     const float* pp = part + (size_t)b * nchunk * 2 * C + c;
     int k = ty;
-    // 8 chunks (16 independent loads) in flight per thread: the kernel is pure L2/HBM latency otherwise;
-    // the additions keep their fixed order
-    for (; k + 56 < nc; k += 64) {
-      float sv[8], qv[8];
+    for (; k + 3 * kCoefSlices < nc; k += 4 * kCoefSlices) {
+      float sv[4], qv[4];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        sv[u] = pp[(size_t)(k + 8 * u) * 2 * C];
-        qv[u] = pp[(size_t)(k + 8 * u) * 2 * C + C];
+      for (int u = 0; u < 4; u++) {
+        sv[u] = pp[(size_t)(k + kCoefSlices * u) * 2 * C];
+        qv[u] = pp[(size_t)(k + kCoefSlices * u) * 2 * C + C];
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) { S += (double)sv[u]; Q += (double)qv[u]; }
+      for (int u = 0; u < 4; u++) { S += (double)sv[u]; Q += (double)qv[u]; }
     }
-    for (; k < nc; k += 8) {
+    for (; k < nc; k += kCoefSlices) {
       S += (double)pp[(size_t)k * 2 * C];
       Q += (double)pp[(size_t)k * 2 * C + C];
     }
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) adain_coef_kernel(const float* __restrict
   if (ty == 0 && c < C) {
     S = 0.0; Q = 0.0;
 #pragma unroll
-    for (int y = 0; y < 8; y++) { S += rs[y][tx]; Q += rq[y][tx]; }
+    for (int y = 0; y < kCoefSlices; y++) { S += rs[y][tx]; Q += rq[y][tx]; }
     const double mean = S / (double)L;
     double var = Q / (double)L - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -148,7 +149,7 @@ void launch_adain_coef(const float* part, int C, int max_len, const int* len, co
   if (g_dry_run) return;
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
   dim3 g((C + 31) / 32, B);
-  adain_coef_kernel<<<g, 256, 0, st>>>(part, C, nchunk, len, sty, sld, soff, eps, scale, shift);
+  adain_coef_kernel<<<g, 32 * kCoefSlices, 0, st>>>(part, C, nchunk, len, sty, sld, soff, eps, scale, shift);
   post_launch("adain_coef", st);
 }
 
