@@ -5,18 +5,19 @@
 // as ONE persistent tcgen05 kernel per conv.  Compared with the generic conv_tc path (colstats ->
 // adain_coef -> apply_bf16 -> conv_tc) it removes three HBM passes and most of the L2->SM operand
 // traffic:
-//   * the AdaIN scale/shift + Snake operand transform runs inside the kernel: 8 producer warps read the
+//   * the AdaIN scale/shift + Snake operand transform runs inside the kernel: 6 producer warps read the
 //     raw activations (fp32 residual stream or bf16 intermediate) once per tile -- a halo tile of
 //     128*MSUB + 2*pad rows per 64-channel chunk -- and write the bf16 operand straight into the
 //     128B-swizzled smem layout the tensor core reads;
 //   * every tap of the conv reads a ROW-SHIFTED VIEW of that one halo tile (UMMA descriptor start
-//     address + tap*dil*128 B), so A is fetched once per tile instead of once per tap, and each weight
-//     tile (TMA, 4/3-stage ring) is shared by MSUB 128-row sub-tiles;
-//   * the epilogue (TMEM -> registers -> smem transpose -> global) adds bias / residual, writes fp32
-//     and/or bf16, and emits the per-128-row column sums (sum x, sum x^2) the next AdaIN needs, so no
-//     separate statistics pass reads the tensor again.
-// TMEM holds two accumulator sets (2 x MSUB x BN = 512 columns): the epilogue of tile i overlaps the
-// MMAs of tile i+1; the operand producers run one channel chunk ahead of the MMA warp.
+//     address + tap*dil*128 B), so the activations are fetched once per tile instead of once per tap, and
+//     each weight tile (TMA ring; resident when the whole set fits) is shared by all rows of the tile;
+//   * the epilogue adds bias / residual, writes bf16 (conv1) or fp32 (conv2), and emits the per-128-row
+//     column sums (sum x, sum x^2) the next AdaIN needs, so no separate statistics pass reads the tensor
+//     again.  Two accumulator layouts: rows as M with a smem-transposed epilogue (C = 256), or the
+//     transposed accumulator described at ArbCfg (C = 128) whose epilogue needs no transpose at all.
+// TMEM holds two accumulator sets (512 columns): the epilogue of tile i overlaps the MMAs of tile i+1;
+// the operand producers run one channel chunk (or more, with three slots) ahead of the MMA warp.
 //
 // Warp roles (512 threads, 1 CTA/SM, persistent over a contiguous range of tiles):
 //   warp 0      weight-tile TMA producer          warp 1        TMEM alloc + tcgen05.mma issuer

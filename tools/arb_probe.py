@@ -1,5 +1,8 @@
 """Probe of the fused res-block conv kernel (kernels_arb.cu) against a float64 reference with the same
-bf16 operand rounding.  Prints max-abs / rel-L2 errors for both UMMA base-offset conventions.
+bf16 operand rounding.  Prints max-abs / rel-L2 errors per case.  (History: the first version of this probe ran the
+kernel with both UMMA smem-descriptor base-offset conventions for the row-shifted operand views; base_offset = 0 --
+swizzle as a function of absolute smem address bits -- is the one that is correct on B200, the other gave rel-L2
+errors of 0.4-0.9, and the kernel now hard-codes it.)
 
     python tools/arb_probe.py
 """
@@ -80,7 +83,7 @@ def main():
     lib.kkx_test_last_error.restype = C.c_char_p
     cases = [(128, 3, 1, [300]), (128, 11, 5, [700, 13, 257]), (128, 7, 3, [256, 512, 1]), (256, 7, 1, [333]),
              (256, 11, 5, [129, 640]), (256, 3, 3, [128, 127])]
-    for mode in (0, 1):
+    for mode in (0,):
         for (Cc, k, dil, lens) in cases:
             for (in_bf16, want_bf16, use_res, osc, acc) in [(0, 1, 0, 1.0, 0), (1, 0, 1, 1.0 / 3, 1)]:
                 out, ref, sums, rs = run_case(lib, Cc, k, dil, lens, in_bf16, want_bf16, use_res, osc, acc, mode)
