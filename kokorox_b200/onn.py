@@ -86,6 +86,34 @@ def load_library(path: Optional[str] = None):
         return lib
 
 
+def parse_style_name(style_name: str, voice_ids) -> tuple:
+    """The parsing half of TTSKoko::mix_styles (koko.rs:1255-1295): ``"af_sky"`` or ``"af_sky.4+af_nicole.5"`` ->
+    ([voice ids], [f32 portions]).  A single voice is one entry with portion 1.0 (the reference copies the row);
+    in a mix every ``name.weight`` part contributes ``weight * 0.1`` (f32, not renormalised); parts without a
+    numeric weight are skipped like the reference's ``if let Ok(portion)``; unknown voices are errors with the
+    reference's messages."""
+    if "+" not in style_name:
+        if style_name not in voice_ids:
+            raise KkxError(-1, f"can not found from styles_map: {style_name}")
+        return [voice_ids[style_name]], [np.float32(1.0)]
+    vs, ps = [], []
+    for part in style_name.split("+"):
+        if "." in part:
+            name, portion = part.split(".", 1)
+            try:
+                w = np.float32(float(portion))
+            except ValueError:
+                continue
+            if name not in voice_ids:
+                raise KkxError(-1, f"Voice '{name}' not found in available voices")
+            vs.append(voice_ids[name])
+            ps.append(np.float32(w * np.float32(0.1)))
+    if not vs:
+        raise KkxError(-1, f"Invalid voice mix format '{style_name}'. Use format: voice1.weight+voice2.weight "
+                           "(e.g., jf_alpha.4+am_echo.6)")
+    return vs, ps
+
+
 def _fp(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
@@ -220,30 +248,10 @@ class B200Koko:
         self._voice_table = table
 
     def _parse_style(self, style_name: str):
-        """The parsing half of TTSKoko::mix_styles (koko.rs:1255-1306): -> ([voice ids], [f32 portions])."""
         ids = getattr(self, "_voice_ids", None)
         if ids is None:
             raise KkxError(-5, "no voices loaded")
-        if "+" not in style_name:
-            if style_name not in ids:
-                raise KkxError(-1, f"can not found from styles_map: {style_name}")
-            return [ids[style_name]], [np.float32(1.0)]
-        vs, ps = [], []
-        for part in style_name.split("+"):
-            if "." in part:
-                name, portion = part.split(".", 1)
-                try:
-                    w = np.float32(float(portion))
-                except ValueError:
-                    continue
-                if name not in ids:
-                    raise KkxError(-1, f"Voice '{name}' not found in available voices")
-                vs.append(ids[name])
-                ps.append(np.float32(w * np.float32(0.1)))
-        if not vs:
-            raise KkxError(-1, f"Invalid voice mix format '{style_name}'. Use format: voice1.weight+voice2.weight "
-                               "(e.g., jf_alpha.4+am_echo.6)")
-        return vs, ps
+        return parse_style_name(style_name, ids)
 
     def mix_styles(self, style_name: str, tokens_len: int) -> np.ndarray:
         """Host mirror of TTSKoko::mix_styles (same f32 arithmetic and order) -> [1,256]; the device path of

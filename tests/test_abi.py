@@ -68,3 +68,22 @@ def test_python_shim_mirrors_reference_names():
     # OrtKoko::new / OrtKoko::infer / init_ort (ort_koko.rs:31-42, mod.rs:19-49)
     from kokorox_b200 import onn
     assert callable(onn.init_ort) and hasattr(onn.B200Koko, "new") and hasattr(onn.B200Koko, "infer")
+
+
+def test_parse_style_name_mirrors_mix_styles():
+    # TTSKoko::mix_styles parsing (koko.rs:1255-1295): single voice, weighted mixes (weight * 0.1 in f32, not
+    # renormalised), skipped malformed parts, the reference's error cases
+    import numpy as np
+    import pytest
+    from kokorox_b200.onn import KkxError, parse_style_name
+    ids = {"af_sky": 0, "af_nicole": 1, "am_echo": 2}
+    assert parse_style_name("af_sky", ids) == ([0], [np.float32(1.0)])
+    v, p = parse_style_name("af_sky.4+af_nicole.5", ids)
+    assert v == [0, 1] and p == [np.float32(4.0) * np.float32(0.1), np.float32(5.0) * np.float32(0.1)]
+    v, p = parse_style_name("af_sky.4+am_echo", ids)              # part without a weight is skipped
+    assert v == [0]
+    v, p = parse_style_name("af_sky.x+am_echo.2", ids)            # non-numeric weight is skipped
+    assert v == [2]
+    for bad in ("nobody", "nobody.4+af_sky.5", "af_sky+am_echo"):
+        with pytest.raises(KkxError):
+            parse_style_name(bad, ids)
