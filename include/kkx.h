@@ -67,7 +67,13 @@ KKX_API const char* kkx_last_error(const kkx_ctx* ctx);
  *   out_audio  receives a library-owned pinned host buffer of *out_samples f32 (24 kHz mono,
  *              = 600 * sum(pred_dur)); valid until kkx_release(ctx, ptr) -- outputs[0]
  *   out_pred_dur  nullable; [n_tokens] predicted integer frame durations (not observable
- *              through the reference graph; exposed for parity tests). */
+ *              through the reference graph; exposed for parity tests).
+ * Thread-safe.  By default concurrent callers run one after another, like the reference's
+ * Mutex<Session> (ort_koko.rs:14,77).  With option "coalesce" = K > 1 the callers that are waiting while a
+ * step runs are merged into ONE ragged batch of up to K utterances (the batching queue SURVEY 8f row 4 asks the
+ * servers for, openai lib.rs:400-412): each caller still gets exactly the waveform it would get alone (batched
+ * and single results are bit-identical), as a view into a shared pinned buffer that is recycled once every
+ * caller of that batch has called kkx_release.  A request that fails validation fails alone. */
 KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur);
 
@@ -124,7 +130,12 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *   "precision"   0 = fp32 SIMT everywhere, 1 = bf16 tensor-core (tcgen05) decoder+generator
  *   "noise_seed"  seed of the on-device Philox N(0,1) generator for the SineGen noise
  *   "max_frames"  frame budget per frame-phase group (memory control for large batches)
- *   "stft_replicate" 0 = reflect edge padding (upstream STFT), 1 = replicate (conv-STFT export)  */
+ *   "stft_replicate" 0 = reflect edge padding (upstream STFT), 1 = replicate (conv-STFT export)
+ *   "coalesce"    0/1 = off; K > 1 (<= 512) = merge up to K concurrent kkx_infer callers per step
+ *   "coalesce_wait_us"  how long the caller that found the queue idle waits for company (default 0: no
+ *                 added latency -- batches form from whatever queued up behind the running step)
+ * kkx_get_stat keys: "launches", "last_frames", "gpu_us", "precision", "coalesced_batches",
+ * "coalesced_requests", "coalesced_largest". */
 KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value);
 KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key); /* "launches", "last_frames", "gpu_us" ... */
 

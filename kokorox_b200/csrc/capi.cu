@@ -4,7 +4,10 @@
 // panic into abort(); a library must not).
 #include "../../include/kkx.h"
 #include "model.h"
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <map>
 #include <set>
@@ -16,11 +19,32 @@ struct kkx_ctx {
   std::unique_ptr<Model> model;
   std::mutex mu;  // single-flight like the reference's Mutex<Session> (ort_koko.rs:14,77-78)
   std::string err;
+  // pinned result buffers; their own lock, so that kkx_release never waits for the step `mu` is held across
+  std::mutex pool_mu;
   std::map<float*, size_t> pinned;       // audio buffers handed out -> capacity (floats)
   std::vector<std::pair<float*, size_t>> pinned_free;  // returned buffers kept for reuse
+  size_t pinned_free_floats = 0;
+
+  // Request coalescing: concurrent kkx_infer callers queue here; one of them becomes the
+  // leader, runs everything queued as ONE ragged batch and hands each caller a view into the shared result
+  // buffer.  The reference queues the same callers on Mutex<Session> and runs them one by one (ort_koko.rs:77).
+  struct Waiter {
+    const int64_t* tokens; int32_t n; const float* style; float speed; int32_t* pred_dur;
+    float* audio = nullptr; int64_t samples = 0; int rc = 0; std::string err; bool done = false;
+  };
+  struct SharedBuf { float* base; size_t cap; int refs; };
+  std::mutex qmu;
+  std::condition_variable qcv;
+  std::deque<Waiter*> queue;
+  bool leader = false;
+  int coalesce_max = 0;          // 0/1 = off (reference behaviour); >1 = largest batch a leader gathers
+  int coalesce_wait_us = 0;      // how long a leader waits for company before it runs
+  int64_t coalesced_batches = 0, coalesced_requests = 0, coalesced_largest = 0;
+  std::map<float*, SharedBuf*> views;   // per-caller view -> the shared buffer it pins (guarded by pool_mu)
 };
 
 static thread_local std::string g_err;
+static constexpr int kMaxCoalesce = 512;
 
 template <class F>
 static int guarded(kkx_ctx* ctx, F&& f) {
@@ -76,6 +100,9 @@ KKX_API void kkx_destroy(kkx_ctx* ctx) {
     if (ctx->model) cudaSetDevice(ctx->model->device());
     for (auto& p : ctx->pinned) cudaFreeHost(p.first);
     for (auto& p : ctx->pinned_free) cudaFreeHost(p.first);
+    std::set<kkx_ctx::SharedBuf*> shared;
+    for (auto& v : ctx->views) shared.insert(v.second);
+    for (auto* sb : shared) { cudaFreeHost(sb->base); delete sb; }
     ctx->model.reset();
   } catch (...) {}
   delete ctx;
@@ -93,12 +120,19 @@ static int check_ctx(kkx_ctx* ctx) {
 static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
   float* host = nullptr;
   size_t cap = 0;
-  for (size_t i = 0; i < ctx->pinned_free.size(); i++)
-    if (ctx->pinned_free[i].second >= need_floats) {
-      host = ctx->pinned_free[i].first; cap = ctx->pinned_free[i].second;
-      ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
-      break;
+  {
+    std::lock_guard<std::mutex> pl(ctx->pool_mu);
+    size_t best = ctx->pinned_free.size();   // smallest buffer that fits
+    for (size_t i = 0; i < ctx->pinned_free.size(); i++)
+      if (ctx->pinned_free[i].second >= need_floats &&
+          (best == ctx->pinned_free.size() || ctx->pinned_free[i].second < ctx->pinned_free[best].second))
+        best = i;
+    if (best < ctx->pinned_free.size()) {
+      host = ctx->pinned_free[best].first; cap = ctx->pinned_free[best].second;
+      ctx->pinned_free.erase(ctx->pinned_free.begin() + best);
+      ctx->pinned_free_floats -= cap;
     }
+  }
   if (!host) {
     cap = std::max<size_t>(need_floats + need_floats / 8, 1024);
     KKX_CUDA(cudaMallocHost(&host, cap * sizeof(float)));
@@ -106,8 +140,34 @@ static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
   *cap_out = cap;
   return host;
 }
+static void hand_out(kkx_ctx* ctx, float* host, size_t cap) {
+  std::lock_guard<std::mutex> pl(ctx->pool_mu);
+  ctx->pinned[host] = cap;
+}
 
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
+// One ragged batch through the model into a pooled pinned buffer (caller holds ctx->mu; throws).  The buffer is
+// handed to the model as a sink: every frame group's audio is copied out on a second stream while the next
+// group computes.
+static void run_batch_locked(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                             const float* styles, const float* speeds, float** host_out, size_t* cap_out,
+                             int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+  Model& m = *ctx->model;
+  m.stage(batch, tokens, tok_offsets, styles, speeds);
+  float* host = nullptr;
+  size_t cap = 0;
+  m.host_sink = [&](long long n) { host = take_pinned(ctx, (size_t)n, &cap); return host; };
+  try {
+    m.run();
+    m.host_sink = nullptr;
+    const long long n = m.total_samples();
+    if (!host) host = take_pinned(ctx, (size_t)n, &cap);
+    m.fetch(m.sink_filled() ? nullptr : host, n, out_sample_offsets, out_pred_dur);
+  } catch (...) { m.host_sink = nullptr; if (host) cudaFreeHost(host); throw; }
+  *host_out = host;
+  *cap_out = cap;
+}
 
 KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
                     const float* styles, const float* speeds, float** out_audio,
@@ -118,23 +178,107 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded(ctx, [&] {
     if (!out_audio) throw ArgError("out_audio is null");
-    Model& m = *ctx->model;
-    m.stage(batch, tokens, tok_offsets, styles, speeds);
-    // the pinned result buffer is handed to the model as a sink: every frame group's audio is copied out on a
-    // second stream while the next group computes
     float* host = nullptr;
     size_t cap = 0;
-    m.host_sink = [&](long long n) { host = take_pinned(ctx, (size_t)n, &cap); return host; };
-    try {
-      m.run();
-      m.host_sink = nullptr;
-      const long long n = m.total_samples();
-      if (!host) host = take_pinned(ctx, (size_t)n, &cap);
-      m.fetch(m.sink_filled() ? nullptr : host, n, out_sample_offsets, out_pred_dur);
-    } catch (...) { m.host_sink = nullptr; if (host) cudaFreeHost(host); throw; }
-    ctx->pinned[host] = cap;
+    run_batch_locked(ctx, batch, tokens, tok_offsets, styles, speeds, &host, &cap, out_sample_offsets, out_pred_dur);
+    hand_out(ctx, host, cap);
     *out_audio = host;
   });
+}
+
+// Leader side of the coalescer: run `batch` as one ragged batch; on failure re-run the requests one by one so
+// that only the offending caller sees the error.
+static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& batch) {
+  const int B = (int)batch.size();
+  std::vector<int32_t> offs(B + 1, 0);
+  for (int i = 0; i < B; i++) offs[i + 1] = offs[i] + std::max(batch[i]->n, 0);
+  std::vector<int64_t> toks((size_t)std::max(offs[B], 1));
+  std::vector<float> styles((size_t)B * 256), speeds(B);
+  std::vector<int64_t> soff(B + 1, 0);
+  std::vector<int32_t> dur((size_t)std::max(offs[B], 1));
+  bool args_ok = true;
+  for (int i = 0; i < B; i++) {
+    kkx_ctx::Waiter& w = *batch[i];
+    if (!w.tokens || !w.style || w.n <= 0) { args_ok = false; continue; }
+    memcpy(&toks[offs[i]], w.tokens, (size_t)w.n * sizeof(int64_t));
+    memcpy(&styles[(size_t)i * 256], w.style, 256 * sizeof(float));
+    speeds[i] = w.speed;
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  float* host = nullptr;
+  size_t cap = 0;
+  int rc = KKX_ERR_ARG;
+  if (args_ok)
+    rc = guarded(ctx, [&] {
+      run_batch_locked(ctx, B, toks.data(), offs.data(), styles.data(), speeds.data(), &host, &cap, soff.data(), dur.data());
+    });
+  if (rc == KKX_OK) {
+    auto* sb = new kkx_ctx::SharedBuf{host, cap, B};
+    std::lock_guard<std::mutex> pl(ctx->pool_mu);
+    for (int i = 0; i < B; i++) {
+      kkx_ctx::Waiter& w = *batch[i];
+      w.audio = host + soff[i];
+      w.samples = soff[i + 1] - soff[i];
+      if (w.pred_dur) memcpy(w.pred_dur, &dur[offs[i]], (size_t)w.n * sizeof(int32_t));
+      w.rc = KKX_OK;
+      ctx->views[w.audio] = sb;
+    }
+    ctx->coalesced_batches++;
+    ctx->coalesced_requests += B;
+    ctx->coalesced_largest = std::max<int64_t>(ctx->coalesced_largest, B);
+    return;
+  }
+  for (int i = 0; i < B; i++) {   // isolate the failure
+    kkx_ctx::Waiter& w = *batch[i];
+    const int32_t o1[2] = {0, w.n};
+    int64_t s1[2] = {0, 0};
+    float* h1 = nullptr;
+    size_t c1 = 0;
+    w.rc = guarded(ctx, [&] {
+      if (!w.tokens || !w.style) throw ArgError("null argument");
+      run_batch_locked(ctx, 1, w.tokens, o1, w.style, &w.speed, &h1, &c1, s1, w.pred_dur);
+    });
+    if (w.rc == KKX_OK) {
+      hand_out(ctx, h1, c1);
+      w.audio = h1;
+      w.samples = s1[1];
+      ctx->coalesced_batches++;
+      ctx->coalesced_requests++;
+    } else {
+      w.err = ctx->err;
+    }
+  }
+}
+
+static int infer_coalesced(kkx_ctx* ctx, kkx_ctx::Waiter& w) {
+  std::unique_lock<std::mutex> ql(ctx->qmu);
+  ctx->queue.push_back(&w);
+  if (ctx->leader) ctx->qcv.notify_all();   // a leader may be waiting for company
+  while (!w.done) {
+    if (ctx->leader) { ctx->qcv.wait(ql); continue; }
+    ctx->leader = true;
+    const size_t want = (size_t)std::max(ctx->coalesce_max, 1);
+    if (ctx->coalesce_wait_us > 0 && ctx->queue.size() < want)
+      ctx->qcv.wait_for(ql, std::chrono::microseconds(ctx->coalesce_wait_us), [&] { return ctx->queue.size() >= want; });
+    // FIFO, bounded by the batch size and by the 64 x 512-token working set the step is sized for
+    std::vector<kkx_ctx::Waiter*> batch;
+    long long tok = 0;
+    while (!ctx->queue.empty() && batch.size() < want) {
+      kkx_ctx::Waiter* q = ctx->queue.front();
+      if (!batch.empty() && tok + q->n > 64 * 512) break;
+      tok += std::max(q->n, 0);
+      batch.push_back(q);
+      ctx->queue.pop_front();
+    }
+    ql.unlock();
+    serve_coalesced(ctx, batch);
+    ql.lock();
+    for (auto* b : batch) b->done = true;
+    ctx->leader = false;
+    ctx->qcv.notify_all();
+  }
+  if (w.rc != KKX_OK) g_err = w.err;
+  return w.rc;
 }
 
 KKX_API int kkx_load_voices(kkx_ctx* ctx, const float* table, int32_t n_voices) {
@@ -163,7 +307,7 @@ KKX_API int kkx_infer_batch_voices(kkx_ctx* ctx, int32_t batch, const int64_t* t
     try {
       m.fetch(host, n, out_sample_offsets, out_pred_dur);
     } catch (...) { cudaFreeHost(host); throw; }
-    ctx->pinned[host] = cap;
+    hand_out(ctx, host, cap);
     *out_audio = host;
   });
 }
@@ -188,7 +332,7 @@ KKX_API int kkx_infer_batch_pcm16(kkx_ctx* ctx, int32_t batch, const int64_t* to
     try {
       m.fetch_pcm16(reinterpret_cast<short*>(host), n, out_sample_offsets, out_pred_dur);
     } catch (...) { cudaFreeHost(host); throw; }
-    ctx->pinned[host] = cap;
+    hand_out(ctx, host, cap);
     *out_pcm = reinterpret_cast<int16_t*>(host);
   });
 }
@@ -198,6 +342,13 @@ KKX_API void kkx_release_pcm16(kkx_ctx* ctx, int16_t* pcm) { kkx_release(ctx, re
 KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {
   if (out_samples) *out_samples = 0;
+  if (ctx && ctx->model && ctx->coalesce_max > 1) {
+    if (out_audio) *out_audio = nullptr; else { g_err = ctx->err = "out_audio is null"; return KKX_ERR_ARG; }
+    kkx_ctx::Waiter w{tokens, n_tokens, style256, speed, out_pred_dur};
+    const int rc = infer_coalesced(ctx, w);
+    if (rc == KKX_OK) { *out_audio = w.audio; if (out_samples) *out_samples = w.samples; }
+    return rc;
+  }
   const int32_t offs[2] = {0, n_tokens};
   int64_t soff[2] = {0, 0};
   const int rc = kkx_infer_batch(ctx, 1, tokens, offs, style256, &speed, out_audio, soff, out_pred_dur);
@@ -207,16 +358,32 @@ KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, con
 
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio) {
   if (!ctx || !audio) return;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  auto it = ctx->pinned.find(audio);
-  if (it != ctx->pinned.end()) {
-    if (ctx->pinned_free.size() < 4) {
+  float* to_free = nullptr;
+  {
+    std::lock_guard<std::mutex> pl(ctx->pool_mu);
+    auto vit = ctx->views.find(audio);
+    if (vit != ctx->views.end()) {     // a coalesced caller's view: the shared buffer goes back with its last view
+      kkx_ctx::SharedBuf* sb = vit->second;
+      ctx->views.erase(vit);
+      if (--sb->refs > 0) return;
+      ctx->pinned[sb->base] = sb->cap;
+      audio = sb->base;
+      delete sb;
+    }
+    auto it = ctx->pinned.find(audio);
+    if (it == ctx->pinned.end()) return;
+    // keep returned buffers for reuse (pinned allocation costs milliseconds and synchronises the device)
+    if (ctx->pinned_free.size() < 64 && ctx->pinned_free_floats + it->second <= (size_t(1) << 28)) {
       ctx->pinned_free.push_back({it->first, it->second});
+      ctx->pinned_free_floats += it->second;
     } else {
-      if (ctx->model) cudaSetDevice(ctx->model->device());
-      cudaFreeHost(audio);
+      to_free = audio;
     }
     ctx->pinned.erase(it);
+  }
+  if (to_free) {
+    if (ctx->model) cudaSetDevice(ctx->model->device());
+    cudaFreeHost(to_free);
   }
 }
 
@@ -259,6 +426,15 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "noise_seed") o.noise_seed = (unsigned long long)value;
     else if (k == "max_frames") { if (value < 1) throw ArgError("max_frames must be >= 1"); o.max_frames = (int)value; }
     else if (k == "stft_replicate") o.stft_replicate = value ? 1 : 0;
+    else if (k == "coalesce") {
+      if (value < 0 || value > kMaxCoalesce) throw ArgError("coalesce must be in 0..512");
+      std::lock_guard<std::mutex> ql(ctx->qmu);
+      ctx->coalesce_max = (int)value;
+    } else if (k == "coalesce_wait_us") {
+      if (value < 0 || value > 1000000) throw ArgError("coalesce_wait_us must be in 0..1000000");
+      std::lock_guard<std::mutex> ql(ctx->qmu);
+      ctx->coalesce_wait_us = (int)value;
+    }
     else throw ArgError("unknown option: " + k);
   });
 }
@@ -271,6 +447,9 @@ KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key) {
   if (k == "last_frames") return ctx->model->last_frames;
   if (k == "gpu_us") return (int64_t)ctx->model->last_gpu_us;
   if (k == "precision") return ctx->model->opt.precision;
+  if (k == "coalesced_batches") return ctx->coalesced_batches;
+  if (k == "coalesced_requests") return ctx->coalesced_requests;
+  if (k == "coalesced_largest") return ctx->coalesced_largest;
   return -1;
 }
 

@@ -143,6 +143,7 @@ class B200Koko:
         self.device = device
         self._outstanding = 0
         self._closing = False
+        self._count_lock = threading.RLock()   # re-entrant: a GC-run finalizer may fire inside the block
 
     @classmethod
     def new(cls, model_path: str, device: int = 0) -> "B200Koko":
@@ -165,7 +166,8 @@ class B200Koko:
         try:
             if session._ctx.value:
                 session._lib.kkx_release(session._ctx, C.cast(C.c_void_p(addr), C.POINTER(C.c_float)))
-            session._outstanding -= 1
+            with session._count_lock:
+                session._outstanding -= 1
             if session._closing and session._outstanding <= 0:
                 session._closing = False
                 session.close()
@@ -194,6 +196,29 @@ class B200Koko:
         reference's output the same way (koko.rs:1179)."""
         outs = self.infer_batch([list(t) for t in tokens], styles, [speed] * len(tokens))
         return outs[0] if len(outs) == 1 else np.concatenate(outs)
+
+    def infer_one(self, tokens: Sequence[int], style, speed: float = 1.0, return_durations: bool = False):
+        """One utterance through ``kkx_infer`` -- the call a server thread makes per request.  Safe to call from
+        many threads at once; with ``set_option("coalesce", K)`` the concurrent calls are merged into ragged
+        batches inside the library (the reference serialises them on its session mutex, ort_koko.rs:77)."""
+        self._require()
+        tk = np.ascontiguousarray(np.asarray(tokens, dtype=np.int64).reshape(-1))
+        st = np.ascontiguousarray(np.asarray(style, dtype=np.float32).reshape(-1))
+        if st.size != 256:
+            raise KkxError(-1, f"style must have 256 values, got {st.size}")
+        audio = C.POINTER(C.c_float)()
+        ns = C.c_int64(0)
+        dur = np.zeros(max(tk.size, 1), dtype=np.int32)
+        rc = self._lib.kkx_infer(self._ctx, tk.ctypes.data_as(C.POINTER(C.c_int64)), int(tk.size), _fp(st),
+                                 C.c_float(speed), C.byref(audio), C.byref(ns),
+                                 dur.ctypes.data_as(C.POINTER(C.c_int32)))
+        self._check(rc)
+        out = np.ctypeslib.as_array(audio, shape=(max(int(ns.value), 1),))
+        with self._count_lock:
+            self._outstanding += 1
+        weakref.finalize(out, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
+        out = out[:int(ns.value)]
+        return (out, dur[:tk.size]) if return_durations else out
 
     def infer_batch(self, tokens: Sequence[Sequence[int]], styles, speeds: Sequence[float],
                     return_durations: bool = False):
@@ -225,7 +250,8 @@ class B200Koko:
         # the library's pool (kkx_release) when the last view is garbage-collected; the views keep this
         # session alive until then.
         base = np.ctypeslib.as_array(audio, shape=(max(total, 1),))
-        self._outstanding += 1
+        with self._count_lock:
+            self._outstanding += 1
         weakref.finalize(base, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
         outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
         del base
@@ -294,7 +320,8 @@ class B200Koko:
             ip(rows), _fp(sp), C.byref(audio), soff.ctypes.data_as(C.POINTER(C.c_int64)), ip(dur)))
         total = int(soff[-1])
         base = np.ctypeslib.as_array(audio, shape=(max(total, 1),))
-        self._outstanding += 1
+        with self._count_lock:
+            self._outstanding += 1
         weakref.finalize(base, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
         outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
         del base
@@ -320,7 +347,8 @@ class B200Koko:
             _fp(st), _fp(sp), C.byref(pcm), soff.ctypes.data_as(C.POINTER(C.c_int64)), None))
         total = int(soff[-1])
         base = np.ctypeslib.as_array(pcm, shape=(max(total, 1),))
-        self._outstanding += 1
+        with self._count_lock:
+            self._outstanding += 1
         weakref.finalize(base, B200Koko._release_buffer, self, C.cast(pcm, C.c_void_p).value)
         outs = [base[int(soff[b]):int(soff[b + 1])] for b in range(B)]
         del base

@@ -292,3 +292,72 @@ def test_pcm16_output_fused_into_istft(model):
         assert b.dtype == np.int16 and len(a) == len(b)
         want = np.trunc(np.clip(a, -1.0, 1.0).astype(np.float32) * np.float32(32767.0)).astype(np.int16)
         assert np.array_equal(want, b)
+
+
+def _run_threads(fn, n):
+    import threading
+    res, errs = [None] * n, [None] * n
+
+    def work(i):
+        try:
+            res[i] = fn(i)
+        except Exception as e:  # noqa: BLE001 -- collected and asserted by the caller
+            errs[i] = e
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return res, errs
+
+
+def test_concurrent_callers_are_coalesced_into_one_batch(model):
+    # SURVEY 8f row 4 / 8b "thread-safe": 16 threads call kkx_infer at once, the way the reference's server
+    # threads call OrtKoko::infer (openai lib.rs:400-412) and queue on Mutex<Session> (ort_koko.rs:77).  With
+    # "coalesce" on they leave as ONE ragged batch; every caller must get exactly its own B=1 result.
+    from kokorox_b200.onn import KkxError
+    n = 16
+    rng = np.random.default_rng(11)
+    cases = [synth_case(int(k), 7000 + i, 7100 + i) for i, k in enumerate(rng.integers(4, 120, size=n))]
+    speeds = rng.uniform(0.8, 1.3, size=n).astype(np.float32).tolist()
+    model.set_noise(None)
+    model.set_option("precision", 1)
+    try:
+        alone = [model.infer_one(cases[i][0], cases[i][1], speeds[i], return_durations=True) for i in range(n)]
+        b0, r0 = model.get_stat("coalesced_batches"), model.get_stat("coalesced_requests")
+        assert b0 == 0 and r0 == 0          # off by default: the reference's one-by-one behaviour
+        model.set_option("coalesce", n)
+        model.set_option("coalesce_wait_us", 500000)   # the first caller waits until all 16 have queued
+        res, errs = _run_threads(lambda i: model.infer_one(cases[i][0], cases[i][1], speeds[i], return_durations=True), n)
+        assert all(e is None for e in errs), errs
+        assert model.get_stat("coalesced_requests") == n
+        assert model.get_stat("coalesced_batches") == 1 and model.get_stat("coalesced_largest") == n
+        for i in range(n):
+            assert np.array_equal(res[i][1], alone[i][1])
+            assert np.array_equal(res[i][0], alone[i][0]), f"caller {i}: coalesced result differs from its own call"
+        # the shared buffer returns to the pool with its last view; the next round reuses it
+        del res
+        res, errs = _run_threads(lambda i: model.infer_one(cases[i][0], cases[i][1], speeds[i]), n)
+        assert all(e is None for e in errs), errs
+        assert all(np.array_equal(res[i], alone[i][0]) for i in range(n))
+        # a bad request fails alone (id 9999 is outside the vocabulary); its batch mates still get audio
+        before = model.get_stat("coalesced_requests")
+
+        def one(i):
+            ids = list(cases[i][0])
+            if i == 5:
+                ids[2] = 9999
+            return model.infer_one(ids, cases[i][1], speeds[i])
+        res, errs = _run_threads(one, n)
+        assert isinstance(errs[5], KkxError) and res[5] is None
+        assert all(errs[i] is None and np.array_equal(res[i], alone[i][0]) for i in range(n) if i != 5)
+        assert model.get_stat("coalesced_requests") == before + n - 1
+        # no waiting window: still correct, batches form from whoever queued behind the running step
+        model.set_option("coalesce_wait_us", 0)
+        res, errs = _run_threads(lambda i: model.infer_one(cases[i][0], cases[i][1], speeds[i]), n)
+        assert all(e is None for e in errs), errs
+        assert all(np.array_equal(res[i], alone[i][0]) for i in range(n))
+    finally:
+        model.set_option("coalesce", 0)
+        model.set_option("coalesce_wait_us", 0)
+        model.set_option("precision", 0)
