@@ -24,6 +24,7 @@ struct kkx_ctx {
   std::map<float*, size_t> pinned;       // audio buffers handed out -> capacity (floats)
   std::vector<std::pair<float*, size_t>> pinned_free;  // returned buffers kept for reuse
   size_t pinned_free_floats = 0;
+  size_t pinned_hi = 0;                  // largest request so far: big buffers are sized alike so they recycle
 
   // Request coalescing: concurrent kkx_infer callers queue here; one of them becomes the
   // leader, runs everything queued as ONE ragged batch and hands each caller a view into the shared result
@@ -119,9 +120,10 @@ static int check_ctx(kkx_ctx* ctx) {
 // shared tail of the infer entry points: run the staged batch and hand out a pooled pinned buffer
 static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
   float* host = nullptr;
-  size_t cap = 0;
+  size_t cap = 0, hi = 0;
   {
     std::lock_guard<std::mutex> pl(ctx->pool_mu);
+    hi = ctx->pinned_hi = std::max(ctx->pinned_hi, need_floats);
     size_t best = ctx->pinned_free.size();   // smallest buffer that fits
     for (size_t i = 0; i < ctx->pinned_free.size(); i++)
       if (ctx->pinned_free[i].second >= need_floats &&
@@ -134,7 +136,10 @@ static float* take_pinned(kkx_ctx* ctx, size_t need_floats, size_t* cap_out) {
     }
   }
   if (!host) {
-    cap = std::max<size_t>(need_floats + need_floats / 8, 1024);
+    // pinned allocation costs ~1 ms per MB and synchronises the device: give every request in the top size class
+    // the same capacity, so a stream of similar batches reuses the pooled buffers instead of outgrowing them
+    const size_t base = need_floats >= hi / 2 ? hi : need_floats;
+    cap = std::max<size_t>(base + base / 8, 1024);
     KKX_CUDA(cudaMallocHost(&host, cap * sizeof(float)));
   }
   *cap_out = cap;
@@ -150,11 +155,9 @@ KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
 // One ragged batch through the model into a pooled pinned buffer (caller holds ctx->mu; throws).  The buffer is
 // handed to the model as a sink: every frame group's audio is copied out on a second stream while the next
 // group computes.
-static void run_batch_locked(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
-                             const float* styles, const float* speeds, float** host_out, size_t* cap_out,
-                             int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+static void run_staged_locked(kkx_ctx* ctx, float** host_out, size_t* cap_out, int64_t* out_sample_offsets,
+                              int32_t* out_pred_dur) {
   Model& m = *ctx->model;
-  m.stage(batch, tokens, tok_offsets, styles, speeds);
   float* host = nullptr;
   size_t cap = 0;
   m.host_sink = [&](long long n) { host = take_pinned(ctx, (size_t)n, &cap); return host; };
@@ -167,6 +170,12 @@ static void run_batch_locked(kkx_ctx* ctx, int32_t batch, const int64_t* tokens,
   } catch (...) { m.host_sink = nullptr; if (host) cudaFreeHost(host); throw; }
   *host_out = host;
   *cap_out = cap;
+}
+static void run_batch_locked(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
+                             const float* styles, const float* speeds, float** host_out, size_t* cap_out,
+                             int64_t* out_sample_offsets, int32_t* out_pred_dur) {
+  ctx->model->stage(batch, tokens, tok_offsets, styles, speeds);
+  run_staged_locked(ctx, host_out, cap_out, out_sample_offsets, out_pred_dur);
 }
 
 KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
@@ -300,13 +309,9 @@ KKX_API int kkx_infer_batch_voices(kkx_ctx* ctx, int32_t batch, const int64_t* t
     if (!out_audio) throw ArgError("out_audio is null");
     Model& m = *ctx->model;
     m.stage_voices(batch, tokens, tok_offsets, mix_offsets, voice_ids, voice_portions, style_rows, speeds);
-    m.run();
-    const long long n = m.total_samples();
+    float* host = nullptr;
     size_t cap = 0;
-    float* host = take_pinned(ctx, (size_t)n, &cap);
-    try {
-      m.fetch(host, n, out_sample_offsets, out_pred_dur);
-    } catch (...) { cudaFreeHost(host); throw; }
+    run_staged_locked(ctx, &host, &cap, out_sample_offsets, out_pred_dur);
     hand_out(ctx, host, cap);
     *out_audio = host;
   });
