@@ -114,6 +114,19 @@ KKX_API int kkx_infer_batch_pcm16(kkx_ctx* ctx, int32_t batch, const int64_t* to
                           int64_t* out_sample_offsets, int32_t* out_pred_dur);
 KKX_API void kkx_release_pcm16(kkx_ctx* ctx, int16_t* pcm);
 
+/* ---- output containers (host-side byte work after the pcm16 / f32 result; no GPU involved, no ctx needed).
+ * kkx_wav_header_pcm16: the 44-byte RIFF/WAVE header of the WebSocket server's `encode_audio`
+ *   (kokorox-websocket/src/lib.rs:707-731): PCM format 1, mono, 16 bit, sizes filled in from n_samples.
+ * kkx_wav_header_f32_stream: the streaming header of utils/wav.rs:19-43: IEEE-float format 3, both size fields
+ *   0xFFFFFFFF placeholders; f32 samples follow as little-endian bytes (wav.rs:45-50), i.e. the result buffer as is.
+ * kkx_encode_wav16_base64: `encode_audio` end to end for a pcm16 result: base64 (standard alphabet, '=' padded)
+ *   of header + samples.  Returns the number of characters (without the terminating NUL, which is written when
+ *   capacity allows); writes nothing if capacity is too small, so call with dst = NULL to size the buffer. */
+KKX_API int32_t kkx_wav_header_pcm16(uint8_t* dst44, int64_t n_samples, int32_t sample_rate);
+KKX_API int32_t kkx_wav_header_f32_stream(uint8_t* dst44, int32_t channels, int32_t sample_rate);
+KKX_API int64_t kkx_encode_wav16_base64(const int16_t* pcm, int64_t n_samples, int32_t sample_rate, char* dst,
+                                int64_t capacity);
+
 /* ---- device-resident variant (bench.py `value`: inputs already in HBM, output stays in HBM).
  * Stages the batch on the device once; kkx_run_staged() then runs the whole forward with no
  * host<->device payload traffic (only the per-item frame counts cross, 4 bytes per item).

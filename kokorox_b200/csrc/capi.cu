@@ -344,6 +344,66 @@ KKX_API int kkx_infer_batch_pcm16(kkx_ctx* ctx, int32_t batch, const int64_t* to
 
 KKX_API void kkx_release_pcm16(kkx_ctx* ctx, int16_t* pcm) { kkx_release(ctx, reinterpret_cast<float*>(pcm)); }
 
+// ---- output containers: host-side byte work (little-endian host assumed, as everywhere in this library)
+static void put_u16(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+static void put_u32(uint8_t* p, uint32_t v) { put_u16(p, v & 0xFFFF); put_u16(p + 2, v >> 16); }
+static void wav_header(uint8_t* h, uint32_t riff_size, uint32_t data_size, uint32_t format, uint32_t channels,
+                       uint32_t rate, uint32_t bits) {
+  memcpy(h, "RIFF", 4); put_u32(h + 4, riff_size); memcpy(h + 8, "WAVEfmt ", 8);
+  put_u32(h + 16, 16); put_u16(h + 20, format); put_u16(h + 22, channels); put_u32(h + 24, rate);
+  put_u32(h + 28, rate * channels * bits / 8); put_u16(h + 32, channels * bits / 8); put_u16(h + 34, bits);
+  memcpy(h + 36, "data", 4); put_u32(h + 40, data_size);
+}
+
+KKX_API int32_t kkx_wav_header_pcm16(uint8_t* dst44, int64_t n_samples, int32_t sample_rate) {
+  if (!dst44 || n_samples < 0 || sample_rate <= 0) return KKX_ERR_ARG;
+  const uint32_t bytes = (uint32_t)(n_samples * 2);     // u32 arithmetic like the reference (`as u32`)
+  wav_header(dst44, 36u + bytes, bytes, 1, 1, (uint32_t)sample_rate, 16);
+  return 44;
+}
+
+KKX_API int32_t kkx_wav_header_f32_stream(uint8_t* dst44, int32_t channels, int32_t sample_rate) {
+  if (!dst44 || channels <= 0 || sample_rate <= 0) return KKX_ERR_ARG;
+  wav_header(dst44, 0xFFFFFFFFu, 0xFFFFFFFFu, 3, (uint32_t)channels, (uint32_t)sample_rate, 32);
+  return 44;
+}
+
+KKX_API int64_t kkx_encode_wav16_base64(const int16_t* pcm, int64_t n_samples, int32_t sample_rate, char* dst,
+                                int64_t capacity) {
+  if (n_samples < 0 || sample_rate <= 0 || (!pcm && n_samples > 0)) return KKX_ERR_ARG;
+  const int64_t nbytes = 44 + n_samples * 2;
+  const int64_t nchars = (nbytes + 2) / 3 * 4;
+  if (!dst || capacity < nchars) return nchars;
+  static const char T[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  uint8_t head[48];
+  kkx_wav_header_pcm16(head, n_samples, sample_rate);
+  const uint8_t* body = reinterpret_cast<const uint8_t*>(pcm);
+  const int64_t nbody = n_samples * 2;
+  // the header is 44 = 14 * 3 + 2 bytes: borrow up to 4 body bytes so that it ends on a 3-byte group
+  const int borrow = (int)std::min<int64_t>(4, nbody);
+  for (int i = 0; i < borrow; i++) head[44 + i] = body[i];
+  const int hbytes = 44 + borrow;                        // 48 when there is a body: 16 whole groups
+  char* o = dst;
+  auto group = [&](const uint8_t* p, int n) {            // n in 1..3 input bytes -> 4 chars
+    const uint32_t v = ((uint32_t)p[0] << 16) | ((n > 1 ? (uint32_t)p[1] : 0u) << 8) | (n > 2 ? (uint32_t)p[2] : 0u);
+    o[0] = T[v >> 18]; o[1] = T[(v >> 12) & 63];
+    o[2] = n > 1 ? T[(v >> 6) & 63] : '=';
+    o[3] = n > 2 ? T[v & 63] : '=';
+    o += 4;
+  };
+  int hp = 0;
+  for (; hp + 3 <= hbytes; hp += 3) group(head + hp, 3);
+  if (hp < hbytes) {                                     // only when the body has < 4 bytes (0 or 2): tail of the stream
+    group(head + hp, hbytes - hp);
+  } else {
+    int64_t bp = borrow;
+    for (; bp + 3 <= nbody; bp += 3) group(body + bp, 3);
+    if (bp < nbody) group(body + bp, (int)(nbody - bp));
+  }
+  if (capacity > nchars) *o = 0;
+  return nchars;
+}
+
 KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {
   if (out_samples) *out_samples = 0;

@@ -67,6 +67,10 @@ def load_library(path: Optional[str] = None):
         lib.kkx_infer_batch_pcm16.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32), P(P(i16)), P(i64), P(i32)]
         lib.kkx_release_pcm16.argtypes = [vp, P(i16)]
         lib.kkx_release_pcm16.restype = None
+        lib.kkx_wav_header_pcm16.argtypes = [P(C.c_uint8), i64, i32]
+        lib.kkx_wav_header_f32_stream.argtypes = [P(C.c_uint8), i32, i32]
+        lib.kkx_encode_wav16_base64.argtypes = [P(i16), i64, i32, C.c_char_p, i64]
+        lib.kkx_encode_wav16_base64.restype = i64
         lib.kkx_stage_batch.argtypes = [vp, i32, P(i64), P(i32), P(f32), P(f32)]
         lib.kkx_run_staged.argtypes = [vp, P(i64), P(i64)]
         lib.kkx_fetch_staged.argtypes = [vp, P(f32), i64, P(i64), P(i32)]
@@ -112,6 +116,33 @@ def parse_style_name(style_name: str, voice_ids) -> tuple:
         raise KkxError(-1, f"Invalid voice mix format '{style_name}'. Use format: voice1.weight+voice2.weight "
                            "(e.g., jf_alpha.4+am_echo.6)")
     return vs, ps
+
+
+def encode_audio(pcm: np.ndarray, sample_rate: int = 24000) -> str:
+    """``encode_audio`` of the WebSocket server (kokorox-websocket/src/lib.rs:696-736) for a 16-bit PCM result
+    (``infer_batch_pcm16``): base64 of a 44-byte PCM WAV header + the samples.  Host-side byte work in libkkx."""
+    lib = load_library()
+    a = np.ascontiguousarray(np.asarray(pcm, dtype=np.int16).reshape(-1))
+    ptr = a.ctypes.data_as(C.POINTER(C.c_int16))
+    n = lib.kkx_encode_wav16_base64(ptr, a.size, int(sample_rate), None, 0)
+    if n < 0:
+        raise KkxError(int(n), "encode_audio: bad argument")
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.kkx_encode_wav16_base64(ptr, a.size, int(sample_rate), buf, int(n) + 1)
+    return buf.raw[:int(n)].decode("ascii")
+
+
+def wav_header(n_samples: Optional[int] = None, sample_rate: int = 24000, channels: int = 1) -> bytes:
+    """44-byte WAV header: ``n_samples`` given -> the sized PCM16 mono header of ``encode_audio``
+    (websocket lib.rs:707-731); ``None`` -> the streaming IEEE-float header of utils/wav.rs:19-43 (sizes are
+    0xFFFFFFFF placeholders; the f32 result buffer follows as is, wav.rs:45-50)."""
+    lib = load_library()
+    buf = (C.c_uint8 * 44)()
+    rc = (lib.kkx_wav_header_f32_stream(buf, int(channels), int(sample_rate)) if n_samples is None
+          else lib.kkx_wav_header_pcm16(buf, int(n_samples), int(sample_rate)))
+    if rc != 44:
+        raise KkxError(int(rc), "wav_header: bad argument")
+    return bytes(buf)
 
 
 def _fp(a: np.ndarray):

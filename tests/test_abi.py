@@ -87,3 +87,23 @@ def test_parse_style_name_mirrors_mix_styles():
     for bad in ("nobody", "nobody.4+af_sky.5", "af_sky+am_echo"):
         with pytest.raises(KkxError):
             parse_style_name(bad, ids)
+
+
+def test_output_containers_match_the_reference_encoders():
+    # websocket lib.rs:696-736 (encode_audio: PCM16 WAV + base64) and utils/wav.rs:19-50 (streaming float WAV);
+    # host-side byte work in libkkx, no GPU involved
+    import base64
+    import struct
+    from kokorox_b200.onn import encode_audio, wav_header
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 3, 4, 5, 7, 600, 24001):
+        pcm = rng.integers(-32768, 32768, size=n).astype(np.int16)
+        data = pcm.astype("<i2").tobytes()
+        want = (b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " +
+                struct.pack("<IHHIIHH", 16, 1, 1, 24000, 24000 * 2, 2, 16) + b"data" + struct.pack("<I", len(data)) + data)
+        got = encode_audio(pcm)
+        assert got == base64.b64encode(want).decode(), n
+        assert wav_header(n) == want[:44]
+    h = wav_header(None, 24000, 1)
+    assert h == (b"RIFF" + b"\xff" * 4 + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 24000, 24000 * 4, 4, 32) +
+                 b"data" + b"\xff" * 4)
