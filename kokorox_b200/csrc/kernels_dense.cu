@@ -688,11 +688,28 @@ __device__ __forceinline__ void lstm_mbar_wait(uint32_t bar, uint32_t parity) {
 constexpr int kHQ = 68;                 // floats per h quarter (64 + 4 pad)
 constexpr int kHItem = 4 * kHQ;         // floats per item in an h buffer
 
+#ifdef KKX_LSTM_TIMING
+#define LT_DECL long long lt_acc[4] = {0, 0, 0, 0}; long long lt_t = clock64();
+#define LT(i) { const long long n_ = clock64(); lt_acc[i] += n_ - lt_t; lt_t = n_; }
+#define LT_DUMP if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && (warp == 0 || warp == 4) && maxN > 100) \
+    printf("lstm G=%d warp %d steps %d: wait %lld dot %lld sync %lld gate+rest %lld (cycles per step)\n", G, warp, maxN, \
+           lt_acc[0] / maxN, lt_acc[1] / maxN, lt_acc[2] / maxN, lt_acc[3] / maxN);
+#else
+#define LT_DECL
+#define LT(i)
+#define LT_DUMP
+#endif
+// G items per cluster.  Lane quarter q finishes (adds the input projection, writes the gate pre-activations of)
+// the items g = 4i + q; warp w runs the gate non-linearities of the items g = w + 8i.  G = 10 and 12 exist because
+// only 15 clusters of 8 CTAs are co-resident on a B200 (cudaOccupancyMaxActiveClusters): 64 items at G = 8 need
+// 16 clusters, and the one left over used to run as a second wave, doubling the kernel's time.
 template <int G>
 __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __restrict__ xproj,
                                                               const float* __restrict__ whhT,
                                                               float* __restrict__ out, int ldo, int ocol,
                                                               const int* off, const int* len, int B) {
+  constexpr int NQ = (G + 3) / 4;                      // item slots of a lane quarter
+  constexpr int NW = (G + 7) / 8;                      // item slots of a warp (gate phase)
   extern __shared__ float4 lsm4[];
   float* hbuf = reinterpret_cast<float*>(lsm4);        // [2][G][4][68]
   float* gates = hbuf + 2 * G * kHItem;                // [G][128]
@@ -715,14 +732,26 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar1), "r"(kStepBytes) : "memory");
   }
 
-  int ioff[G], ilen[G];
   int maxN = 0;
-#pragma unroll
   for (int g = 0; g < G; g++) {
     const int item = group * G + g;
-    ioff[g] = item < B ? off[item] : 0;
-    ilen[g] = item < B ? len[item] : 0;
-    maxN = max(maxN, ilen[g]);
+    maxN = max(maxN, item < B ? len[item] : 0);
+  }
+  int qoff[NQ], qlen[NQ];                              // the items this lane quarter finishes
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    const int g = 4 * i + q, item = group * G + g;
+    const bool ok = g < G && item < B;
+    qoff[i] = ok ? off[item] : 0;
+    qlen[i] = ok ? len[item] : 0;
+  }
+  int woff[NW], wlen[NW];                              // the items this warp runs the gate phase for
+#pragma unroll
+  for (int i = 0; i < NW; i++) {
+    const int g = warp + 8 * i, item = group * G + g;
+    const bool ok = g < G && item < B;
+    woff[i] = ok ? off[item] : 0;
+    wlen[i] = ok ? len[item] : 0;
   }
   // global gate rows of this thread's row pair (same gate block: 2rp and 2rp+1 never straddle 32);
   // local row rl = gate*32 + j  <->  W_hh row gate*256 + r*32 + j
@@ -739,21 +768,26 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
       w1[kk] = make_float2(a.y, b2.y);
     }
   }
-  float c = 0.f;                                         // cell state of (item tid>>5, unit tid&31)
-  float2 xpn[G];
+  float c[NW];                                           // cell state of (item warp + 8i, unit lane)
 #pragma unroll
-  for (int g = 0; g < G; g++) {
-    xpn[g] = make_float2(0.f, 0.f);
-    if ((g & 3) == q && ilen[g] > 0) {
-      const int t = dir == 0 ? 0 : ilen[g] - 1;
-      xpn[g] = *reinterpret_cast<const float2*>(xproj + (size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow0);
+  for (int i = 0; i < NW; i++) c[i] = 0.f;
+  const float* const xrow = xproj + dir * 1024 + grow0;
+  float2 xpn[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; i++) {
+    xpn[i] = make_float2(0.f, 0.f);
+    if (qlen[i] > 0) {
+      const int t = dir == 0 ? 0 : qlen[i] - 1;
+      xpn[i] = *reinterpret_cast<const float2*>(xrow + (size_t)(qoff[i] + t) * 2048);
     }
   }
   cluster.sync();
-
+  LT_DECL
   for (int s = 0; s < maxN; s++) {
     const uint32_t bcur = (s & 1) ? bar1 : bar0;
+    LT(3)
     if (s > 0) lstm_mbar_wait(bcur, (uint32_t)((s - 1) >> 1) & 1u);   // h_s complete in hbuf[s&1]
+    LT(0)
     // re-arm this buffer's barrier for its next use (h_{s+2}); no slice of h_{s+2} can be complete before
     // this CTA has sent h_{s+1}, and early bytes only drive the (signed) tx-count of the new phase
     if (tid == 0 && s + 2 < maxN)
@@ -761,14 +795,14 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
     const float* hc = hbuf + (s & 1) * G * kHItem;
     float* hn_local = hbuf + ((s + 1) & 1) * G * kHItem;
     // input projections were fetched one step ahead (xpn); fetch the next step's now so that the global
-    // latency hides behind a whole step.  Lane quarter q finishes the items g with (g & 3) == q.
-    float2 xp[G];
+    // latency hides behind a whole step
+    float2 xp[NQ];
 #pragma unroll
-    for (int g = 0; g < G; g++) {
-      xp[g] = xpn[g];
-      if ((g & 3) == q && s + 1 < ilen[g]) {
-        const int t = dir == 0 ? s + 1 : ilen[g] - 2 - s;
-        xpn[g] = *reinterpret_cast<const float2*>(xproj + (size_t)(ioff[g] + t) * 2048 + dir * 1024 + grow0);
+    for (int i = 0; i < NQ; i++) {
+      xp[i] = xpn[i];
+      if (s + 1 < qlen[i]) {
+        const int t = dir == 0 ? s + 1 : qlen[i] - 2 - s;
+        xpn[i] = *reinterpret_cast<const float2*>(xrow + (size_t)(qoff[i] + t) * 2048);
       }
     }
     float2 acc0[G], acc1[G];               // (even-k, odd-k) partial sums of the two rows
@@ -791,43 +825,48 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
       a0 += __shfl_xor_sync(0xffffffffu, a0, 8);  a1 += __shfl_xor_sync(0xffffffffu, a1, 8);
       a0 += __shfl_xor_sync(0xffffffffu, a0, 16); a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
       if ((g & 3) == q)
-        *reinterpret_cast<float2*>(gates + g * 128 + 2 * rp) = make_float2(a0 + xp[g].x, a1 + xp[g].y);
+        *reinterpret_cast<float2*>(gates + g * 128 + 2 * rp) = make_float2(a0 + xp[g >> 2].x, a1 + xp[g >> 2].y);
     }
+    LT(1)
     __syncthreads();
-    if (tid < 32 * G) {
-      const int g = tid >> 5, j = tid & 31;
-      const float* gp = gates + g * 128;
-      const float ig = 1.0f / (1.0f + expf(-gp[j]));
-      const float fg = 1.0f / (1.0f + expf(-gp[32 + j]));
-      const float gg = tanhf(gp[64 + j]);
-      const float og = 1.0f / (1.0f + expf(-gp[96 + j]));
-      c = fg * c + ig * gg;
-      const float hv = og * tanhf(c);
-      if (s < ilen[g]) {
-        const int t = dir == 0 ? s : ilen[g] - 1 - s;
-        out[(size_t)(ioff[g] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
-      }
-      // gather 4 consecutive hidden units into one lane, push 16 bytes to every CTA of the cluster
-      const float h1 = __shfl_down_sync(0xffffffffu, hv, 1);
-      const float h2 = __shfl_down_sync(0xffffffffu, hv, 2);
-      const float h3 = __shfl_down_sync(0xffffffffu, hv, 3);
-      if ((j & 3) == 0 && s + 1 < maxN) {
-        const int u = r * 32 + j;                        // hidden unit -> padded quarter layout
-        const uint32_t dst = lstm_smem_u32(hn_local + g * kHItem + (u >> 6) * kHQ + (u & 63));
-        const uint32_t bnext = (s & 1) ? bar0 : bar1;
+    LT(2)
 #pragma unroll
-        for (int d = 0; d < 8; d++) {
-          const uint32_t ra = lstm_mapa(dst, (uint32_t)d), rb = lstm_mapa(bnext, (uint32_t)d);
-          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-                       ::"r"(ra), "f"(hv), "f"(h1), "f"(h2), "f"(h3), "r"(rb) : "memory");
+    for (int i = 0; i < NW; i++) {
+      const int g = warp + 8 * i, j = lane;
+      if (g < G) {
+        const float* gp = gates + g * 128;
+        const float ig = 1.0f / (1.0f + expf(-gp[j]));
+        const float fg = 1.0f / (1.0f + expf(-gp[32 + j]));
+        const float gg = tanhf(gp[64 + j]);
+        const float og = 1.0f / (1.0f + expf(-gp[96 + j]));
+        c[i] = fg * c[i] + ig * gg;
+        const float hv = og * tanhf(c[i]);
+        if (s < wlen[i]) {
+          const int t = dir == 0 ? s : wlen[i] - 1 - s;
+          out[(size_t)(woff[i] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
+        }
+        // gather 4 consecutive hidden units into one lane, push 16 bytes to every CTA of the cluster
+        const float h1 = __shfl_down_sync(0xffffffffu, hv, 1);
+        const float h2 = __shfl_down_sync(0xffffffffu, hv, 2);
+        const float h3 = __shfl_down_sync(0xffffffffu, hv, 3);
+        if ((j & 3) == 0 && s + 1 < maxN) {
+          const int u = r * 32 + j;                        // hidden unit -> padded quarter layout
+          const uint32_t dst = lstm_smem_u32(hn_local + g * kHItem + (u >> 6) * kHQ + (u & 63));
+          const uint32_t bnext = (s & 1) ? bar0 : bar1;
+#pragma unroll
+          for (int d = 0; d < 8; d++) {
+            const uint32_t ra = lstm_mapa(dst, (uint32_t)d), rb = lstm_mapa(bnext, (uint32_t)d);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                         ::"r"(ra), "f"(hv), "f"(h1), "f"(h2), "f"(h3), "r"(rb) : "memory");
+          }
         }
       }
     }
     __syncthreads();   // gates[] is rewritten by the next step's dot loop
   }
+  LT_DUMP
   cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
-
 template <int G>
 static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                                 const int* off, const int* len, int B, cudaStream_t st) {
@@ -849,6 +888,12 @@ static void launch_lstm_cluster(const float* xproj, const float* whhT, float* ou
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  static const bool dbg = getenv("KKX_LSTM_DEBUG") != nullptr;
+  if (dbg) {
+    int ncl = -1;
+    cudaOccupancyMaxActiveClusters(&ncl, lstm_cluster_kernel<G>, &cfg);
+    fprintf(stderr, "lstm_cluster<%d>: B=%d clusters=%d max active clusters=%d\n", G, B, 2 * groups, ncl);
+  }
   KKX_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<G>, xproj, whhT, out, ldo, ocol, off, len, B));
 }
 
@@ -859,14 +904,35 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
   if (simple) {
     dim3 g(B, 2);
     lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);
-  } else if (B <= 8) {
-    launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st);    // 2B clusters <= 16
-  } else if (B <= 16) {
-    launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-  } else if (B <= 32) {
-    launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st);
   } else {
-    launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);    // 64 items -> 16 clusters
+    // smallest group size whose clusters are all co-resident: 15 clusters of 8 CTAs fit a B200
+    // (cudaOccupancyMaxActiveClusters); one cluster too many runs as a second wave and doubles the time
+    static int max_clusters[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 64) dev = 63;
+    if (max_clusters[dev] == 0) {       // depends on how the part's GPCs are populated: ask, do not assume
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(8 * 64, 2, 1);
+      cfg.blockDim = dim3(256, 1, 1);
+      cfg.dynamicSmemBytes = (size_t)(2 * 8 * kHItem + 8 * 128) * sizeof(float) + 16;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8>, &cfg) != cudaSuccess || n <= 0) { n = 15; cudaGetLastError(); }
+      max_clusters[dev] = n;
+    }
+    const int kMaxClusters = max_clusters[dev];
+    auto fits = [&](int G) { return 2 * ((B + G - 1) / G) <= kMaxClusters; };
+    if (fits(1)) launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else if (fits(2)) launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else if (fits(4)) launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else if (fits(8)) launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else if (fits(10)) launch_lstm_cluster<10>(xproj, whhT, out, ldo, ocol, off, len, B, st);   // 64 items -> 14 clusters
+    else if (fits(12)) launch_lstm_cluster<12>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);                  // several waves anyway
   }
   post_launch("lstm", st);
 }
