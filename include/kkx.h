@@ -143,6 +143,8 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *   "precision"   0 = fp32 SIMT everywhere, 1 = bf16 tensor-core (tcgen05) decoder+generator
  *   "noise_seed"  seed of the on-device Philox N(0,1) generator for the SineGen noise
  *   "max_frames"  frame budget per frame-phase group (memory control for large batches)
+ *   "max_tokens"  token budget per pass of one kkx_infer_batch call (default 40960): larger batches are run in
+ *                 several passes and concatenated, so a call may carry any number of utterances
  *   "stft_replicate" 0 = reflect edge padding (upstream STFT), 1 = replicate (conv-STFT export)
  *   "coalesce"    0/1 = off; K > 1 (<= 512) = merge up to K concurrent kkx_infer callers per step
  *   "coalesce_wait_us"  how long the caller that found the queue idle waits for company (default 0: no

@@ -38,6 +38,7 @@ struct kkx_ctx {
   std::condition_variable qcv;
   std::deque<Waiter*> queue;
   bool leader = false;
+  long long max_tokens = 40960;  // tokens per pass of one call (64 x 512-token utterances + slack)
   int coalesce_max = 0;          // 0/1 = off (reference behaviour); >1 = largest batch a leader gathers
   int coalesce_wait_us = 0;      // how long a leader waits for company before it runs
   int64_t coalesced_batches = 0, coalesced_requests = 0, coalesced_largest = 0;
@@ -171,11 +172,63 @@ static void run_staged_locked(kkx_ctx* ctx, float** host_out, size_t* cap_out, i
   *host_out = host;
   *cap_out = cap;
 }
+static void recycle_pinned(kkx_ctx* ctx, float* host, size_t cap) {
+  float* to_free = nullptr;
+  {
+    std::lock_guard<std::mutex> pl(ctx->pool_mu);
+    if (ctx->pinned_free.size() < 64 && ctx->pinned_free_floats + cap <= (size_t(1) << 28)) {
+      ctx->pinned_free.push_back({host, cap});
+      ctx->pinned_free_floats += cap;
+    } else {
+      to_free = host;
+    }
+  }
+  if (to_free) cudaFreeHost(to_free);
+}
+
+// A call may carry any number of utterances; the device working set is bounded by running at most `max_tokens`
+// tokens per pass (the token phase keeps ~75 KB per token row; the frame phase has its own budget, max_frames).
+// Utterances are independent and a batch's results do not depend on its composition, so the split is invisible
+// apart from one host-side concatenation.
 static void run_batch_locked(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
                              const float* styles, const float* speeds, float** host_out, size_t* cap_out,
                              int64_t* out_sample_offsets, int32_t* out_pred_dur) {
-  ctx->model->stage(batch, tokens, tok_offsets, styles, speeds);
-  run_staged_locked(ctx, host_out, cap_out, out_sample_offsets, out_pred_dur);
+  if (batch <= 0 || !tok_offsets) throw ArgError("batch must be >= 1");
+  const long long budget = ctx->max_tokens;
+  if (batch == 1 || (long long)tok_offsets[batch] - tok_offsets[0] <= budget) {
+    ctx->model->stage(batch, tokens, tok_offsets, styles, speeds);
+    run_staged_locked(ctx, host_out, cap_out, out_sample_offsets, out_pred_dur);
+    return;
+  }
+  if (!styles) throw ArgError("null input pointer");
+  struct Part { float* host; size_t cap; int b0, b1; };
+  std::vector<Part> parts;
+  std::vector<int64_t> soff((size_t)batch + 1, 0);
+  try {
+    for (int b0 = 0; b0 < batch;) {
+      int b1 = b0 + 1;
+      while (b1 < batch && (long long)tok_offsets[b1 + 1] - tok_offsets[b0] <= budget) b1++;
+      std::vector<int64_t> so((size_t)(b1 - b0) + 1, 0);
+      Part p{nullptr, 0, b0, b1};
+      ctx->model->stage(b1 - b0, tokens, tok_offsets + b0, styles + (size_t)b0 * 256, speeds + b0);
+      run_staged_locked(ctx, &p.host, &p.cap, so.data(),
+                        out_pred_dur ? out_pred_dur + (tok_offsets[b0] - tok_offsets[0]) : nullptr);
+      parts.push_back(p);
+      for (int i = 0; i < b1 - b0; i++) soff[b0 + i + 1] = soff[b0] + so[i + 1];
+      b0 = b1;
+    }
+    size_t cap = 0;
+    float* host = take_pinned(ctx, (size_t)soff[batch], &cap);
+    for (const Part& p : parts)
+      memcpy(host + soff[p.b0], p.host, (size_t)(soff[p.b1] - soff[p.b0]) * sizeof(float));
+    for (const Part& p : parts) recycle_pinned(ctx, p.host, p.cap);
+    if (out_sample_offsets) memcpy(out_sample_offsets, soff.data(), soff.size() * sizeof(int64_t));
+    *host_out = host;
+    *cap_out = cap;
+  } catch (...) {
+    for (const Part& p : parts) cudaFreeHost(p.host);
+    throw;
+  }
 }
 
 KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, const int32_t* tok_offsets,
@@ -491,6 +544,7 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "noise_seed") o.noise_seed = (unsigned long long)value;
     else if (k == "max_frames") { if (value < 1) throw ArgError("max_frames must be >= 1"); o.max_frames = (int)value; }
     else if (k == "stft_replicate") o.stft_replicate = value ? 1 : 0;
+    else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {
       if (value < 0 || value > kMaxCoalesce) throw ArgError("coalesce must be in 0..512");
       std::lock_guard<std::mutex> ql(ctx->qmu);

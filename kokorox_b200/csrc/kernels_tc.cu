@@ -853,7 +853,16 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
     static const bool bn64 = [] { const char* e = getenv("KKX_TC_BN64"); return e && e[0] == '1'; }();
     static const bool persist = [] { const char* e = getenv("KKX_TC_PERSIST"); return !e || e[0] != '0'; }();
-    if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) launch_gemm32p(a, st);
+    // Small problems (one utterance): fewer 128-wide tiles than SMs -> 64-wide single-tile CTAs fill twice as many
+    // SMs and shorten the latency-bound launch (B=1, 510 tokens: 3.4 -> 2.8 ms over the 74 GEMMs of a step).  The
+    // per-element accumulation order is the same in both kernels, so results do not depend on the choice.
+    static const int nsm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    const long long tiles128 = (long long)(a.ntiles_m > 0 ? a.ntiles_m : (a.sum_m + 127) / 128) * ((a.Co + 127) / 128);
+    const bool small = tiles128 < nsm && a.tmB_c && a.tmB2_c && a.cluster < 2;
+    if (a.Co > 64 && small) {
+      TcConvArgs b = a; b.tmB = a.tmB_c; b.tmB2 = a.tmB2_c;
+      launch_tc<64, 4, 1>(b, st);
+    } else if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) launch_gemm32p(a, st);
     else if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);
     else if (a.Co > 64 && !(bn64 && a.tmB_c)) launch_tc<128, 3, 1>(a, st);
     else if (a.Co > 64) {   // experiment: 64-wide tiles (4 stages of 48 KB) with the half-height weight boxes

@@ -361,3 +361,28 @@ def test_concurrent_callers_are_coalesced_into_one_batch(model):
         model.set_option("coalesce", 0)
         model.set_option("coalesce_wait_us", 0)
         model.set_option("precision", 0)
+
+
+def test_oversized_batch_runs_in_passes(model):
+    # a call may carry more tokens than one pass holds ("max_tokens"): the library runs several passes and
+    # concatenates; every waveform, offset and duration must equal the single-pass result bit for bit
+    rng = np.random.default_rng(21)
+    B = 14
+    cases = [synth_case(int(n), 8000 + i, 8100 + i) for i, n in enumerate(rng.integers(20, 200, size=B))]
+    speeds = rng.uniform(0.8, 1.3, size=B).astype(np.float32).tolist()
+    model.set_noise(None)
+    model.set_option("precision", 1)
+    try:
+        ref, rdur = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds, return_durations=True)
+        ref = [r.copy() for r in ref]
+        model.set_option("max_tokens", 512)
+        got, gdur = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds, return_durations=True)
+        assert len(got) == B
+        for b in range(B):
+            assert np.array_equal(gdur[b], rdur[b])
+            assert np.array_equal(got[b], ref[b]), f"item {b} differs when the batch is split into passes"
+        with pytest.raises(Exception):
+            model.set_option("max_tokens", 10)
+    finally:
+        model.set_option("max_tokens", 40960)
+        model.set_option("precision", 0)
