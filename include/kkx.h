@@ -53,8 +53,9 @@ KKX_API int kkx_create(const char* weights_path, int device_ordinal, kkx_ctx** o
 /* Drop of OrtKoko (koko.rs:1338-1375 `cleanup`): frees all device and pinned host memory. */
 KKX_API void kkx_destroy(kkx_ctx* ctx);
 
-/* Error string of the last failed call on this ctx (ctx == NULL: last failed kkx_create /
- * kkx_init on this thread).  The Rust shim turns rc<0 into Err(kkx_last_error()), matching
+/* Error string of the CALLING THREAD's last failed call (the ctx argument is accepted for symmetry and may be
+ * NULL): thread-local, so threads sharing one ctx never see -- or race with -- each other's messages; read it
+ * on the thread that got the error code.  The Rust shim turns rc<0 into Err(kkx_last_error()), matching
  * the Result<_, String> / Box<dyn Error> returns of ort_koko.rs:31,42. */
 KKX_API const char* kkx_last_error(const kkx_ctx* ctx);
 

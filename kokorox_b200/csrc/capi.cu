@@ -18,7 +18,6 @@ using namespace kkx;
 struct kkx_ctx {
   std::unique_ptr<Model> model;
   std::mutex mu;  // single-flight like the reference's Mutex<Session> (ort_koko.rs:14,77-78)
-  std::string err;
   // pinned result buffers; their own lock, so that kkx_release never waits for the step `mu` is held across
   std::mutex pool_mu;
   std::map<float*, size_t> pinned;       // audio buffers handed out -> capacity (floats)
@@ -62,7 +61,7 @@ static int guarded(kkx_ctx* ctx, F&& f) {
   } catch (...) { rc = KKX_ERR_CUDA; msg = "unknown error"; }
   g_launch_stats = nullptr;
   g_dry_run = false;
-  if (ctx) ctx->err = msg;
+  (void)ctx;
   g_err = msg;
   return rc;
 }
@@ -110,11 +109,14 @@ KKX_API void kkx_destroy(kkx_ctx* ctx) {
   delete ctx;
 }
 
-KKX_API const char* kkx_last_error(const kkx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+// The message of the calling thread's last failed call (any ctx).  Thread-local on purpose: with many threads
+// sharing one ctx (the reference's Arc<OrtKoko>), a per-ctx string could be rewritten by another thread while the
+// caller still reads it.
+KKX_API const char* kkx_last_error(const kkx_ctx* ctx) { (void)ctx; return g_err.c_str(); }
 
 static int check_ctx(kkx_ctx* ctx) {
   if (!ctx) { g_err = "null ctx"; return KKX_ERR_ARG; }
-  if (!ctx->model) { ctx->err = "Session is not initialized."; return KKX_ERR_STATE; }
+  if (!ctx->model) { g_err = "Session is not initialized."; return KKX_ERR_STATE; }
   return KKX_OK;
 }
 
@@ -307,7 +309,7 @@ static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& b
       ctx->coalesced_batches++;
       ctx->coalesced_requests++;
     } else {
-      w.err = ctx->err;
+      w.err = g_err;      // guarded() left the message in this (the leader's) thread
     }
   }
 }
@@ -461,7 +463,7 @@ KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, con
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {
   if (out_samples) *out_samples = 0;
   if (ctx && ctx->model && ctx->coalesce_max > 1) {
-    if (out_audio) *out_audio = nullptr; else { g_err = ctx->err = "out_audio is null"; return KKX_ERR_ARG; }
+    if (out_audio) *out_audio = nullptr; else { g_err = "out_audio is null"; return KKX_ERR_ARG; }
     kkx_ctx::Waiter w{tokens, n_tokens, style256, speed, out_pred_dur};
     const int rc = infer_coalesced(ctx, w);
     if (rc == KKX_OK) { *out_audio = w.audio; if (out_samples) *out_samples = w.samples; }
@@ -633,7 +635,7 @@ KKX_API int64_t kkx_debug_stage(kkx_ctx* ctx, const char* name, int32_t item, fl
   if (check_ctx(ctx) || !name) return -1;
   std::lock_guard<std::mutex> lk(ctx->mu);
   const DebugStage* s = ctx->model->debug_stage(name, item);
-  if (!s) { ctx->err = std::string("no such debug stage: ") + name; return -1; }
+  if (!s) { g_err = std::string("no such debug stage: ") + name; return -1; }
   if (rows) *rows = s->rows;
   if (cols) *cols = s->cols;
   const int64_t n = (int64_t)s->data.size();
