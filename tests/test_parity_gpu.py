@@ -386,3 +386,27 @@ def test_oversized_batch_runs_in_passes(model):
     finally:
         model.set_option("max_tokens", 40960)
         model.set_option("precision", 0)
+
+
+def test_two_sessions_run_concurrently(model, weights_path):
+    # one process may hold several sessions (one per GPU, or en + zh models on one GPU: koko.rs TTSManager); two
+    # threads driving two sessions at the same time must each get exactly what they get alone
+    from kokorox_b200.onn import B200Koko
+    other = B200Koko.new(weights_path)
+    try:
+        cases = [synth_case(60 + 7 * i, 9000 + i, 9100 + i) for i in range(6)]
+        for m in (model, other):
+            m.set_noise(None)
+            m.set_option("precision", 1)
+        alone = [model.infer_one(c[0], c[1], 1.0) .copy() for c in cases]
+
+        def work(i):
+            m = model if i % 2 == 0 else other
+            return [m.infer_one(c[0], c[1], 1.0).copy() for c in cases]
+        res, errs = _run_threads(work, 2)
+        assert all(e is None for e in errs), errs
+        for r in res:
+            assert all(np.array_equal(a, b) for a, b in zip(r, alone))
+    finally:
+        other.close()
+        model.set_option("precision", 0)
