@@ -414,6 +414,16 @@ __device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5
 // CPU reference evaluates it -- src = fma(1/300, n+0.5, -0.5) clamped at 0, lambda = src - i0,
 // value = fma(p[i0], 1-lambda, p[i1]*lambda) -- then sin, *0.1, uv gating, noise, Linear(9->1),
 // tanh.
+// sin of a harmonic phase that reaches 1e5..1e6 rad late in an utterance.  libm's sinf leaves its fast path
+// above ~1e5 rad (Payne-Hanek reduction, divergent: most of this kernel's time); here the argument is reduced in
+// fp64 (turns = ph / 2pi, exact to ~1e-11 of a turn) and sinpif evaluates the reduced angle.  Error vs the exact
+// sin(ph): <= 2e-7 absolute (the fp32 rounding of the reduced angle).
+__device__ __forceinline__ float sin_reduced(float ph) {
+  const double t = (double)ph * 0.15915494309189535;
+  const double fr = t - rint(t);
+  return sinpif((float)(2.0 * fr));
+}
+
 __global__ void __launch_bounds__(256) sine_source_kernel(
     const float* __restrict__ f0, const int* f0_off, const int* f0_len,
     const float* __restrict__ phase, const int* ph_off, const float* __restrict__ noise,
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(256) sine_source_kernel(
   for (int h = 0; h < 9; h++) {
     const float p0 = pp[(size_t)h * L + i0], p1 = pp[(size_t)h * L + i1];
     const float ph = __fmaf_rn(p0, w0, __fmul_rn(p1, lam));
-    const float sw = __fmul_rn(sinf(ph), 0.1f);
+    const float sw = __fmul_rn(sin_reduced(ph), 0.1f);
     const float v = __fadd_rn(__fmul_rn(sw, uv), __fmul_rn(namp, nz[h]));
     acc = fmaf(lin_w[h], v, acc);
   }
