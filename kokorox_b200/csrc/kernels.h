@@ -100,6 +100,9 @@ struct ArbConvArgs {
   const float* res = nullptr; float oscale = 1.f; int accumulate = 0;
   float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
   long long* timing = nullptr;                         // diagnostics (-DKKX_ARB_TIMING builds): per-role phase cycle counters
+  // "post" variant (generator conv_post): operand transform = LeakyReLU(slope) instead of AdaIN + Snake, weights
+  // zero-padded to C output channels, fp32 output [rows, ldo] of the first `cout` channels, no statistics
+  int post = 0, cout = 0, ldo = 0; float slope = 0.f;
 };
 int arb_tile_rows(int C, int ks);   // rows per persistent-kernel tile for this shape (128, 256 or 512)
 bool arb_conv_supported(int C, int ks, int dil, int B);

@@ -99,9 +99,14 @@ struct TileCur {
 // The two roles are separate instantiations so that each carries only its own epilogue / producer code:
 // with 16 warps in four different roles the hot code of all roles has to stay inside the instruction cache
 // (an earlier, more generic version of this kernel lost ~40 % of its time to instruction-fetch stalls).
-template <int BN, int MSUB, bool CONV2, bool T>
+// POST (generator conv_post, 128 -> 22 channels, k = 7): the same pipeline with LeakyReLU as the operand transform,
+// the weight set zero-padded to 128 output channels and an fp32 [rows, ldo] store of the first `cout` channels.
+// The generic path re-fetched the activation tile for each of the 7 taps and needed a separate LeakyReLU -> bf16
+// pass over the 4.7 GB stage output.
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
   static_assert(!T || (BN == 128 && (MSUB == 2 || MSUB == 4)), "transposed mode: C = 128, 256- or 512-row tiles");
+  static_assert(!POST || (T && !CONV2 && MSUB == 2), "post variant: transposed accumulator, fp32 input");
   // T with MSUB = 4 (k >= 7): 512-row tiles, i.e. TWO 128x256 MMAs per weight tile.  The k = 7 / 11 convs are
   // bound by what an SM can ingest from L2 (the weight set is re-streamed for every tile: 352 KB per tile at
   // k = 11); doubling the rows per weight tile halves that.  The two accumulators fill TMEM, so the epilogue
@@ -340,6 +345,14 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
               if (FULL || j < left) op[j * 128] = o.x;
               if (FULL || j + 1 < left) op[(j + 1) * 128] = o.y;
             }
+          }
+        } else if (POST) {
+          // fp32 [rows, ldo] store of the real output channels (co < cout: 88 contiguous bytes per row for 22)
+          if (co < a.cout) {
+            float* op = a.out_f32 + (size_t)(off + row) * a.ldo + co;
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (FULL || j < left) op[(size_t)j * a.ldo] = __uint_as_float(v[j]) + bias_c;
           }
         } else {
           // bf16 output: lanes 2i / 2i+1 exchange so that each lane stores one 4-byte word (two channels):
@@ -594,7 +607,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       const int b = sc_.b;
       const int sa = gA % NA;
       if (s_g == 0) {
-        if (b != coef_b) {   // new item: rebuild the coefficient table (all producer threads take this branch together)
+        if (!POST && b != coef_b) {   // new item: rebuild the coefficient table (all producer threads take this branch together)
           asm volatile("bar.sync 3, %0;" ::"n"(kProdThreads) : "memory");
           for (int ch = pt; ch < BN; ch += kProdThreads) {
             const float al = a.alpha[ch], s = a.scale[(size_t)b * BN + ch], h = a.shift[(size_t)b * BN + ch];
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
         }
         const float* cp = coef + s_c * 64 + cg * 8;
 #pragma unroll
-        for (int e = 0; e < 4; e += 2) {
+        for (int e = 0; !POST && e < 4; e += 2) {
           const float4 t0 = *reinterpret_cast<const float4*>(cp + 2 * e);
           const float4 t1 = *reinterpret_cast<const float4*>(cp + BN + 2 * e);
           const float4 t2 = *reinterpret_cast<const float4*>(cp + 2 * BN + 2 * e);
@@ -641,6 +654,11 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
         uint32_t pw[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {   // packed fp32 math around the two scalar MUFU.SIN
+          if (POST) {      // LeakyReLU: max(x, slope * x) for 0 < slope < 1
+            const float2 lx = __fmul2_rn(xv[e], make_float2(a.slope, a.slope));
+            pw[e] = pack_bf16(fmaxf(xv[e].x, lx.x), fmaxf(xv[e].y, lx.y)) & inmask;
+            continue;
+          }
           const float2 u = __ffma2_rn(xv[e], cA[e], cB[e]);
           const float2 sn = make_float2(__sinf(u.x), __sinf(u.y));
           const float2 y = __fmul2_rn(__ffma2_rn(sn, sn, u), cI[e]);
@@ -685,7 +703,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   }
 }
 
-template <int BN, int MSUB, bool CONV2, bool T>
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   using Cfg = ArbCfg<BN, MSUB, T>;
   static bool attr_set[64] = {false};
@@ -693,13 +711,13 @@ void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     attr_set[dev] = true;
   }
   const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
-  arb_conv_kernel<BN, MSUB, CONV2, T><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  arb_conv_kernel<BN, MSUB, CONV2, T, POST><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 }  // namespace
@@ -725,6 +743,15 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
   if (g_dry_run) return;
   if (a.total_tiles <= 0 || a.B <= 0) return;
   if (!arb_conv_supported(a.C, a.ks, a.dil, a.B)) throw ArgError("launch_arb_conv: unsupported shape");
+  if (a.post) {
+    if (a.C != 128 || a.in_bf16 || !a.out_f32 || a.out_bf16 || a.res || a.accumulate || a.part || a.cout < 1 || a.cout > 128 ||
+        a.ldo < a.cout || !(a.slope > 0.f && a.slope < 1.f))
+      throw ArgError("launch_arb_conv: unsupported post-conv arguments");
+    if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.C * a.cout * a.ks;
+    launch_arb_t<128, 2, false, true, true>(a, st);
+    post_launch("post_conv", st);
+    return;
+  }
   // two roles: fp32 in -> bf16 out (+statistics), or bf16 in + fp32 residual -> fp32 out
   if (a.in_bf16 ? (!a.out_f32 || a.out_bf16 || !a.res) : (!a.out_bf16 || a.out_f32 || a.res || a.accumulate))
     throw ArgError("launch_arb_conv: unsupported input/output combination");

@@ -388,6 +388,14 @@ void Model::load_weights(const WeightFile& wf) {
   UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1, W.tups1); W.ups1_b = U(G + "ups.1.bias");
   W.post_w = CW(G + "conv_post.weight", 22, 128, 7); W.post_b = U(G + "conv_post.bias");
   W.t_post = make_tc(convCoKsCi(wf, G + "conv_post.weight", 22, 128, 7), 22, 7, 128);
+  {
+    std::vector<float> wp = convCoKsCi(wf, G + "conv_post.weight", 22, 128, 7);
+    wp.resize((size_t)128 * 7 * 128, 0.f);                 // rows 22..127 are zero
+    W.t_post_arb = make_tc(wp, 128, 7, 128);
+    std::vector<float> b128 = raw(wf, G + "conv_post.bias");
+    b128.resize(128, 0.f);
+    W.post_b128 = up(b128);
+  }
   W.t_nc1 = make_tc(convCoKsCi(wf, G + "noise_convs.1.weight", 128, 22, 1), 128, 1, 22);
   // noise_convs[0] as a 1-tap GEMM over the im2col operand: K index = tap*22 + c
   W.t_nc0 = make_tc(convCoKsCi(wf, G + "noise_convs.0.weight", 256, 22, 12), 256, 1, 12 * 22);

@@ -86,6 +86,7 @@ struct Weights {
   std::vector<TcW> tups0, tups1;   // per-phase bf16 [Co][2][Ci]
   TcW t_post, t_nc0, t_nc1, t_asr; // conv_post, noise_convs (nc0 as an im2col GEMM, K = 12*22), asr_res
   float *ups0_b, *ups1_b, *post_w, *post_b;
+  TcW t_post_arb; float* post_b128 = nullptr;   // conv_post zero-padded to 128 output channels for the fused kernel
   // style FC tables (all AdaIN / AdaLN fcs of one style half concatenated)
   float *sty_pro_w, *sty_pro_b, *sty_dec_w, *sty_dec_b;
   int sty_pro_n = 0, sty_dec_n = 0;

@@ -640,7 +640,16 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
 
   // ---- head (K11)
   float* cp = A.alloc<float>((size_t)G120.rows * 24);
-  if (opt.precision == 1) {
+  static const bool post_fused = [] { const char* e = getenv("KKX_POST_FUSED"); return !e || e[0] != '0'; }();
+  if (opt.precision == 1 && post_fused && arb_conv_supported(128, 7, 1, B)) {
+    // fused: LeakyReLU in the operand producer, all 7 taps from one activation tile (kernels_arb.cu, POST)
+    ArbConvArgs pc;
+    pc.C = 128; pc.ks = 7; pc.dil = 1; pc.pad = 3; pc.off = G120.d_off; pc.len = G120.d_len; pc.B = B;
+    pc.sum_m = G120.sum_len; pc.tile_start = G120.d_tiles256; pc.total_tiles = G120.ntiles256;
+    pc.x = acc1; pc.in_bf16 = 0; pc.tmB = W.t_post_arb.tmap; pc.bias = W.post_b128;
+    pc.out_f32 = cp; pc.post = 1; pc.cout = 22; pc.ldo = 24; pc.slope = 0.01f;
+    launch_arb_conv(pc, st);
+  } else if (opt.precision == 1) {
     void* pb = A.alloc_bytes((size_t)G120.rows * 128 * 2);
     launch_apply_bf16(acc1, 128, 128, nullptr, nullptr, ACT_LRELU, 0.01f, nullptr, pb, 128, G120.rows, G120.d_off,
                       G120.d_len, B, G120.max_len, st);
