@@ -579,11 +579,12 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
   __shared__ float fr[NF][20];             // windowed time frames
   // twiddles / window in shared memory: the lookups below are indexed per lane (j varies across a
   // warp), which would serialise on the constant cache
-  __shared__ float s_cos[20], s_sin[20], s_win[20];
-  if (threadIdx.x < 20) {
-    s_cos[threadIdx.x] = c_cos20[threadIdx.x];
-    s_sin[threadIdx.x] = c_sin20[threadIdx.x];
-    s_win[threadIdx.x] = c_hann20[threadIdx.x];
+  __shared__ float s_win[20];
+  __shared__ float2 s_tw[10][20];          // (cos, sin)(2 pi j k / 20) as [k][j]: no integer modulo in the inner loop,
+  if (threadIdx.x < 20) s_win[threadIdx.x] = c_hann20[threadIdx.x];   // and lanes (j) hit consecutive banks
+  if (threadIdx.x < 200) {
+    const int k = threadIdx.x / 20, j = threadIdx.x - k * 20, m = (j * k) % 20;
+    s_tw[k][j] = make_float2(c_cos20[m], c_sin20[m]);
   }
   const int b = blockIdx.y;
   const int F = h_len[b];
@@ -614,8 +615,8 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
     float acc = sp[0] + ((j & 1) ? -sp[10] : sp[10]);   // bins 0 and 10: real part only
 #pragma unroll
     for (int k = 1; k < 10; k++) {
-      const int m = (j * k) % 20;
-      acc += 2.0f * (sp[k] * s_cos[m] - sp[11 + k] * s_sin[m]);
+      const float2 tw = s_tw[k][j];
+      acc += 2.0f * (sp[k] * tw.x - sp[11 + k] * tw.y);
     }
     fr[lf][j] = acc * (1.0f / 20.0f) * s_win[j];
   }
@@ -625,15 +626,17 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp
   for (int i = threadIdx.x; i < FR * 5; i += 256) {
     const long long n = (long long)f0 * 5 + i;
     if (n >= S) break;
-    const long long p = n + 10;
-    const int fhi = (int)(p / 5);
+    // p = n + 10 = 5 * f0 + (i + 10): frame and in-frame position from the small local index (32-bit math)
+    const int pl = i + 10;
+    const int fl = pl / 5;                 // fhi - f0
+    const int j0 = pl - fl * 5;            // position inside frame fhi
     float acc = 0.f, env = 0.f;
 #pragma unroll
     for (int d = 0; d < 4; d++) {
-      const int f = fhi - d;
+      const int f = f0 + fl - d;
       if (f < 0 || f >= F) continue;
-      const int j = (int)(p - (long long)f * 5);
-      acc += fr[f - (f0 - HALO)][j];
+      const int j = j0 + 5 * d;
+      acc += fr[fl - d + HALO][j];
       env += s_win[j] * s_win[j];
     }
     const float smp = acc / env;
