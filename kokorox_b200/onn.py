@@ -225,8 +225,10 @@ class B200Koko:
         """ort_koko.rs:37-91.  tokens [B][N] (rectangular, incl. the 0 pads), styles [B][256],
         one speed.  Returns the waveform(s) as one flat f32 array -- the caller flattens the
         reference's output the same way (koko.rs:1179)."""
+        if len(tokens) == 1:      # the only shape the reference sends (koko.rs:1175): the coalescable entry point
+            return self.infer_one(tokens[0], np.asarray(styles, dtype=np.float32).reshape(-1), speed)
         outs = self.infer_batch([list(t) for t in tokens], styles, [speed] * len(tokens))
-        return outs[0] if len(outs) == 1 else np.concatenate(outs)
+        return np.concatenate(outs)
 
     def infer_one(self, tokens: Sequence[int], style, speed: float = 1.0, return_durations: bool = False):
         """One utterance through ``kkx_infer`` -- the call a server thread makes per request.  Safe to call from
