@@ -335,7 +335,11 @@ static int infer_coalesced(kkx_ctx* ctx, kkx_ctx::Waiter& w) {
       ctx->queue.pop_front();
     }
     ql.unlock();
-    serve_coalesced(ctx, batch);
+    try {
+      serve_coalesced(ctx, batch);
+    } catch (...) {   // (allocation failure outside guarded()): fail the batch, never leave the queue without a leader
+      for (auto* b : batch) { b->rc = KKX_ERR_CUDA; b->err = "internal error while serving a coalesced batch"; b->audio = nullptr; }
+    }
     ql.lock();
     for (auto* b : batch) b->done = true;
     ctx->leader = false;
