@@ -107,3 +107,54 @@ def test_output_containers_match_the_reference_encoders():
     h = wav_header(None, 24000, 1)
     assert h == (b"RIFF" + b"\xff" * 4 + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 24000, 24000 * 4, 4, 32) +
                  b"data" + b"\xff" * 4)
+
+
+@pytest.mark.parametrize("header", ["kkx.h", "kkx_test.h"])
+def test_headers_are_plain_c(header):
+    # the boundary is bound from Rust FFI / cgo / ctypes: the headers must be valid C99 (and C++11) on their own
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    for comp, lang, std in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++11")):
+        if not shutil.which(comp):
+            continue
+        r = subprocess.run([comp, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, "-x", lang, "-"],
+                           input=f'#include "{header}"\n', text=True, capture_output=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_c_program_links_against_the_library(lib, tmp_path):
+    # a C translation unit that uses only include/kkx.h builds and links against libkkx.so, calls the host-side
+    # entry points and gets the documented "no device / bad argument" codes (no compute without a GPU)
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    from kokorox_b200 import build
+    so = build.build()
+    src = tmp_path / "t.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "kkx.h"
+int main(void) {
+  unsigned char h[44];
+  char b64[128];
+  int16_t pcm[3] = {0, 1, -1};
+  if (kkx_wav_header_pcm16(h, 3, 24000) != 44 || memcmp(h, "RIFF", 4) != 0) return 1;
+  if (kkx_wav_header_f32_stream(h, 1, 24000) != 44 || h[20] != 3) return 2;
+  if (kkx_encode_wav16_base64(pcm, 3, 24000, NULL, 0) != 68) return 3;          /* (44 + 6 + 2) / 3 * 4 */
+  if (kkx_encode_wav16_base64(pcm, 3, 24000, b64, sizeof b64) != 68 || strlen(b64) != 68) return 4;
+  if (kkx_infer(NULL, NULL, 0, NULL, 1.0f, NULL, NULL, NULL) >= 0) return 5;     /* null ctx -> error code */
+  printf("%s\n", kkx_version());
+  return 0;
+}
+""")
+    exe = tmp_path / "t"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        so, "-Wl,-rpath," + os.path.dirname(so)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("kkx "), (r.returncode, r.stdout, r.stderr)
