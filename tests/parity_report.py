@@ -1,6 +1,6 @@
 """Stage-by-stage parity report: CUDA path (through the C ABI) vs the CPU oracle.
 
-Run on the GPU box:  python tools/parity_report.py [--tokens 50] [--seed 0] [--precision 0]
+Run on the GPU box:  python tests/parity_report.py [--tokens 50] [--seed 0] [--precision 0]
 Prints one line per stage (max-abs error, relative L2) and the duration / waveform verdicts.
 """
 import argparse
