@@ -36,3 +36,51 @@ def reduce_step(step_seconds: float, work: Sequence[float], device=None) -> Tupl
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(w, op=dist.ReduceOp.SUM)
     return float(t.item()), [float(x) for x in w.tolist()]
+
+
+class LeastLoadedRouter:
+    """Online counterpart of ``shard_requests`` for a server process that owns one session per GPU (SURVEY.md 8e:
+    "route requests/chunks to GPUs by least outstanding audio-frames").  ``sessions`` are objects with
+    ``infer_one(tokens, style, speed)`` (``B200Koko``); the estimate of a request's work is its token count, which
+    is what the frame count is proportional to before the durations are known.  Thread-safe: the server's request
+    threads call ``infer_one`` concurrently; with ``set_option("coalesce", K)`` on each session the callers routed
+    to one GPU leave as ragged batches.  Chunks of one text must be re-concatenated by the caller in submission
+    order (koko.rs:1179) -- the router does not reorder, it only picks the device."""
+
+    def __init__(self, sessions):
+        import threading
+        if not sessions:
+            raise ValueError("LeastLoadedRouter needs at least one session")
+        self._sessions = list(sessions)
+        self._load = [0] * len(self._sessions)
+        self._served = [0] * len(self._sessions)
+        self._lock = threading.Lock()
+
+    def pick(self, cost: int) -> int:
+        with self._lock:
+            r = min(range(len(self._load)), key=lambda i: (self._load[i], i))
+            self._load[r] += cost
+            return r
+
+    def done(self, r: int, cost: int) -> None:
+        with self._lock:
+            self._load[r] -= cost
+            self._served[r] += 1
+
+    def infer_one(self, tokens, style, speed: float = 1.0):
+        cost = max(len(tokens), 1)
+        r = self.pick(cost)
+        try:
+            return self._sessions[r].infer_one(tokens, style, speed)
+        finally:
+            self.done(r, cost)
+
+    @property
+    def outstanding(self):
+        with self._lock:
+            return list(self._load)
+
+    @property
+    def served(self):
+        with self._lock:
+            return list(self._served)

@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -68,3 +69,53 @@ def test_two_rank_reduction_gloo():
 
 def test_reduce_step_single_process():
     assert reduce_step(1.5, [2.0, 3.0]) == (1.5, [2.0, 3.0])
+
+
+def test_least_loaded_router_balances_concurrent_requests():
+    # online routing by least outstanding work, one session per GPU, request threads in one process
+    import threading
+    import time
+    from kokorox_b200.sharding import LeastLoadedRouter
+
+    class FakeSession:
+        def __init__(self):
+            self.calls, self.active, self.peak = [], 0, 0
+            self.lock = threading.Lock()
+
+        def infer_one(self, tokens, style, speed):
+            with self.lock:
+                self.active += 1
+                self.peak = max(self.peak, self.active)
+            time.sleep(0.0005 * len(tokens))          # "GPU time" proportional to the token count
+            with self.lock:
+                self.active -= 1
+                self.calls.append(len(tokens))
+            return len(tokens)
+
+    sessions = [FakeSession() for _ in range(4)]
+    router = LeastLoadedRouter(sessions)
+    rng = np.random.default_rng(0)
+    lens = rng.integers(10, 200, size=64)
+    out = [None] * len(lens)
+
+    def client(i):
+        out[i] = router.infer_one([0] * int(lens[i]), None, 1.0)
+    threads = [threading.Thread(target=client, args=(i,)) for i in range(len(lens))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert out == [int(n) for n in lens]                      # every caller got its own result
+    assert router.outstanding == [0, 0, 0, 0] and sum(router.served) == len(lens)
+    work = [sum(s.calls) for s in sessions]
+    assert min(work) > 0.6 * max(work), work                 # token work spread over the four devices
+    with pytest.raises(ValueError):
+        LeastLoadedRouter([])
+    # a failing session releases its load
+    class Boom:
+        def infer_one(self, *a):
+            raise RuntimeError("x")
+    r2 = LeastLoadedRouter([Boom()])
+    with pytest.raises(RuntimeError):
+        r2.infer_one([0, 1, 0], None, 1.0)
+    assert r2.outstanding == [0]
