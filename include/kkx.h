@@ -30,11 +30,12 @@ typedef struct kkx_ctx kkx_ctx;
 #endif
 
 #define KKX_OK 0
-#define KKX_ERR_ARG (-1)      /* bad argument (null pointer, token id out of 0..177, n_tokens > 512) */
-#define KKX_ERR_IO (-2)       /* weight file missing / malformed / tensor missing              */
+#define KKX_ERR_ARG (-1)      /* bad argument (null pointer, token id out of 0..177, n_tokens > 512, speed outside [0.1, 10]) */
+#define KKX_ERR_IO (-2)       /* model file missing / malformed / tensor missing or unresolved  */
 #define KKX_ERR_CUDA (-3)     /* CUDA runtime error (message has the cudaError string)          */
 #define KKX_ERR_NO_DEVICE (-4)/* no CUDA device / device ordinal out of range -- there is NO CPU fallback */
-#define KKX_ERR_STATE (-5)    /* ctx not initialised ("Session is not initialized.", ort_koko.rs:88-90) */
+#define KKX_ERR_STATE (-5)    /* ctx not initialised ("Session is not initialized.", ort_koko.rs:88-90), or a call
+                               * out of sequence (run before stage, fetch before run, ticket of a destroyed ctx) */
 
 #define KKX_STYLE_DIM 256     /* ort_koko.rs:61-65: style tensor [B,256]                        */
 #define KKX_MAX_TOKENS 512    /* ALBERT max_position_embeddings; koko.rs:781-783 chunks to <=500 */
@@ -46,9 +47,21 @@ typedef struct kkx_ctx kkx_ctx;
 KKX_API int kkx_init(void);
 
 /* Replaces OrtKoko::new(model_path) -> OrtBase::load_model (ort_koko.rs:31-35,
- * ort_base.rs:14-39): loads a KKXW weight file onto GPU `device_ordinal` and builds every
- * derived weight layout.  On failure *out is NULL and kkx_last_error(NULL) has the reason. */
+ * ort_base.rs:14-39, `commit_from_file(model_path)`): loads the model file onto GPU `device_ordinal` and builds
+ * every derived weight layout.  `weights_path` is what the reference passes -- the downloaded ONNX file
+ * (kokoro-v1.0.onnx, onnx/model.onnx or one of the fp16 / q8 / uint8 / q4 variants of hf_cache.rs:135-144; the
+ * initialisers are read straight from the protobuf, named through the node graph and dequantised at load) -- or a
+ * KKXW file written by kokorox_b200/weightfile.py / convert.py.  The format is detected from the file's magic.
+ * Sessions created from the same (file, device) share one device-resident weight set (the reference's servers hold
+ * two or three sessions of one model, koko main.rs:1477,1596).  A new session runs the benchmarked configuration
+ * ("precision" = 1, see kkx_set_option).  On failure *out is NULL and kkx_last_error(NULL) has the reason; for an
+ * ONNX file that does not resolve it lists the tensors that could not be found. */
 KKX_API int kkx_create(const char* weights_path, int device_ordinal, kkx_ctx** out);
+
+/* Host-only helper (no GPU needed): reads `src_path` exactly as kkx_create would (ONNX or KKXW) and writes the
+ * recovered Kokoro-82M state dict as a KKXW file, e.g. to convert a downloaded model_q8f16.onnx once.
+ * *out_tensors (nullable) receives the tensor count. */
+KKX_API int kkx_convert_model_file(const char* src_path, const char* dst_kkxw_path, int32_t* out_tensors);
 
 /* Drop of OrtKoko (koko.rs:1338-1375 `cleanup`): frees all device and pinned host memory. */
 KKX_API void kkx_destroy(kkx_ctx* ctx);
@@ -64,7 +77,7 @@ KKX_API const char* kkx_last_error(const kkx_ctx* ctx);
  *   tokens     [n_tokens] i64, INCLUDING the leading and trailing 0 pad (koko.rs:1168-1173);
  *              2 <= n_tokens <= 512, ids in 0..177 (tts/vocab.rs:5-20)   -- "input_ids"
  *   style256   [256] f32 (koko.rs:1255-1306 mix_styles row)             -- "style"
- *   speed      > 0                                                        -- "speed"
+ *   speed      in [0.1, 10] (durations are 50/speed frames per token at most) -- "speed"
  *   out_audio  receives a library-owned pinned host buffer of *out_samples f32 (24 kHz mono,
  *              = 600 * sum(pred_dur)); valid until kkx_release(ctx, ptr) -- outputs[0]
  *   out_pred_dur  nullable; [n_tokens] predicted integer frame durations (not observable
@@ -87,8 +100,26 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
                     const float* styles, const float* speeds, float** out_audio,
                     int64_t* out_sample_offsets, int32_t* out_pred_dur);
 
-/* Returns an audio buffer obtained from kkx_infer / kkx_infer_batch to the library. */
+/* Returns an audio buffer obtained from kkx_infer / kkx_infer_batch / kkx_wait to the library. */
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
+/* ---- asynchronous form of kkx_infer.  The reference's WebSocket server synthesises and sends
+ * sentence by sentence, `for sentence ... { synthesize_and_send_chunk(...).await }` (kokorox-websocket/src/lib.rs:
+ * 371-376), so sentence k+1 cannot start while k is on the wire, and its servers block one thread per request on
+ * Mutex<Session> (openai lib.rs:400-412, ort_koko.rs:77).
+ *   kkx_submit  copies the request (the caller's buffers are free again on return), queues it and returns a
+ *               ticket at once; a worker thread owned by the ctx runs whatever is queued as ragged batches of up
+ *               to "async_batch" utterances (each result is bit-identical to the caller's own kkx_infer).
+ *   kkx_poll    1 = finished (kkx_wait will not block), 0 = still queued / running, <0 = unknown ticket.
+ *   kkx_wait    blocks until the request has finished and redeems the ticket (once): same outputs as kkx_infer;
+ *               out_pred_dur (nullable) must hold n_tokens entries.  A failed request returns its own error code
+ *               and message here.  Release the audio with kkx_release. */
+typedef int64_t kkx_ticket;
+KKX_API int kkx_submit(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256, float speed,
+                       kkx_ticket* out_ticket);
+KKX_API int kkx_poll(kkx_ctx* ctx, kkx_ticket ticket);
+KKX_API int kkx_wait(kkx_ctx* ctx, kkx_ticket ticket, float** out_audio, int64_t* out_samples,
+                     int32_t* out_pred_dur);
 
 /* ---- "next" rows of the hot-path scope: the host work either side of the call.
  *
@@ -141,7 +172,9 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
                      int32_t* out_pred_dur);
 
 /* ---- options.  Known keys:
- *   "precision"   0 = fp32 SIMT everywhere, 1 = bf16 tensor-core (tcgen05) decoder+generator
+ *   "precision"   1 (DEFAULT, the benchmarked configuration) = tcgen05 tensor cores: bf16 decoder + generator,
+ *                 split-TF32 predictor; 0 = fp32 SIMT everywhere (verification mode: tightest parity, several
+ *                 times slower)
  *   "noise_seed"  seed of the on-device Philox N(0,1) generator for the SineGen noise
  *   "max_frames"  frame budget per frame-phase group (memory control for large batches)
  *   "max_tokens"  token budget per pass of one kkx_infer_batch call (default 40960): larger batches are run in
@@ -150,8 +183,13 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *   "coalesce"    0/1 = off; K > 1 (<= 512) = merge up to K concurrent kkx_infer callers per step
  *   "coalesce_wait_us"  how long the caller that found the queue idle waits for company (default 0: no
  *                 added latency -- batches form from whatever queued up behind the running step)
+ *   "async_batch" most kkx_submit requests the worker merges into one ragged batch (default 64)
+ *   "latency_graphs" 0/1: replay the token phase of single-utterance calls from a CUDA graph keyed by the token
+ *                 count (default 1)
  * kkx_get_stat keys: "launches", "last_frames", "gpu_us", "precision", "coalesced_batches",
- * "coalesced_requests", "coalesced_largest". */
+ * "coalesced_requests", "coalesced_largest", "async_batches", "async_requests", "frame_groups",
+ * "group_first:<g>" (first item of frame group g of the last run), "weights_sessions" (sessions sharing this
+ * ctx's device weight set), "weights_bytes", "weights_from_onnx", "graph_replays". */
 KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value);
 KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key); /* "launches", "last_frames", "gpu_us" ... */
 
@@ -160,22 +198,6 @@ KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key); /* "launches", "las
  * total_us]}} and returns the full length of the text. */
 KKX_API int kkx_profile_enable(kkx_ctx* ctx, int enable);
 KKX_API int64_t kkx_profile_json(kkx_ctx* ctx, char* buf, int64_t capacity);
-
-/* ---- test-only hooks (parity harness; not used by the Rust shim) -------------------------
- * kkx_set_noise: explicit SineGen noise, element (sample t, harmonic h) of batch item 0 at
- *   noise[t*9+h]; n = number of floats; n == 0 returns to the on-device generator.  With a
- *   batch, item b reads the same buffer (each item from offset 0).
- * kkx_set_inject: teacher-force an intermediate for item 0 of the next call.  name is
- *   "pred_dur" (int32 data), "F0" or "N" (f32 data); count = elements; count == 0 clears.
- * kkx_debug_stage: after a call, copy a named stage tensor of the LAST frame group to host.
- *   Returns the number of floats the stage holds (rows*cols) or <0; rows/cols are written if
- *   non-NULL; at most `capacity` floats are copied (dst may be NULL to query the size).
- *   Stage names match oracle/kokoro_ref.py (`bert`, `d`, `dur_logits`, `F0`, `har`, ...). */
-KKX_API int kkx_set_noise(kkx_ctx* ctx, const float* noise, int64_t n);
-KKX_API int kkx_set_inject(kkx_ctx* ctx, const char* name, const void* data, int64_t count);
-KKX_API int64_t kkx_debug_stage(kkx_ctx* ctx, const char* name, int32_t item, float* dst, int64_t capacity,
-                        int64_t* rows, int64_t* cols);
-KKX_API int kkx_debug_enable(kkx_ctx* ctx, int enable); /* keep stage tensors alive for kkx_debug_stage */
 
 /* Library / build identification, e.g. "kkx 0.1 sm_100a". */
 KKX_API const char* kkx_version(void);

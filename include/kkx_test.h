@@ -1,8 +1,9 @@
 /*
- * kkx_test.h -- op-level test hooks of libkkx.so (parity harness only; the Rust shim binds
- * nothing from this header).  Host pointers in, host pointers out, one ragged item; each call
- * allocates device scratch, runs ONE hand-written kernel and copies the result back, so that
- * tests/ can compare a kernel against the matching torch op in isolation.
+ * kkx_test.h -- test hooks of libkkx.so (parity harness only; the Rust shim binds nothing from
+ * this header): whole-model hooks (noise / teacher forcing / stage dumps) and op-level entry
+ * points.  The op-level calls take host pointers in and out, one ragged item; each allocates
+ * device scratch, runs ONE hand-written kernel and copies the result back, so that tests/ can
+ * compare a kernel against the matching torch op in isolation.
  */
 #ifndef KKX_TEST_H_
 #define KKX_TEST_H_
@@ -10,6 +11,25 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* ---- whole-model hooks (moved here from kkx.h: the parity harness is their only user) -------------------
+ * kkx_set_noise: explicit SineGen noise, element (sample t, harmonic h) at noise[t*9+h]; n = number of floats;
+ *   n == 0 returns to the on-device generator.  With a batch every item reads the same buffer from offset 0.
+ * kkx_set_inject_item: teacher-force an intermediate of batch item `item` (any frame group) in every following
+ *   call: name is "pred_dur" (int32 data, n_tokens entries in 1..500), "F0" or "N" (f32 data, 2T entries);
+ *   count == 0 clears that item's entry.  kkx_set_inject is the item-0 form.
+ * kkx_debug_enable / kkx_debug_select: keep stage tensors alive for kkx_debug_stage -- of every item, or of one
+ *   item only (a B = 64 x 510 batch would otherwise hold tens of GB of host copies).
+ * kkx_debug_stage: after a call, copy a named stage tensor of item `item` to host.  Returns the number of floats the
+ *   stage holds (rows*cols) or <0; rows/cols are written if non-NULL; at most `capacity` floats are copied (dst may
+ *   be NULL to query the size).  Stage names match oracle/kokoro_ref.py (`bert`, `d`, `dur_logits`, `F0`, ...). */
+KKX_API int kkx_set_noise(kkx_ctx* ctx, const float* noise, int64_t n);
+KKX_API int kkx_set_inject(kkx_ctx* ctx, const char* name, const void* data, int64_t count);
+KKX_API int kkx_set_inject_item(kkx_ctx* ctx, int32_t item, const char* name, const void* data, int64_t count);
+KKX_API int kkx_debug_enable(kkx_ctx* ctx, int enable);
+KKX_API int kkx_debug_select(kkx_ctx* ctx, int enable, int32_t item);
+KKX_API int64_t kkx_debug_stage(kkx_ctx* ctx, const char* name, int32_t item, float* dst, int64_t capacity,
+                        int64_t* rows, int64_t* cols);
 
 /* Generic shifted-GEMM kernel (Conv1d / ConvTranspose1d phase / Linear), see kernels.h ConvArgs.
  * in [rows_in, ldi]; w [ks][Ci][Co]; out [out_rows, Co] (pre-filled by the caller; rows not
@@ -51,6 +71,9 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
                               const float* scale, const float* shift, const float* alpha, const float* w,
                               const float* bias, int ks, int dil, const float* res, float oscale,
                               int accumulate, int want_bf16, float* out, float* sums, int desc_mode);
+/* Host-only: the library's tensor spec table (onnx_loader.cu kokoro_tensor_specs) as text lines "name d0 d1 ...\n";
+ * returns the full length, writes at most capacity-1 characters + NUL. */
+KKX_API int64_t kkx_test_tensor_specs(char* buf, int64_t capacity);
 KKX_API const char* kkx_test_last_error(void);
 
 #ifdef __cplusplus

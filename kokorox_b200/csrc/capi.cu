@@ -3,6 +3,7 @@
 // across the ABI (the reference `expect`s on bad outputs, ort_koko.rs:82,86, and its CLI turns a
 // panic into abort(); a library must not).
 #include "../../include/kkx.h"
+#include "../../include/kkx_test.h"
 #include "model.h"
 #include <chrono>
 #include <condition_variable>
@@ -12,6 +13,8 @@
 #include <map>
 #include <set>
 #include <sstream>
+#include <atomic>
+#include <thread>
 
 using namespace kkx;
 
@@ -38,10 +41,27 @@ struct kkx_ctx {
   std::deque<Waiter*> queue;
   bool leader = false;
   long long max_tokens = 40960;  // tokens per pass of one call (64 x 512-token utterances + slack)
-  int coalesce_max = 0;          // 0/1 = off (reference behaviour); >1 = largest batch a leader gathers
-  int coalesce_wait_us = 0;      // how long a leader waits for company before it runs
+  std::atomic<int> coalesce_max{0};      // 0/1 = off (reference behaviour); >1 = largest batch a leader gathers
+  std::atomic<int> coalesce_wait_us{0};  // how long a leader waits for company before it runs
   int64_t coalesced_batches = 0, coalesced_requests = 0, coalesced_largest = 0;
   std::map<float*, SharedBuf*> views;   // per-caller view -> the shared buffer it pins (guarded by pool_mu)
+
+  // Asynchronous requests (kkx_submit / kkx_poll / kkx_wait): a worker thread owned by the ctx drains the queue in
+  // FIFO batches, so a caller can hand in sentence k+1 and go on sending sentence k (websocket lib.rs:371-376).
+  struct AsyncReq {
+    std::vector<int64_t> tokens; float style[256]; std::vector<int32_t> dur;
+    Waiter w{};
+    bool done = false, taken = false;
+  };
+  std::mutex amu;
+  std::condition_variable acv_work, acv_done;
+  std::map<int64_t, std::unique_ptr<AsyncReq>> tickets;
+  std::deque<AsyncReq*> aqueue;
+  std::thread worker;
+  bool worker_started = false, astop = false;
+  int64_t next_ticket = 1;
+  std::atomic<int> async_batch{64};      // most requests the worker merges into one ragged batch
+  int64_t async_batches = 0, async_requests = 0;
 };
 
 static thread_local std::string g_err;
@@ -56,6 +76,7 @@ static int guarded(kkx_ctx* ctx, F&& f) {
     return KKX_OK;
   } catch (const ArgError& e) { rc = KKX_ERR_ARG; msg = e.what();
   } catch (const IoError& e) { rc = KKX_ERR_IO; msg = e.what();
+  } catch (const StateError& e) { rc = KKX_ERR_STATE; msg = e.what();
   } catch (const CudaError& e) { rc = KKX_ERR_CUDA; msg = e.what();
   } catch (const std::exception& e) { rc = KKX_ERR_CUDA; msg = e.what();
   } catch (...) { rc = KKX_ERR_CUDA; msg = "unknown error"; }
@@ -95,8 +116,59 @@ KKX_API int kkx_create(const char* weights_path, int device_ordinal, kkx_ctx** o
   return KKX_OK;
 }
 
+// Host-only: read a model file the way kkx_create does (KKXW or ONNX, see kkx.h) and write the recovered state dict
+// as a KKXW file.  Lets a deployment convert once and lets the CPU test-suite check the ONNX reader without a GPU.
+KKX_API int kkx_convert_model_file(const char* src_path, const char* dst_kkxw_path, int32_t* out_tensors) {
+  if (!src_path || !dst_kkxw_path) { g_err = "kkx_convert_model_file: null argument"; return KKX_ERR_ARG; }
+  return guarded(nullptr, [&] {
+    WeightFile wf(src_path);
+    std::vector<std::string> names;
+    for (auto& sp : kokoro_tensor_specs()) names.push_back(sp.first);
+    std::vector<char> hdr;
+    auto put = [&](const void* p, size_t n) { hdr.insert(hdr.end(), (const char*)p, (const char*)p + n); };
+    std::vector<uint64_t> offs;
+    uint64_t off = 0;
+    for (auto& n : names) {
+      const HostTensor& t = wf.get(n);
+      const uint16_t ln = (uint16_t)n.size();
+      put(&ln, 2); put(n.data(), n.size());
+      const uint32_t dtype = 0, ndim = (uint32_t)t.shape.size();
+      put(&dtype, 4); put(&ndim, 4);
+      for (int d : t.shape) { const uint32_t v = (uint32_t)d; put(&v, 4); }
+      const uint64_t nb = (uint64_t)t.numel * 4;
+      put(&off, 8); put(&nb, 8);
+      offs.push_back(off);
+      off += (nb + 63) / 64 * 64;
+    }
+    const uint32_t n = (uint32_t)names.size();
+    const uint32_t header_bytes = (uint32_t)((16 + hdr.size() + 255) / 256 * 256);
+    FILE* f = fopen(dst_kkxw_path, "wb");
+    if (!f) throw IoError(std::string("cannot write ") + dst_kkxw_path);
+    bool ok = fwrite("KKXW0001", 1, 8, f) == 8 && fwrite(&n, 4, 1, f) == 1 && fwrite(&header_bytes, 4, 1, f) == 1 &&
+              fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
+    std::vector<char> zeros(256, 0);
+    ok = ok && fwrite(zeros.data(), 1, header_bytes - 16 - hdr.size(), f) == header_bytes - 16 - hdr.size();
+    for (size_t i = 0; ok && i < names.size(); i++) {
+      const HostTensor& t = wf.get(names[i]);
+      const size_t nb = t.numel * 4, pad = (nb + 63) / 64 * 64 - nb;
+      ok = fwrite(t.data, 1, nb, f) == nb && fwrite(zeros.data(), 1, pad, f) == pad;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw IoError(std::string("short write: ") + dst_kkxw_path);
+    if (out_tensors) *out_tensors = (int32_t)names.size();
+  });
+}
+
 KKX_API void kkx_destroy(kkx_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->worker_started) {   // stop the async worker; requests still queued fail with KKX_ERR_STATE
+    {
+      std::lock_guard<std::mutex> al(ctx->amu);
+      ctx->astop = true;
+    }
+    ctx->acv_work.notify_all();
+    if (ctx->worker.joinable()) ctx->worker.join();
+  }
   try {
     if (ctx->model) cudaSetDevice(ctx->model->device());
     for (auto& p : ctx->pinned) cudaFreeHost(p.first);
@@ -154,6 +226,16 @@ static void hand_out(kkx_ctx* ctx, float* host, size_t cap) {
 }
 
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio);
+
+// The argument contract of one utterance (kkx.h): checked before a request is queued anywhere.
+static int validate_request(const int64_t* tokens, int32_t n_tokens, const float* style256, float speed) {
+  if (!tokens || !style256) { g_err = "null argument"; return KKX_ERR_ARG; }
+  if (n_tokens < 1 || n_tokens > KKX_MAX_TOKENS) { g_err = "n_tokens must be in 1..512 (got " + std::to_string(n_tokens) + ")"; return KKX_ERR_ARG; }
+  if (!(speed >= kMinSpeed && speed <= kMaxSpeed)) { g_err = "speed must be in [0.1, 10] (got " + std::to_string(speed) + ")"; return KKX_ERR_ARG; }
+  for (int32_t i = 0; i < n_tokens; i++)
+    if (tokens[i] < 0 || tokens[i] > 177) { g_err = "token id out of range 0..177: " + std::to_string(tokens[i]); return KKX_ERR_ARG; }
+  return KKX_OK;
+}
 
 // One ragged batch through the model into a pooled pinned buffer (caller holds ctx->mu; throws).  The buffer is
 // handed to the model as a sink: every frame group's audio is copied out on a second stream while the next
@@ -282,7 +364,7 @@ static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& b
     for (int i = 0; i < B; i++) {
       kkx_ctx::Waiter& w = *batch[i];
       w.audio = host + soff[i];
-      w.samples = soff[i + 1] - soff[i];
+      w.samples = soff[i + 1] - soff[i];   // >= 600: every token lasts at least one frame, so view addresses are distinct
       if (w.pred_dur) memcpy(w.pred_dur, &dur[offs[i]], (size_t)w.n * sizeof(int32_t));
       w.rc = KKX_OK;
       ctx->views[w.audio] = sb;
@@ -321,9 +403,10 @@ static int infer_coalesced(kkx_ctx* ctx, kkx_ctx::Waiter& w) {
   while (!w.done) {
     if (ctx->leader) { ctx->qcv.wait(ql); continue; }
     ctx->leader = true;
-    const size_t want = (size_t)std::max(ctx->coalesce_max, 1);
-    if (ctx->coalesce_wait_us > 0 && ctx->queue.size() < want)
-      ctx->qcv.wait_for(ql, std::chrono::microseconds(ctx->coalesce_wait_us), [&] { return ctx->queue.size() >= want; });
+    const size_t want = (size_t)std::max(ctx->coalesce_max.load(), 1);
+    const int wait_us = ctx->coalesce_wait_us.load();
+    if (wait_us > 0 && ctx->queue.size() < want)
+      ctx->qcv.wait_for(ql, std::chrono::microseconds(wait_us), [&] { return ctx->queue.size() >= want; });
     // FIFO, bounded by the batch size and by the 64 x 512-token working set the step is sized for
     std::vector<kkx_ctx::Waiter*> batch;
     long long tok = 0;
@@ -466,8 +549,11 @@ KKX_API int64_t kkx_encode_wav16_base64(const int16_t* pcm, int64_t n_samples, i
 KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256,
               float speed, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {
   if (out_samples) *out_samples = 0;
-  if (ctx && ctx->model && ctx->coalesce_max > 1) {
+  if (ctx && ctx->model && ctx->coalesce_max.load() > 1) {
     if (out_audio) *out_audio = nullptr; else { g_err = "out_audio is null"; return KKX_ERR_ARG; }
+    // validate BEFORE queueing: a bad request must fail here, alone and at once, not inside somebody's batch
+    const int vrc = validate_request(tokens, n_tokens, style256, speed);
+    if (vrc != KKX_OK) return vrc;
     kkx_ctx::Waiter w{tokens, n_tokens, style256, speed, out_pred_dur};
     const int rc = infer_coalesced(ctx, w);
     if (rc == KKX_OK) { *out_audio = w.audio; if (out_samples) *out_samples = w.samples; }
@@ -478,6 +564,105 @@ KKX_API int kkx_infer(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, con
   const int rc = kkx_infer_batch(ctx, 1, tokens, offs, style256, &speed, out_audio, soff, out_pred_dur);
   if (rc == KKX_OK && out_samples) *out_samples = soff[1];
   return rc;
+}
+
+// ---- asynchronous entry points --------------------------------------------------------------------------------
+static void async_worker(kkx_ctx* ctx) {
+  std::unique_lock<std::mutex> al(ctx->amu);
+  for (;;) {
+    ctx->acv_work.wait(al, [&] { return ctx->astop || !ctx->aqueue.empty(); });
+    if (ctx->astop) {
+      for (auto* r : ctx->aqueue) { r->w.rc = KKX_ERR_STATE; r->w.err = "session destroyed before the request ran"; r->done = true; }
+      ctx->aqueue.clear();
+      ctx->acv_done.notify_all();
+      return;
+    }
+    std::vector<kkx_ctx::AsyncReq*> reqs;
+    std::vector<kkx_ctx::Waiter*> batch;
+    long long tok = 0;
+    const size_t want = (size_t)std::max(ctx->async_batch.load(), 1);
+    while (!ctx->aqueue.empty() && reqs.size() < want) {
+      kkx_ctx::AsyncReq* r = ctx->aqueue.front();
+      if (!reqs.empty() && tok + r->w.n > 64 * 512) break;
+      tok += r->w.n;
+      reqs.push_back(r);
+      batch.push_back(&r->w);
+      ctx->aqueue.pop_front();
+    }
+    al.unlock();
+    try {
+      serve_coalesced(ctx, batch);
+    } catch (...) {
+      for (auto* w : batch) { w->rc = KKX_ERR_CUDA; w->err = "internal error while serving an asynchronous batch"; w->audio = nullptr; }
+    }
+    al.lock();
+    ctx->async_batches++;
+    ctx->async_requests += (int64_t)reqs.size();
+    for (auto* r : reqs) r->done = true;
+    ctx->acv_done.notify_all();
+  }
+}
+
+KKX_API int kkx_submit(kkx_ctx* ctx, const int64_t* tokens, int32_t n_tokens, const float* style256, float speed,
+                       kkx_ticket* out_ticket) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!out_ticket) { g_err = "out_ticket is null"; return KKX_ERR_ARG; }
+  *out_ticket = 0;
+  rc = validate_request(tokens, n_tokens, style256, speed);
+  if (rc) return rc;
+  try {
+    std::unique_ptr<kkx_ctx::AsyncReq> r(new kkx_ctx::AsyncReq());
+    r->tokens.assign(tokens, tokens + n_tokens);      // the caller's buffers are free again when this call returns
+    memcpy(r->style, style256, sizeof r->style);
+    r->dur.assign((size_t)n_tokens, 0);
+    r->w.tokens = r->tokens.data(); r->w.n = n_tokens; r->w.style = r->style; r->w.speed = speed;
+    r->w.pred_dur = r->dur.data();
+    std::lock_guard<std::mutex> al(ctx->amu);
+    if (ctx->astop) { g_err = "Session is not initialized."; return KKX_ERR_STATE; }
+    if (!ctx->worker_started) {
+      ctx->worker = std::thread(async_worker, ctx);
+      ctx->worker_started = true;
+    }
+    const int64_t t = ctx->next_ticket++;
+    ctx->aqueue.push_back(r.get());
+    ctx->tickets[t] = std::move(r);
+    *out_ticket = t;
+  } catch (const std::exception& e) { g_err = e.what(); return KKX_ERR_CUDA; }
+  ctx->acv_work.notify_one();
+  return KKX_OK;
+}
+
+KKX_API int kkx_poll(kkx_ctx* ctx, kkx_ticket ticket) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> al(ctx->amu);
+  auto it = ctx->tickets.find(ticket);
+  if (it == ctx->tickets.end() || it->second->taken) { g_err = "unknown ticket"; return KKX_ERR_ARG; }
+  return it->second->done ? 1 : 0;
+}
+
+KKX_API int kkx_wait(kkx_ctx* ctx, kkx_ticket ticket, float** out_audio, int64_t* out_samples, int32_t* out_pred_dur) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (out_audio) *out_audio = nullptr;
+  if (out_samples) *out_samples = 0;
+  std::unique_ptr<kkx_ctx::AsyncReq> r;
+  {
+    std::unique_lock<std::mutex> al(ctx->amu);
+    auto it = ctx->tickets.find(ticket);
+    if (it == ctx->tickets.end() || it->second->taken) { g_err = "unknown ticket"; return KKX_ERR_ARG; }
+    it->second->taken = true;                         // a ticket is redeemed once
+    kkx_ctx::AsyncReq* p = it->second.get();
+    ctx->acv_done.wait(al, [&] { return p->done; });
+    r = std::move(it->second);
+    ctx->tickets.erase(it);
+  }
+  if (r->w.rc != KKX_OK) { g_err = r->w.err; return r->w.rc; }
+  if (out_pred_dur) memcpy(out_pred_dur, r->dur.data(), r->dur.size() * sizeof(int32_t));
+  if (out_samples) *out_samples = r->w.samples;
+  if (out_audio) *out_audio = r->w.audio; else kkx_release(ctx, r->w.audio);
+  return KKX_OK;
 }
 
 KKX_API void kkx_release(kkx_ctx* ctx, float* audio) {
@@ -553,12 +738,13 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {
       if (value < 0 || value > kMaxCoalesce) throw ArgError("coalesce must be in 0..512");
-      std::lock_guard<std::mutex> ql(ctx->qmu);
-      ctx->coalesce_max = (int)value;
+      ctx->coalesce_max.store((int)value);
     } else if (k == "coalesce_wait_us") {
       if (value < 0 || value > 1000000) throw ArgError("coalesce_wait_us must be in 0..1000000");
-      std::lock_guard<std::mutex> ql(ctx->qmu);
-      ctx->coalesce_wait_us = (int)value;
+      ctx->coalesce_wait_us.store((int)value);
+    } else if (k == "async_batch") {
+      if (value < 1 || value > kMaxCoalesce) throw ArgError("async_batch must be in 1..512");
+      ctx->async_batch.store((int)value);
     }
     else throw ArgError("unknown option: " + k);
   });
@@ -575,6 +761,20 @@ KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key) {
   if (k == "coalesced_batches") return ctx->coalesced_batches;
   if (k == "coalesced_requests") return ctx->coalesced_requests;
   if (k == "coalesced_largest") return ctx->coalesced_largest;
+  if (k == "frame_groups") return (int64_t)ctx->model->group_first().size();
+  if (k.rfind("group_first:", 0) == 0) {     // first item of frame group g of the last run
+    const long g = atol(k.c_str() + 12);
+    const auto& gf = ctx->model->group_first();
+    return g >= 0 && g < (long)gf.size() ? gf[g] : -1;
+  }
+  if (k == "weights_sessions") return (int64_t)ctx->model->weight_sessions();
+  if (k == "weights_bytes") return (int64_t)ctx->model->weight_set().device_bytes;
+  if (k == "weights_from_onnx") return ctx->model->weight_set().format == "onnx" ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> al(ctx->amu);
+    if (k == "async_batches") return ctx->async_batches;
+    if (k == "async_requests") return ctx->async_requests;
+  }
   return -1;
 }
 
@@ -616,21 +816,33 @@ KKX_API int kkx_set_noise(kkx_ctx* ctx, const float* noise, int64_t n) {
   return guarded(ctx, [&] { ctx->model->set_noise(noise, n); });
 }
 
-KKX_API int kkx_set_inject(kkx_ctx* ctx, const char* name, const void* data, int64_t count) {
+KKX_API int kkx_set_inject_item(kkx_ctx* ctx, int32_t item, const char* name, const void* data, int64_t count) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   return guarded(ctx, [&] {
     if (!name) throw ArgError("null name");
-    ctx->model->set_inject(name, count > 0 ? data : nullptr, count);
+    ctx->model->set_inject(name, item, count > 0 ? data : nullptr, count);
   });
+}
+
+KKX_API int kkx_set_inject(kkx_ctx* ctx, const char* name, const void* data, int64_t count) {
+  return kkx_set_inject_item(ctx, 0, name, data, count);
 }
 
 KKX_API int kkx_debug_enable(kkx_ctx* ctx, int enable) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->model->set_debug(enable != 0);
+  ctx->model->set_debug(enable != 0, -1);
+  return KKX_OK;
+}
+
+KKX_API int kkx_debug_select(kkx_ctx* ctx, int enable, int32_t item) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->model->set_debug(enable != 0, item);
   return KKX_OK;
 }
 

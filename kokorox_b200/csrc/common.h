@@ -6,6 +6,9 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <atomic>
+#include <mutex>
+#include <stdlib.h>
 
 namespace kkx {
 
@@ -18,6 +21,9 @@ struct ArgError : std::runtime_error {
 struct IoError : std::runtime_error {
   explicit IoError(const std::string& s) : std::runtime_error(s) {}
 };
+struct StateError : std::runtime_error {   // call sequence error (nothing staged / nothing run yet) -> KKX_ERR_STATE
+  explicit StateError(const std::string& s) : std::runtime_error(s) {}
+};
 
 #define KKX_CUDA(expr)                                                                      \
   do {                                                                                      \
@@ -29,6 +35,42 @@ struct IoError : std::runtime_error {
       throw ::kkx::CudaError(_b);                                                           \
     }                                                                                       \
   } while (0)
+
+// Kernel-variant switches read from the environment exist only in experiment builds (-DKKX_EXPERIMENTS, e.g.
+// KKX_NVCC_EXTRA=-DKKX_EXPERIMENTS python -m kokorox_b200.build --force): the production library always takes the
+// measured-best path, so no environment variable can change which kernel runs or what it computes.
+#ifdef KKX_EXPERIMENTS
+inline bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? (e[0] != '0') : dflt;
+}
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+inline bool env_flag(const char*, bool dflt) { return dflt; }
+inline int env_int(const char*, int dflt) { return dflt; }
+#endif
+
+// One-time per-device setup (cudaFuncSetAttribute for a kernel's dynamic shared memory): two sessions on two
+// threads may reach a launcher's first use together, so the flag is a std::once_flag per device, not a bool.
+struct DevOnce {
+  std::once_flag flag[64];
+  template <class F> void run(int dev, F&& fn) {
+    if (dev >= 0 && dev < 64) std::call_once(flag[dev], fn); else fn();
+  }
+};
+inline int device_sm_count(int dev) {
+  static std::atomic<int> cache[64];
+  if (dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 // Launch-count bookkeeping ("gpu_launches" in bench.py) + optional per-launch error checks.
 struct LaunchStats {
@@ -106,6 +148,33 @@ class Arena {
   void* base_ = nullptr;
   size_t cap_ = 0, used_ = 0;
   bool virtual_ = false;
+};
+
+// Pinned host staging memory for the small index tables a run uploads (level offsets, tile prefix sums, sample
+// offsets).  A cudaMemcpyAsync from PAGEABLE memory synchronises the stream before it starts; from pinned memory
+// it is a true asynchronous copy, so a B = 1 call no longer pays one stream drain per table.  Bump allocator,
+// reset when the stream is known to be idle (start of a call); alloc() returns nullptr when full and the caller
+// drains the stream and resets.
+class PinnedArena {
+ public:
+  ~PinnedArena() { if (base_) cudaFreeHost(base_); }
+  void reserve(size_t bytes) {
+    if (bytes <= cap_) return;
+    if (base_) cudaFreeHost(base_);
+    base_ = nullptr; cap_ = 0; used_ = 0;
+    KKX_CUDA(cudaMallocHost(&base_, bytes));
+    cap_ = bytes;
+  }
+  void reset() { used_ = 0; }
+  void* alloc_bytes(size_t bytes) {
+    const size_t a = (used_ + 63) & ~size_t(63);
+    if (a + bytes > cap_) return nullptr;
+    used_ = a + bytes;
+    return static_cast<char*>(base_) + a;
+  }
+ private:
+  void* base_ = nullptr;
+  size_t cap_ = 0, used_ = 0;
 };
 
 // A ragged "level": B items packed along the row axis with zero gaps between items.

@@ -706,16 +706,11 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
 template <int BN, int MSUB, bool CONV2, bool T, bool POST = false>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   using Cfg = ArbCfg<BN, MSUB, T>;
-  static bool attr_set[64] = {false};
-  static int sms[64] = {0};
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
-    attr_set[dev] = true;
-  }
-  const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); });
+  const int nsm = device_sm_count(dev);
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
   arb_conv_kernel<BN, MSUB, CONV2, T, POST><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
@@ -725,11 +720,11 @@ void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
 // kernel variant per shape: 0 = rows as M (C = 256, or C = 128 with KKX_ARB_NOT=1), 1 = transposed with 256-row
 // tiles, 2 = transposed with 512-row tiles (k >= 7: halves the weight re-streaming the k = 7/11 convs are bound by)
 static int arb_variant(int C, int ks) {
-  static const bool no_t = [] { const char* e = getenv("KKX_ARB_NOT"); return e && e[0] == '1'; }();
+  static const bool no_t = env_flag("KKX_ARB_NOT", false);
   // 512-row tiles measured on B200 (5.7 M rows): conv1 k7 1.40 -> 1.25 ms, conv1 k11 unchanged, conv2 k7 / k11
   // 1.65 -> 1.81 / 1.81 -> 2.19 ms (losing the epilogue/MMA overlap costs more than the halved weight stream
   // saves; ncu shows the tensor pipe already 75 % active at k = 11).  Opt-in: KKX_ARB_512=1.
-  static const bool use_512 = [] { const char* e = getenv("KKX_ARB_512"); return e && e[0] == '1'; }();
+  static const bool use_512 = env_flag("KKX_ARB_512", false);
   if (C != 128 || no_t) return 0;
   return (ks >= 7 && use_512) ? 2 : 1;
 }

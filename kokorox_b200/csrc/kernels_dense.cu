@@ -575,20 +575,19 @@ __global__ void __launch_bounds__(NW * 32) attention_tc_kernel(const float* __re
 void launch_attention(const float* qkv, float* ctx, const int* off, const int* len, int B,
                       int max_len, cudaStream_t st) {
   if (g_dry_run) return;
-  static const bool simt = [] { const char* e = getenv("KKX_ATT_SIMT"); return e && e[0] == '1'; }();
+  static const bool simt = env_flag("KKX_ATT_SIMT", false);
   if (simt) {
     dim3 g((max_len + 31) / 32, 12, B);
     attention_kernel<<<g, 256, 0, st>>>(qkv, ctx, off, len);
   } else {
     constexpr int smem = 4 * 64 * kAttLd * 4;
-    static bool attr_set[64] = {false};
+    static DevOnce once;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 64 && !attr_set[dev]) {
+    once.run(dev, [] {
       KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       KKX_CUDA(cudaFuncSetAttribute(attention_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set[dev] = true;
-    }
+    });
     if (max_len > 64) {   // 128 query rows per CTA: the K/V staging (load + tf32 split) is amortised over twice the MMAs
       dim3 g((max_len + 127) / 128, 12, B);
       attention_tc_kernel<8><<<g, 256, smem, st>>>(qkv, ctx, off, len);
@@ -871,13 +870,10 @@ template <int G>
 static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                                 const int* off, const int* len, int B, cudaStream_t st) {
   const size_t smem = (size_t)(2 * G * kHItem + G * 128) * sizeof(float) + 16;
-  static bool attr_set[64] = {false};
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev] = true;
-  }
+  once.run(dev, [smem] { KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
   const int groups = (B + G - 1) / G;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(8 * groups, 2, 1);
@@ -888,7 +884,7 @@ static void launch_lstm_cluster(const float* xproj, const float* whhT, float* ou
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  static const bool dbg = getenv("KKX_LSTM_DEBUG") != nullptr;
+  static const bool dbg = env_flag("KKX_LSTM_DEBUG", false);
   if (dbg) {
     int ncl = -1;
     cudaOccupancyMaxActiveClusters(&ncl, lstm_cluster_kernel<G>, &cfg);
@@ -900,7 +896,7 @@ static void launch_lstm_cluster(const float* xproj, const float* whhT, float* ou
 void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
                  const int* off, const int* len, int B, cudaStream_t st) {
   if (g_dry_run) return;
-  static const bool simple = [] { const char* e = getenv("KKX_LSTM_SIMPLE"); return e && e[0] == '1'; }();
+  static const bool simple = env_flag("KKX_LSTM_SIMPLE", false);
   if (simple) {
     dim3 g(B, 2);
     lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);

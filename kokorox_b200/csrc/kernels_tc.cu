@@ -13,6 +13,13 @@
 #include <mutex>
 #include "tc_ptx.cuh"
 
+// perf-experiment switches (skip MMAs / loads / stores: wrong results, timing only) exist only in -DKKX_TC_DEBUG builds
+#ifdef KKX_TC_DEBUG
+#define TC_DBG(a, bit) ((a).debug & (bit))
+#else
+#define TC_DBG(a, bit) (0)
+#endif
+
 namespace kkx {
 
 #ifdef KKX_TC_TIMING
@@ -165,8 +172,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         TCT(0);
         const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
         const uint32_t sa = base + s * STAGE_BYTES;
-        const bool skipA2 = MODE && (a.debug & 8);     // perf experiment: pretend the A lo plane needs no L2 traffic
-        const bool skipB2 = MODE && (a.debug & 16);
+        const bool skipA2 = MODE && TC_DBG(a, 8);     // perf experiment: pretend the A lo plane needs no L2 traffic
+        const bool skipB2 = MODE && TC_DBG(a, 16);
         mbar_expect_tx(full_bar(s), STAGE_BYTES - (skipA2 ? A_BYTES : 0) - (skipB2 ? B_BYTES : 0));
         tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
         if (MODE && !skipA2) tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
-            if (!(a.debug & 2)) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+            if (!TC_DBG(a, 2)) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
         } else {
           const int chain = it >> 1, j = chain % 3;
           const bool chain_start = (it & 1) == 0;
@@ -215,9 +222,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
             const uint64_t o = (uint64_t)(2 * k);
-            if (a.debug & 2) continue;                 // perf experiment: no MMAs
+            if (TC_DBG(a, 2)) continue;                 // perf experiment: no MMAs
             if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
-            if (!(a.debug & 32)) {                     // perf experiment: hi*hi only
+            if (!TC_DBG(a, 32)) {                     // perf experiment: hi*hi only
               umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
               umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
             }
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         TCT(0);
 #pragma unroll
         for (int c = 0; c < BN; c += 32) {
-          if (a.debug & 4) continue;                   // perf experiment: chains are not drained
+          if (TC_DBG(a, 4)) continue;                   // perf experiment: chains are not drained
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
 #pragma unroll
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         for (int i = 0; i < 8; i++) {
           const int row = (t >> 3) + 16 * i;
           const int mm = m0 + row;
-          if (mm >= mlen || (a.debug & 1)) continue;
+          if (mm >= mlen || TC_DBG(a, 1)) continue;
           float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
           o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
           if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
           const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            if (!(a.debug & 2)) umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+            if (!TC_DBG(a, 2)) umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(acc));
@@ -504,7 +511,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
           for (int i = 0; i < 8; i++) {
             const int row = (t >> 3) + 16 * i;
             const int mm = m0 + row;
-            if (mm >= mlen || (a.debug & 1)) continue;
+            if (mm >= mlen || TC_DBG(a, 1)) continue;
             float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
             o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
@@ -773,20 +780,15 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
 
 static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
   constexpr int smem = 3 * 4 * 128 * 128 + 128 * 36 * 4 + 14 * 8 + 16 + 1024;
-  static bool attr_set[64] = {false};
-  static int sms[64] = {0};
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(gemm32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    KKX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
-    attr_set[dev] = true;
-  }
-  const int nsm = dev < 64 && sms[dev] > 0 ? sms[dev] : 148;
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(gemm32p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+  const int nsm = device_sm_count(dev);
   const int total = a.ntiles_m * ((a.Co + 127) / 128);
   const int grid = total < nsm ? total : nsm;
   TcConvArgs b = a;
-  static const int l2mb = [] { const char* e = getenv("KKX_TC_GROUP_MB"); return e ? atoi(e) : 24; }();
+  static const int l2mb = env_int("KKX_TC_GROUP_MB", 24);
   const long long per_tile = 128LL * a.Cpad * 8;       // bytes of hi+lo planes of one m-tile
   long long gm = (long long)l2mb * 1000000LL / (per_tile > 0 ? per_tile : 1);
   if (gm < 8) gm = 8;
@@ -799,13 +801,10 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
 template <int BN, int STAGES, int TPC>
 static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (128 * 128 + BN * 128) + 2 * 128 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
-  static bool attr_set[64] = {false};
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel<BN, STAGES, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[dev] = true;
-  }
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel<BN, STAGES, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
   dim3 g((a.max_m + 128 * TPC - 1) / (128 * TPC), (a.Co + BN - 1) / BN, a.B);
   conv_tc_multi_kernel<BN, STAGES, TPC><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
                                                              *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
@@ -815,13 +814,10 @@ template <int BN, int STAGES, int MODE, int CL = 1>
 static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
   constexpr int PLANES = MODE ? 2 : 1;
   constexpr int smem = STAGES * PLANES * (128 * 128 + BN * 128) + (2 * STAGES + 7) * 8 + 16 + 1024;
-  static bool attr_set[64] = {false};
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[dev] = true;
-  }
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
   const unsigned gx = (unsigned)(((a.max_m + 127) / 128 + CL - 1) / CL * CL);
   dim3 g(gx, (a.Co + BN - 1) / BN, a.B);
   const CUtensorMap* mA = reinterpret_cast<const CUtensorMap*>(a.tmA);
@@ -845,18 +841,24 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (g_dry_run) return;
   if (a0.max_m <= 0 || a0.B <= 0) return;
   TcConvArgs a = a0;
+#ifdef KKX_TC_DEBUG
   static const int dbg = [] { const char* e = getenv("KKX_TC_DEBUG"); return e ? atoi(e) : 0; }();
   a.debug = dbg;
+#else
+  a.debug = 0;
+#endif
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
   if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
   if (a.tf32) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
-    static const bool bn64 = [] { const char* e = getenv("KKX_TC_BN64"); return e && e[0] == '1'; }();
-    static const bool persist = [] { const char* e = getenv("KKX_TC_PERSIST"); return !e || e[0] != '0'; }();
+    static const bool bn64 = env_flag("KKX_TC_BN64", false);
+    static const bool persist = env_flag("KKX_TC_PERSIST", true);
     // Small problems (one utterance): fewer 128-wide tiles than SMs -> 64-wide single-tile CTAs fill twice as many
     // SMs and shorten the latency-bound launch (B=1, 510 tokens: 3.4 -> 2.8 ms over the 74 GEMMs of a step).  The
     // per-element accumulation order is the same in both kernels, so results do not depend on the choice.
-    static const int nsm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const int nsm = device_sm_count(cur_dev);
     const long long tiles128 = (long long)(a.ntiles_m > 0 ? a.ntiles_m : (a.sum_m + 127) / 128) * ((a.Co + 127) / 128);
     const bool small = tiles128 < nsm && a.tmB_c && a.tmB2_c && a.cluster < 2;
     if (a.Co > 64 && small) {
@@ -880,7 +882,7 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   // kernel is bound by L2->SM operand traffic (A re-fetched per tap, B per tile), not by prologue /
   // epilogue serialisation (KKX_TC_DEBUG experiments, profiles/r1_conv_tc_experiments.txt).  Kept
   // opt-in (KKX_TC_MULTI=1) as the base for the halo-reuse kernel.
-  static const bool multi_ok = [] { const char* e = getenv("KKX_TC_MULTI"); return e && e[0] == '1'; }();
+  static const bool multi_ok = env_flag("KKX_TC_MULTI", false);
   const long long tiles = (a.sum_m + 127) / 128 * ((a.Co + 127) / 128);
   if (multi_ok && tiles >= 4 * 2 * 148 && a.Co > 64) {
     if (a.Co > 128) launch_tc_multi<256, 2, 4>(a, st);   // 96 + 37 KB smem, 512 TMEM cols: 1 CTA/SM

@@ -6,26 +6,45 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <stdlib.h>
+#include <sys/stat.h>
 
 namespace kkx {
 
 thread_local bool g_dry_run = false;
 
 // ============================================================================ weight file
+namespace {
+// a + b with overflow detection (extents come from a file)
+bool add_ok(size_t a, size_t b, size_t* out) { *out = a + b; return *out >= a; }
+}  // namespace
+
 WeightFile::WeightFile(const std::string& path) {
   std::ifstream f(path, std::ios::binary | std::ios::ate);
   if (!f) throw IoError("cannot open weight file: " + path);
   const std::streamsize sz = f.tellg();
+  if (sz < 16) throw IoError(path + ": not a model file (shorter than 16 bytes)");
   f.seekg(0);
   buf_.resize((size_t)sz);
   if (!f.read(buf_.data(), sz)) throw IoError("short read: " + path);
-  if (sz < 16 || memcmp(buf_.data(), "KKXW0001", 8) != 0)
-    throw IoError(path + ": not a KKXW0001 weight file");
+  if (memcmp(buf_.data(), "KKXW0001", 8) == 0) {
+    format_ = "kkxw";
+    load_kkxw(path);
+    return;
+  }
+  // anything else must be an ONNX ModelProto -- the file OrtKoko::new is given (ort_base.rs:27-33)
+  format_ = "onnx";
+  load_onnx_weights(path, buf_, *this);
+  std::vector<char>().swap(buf_);   // every tensor was converted into owned_ storage
+}
+
+void WeightFile::load_kkxw(const std::string& path) {
+  const size_t sz = buf_.size();
   uint32_t n, hb;
   memcpy(&n, buf_.data() + 8, 4);
   memcpy(&hb, buf_.data() + 12, 4);
   size_t p = 16;
-  auto need = [&](size_t k) { if (p + k > (size_t)sz) throw IoError(path + ": truncated header"); };
+  auto need = [&](size_t k) { if (k > sz || p > sz - k) throw IoError(path + ": truncated header"); };
   for (uint32_t i = 0; i < n; i++) {
     need(2);
     uint16_t ln; memcpy(&ln, buf_.data() + p, 2); p += 2;
@@ -35,18 +54,39 @@ WeightFile::WeightFile(const std::string& path) {
     uint32_t dtype, ndim; memcpy(&dtype, buf_.data() + p, 4); memcpy(&ndim, buf_.data() + p + 4, 4); p += 8;
     if (dtype != 0 || ndim > 8) throw IoError(name + ": unsupported dtype/rank");
     HostTensor t;
-    need(4 * ndim + 16);
+    need(4 * (size_t)ndim + 16);
     size_t numel = 1;
     for (uint32_t d = 0; d < ndim; d++) {
       uint32_t v; memcpy(&v, buf_.data() + p, 4); p += 4;
+      if (v > 0x7fffffffu || (v != 0 && numel > (size_t(1) << 40) / v)) throw IoError(name + ": bad dims");
       t.shape.push_back((int)v); numel *= v;
     }
     uint64_t off, nb; memcpy(&off, buf_.data() + p, 8); memcpy(&nb, buf_.data() + p + 8, 8); p += 16;
-    if (nb != numel * 4 || (size_t)hb + off + nb > (size_t)sz) throw IoError(name + ": bad extent");
-    t.data = reinterpret_cast<const float*>(buf_.data() + hb + off);
+    // overflow-checked extent: hb + off + nb <= sz, 4-byte aligned payload
+    size_t start, end;
+    if (nb != (uint64_t)numel * 4 || off > sz || nb > sz || !add_ok((size_t)hb, (size_t)off, &start) ||
+        !add_ok(start, (size_t)nb, &end) || end > sz || (start & 3) != 0)
+      throw IoError(name + ": bad extent");
+    t.data = reinterpret_cast<const float*>(buf_.data() + start);
     t.numel = numel;
     t_[name] = t;
   }
+}
+
+void WeightFile::put(const std::string& name, const std::vector<int>& shape, std::vector<float>&& data) {
+  size_t numel = 1;
+  for (int d : shape) numel *= (size_t)d;
+  if (numel != data.size()) throw IoError(name + ": shape does not match the element count");
+  owned_.push_back(std::move(data));
+  HostTensor t;
+  t.shape = shape; t.data = owned_.back().data(); t.numel = numel;
+  t_[name] = t;
+}
+
+std::vector<std::string> WeightFile::names() const {
+  std::vector<std::string> v;
+  for (auto& kv : t_) v.push_back(kv.first);
+  return v;
 }
 
 const HostTensor& WeightFile::get(const std::string& name) const {
@@ -56,7 +96,8 @@ const HostTensor& WeightFile::get(const std::string& name) const {
 }
 
 // ============================================================================ construction
-Model::Model(const std::string& weights_path, int device) : device_(device) {
+namespace {
+int check_device(int device) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     throw CudaError("no CUDA device available (this backend has no CPU fallback)");
@@ -70,27 +111,64 @@ Model::Model(const std::string& weights_path, int device) : device_(device) {
              prop.major, prop.minor);
     throw CudaError(b);
   }
+  return device;
+}
+std::mutex g_ws_mu;
+std::map<std::string, std::weak_ptr<const WeightSet>> g_ws_cache;
+}  // namespace
+
+std::shared_ptr<const WeightSet> WeightSet::acquire(const std::string& path, int device) {
+  // key: canonical path + size + mtime + device, so a replaced file is re-read
+  std::string key = path;
+  if (char* rp = realpath(path.c_str(), nullptr)) { key = rp; free(rp); }
+  struct stat stt;
+  if (stat(path.c_str(), &stt) != 0) throw IoError("cannot open weight file: " + path);
+  key += "|" + std::to_string((long long)stt.st_size) + "|" + std::to_string((long long)stt.st_mtime) + "." +
+         std::to_string((long long)stt.st_mtim.tv_nsec) + "|" + std::to_string(device);
+  std::lock_guard<std::mutex> lk(g_ws_mu);   // held across the load: a second session of the same file waits and shares
+  auto it = g_ws_cache.find(key);
+  if (it != g_ws_cache.end())
+    if (auto sp = it->second.lock()) return sp;
+  KKX_CUDA(cudaSetDevice(device));
+  std::shared_ptr<WeightSet> ws(new WeightSet());
+  ws->device = device;
+  WeightFile wf(path);
+  ws->format = wf.format();
+  ws->load(wf);
+  g_ws_cache[key] = ws;
+  for (auto i = g_ws_cache.begin(); i != g_ws_cache.end();)   // drop entries whose sets are gone
+    i = i->second.expired() ? g_ws_cache.erase(i) : std::next(i);
+  return ws;
+}
+
+WeightSet::~WeightSet() {
+  cudaSetDevice(device);
+  for (void* p : owned_) cudaFree(p);
+}
+
+Model::Model(const std::string& weights_path, int device)
+    : device_(check_device(device)), ws_(WeightSet::acquire(weights_path, device_)), W(ws_->W) {
   KKX_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   KKX_CUDA(cudaEventCreate(&ev0_));
   KKX_CUDA(cudaEventCreate(&ev1_));
   KKX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
   KKX_CUDA(cudaEventCreateWithFlags(&ev_grp_, cudaEventDisableTiming));
+  pin_.reserve(size_t(4) << 20);
   const char* dbg = getenv("KKX_DEBUG_SYNC");
   stats.check_each = dbg && dbg[0] == '1';
   const char* det = getenv("KKX_PROFILE_DETAIL");
   stats.detail = det && det[0] == '1';
-  WeightFile wf(weights_path);
-  load_weights(wf);
 }
 
 Model::~Model() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
-  for (void* p : owned_) cudaFree(p);
   if (d_audio_) cudaFree(d_audio_);
   if (d_pcm_) cudaFree(d_pcm_);
   if (d_voices_) cudaFree(d_voices_);
   if (d_noise_) cudaFree(d_noise_);
+  if (h_pred_dur_) cudaFreeHost(h_pred_dur_);
+  if (h_T_) cudaFreeHost(h_T_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -98,10 +176,12 @@ Model::~Model() {
   if (stream_) cudaStreamDestroy(stream_);
 }
 
-float* Model::up(const std::vector<float>& v) {
+float* WeightSet::up(const std::vector<float>& v) {
   float* d = nullptr;
-  KKX_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(float)));
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(float);
+  KKX_CUDA(cudaMalloc(&d, bytes));
   owned_.push_back(d);
+  device_bytes += bytes;
   KKX_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
   return d;
 }
@@ -153,7 +233,7 @@ uint16_t f2bf(float f) {  // round-to-nearest-even fp32 -> bf16
 }
 }  // namespace
 
-TcW Model::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
+TcW WeightSet::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
   TcW t;
   t.Ci = Ci; t.Co = Co; t.ks = ks; t.Cpad = (Ci + 63) & ~63;
   std::vector<uint16_t> h((size_t)Co * ks * t.Cpad, 0);
@@ -163,6 +243,7 @@ TcW Model::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
         h[((size_t)o * ks + k) * t.Cpad + c] = f2bf(w[((size_t)o * ks + k) * Ci + c]);
   KKX_CUDA(cudaMalloc(&t.w, h.size() * 2));
   owned_.push_back(t.w);
+  device_bytes += h.size() * 2;
   KKX_CUDA(cudaMemcpy(t.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   make_tmap_bf16(t.tmap, t.w, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n(Co));
   return t;
@@ -184,7 +265,7 @@ std::vector<float> concat(std::initializer_list<const HostTensor*> ts) {
 }
 }  // namespace
 
-TcW32 Model::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) {
+TcW32 WeightSet::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) {
   TcW32 t;
   t.Ci = Ci; t.Co = Co; t.ks = ks; t.Cpad = (Ci + 63) & ~63;
   std::vector<float> hi((size_t)Co * ks * t.Cpad, 0.f), lo((size_t)Co * ks * t.Cpad, 0.f);
@@ -207,7 +288,7 @@ TcW32 Model::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) {
   return t;
 }
 
-void Model::load_weights(const WeightFile& wf) {
+void WeightSet::load(const WeightFile& wf) {
   auto U = [&](const std::string& n) { return up(raw(wf, n)); };
   auto LT = [&](const std::string& n, int N, int K) { return up(linT(wf, n, N, K)); };
   auto CW = [&](const std::string& n, int Co, int Ci, int k) { return up(convW(wf, n, Co, Ci, k)); };
@@ -423,47 +504,61 @@ void Model::load_weights(const WeightFile& wf) {
 }
 
 // ============================================================================ helpers
-Level Model::make_level(const std::vector<int>& lens, Arena& A) {
+void Model::upload(void* dst, const void* src, size_t bytes) {
+  if (bytes == 0 || g_dry_run) return;
+  void* stg = pin_.alloc_bytes(bytes);
+  if (!stg) {   // staging full: everything issued so far has to land before the arena can be reused
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    pin_.reset();
+    pin_.reserve(std::max<size_t>(bytes * 2, size_t(4) << 20));
+    stg = pin_.alloc_bytes(bytes);
+    if (!stg) throw CudaError("pinned staging arena exhausted");
+  }
+  memcpy(stg, src, bytes);
+  KKX_CUDA(cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, stream_));
+}
+
+Level Model::make_level(const std::vector<int>& lens, Arena& A, int first_off) {
   Level L;
   L.B = (int)lens.size();
   L.len = lens;
   L.off.resize(L.B);
-  int o = kGapRows;
+  long long o = first_off;
   for (int b = 0; b < L.B; b++) {
-    L.off[b] = o;
-    o = (o + lens[b] + kGapRows + 7) & ~7;
+    L.off[b] = (int)o;
+    o = (o + lens[b] + kGapRows + 7) & ~7LL;
+    if (o > 0x7fffff00LL) throw ArgError("batch too large: packed row offsets exceed int32");
     L.max_len = std::max(L.max_len, lens[b]);
     L.sum_len += lens[b];
   }
-  L.rows = o;
-  L.d_off = A.alloc<int>(L.B);
-  L.d_len = A.alloc<int>(L.B);
-  L.d_tiles128 = A.alloc<int>(L.B + 1);
-  L.d_tiles256 = A.alloc<int>(L.B + 1);
-  L.d_tiles512 = A.alloc<int>(L.B + 1);
-  std::vector<int> t128(L.B + 1, 0), t256(L.B + 1, 0), t512(L.B + 1, 0);
+  L.rows = (int)o;
+  // one device block, one upload: off[B] len[B] tiles128[B+1] tiles256[B+1] tiles512[B+1]
+  const size_t n = (size_t)5 * L.B + 3;
+  int* d = A.alloc<int>(n);
+  L.d_off = d; L.d_len = d + L.B;
+  L.d_tiles128 = d + 2 * L.B; L.d_tiles256 = L.d_tiles128 + L.B + 1; L.d_tiles512 = L.d_tiles256 + L.B + 1;
+  std::vector<int> h(n, 0);
+  int* t128 = h.data() + 2 * L.B; int* t256 = t128 + L.B + 1; int* t512 = t256 + L.B + 1;
   for (int b = 0; b < L.B; b++) {
+    h[b] = L.off[b]; h[L.B + b] = lens[b];
     t128[b + 1] = t128[b] + (lens[b] + 127) / 128;
     t256[b + 1] = t256[b] + (lens[b] + 255) / 256;
     t512[b + 1] = t512[b] + (lens[b] + 511) / 512;
   }
   L.ntiles128 = t128[L.B]; L.ntiles256 = t256[L.B]; L.ntiles512 = t512[L.B];
-  if (!g_dry_run) {
-    KKX_CUDA(cudaMemcpyAsync(L.d_off, L.off.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    KKX_CUDA(cudaMemcpyAsync(L.d_len, L.len.data(), L.B * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    KKX_CUDA(cudaMemcpyAsync(L.d_tiles128, t128.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    KKX_CUDA(cudaMemcpyAsync(L.d_tiles256, t256.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    KKX_CUDA(cudaMemcpyAsync(L.d_tiles512, t512.data(), (L.B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
-    KKX_CUDA(cudaStreamSynchronize(stream_));  // L.off / L.len are locals of the caller's frame
-  }
+  upload(d, h.data(), n * sizeof(int));
   return L;
 }
 
 void Model::capture(const char* name, const float* p, int ld, int col, int cols, const Level& L,
                     int item0) {
   if (!debug_ || g_dry_run) return;
+  bool any = false;
+  for (int b = 0; b < L.B; b++) any = any || want_debug(item0 + b);
+  if (!any) return;
   KKX_CUDA(cudaStreamSynchronize(stream_));
   for (int b = 0; b < L.B; b++) {
+    if (!want_debug(item0 + b)) continue;
     DebugStage s;
     s.rows = L.len[b]; s.cols = cols;
     s.data.resize((size_t)s.rows * cols);
@@ -481,6 +576,7 @@ const DebugStage* Model::debug_stage(const std::string& name, int item) const {
 
 void Model::set_noise(const float* noise, long long n) {
   KKX_CUDA(cudaSetDevice(device_));
+  KKX_CUDA(cudaStreamSynchronize(stream_));
   if (d_noise_) { cudaFree(d_noise_); d_noise_ = nullptr; }
   noise_n_ = 0;
   if (noise && n > 0) {
@@ -490,13 +586,23 @@ void Model::set_noise(const float* noise, long long n) {
   }
 }
 
-void Model::set_inject(const std::string& name, const void* data, long long count) {
+void Model::set_inject(const std::string& name, int item, const void* data, long long count) {
+  if (item < 0) throw ArgError("inject: item index must be >= 0");
+  const bool clear = !data || count <= 0;
   if (name == "pred_dur") {
-    inj_dur_.assign((const int*)data, (const int*)data + (data ? count : 0));
-  } else if (name == "F0") {
-    inj_f0_.assign((const float*)data, (const float*)data + (data ? count : 0));
-  } else if (name == "N") {
-    inj_n_.assign((const float*)data, (const float*)data + (data ? count : 0));
+    if (clear) { inj_dur_.erase(item); return; }
+    const int* d = static_cast<const int*>(data);
+    long long sum = 0;
+    for (long long i = 0; i < count; i++) {
+      if (d[i] < 1 || d[i] > 500) throw ArgError("inject pred_dur: every duration must be in 1..500");
+      sum += d[i];
+    }
+    if (sum > kMaxItemFrames) throw ArgError("inject pred_dur: more than " + std::to_string(kMaxItemFrames) + " frames");
+    inj_dur_[item].assign(d, d + count);
+  } else if (name == "F0" || name == "N") {
+    auto& m = name == "F0" ? inj_f0_ : inj_n_;
+    if (clear) { m.erase(item); return; }
+    m[item].assign(static_cast<const float*>(data), static_cast<const float*>(data) + count);
   } else {
     throw ArgError("unknown inject name: " + name);
   }
@@ -506,36 +612,42 @@ void Model::set_inject(const std::string& name, const void* data, long long coun
 // ============================================================================ staging / IO
 void Model::stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
                   const float* speeds) {
+  // ---- validate everything first: a rejected batch must leave the session exactly as it was
   if (B <= 0) throw ArgError("batch must be >= 1");
   if (!tokens || !tok_offsets || !speeds) throw ArgError("null input pointer");   // styles == nullptr: filled by stage_voices
-  KKX_CUDA(cudaSetDevice(device_));
+  if (tok_offsets[0] < 0) throw ArgError("tok_offsets[0] must be >= 0");
   std::vector<int> lens(B);
   for (int b = 0; b < B; b++) {
-    const int n = tok_offsets[b + 1] - tok_offsets[b];
+    const long long n = (long long)tok_offsets[b + 1] - tok_offsets[b];
     if (n < 1 || n > 512) throw ArgError("n_tokens must be in 1..512 (got " + std::to_string(n) + ")");
-    if (!(speeds[b] > 0.f)) throw ArgError("speed must be > 0");
-    lens[b] = n;
+    if (!(speeds[b] >= kMinSpeed && speeds[b] <= kMaxSpeed))
+      throw ArgError("speed must be in [0.1, 10] (got " + std::to_string(speeds[b]) + ")");
+    lens[b] = (int)n;
+    for (int t = 0; t < lens[b]; t++) {
+      const int64_t id = tokens[tok_offsets[b] + t];
+      if (id < 0 || id > 177) throw ArgError("token id out of range 0..177: " + std::to_string(id));
+    }
   }
+  // ---- commit
+  KKX_CUDA(cudaSetDevice(device_));
+  staged_ = false; ran_ = false; B_ = 0;
+  pin_.reset();                                  // the stream is idle here: run() drains it before returning
   ioA_.reserve((size_t)B * (560 * 4 + 1024 + 64) + (1 << 20));
   ioA_.reset();
   g_dry_run = false;
   tokL_ = make_level(lens, ioA_);
   std::vector<int> ids((size_t)tokL_.rows, 0);
   for (int b = 0; b < B; b++)
-    for (int t = 0; t < lens[b]; t++) {
-      const int64_t id = tokens[tok_offsets[b] + t];
-      if (id < 0 || id > 177) throw ArgError("token id out of range 0..177: " + std::to_string(id));
-      ids[tokL_.off[b] + t] = (int)id;
-    }
+    for (int t = 0; t < lens[b]; t++) ids[tokL_.off[b] + t] = (int)tokens[tok_offsets[b] + t];
   d_ids_ = ioA_.alloc<int>(tokL_.rows);
   d_styles_ = ioA_.alloc<float>((size_t)B * 256);
   d_speeds_ = ioA_.alloc<float>(B);
-  KKX_CUDA(cudaMemcpyAsync(d_ids_, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
-  if (styles) KKX_CUDA(cudaMemcpyAsync(d_styles_, styles, (size_t)B * 256 * sizeof(float), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaMemcpyAsync(d_speeds_, speeds, B * sizeof(float), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaStreamSynchronize(stream_));
+  upload(d_ids_, ids.data(), ids.size() * sizeof(int));
+  if (styles) upload(d_styles_, styles, (size_t)B * 256 * sizeof(float));
+  upload(d_speeds_, speeds, B * sizeof(float));
   B_ = B;
   tok_len_ = lens;
+  staged_ = true;
 }
 
 void Model::load_voices(const float* table, int n_voices) {
@@ -554,6 +666,7 @@ void Model::stage_voices(int B, const int64_t* tokens, const int32_t* tok_offset
                          const float* speeds) {
   if (!d_voices_) throw ArgError("no voice table loaded (kkx_load_voices)");
   if (B <= 0 || !mix_offsets || !voice_ids || !portions || !style_rows) throw ArgError("null input pointer");
+  if (mix_offsets[0] < 0) throw ArgError("mix_offsets[0] must be >= 0");
   for (int b = 0; b < B; b++) {
     if (mix_offsets[b + 1] <= mix_offsets[b]) throw ArgError("every item needs at least one voice");
     if (style_rows[b] < 0 || style_rows[b] > 510) throw ArgError("style row must be in 0..510 (koko.rs:1262 indexes a 511-row table)");
@@ -561,21 +674,23 @@ void Model::stage_voices(int B, const int64_t* tokens, const int32_t* tok_offset
       if (voice_ids[i] < 0 || voice_ids[i] >= n_voices_) throw ArgError("voice id out of range");
   }
   stage(B, tokens, tok_offsets, nullptr, speeds);
+  staged_ = false;                               // not runnable until the styles are mixed
   const int nmix = mix_offsets[B];
   int* d_mo = ioA_.alloc<int>(B + 1);
   int* d_vi = ioA_.alloc<int>(nmix);
   float* d_po = ioA_.alloc<float>(nmix);
   int* d_rows = ioA_.alloc<int>(B);
-  KKX_CUDA(cudaMemcpyAsync(d_mo, mix_offsets, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaMemcpyAsync(d_vi, voice_ids, nmix * sizeof(int), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaMemcpyAsync(d_po, portions, nmix * sizeof(float), cudaMemcpyHostToDevice, stream_));
-  KKX_CUDA(cudaMemcpyAsync(d_rows, style_rows, B * sizeof(int), cudaMemcpyHostToDevice, stream_));
+  upload(d_mo, mix_offsets, (B + 1) * sizeof(int));
+  upload(d_vi, voice_ids, nmix * sizeof(int));
+  upload(d_po, portions, nmix * sizeof(float));
+  upload(d_rows, style_rows, B * sizeof(int));
   g_launch_stats = nullptr;
   launch_mix_styles(d_voices_, d_mo, d_vi, d_po, d_rows, d_styles_, B, stream_);
-  KKX_CUDA(cudaStreamSynchronize(stream_));   // the index arrays are the caller's
+  staged_ = true;
 }
 
 void Model::fetch_pcm16(short* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur) {
+  if (!ran_) throw StateError("no completed run to fetch from");
   if (!d_pcm_ || !pcm_valid_) throw ArgError("the last run did not produce 16-bit PCM");
   fetch(nullptr, 0, sample_offsets, pred_dur);
   if (dst) {
@@ -586,13 +701,14 @@ void Model::fetch_pcm16(short* dst, long long capacity, int64_t* sample_offsets,
 }
 
 void Model::fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur) {
+  if (!ran_ || B_ <= 0 || (int)sample_off_.size() != B_ + 1) throw StateError("no completed run to fetch from");
   KKX_CUDA(cudaSetDevice(device_));
   if (sample_offsets)
     for (int b = 0; b <= B_; b++) sample_offsets[b] = sample_off_[b];
   if (pred_dur) {
     size_t k = 0;
     for (int b = 0; b < B_; b++)
-      for (int t = 0; t < tok_len_[b]; t++) pred_dur[k++] = pred_dur_h_[tokL_.off[b] + t];
+      for (int t = 0; t < tok_len_[b]; t++) pred_dur[k++] = h_pred_dur_[tokL_.off[b] + t];
   }
   if (dst) {
     if (capacity < total_samples_) throw ArgError("audio buffer too small");
@@ -603,8 +719,9 @@ void Model::fetch(float* dst, long long capacity, int64_t* sample_offsets, int32
 
 // ============================================================================ forward
 void Model::run() {
-  if (B_ <= 0) throw ArgError("no batch staged");
+  if (!staged_ || B_ <= 0) throw StateError("no batch staged");
   KKX_CUDA(cudaSetDevice(device_));
+  ran_ = false;
   g_launch_stats = &stats;
   stats.launches = 0;
   stats.conv_flops = 0;
@@ -612,10 +729,16 @@ void Model::run() {
   stats.n_events = 0;
   stats.names.clear();
   dbg_.clear();
+  group_first_.clear();
   KKX_CUDA(cudaEventRecord(ev0_, stream_));
   if (stats.profile) cudaEventRecord(stats.next_event(), stream_);
   Run r;
-  token_phase(r);
+  try {
+    token_phase(r);
+  } catch (...) {
+    cudaStreamSynchronize(stream_);   // nothing may still be reading the staging / arenas when the caller retries
+    throw;
+  }
 
   // frame-phase groups under the frame budget
   sample_off_.assign(B_ + 1, 0);
@@ -627,56 +750,67 @@ void Model::run() {
   if ((size_t)total_samples_ > audio_cap_) {
     KKX_CUDA(cudaStreamSynchronize(stream_));
     if (d_audio_) cudaFree(d_audio_);
-    audio_cap_ = (size_t)total_samples_ + (size_t)total_samples_ / 4;
-    KKX_CUDA(cudaMalloc(&d_audio_, audio_cap_ * sizeof(float)));
+    d_audio_ = nullptr; audio_cap_ = 0;
+    const size_t cap = (size_t)total_samples_ + (size_t)total_samples_ / 4;
+    KKX_CUDA(cudaMalloc(&d_audio_, cap * sizeof(float)));
+    audio_cap_ = cap;
   }
   if (want_pcm_ && (size_t)total_samples_ > pcm_cap_) {
     KKX_CUDA(cudaStreamSynchronize(stream_));
     if (d_pcm_) cudaFree(d_pcm_);
-    pcm_cap_ = (size_t)total_samples_ + (size_t)total_samples_ / 4;
-    KKX_CUDA(cudaMalloc(&d_pcm_, pcm_cap_ * sizeof(short)));
+    d_pcm_ = nullptr; pcm_cap_ = 0;
+    const size_t cap = (size_t)total_samples_ + (size_t)total_samples_ / 4;
+    KKX_CUDA(cudaMalloc(&d_pcm_, cap * sizeof(short)));
+    pcm_cap_ = cap;
   }
   pcm_valid_ = want_pcm_;
   sink_filled_ = false;
   float* sink = (host_sink && !debug_) ? host_sink(total_samples_) : nullptr;
   // (both streams are idle here: the previous run synchronised them, and d_audio_ was sized above)
-  int b0 = 0;
-  while (b0 < B_) {
-    int b1 = b0; long long fr = 0;
-    // at most 512 items per group: the fused generator kernels keep per-item tables in shared memory, and a
-    // batch must take the same code path as a single call (results are bit-identical either way)
-    while (b1 < B_ && b1 - b0 < 512 && (b1 == b0 || fr + r.T[b1] <= opt.max_frames)) { fr += r.T[b1]; b1++; }
-    // size the arena with a dry run of the same allocation sequence (no launches, no copies)
-    frA_.reset();
-    frA_.set_virtual(true);
-    g_dry_run = true;
-    try {
-      frame_phase(r, b0, b1, true);
-    } catch (...) {
-      g_dry_run = false; frA_.set_virtual(false);
-      throw;
+  try {
+    int b0 = 0;
+    while (b0 < B_) {
+      int b1 = b0; long long fr = 0;
+      // at most 512 items per group: the fused generator kernels keep per-item tables in shared memory, and a
+      // batch must take the same code path as a single call (results are bit-identical either way)
+      while (b1 < B_ && b1 - b0 < 512 && (b1 == b0 || fr + r.T[b1] <= opt.max_frames)) { fr += r.T[b1]; b1++; }
+      group_first_.push_back(b0);
+      // size the arena with a dry run of the same allocation sequence (no launches, no copies)
+      frA_.reset();
+      frA_.set_virtual(true);
+      g_dry_run = true;
+      try {
+        frame_phase(r, b0, b1, true);
+      } catch (...) {
+        g_dry_run = false; frA_.set_virtual(false);
+        throw;
+      }
+      g_dry_run = false;
+      frA_.set_virtual(false);
+      const size_t need = frA_.used();
+      if (need + (1 << 20) > frA_.capacity()) {
+        KKX_CUDA(cudaStreamSynchronize(stream_));
+        frA_.reserve(need + need / 8 + (1 << 20));
+      }
+      frA_.reset();
+      frame_phase(r, b0, b1, false);
+      if (sink) {   // this group's audio goes to the host while the next group computes
+        const long long s0 = sample_off_[b0], s1 = sample_off_[b1];
+        KKX_CUDA(cudaEventRecord(ev_grp_, stream_));
+        KKX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_grp_, 0));
+        if (s1 > s0)
+          KKX_CUDA(cudaMemcpyAsync(sink + s0, d_audio_ + s0, (size_t)(s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, copy_stream_));
+      }
+      b0 = b1;
     }
-    g_dry_run = false;
-    frA_.set_virtual(false);
-    const size_t need = frA_.used();
-    if (need + (1 << 20) > frA_.capacity()) {
-      KKX_CUDA(cudaStreamSynchronize(stream_));
-      frA_.reserve(need + need / 8 + (1 << 20));
-    }
-    frA_.reset();
-    frame_phase(r, b0, b1, false);
-    if (sink) {   // this group's audio goes to the host while the next group computes
-      const long long s0 = sample_off_[b0], s1 = sample_off_[b1];
-      KKX_CUDA(cudaEventRecord(ev_grp_, stream_));
-      KKX_CUDA(cudaStreamWaitEvent(copy_stream_, ev_grp_, 0));
-      if (s1 > s0)
-        KKX_CUDA(cudaMemcpyAsync(sink + s0, d_audio_ + s0, (size_t)(s1 - s0) * sizeof(float), cudaMemcpyDeviceToHost, copy_stream_));
-    }
-    b0 = b1;
+    KKX_CUDA(cudaEventRecord(ev1_, stream_));
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    if (sink) { KKX_CUDA(cudaStreamSynchronize(copy_stream_)); sink_filled_ = true; }
+  } catch (...) {
+    cudaStreamSynchronize(stream_);
+    cudaStreamSynchronize(copy_stream_);
+    throw;
   }
-  KKX_CUDA(cudaEventRecord(ev1_, stream_));
-  KKX_CUDA(cudaStreamSynchronize(stream_));
-  if (sink) { KKX_CUDA(cudaStreamSynchronize(copy_stream_)); sink_filled_ = true; }
   arb_timing_dump();
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0_, ev1_);
@@ -691,6 +825,7 @@ void Model::run() {
     }
   }
   g_launch_stats = nullptr;
+  ran_ = true;
 }
 
 }  // namespace kkx

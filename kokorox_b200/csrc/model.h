@@ -2,6 +2,7 @@
 #pragma once
 #include "common.h"
 #include "kernels.h"
+#include <deque>
 #include <functional>
 #include <map>
 #include <memory>
@@ -17,17 +18,35 @@ struct HostTensor {
   size_t numel = 0;
 };
 
-// Reads a KKXW0001 file (kokorox_b200/weightfile.py) into host memory.
+// The checkpoint as named fp32 host tensors (upstream state-dict names, weight-norm folded).  Two sources,
+// dispatched on the file's magic -- OrtKoko::new receives the path of the downloaded model file
+// (ort_koko.rs:31-35, ort_base.rs:27-33, hf_cache.rs:135-144), so kkx_create accepts that file as it is:
+//   * "KKXW0001": the flat file kokorox_b200/weightfile.py writes (random-init recipe, .pth converter);
+//   * an ONNX ModelProto (kokoro-v1.0.onnx / onnx/model*.onnx): onnx_loader.cu reads the protobuf wire format,
+//     names the anonymised initialisers through the node graph and dequantises fp16 / int8 / 4-bit variants.
 class WeightFile {
  public:
   explicit WeightFile(const std::string& path);
   const HostTensor& get(const std::string& name) const;
   bool has(const std::string& name) const { return t_.count(name) != 0; }
+  // takes ownership of `data` (used by the ONNX reader); an existing entry of that name is replaced
+  void put(const std::string& name, const std::vector<int>& shape, std::vector<float>&& data);
+  void erase(const std::string& name) { t_.erase(name); }
+  std::vector<std::string> names() const;
+  const std::string& format() const { return format_; }   // "kkxw" or "onnx"
 
  private:
+  void load_kkxw(const std::string& path);
   std::vector<char> buf_;
+  std::deque<std::vector<float>> owned_;
   std::map<std::string, HostTensor> t_;
+  std::string format_;
 };
+// onnx_loader.cu: fills `out` with the Kokoro-82M state dict recovered from an ONNX file image; throws IoError
+// listing every tensor it could not resolve.
+void load_onnx_weights(const std::string& path, const std::vector<char>& bytes, WeightFile& out);
+// (name, shape) of every tensor of Kokoro-82M that WeightSet::load reads (onnx_loader.cu)
+std::vector<std::pair<std::string, std::vector<int>>> kokoro_tensor_specs();
 
 // bf16 weight [Co][ks][Cpad] + its TMA descriptor (tensor-core path)
 struct TcW {
@@ -97,18 +116,50 @@ void arb_timing_dump();  // diagnostics (model_forward.cu); no-op unless KKX_ARB
 struct DebugStage { std::vector<float> data; long long rows = 0, cols = 0; };
 
 struct Options {
-  int precision = 0;
+  // 1 (default) = the benchmarked configuration: decoder + generator convs on tcgen05 with bf16 operands, predictor
+  // on split-TF32 tensor cores; 0 = fp32 SIMT everywhere (verification mode, tightest parity, ~6x slower)
+  int precision = 1;
   unsigned long long noise_seed = 0x5eed;
   int max_frames = 49152;
   int stft_replicate = 0;
 };
+
+// Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
+// tensor-core copies with their TMA descriptors).  Immutable after construction and shared by every session created
+// from the same (file, device): the reference's servers build two or three sessions of one model (koko main.rs:1477,
+// 1596; TTSManager koko.rs:129-142) and each OrtKoko::new re-loads the file; here the second kkx_create is free.
+class WeightSet {
+ public:
+  static std::shared_ptr<const WeightSet> acquire(const std::string& path, int device);
+  ~WeightSet();
+  WeightSet(const WeightSet&) = delete;
+  WeightSet& operator=(const WeightSet&) = delete;
+  Weights W;
+  int device = 0;
+  size_t device_bytes = 0;
+  std::string format;          // "kkxw" / "onnx"
+
+ private:
+  WeightSet() = default;
+  void load(const WeightFile& wf);
+  float* up(const std::vector<float>& v);
+  TcW make_tc(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
+  TcW32 make_tc32(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
+  std::vector<void*> owned_;
+};
+
+// Hard limits that keep every row / sample index inside int32 and the frame arena inside one GPU:
+constexpr float kMinSpeed = 0.1f, kMaxSpeed = 10.f;   // dur per token <= 50 / speed <= 500 frames
+constexpr int kMaxItemFrames = 65536;                  // one utterance: <= 27 min of audio (120*T+1 rows fit int32)
 
 class Model {
  public:
   Model(const std::string& weights_path, int device);
   ~Model();
 
-  // Stage inputs on the device (H2D), run the forward pass, fetch results (D2H).
+  // Stage inputs on the device (H2D), run the forward pass, fetch results (D2H).  stage() validates everything
+  // before it touches the session state, so a rejected batch leaves the previous one intact; run() needs a staged
+  // batch and fetch() a completed run (StateError otherwise).
   void stage(int B, const int64_t* tokens, const int32_t* tok_offsets, const float* styles,
              const float* speeds);
   // styles taken from the device-resident voice table (load_voices) instead of host vectors
@@ -127,9 +178,10 @@ class Model {
   void fetch(float* dst, long long capacity, int64_t* sample_offsets, int32_t* pred_dur);
 
   void set_noise(const float* noise, long long n);
-  void set_inject(const std::string& name, const void* data, long long count);
-  void set_debug(bool on) { debug_ = on; }
+  void set_inject(const std::string& name, int item, const void* data, long long count);
+  void set_debug(bool on, int item = -1) { debug_ = on; debug_item_ = item; }
   const DebugStage* debug_stage(const std::string& name, int item) const;
+  const std::vector<int>& group_first() const { return group_first_; }   // first item of each frame group of the last run
 
   Options opt;
   LaunchStats stats;
@@ -138,6 +190,8 @@ class Model {
   std::map<std::string, std::pair<long long, double>> prof_;  // kernel -> (launches, total us)
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
+  const WeightSet& weight_set() const { return *ws_; }
+  long weight_sessions() const { return ws_.use_count(); }   // sessions sharing this device weight set
 
  private:
   struct Run {  // per-call state
@@ -151,10 +205,6 @@ class Model {
     std::vector<int> T;        // frames per item (host)
     Level styL;                // one item of B rows (style FC GEMMs)
   };
-  void load_weights(const WeightFile& wf);
-  float* up(const std::vector<float>& v);
-  TcW make_tc(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
-  TcW32 make_tc32(const std::vector<float>& w_co_ks_ci, int Co, int ks, int Ci);
   // Linear / Conv1d on the precision-critical path: split-TF32 tensor cores when precision==1 and
   // the weight has a TcW32, fp32 SIMT otherwise.
   void gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
@@ -175,19 +225,25 @@ class Model {
   void arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
            int sld, float* xw, float* t1, float* out, float oscale, bool accumulate,
            const float* part_x = nullptr);
-  Level make_level(const std::vector<int>& lens, Arena& A);
+  // first_off: row offset of item 0 (kGapRows for activations; 0 for the per-item style tables)
+  Level make_level(const std::vector<int>& lens, Arena& A, int first_off = kGapRows);
+  // copy `bytes` of host data to device memory through the pinned staging arena (true async copy on stream_)
+  void upload(void* dst, const void* src, size_t bytes);
   void capture(const char* name, const float* p, int ld, int col, int cols, const Level& L,
                int item0);
+  bool want_debug(int item) const { return debug_ && (debug_item_ < 0 || debug_item_ == item); }
 
   int device_ = 0;
+  std::shared_ptr<const WeightSet> ws_;
+  const Weights& W;
   cudaStream_t stream_ = nullptr;
-  std::vector<void*> owned_;  // device weight allocations
-  Weights W;
   Arena tokA_, frA_, ioA_;
-  bool debug_ = false;
+  PinnedArena pin_;
+  bool debug_ = false; int debug_item_ = -1;
   std::map<std::string, DebugStage> dbg_;
   // staged inputs
   int B_ = 0;
+  bool staged_ = false, ran_ = false;
   std::vector<int> tok_len_;
   int* d_ids_ = nullptr; float* d_styles_ = nullptr; float* d_speeds_ = nullptr;
   Level tokL_;
@@ -196,11 +252,14 @@ class Model {
   short* d_pcm_ = nullptr; size_t pcm_cap_ = 0; bool want_pcm_ = false, pcm_valid_ = false;   // optional 16-bit PCM twin of d_audio_
   float* d_voices_ = nullptr; int n_voices_ = 0;                           // [V][511][256] voice table
   std::vector<long long> sample_off_;
-  std::vector<int> pred_dur_h_;
+  int* h_pred_dur_ = nullptr; size_t h_pred_dur_cap_ = 0;                  // pinned: per-row integer durations of the last run
+  int* h_T_ = nullptr; size_t h_T_cap_ = 0;                                // pinned: frames per item
   long long total_samples_ = 0;
+  std::vector<int> group_first_;
   // test hooks
   float* d_noise_ = nullptr; long long noise_n_ = 0;
-  std::vector<int> inj_dur_; std::vector<float> inj_f0_, inj_n_;
+  std::map<int, std::vector<int>> inj_dur_;
+  std::map<int, std::vector<float>> inj_f0_, inj_n_;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   cudaStream_t copy_stream_ = nullptr; cudaEvent_t ev_grp_ = nullptr; bool sink_filled_ = false;
 };

@@ -13,7 +13,7 @@ namespace {
 // -DKKX_ARB_TIMING build); 4 variants (conv1/conv2 x C128/C256) x 32 slots
 long long* g_arb_timing = nullptr;
 long long* arb_timing_buf() {
-  static const bool on = [] { const char* e = getenv("KKX_ARB_TIMING"); return e && e[0] == '1'; }();
+  static const bool on = env_flag("KKX_ARB_TIMING", false);
   if (!on) return nullptr;
   if (!g_arb_timing) {
     KKX_CUDA(cudaMalloc(&g_arb_timing, 128 * sizeof(long long)));
@@ -87,7 +87,7 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
     // 2-CTA clusters with TMA-multicast weight tiles: measured on B200 NOT faster (13.9 vs 12.4 ms for the 12 qkv
     // GEMMs): these GEMMs are bound by what each SM can ingest (~28 B/clk: 64 KB of hi/lo planes per 128x128x32
     // step), which multicast does not change.  Opt-in (KKX_TC_CLUSTER=1).
-    static const bool cl_ok = [] { const char* e = getenv("KKX_TC_CLUSTER"); return e && e[0] == '1'; }();
+    static const bool cl_ok = env_flag("KKX_TC_CLUSTER", false);
     if (w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = cl_ok ? 2 : 1; }
     a.Cpad = w32->Cpad; a.Ci = K; a.Co = N; a.ks = ks; a.dil = 1; a.pad = pad;
     a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
@@ -123,14 +123,7 @@ void Model::token_phase(Run& r) {
   Arena& A = tokA_;
 
   // style-parameter tables for every AdaIN / AdaLN of the model: two GEMMs over the batch
-  r.styL = make_level(std::vector<int>{B}, A);
-  // make_level puts the single item at row kGapRows; style rows live at [0,B) -> use explicit offsets
-  {
-    int zero = 0;
-    KKX_CUDA(cudaMemcpyAsync(r.styL.d_off, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
-    KKX_CUDA(cudaStreamSynchronize(st));
-    r.styL.off[0] = 0;
-  }
+  r.styL = make_level(std::vector<int>{B}, A, 0);   // one "item" of B rows at row 0
   r.sty_pro = A.alloc<float>((size_t)B * W.sty_pro_n);
   r.sty_dec = A.alloc<float>((size_t)B * W.sty_dec_n);
   launch_conv_f32(gemm_args(r.styL, d_styles_ + 128, 256, 128, W.sty_pro_w, W.sty_pro_b, W.sty_pro_n,
@@ -206,10 +199,11 @@ void Model::token_phase(Run& r) {
   r.total = A.alloc<int>(B);
   launch_duration(logits, 50, d_speeds_, r.pred_dur, durf, L.d_off, L.d_len, B, L.max_len, st);
   capture("dur_float", durf, 1, 0, 1, L, 0);
-  if (!inj_dur_.empty()) {
-    if ((int)inj_dur_.size() != L.len[0]) throw ArgError("inject pred_dur: length != n_tokens of item 0");
-    KKX_CUDA(cudaMemcpyAsync(r.pred_dur + L.off[0], inj_dur_.data(), inj_dur_.size() * sizeof(int),
-                             cudaMemcpyHostToDevice, st));
+  for (auto& kv : inj_dur_) {   // test hook: teacher-forced durations of single items
+    const int b = kv.first;
+    if (b >= B) throw ArgError("inject pred_dur: item index out of range");
+    if ((int)kv.second.size() != L.len[b]) throw ArgError("inject pred_dur: length != n_tokens of the item");
+    upload(r.pred_dur + L.off[b], kv.second.data(), kv.second.size() * sizeof(int));
   }
   launch_dur_scan(r.pred_dur, r.cum, 512, r.total, L.d_off, L.d_len, B, st);
 
@@ -233,10 +227,28 @@ void Model::token_phase(Run& r) {
   split_hi_ = split_lo_ = nullptr; split_cap_ = 0;
   // ---- the one mid-pipeline host sync: frame counts decide every later launch shape
   r.T.resize(B);
-  pred_dur_h_.resize(R);
-  KKX_CUDA(cudaMemcpyAsync(r.T.data(), r.total, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  KKX_CUDA(cudaMemcpyAsync(pred_dur_h_.data(), r.pred_dur, R * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (R > h_pred_dur_cap_) {
+    if (h_pred_dur_) cudaFreeHost(h_pred_dur_);
+    h_pred_dur_ = nullptr; h_pred_dur_cap_ = 0;
+    KKX_CUDA(cudaMallocHost(&h_pred_dur_, (R + R / 4) * sizeof(int)));
+    h_pred_dur_cap_ = R + R / 4;
+  }
+  if ((size_t)B > h_T_cap_) {
+    if (h_T_) cudaFreeHost(h_T_);
+    h_T_ = nullptr; h_T_cap_ = 0;
+    KKX_CUDA(cudaMallocHost(&h_T_, ((size_t)B + 64) * sizeof(int)));
+    h_T_cap_ = (size_t)B + 64;
+  }
+  KKX_CUDA(cudaMemcpyAsync(h_T_, r.total, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  KKX_CUDA(cudaMemcpyAsync(h_pred_dur_, r.pred_dur, R * sizeof(int), cudaMemcpyDeviceToHost, st));
   KKX_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < B; b++) {
+    r.T[b] = h_T_[b];
+    // 1 <= dur <= 50 / speed per token by construction; the cap bounds every later row / sample index
+    if (r.T[b] < 1 || r.T[b] > kMaxItemFrames)
+      throw ArgError("item " + std::to_string(b) + ": " + std::to_string(r.T[b]) + " frames is outside 1.." +
+                     std::to_string(kMaxItemFrames) + " (utterance too long for one call at this speed)");
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,7 +336,7 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
   const float* cur = x;
   const bool tc = opt.precision == 1;
   void* abuf = tc ? A.alloc_bytes((size_t)L.rows * w.t1[0].Cpad * 2) : nullptr;
-  static const bool fused_ok = [] { const char* e = getenv("KKX_ARB_FUSED"); return !e || e[0] != '0'; }();
+  static const bool fused_ok = env_flag("KKX_ARB_FUSED", true);
   if (tc && fused_ok && arb_conv_supported(C, k, 5, B)) {
     // fused path (kernels_arb.cu): AdaIN + Snake inside the conv kernel, bf16 intermediate, column
     // statistics for the next AdaIN from the conv epilogues -- one colstats pass per res-block
@@ -424,12 +436,9 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   int* d_ph_off = A.alloc<int>(B);
   long long* d_s_loc = A.alloc<long long>(B);
   long long* d_s_glob = A.alloc<long long>(B);
-  if (!dry) {
-    KKX_CUDA(cudaMemcpyAsync(d_ph_off, ph_off.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
-    KKX_CUDA(cudaMemcpyAsync(d_s_loc, s_loc.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
-    KKX_CUDA(cudaMemcpyAsync(d_s_glob, s_glob.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
-    KKX_CUDA(cudaStreamSynchronize(st));
-  }
+  upload(d_ph_off, ph_off.data(), B * sizeof(int));
+  upload(d_s_loc, s_loc.data(), B * sizeof(long long));
+  upload(d_s_glob, s_glob.data(), B * sizeof(long long));
 
   // ---- length regulation (K4/K5)
   int* idx = A.alloc<int>(FR.rows);
@@ -440,13 +449,18 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   launch_gather_rows(r.t_en, 512, tok_off, idx, FR.d_off, FR.d_len, 512, x514, 520, 0, B, FR.max_len, st);
   if (debug_ && !dry) {
     // idx as float for the debug channel
-    KKX_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> hi(FR.rows);
-    KKX_CUDA(cudaMemcpy(hi.data(), idx, FR.rows * sizeof(int), cudaMemcpyDeviceToHost));
-    for (int b = 0; b < B; b++) {
-      DebugStage s; s.rows = FR.len[b]; s.cols = 1; s.data.resize(FR.len[b]);
-      for (int j = 0; j < FR.len[b]; j++) s.data[j] = (float)hi[FR.off[b] + j];
-      dbg_["idx#" + std::to_string(b0 + b)] = std::move(s);
+    bool any = false;
+    for (int b = 0; b < B; b++) any = any || want_debug(b0 + b);
+    if (any) {
+      KKX_CUDA(cudaStreamSynchronize(st));
+      std::vector<int> hi(FR.rows);
+      KKX_CUDA(cudaMemcpy(hi.data(), idx, FR.rows * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int b = 0; b < B; b++) {
+        if (!want_debug(b0 + b)) continue;
+        DebugStage s; s.rows = FR.len[b]; s.cols = 1; s.data.resize(FR.len[b]);
+        for (int j = 0; j < FR.len[b]; j++) s.data[j] = (float)hi[FR.off[b] + j];
+        dbg_["idx#" + std::to_string(b0 + b)] = std::move(s);
+      }
     }
   }
   capture("en", en, 640, 0, 640, FR, b0);
@@ -478,14 +492,15 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   }
   float* f0 = curves[0]; float* nc = curves[1];
   split_hi_ = split_lo_ = nullptr; split_cap_ = 0;   // decoder / generator use the bf16 operand path
-  if (!dry && b0 == 0) {
-    if (!inj_f0_.empty()) {
-      if ((int)inj_f0_.size() != FR2.len[0]) throw ArgError("inject F0: length != 2T of item 0");
-      KKX_CUDA(cudaMemcpyAsync(f0 + FR2.off[0], inj_f0_.data(), inj_f0_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    }
-    if (!inj_n_.empty()) {
-      if ((int)inj_n_.size() != FR2.len[0]) throw ArgError("inject N: length != 2T of item 0");
-      KKX_CUDA(cudaMemcpyAsync(nc + FR2.off[0], inj_n_.data(), inj_n_.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (!dry) {   // test hook: teacher-forced F0 / N curves of single items (any frame group)
+    for (int k = 0; k < 2; k++) {
+      for (auto& kv : (k == 0 ? inj_f0_ : inj_n_)) {
+        const int b = kv.first - b0;
+        if (kv.first >= B_) throw ArgError("inject F0/N: item index out of range");
+        if (b < 0 || b >= B) continue;
+        if ((int)kv.second.size() != FR2.len[b]) throw ArgError("inject F0/N: length != 2T of the item");
+        upload((k == 0 ? f0 : nc) + FR2.off[b], kv.second.data(), kv.second.size() * sizeof(float));
+      }
     }
   }
   capture("F0", f0, 1, 0, 1, FR2, b0);
@@ -523,8 +538,11 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   launch_sine_source(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, d_noise_, opt.noise_seed, W.lin_w,
                      W.lin_b, src, d_s_loc, B, maxS, st);
   if (debug_ && !dry) {
-    KKX_CUDA(cudaStreamSynchronize(st));
+    bool any = false;
+    for (int b = 0; b < B; b++) any = any || want_debug(b0 + b);
+    if (any) KKX_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < B; b++) {
+      if (!want_debug(b0 + b)) continue;
       DebugStage s; s.rows = 600LL * T[b]; s.cols = 1; s.data.resize(s.rows);
       KKX_CUDA(cudaMemcpy(s.data.data(), src + s_loc[b], s.rows * sizeof(float), cudaMemcpyDeviceToHost));
       dbg_["har_source#" + std::to_string(b0 + b)] = std::move(s);
@@ -640,7 +658,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
 
   // ---- head (K11)
   float* cp = A.alloc<float>((size_t)G120.rows * 24);
-  static const bool post_fused = [] { const char* e = getenv("KKX_POST_FUSED"); return !e || e[0] != '0'; }();
+  static const bool post_fused = env_flag("KKX_POST_FUSED", true);
   if (opt.precision == 1 && post_fused && arb_conv_supported(128, 7, 1, B)) {
     // fused: LeakyReLU in the operand producer, all 7 taps from one activation tile (kernels_arb.cu, POST)
     ArbConvArgs pc;

@@ -1,6 +1,7 @@
 // testapi.cu -- op-level test hooks (include/kkx_test.h).  Parity harness only.
 #include "../../include/kkx_test.h"
 #include "kernels.h"
+#include "model.h"
 #include <algorithm>
 #include <cstring>
 #include <limits>
@@ -39,6 +40,21 @@ template <class F> int run(int device, F&& f) {
 extern "C" {
 
 KKX_API const char* kkx_test_last_error(void) { return t_err.c_str(); }
+
+KKX_API int64_t kkx_test_tensor_specs(char* buf, int64_t capacity) {
+  std::string s;
+  for (auto& sp : kokoro_tensor_specs()) {
+    s += sp.first;
+    for (int d : sp.second) s += " " + std::to_string(d);
+    s += "\n";
+  }
+  if (buf && capacity > 0) {
+    const size_t n = std::min<size_t>(s.size(), (size_t)capacity - 1);
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
+}
 
 KKX_API int kkx_test_conv(int device, const float* in, int rows_in, int ldi, int Ci, const float* w,
                           const float* bias, int Co, int ks, int dil, int pad, int stride,

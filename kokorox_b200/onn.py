@@ -79,6 +79,14 @@ def load_library(path: Optional[str] = None):
         lib.kkx_get_stat.restype = i64
         lib.kkx_set_noise.argtypes = [vp, P(f32), i64]
         lib.kkx_set_inject.argtypes = [vp, C.c_char_p, vp, i64]
+        lib.kkx_set_inject_item.argtypes = [vp, i32, C.c_char_p, vp, i64]
+        lib.kkx_debug_select.argtypes = [vp, C.c_int, i32]
+        lib.kkx_submit.argtypes = [vp, P(i64), i32, P(f32), f32, P(i64)]
+        lib.kkx_poll.argtypes = [vp, i64]
+        lib.kkx_wait.argtypes = [vp, i64, P(P(f32)), P(i64), P(i32)]
+        lib.kkx_convert_model_file.argtypes = [C.c_char_p, C.c_char_p, P(i32)]
+        lib.kkx_test_tensor_specs.argtypes = [C.c_char_p, i64]
+        lib.kkx_test_tensor_specs.restype = i64
         lib.kkx_debug_stage.argtypes = [vp, C.c_char_p, i32, P(f32), i64, P(i64), P(i64)]
         lib.kkx_debug_stage.restype = i64
         lib.kkx_debug_enable.argtypes = [vp, C.c_int]
@@ -143,6 +151,30 @@ def wav_header(n_samples: Optional[int] = None, sample_rate: int = 24000, channe
     if rc != 44:
         raise KkxError(int(rc), "wav_header: bad argument")
     return bytes(buf)
+
+
+def convert_model_file(src: str, dst: str) -> int:
+    """Host-only: read ``src`` the way ``kkx_create`` does (ONNX -- fp32 / fp16 / int8 / 4-bit variants -- or KKXW)
+    and write the recovered state dict as a KKXW file.  Returns the tensor count."""
+    lib = load_library()
+    n = C.c_int32(0)
+    rc = lib.kkx_convert_model_file(os.fsencode(src), os.fsencode(dst), C.byref(n))
+    if rc != 0:
+        raise KkxError(rc, (lib.kkx_last_error(None) or b"").decode())
+    return int(n.value)
+
+
+def library_tensor_specs():
+    """[(name, shape)] the C++ loader expects (test hook; compared with weightfile.weight_specs)."""
+    lib = load_library()
+    n = lib.kkx_test_tensor_specs(None, 0)
+    buf = C.create_string_buffer(int(n) + 1)
+    lib.kkx_test_tensor_specs(buf, n + 1)
+    out = []
+    for line in buf.value.decode().splitlines():
+        parts = line.split()
+        out.append((parts[0], tuple(int(x) for x in parts[1:])))
+    return out
 
 
 def _fp(a: np.ndarray):
@@ -252,6 +284,48 @@ class B200Koko:
         weakref.finalize(out, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
         out = out[:int(ns.value)]
         return (out, dur[:tk.size]) if return_durations else out
+
+    # -- asynchronous form (kkx_submit / kkx_poll / kkx_wait): sentence k+1 synthesises while k is being sent
+    def submit(self, tokens: Sequence[int], style, speed: float = 1.0) -> int:
+        """Queue one utterance and return a ticket at once; the inputs are copied by the library."""
+        self._require()
+        tk = np.ascontiguousarray(np.asarray(tokens, dtype=np.int64).reshape(-1))
+        st = np.ascontiguousarray(np.asarray(style, dtype=np.float32).reshape(-1))
+        if st.size != 256:
+            raise KkxError(-1, f"style must have 256 values, got {st.size}")
+        t = C.c_int64(0)
+        self._check(self._lib.kkx_submit(self._ctx, tk.ctypes.data_as(C.POINTER(C.c_int64)), int(tk.size), _fp(st),
+                                         C.c_float(speed), C.byref(t)))
+        with self._count_lock:
+            self._tickets = getattr(self, "_tickets", {})
+            self._tickets[int(t.value)] = int(tk.size)
+        return int(t.value)
+
+    def poll(self, ticket: int) -> bool:
+        self._require()
+        rc = self._lib.kkx_poll(self._ctx, int(ticket))
+        if rc < 0:
+            self._check(rc)
+        return rc == 1
+
+    def wait(self, ticket: int, return_durations: bool = False):
+        """Block until the ticket's request has finished; returns what ``infer_one`` returns."""
+        self._require()
+        with self._count_lock:
+            n = getattr(self, "_tickets", {}).pop(int(ticket), None)
+        if n is None:
+            raise KkxError(-1, "unknown ticket")
+        audio = C.POINTER(C.c_float)()
+        ns = C.c_int64(0)
+        dur = np.zeros(max(n, 1), dtype=np.int32)
+        self._check(self._lib.kkx_wait(self._ctx, int(ticket), C.byref(audio), C.byref(ns),
+                                       dur.ctypes.data_as(C.POINTER(C.c_int32))))
+        out = np.ctypeslib.as_array(audio, shape=(max(int(ns.value), 1),))
+        with self._count_lock:
+            self._outstanding += 1
+        weakref.finalize(out, B200Koko._release_buffer, self, C.cast(audio, C.c_void_p).value)
+        out = out[:int(ns.value)]
+        return (out, dur[:n]) if return_durations else out
 
     def infer_batch(self, tokens: Sequence[Sequence[int]], styles, speeds: Sequence[float],
                     return_durations: bool = False):
@@ -434,13 +508,15 @@ class B200Koko:
             a = np.ascontiguousarray(noise, dtype=np.float32).reshape(-1)
             self._check(self._lib.kkx_set_noise(self._ctx, _fp(a), a.size))
 
-    def set_inject(self, name: str, data: Optional[np.ndarray]) -> None:
+    def set_inject(self, name: str, data: Optional[np.ndarray], item: int = 0) -> None:
+        """Teacher-force ``pred_dur`` / ``F0`` / ``N`` of batch item ``item`` (test hook, kkx_test.h)."""
         self._require()
         if data is None:
-            self._check(self._lib.kkx_set_inject(self._ctx, name.encode(), None, 0))
+            self._check(self._lib.kkx_set_inject_item(self._ctx, int(item), name.encode(), None, 0))
             return
         a = np.ascontiguousarray(data, dtype=np.int32 if name == "pred_dur" else np.float32).reshape(-1)
-        self._check(self._lib.kkx_set_inject(self._ctx, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+        self._check(self._lib.kkx_set_inject_item(self._ctx, int(item), name.encode(), a.ctypes.data_as(C.c_void_p),
+                                                  a.size))
 
     def profile_enable(self, on: bool = True) -> None:
         self._require()
@@ -455,9 +531,13 @@ class B200Koko:
         self._lib.kkx_profile_json(self._ctx, buf, n + 1)
         return json.loads(buf.value.decode())
 
-    def debug_enable(self, on: bool = True) -> None:
+    def debug_enable(self, on: bool = True, item: Optional[int] = None) -> None:
+        """Keep stage tensors of every item (``item`` None) or of one batch item for ``debug_stage``."""
         self._require()
-        self._check(self._lib.kkx_debug_enable(self._ctx, 1 if on else 0))
+        if item is None:
+            self._check(self._lib.kkx_debug_enable(self._ctx, 1 if on else 0))
+        else:
+            self._check(self._lib.kkx_debug_select(self._ctx, 1 if on else 0, int(item)))
 
     def debug_stage(self, name: str, item: int = 0) -> Optional[np.ndarray]:
         self._require()

@@ -5,7 +5,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import ensure_weights, synth_batch  # noqa: E402
+from kokorox_b200.synth import ensure_weights, synth_batch  # noqa: E402
 
 
 def main():

@@ -21,7 +21,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import ensure_weights  # noqa: E402
+from kokorox_b200.synth import ensure_weights  # noqa: E402
 
 N_REQ = 4096
 TOKEN_BUDGET = 64 * 512

@@ -4,7 +4,7 @@ import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import ensure_weights, synth_batch  # noqa: E402
+from kokorox_b200.synth import ensure_weights, synth_batch  # noqa: E402
 import torch
 from kokorox_b200.onn import B200Koko
 
