@@ -185,7 +185,9 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *                 added latency -- batches form from whatever queued up behind the running step)
  *   "async_batch" most kkx_submit requests the worker merges into one ragged batch (default 64)
  *   "latency_graphs" 0/1: replay the token phase of single-utterance calls from a CUDA graph keyed by the token
- *                 count (default 1)
+ *                 count (default 1; captured on the second call with a given count)
+ *   "fork_max_batch" largest batch whose independent branches (text encoder | ALBERT, F0 | N, harmonic source |
+ *                 decoder) run on two streams (default 4; 0 = never).  Results do not depend on either option.
  * kkx_get_stat keys: "launches", "last_frames", "gpu_us", "precision", "coalesced_batches",
  * "coalesced_requests", "coalesced_largest", "async_batches", "async_requests", "frame_groups",
  * "group_first:<g>" (first item of frame group g of the last run), "weights_sessions" (sessions sharing this

@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libkkx.so")
+LOADGEN = os.path.join(OUT_DIR, "kkx_loadgen")   # native load generator (csrc/loadgen.cpp), a client of the C ABI
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -31,7 +32,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".h", ".cuh")):
+            if f.endswith((".cu", ".h", ".cuh", ".cpp")):
                 with open(os.path.join(root, f), "rb") as fh:
                     h.update(f.encode())
                     h.update(fh.read())
@@ -45,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     dig = _digest()
 
     def fresh():
-        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+        return os.path.exists(LIB) and os.path.exists(LOADGEN) and os.path.exists(stamp) and open(stamp).read() == dig
     if not force and fresh():
         return LIB
     # several ranks of one torchrun launch may get here at once on a box without a prebuilt library: one builds,
@@ -85,6 +86,14 @@ def _build_locked(stamp: str, dig: str, verbose: bool) -> str:
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIB)          # a process that already mapped the old library keeps its copy
+    # the native load generator links the shared library like any other client of include/kkx.h
+    tmpg = LOADGEN + ".tmp%d" % os.getpid()
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-pthread", os.path.join(CSRC, "loadgen.cpp"), "-o", tmpg,
+           "-L" + OUT_DIR, "-lkkx", "-Wl,-rpath,$ORIGIN", "-ldl", "-lrt"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"loadgen link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmpg, LOADGEN)
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

@@ -735,6 +735,8 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "noise_seed") o.noise_seed = (unsigned long long)value;
     else if (k == "max_frames") { if (value < 1) throw ArgError("max_frames must be >= 1"); o.max_frames = (int)value; }
     else if (k == "stft_replicate") o.stft_replicate = value ? 1 : 0;
+    else if (k == "latency_graphs") o.latency_graphs = value ? 1 : 0;
+    else if (k == "fork_max_batch") { if (value < 0 || value > 512) throw ArgError("fork_max_batch must be in 0..512"); o.fork_max_batch = (int)value; }
     else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {
       if (value < 0 || value > kMaxCoalesce) throw ArgError("coalesce must be in 0..512");
@@ -761,6 +763,7 @@ KKX_API int64_t kkx_get_stat(kkx_ctx* ctx, const char* key) {
   if (k == "coalesced_batches") return ctx->coalesced_batches;
   if (k == "coalesced_requests") return ctx->coalesced_requests;
   if (k == "coalesced_largest") return ctx->coalesced_largest;
+  if (k == "graph_replays") return ctx->model->graph_replays;
   if (k == "frame_groups") return (int64_t)ctx->model->group_first().size();
   if (k.rfind("group_first:", 0) == 0) {     // first item of frame group g of the last run
     const long g = atol(k.c_str() + 12);

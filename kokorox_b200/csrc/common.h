@@ -132,6 +132,7 @@ class Arena {
   void set_virtual(bool v) { virtual_ = v; }
   size_t used() const { return used_; }
   size_t capacity() const { return cap_; }
+  const void* base() const { return base_; }
   void* alloc_bytes(size_t bytes) {
     size_t a = (used_ + 255) & ~size_t(255);
     if (!virtual_ && a + bytes > cap_) {

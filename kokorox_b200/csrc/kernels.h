@@ -204,8 +204,9 @@ void launch_sine_source(const float* f0, const int* f0_off, const int* f0_len, c
 void launch_stft(const float* x, const long long* s_off, float* har, int ldh, const int* h_off,
                  const int* h_len, int replicate_pad, int B, int max_len, cudaStream_t st);
 // K11 head: mag = exp(cp[:, :11]), ph = sin(cp[:, 11:]) -> iSTFT -> audio [600T]
+//   fast != 0: SFU exp / sin / cos and a reciprocal envelope (tensor-core configuration); 0: libm + true division
 void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio, short* pcm /*nullable*/,
-                  const long long* s_off, int B, int max_len, cudaStream_t st);
+                  const long long* s_off, int fast, int B, int max_len, cudaStream_t st);
 
 // mix_styles (koko.rs:1255-1306) on a device-resident voice table [V][511][256]
 void launch_mix_styles(const float* table, const int* mix_off, const int* voice_ids, const float* portions,

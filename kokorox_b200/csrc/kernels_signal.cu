@@ -567,91 +567,164 @@ void launch_stft(const float* x, const long long* s_off, float* har, int ldh, co
   post_launch("stft", st);
 }
 
-// K11 head + iSTFT.  CTA = 128 frames (+3 frames of left halo): each frame's spectrum
-// (mag*cos(ph), mag*sin(ph)) is inverse-transformed (one-sided irfft, n=20) and windowed into
-// shared memory, then 640 output samples are overlap-added, divided by the window envelope and
-// stored coalesced.  Output sample n (after the n_fft/2 trim) sits at untrimmed position n+10.
-__global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ cp, int ldc,
-                                                    const int* h_off, const int* h_len,
-                                                    float* audio, const long long* s_off, short* pcm) {
-  constexpr int FR = 128, HALO = 3, NF = FR + HALO + 2;
-  __shared__ float spec[NF][22];           // (re, im) of the 11 bins of frames f0-3 .. f0+129
-  __shared__ float fr[NF][20];             // windowed time frames
-  // twiddles / window in shared memory: the lookups below are indexed per lane (j varies across a
-  // warp), which would serialise on the constant cache
+// K11 head + iSTFT, one thread per STFT frame.
+//
+// Output sample n (after the n_fft/2 = 10 trim) sits at untrimmed position p = n + 10; the five samples p = 5q .. 5q+4
+// ("group q", q = 2 .. F) are the overlap-add of frames q, q-1, q-2, q-3 at in-frame positions j0 + 5d.  A CTA of 128
+// threads owns kIstftGroups = 124 consecutive groups (620 samples = 155 float4) and the 127 frames they touch:
+//   1. the [127, 24] fp32 block of conv_post rows is staged in shared memory with coalesced 128-bit loads
+//      (row pitch 24 floats -> 25 in smem, conflict-free for the per-thread row reads);
+//   2. thread t turns its frame's 22 logits into the spectrum (mag = exp(x), phase = sin(x') -> mag*(cos, sin)) and
+//      runs the real inverse DFT of size 20 entirely in registers: x[j] = C[j] - S[j], x[20-j] = C[j] + S[j] with
+//      C[j] = sum_k Re_k cos(2 pi j k / 20), S[j] = sum_k Im_k sin(2 pi j k / 20) for j = 0..10 (the twiddles are
+//      compile-time constants, ~200 FFMA per frame instead of ~360 shared-memory complex products), applies the
+//      synthesis window and writes the 20 samples to shared memory (pitch 21);
+//   3. thread t >= 3 adds the four overlapping frames of its group, divides by the window envelope and puts the five
+//      samples into a staging row, from which the CTA stores 128-bit vectors (fp32) / 64-bit vectors (pcm16).
+// FAST (tensor-core configuration, 3e-2 waveform tolerance): ex2 / sin / cos via the SFU intrinsics and a reciprocal
+// multiply for the envelope; the fp32 verification configuration keeps libm expf / sinf / sincosf and a true division.
+constexpr int kIstftGroups = 124;
+constexpr int kIstftFrames = kIstftGroups + 3;   // 127
+__host__ __device__ constexpr float tw_cos(int m) {   // cos(2 pi m / 20), m taken mod 20
+  constexpr float c[20] = {1.0f, 0.95105651629515357f, 0.80901699437494742f, 0.58778525229247313f, 0.30901699437494742f,
+                           0.0f, -0.30901699437494742f, -0.58778525229247313f, -0.80901699437494742f, -0.95105651629515357f,
+                           -1.0f, -0.95105651629515357f, -0.80901699437494742f, -0.58778525229247313f, -0.30901699437494742f,
+                           0.0f, 0.30901699437494742f, 0.58778525229247313f, 0.80901699437494742f, 0.95105651629515357f};
+  return c[m % 20];
+}
+__host__ __device__ constexpr float tw_sin(int m) { return tw_cos(m + 15); }   // sin(x) = cos(x - pi/2)
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) istft_kernel(const float* __restrict__ cp, int ldc,
+                                                    const int* __restrict__ h_off, const int* __restrict__ h_len,
+                                                    float* __restrict__ audio, const long long* __restrict__ s_off,
+                                                    short* __restrict__ pcm) {
+  __shared__ __align__(16) float s_in[kIstftFrames * 25];    // staged conv_post rows (22 used of 24, pitch 25)
+  __shared__ float s_fr[kIstftFrames * 21];                  // windowed time frames, pitch 21
+  __shared__ __align__(16) float s_out[kIstftGroups * 5];    // 620 output samples
   __shared__ float s_win[20];
-  __shared__ float2 s_tw[10][20];          // (cos, sin)(2 pi j k / 20) as [k][j]: no integer modulo in the inner loop,
-  if (threadIdx.x < 20) s_win[threadIdx.x] = c_hann20[threadIdx.x];   // and lanes (j) hit consecutive banks
-  if (threadIdx.x < 200) {
-    const int k = threadIdx.x / 20, j = threadIdx.x - k * 20, m = (j * k) % 20;
-    s_tw[k][j] = make_float2(c_cos20[m], c_sin20[m]);
-  }
   const int b = blockIdx.y;
   const int F = h_len[b];
-  const int f0 = blockIdx.x * FR;
-  if (f0 >= F) return;
-  const long long S = (long long)(F - 1) * 5;
-  // phase 0: spectrum of each (frame, bin) once: mag = exp(x), phase = sin(x') -> mag*(cos, sin)
-  for (int i = threadIdx.x; i < NF * 11; i += 256) {
-    const int lf = i / 11, k = i % 11;
-    const int f = f0 - HALO + lf;
-    float re = 0.f, im = 0.f;
+  const int q0 = 2 + kIstftGroups * blockIdx.x;              // first output group of this CTA
+  if (q0 > F) return;
+  const int fbase = q0 - 3;                                  // frame of thread 0
+  const int t = threadIdx.x;
+  if (t < 20) s_win[t] = c_hann20[t];
+  // ---- 1. stage the rows [fbase, fbase + 127) x 24 floats (contiguous in global memory when ldc == 24)
+  {
+    const int lo = max(fbase, 0), hi = min(fbase + kIstftFrames, F);   // existing frames
+    const float* src = cp + (size_t)(h_off[b] + lo) * ldc;
+    const int nvec = (hi - lo) * 6;                                    // float4 per row: 24 / 4 (ldc == 24, 16-byte aligned rows)
+    for (int v = t; v < nvec; v += 128) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src) + v);
+      const int row = v / 6 + (lo - fbase), c4 = (v % 6) * 4;
+      float* d = s_in + row * 25 + c4;
+      d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+    }
+  }
+  __syncthreads();
+  // ---- 2. spectrum + inverse DFT of this thread's frame
+  const int f = fbase + t;
+  if (t < kIstftFrames) {
+    float xr[20];
     if (f >= 0 && f < F) {
-      const float* c = cp + (size_t)(h_off[b] + f) * ldc;
-      const float mag = expf(c[k]);
-      float sn, cs;
-      sincosf(sinf(c[11 + k]), &sn, &cs);
-      re = mag * cs;
-      im = mag * sn;
+      const float* c = s_in + t * 25;
+      float re[11], im[11];
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        float mag, sn, cs;
+        if (FAST) {
+          mag = __expf(c[k]);
+          __sincosf(__sinf(c[11 + k]), &sn, &cs);
+        } else {
+          mag = expf(c[k]);
+          sincosf(sinf(c[11 + k]), &sn, &cs);
+        }
+        re[k] = mag * cs;
+        im[k] = mag * sn;
+      }
+      // bins 0 and 10 contribute their real part only (one-sided inverse of a real signal)
+#pragma unroll
+      for (int j = 0; j <= 10; j++) {
+        float C = 0.f, S = 0.f;
+#pragma unroll
+        for (int k = 1; k < 10; k++) {
+          C = fmaf(re[k], tw_cos(j * k), C);
+          S = fmaf(im[k], tw_sin(j * k), S);
+        }
+        const float base = re[0] + ((j & 1) ? -re[10] : re[10]);
+        xr[j] = fmaf(2.0f, C - S, base);
+        if (j >= 1 && j <= 9) xr[20 - j] = fmaf(2.0f, C + S, base);
+      }
+#pragma unroll
+      for (int j = 0; j < 20; j++) xr[j] = xr[j] * (1.0f / 20.0f) * s_win[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 20; j++) xr[j] = 0.f;
     }
-    spec[lf][k] = re;
-    spec[lf][11 + k] = im;
+#pragma unroll
+    for (int j = 0; j < 20; j++) s_fr[t * 21 + j] = xr[j];
   }
   __syncthreads();
-  // phase 1: one-sided inverse DFT (n = 20) + synthesis window
-  for (int i = threadIdx.x; i < NF * 20; i += 256) {
-    const int lf = i / 20, j = i % 20;
-    const float* sp = spec[lf];
-    float acc = sp[0] + ((j & 1) ? -sp[10] : sp[10]);   // bins 0 and 10: real part only
+  // ---- 3. overlap-add of group q = q0 + (t - 3): frames t, t-1, t-2, t-3 of this CTA
+  const long long S_total = (long long)(F - 1) * 5;
+  if (t >= 3 && t < kIstftFrames) {
+    const int q = q0 + (t - 3);
+    if (q <= F) {
 #pragma unroll
-    for (int k = 1; k < 10; k++) {
-      const float2 tw = s_tw[k][j];
-      acc += 2.0f * (sp[k] * tw.x - sp[11 + k] * tw.y);
+      for (int j0 = 0; j0 < 5; j0++) {
+        float acc = 0.f, env = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          const int ff = q - d;
+          if (ff < 0 || ff >= F) continue;
+          const int j = j0 + 5 * d;
+          acc += s_fr[(t - d) * 21 + j];
+          env = fmaf(s_win[j], s_win[j], env);
+        }
+        s_out[(t - 3) * 5 + j0] = FAST ? acc * __frcp_rn(env) : acc / env;
+      }
     }
-    fr[lf][j] = acc * (1.0f / 20.0f) * s_win[j];
   }
   __syncthreads();
-  // phase 2: overlap-add.  Sample n covers untrimmed position p = n + 10; frames f with
-  // 5f <= p < 5f+20.
-  for (int i = threadIdx.x; i < FR * 5; i += 256) {
-    const long long n = (long long)f0 * 5 + i;
-    if (n >= S) break;
-    // p = n + 10 = 5 * f0 + (i + 10): frame and in-frame position from the small local index (32-bit math)
-    const int pl = i + 10;
-    const int fl = pl / 5;                 // fhi - f0
-    const int j0 = pl - fl * 5;            // position inside frame fhi
-    float acc = 0.f, env = 0.f;
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-      const int f = f0 + fl - d;
-      if (f < 0 || f >= F) continue;
-      const int j = j0 + 5 * d;
-      acc += fr[fl - d + HALO][j];
-      env += s_win[j] * s_win[j];
+  // ---- 4. vector stores: sample n = 5 (q - 2) + j0 -> CTA base n0 = 620 * blockIdx.x (16-byte aligned: item offsets
+  // are multiples of 600 samples)
+  const long long n0 = (long long)kIstftGroups * 5 * blockIdx.x;
+  const long long remain = S_total - n0;
+  const int count = remain < kIstftGroups * 5 ? (int)remain : kIstftGroups * 5;
+  float* dst = audio + s_off[b] + n0;
+  for (int v = t; v * 4 < count; v += 128) {
+    const float4 x = *reinterpret_cast<const float4*>(s_out + v * 4);
+    if (v * 4 + 4 <= count) {
+      *reinterpret_cast<float4*>(dst + v * 4) = x;
+    } else {
+      for (int e = 0; v * 4 + e < count; e++) dst[v * 4 + e] = s_out[v * 4 + e];
     }
-    const float smp = acc / env;
-    audio[s_off[b] + n] = smp;
+  }
+  if (pcm) {
     // optional 16-bit PCM: trunc(clamp(s, -1, 1) * 32767), the f32 -> i16 conversion of the reference's WebSocket
     // server (kokorox-websocket/src/lib.rs:699-703; Rust `as i16` truncates toward zero, NaN -> 0)
-    if (pcm) pcm[s_off[b] + n] = (short)__float2int_rz(fminf(fmaxf(smp, -1.0f), 1.0f) * 32767.0f);
+    short* pd = pcm + s_off[b] + n0;
+    auto to_i16 = [](float x) { return (short)__float2int_rz(fminf(fmaxf(x, -1.0f), 1.0f) * 32767.0f); };
+    for (int v = t; v * 4 < count; v += 128) {
+      if (v * 4 + 4 <= count) {
+        *reinterpret_cast<short4*>(pd + v * 4) = make_short4(to_i16(s_out[v * 4]), to_i16(s_out[v * 4 + 1]),
+                                                             to_i16(s_out[v * 4 + 2]), to_i16(s_out[v * 4 + 3]));
+      } else {
+        for (int e = 0; v * 4 + e < count; e++) pd[v * 4 + e] = to_i16(s_out[v * 4 + e]);
+      }
+    }
   }
 }
 void launch_istft(const float* cp, int ldc, const int* h_off, const int* h_len, float* audio, short* pcm,
-                  const long long* s_off, int B, int max_len, cudaStream_t st) {
+                  const long long* s_off, int fast, int B, int max_len, cudaStream_t st) {
   if (g_dry_run) return;
+  if (ldc != 24 || (reinterpret_cast<uintptr_t>(cp) & 15)) throw ArgError("launch_istft: conv_post rows must have pitch 24 and 16-byte alignment");
   ensure_tables();
-  dim3 g((max_len + 127) / 128, B);
-  istft_kernel<<<g, 256, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off, pcm);
+  // groups q = 2 .. F of an item with F = max_len frames -> F - 1 groups
+  dim3 g((max_len - 1 + kIstftGroups - 1) / kIstftGroups > 0 ? (max_len - 1 + kIstftGroups - 1) / kIstftGroups : 1, B);
+  if (fast) istft_kernel<true><<<g, 128, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off, pcm);
+  else istft_kernel<false><<<g, 128, 0, st>>>(cp, ldc, h_off, h_len, audio, s_off, pcm);
   post_launch("istft", st);
 }
 

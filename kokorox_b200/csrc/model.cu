@@ -149,11 +149,16 @@ WeightSet::~WeightSet() {
 Model::Model(const std::string& weights_path, int device)
     : device_(check_device(device)), ws_(WeightSet::acquire(weights_path, device_)), W(ws_->W) {
   KKX_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  KKX_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+  KKX_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  KKX_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  cur_ = stream_;
   KKX_CUDA(cudaEventCreate(&ev0_));
   KKX_CUDA(cudaEventCreate(&ev1_));
   KKX_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
   KKX_CUDA(cudaEventCreateWithFlags(&ev_grp_, cudaEventDisableTiming));
   pin_.reserve(size_t(4) << 20);
+  graph_pin_.reserve(size_t(1) << 20);
   const char* dbg = getenv("KKX_DEBUG_SYNC");
   stats.check_each = dbg && dbg[0] == '1';
   const char* det = getenv("KKX_PROFILE_DETAIL");
@@ -163,6 +168,8 @@ Model::Model(const std::string& weights_path, int device)
 Model::~Model() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  if (stream2_) cudaStreamSynchronize(stream2_);
+  clear_graphs();
   if (d_audio_) cudaFree(d_audio_);
   if (d_pcm_) cudaFree(d_pcm_);
   if (d_voices_) cudaFree(d_voices_);
@@ -173,7 +180,27 @@ Model::~Model() {
   if (ev1_) cudaEventDestroy(ev1_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (ev_grp_) cudaEventDestroy(ev_grp_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
+  if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Model::clear_graphs() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+  graph_pin_.reset();
+}
+
+void Model::fork_lane1() {
+  KKX_CUDA(cudaEventRecord(ev_fork_, stream_));
+  KKX_CUDA(cudaStreamWaitEvent(stream2_, ev_fork_, 0));
+}
+
+void Model::join_lane1() {
+  KKX_CUDA(cudaEventRecord(ev_join_, stream2_));
+  KKX_CUDA(cudaStreamWaitEvent(stream_, ev_join_, 0));
 }
 
 float* WeightSet::up(const std::vector<float>& v) {
@@ -506,16 +533,25 @@ void WeightSet::load(const WeightFile& wf) {
 // ============================================================================ helpers
 void Model::upload(void* dst, const void* src, size_t bytes) {
   if (bytes == 0 || g_dry_run) return;
+  if (capturing_) {
+    // the memcpy node keeps this staging address: it has to stay valid (and unchanged) for every replay
+    void* stg = graph_pin_.alloc_bytes(bytes);
+    if (!stg) throw CudaError("graph staging arena exhausted");
+    memcpy(stg, src, bytes);
+    KKX_CUDA(cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, cur_));
+    return;
+  }
   void* stg = pin_.alloc_bytes(bytes);
   if (!stg) {   // staging full: everything issued so far has to land before the arena can be reused
     KKX_CUDA(cudaStreamSynchronize(stream_));
+    KKX_CUDA(cudaStreamSynchronize(stream2_));
     pin_.reset();
     pin_.reserve(std::max<size_t>(bytes * 2, size_t(4) << 20));
     stg = pin_.alloc_bytes(bytes);
     if (!stg) throw CudaError("pinned staging arena exhausted");
   }
   memcpy(stg, src, bytes);
-  KKX_CUDA(cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, stream_));
+  KKX_CUDA(cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, cur_));
 }
 
 Level Model::make_level(const std::vector<int>& lens, Arena& A, int first_off) {
@@ -631,6 +667,7 @@ void Model::stage(int B, const int64_t* tokens, const int32_t* tok_offsets, cons
   // ---- commit
   KKX_CUDA(cudaSetDevice(device_));
   staged_ = false; ran_ = false; B_ = 0;
+  use_lane(0);
   pin_.reset();                                  // the stream is idle here: run() drains it before returning
   ioA_.reserve((size_t)B * (560 * 4 + 1024 + 64) + (1 << 20));
   ioA_.reset();
@@ -686,6 +723,7 @@ void Model::stage_voices(int B, const int64_t* tokens, const int32_t* tok_offset
   upload(d_rows, style_rows, B * sizeof(int));
   g_launch_stats = nullptr;
   launch_mix_styles(d_voices_, d_mo, d_vi, d_po, d_rows, d_styles_, B, stream_);
+  // (host-mixed and device-mixed styles live at the same address, so token-phase graphs serve both entry points)
   staged_ = true;
 }
 
@@ -722,6 +760,7 @@ void Model::run() {
   if (!staged_ || B_ <= 0) throw StateError("no batch staged");
   KKX_CUDA(cudaSetDevice(device_));
   ran_ = false;
+  use_lane(0);
   g_launch_stats = &stats;
   stats.launches = 0;
   stats.conv_flops = 0;
@@ -736,7 +775,16 @@ void Model::run() {
   try {
     token_phase(r);
   } catch (...) {
+    if (capturing_) {                 // a failed capture must be ended before the stream is usable again
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(stream_, &g);
+      if (g) cudaGraphDestroy(g);
+      capturing_ = false;
+    }
     cudaStreamSynchronize(stream_);   // nothing may still be reading the staging / arenas when the caller retries
+    cudaStreamSynchronize(stream2_);
+    cudaGetLastError();
+    use_lane(0);
     throw;
   }
 
@@ -808,7 +856,9 @@ void Model::run() {
     if (sink) { KKX_CUDA(cudaStreamSynchronize(copy_stream_)); sink_filled_ = true; }
   } catch (...) {
     cudaStreamSynchronize(stream_);
+    cudaStreamSynchronize(stream2_);
     cudaStreamSynchronize(copy_stream_);
+    use_lane(0);
     throw;
   }
   arb_timing_dump();

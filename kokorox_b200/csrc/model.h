@@ -8,6 +8,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace kkx {
@@ -122,6 +123,11 @@ struct Options {
   unsigned long long noise_seed = 0x5eed;
   int max_frames = 49152;
   int stft_replicate = 0;
+  // latency path (calls of one utterance): replay the token phase from a CUDA graph keyed by the token count, and
+  // run independent branches (text encoder | ALBERT + durations, F0 | N, harmonic source + noise blocks | decoder)
+  // on two streams for batches of at most fork_max_batch utterances (their kernels do not fill the GPU)
+  int latency_graphs = 1;
+  int fork_max_batch = 4;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
@@ -212,12 +218,28 @@ class Model {
             int pad = 0, const float* pscale = nullptr, const float* pshift = nullptr, int pact = ACT_NONE,
             float pslope = 0.f, const float* res = nullptr, int ldr = 0, const Level* Lres = nullptr,
             int res_shift = 0, float oscale = 1.f);
-  float* split_hi_ = nullptr; float* split_lo_ = nullptr; size_t split_cap_ = 0;  // scratch planes (floats)
+  float* split_hi_ = nullptr; float* split_lo_ = nullptr; size_t split_cap_ = 0;  // scratch planes (floats) of the current lane
+  // Two execution lanes: lane 0 = stream_, lane 1 = stream2_ (forked branches of small batches).  cur_ is the stream
+  // every launcher of the forward pass uses; each lane has its own split-TF32 scratch planes.
+  struct Lane { float* hi = nullptr; float* lo = nullptr; size_t cap = 0; };
+  Lane lane_[2];
+  int lane_id_ = 0;
+  void set_lane_scratch(int i, float* hi, float* lo, size_t cap) { lane_[i].hi = hi; lane_[i].lo = lo; lane_[i].cap = cap; if (i == lane_id_) use_lane(i); }
+  void use_lane(int i) {
+    lane_id_ = i; cur_ = i ? stream2_ : stream_;
+    split_hi_ = lane_[i].hi; split_lo_ = lane_[i].lo; split_cap_ = lane_[i].cap;
+  }
+  void fork_lane1();   // lane 1 starts after everything issued so far on lane 0
+  void join_lane1();   // lane 0 continues after everything issued so far on lane 1
+  bool can_fork(int B) const { return B <= opt.fork_max_batch && !debug_ && !stats.profile && !stats.check_each; }
   void tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, int dil, int pad, const Level& Lin,
                const Level& Lm, const float* bias, float* out, int ldo, int ocol, const Level& Lout, int ors,
                int oro, const float* res, int ldr, const Level* Lres, int res_shift, float oscale,
                bool accumulate);
-  void token_phase(Run& r);
+  void token_phase(Run& r);          // graph replay or eager issue, then the one host sync of the call
+  void token_issue(Run& r);          // every token-rate launch + the D2H of frame counts / durations (no sync)
+  void token_finish(Run& r);         // sync, read T_b, validate
+  size_t token_arena_bytes() const;
   void frame_phase(Run& r, int b0, int b1, bool dry);
   void adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ldx, const Level& Lin,
                  const Level& Lout, const float* sty, int sld, float* out, int ldo, int ocol,
@@ -237,6 +259,25 @@ class Model {
   std::shared_ptr<const WeightSet> ws_;
   const Weights& W;
   cudaStream_t stream_ = nullptr;
+  cudaStream_t stream2_ = nullptr;   // lane 1
+  cudaStream_t cur_ = nullptr;       // stream of the current lane
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  // token-phase CUDA graphs of single-utterance calls: key = token count + every address the captured nodes embed
+  struct GraphKey {
+    int n_tokens, precision; const void *tok_base, *io_ids, *io_level, *h_T, *h_dur;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(n_tokens, precision, tok_base, io_ids, io_level, h_T, h_dur) <
+             std::tie(o.n_tokens, o.precision, o.tok_base, o.io_ids, o.io_level, o.h_T, o.h_dur);
+    }
+  };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; Run run; long long launches = 0; };
+  std::map<GraphKey, GraphEntry> graphs_;
+  PinnedArena graph_pin_;            // staging of uploads captured into graphs: must outlive the call, never reset
+  bool capturing_ = false;
+  void clear_graphs();
+ public:
+  long long graph_replays = 0;
+ private:
   Arena tokA_, frA_, ioA_;
   PinnedArena pin_;
   bool debug_ = false; int debug_item_ = -1;

@@ -67,14 +67,14 @@ void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, in
   a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lout.d_off; a.ors = ors; a.oro = oro;
   a.res = res; a.ldr = ldr; a.rcol = 0; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift;
   a.oscale = oscale; a.accumulate = accumulate ? 1 : 0;
-  launch_conv_tc(a, stream_);
+  launch_conv_tc(a, cur_);
 }
 
 void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
                  const float* bias, int N, float* out, int ldo, int ocol, int eact, int ks, int pad,
                  const float* pscale, const float* pshift, int pact, float pslope, const float* res, int ldr,
                  const Level* Lres, int res_shift, float oscale) {
-  cudaStream_t st = stream_;
+  cudaStream_t st = cur_;
   if (opt.precision == 1 && w32 && w32->hi && split_hi_ && (size_t)Lin.rows * w32->Cpad <= split_cap_) {
     if (g_dry_run) return;
     launch_apply_tf32(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
@@ -108,19 +108,94 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
 
 // ------------------------------------------------------------------------------------------
 // Token phase: everything at phoneme-token rate, for the whole batch.
+size_t Model::token_arena_bytes() const {
+  const size_t R = (size_t)tokL_.rows;
+  return R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048 + 2048 + 2 * 512) * sizeof(float) +
+         (size_t)B_ * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20);
+}
+
 void Model::token_phase(Run& r) {
+  // host buffers the D2H at the end of the phase lands in (pinned; sized before any capture)
+  const size_t R = (size_t)tokL_.rows;
+  if (R > h_pred_dur_cap_) {
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    if (h_pred_dur_) cudaFreeHost(h_pred_dur_);
+    h_pred_dur_ = nullptr; h_pred_dur_cap_ = 0;
+    KKX_CUDA(cudaMallocHost(&h_pred_dur_, (R + R / 4) * sizeof(int)));
+    h_pred_dur_cap_ = R + R / 4;
+  }
+  if ((size_t)B_ > h_T_cap_) {
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    if (h_T_) cudaFreeHost(h_T_);
+    h_T_ = nullptr; h_T_cap_ = 0;
+    KKX_CUDA(cudaMallocHost(&h_T_, ((size_t)B_ + 64) * sizeof(int)));
+    h_T_cap_ = (size_t)B_ + 64;
+  }
+  const size_t need = token_arena_bytes();
+  if (need > tokA_.capacity()) {
+    KKX_CUDA(cudaStreamSynchronize(stream_));
+    clear_graphs();                      // captured nodes embed addresses of the old arena
+    tokA_.reserve(need);
+  }
+  // Single-utterance calls: the launch sequence of the token phase depends only on the token count, so it is
+  // captured once (on the second call with that count) and replayed afterwards -- ~190 launches become one.
+  const bool graph_ok = opt.latency_graphs && B_ == 1 && !debug_ && !stats.profile && !stats.check_each && inj_dur_.empty();
+  if (graph_ok) {
+    const GraphKey key{tok_len_[0], opt.precision, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
+    auto it = graphs_.find(key);
+    if (it != graphs_.end() && it->second.exec) {
+      r = it->second.run;
+      if (cudaGraphLaunch(it->second.exec, stream_) == cudaSuccess) {
+        stats.launches += it->second.launches;
+        graph_replays++;
+        token_finish(r);
+        return;
+      }
+      cudaGetLastError();
+      cudaGraphExecDestroy(it->second.exec);
+      graphs_.erase(it);
+    } else if (it != graphs_.end()) {
+      if (graphs_.size() > 64) clear_graphs();          // bound the cache; entries are cheap to rebuild
+      GraphEntry e;
+      const long long l0 = stats.launches;
+      cudaGraph_t g = nullptr;
+      KKX_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      capturing_ = true;
+      token_issue(r);                                   // (throws -> Model::run ends the capture)
+      capturing_ = false;
+      KKX_CUDA(cudaStreamEndCapture(stream_, &g));
+      const cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) { cudaGetLastError(); e.exec = nullptr; }
+      e.run = r;
+      e.launches = stats.launches - l0;
+      if (e.exec && cudaGraphLaunch(e.exec, stream_) == cudaSuccess) {
+        graphs_[key] = e;
+        graph_replays++;
+        token_finish(r);
+        return;
+      }
+      cudaGetLastError();
+      if (e.exec) cudaGraphExecDestroy(e.exec);
+      graphs_.erase(key);
+      stats.launches = l0;                              // fall through to an eager run
+    } else {
+      graphs_[key] = GraphEntry();                      // first sighting: run eagerly (also warms kernel attributes)
+    }
+  }
+  token_issue(r);
+  token_finish(r);
+}
+
+void Model::token_issue(Run& r) {
+  use_lane(0);
   cudaStream_t st = stream_;
   const Level& L = tokL_;
   const size_t R = (size_t)L.rows;
   const int B = B_;
-  const size_t need = R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048) * sizeof(float) +
-                      (size_t)B * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20);
-  if (need > tokA_.capacity()) {
-    KKX_CUDA(cudaStreamSynchronize(st));
-    tokA_.reserve(need);
-  }
   tokA_.reset();
   Arena& A = tokA_;
+  const bool fork = can_fork(B);
 
   // style-parameter tables for every AdaIN / AdaLN of the model: two GEMMs over the batch
   r.styL = make_level(std::vector<int>{B}, A, 0);   // one "item" of B rows at row 0
@@ -131,10 +206,40 @@ void Model::token_phase(Run& r) {
   launch_conv_f32(gemm_args(r.styL, d_styles_, 256, 128, W.sty_dec_w, W.sty_dec_b, W.sty_dec_n,
                             r.sty_dec, W.sty_dec_n, 0), st);
 
-  // scratch planes for the split-TF32 operand producer (largest K on this path: 2048)
-  split_cap_ = R * 2048;
-  split_hi_ = A.alloc<float>(split_cap_);
-  split_lo_ = A.alloc<float>(split_cap_);
+  // scratch planes for the split-TF32 operand producer (largest K on this path: 2048; the text encoder's lane: 512)
+  {
+    float* hi = A.alloc<float>(R * 2048); float* lo = A.alloc<float>(R * 2048);
+    set_lane_scratch(0, hi, lo, R * 2048);
+    float* hi1 = A.alloc<float>(R * 512); float* lo1 = A.alloc<float>(R * 512);
+    set_lane_scratch(1, hi1, lo1, R * 512);
+  }
+
+  // ---- TextEncoder (A.4) -- independent of the duration path: on lane 1 for small batches, so that its CNN and
+  // LSTM run beside ALBERT instead of after it
+  float* ta = A.alloc<float>(R * 512);
+  float* tb = A.alloc<float>(R * 512);
+  float* xp_te = A.alloc<float>(R * 2048);
+  r.t_en = A.alloc<float>(R * 512);
+  auto text_encoder = [&] {
+    cudaStream_t ts = cur_;
+    launch_embed_rows(d_ids_, W.temb, 512, ta, 512, L.d_off, L.d_len, B, L.max_len, ts);
+    for (int i = 0; i < 3; i++) {
+      gemm(L, L, ta, 512, 512, W.tcnn_w[i], &W.t_tcnn[i], W.tcnn_b[i], 512, tb, 512, 0, ACT_NONE, 5, 2);
+      LnArgs ln;
+      ln.x = tb; ln.ldx = 512; ln.w = W.tln_g[i]; ln.b = W.tln_b[i]; ln.eps = 1e-5f; ln.slope = 0.2f;
+      ln.out = ta; ln.ldo = 512; ln.off = L.d_off; ln.len = L.d_len; ln.B = B; ln.max_len = L.max_len;
+      ln.C = 512;
+      launch_layernorm(ln, ts);
+    }
+    gemm(L, L, ta, 512, 512, W.te_lstm.wih, &W.te_lstm.t_ih, W.te_lstm.bias, 2048, xp_te, 2048, 0);
+    launch_lstm(xp_te, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, ts);
+  };
+  if (fork) {
+    fork_lane1();
+    use_lane(1);
+    text_encoder();
+    use_lane(0);
+  }
 
   // ---- ALBERT (A.2)
   float* e = A.alloc<float>(R * 128);
@@ -207,41 +312,21 @@ void Model::token_phase(Run& r) {
   }
   launch_dur_scan(r.pred_dur, r.cum, 512, r.total, L.d_off, L.d_len, B, st);
 
-  // ---- TextEncoder (A.4) -- independent of the duration path; issued before the host sync
-  float* ta = A.alloc<float>(R * 512);
-  float* tb = A.alloc<float>(R * 512);
-  r.t_en = A.alloc<float>(R * 512);
-  launch_embed_rows(d_ids_, W.temb, 512, ta, 512, L.d_off, L.d_len, B, L.max_len, st);
-  for (int i = 0; i < 3; i++) {
-    gemm(L, L, ta, 512, 512, W.tcnn_w[i], &W.t_tcnn[i], W.tcnn_b[i], 512, tb, 512, 0, ACT_NONE, 5, 2);
-    LnArgs ln;
-    ln.x = tb; ln.ldx = 512; ln.w = W.tln_g[i]; ln.b = W.tln_b[i]; ln.eps = 1e-5f; ln.slope = 0.2f;
-    ln.out = ta; ln.ldo = 512; ln.off = L.d_off; ln.len = L.d_len; ln.B = B; ln.max_len = L.max_len;
-    ln.C = 512;
-    launch_layernorm(ln, st);
-  }
-  gemm(L, L, ta, 512, 512, W.te_lstm.wih, &W.te_lstm.t_ih, W.te_lstm.bias, 2048, xp, 2048, 0);
-  launch_lstm(xp, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, st);
+  if (fork) join_lane1();
+  else text_encoder();               // large batches: same stream, after the duration path
   capture("t_en", r.t_en, 512, 0, 512, L, 0);
 
-  split_hi_ = split_lo_ = nullptr; split_cap_ = 0;
-  // ---- the one mid-pipeline host sync: frame counts decide every later launch shape
-  r.T.resize(B);
-  if (R > h_pred_dur_cap_) {
-    if (h_pred_dur_) cudaFreeHost(h_pred_dur_);
-    h_pred_dur_ = nullptr; h_pred_dur_cap_ = 0;
-    KKX_CUDA(cudaMallocHost(&h_pred_dur_, (R + R / 4) * sizeof(int)));
-    h_pred_dur_cap_ = R + R / 4;
-  }
-  if ((size_t)B > h_T_cap_) {
-    if (h_T_) cudaFreeHost(h_T_);
-    h_T_ = nullptr; h_T_cap_ = 0;
-    KKX_CUDA(cudaMallocHost(&h_T_, ((size_t)B + 64) * sizeof(int)));
-    h_T_cap_ = (size_t)B + 64;
-  }
+  set_lane_scratch(0, nullptr, nullptr, 0);
+  set_lane_scratch(1, nullptr, nullptr, 0);
+  // ---- frame counts decide every later launch shape: they go to the host, and token_finish() waits for them
   KKX_CUDA(cudaMemcpyAsync(h_T_, r.total, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   KKX_CUDA(cudaMemcpyAsync(h_pred_dur_, r.pred_dur, R * sizeof(int), cudaMemcpyDeviceToHost, st));
-  KKX_CUDA(cudaStreamSynchronize(st));
+}
+
+void Model::token_finish(Run& r) {
+  const int B = B_;
+  KKX_CUDA(cudaStreamSynchronize(stream_));   // the one mid-pipeline host sync
+  r.T.resize(B);
   for (int b = 0; b < B; b++) {
     r.T[b] = h_T_[b];
     // 1 <= dur <= 50 / speed per token by construction; the cap bounds every later row / sample index
@@ -257,7 +342,7 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
                       const Level& Lout, const float* sty, int sld, float* out, int ldo, int ocol,
                       bool dry) {
   (void)r; (void)dry;
-  cudaStream_t st = stream_;
+  cudaStream_t st = cur_;
   const int B = Lin.B;
   const int nch_in = (Lin.max_len + kStatRows - 1) / kStatRows;
   const int nch_out = (Lout.max_len + kStatRows - 1) / kStatRows;
@@ -326,7 +411,7 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
 void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
                 int sld, float* xw, float* t1, float* out, float oscale, bool accumulate, const float* part_x) {
   (void)r;
-  cudaStream_t st = stream_;
+  cudaStream_t st = cur_;
   const int B = L.B, C = w.c, k = w.k;
   const int nch = (L.max_len + kStatRows - 1) / kStatRows;
   float* part = A.alloc<float>((size_t)B * nch * 2 * C);
@@ -406,9 +491,13 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
 // ------------------------------------------------------------------------------------------
 // Frame phase for items [b0, b1): length regulation, F0/N, decoder, generator, iSTFT.
 void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
+  use_lane(0);
   cudaStream_t st = stream_;
   Arena& A = frA_;
   const int B = b1 - b0;
+  // small batches: independent branches run on two streams (N | F0, harmonic source + noise blocks | decoder)
+  const bool fork = !dry && can_fork(B);
+  cudaStream_t st1 = fork ? stream2_ : stream_;
   std::vector<int> T(r.T.begin() + b0, r.T.begin() + b1), T2(B), T20(B), T120(B), one(B, 1);
   long long maxS = 0;
   for (int b = 0; b < B; b++) {
@@ -469,29 +558,36 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   // ---- F0 / N predictor (A.7)
   float* xp = A.alloc<float>((size_t)FR.rows * 2048);
   float* shd = A.alloc<float>((size_t)FR.rows * 512);
-  split_cap_ = std::max((size_t)FR.rows * 640, (size_t)FR2.rows * 512);
-  split_hi_ = A.alloc<float>(split_cap_);
-  split_lo_ = A.alloc<float>(split_cap_);
+  {
+    const size_t cap = std::max((size_t)FR.rows * 640, (size_t)FR2.rows * 512);
+    float* hi = A.alloc<float>(cap); float* lo = A.alloc<float>(cap);
+    set_lane_scratch(0, hi, lo, cap);
+    float* hi1 = A.alloc<float>(cap); float* lo1 = A.alloc<float>(cap);
+    set_lane_scratch(1, hi1, lo1, cap);
+  }
   gemm(FR, FR, en, 640, 640, W.shared_lstm.wih, &W.shared_lstm.t_ih, W.shared_lstm.bias, 2048, xp, 2048, 0);
   launch_lstm(xp, W.shared_lstm.whhT, shd, 512, 0, FR.d_off, FR.d_len, B, st);
   capture("shared_lstm", shd, 512, 0, 512, FR, b0);
   float* curves[2];
+  if (fork) fork_lane1();
   for (int k = 0; k < 2; k++) {
     const AdaBlkW* blk = k == 0 ? W.f0blk : W.nblk;
-    const size_t mark = A.used();
+    if (fork) use_lane(k);                       // F0 stack on lane 0, N stack on lane 1
     float* y0 = A.alloc<float>((size_t)FR.rows * 512);
     float* y1 = A.alloc<float>((size_t)FR2.rows * 256);
     float* y2 = A.alloc<float>((size_t)FR2.rows * 256);
     adain_blk(r, A, blk[0], shd, 512, FR, FR, sty_pro, W.sty_pro_n, y0, 512, 0, dry);
     adain_blk(r, A, blk[1], y0, 512, FR, FR2, sty_pro, W.sty_pro_n, y1, 256, 0, dry);
     adain_blk(r, A, blk[2], y1, 256, FR2, FR2, sty_pro, W.sty_pro_n, y2, 256, 0, dry);
-    (void)mark;
     curves[k] = A.alloc<float>(FR2.rows);
     launch_conv_f32(gemm_args(FR2, y2, 256, 256, k == 0 ? W.f0proj_w : W.nproj_w,
-                              k == 0 ? W.f0proj_b : W.nproj_b, 1, curves[k], 1, 0), st);
+                              k == 0 ? W.f0proj_b : W.nproj_b, 1, curves[k], 1, 0), cur_);
   }
+  use_lane(0);
+  if (fork) join_lane1();
   float* f0 = curves[0]; float* nc = curves[1];
-  split_hi_ = split_lo_ = nullptr; split_cap_ = 0;   // decoder / generator use the bf16 operand path
+  set_lane_scratch(0, nullptr, nullptr, 0);          // decoder / generator use the bf16 operand path
+  set_lane_scratch(1, nullptr, nullptr, 0);
   if (!dry) {   // test hook: teacher-forced F0 / N curves of single items (any frame group)
     for (int k = 0; k < 2; k++) {
       for (auto& kv : (k == 0 ? inj_f0_ : inj_n_)) {
@@ -505,6 +601,71 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   }
   capture("F0", f0, 1, 0, 1, FR2, b0);
   capture("N", nc, 1, 0, 1, FR2, b0);
+
+  // ---- harmonic source, STFT and both noise res-blocks (A.9, K9/K10): they need only F0, so for small batches
+  // they run on lane 1 beside the decoder (lane 0) and join before the first `x += x_source`
+  if (fork) { fork_lane1(); use_lane(1); }
+  float* phase = A.alloc<float>((size_t)9 * FR2.sum_len + 16);
+  float* src = A.alloc<float>((size_t)600 * FR.sum_len + 16);
+  float* har = A.alloc<float>((size_t)G120.rows * 24);
+  launch_sine_phase(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, B, st1);
+  if (!dry && d_noise_) {
+    for (int b = 0; b < B; b++)
+      if (600LL * T[b] * 9 > noise_n_) throw ArgError("noise buffer smaller than 600*T*9");
+  }
+  launch_sine_source(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, d_noise_, opt.noise_seed, W.lin_w,
+                     W.lin_b, src, d_s_loc, B, maxS, st1);
+  if (debug_ && !dry) {
+    bool any = false;
+    for (int b = 0; b < B; b++) any = any || want_debug(b0 + b);
+    if (any) KKX_CUDA(cudaStreamSynchronize(st1));
+    for (int b = 0; b < B; b++) {
+      if (!want_debug(b0 + b)) continue;
+      DebugStage s; s.rows = 600LL * T[b]; s.cols = 1; s.data.resize(s.rows);
+      KKX_CUDA(cudaMemcpy(s.data.data(), src + s_loc[b], s.rows * sizeof(float), cudaMemcpyDeviceToHost));
+      dbg_["har_source#" + std::to_string(b0 + b)] = std::move(s);
+    }
+  }
+  launch_stft(src, d_s_loc, har, 24, G120.d_off, G120.d_len, opt.stft_replicate, B, G120.max_len, st1);
+  capture("har", har, 24, 0, 22, G120, b0);
+
+  // ---- generator stage 0 (20T rows, 256 ch)
+  const size_t n20 = (size_t)G20.rows * 256, n120 = (size_t)G120.rows * 128;
+  float* xs0 = A.alloc<float>(n20);
+  float* x0 = A.alloc<float>(n20);
+  float* w0 = A.alloc<float>(n20);
+  float* t0 = A.alloc<float>(n20);
+  float* acc0 = A.alloc<float>(n20);
+  if (opt.precision == 1) {
+    void* col = A.alloc_bytes((size_t)G20.rows * W.t_nc0.Cpad * 2);
+    launch_im2col_bf16(har, 24, 22, 12, 6, 3, col, W.t_nc0.Cpad, G20.rows, G120.d_off, G120.d_len, G20.d_off,
+                       G20.d_len, B, G20.max_len, st1);
+    tc_conv(A, col, G20.rows, W.t_nc0, 1, 0, G20, G20, W.nc0_b, xs0, 256, 0, G20, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+  } else {
+    ConvArgs c = gemm_args(G20, har, 24, 22, W.nc0_w, W.nc0_b, 256, xs0, 256, 0);
+    c.in_off = G120.d_off; c.in_len = G120.d_len;
+    c.ks = 12; c.stride = 6; c.pad = 3;
+    launch_conv_f32(c, st1);
+  }
+  arb(r, A, W.nres[0], xs0, G20, sty_dec, W.sty_dec_n, w0, t0, xs0, 1.f, false);
+  capture("gen.x_source.0", xs0, 256, 0, 256, G20, b0);
+  // (stage-1 buffers; the stage-1 noise branch is part of the same lane)
+  float* xs1 = A.alloc<float>(n120);
+  float* x1 = A.alloc<float>(n120);
+  float* w1 = A.alloc<float>(n120);
+  float* t1 = A.alloc<float>(n120);
+  float* acc1 = A.alloc<float>(n120);
+  if (opt.precision == 1) {
+    void* hb = A.alloc_bytes((size_t)G120.rows * W.t_nc1.Cpad * 2);
+    launch_apply_bf16(har, 24, 22, nullptr, nullptr, ACT_NONE, 0.f, nullptr, hb, W.t_nc1.Cpad, G120.rows, G120.d_off,
+                      G120.d_len, B, G120.max_len, st1);
+    tc_conv(A, hb, G120.rows, W.t_nc1, 1, 0, G120, G120, W.nc1_b, xs1, 128, 0, G120, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
+  } else {
+    launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st1);
+  }
+  arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
+  capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
+  use_lane(0);
 
   // ---- decoder (A.8)
   float* xA = A.alloc<float>((size_t)FR.rows * 1096);
@@ -526,51 +687,6 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   adain_blk(r, A, W.dec[3], dcur, 1096, FR, FR2, sty_dec, W.sty_dec_n, y, 512, 0, dry);
   capture("dec.decode.3", y, 512, 0, 512, FR2, b0);
 
-  // ---- generator: harmonic source + STFT (A.9, K9/K10)
-  float* phase = A.alloc<float>((size_t)9 * FR2.sum_len + 16);
-  float* src = A.alloc<float>((size_t)600 * FR.sum_len + 16);
-  float* har = A.alloc<float>((size_t)G120.rows * 24);
-  launch_sine_phase(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, B, st);
-  if (!dry && d_noise_) {
-    for (int b = 0; b < B; b++)
-      if (600LL * T[b] * 9 > noise_n_) throw ArgError("noise buffer smaller than 600*T*9");
-  }
-  launch_sine_source(f0, FR2.d_off, FR2.d_len, phase, d_ph_off, d_noise_, opt.noise_seed, W.lin_w,
-                     W.lin_b, src, d_s_loc, B, maxS, st);
-  if (debug_ && !dry) {
-    bool any = false;
-    for (int b = 0; b < B; b++) any = any || want_debug(b0 + b);
-    if (any) KKX_CUDA(cudaStreamSynchronize(st));
-    for (int b = 0; b < B; b++) {
-      if (!want_debug(b0 + b)) continue;
-      DebugStage s; s.rows = 600LL * T[b]; s.cols = 1; s.data.resize(s.rows);
-      KKX_CUDA(cudaMemcpy(s.data.data(), src + s_loc[b], s.rows * sizeof(float), cudaMemcpyDeviceToHost));
-      dbg_["har_source#" + std::to_string(b0 + b)] = std::move(s);
-    }
-  }
-  launch_stft(src, d_s_loc, har, 24, G120.d_off, G120.d_len, opt.stft_replicate, B, G120.max_len, st);
-  capture("har", har, 24, 0, 22, G120, b0);
-
-  // ---- generator stage 0 (20T rows, 256 ch)
-  const size_t n20 = (size_t)G20.rows * 256, n120 = (size_t)G120.rows * 128;
-  float* xs0 = A.alloc<float>(n20);
-  float* x0 = A.alloc<float>(n20);
-  float* w0 = A.alloc<float>(n20);
-  float* t0 = A.alloc<float>(n20);
-  float* acc0 = A.alloc<float>(n20);
-  if (opt.precision == 1) {
-    void* col = A.alloc_bytes((size_t)G20.rows * W.t_nc0.Cpad * 2);
-    launch_im2col_bf16(har, 24, 22, 12, 6, 3, col, W.t_nc0.Cpad, G20.rows, G120.d_off, G120.d_len, G20.d_off,
-                       G20.d_len, B, G20.max_len, st);
-    tc_conv(A, col, G20.rows, W.t_nc0, 1, 0, G20, G20, W.nc0_b, xs0, 256, 0, G20, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
-  } else {
-    ConvArgs c = gemm_args(G20, har, 24, 22, W.nc0_w, W.nc0_b, 256, xs0, 256, 0);
-    c.in_off = G120.d_off; c.in_len = G120.d_len;
-    c.ks = 12; c.stride = 6; c.pad = 3;
-    launch_conv_f32(c, st);
-  }
-  arb(r, A, W.nres[0], xs0, G20, sty_dec, W.sty_dec_n, w0, t0, xs0, 1.f, false);
-  capture("gen.x_source.0", xs0, 256, 0, 256, G20, b0);
   void* ybf = nullptr;
   if (opt.precision == 1) {
     ybf = A.alloc_bytes((size_t)FR2.rows * 512 * 2);
@@ -591,6 +707,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     c.pact = ACT_LRELU; c.pslope = 0.1f;
     launch_conv_f32(c, st);
   }
+  if (fork) join_lane1();
   capture("gen.ups.0", x0, 256, 0, 256, G20, b0);
   {
     float* px = nullptr;
@@ -606,21 +723,6 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   capture("gen.stage.0", acc0, 256, 0, 256, G20, b0);
 
   // ---- generator stage 1 (120T+1 rows, 128 ch)
-  float* xs1 = A.alloc<float>(n120);
-  float* x1 = A.alloc<float>(n120);
-  float* w1 = A.alloc<float>(n120);
-  float* t1 = A.alloc<float>(n120);
-  float* acc1 = A.alloc<float>(n120);
-  if (opt.precision == 1) {
-    void* hb = A.alloc_bytes((size_t)G120.rows * W.t_nc1.Cpad * 2);
-    launch_apply_bf16(har, 24, 22, nullptr, nullptr, ACT_NONE, 0.f, nullptr, hb, W.t_nc1.Cpad, G120.rows, G120.d_off,
-                      G120.d_len, B, G120.max_len, st);
-    tc_conv(A, hb, G120.rows, W.t_nc1, 1, 0, G120, G120, W.nc1_b, xs1, 128, 0, G120, 1, 0, nullptr, 0, nullptr, 0, 1.f, false);
-  } else {
-    launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st);
-  }
-  arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
-  capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
   void* abf = nullptr;
   if (opt.precision == 1) {
     abf = A.alloc_bytes((size_t)G20.rows * 256 * 2);
@@ -678,7 +780,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     launch_conv_f32(c, st);
   }
   capture("conv_post", cp, 24, 0, 22, G120, b0);
-  launch_istft(cp, 24, G120.d_off, G120.d_len, d_audio_, want_pcm_ ? d_pcm_ : nullptr, d_s_glob, B, G120.max_len, st);
+  launch_istft(cp, 24, G120.d_off, G120.d_len, d_audio_, want_pcm_ ? d_pcm_ : nullptr, d_s_glob, opt.precision == 1, B, G120.max_len, st);
 }
 
 }  // namespace kkx
