@@ -47,6 +47,10 @@ KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whh
                                 const int* len, int rows, float* out);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
+/* ragged batch through the tcgen05 / TMEM attention kernel (kernels_attn.cu), or the mma.sync kernel (umma = 0):
+ * qkv [rows,2304] with items at off[b] (len[b] rows) -> ctx [rows,768] (rows outside the items are left untouched) */
+KKX_API int kkx_test_attention_batch(int device, const float* qkv, int B, const int* off, const int* len, int rows,
+                                     int umma, float* ctx);
 /* x [L,C] + style row (gamma|beta, 2C) -> scale [C], shift [C] (InstanceNorm stats + AdaIN) */
 KKX_API int kkx_test_adain_coef(int device, const float* x, int L, int C, const float* gamma_beta,
                                 float* scale, float* shift);
@@ -62,6 +66,10 @@ KKX_API int kkx_test_conv_tc(int device, const float* x, int L, int Ci, const fl
  * fp32, nprod = 3 or 4 partial products, eact 0 / 3 (gelu_new).  out [L, Co]. */
 KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const float* w, const float* bias,
                                int Co, int ks, int dil, int pad, int nprod, int eact, float* out);
+/* The same with split-FP16 operand planes ("3xFP16": fp16 hi/lo planes, kind::f16 MMAs, power-of-two scaling undone in
+ * the epilogue); problems with >= 148 output tiles take the persistent kernel, smaller ones the single-tile kernel. */
+KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                                int Co, int ks, int dil, int pad, int eact, float* out);
 /* Fused generator res-block conv (kernels_arb.cu): out = (conv1d(snake(x*scale_b+shift_b), w, dilation) + bias + res)
  * * oscale (+ out when accumulate); B ragged items packed along rows (x, res, out: [sum lens, C]); C in
  * {128, 256}; w [C][ks][C]; x optionally rounded to bf16 first (in_bf16); result as fp32 or, want_bf16, the

@@ -736,6 +736,8 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "max_frames") { if (value < 1) throw ArgError("max_frames must be >= 1"); o.max_frames = (int)value; }
     else if (k == "stft_replicate") o.stft_replicate = value ? 1 : 0;
     else if (k == "latency_graphs") o.latency_graphs = value ? 1 : 0;
+    else if (k == "attention_umma") o.attention_umma = value ? 1 : 0;
+    else if (k == "split_f16") o.split_f16 = value ? 1 : 0;
     else if (k == "fork_max_batch") { if (value < 0 || value > 512) throw ArgError("fork_max_batch must be in 0..512"); o.fork_max_batch = (int)value; }
     else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {

@@ -44,8 +44,12 @@ struct TcConvArgs {
   const void* tmB_c = nullptr;   // split-TF32 cluster mode: weight maps with half-height boxes (BN/2 rows)
   const void* tmB2_c = nullptr;
   int cluster = 1;               // CTAs per cluster along M sharing each weight tile by TMA multicast (1 or 2)
-  int tf32 = 0;               // 1 = split-TF32 operands (fp32 containers), nprod products (3 or 4)
+  int tf32 = 0;               // 1 = split-precision operands (hi / lo planes), nprod products (3 or 4)
   int nprod = 3;
+  int f16 = 0;                // split planes are fp16 (2 B, 64 K-elements per 128-byte span) instead of tf32-in-fp32:
+                              // the same 11-bit significands, half the operand bytes and twice the MMA rate
+  float wscale = 1.f;         // the accumulator is multiplied by this before the bias (undoes the power-of-two
+                              // scaling of fp16 weight / activation planes; 1 for tf32)
   int eact = ACT_NONE;
   int Cpad = 0, Ci = 0, Co = 0, ks = 1, dil = 1, pad = 0;
   const int* in_off = nullptr; const int* m_len = nullptr; int max_m = 0; int B = 1; long long sum_m = 0;
@@ -64,11 +68,21 @@ void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long o
                     long long pitch_elems, int box_outer);
 void make_tmap_f32(void* out_map, const void* ptr, long long inner, long long outer,
                    long long pitch_elems, int box_outer);
+void make_tmap_f16(void* out_map, const void* ptr, long long inner, long long outer,
+                   long long pitch_elems, int box_outer);
 inline int tc_box_n(int Co) { return Co > 128 ? 256 : (Co > 64 ? 128 : 64); }
 inline int tc_box_n_tf32(int Co) { return Co > 64 ? 128 : 64; }
 void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
                        float slope, float* out_hi, float* out_lo, int Cpad, int rows_total,
                        const int* off, const int* len, int B, int max_len, cudaStream_t st);
+// fp16 hi / lo planes of kSplitF16Scale * act(x * scale + shift) (saturating at the fp16 range), [rows, Cpad] halves
+constexpr float kSplitF16Scale = 16.f;
+// host: fp16 hi / lo planes of w * 2^s, s chosen so that max|w| * 2^s lies in [2^13, 2^14) (the lo plane of every
+// weight down to 2^-14 of the largest then stays a normal fp16); returns 2^-s
+float split_f16_host(const float* w, size_t n, unsigned short* hi, unsigned short* lo);
+void launch_apply_f16x2(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                        float slope, void* out_hi, void* out_lo, int Cpad, int rows_total,
+                        const int* off, const int* len, int B, int max_len, cudaStream_t st);
 // bf16 operand producers (AdaIN scale/shift + activation fused; zero halo rows and pad columns)
 void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
                        float slope, const float* alpha, void* out, int Cpad, int rows_total,
@@ -143,6 +157,13 @@ void launch_copy_row(float* u, int C, int dst_row, int src_row, const int* off, 
 // softmax(QK^T/8)V per item and head; qkv [rows, 2304] (q|k|v, head h at h*64); ctx [rows,768]
 void launch_attention(const float* qkv, float* ctx, const int* off, const int* len, int B,
                       int max_len, cudaStream_t st);
+
+// The same on tcgen05 / TMEM fed by TMA (kernels_attn.cu): split-TF32 products, P kept in tensor memory as the A
+// operand of the second MMA.  scratch: attention_umma_scratch_floats(rows_total, B) floats (tf32 hi/lo planes of
+// Q/8, K and the transposed V); rows_total = rows of the packed qkv / ctx matrices (Level.rows).
+size_t attention_umma_scratch_floats(int rows_total, int B);
+void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
+                           int max_len, int rows_total, cudaStream_t st);
 
 // Bidirectional LSTM recurrence, H=256.  xproj [rows, 2048] = x W_ih^T + b_ih + b_hh for
 // (fwd i,f,g,o | bwd i,f,g,o); whhT [2][256][1024] (k-major); out [rows, ldo] cols ocol..+512.

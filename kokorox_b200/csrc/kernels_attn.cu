@@ -1,0 +1,366 @@
+// kernels_attn.cu -- ALBERT self-attention (12 heads x 64, N <= 512, key-padding mask) on tcgen05 / TMEM, fed by TMA.
+//
+// north_star: "the ALBERT/PL-BERT encoder ... use tcgen05/TMEM tiles fed by TMA".  Round 1 ran attention on legacy
+// mma.sync fragments (kernels_dense.cu attention_tc_kernel, kept as the fallback); this is the Blackwell-native form.
+// The path feeds the duration predictor, whose integer durations must match the fp32 oracle bit for bit, so every
+// product is split-TF32 ("3xTF32": hi*hi + hi*lo + lo*hi, fp32 accumulation) exactly like the mma.sync kernel.
+//
+// Two kernels per layer:
+//   attn_prep_kernel   qkv [rows, 2304] fp32 -> tf32 hi/lo planes  Q/8 [rows, 768], K [rows, 768] and the TRANSPOSED
+//                      V^T [(item, head, d), key] (pitch 512), so that both MMAs take K-major operands straight from
+//                      128B-swizzled TMA boxes (keys beyond the item's length are zero-filled up to a multiple of 64);
+//   attn_umma_kernel   one CTA per (item, head, 128 query rows), 6 warps:
+//       warp 0     TMA producer: the Q planes once, then a 2-stage ring of (K, V^T) tiles of 64 keys (64 KB / stage)
+//       warp 1     MMA issuer:  S_j = Q K_j^T (M 128, N 64 keys, K 64: 24 UMMAs) into one of two TMEM S buffers,
+//                               O_j = P_j V_j  (A = P from TENSOR MEMORY, B = V^T tile: 24 UMMAs) into the TMEM O tile
+//       warps 2-5  softmax: thread = query row = TMEM lane, so row max / sum are thread-local (no shuffles): tcgen05.ld
+//                  of S_j, mask, online max, exp, split P into tf32 hi/lo and tcgen05.st them back to TMEM as the A
+//                  operand of the second MMA; then the O tile is drained and folded into the fp32 running output with
+//                  the flash rescaling (each 64-key chain is added in fp32 RN -- the tensor core truncates per
+//                  accumulate, the same chain splitting the split-TF32 GEMMs use).
+//   S_{j+1} is issued before the softmax of tile j starts, so the tensor pipe works under the exponentials.
+// TMEM columns: S0 0..63, S1 64..127, P_hi 128..191, P_lo 192..255, O 256..319.
+#include "kernels.h"
+#include <cuda.h>
+#include "tc_ptx.cuh"
+
+namespace kkx {
+
+namespace {
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kVtPitch = 512;          // keys per V^T row (ALBERT max_position_embeddings)
+
+// ------------------------------------------------------------------------------------------ operand planes
+__global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict__ qkv, float* __restrict__ qh,
+                                                        float* __restrict__ ql, float* __restrict__ kh,
+                                                        float* __restrict__ kl, float* __restrict__ vth,
+                                                        float* __restrict__ vtl, const int* __restrict__ off,
+                                                        const int* __restrict__ len) {
+  __shared__ float s_h[64][33], s_l[64][33];
+  const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 32;
+  const int N = len[b];
+  const int NR = (N + 63) & ~63;                       // V^T is consumed in tiles of 64 keys: zero-fill up to there
+  if (t0 >= NR) return;
+  const int tid = threadIdx.x, r = tid >> 3, c8 = (tid & 7) << 3;
+  const int token = t0 + r;
+  const bool valid = token < N;
+  const size_t row = (size_t)off[b] + token;
+  float q[8], k[8], v[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { q[e] = 0.f; k[e] = 0.f; v[e] = 0.f; }
+  if (valid) {
+    const float* src = qkv + row * 2304 + h * 64 + c8;
+    const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(src + 768), b1 = *reinterpret_cast<const float4*>(src + 772);
+    const float4 c0 = *reinterpret_cast<const float4*>(src + 1536), c1 = *reinterpret_cast<const float4*>(src + 1540);
+    q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = a0.w; q[4] = a1.x; q[5] = a1.y; q[6] = a1.z; q[7] = a1.w;
+    k[0] = b0.x; k[1] = b0.y; k[2] = b0.z; k[3] = b0.w; k[4] = b1.x; k[5] = b1.y; k[6] = b1.z; k[7] = b1.w;
+    v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
+    float o[4][8];   // qh ql kh kl
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const float qs = q[e] * 0.125f;                  // 1/sqrt(64), exact
+      o[0][e] = __uint_as_float(to_tf32(qs)); o[1][e] = __uint_as_float(to_tf32(qs - o[0][e]));
+      o[2][e] = __uint_as_float(to_tf32(k[e])); o[3][e] = __uint_as_float(to_tf32(k[e] - o[2][e]));
+    }
+    float* dst[4] = {qh, ql, kh, kl};
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      float* d = dst[p] + row * 768 + h * 64 + c8;
+      *reinterpret_cast<float4*>(d) = make_float4(o[p][0], o[p][1], o[p][2], o[p][3]);
+      *reinterpret_cast<float4*>(d + 4) = make_float4(o[p][4], o[p][5], o[p][6], o[p][7]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const float hi = __uint_as_float(to_tf32(v[e]));
+    s_h[c8 + e][r] = hi;
+    s_l[c8 + e][r] = __uint_as_float(to_tf32(v[e] - hi));
+  }
+  __syncthreads();
+  // V^T rows: (item, head, d), 32 keys of this block contiguous
+  const int d = tid >> 2, seg = (tid & 3) << 3;
+  const size_t vrow = ((size_t)(b * 12 + h) * 64 + d) * kVtPitch + t0 + seg;
+  *reinterpret_cast<float4*>(vth + vrow) = make_float4(s_h[d][seg], s_h[d][seg + 1], s_h[d][seg + 2], s_h[d][seg + 3]);
+  *reinterpret_cast<float4*>(vth + vrow + 4) = make_float4(s_h[d][seg + 4], s_h[d][seg + 5], s_h[d][seg + 6], s_h[d][seg + 7]);
+  *reinterpret_cast<float4*>(vtl + vrow) = make_float4(s_l[d][seg], s_l[d][seg + 1], s_l[d][seg + 2], s_l[d][seg + 3]);
+  *reinterpret_cast<float4*>(vtl + vrow + 4) = make_float4(s_l[d][seg + 4], s_l[d][seg + 5], s_l[d][seg + 6], s_l[d][seg + 7]);
+}
+
+// ------------------------------------------------------------------------------------------ the attention kernel
+constexpr uint32_t kQPlane = 2 * 128 * 128;            // one Q plane: two K-chunks of [128 rows x 32 floats] = 32 KB
+constexpr uint32_t kTilePlane = 2 * 64 * 128;          // one K / V^T plane of a 64-key tile: two chunks of [64 x 32] = 16 KB
+constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 64 KB
+constexpr int kAttnSmem = 2 * kQPlane + 2 * kStage + 16 * 8 + 16 + 1024;
+constexpr uint32_t kColS0 = 0, kColPH = 128, kColPL = 192, kColO = 256;
+
+__global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
+                                                           const __grid_constant__ CUtensorMap tmQl,
+                                                           const __grid_constant__ CUtensorMap tmKh,
+                                                           const __grid_constant__ CUtensorMap tmKl,
+                                                           const __grid_constant__ CUtensorMap tmVh,
+                                                           const __grid_constant__ CUtensorMap tmVl,
+                                                           const int* __restrict__ off, const int* __restrict__ len,
+                                                           float* __restrict__ ctx) {
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+  const int N = len[b];
+  if (q0 >= N) return;                                  // (uniform per CTA, before any barrier / TMEM allocation)
+  const int nt = (N + 63) >> 6;                         // key tiles
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_h = base, q_l = base + kQPlane;
+  const uint32_t st0 = base + 2 * kQPlane;
+  const uint32_t bar_base = st0 + 2 * kStage;
+  const uint32_t q_full = bar_base;
+  auto full_bar = [&](int s) { return bar_base + (1 + s) * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
+  auto sfull_bar = [&](int i) { return bar_base + (5 + i) * 8; };
+  auto sfree_bar = [&](int i) { return bar_base + (7 + i) * 8; };
+  const uint32_t p_full = bar_base + 9 * 8, o_full = bar_base + 10 * 8;
+  const uint32_t tmem_slot = bar_base + 16 * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVh) : "memory");
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
+      mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 4);
+    }
+    mbar_init(p_full, 4); mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qrow = off[b] + q0, krow0 = off[b], vrow = (b * 12 + h) * 64;
+      mbar_expect_tx(q_full, 2 * kQPlane);
+      for (int c = 0; c < 2; c++) {
+        tma_load_2d(q_h + c * (kQPlane / 2), &tmQh, h * 64 + 32 * c, qrow, q_full);
+        tma_load_2d(q_l + c * (kQPlane / 2), &tmQl, h * 64 + 32 * c, qrow, q_full);
+      }
+      for (int j = 0; j < nt; j++) {
+        const int s = j & 1;
+        mbar_wait(empty_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        const uint32_t sa = st0 + s * kStage;
+        mbar_expect_tx(full_bar(s), kStage);
+        for (int c = 0; c < 2; c++) {
+          const uint32_t co = c * (kTilePlane / 2);
+          tma_load_2d(sa + co, &tmKh, h * 64 + 32 * c, krow0 + j * 64, full_bar(s));
+          tma_load_2d(sa + kTilePlane + co, &tmKl, h * 64 + 32 * c, krow0 + j * 64, full_bar(s));
+          tma_load_2d(sa + 2 * kTilePlane + co, &tmVh, j * 64 + 32 * c, vrow, full_bar(s));
+          tma_load_2d(sa + 3 * kTilePlane + co, &tmVl, j * 64 + 32 * c, vrow, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      mbar_wait(q_full, 0u);
+      tc_fence_after();
+      auto issue_s = [&](int j) {                      // S_j = (Q/8) K_j^T, small terms first (as the mma.sync kernel)
+        const int s = j & 1;
+        mbar_wait(full_bar(s), ((uint32_t)(j >> 1)) & 1u);
+        tc_fence_after();
+        if (j >= 2) {                                  // the softmax warps have read S_{j-2} out of this buffer
+          mbar_wait(sfree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t sa = st0 + s * kStage;
+        const uint32_t t_s = tmem_base + kColS0 + 64u * (uint32_t)s;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const uint64_t ah = umma_desc_sw128(q_h + c * (kQPlane / 2)), al = umma_desc_sw128(q_l + c * (kQPlane / 2));
+          const uint64_t bh = umma_desc_sw128(sa + c * (kTilePlane / 2)), bl = umma_desc_sw128(sa + kTilePlane + c * (kTilePlane / 2));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {                // 4 x (K = 8 tf32 = 32 B)
+            const uint64_t o = (uint64_t)(2 * k);
+            umma_tf32(t_s, al + o, bh + o, idesc, (c | k) ? 1u : 0u);
+            umma_tf32(t_s, ah + o, bl + o, idesc, 1u);
+            umma_tf32(t_s, ah + o, bh + o, idesc, 1u);
+          }
+        }
+        umma_commit(sfull_bar(s));
+      };
+      issue_s(0);
+      for (int j = 0; j < nt; j++) {
+        if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
+        const int s = j & 1;
+        mbar_wait(p_full, (uint32_t)j & 1u);           // P_j is in TMEM (and O_{j-1} has been drained)
+        tc_fence_after();
+        const uint32_t sa = st0 + s * kStage;
+        const uint32_t t_o = tmem_base + kColO, t_ph = tmem_base + kColPH, t_pl = tmem_base + kColPL;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {               // 8 keys per UMMA
+          const int c = kk >> 2;
+          const uint64_t o = (uint64_t)(2 * (kk & 3));
+          const uint64_t vh = umma_desc_sw128(sa + 2 * kTilePlane + c * (kTilePlane / 2)) + o;
+          const uint64_t vl = umma_desc_sw128(sa + 3 * kTilePlane + c * (kTilePlane / 2)) + o;
+          umma_tf32_ts(t_o, t_pl + 8u * kk, vh, idesc, kk ? 1u : 0u);
+          umma_tf32_ts(t_o, t_ph + 8u * kk, vl, idesc, 1u);
+          umma_tf32_ts(t_o, t_ph + 8u * kk, vh, idesc, 1u);
+        }
+        umma_commit(o_full);
+        umma_commit(empty_bar(s));                     // K_j and V^T_j are consumed
+      }
+    }
+  } else {
+    const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;                     // query row of this thread
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY, l = 0.f;
+    float o[64];
+#pragma unroll
+    for (int e = 0; e < 64; e++) o[e] = 0.f;
+    for (int j = 0; j < nt; j++) {
+      const int s = j & 1;
+      mbar_wait(sfull_bar(s), ((uint32_t)(j >> 1)) & 1u);
+      tc_fence_after();
+      float sc[64];
+      {
+        uint32_t v[32];
+        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s, v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(v[e]);
+        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s + 32u, v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) sc[32 + e] = __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sfree_bar(s));
+      // key-padding mask + online softmax, all in this thread
+      const int kbase = j * 64;
+      float cm = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 64; e++) {
+        if (kbase + e >= N) sc[e] = -INFINITY;
+        cm = fmaxf(cm, sc[e]);
+      }
+      const float mn = fmaxf(m, cm);                   // finite: every tile holds at least one valid key
+      const float corr = expf(m - mn);
+      float ps = 0.f;
+#pragma unroll
+      for (int e = 0; e < 64; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
+      l = l * corr + ps;
+      m = mn;
+      // P_j -> TMEM as tf32 hi / lo (A operand of the second MMA).  MMA_{j-1} has finished reading the previous P:
+      // this thread waited for o_full(j-1) below.
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t ph[32], pl[32];
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const float p = sc[half * 32 + e];
+          ph[e] = to_tf32(p);
+          pl[e] = to_tf32(p - __uint_as_float(ph[e]));
+        }
+        tmem_st32(tq + kColPH + 32u * half, ph);
+        tmem_st32(tq + kColPL + 32u * half, pl);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+#pragma unroll
+      for (int e = 0; e < 64; e++) o[e] *= corr;       // under the second MMA
+      mbar_wait(o_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      {
+        uint32_t v[32];
+        tmem_ld32(tq + kColO, v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]);
+        tmem_ld32(tq + kColO + 32u, v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) o[32 + e] += __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+    }
+    if (q0 + row < N) {
+      const float inv = 1.0f / l;
+      float* dst = ctx + ((size_t)off[b] + q0 + row) * 768 + h * 64;
+#pragma unroll
+      for (int e = 0; e < 64; e += 4)
+        *reinterpret_cast<float4*>(dst + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+}  // namespace
+
+size_t attention_umma_scratch_floats(int rows_total, int B) {
+  return (size_t)4 * rows_total * 768 + (size_t)2 * B * 768 * kVtPitch;
+}
+
+void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
+                           int max_len, int rows_total, cudaStream_t st) {
+  if (g_dry_run) return;
+  if (max_len > kVtPitch) throw ArgError("launch_attention_umma: more than 512 tokens");
+  const size_t plane = (size_t)rows_total * 768;
+  float* qh = scratch; float* ql = qh + plane; float* kh = ql + plane; float* kl = kh + plane;
+  float* vth = kl + plane; float* vtl = vth + (size_t)B * 768 * kVtPitch;
+  static DevOnce once;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); });
+  dim3 gp((((max_len + 63) & ~63) + 31) / 32, 12, B);
+  attn_prep_kernel<<<gp, 256, 0, st>>>(qkv, qh, ql, kh, kl, vth, vtl, off, len);
+  post_launch("attn_prep", st);
+  alignas(64) CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl;
+  make_tmap_f32(&mQh, qh, 768, rows_total, 768, 128);
+  make_tmap_f32(&mQl, ql, 768, rows_total, 768, 128);
+  make_tmap_f32(&mKh, kh, 768, rows_total, 768, 64);
+  make_tmap_f32(&mKl, kl, 768, rows_total, 768, 64);
+  make_tmap_f32(&mVh, vth, kVtPitch, (long long)B * 768, kVtPitch, 64);
+  make_tmap_f32(&mVl, vtl, kVtPitch, (long long)B * 768, kVtPitch, 64);
+  dim3 g((max_len + 127) / 128, 12, B);
+  attn_umma_kernel<<<g, 192, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx);
+  post_launch("attention", st);
+}
+
+}  // namespace kkx

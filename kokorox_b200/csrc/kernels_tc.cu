@@ -10,6 +10,7 @@
 #include "kernels.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <mutex>
 #include "tc_ptx.cuh"
 
@@ -55,13 +56,13 @@ static EncodeTiledFn get_encode() {
 // bf16 row-major [outer, inner] with row pitch `pitch_elems`; box = [box_outer, 64] elements,
 // 128-byte swizzle (one box row = 128 B = one swizzle span).
 static void make_tmap(void* out_map, const void* ptr, long long inner, long long outer,
-                      long long pitch_elems, int box_outer, bool f32) {
+                      long long pitch_elems, int box_outer, bool f32, bool f16 = false) {
   const int esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()((CUtensorMap*)out_map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+  CUresult r = get_encode()((CUtensorMap*)out_map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 2, const_cast<void*>(ptr),
                             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -78,6 +79,12 @@ void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long o
 void make_tmap_f32(void* out_map, const void* ptr, long long inner, long long outer,
                    long long pitch_elems, int box_outer) {
   make_tmap(out_map, ptr, inner, outer, pitch_elems, box_outer, true);
+}
+
+// fp16 planes: box = [box_outer, 64] elements = 128 B rows
+void make_tmap_f16(void* out_map, const void* ptr, long long inner, long long outer,
+                   long long pitch_elems, int box_outer) {
+  make_tmap(out_map, ptr, inner, outer, pitch_elems, box_outer, false, true);
 }
 
 __device__ __forceinline__ float gelu_new_f(float v) {
@@ -104,7 +111,9 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap tmB2,
                                                       TcConvArgs a) {
   constexpr uint32_t PLANES = MODE ? 2 : 1;
-  constexpr int KE = MODE ? 32 : 64;   // K elements per pipeline stage (one 128-byte swizzle span)
+  const int KE = (MODE && !a.f16) ? 32 : 64;   // K elements per pipeline stage (one 128-byte swizzle span)
+  const bool f16 = MODE && a.f16;              // split-FP16 planes instead of split-TF32
+  const int cs = f16 ? 0 : 1;                  // log2(stages per hi*hi chain): a chain is 64 K-elements either way
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -194,7 +203,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = MODE ? umma_idesc_tf32(128, BN) : umma_idesc_bf16(128, BN);
+      const uint32_t idesc = MODE ? (f16 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN)) : umma_idesc_bf16(128, BN);
       TCT_DECL(3);
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
@@ -209,8 +218,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           for (int k = 0; k < 4; k++)  // 4 x (K=16 bf16 = 32 B) inside the 128-byte swizzle span
             if (!TC_DBG(a, 2)) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
         } else {
-          const int chain = it >> 1, j = chain % 3;
-          const bool chain_start = (it & 1) == 0;
+          const int chain = it >> cs, j = chain % 3;
+          const bool chain_start = (it & cs) == 0;
           if (chain_start && chain >= 3) {       // ring slot j must have been drained by the epilogue
             mbar_wait(bempty_bar(j), (uint32_t)(chain / 3 - 1) & 1u);
             tc_fence_after();
@@ -220,17 +229,17 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
           const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
 #pragma unroll
-          for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
+          for (int k = 0; k < 4; k++) {  // 4 x (32 B of K: 8 tf32 or 16 fp16)
             const uint64_t o = (uint64_t)(2 * k);
             if (TC_DBG(a, 2)) continue;                 // perf experiment: no MMAs
-            if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
+            if (a.nprod >= 4) umma_split(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u, f16);
             if (!TC_DBG(a, 32)) {                     // perf experiment: hi*hi only
-              umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
-              umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
+              umma_split(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u, f16);
+              umma_split(t_small, ah + o, bl + o, idesc, 1u, f16);
             }
-            umma_tf32(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u);
+            umma_split(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u, f16);
           }
-          if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
+          if ((it & cs) == cs || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
         }
         if (CL == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs have read it
         else umma_commit_mc(empty_bar(s), cmask);   // ... in every CTA of the cluster (they all write into it)
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     if (MODE) {
 #pragma unroll
       for (int e = 0; e < (MODE ? BN : 1); e++) racc[e] = 0.f;
-      const int nchains = (num_k + 1) >> 1;
+      const int nchains = (num_k + cs) >> cs;
       for (int ch = 0; ch < nchains; ch++) {
         const int j = ch % 3;
         mbar_wait(bfull_bar(j), (uint32_t)(ch / 3) & 1u);
@@ -332,7 +341,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           const int mm = m0 + row;
           if (mm >= mlen || TC_DBG(a, 1)) continue;
           float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          o.x = fmaf(o.x, a.wscale, bb.x); o.y = fmaf(o.y, a.wscale, bb.y); o.z = fmaf(o.z, a.wscale, bb.z); o.w = fmaf(o.w, a.wscale, bb.w);
           if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
           o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
           o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
@@ -513,7 +522,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
             const int mm = m0 + row;
             if (mm >= mlen || TC_DBG(a, 1)) continue;
             float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            o.x = fmaf(o.x, a.wscale, bb.x); o.y = fmaf(o.y, a.wscale, bb.y); o.z = fmaf(o.z, a.wscale, bb.z); o.w = fmaf(o.w, a.wscale, bb.w);
             if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
             o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
             o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
@@ -556,7 +565,10 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap tmA2,
                                                          const __grid_constant__ CUtensorMap tmB2,
                                                          TcConvArgs a) {
-  constexpr int BN = 128, STAGES = 3, KE = 32;
+  constexpr int BN = 128, STAGES = 3;
+  const bool f16 = a.f16 != 0;                 // split-FP16 planes instead of split-TF32
+  const int KE = f16 ? 64 : 32;                // K elements per 128-byte span
+  const int cs = f16 ? 0 : 1;                  // log2(stages per hi*hi chain): a chain is 64 K-elements either way
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   constexpr int PITCH = 36;
   constexpr uint32_t STG_BYTES = 128 * PITCH * 4;
@@ -574,7 +586,7 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.Cpad / KE;
   const int num_k = a.ks * kchunks;
-  const int nchains = (num_k + 1) >> 1;
+  const int nchains = (num_k + cs) >> cs;
   const int ntm = a.ntiles_m;
   const int total = ntm * ((a.Co + BN - 1) / BN);
 
@@ -639,7 +651,7 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+      const uint32_t idesc = f16 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN);
       int g = 0, gc = 0, ti = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
         // the small-terms accumulator of the previous tile must have been pulled into registers
@@ -649,8 +661,8 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
           mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
           tc_fence_after();
           const uint32_t sa = base + s * STAGE_BYTES;
-          const int G = gc + (it >> 1), j = G % 3;
-          const bool chain_start = (it & 1) == 0;
+          const int G = gc + (it >> cs), j = G % 3;
+          const bool chain_start = (it & cs) == 0;
           if (chain_start && G >= 3) {           // ring slot j must have been drained by the epilogue
             mbar_wait(bempty_bar(j), (uint32_t)(G / 3 - 1) & 1u);
             tc_fence_after();
@@ -659,14 +671,14 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
           const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
 #pragma unroll
-          for (int k = 0; k < 4; k++) {  // 4 x (K=8 tf32 = 32 B)
+          for (int k = 0; k < 4; k++) {  // 4 x (32 B of K: 8 tf32 or 16 fp16)
             const uint64_t o = (uint64_t)(2 * k);
-            if (a.nprod >= 4) umma_tf32(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u);
-            umma_tf32(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u);
-            umma_tf32(t_small, ah + o, bl + o, idesc, 1u);
-            umma_tf32(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u);
+            if (a.nprod >= 4) umma_split(t_small, al + o, bl + o, idesc, (it | k) ? 1u : 0u, f16);
+            umma_split(t_small, al + o, bh + o, idesc, (a.nprod >= 4 || (it | k)) ? 1u : 0u, f16);
+            umma_split(t_small, ah + o, bl + o, idesc, 1u, f16);
+            umma_split(t_big, ah + o, bh + o, idesc, (chain_start && k == 0) ? 0u : 1u, f16);
           }
-          if ((it & 1) == 1 || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
+          if ((it & cs) == cs || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
           umma_commit(empty_bar(s));
         }
         umma_commit(sfull_bar);
@@ -750,7 +762,7 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
             const int mm = m0 + row;
             if (mm >= mlen) continue;
             float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            o.x = fmaf(o.x, a.wscale, bb.x); o.y = fmaf(o.y, a.wscale, bb.y); o.z = fmaf(o.z, a.wscale, bb.z); o.w = fmaf(o.w, a.wscale, bb.w);
             if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
             o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
             o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
@@ -789,7 +801,7 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
   const int grid = total < nsm ? total : nsm;
   TcConvArgs b = a;
   static const int l2mb = env_int("KKX_TC_GROUP_MB", 24);
-  const long long per_tile = 128LL * a.Cpad * 8;       // bytes of hi+lo planes of one m-tile
+  const long long per_tile = 128LL * a.Cpad * (a.f16 ? 4 : 8);       // bytes of hi+lo planes of one m-tile
   long long gm = (long long)l2mb * 1000000LL / (per_tile > 0 ? per_tile : 1);
   if (gm < 8) gm = 8;
   if (gm > a.ntiles_m) gm = a.ntiles_m;
@@ -1081,6 +1093,96 @@ void launch_apply_tf32(const float* x, int ldx, int C, const float* scale, const
   const int vec_ok = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
   apply_tf32_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, out_hi, out_lo, Cpad, rows_total, off, len, vec_ok);
   post_launch("apply_tf32", st);
+}
+
+// Split-FP16 operand producer: the same prologue arithmetic, then v * 16 as two fp16 planes hi = rn(v), lo = rn(v - hi).
+// fp16 and tf32 carry the same 11-bit significand, so hi + lo holds 22 bits exactly like the tf32 pair; the factor 16
+// (undone, exactly, in the GEMM epilogue) keeps lo out of the fp16 subnormal range for |v| >= 2^-7, below which the
+// absolute error is <= 2^-29.  Values beyond +-4094 would saturate (Kokoro's activations are O(1) .. O(10^2)).
+__global__ void __launch_bounds__(256) apply_f16x2_kernel(const float* __restrict__ x, int ldx, int C,
+                                                          const float* scale, const float* shift,
+                                                          int act, float slope, __half* out_hi, __half* out_lo,
+                                                          int Cpad, int rows_total, const int* off,
+                                                          const int* len, int vec_ok) {
+  const int b = blockIdx.y;
+  const int L = len[b], o = off[b];
+  const int r_begin = o - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : o + L + kGapRows;
+  const int rb = r_begin + blockIdx.x * kApplyRows;
+  if (rb >= r_end) return;
+  const int re = min(r_end, rb + kApplyRows);
+  const float* sc = scale ? scale + (size_t)b * C : nullptr;
+  const float* sh = shift ? shift + (size_t)b * C : nullptr;
+  const int cq = Cpad >> 2;
+  const int total = (re - rb) * cq;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = rb + i / cq;
+    const int c = (i % cq) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r >= o && r < o + L && c < C) {
+      const float* xp = x + (size_t)r * ldx + c;
+      if (vec_ok && c + 3 < C) {
+        const float4 t = *reinterpret_cast<const float4*>(xp);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (c + e < C) v[e] = xp[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        if (c + e < C) {
+          if (sc) v[e] = v[e] * sc[c + e] + sh[c + e];            // same arithmetic as the fp32 SIMT prologue
+          if (act == ACT_LRELU) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+        } else v[e] = 0.f;
+      }
+    }
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float s = fminf(fmaxf(v[e] * kSplitF16Scale, -65504.f), 65504.f);
+      hi[e] = __float2half_rn(s);
+      lo[e] = __float2half_rn(s - __half2float(hi[e]));
+    }
+    *reinterpret_cast<uint2*>(out_hi + (size_t)r * Cpad + c) =
+        make_uint2((uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16),
+                   (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16));
+    *reinterpret_cast<uint2*>(out_lo + (size_t)r * Cpad + c) =
+        make_uint2((uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16),
+                   (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16));
+  }
+}
+float split_f16_host(const float* w, size_t n, unsigned short* hi, unsigned short* lo) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; i++) mx = fmaxf(mx, fabsf(w[i]));
+  int s = 0;
+  if (mx > 0.f && isfinite(mx)) {
+    int e;
+    frexpf(mx, &e);                    // mx = m * 2^e, m in [0.5, 1)
+    s = 14 - e;                        // mx * 2^s in [2^13, 2^14)
+  }
+  if (s > 60) s = 60;
+  if (s < -60) s = -60;
+  const float up = ldexpf(1.f, s);
+  for (size_t i = 0; i < n; i++) {
+    const float v = w[i] * up;         // exact (power of two)
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi[i] = __half_as_ushort(h);
+    lo[i] = __half_as_ushort(l);
+  }
+  return ldexpf(1.f, -s);
+}
+
+void launch_apply_f16x2(const float* x, int ldx, int C, const float* scale, const float* shift, int act,
+                        float slope, void* out_hi, void* out_lo, int Cpad, int rows_total,
+                        const int* off, const int* len, int B, int max_len, cudaStream_t st) {
+  if (g_dry_run) return;
+  const int rows = max_len + 2 * kGapRows + 8;
+  dim3 g((rows + kApplyRows - 1) / kApplyRows, B);
+  const int vec_ok = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  apply_f16x2_kernel<<<g, 256, 0, st>>>(x, ldx, C, scale, shift, act, slope, static_cast<__half*>(out_hi),
+                                        static_cast<__half*>(out_lo), Cpad, rows_total, off, len, vec_ok);
+  post_launch("apply_f16x2", st);
 }
 
 // Depthwise ConvTranspose1d(k3,s2,p1,op1) on lrelu(x*scale+shift) -> bf16 operand [2T rows, Cpad]

@@ -312,6 +312,26 @@ TcW32 WeightSet::make_tc32(const std::vector<float>& w, int Co, int ks, int Ci) 
     make_tmap_f32(t.tm_lo_c, t.lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 64);
     t.has_c = true;
   }
+  // split-FP16 planes of the same (zero-padded) matrix
+  {
+    std::vector<float> wp((size_t)Co * ks * t.Cpad, 0.f);
+    for (int o = 0; o < Co; o++)
+      for (int k = 0; k < ks; k++)
+        for (int c = 0; c < Ci; c++) wp[((size_t)o * ks + k) * t.Cpad + c] = w[((size_t)o * ks + k) * Ci + c];
+    std::vector<unsigned short> h16(wp.size()), l16(wp.size());
+    t.wscale16 = split_f16_host(wp.data(), wp.size(), h16.data(), l16.data());
+    KKX_CUDA(cudaMalloc(&t.h_hi, h16.size() * 2)); owned_.push_back(t.h_hi);
+    KKX_CUDA(cudaMalloc(&t.h_lo, l16.size() * 2)); owned_.push_back(t.h_lo);
+    device_bytes += h16.size() * 4;
+    KKX_CUDA(cudaMemcpy(t.h_hi, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice));
+    KKX_CUDA(cudaMemcpy(t.h_lo, l16.data(), l16.size() * 2, cudaMemcpyHostToDevice));
+    make_tmap_f16(t.tm16_hi, t.h_hi, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
+    make_tmap_f16(t.tm16_lo, t.h_lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n_tf32(Co));
+    if (t.has_c) {
+      make_tmap_f16(t.tm16_hi_c, t.h_hi, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 64);
+      make_tmap_f16(t.tm16_lo_c, t.h_lo, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 64);
+    }
+  }
   return t;
 }
 

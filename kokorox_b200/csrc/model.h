@@ -64,6 +64,13 @@ struct TcW32 {
   alignas(64) unsigned char tm_lo_c[128];
   bool has_c = false;
   int Cpad = 0, Ci = 0, Co = 0, ks = 0;
+  // split-FP16 planes of w * 2^s (same layout, 2-byte elements) + their TMA descriptors; wscale16 = 2^-s
+  void* h_hi = nullptr; void* h_lo = nullptr;
+  alignas(64) unsigned char tm16_hi[128];
+  alignas(64) unsigned char tm16_lo[128];
+  alignas(64) unsigned char tm16_hi_c[128];
+  alignas(64) unsigned char tm16_lo_c[128];
+  float wscale16 = 1.f;
 };
 struct LstmW { float* wih = nullptr; float* bias = nullptr; float* whhT = nullptr; int in = 0; TcW32 t_ih; };
 struct AdaBlkW {  // AdainResBlk1d
@@ -128,6 +135,11 @@ struct Options {
   // on two streams for batches of at most fork_max_batch utterances (their kernels do not fill the GPU)
   int latency_graphs = 1;
   int fork_max_batch = 4;
+  // ALBERT attention kernel: 1 = tcgen05 / TMEM / TMA (kernels_attn.cu), 0 = the mma.sync kernel of round 1
+  int attention_umma = 0;
+  // split-precision GEMMs of the predictor path: 1 = fp16 hi/lo planes ("3xFP16": the same 22 significand bits as
+  // 3xTF32 at half the operand bytes and twice the MMA rate), 0 = tf32 hi/lo planes
+  int split_f16 = 0;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32

@@ -77,18 +77,30 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
   cudaStream_t st = cur_;
   if (opt.precision == 1 && w32 && w32->hi && split_hi_ && (size_t)Lin.rows * w32->Cpad <= split_cap_) {
     if (g_dry_run) return;
-    launch_apply_tf32(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
-                      Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
+    const bool f16 = opt.split_f16 && w32->h_hi;
     alignas(64) unsigned char tA[128], tA2[128];
-    make_tmap_f32(tA, split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
-    make_tmap_f32(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
     TcConvArgs a;
-    a.tmA = tA; a.tmA2 = tA2; a.tmB = w32->tm_hi; a.tmB2 = w32->tm_lo; a.tf32 = 1; a.nprod = 3; a.eact = eact;
-    // 2-CTA clusters with TMA-multicast weight tiles: measured on B200 NOT faster (13.9 vs 12.4 ms for the 12 qkv
-    // GEMMs): these GEMMs are bound by what each SM can ingest (~28 B/clk: 64 KB of hi/lo planes per 128x128x32
-    // step), which multicast does not change.  Opt-in (KKX_TC_CLUSTER=1).
-    static const bool cl_ok = env_flag("KKX_TC_CLUSTER", false);
-    if (w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = cl_ok ? 2 : 1; }
+    if (f16) {
+      // the scratch planes hold 2-byte elements in this mode (half of the fp32-sized buffers is used)
+      launch_apply_f16x2(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
+                         Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
+      make_tmap_f16(tA, split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      make_tmap_f16(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      a.tmB = w32->tm16_hi; a.tmB2 = w32->tm16_lo; a.f16 = 1;
+      a.wscale = w32->wscale16 / kSplitF16Scale;
+      if (w32->has_c) { a.tmB_c = w32->tm16_hi_c; a.tmB2_c = w32->tm16_lo_c; }
+    } else {
+      launch_apply_tf32(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
+                        Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
+      make_tmap_f32(tA, split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      make_tmap_f32(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      a.tmB = w32->tm_hi; a.tmB2 = w32->tm_lo;
+      // 2-CTA clusters with TMA-multicast weight tiles: measured on B200 NOT faster (13.9 vs 12.4 ms for the 12 qkv
+      // GEMMs); opt-in in experiment builds (KKX_TC_CLUSTER=1)
+      static const bool cl_ok = env_flag("KKX_TC_CLUSTER", false);
+      if (w32->has_c) { a.tmB_c = w32->tm_hi_c; a.tmB2_c = w32->tm_lo_c; a.cluster = cl_ok ? 2 : 1; }
+    }
+    a.tmA = tA; a.tmA2 = tA2; a.tf32 = 1; a.nprod = 3; a.eact = eact;
     a.Cpad = w32->Cpad; a.Ci = K; a.Co = N; a.ks = ks; a.dil = 1; a.pad = pad;
     a.in_off = Lin.d_off; a.m_len = Lm.d_len; a.max_m = Lm.max_len; a.B = Lm.B; a.sum_m = Lm.sum_len;
     a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lm.d_off;
@@ -111,7 +123,8 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
 size_t Model::token_arena_bytes() const {
   const size_t R = (size_t)tokL_.rows;
   return R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048 + 2048 + 2 * 512) * sizeof(float) +
-         (size_t)B_ * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20);
+         (size_t)B_ * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20) +
+         (opt.attention_umma ? attention_umma_scratch_floats((int)R, B_) * sizeof(float) + 1024 : 0);
 }
 
 void Model::token_phase(Run& r) {
@@ -141,7 +154,7 @@ void Model::token_phase(Run& r) {
   // captured once (on the second call with that count) and replayed afterwards -- ~190 launches become one.
   const bool graph_ok = opt.latency_graphs && B_ == 1 && !debug_ && !stats.profile && !stats.check_each && inj_dur_.empty();
   if (graph_ok) {
-    const GraphKey key{tok_len_[0], opt.precision, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
+    const GraphKey key{tok_len_[0], opt.precision * 4 + opt.attention_umma * 2 + opt.split_f16, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
     auto it = graphs_.find(key);
     if (it != graphs_.end() && it->second.exec) {
       r = it->second.run;
@@ -249,12 +262,14 @@ void Model::token_issue(Run& r) {
   float* tmp = A.alloc<float>(R * 768);
   float* qkv = A.alloc<float>(R * 2304);
   float* ff = A.alloc<float>(R * 2048);
+  float* att_scratch = opt.attention_umma ? A.alloc<float>(attention_umma_scratch_floats((int)R, B)) : nullptr;
   launch_albert_embed(d_ids_, W.word, W.pos, W.type, W.emb_lnw, W.emb_lnb, e, L.d_off, L.d_len, B,
                       L.max_len, st);
   gemm(L, L, e, 128, 128, W.map_w, &W.t_map, W.map_b, 768, h, 768, 0);
   for (int layer = 0; layer < 12; layer++) {
     gemm(L, L, h, 768, 768, W.qkv_w, &W.t_qkv, W.qkv_b, 2304, qkv, 2304, 0);
-    launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
+    if (att_scratch) launch_attention_umma(qkv, att_scratch, ctx, L.d_off, L.d_len, B, L.max_len, L.rows, st);
+    else launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
     gemm(L, L, ctx, 768, 768, W.dense_w, &W.t_dense, W.dense_b, 768, tmp, 768, 0);
     LnArgs ln;
     ln.x = h; ln.ldx = 768; ln.res = tmp; ln.ldr = 768; ln.w = W.attn_lnw; ln.b = W.attn_lnb;

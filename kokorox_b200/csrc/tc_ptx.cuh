@@ -74,6 +74,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// kind::f16 with fp16 operands (A/B format 0), fp32 accumulate; K = 16 per instruction
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// split-precision product: tf32 planes (f16 = false) or fp16 planes (f16 = true); both step 32 bytes of K per
+// instruction, so the smem descriptors advance identically
+__device__ __forceinline__ void umma_split(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc, bool f16) {
+  if (f16) umma_bf16(tmem_d, adesc, bdesc, idesc, acc);     // kind::f16; the instruction descriptor selects fp16
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, acc);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

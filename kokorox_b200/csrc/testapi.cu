@@ -178,6 +178,56 @@ KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const 
   });
 }
 
+KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                                int Co, int ks, int dil, int pad, int eact, float* out) {
+  return run(device, [&] {
+    const int Cpad = (Ci + 63) & ~63;
+    const int off = kGapRows, rows_total = (off + L + kGapRows + 7) & ~7;
+    std::vector<float> wp((size_t)Co * ks * Cpad, 0.f);
+    for (int o = 0; o < Co; o++)
+      for (int k = 0; k < ks; k++)
+        for (int c = 0; c < Ci; c++) wp[((size_t)o * ks + k) * Cpad + c] = w[((size_t)o * ks + k) * Ci + c];
+    std::vector<unsigned short> whi(wp.size()), wlo(wp.size());
+    const float wscale = split_f16_host(wp.data(), wp.size(), whi.data(), wlo.data());
+    std::vector<float> xin((size_t)rows_total * Ci, 0.f);
+    memcpy(xin.data() + (size_t)off * Ci, x, (size_t)L * Ci * 4);
+    DevBuf dx(xin.data(), xin.size() * 4), dwh(whi.data(), whi.size() * 2), dwl(wlo.data(), wlo.size() * 2);
+    DevBuf db(bias, bias ? Co * 4 : 0), dout(nullptr, (size_t)L * Co * 4);
+    DevBuf dah(nullptr, (size_t)rows_total * Cpad * 2), dal(nullptr, (size_t)rows_total * Cpad * 2);
+    KKX_CUDA(cudaMemset(dah.p, 0xFF, (size_t)rows_total * Cpad * 2));
+    KKX_CUDA(cudaMemset(dal.p, 0xFF, (size_t)rows_total * Cpad * 2));
+    int meta[4] = {off, L, 0, 0};
+    DevBuf dm(meta, sizeof meta);
+    launch_apply_f16x2(dx.as<float>(), Ci, Ci, nullptr, nullptr, ACT_NONE, 0.f, dah.p, dal.p, Cpad,
+                       rows_total, dm.as<int>(), dm.as<int>() + 1, 1, L, 0);
+    alignas(64) unsigned char tA[128], tA2[128], tB[128], tB2[128], tBc[128], tB2c[128];
+    make_tmap_f16(tA, dah.p, Cpad, rows_total, Cpad, 128);
+    make_tmap_f16(tA2, dal.p, Cpad, rows_total, Cpad, 128);
+    make_tmap_f16(tB, dwh.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, tc_box_n_tf32(Co));
+    make_tmap_f16(tB2, dwl.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, tc_box_n_tf32(Co));
+    // tile table of the one item, so that large problems take the persistent kernel like the model does
+    const int nt = (L + 127) / 128;
+    int tiles[2] = {0, nt};
+    DevBuf dt(tiles, sizeof tiles);
+    TcConvArgs a;
+    a.tmA = tA; a.tmA2 = tA2; a.tmB = tB; a.tmB2 = tB2; a.tf32 = 1; a.nprod = 3; a.eact = eact;
+    a.f16 = 1; a.wscale = wscale / kSplitF16Scale;
+    if (tc_box_n_tf32(Co) == 128) {
+      make_tmap_f16(tBc, dwh.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, 64);
+      make_tmap_f16(tB2c, dwl.p, (long long)ks * Cpad, Co, (long long)ks * Cpad, 64);
+      a.tmB_c = tBc; a.tmB2_c = tB2c;
+    }
+    a.Cpad = Cpad; a.Ci = Ci; a.Co = Co; a.ks = ks; a.dil = dil; a.pad = pad;
+    a.in_off = dm.as<int>(); a.m_len = dm.as<int>() + 1; a.max_m = L; a.B = 1; a.sum_m = L;
+    a.bias = bias ? db.as<float>() : nullptr;
+    a.out = dout.as<float>(); a.ldo = Co; a.ocol = 0; a.out_off = dm.as<int>() + 2; a.ors = 1; a.oro = 0;
+    a.tile_start = dt.as<int>(); a.ntiles_m = nt;
+    launch_conv_tc(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)L * Co * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out) {
   return run(device, [&] {
     DevBuf dx(xproj, (size_t)N * 2048 * 4), dw(whhT, (size_t)2 * 256 * 1024 * 4), dout(nullptr, (size_t)N * 512 * 4);
@@ -208,6 +258,28 @@ KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) 
     launch_attention(dq.as<float>(), dout.as<float>(), dm.as<int>(), dm.as<int>() + 1, 1, N, 0);
     KKX_CUDA(cudaDeviceSynchronize());
     KKX_CUDA(cudaMemcpy(ctx, dout.p, (size_t)N * 768 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+KKX_API int kkx_test_attention_batch(int device, const float* qkv, int B, const int* off, const int* len, int rows,
+                                     int umma, float* ctx) {
+  return run(device, [&] {
+    int max_len = 0;
+    for (int b = 0; b < B; b++) max_len = std::max(max_len, len[b]);
+    DevBuf dq(qkv, (size_t)rows * 2304 * 4), dout(ctx, (size_t)rows * 768 * 4);
+    DevBuf doff(off, (size_t)B * 4), dlen(len, (size_t)B * 4);
+    if (umma) {
+      // scratch deliberately filled with NaN patterns: stale gap rows must never reach a valid result
+      const size_t nf = attention_umma_scratch_floats(rows, B);
+      DevBuf ds(nullptr, nf * 4);
+      KKX_CUDA(cudaMemset(ds.p, 0xFF, nf * 4));
+      launch_attention_umma(dq.as<float>(), ds.as<float>(), dout.as<float>(), doff.as<int>(), dlen.as<int>(), B, max_len, rows, 0);
+      KKX_CUDA(cudaDeviceSynchronize());
+    } else {
+      launch_attention(dq.as<float>(), dout.as<float>(), doff.as<int>(), dlen.as<int>(), B, max_len, 0);
+      KKX_CUDA(cudaDeviceSynchronize());
+    }
+    KKX_CUDA(cudaMemcpy(ctx, dout.p, (size_t)rows * 768 * 4, cudaMemcpyDeviceToHost));
   });
 }
 

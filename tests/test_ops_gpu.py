@@ -169,6 +169,45 @@ def test_attention_matches_torch(lib, N):
     np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("lens", [[3], [64], [65], [130], [512], [52, 512, 1, 200, 129, 383]])
+def test_attention_tcgen05_matches_torch_and_mma_sync(lib, lens):
+    """kernels_attn.cu: S and P V on tcgen05 with P in tensor memory, against torch fp32 softmax attention and the
+    round-1 mma.sync kernel.  Ragged items packed with gap rows; gap rows carry NaN so that a stale row reaching a
+    valid result would show."""
+    i32 = C.POINTER(C.c_int32)
+    B = len(lens)
+    off, o = [], 32
+    for n in lens:
+        off.append(o)
+        o = (o + n + 32 + 7) & ~7
+    rows = o
+    qkv = np.full((rows, 2304), np.nan, np.float32)
+    for b, n in enumerate(lens):
+        qkv[off[b]:off[b] + n] = rnd(n, 2304, seed=100 * n + b)
+    offa, lena = np.asarray(off, np.int32), np.asarray(lens, np.int32)
+    outs = []
+    for umma in (1, 0):
+        out = np.zeros((rows, 768), np.float32)
+        rc = lib.kkx_test_attention_batch(0, fp(qkv), B, offa.ctypes.data_as(i32), lena.ctypes.data_as(i32), rows, umma, fp(out))
+        assert rc == 0, lib.kkx_test_last_error()
+        outs.append(out)
+    for b, n in enumerate(lens):
+        t = torch.from_numpy(qkv[off[b]:off[b] + n])
+        q, k, v = (t[:, i * 768:(i + 1) * 768].view(n, 12, 64).transpose(0, 1) for i in range(3))
+        p = torch.softmax(q.double() @ k.double().transpose(1, 2) / 8.0, -1)
+        ref = (p @ v.double()).transpose(0, 1).reshape(n, 768).numpy()
+        for name, out in zip(("tcgen05", "mma.sync"), outs):
+            got = out[off[b]:off[b] + n]
+            assert np.isfinite(got).all(), f"{name}: item {b} has non-finite values"
+            err = np.abs(got - ref).max()
+            assert err < 2e-5, f"{name}: item {b} (N={n}) max abs error {err}"
+    # rows outside the items are never written
+    mask = np.ones(rows, bool)
+    for b, n in enumerate(lens):
+        mask[off[b]:off[b] + n] = False
+    assert not outs[0][mask].any()
+
+
 @pytest.mark.parametrize("L,Cc", [(50, 128), (1000, 256), (20001, 128)])
 def test_instance_norm_adain_coefficients(lib, L, Cc):
     x = (rnd(L, Cc, seed=L) * 2 + 3 * rnd(1, Cc, seed=L + 1)).astype(np.float32)
@@ -264,6 +303,35 @@ def test_split_tf32_gemm_is_fp32_grade(lib, L, Ci, Co, k, nprod):
     rms_32 = np.sqrt(((ref32 - ref64) ** 2).mean())
     print(f"split-TF32 x{nprod}: max err {e_tc:.3e} (torch fp32 {e_32:.3e}), rms err {rms_tc:.3e} (fp32 {rms_32:.3e})")
     assert e_tc < 2e-5 and rms_tc < 8 * max(rms_32, 1e-8)
+
+
+@pytest.mark.parametrize("L,Ci,Co,k", [(512, 768, 2304, 1), (300, 2048, 768, 1), (200, 128, 768, 1), (140, 640, 2048, 1),
+                                       (333, 512, 512, 5), (257, 512, 256, 3), (64, 512, 50, 1), (52, 768, 768, 1),
+                                       (20000, 768, 768, 1), (9000, 512, 512, 3)])
+def test_split_fp16_gemm_is_fp32_grade(lib, L, Ci, Co, k):
+    """"3xFP16": fp16 hi/lo operand planes (the same 22 significand bits as the tf32 pair) on kind::f16 MMAs with the
+    power-of-two plane scaling undone in the epilogue -- must be as close to the fp64 result as torch's own fp32.
+    The two largest cases take the persistent kernel (>= 148 tiles), the others the single-tile kernel.  Inputs span
+    five decades (row scales 1e-3 .. 30) so that small activations and the saturating range are exercised."""
+    x = rnd(L, Ci, seed=L + Ci)
+    x *= np.exp(np.random.default_rng(7).uniform(np.log(1e-3), np.log(30.0), size=(L, 1))).astype(np.float32)
+    w = rnd(Co, Ci, k, seed=L + Co, scale=0.5 / np.sqrt(Ci * k))
+    b = rnd(Co, seed=3)
+    pad = (k - 1) // 2
+    tx, tw, tb = torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b)
+    ref64 = F.conv1d(tx.double().T[None], tw.double(), tb.double(), padding=pad)[0].T.numpy()
+    ref32 = F.conv1d(tx.T[None], tw, tb, padding=pad)[0].T.numpy()
+    out = np.zeros((L, Co), np.float32)
+    rc = lib.kkx_test_conv_f16x3(0, fp(x), L, Ci, fp(np.ascontiguousarray(w.transpose(0, 2, 1))), fp(b), Co, k, 1, pad,
+                                 0, fp(out))
+    assert rc == 0, lib.kkx_test_last_error()
+    scale = np.abs(ref64).max(axis=1, keepdims=True) + 1e-6          # per-row magnitude (rows differ by 4 decades)
+    e_tc = (np.abs(out - ref64) / scale).max()
+    e_32 = (np.abs(ref32 - ref64) / scale).max()
+    rms_tc = np.sqrt((((out - ref64) / scale) ** 2).mean())
+    rms_32 = np.sqrt((((ref32 - ref64) / scale) ** 2).mean())
+    print(f"split-FP16 x3: max rel err {e_tc:.3e} (torch fp32 {e_32:.3e}), rms {rms_tc:.3e} (fp32 {rms_32:.3e})")
+    assert e_tc < 4e-6 and rms_tc < 8 * max(rms_32, 1e-9)
 
 
 @pytest.mark.parametrize("Cc,k,dil", [(128, 3, 1), (128, 11, 5), (256, 7, 3)])

@@ -352,6 +352,7 @@ def test_latency_path_graphs_and_forks_do_not_change_results(model):
     """Single-utterance calls replay the token phase from a CUDA graph (captured on the second call with a given
     token count) and small batches run independent branches on two streams; neither may change a single bit."""
     model.set_noise(None)
+    model.debug_enable(False)                  # stage dumps (left on by earlier tests) disable both mechanisms
     model.set_option("precision", 1)
     try:
         for n in (50, 128, 510):
@@ -390,6 +391,32 @@ def test_latency_path_graphs_and_forks_do_not_change_results(model):
     finally:
         model.set_option("latency_graphs", 1)
         model.set_option("fork_max_batch", 4)
+        model.set_option("precision", 0)
+
+
+@pytest.mark.parametrize("opts", [{"attention_umma": 1}, {"split_f16": 1}, {"attention_umma": 1, "split_f16": 1}])
+@pytest.mark.parametrize("n_tokens,seed,speed", [(50, 0, 1.0), (300, 4, 1.3), (510, 1, 1.0), (510, 1000, 1.0)])
+def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, seed, speed):
+    """The tcgen05 attention kernel and the split-FP16 GEMMs replace fp32-grade kernels on the path that decides
+    the integer durations: every seeded case must still match the oracle bit for bit, with dur_float as close as the
+    round-1 kernels get it."""
+    ids, style = synth_case(n_tokens, seed, 100 + seed)
+    noise = make_noise(12 * len(ids) if n_tokens > 60 else 50 * len(ids))
+    ref = oracle.forward(ids, style, speed, noise=noise, stages=True)
+    model.set_option("precision", 1)
+    for k, v in opts.items():
+        model.set_option(k, v)
+    try:
+        audio, dur = run_cuda(model, ids, style, speed, noise, stages=True)
+        assert np.array_equal(dur, ref["pred_dur"]), np.flatnonzero(dur != ref["pred_dur"])
+        assert rel_l2(ref["stages"]["dur_float"], model.debug_stage("dur_float")) < 1e-5
+        assert rel_l2(ref["stages"]["bert"], model.debug_stage("bert")) < 1e-4
+        assert rel_l2(ref["stages"]["F0"], model.debug_stage("F0")) < 1e-4
+        assert rel_l2(ref["stages"]["N"], model.debug_stage("N")) < 1e-4
+        assert audio.shape == ref["audio"].shape and np.isfinite(audio).all()
+    finally:
+        for k in opts:
+            model.set_option(k, 0)
         model.set_option("precision", 0)
 
 
