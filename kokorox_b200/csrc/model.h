@@ -136,10 +136,10 @@ struct Options {
   int latency_graphs = 1;
   int fork_max_batch = 4;
   // ALBERT attention kernel: 1 = tcgen05 / TMEM / TMA (kernels_attn.cu), 0 = the mma.sync kernel of round 1
-  int attention_umma = 0;
+  int attention_umma = 1;
   // split-precision GEMMs of the predictor path: 1 = fp16 hi/lo planes ("3xFP16": the same 22 significand bits as
   // 3xTF32 at half the operand bytes and twice the MMA rate), 0 = tf32 hi/lo planes
-  int split_f16 = 0;
+  int split_f16 = 1;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
