@@ -82,6 +82,12 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
 /* Host-only: the library's tensor spec table (onnx_loader.cu kokoro_tensor_specs) as text lines "name d0 d1 ...\n";
  * returns the full length, writes at most capacity-1 characters + NUL. */
 KKX_API int64_t kkx_test_tensor_specs(char* buf, int64_t capacity);
+/* The same kernel on a bf16 residual stream: x and res are rounded to bf16 first; res == NULL is conv1 (bf16 x -> bf16
+ * out), res != NULL is conv2 (bf16 residual -> the next bf16 x when want_bf16, else the fp32 block output). */
+KKX_API int kkx_test_arb_conv_stream(int device, const float* x, int B, const int* lens, int C, const float* scale,
+                                     const float* shift, const float* alpha, const float* w, const float* bias, int ks,
+                                     int dil, const float* res, float oscale, int accumulate, int want_bf16, float* out,
+                                     float* sums);
 KKX_API const char* kkx_test_last_error(void);
 
 #ifdef __cplusplus

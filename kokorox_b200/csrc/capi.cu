@@ -334,7 +334,7 @@ KKX_API int kkx_infer_batch(kkx_ctx* ctx, int32_t batch, const int64_t* tokens, 
 
 // Leader side of the coalescer: run `batch` as one ragged batch; on failure re-run the requests one by one so
 // that only the offending caller sees the error.
-static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& batch) {
+static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& batch, bool count = true) {
   const int B = (int)batch.size();
   std::vector<int32_t> offs(B + 1, 0);
   for (int i = 0; i < B; i++) offs[i + 1] = offs[i] + std::max(batch[i]->n, 0);
@@ -369,9 +369,11 @@ static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& b
       w.rc = KKX_OK;
       ctx->views[w.audio] = sb;
     }
-    ctx->coalesced_batches++;
-    ctx->coalesced_requests += B;
-    ctx->coalesced_largest = std::max<int64_t>(ctx->coalesced_largest, B);
+    if (count) {     // (the asynchronous worker keeps its own counters)
+      ctx->coalesced_batches++;
+      ctx->coalesced_requests += B;
+      ctx->coalesced_largest = std::max<int64_t>(ctx->coalesced_largest, B);
+    }
     return;
   }
   for (int i = 0; i < B; i++) {   // isolate the failure
@@ -388,8 +390,7 @@ static void serve_coalesced(kkx_ctx* ctx, const std::vector<kkx_ctx::Waiter*>& b
       hand_out(ctx, h1, c1);
       w.audio = h1;
       w.samples = s1[1];
-      ctx->coalesced_batches++;
-      ctx->coalesced_requests++;
+      if (count) { ctx->coalesced_batches++; ctx->coalesced_requests++; }
     } else {
       w.err = g_err;      // guarded() left the message in this (the leader's) thread
     }
@@ -591,7 +592,7 @@ static void async_worker(kkx_ctx* ctx) {
     }
     al.unlock();
     try {
-      serve_coalesced(ctx, batch);
+      serve_coalesced(ctx, batch, false);
     } catch (...) {
       for (auto* w : batch) { w->rc = KKX_ERR_CUDA; w->err = "internal error while serving an asynchronous batch"; w->audio = nullptr; }
     }
@@ -738,6 +739,7 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "latency_graphs") o.latency_graphs = value ? 1 : 0;
     else if (k == "attention_umma") o.attention_umma = value ? 1 : 0;
     else if (k == "split_f16") o.split_f16 = value ? 1 : 0;
+    else if (k == "stream_bf16") o.stream_bf16 = value ? 1 : 0;
     else if (k == "fork_max_batch") { if (value < 0 || value > 512) throw ArgError("fork_max_batch must be in 0..512"); o.fork_max_batch = (int)value; }
     else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {

@@ -112,6 +112,8 @@ struct ArbConvArgs {
   __nv_bfloat16* out_bf16 = nullptr;                   // y (+res) as bf16, unscaled (nullable)
   float* out_f32 = nullptr;                            // (y + res) * oscale (+ previous value) (nullable)
   const float* res = nullptr; float oscale = 1.f; int accumulate = 0;
+  int res_bf16 = 0;                                    // `res` points at bf16 data (bf16 residual stream); conv1 of such a
+                                                       // stream has in_bf16 = 1, conv2 writes out_bf16 (next x) or out_f32
   float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
   long long* timing = nullptr;                         // diagnostics (-DKKX_ARB_TIMING builds): per-role phase cycle counters
   // "post" variant (generator conv_post): operand transform = LeakyReLU(slope) instead of AdaIN + Snake, weights
@@ -174,11 +176,13 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
 //   partial sums over row chunks, then scale[b,c] = rstd*(1+gamma), shift[b,c] = beta - mean*scale
 //   with gamma = sty[b*sld + soff + c], beta = sty[b*sld + soff + C + c].
 constexpr int kStatRows = 128;
+// out_bf16 (nullable, needs ldx == C): also write a bf16 copy [rows, C] of x -- the start of a bf16 residual stream
 void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
-                     int B, int max_len, cudaStream_t st);  // part [B][nchunk_max][2][C]
-// out = a + b (all [rows, C], row pitch C) and the chunk statistics of the sum, in one pass
+                     int B, int max_len, cudaStream_t st, void* out_bf16 = nullptr);  // part [B][nchunk_max][2][C]
+// out = a + b (all [rows, C], row pitch C) and the chunk statistics of the sum, in one pass; with out_bf16 the sum is
+// written ONLY as bf16 [rows, C] (statistics still from the fp32 sum) and `out` is left untouched
 void launch_add_rows_stats(const float* a, const float* b, float* out, int C, float* part, const int* off,
-                           const int* len, int B, int max_len, cudaStream_t st);
+                           const int* len, int B, int max_len, cudaStream_t st, void* out_bf16 = nullptr);
 void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
                        int sld, int soff, float eps, float* scale, float* shift, int B,
                        cudaStream_t st);

@@ -103,8 +103,16 @@ struct TileCur {
 // the weight set zero-padded to 128 output channels and an fp32 [rows, ldo] store of the first `cout` channels.
 // The generic path re-fetched the activation tile for each of the 7 taps and needed a separate LeakyReLU -> bf16
 // pass over the 4.7 GB stage output.
-template <int BN, int MSUB, bool CONV2, bool T, bool POST = false>
+// SB ("stream in bf16"): the res-block's residual stream x is stored as bf16 between iterations instead of fp32.  The
+// k = 3 / k = 7 convs are HBM-bound (16 B per row-channel and iteration with an fp32 stream); with a bf16 stream an
+// iteration moves 10 B: conv1 reads bf16 x (SB = 1), conv2 reads the bf16 residual and writes either the next bf16 x
+// (SB = 1) or -- last iteration -- the fp32 block output (SB = 2).  The AdaIN statistics still come from the fp32
+// accumulator, before any rounding.
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
+  static_assert(SB == 0 || (!POST && (CONV2 || SB == 1)), "stream-bf16 variants: conv1 SB=1, conv2 SB=1 (bf16 out) / SB=2 (fp32 out)");
+  constexpr bool XIN_BF = CONV2 || SB != 0;          // element type of the operand the producers read
+  constexpr bool OUT_BF = !CONV2 || SB == 1;         // epilogue writes bf16 (conv1 always; conv2 when the stream stays bf16)
   static_assert(!T || (BN == 128 && (MSUB == 2 || MSUB == 4)), "transposed mode: C = 128, 256- or 512-row tiles");
   static_assert(!POST || (T && !CONV2 && MSUB == 2), "post variant: transposed accumulator, fp32 input");
   // T with MSUB = 4 (k >= 7): 512-row tiles, i.e. TWO 128x256 MMAs per weight tile.  The k = 7 / 11 convs are
@@ -285,11 +293,18 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     auto fetchT = [&](int L, int off, int m0, int ch, float (&rv)[32]) {
       if (!CONV2) return;
       const int row = m0 + eg * RW + ch * 32;
-      const float* rp = a.res + (size_t)(off + row) * 128 + co;
       const int left = L - row;
+      if (SB) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + (size_t)(off + row) * 128 + co;
 #pragma unroll
-      for (int j = 0; j < 32; j++)
-        if (j < left) rv[j] = rp[j * 128];
+        for (int j = 0; j < 32; j++)
+          if (j < left) rv[j] = __bfloat162float(rp[j * 128]);
+      } else {
+        const float* rp = a.res + (size_t)(off + row) * 128 + co;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          if (j < left) rv[j] = rp[j * 128];
+      }
     };
     int ti = 0;
     TileCur cur;
@@ -328,7 +343,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty(buf)) : "memory");
         }
         TICK(1);
-        if (CONV2) {
+        if (CONV2 && !OUT_BF) {
           float* op = a.out_f32 + (size_t)(off + row) * 128 + co;
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -361,7 +376,9 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
           __nv_bfloat16* op = a.out_bf16 + (size_t)(off + row + odd) * 128 + (co & ~1);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            float2 o = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), bias2);
+            float2 o = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            if (CONV2) o = __fadd2_rn(o, make_float2(rv[j], rv[j + 1]));      // bf16 stream: x_next = y + x (+ bias below)
+            o = __fadd2_rn(o, bias2);
             if (!FULL) { o.x = j < left ? o.x : 0.f; o.y = j + 1 < left ? o.y : 0.f; }
             s2 = __fadd2_rn(s2, o);
             q2 = __ffma2_rn(o, o, q2);
@@ -421,11 +438,22 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       if (!CONV2) return;
       const int sub = e / NCH, ci = e & (NCH - 1);
       const int row = m0 + sub * 128 + tr;
-      const float* rp = a.res + (size_t)(off + row) * BN + ((2 * ci + eg) * 32 + c4);
       const int left = L - row;            // row i valid iff 16*i < left
+      if (SB) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(a.res) + (size_t)(off + row) * BN + ((2 * ci + eg) * 32 + c4);
 #pragma unroll
-      for (int i = 0; i < 8; i++)
-        if (16 * i < left) rv[i] = *reinterpret_cast<const float4*>(rp + i * RS);
+        for (int i = 0; i < 8; i++)
+          if (16 * i < left) {
+            const uint2 w = *reinterpret_cast<const uint2*>(rp + i * RS);
+            rv[i] = make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xFFFF0000u),
+                                __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xFFFF0000u));
+          }
+      } else {
+        const float* rp = a.res + (size_t)(off + row) * BN + ((2 * ci + eg) * 32 + c4);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (16 * i < left) rv[i] = *reinterpret_cast<const float4*>(rp + i * RS);
+      }
     };
     int ti = 0;
     TileCur cur;
@@ -492,7 +520,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
           if (!FULL) { o01.x = ok ? o01.x : 0.f; o01.y = ok ? o01.y : 0.f; o23.x = ok ? o23.x : 0.f; o23.y = ok ? o23.y : 0.f; }
           s01 = __fadd2_rn(s01, o01); s23 = __fadd2_rn(s23, o23);
           q01 = __ffma2_rn(o01, o01, q01); q23 = __ffma2_rn(o23, o23, q23);
-          if (!CONV2) {
+          if (OUT_BF) {
             uint2 pk;
             pk.x = pack_bf16(o01.x, o01.y); pk.y = pack_bf16(o23.x, o23.y);
             if (ok) *reinterpret_cast<uint2*>(a.out_bf16 + g0 + i * RS) = pk;
@@ -572,9 +600,9 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     const int ngc = (ra_used + GR - 1) / GR;                 // load groups per chunk
     float* const coef = reinterpret_cast<float*>(gbase + (coef_base - base));   // [3][BN]: al*sc, al*sh, 1/al
     const int F = (t_end - t_begin) * KCH * ngc;
-    using Raw = typename std::conditional<CONV2, uint4, float4>::type;
-    constexpr int RPP = CONV2 ? 1 : 2;      // raw vectors per pass (8 channels)
-    constexpr int XE = CONV2 ? 2 : 4;       // bytes per input element
+    using Raw = typename std::conditional<XIN_BF, uint4, float4>::type;
+    constexpr int RPP = XIN_BF ? 1 : 2;     // raw vectors per pass (8 channels)
+    constexpr int XE = XIN_BF ? 2 : 4;      // bytes per input element
     // this thread's byte offset inside an A slot, minus the row part: 16-byte chunk cg of row r sits at
     // chunk position cg ^ (r & 7); all rows this thread writes have r = rl (mod 8)
     const uint32_t sw = (uint32_t)rl * 128u + (uint32_t)((cg ^ (rl & 7)) << 4);
@@ -639,7 +667,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
         // straight-line: rows outside the item produce zeros through a select, only the store is predicated
         const uint32_t inmask = (unsigned)(row + p * kProdRows) < (unsigned)L ? 0xFFFFFFFFu : 0u;
         float2 xv[4];
-        if (CONV2) {
+        if (XIN_BF) {
           const uint4 raw = *reinterpret_cast<const uint4*>(&rb[p][0]);
           xv[0] = make_float2(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u));
           xv[1] = make_float2(__uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
@@ -703,16 +731,16 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   }
 }
 
-template <int BN, int MSUB, bool CONV2, bool T, bool POST = false>
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   using Cfg = ArbCfg<BN, MSUB, T>;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); });
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); });
   const int nsm = device_sm_count(dev);
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
-  arb_conv_kernel<BN, MSUB, CONV2, T, POST><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 }  // namespace
@@ -747,18 +775,34 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
     post_launch("post_conv", st);
     return;
   }
-  // two roles: fp32 in -> bf16 out (+statistics), or bf16 in + fp32 residual -> fp32 out
-  if (a.in_bf16 ? (!a.out_f32 || a.out_bf16 || !a.res) : (!a.out_bf16 || a.out_f32 || a.res || a.accumulate))
+  // roles: conv1 = (fp32 | bf16 stream) in -> bf16 out (+statistics); conv2 = bf16 in + (fp32 | bf16) residual ->
+  // fp32 out (block output / fp32 stream) or bf16 out (next x of a bf16 stream)
+  const bool conv2 = a.res != nullptr;
+  if (conv2 ? (!a.in_bf16 || (a.out_f32 != nullptr) == (a.out_bf16 != nullptr) || (a.out_bf16 && (!a.res_bf16 || a.accumulate)))
+            : (!a.out_bf16 || a.out_f32 || a.accumulate || a.res_bf16))
     throw ArgError("launch_arb_conv: unsupported input/output combination");
+  const int variant = arb_variant(a.C, a.ks);
+  const bool stream_bf = conv2 ? a.res_bf16 != 0 : a.in_bf16 != 0;
+  if (stream_bf && !(variant == 1 || a.C == 256)) throw ArgError("launch_arb_conv: the bf16 stream needs the default kernel variants");
   if (g_launch_stats) {
     const double fl = 2.0 * (double)a.sum_m * a.C * a.C * a.ks;
     g_launch_stats->conv_flops += fl;
     g_launch_stats->arb_flops += fl;
-    // every tensor once: conv1 reads fp32, writes bf16; conv2 reads bf16 + fp32 residual, writes fp32
-    g_launch_stats->arb_bytes += (double)a.sum_m * a.C * (a.in_bf16 ? 10.0 : 6.0);
+    // every tensor once: conv1 reads x (4 / 2 B), writes bf16; conv2 reads bf16 + the residual (4 / 2 B), writes 4 / 2 B
+    const double bytes = conv2 ? 2.0 + (a.res_bf16 ? 2.0 : 4.0) + (a.out_bf16 ? 2.0 : 4.0) : (a.in_bf16 ? 2.0 : 4.0) + 2.0;
+    g_launch_stats->arb_bytes += (double)a.sum_m * a.C * bytes;
   }
-  const int variant = arb_variant(a.C, a.ks);
-  if (variant == 2) {
+  if (stream_bf) {
+    if (a.C == 128) {
+      if (!conv2) launch_arb_t<128, 2, false, true, false, 1>(a, st);
+      else if (a.out_bf16) launch_arb_t<128, 2, true, true, false, 1>(a, st);
+      else launch_arb_t<128, 2, true, true, false, 2>(a, st);
+    } else {
+      if (!conv2) launch_arb_t<256, 1, false, false, false, 1>(a, st);
+      else if (a.out_bf16) launch_arb_t<256, 1, true, false, false, 1>(a, st);
+      else launch_arb_t<256, 1, true, false, false, 2>(a, st);
+    }
+  } else if (variant == 2) {
     if (a.in_bf16) launch_arb_t<128, 4, true, true>(a, st); else launch_arb_t<128, 4, false, true>(a, st);
   } else if (variant == 1) {
     if (a.in_bf16) launch_arb_t<128, 2, true, true>(a, st); else launch_arb_t<128, 2, false, true>(a, st);
@@ -768,7 +812,7 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
     if (a.in_bf16) launch_arb_t<256, 1, true, false>(a, st); else launch_arb_t<256, 1, false, false>(a, st);
   }
   if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
-    char nm[96]; snprintf(nm, sizeof nm, "arb_conv[c%d k%d d%d %s m%lld]", a.C, a.ks, a.dil, a.in_bf16 ? "bf16" : "f32", a.sum_m);
+    char nm[96]; snprintf(nm, sizeof nm, "arb_conv[c%d k%d d%d %s%s m%lld]", a.C, a.ks, a.dil, conv2 ? "conv2" : "conv1", stream_bf ? " sb" : "", a.sum_m);
     post_launch(nm, st);
   } else post_launch("arb_conv", st);
 }

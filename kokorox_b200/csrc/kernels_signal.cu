@@ -1,6 +1,7 @@
 // kernels_signal.cu -- HBM-bound kernels: instance-norm statistics, duration head + exact
 // integer length regulation (K4/K5), harmonic source (K9), STFT (K10), iSTFT head (K11).
 #include "kernels.h"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace kkx {
@@ -16,7 +17,8 @@ template <int VEC, bool ADD>
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, int ldx, int C,
                                                        float* __restrict__ part, int nchunk,
                                                        const int* off, const int* len,
-                                                       const float* __restrict__ y, float* __restrict__ out) {
+                                                       const float* __restrict__ y, float* __restrict__ out,
+                                                       __nv_bfloat16* __restrict__ out_b) {
   __shared__ float red[2][256 * VEC];
   const int b = blockIdx.y, ch = blockIdx.x;
   const int L = len[b];
@@ -42,7 +44,12 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
             const size_t o = (size_t)(p - x);
             const float4 w4 = *reinterpret_cast<const float4*>(y + o);
             v4.x += w4.x; v4.y += w4.y; v4.z += w4.z; v4.w += w4.w;
-            *reinterpret_cast<float4*>(out + o) = v4;
+            if (!out_b) *reinterpret_cast<float4*>(out + o) = v4;
+          }
+          if (out_b) {     // bf16 copy of the tensor the statistics describe (start of a bf16 residual stream); ldx == C
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v4.x, v4.y), hi2 = __floats2bfloat162_rn(v4.z, v4.w);
+            *reinterpret_cast<uint2*>(out_b + (size_t)(p - x)) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
           }
           s[0] += v4.x; q[0] = fmaf(v4.x, v4.x, q[0]);
           s[1 % VEC] += v4.y; q[1 % VEC] = fmaf(v4.y, v4.y, q[1 % VEC]);
@@ -70,24 +77,28 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
   }
 }
 void launch_colstats(const float* x, int ldx, int C, float* part, const int* off, const int* len,
-                     int B, int max_len, cudaStream_t st) {
+                     int B, int max_len, cudaStream_t st, void* out_bf16) {
   if (g_dry_run) return;
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
   dim3 g(nchunk, B);
-  if ((C % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0))
-    colstats_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr);
+  const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (out_bf16 && (!vec || ldx != C || (reinterpret_cast<uintptr_t>(out_bf16) & 7)))
+    throw ArgError("launch_colstats: the bf16 copy needs ldx == C, C % 4 == 0 and aligned tensors");
+  if (vec)
+    colstats_kernel<4, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr, static_cast<__nv_bfloat16*>(out_bf16));
   else
-    colstats_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr);
+    colstats_kernel<1, false><<<g, 256, 0, st>>>(x, ldx, C, part, nchunk, off, len, nullptr, nullptr, nullptr);
   post_launch("colstats", st);
 }
 void launch_add_rows_stats(const float* a, const float* b, float* out, int C, float* part, const int* off,
-                           const int* len, int B, int max_len, cudaStream_t st) {
+                           const int* len, int B, int max_len, cudaStream_t st, void* out_bf16) {
   if (g_dry_run) return;
-  if (C % 4 != 0 || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15))
+  if (C % 4 != 0 || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_bf16) & 7))
     throw ArgError("launch_add_rows_stats: needs C % 4 == 0 and 16-byte aligned tensors");
   const int nchunk = (max_len + kStatRows - 1) / kStatRows;
   dim3 g(nchunk, B);
-  colstats_kernel<4, true><<<g, 256, 0, st>>>(a, C, C, part, nchunk, off, len, b, out);
+  colstats_kernel<4, true><<<g, 256, 0, st>>>(a, C, C, part, nchunk, off, len, b, out, static_cast<__nv_bfloat16*>(out_bf16));
   post_launch("add_rows_stats", st);
 }
 

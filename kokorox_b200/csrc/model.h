@@ -140,6 +140,9 @@ struct Options {
   // split-precision GEMMs of the predictor path: 1 = fp16 hi/lo planes ("3xFP16": the same 22 significand bits as
   // 3xTF32 at half the operand bytes and twice the MMA rate), 0 = tf32 hi/lo planes
   int split_f16 = 1;
+  // generator res-blocks: keep the residual stream between the three iterations of a block in bf16 (10 instead of
+  // 16 bytes per row-channel and iteration; the k = 3 / k = 7 convs are HBM-bound)
+  int stream_bf16 = 0;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
@@ -258,7 +261,8 @@ class Model {
                  bool dry);
   void arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
            int sld, float* xw, float* t1, float* out, float oscale, bool accumulate,
-           const float* part_x = nullptr);
+           const float* part_x = nullptr, const void* x_bf16 = nullptr);
+  bool use_stream_bf16(int C, int k, int B) const;
   // first_off: row offset of item 0 (kGapRows for activations; 0 for the per-item style tables)
   Level make_level(const std::vector<int>& lens, Arena& A, int first_off = kGapRows);
   // copy `bytes` of host data to device memory through the pinned staging arena (true async copy on stream_)

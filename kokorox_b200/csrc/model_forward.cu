@@ -423,8 +423,13 @@ void Model::adain_blk(Run& r, Arena& A, const AdaBlkW& w, const float* x, int ld
 
 // AdaINResBlock1 (A.9): three (AdaIN -> Snake -> dilated conv -> AdaIN -> Snake -> conv) + residual
 // iterations.  Reads x, uses xw/t1 as work buffers, writes (or accumulates) oscale * result to out.
+bool Model::use_stream_bf16(int C, int k, int B) const {
+  return opt.precision == 1 && opt.stream_bf16 && arb_conv_supported(C, k, 5, B) && arb_tile_rows(C, k) == (C == 128 ? 256 : 128);
+}
+
 void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L, const float* sty,
-                int sld, float* xw, float* t1, float* out, float oscale, bool accumulate, const float* part_x) {
+                int sld, float* xw, float* t1, float* out, float oscale, bool accumulate, const float* part_x,
+                const void* x_bf16) {
   (void)r;
   cudaStream_t st = cur_;
   const int B = L.B, C = w.c, k = w.k;
@@ -446,14 +451,21 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
     base.tile_start = trows == 512 ? L.d_tiles512 : trows == 256 ? L.d_tiles256 : L.d_tiles128;
     base.total_tiles = trows == 512 ? L.ntiles512 : trows == 256 ? L.ntiles256 : L.ntiles128;
     base.scale = sc; base.shift = sh; base.nchunk = nch;
+    // bf16 residual stream: x0 arrives as bf16 (from the caller's add_rows_stats, or copied by the statistics pass
+    // below), x1 / x2 live in `xw` as bf16 and the block output leaves in fp32
+    const bool sb = use_stream_bf16(C, k, B);
+    void* xb0 = nullptr;
+    if (sb && !x_bf16) xb0 = A.alloc_bytes((size_t)L.rows * C * 2);
     // statistics of the block input: shared by the three res-blocks of a stage (computed once by the caller)
-    if (!part_x) launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st);
+    if (!part_x) launch_colstats(cur, C, C, part, L.d_off, L.d_len, B, L.max_len, st, xb0);
+    else if (sb && !x_bf16) throw ArgError("arb: a bf16 stream with caller-provided statistics needs the bf16 input too");
+    const void* curb = sb ? (x_bf16 ? x_bf16 : xb0) : nullptr;
     long long* tim = arb_timing_buf();
     for (int j = 0; j < 3; j++) {
       launch_adain_coef(j == 0 && part_x ? part_x : part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
       ArbConvArgs c1 = base;
       if (tim) c1.timing = tim + (C == 128 ? 0 : 64);
-      c1.x = cur; c1.in_bf16 = 0; c1.alpha = w.a1[j]; c1.tmB = w.t1[j].tmap; c1.dil = dil[j];
+      c1.x = sb ? curb : (const void*)cur; c1.in_bf16 = sb ? 1 : 0; c1.alpha = w.a1[j]; c1.tmB = w.t1[j].tmap; c1.dil = dil[j];
       c1.pad = dil[j] * (k - 1) / 2; c1.bias = w.b1[j];
       c1.out_bf16 = static_cast<__nv_bfloat16*>(abuf); c1.part = part;
       launch_arb_conv(c1, st);
@@ -462,8 +474,15 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
       ArbConvArgs c2 = base;
       if (tim) c2.timing = tim + (C == 128 ? 32 : 96);
       c2.x = abuf; c2.in_bf16 = 1; c2.alpha = w.a2[j]; c2.tmB = w.t2[j].tmap; c2.dil = 1; c2.pad = (k - 1) / 2;
-      c2.bias = w.b2[j]; c2.out_f32 = dst; c2.res = cur;
-      if (j == 2) { c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; } else c2.part = part;
+      c2.bias = w.b2[j];
+      if (sb) {
+        c2.res = static_cast<const float*>(curb); c2.res_bf16 = 1;
+        if (j == 2) { c2.out_f32 = out; c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; }
+        else { c2.out_bf16 = reinterpret_cast<__nv_bfloat16*>(xw); c2.part = part; curb = xw; }
+      } else {
+        c2.out_f32 = dst; c2.res = cur;
+        if (j == 2) { c2.oscale = oscale; c2.accumulate = accumulate ? 1 : 0; } else c2.part = part;
+      }
       launch_arb_conv(c2, st);
       cur = dst;
     }
@@ -726,14 +745,18 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   capture("gen.ups.0", x0, 256, 0, 256, G20, b0);
   {
     float* px = nullptr;
+    void* xb = nullptr;
     if (opt.precision == 1) {   // x0 += x_source and the statistics of the sum (input of three res-blocks) in one pass
       px = A.alloc<float>((size_t)B * ((G20.max_len + kStatRows - 1) / kStatRows) * 2 * 256);
-      launch_add_rows_stats(x0, xs0, x0, 256, px, G20.d_off, G20.d_len, B, G20.max_len, st);
+      // (bf16 residual stream: the sum is written once, as the bf16 x0 all three res-blocks read)
+      const bool sb0 = use_stream_bf16(256, 3, B) && use_stream_bf16(256, 7, B) && use_stream_bf16(256, 11, B);
+      xb = sb0 ? A.alloc_bytes((size_t)G20.rows * 256 * 2) : nullptr;
+      launch_add_rows_stats(x0, xs0, x0, 256, px, G20.d_off, G20.d_len, B, G20.max_len, st, xb);
     } else {
       launch_add_rows(x0, xs0, x0, 256, G20.d_off, G20.d_len, B, G20.max_len, st);
     }
     for (int j = 0; j < 3; j++)
-      arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0, px);
+      arb(r, A, W.res[j], x0, G20, sty_dec, W.sty_dec_n, w0, t0, acc0, 1.0f / 3.0f, j > 0, px, xb);
   }
   capture("gen.stage.0", acc0, 256, 0, 256, G20, b0);
 
@@ -762,14 +785,17 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   capture("gen.ups.1", x1, 128, 0, 128, G120, b0);
   {
     float* px = nullptr;
+    void* xb = nullptr;
     if (opt.precision == 1) {
       px = A.alloc<float>((size_t)B * ((G120.max_len + kStatRows - 1) / kStatRows) * 2 * 128);
-      launch_add_rows_stats(x1, xs1, x1, 128, px, G120.d_off, G120.d_len, B, G120.max_len, st);
+      const bool sb1 = use_stream_bf16(128, 3, B) && use_stream_bf16(128, 7, B) && use_stream_bf16(128, 11, B);
+      xb = sb1 ? A.alloc_bytes((size_t)G120.rows * 128 * 2) : nullptr;
+      launch_add_rows_stats(x1, xs1, x1, 128, px, G120.d_off, G120.d_len, B, G120.max_len, st, xb);
     } else {
       launch_add_rows(x1, xs1, x1, 128, G120.d_off, G120.d_len, B, G120.max_len, st);
     }
     for (int j = 0; j < 3; j++)
-      arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0, px);
+      arb(r, A, W.res[3 + j], x1, G120, sty_dec, W.sty_dec_n, w1, t1, acc1, 1.0f / 3.0f, j > 0, px, xb);
   }
   capture("gen.stage.1", acc1, 128, 0, 128, G120, b0);
 

@@ -305,10 +305,12 @@ static inline uint16_t host_bf16(float f) {
   return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
 }
 
-KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens, int C, int in_bf16,
-                              const float* scale, const float* shift, const float* alpha, const float* w,
-                              const float* bias, int ks, int dil, const float* res, float oscale,
-                              int accumulate, int want_bf16, float* out, float* sums, int desc_mode) {
+}  // extern "C"
+
+static int arb_conv_test(int device, const float* x, int B, const int* lens, int C, int in_bf16,
+                         const float* scale, const float* shift, const float* alpha, const float* w,
+                         const float* bias, int ks, int dil, const float* res, int res_bf16, float oscale,
+                         int accumulate, int want_bf16, float* out, float* sums, int desc_mode) {
   return run(device, [&] {
     if (!arb_conv_supported(C, ks, dil, B)) throw ArgError("kkx_test_arb_conv: unsupported shape");
     // ragged Level layout with NaN-filled gap rows: the kernel must never consume a gap row
@@ -336,7 +338,10 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
     for (size_t i = 0; i < hw.size(); i++) hw[i] = host_bf16(w[i]);
     DevBuf dx(in_bf16 ? (const void*)hxb.data() : (const void*)hx.data(), hx.size() * (in_bf16 ? 2 : 4));
     DevBuf dw(hw.data(), hw.size() * 2), db(bias, C * 4), dsc(scale, (size_t)B * C * 4), dsh(shift, (size_t)B * C * 4);
-    DevBuf dal(alpha, C * 4), dres(res ? hres.data() : nullptr, res ? hres.size() * 4 : 0);
+    std::vector<uint16_t> hresb;
+    if (res && res_bf16) { hresb.resize(hres.size()); for (size_t i = 0; i < hres.size(); i++) hresb[i] = host_bf16(hres[i]); }
+    DevBuf dal(alpha, C * 4), dres(res ? (res_bf16 ? (const void*)hresb.data() : (const void*)hres.data()) : nullptr,
+                                   res ? hres.size() * (res_bf16 ? 2 : 4) : 0);
     DevBuf dout(hout.data(), hout.size() * 4), doutb(nullptr, hout.size() * 2);
     KKX_CUDA(cudaMemset(doutb.p, 0xFF, hout.size() * 2));
     const int nchunk = (maxL + 127) / 128;
@@ -352,7 +357,7 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
     a.sum_m = sumL; a.bias = db.as<float>();
     a.out_bf16 = want_bf16 ? doutb.as<__nv_bfloat16>() : nullptr;
     a.out_f32 = want_bf16 ? nullptr : dout.as<float>();
-    a.res = res ? dres.as<float>() : nullptr; a.oscale = oscale; a.accumulate = accumulate;
+    a.res = res ? dres.as<float>() : nullptr; a.res_bf16 = res ? res_bf16 : 0; a.oscale = oscale; a.accumulate = accumulate;
     a.part = sums ? dpart.as<float>() : nullptr; a.nchunk = nchunk; (void)desc_mode;
     launch_arb_conv(a, 0);
     KKX_CUDA(cudaDeviceSynchronize());
@@ -380,6 +385,24 @@ KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens
           }
     }
   });
+}
+
+extern "C" {
+
+KKX_API int kkx_test_arb_conv(int device, const float* x, int B, const int* lens, int C, int in_bf16,
+                              const float* scale, const float* shift, const float* alpha, const float* w,
+                              const float* bias, int ks, int dil, const float* res, float oscale,
+                              int accumulate, int want_bf16, float* out, float* sums, int desc_mode) {
+  return arb_conv_test(device, x, B, lens, C, in_bf16, scale, shift, alpha, w, bias, ks, dil, res, 0, oscale, accumulate,
+                       want_bf16, out, sums, desc_mode);
+}
+
+KKX_API int kkx_test_arb_conv_stream(int device, const float* x, int B, const int* lens, int C, const float* scale,
+                                     const float* shift, const float* alpha, const float* w, const float* bias, int ks,
+                                     int dil, const float* res, float oscale, int accumulate, int want_bf16, float* out,
+                                     float* sums) {
+  return arb_conv_test(device, x, B, lens, C, 1, scale, shift, alpha, w, bias, ks, dil, res, 1, oscale, accumulate,
+                       want_bf16, out, sums, 0);
 }
 
 }  // extern "C"

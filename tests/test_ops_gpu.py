@@ -368,3 +368,28 @@ def test_fused_arb_conv(lib, Cc, k, dil, lens, variant):
         np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-3)         # fast-sin + bf16 re-rounding flips
     assert not np.isnan(out).any()
     np.testing.assert_allclose(sums, rs, rtol=1e-3, atol=1e-2 * float(np.abs(rs).max()) * 1e-2)
+
+
+@pytest.mark.parametrize("Cc,k,dil,lens", [(128, 3, 1, [300]), (128, 11, 5, [700, 13, 257]), (128, 7, 3, [256, 512, 1]),
+                                            (256, 7, 1, [333]), (256, 11, 5, [129, 640]), (256, 3, 3, [128, 127])])
+@pytest.mark.parametrize("variant", ["conv1_bf16_in", "conv2_bf16_stream", "conv2_bf16_res_to_f32"])
+def test_fused_arb_conv_bf16_residual_stream(lib, Cc, k, dil, lens, variant):
+    # the res-block's residual stream kept in bf16 between iterations (kernels_arb.cu, SB variants): conv1 reads bf16 x;
+    # conv2 adds the bf16 residual and writes the next bf16 x, or (last iteration) the fp32 block output.  Statistics
+    # come from the fp32 accumulator either way.
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from arb_probe import run_case_stream
+    lib.kkx_test_arb_conv_stream.restype = C.c_int
+    if variant == "conv1_bf16_in":
+        out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 0, 1, 1.0, 0)
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=1e-3)
+    elif variant == "conv2_bf16_stream":
+        out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 1, 1, 1.0, 0)
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=1e-3)
+    else:
+        out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 1, 0, 1.0 / 3.0, 1)
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-3)
+    assert not np.isnan(out).any()
+    np.testing.assert_allclose(sums, rs, rtol=1e-3, atol=1e-2 * float(np.abs(rs).max()) * 1e-2)

@@ -394,6 +394,39 @@ def test_latency_path_graphs_and_forks_do_not_change_results(model):
         model.set_option("precision", 0)
 
 
+@pytest.mark.parametrize("n_tokens,seed", [(50, 0), (510, 1)])
+def test_bf16_residual_stream_parity(model, oracle, n_tokens, seed):
+    """"stream_bf16": the generator res-blocks keep their residual stream in bf16 between iterations.  Same bars as the
+    tensor-core configuration: every stage and the teacher-forced waveform within rel-L2 3e-2 / max-abs 0.15 of the
+    oracle, and a ragged batch still equals its single calls bit for bit."""
+    ids, style = synth_case(n_tokens, seed, 100 + seed)
+    noise = make_noise(12 * len(ids) if n_tokens > 60 else 50 * len(ids))
+    ref = oracle.forward(ids, style, 1.0, noise=noise, stages=True)
+    model.set_option("precision", 1)
+    model.set_option("stream_bf16", 1)
+    try:
+        audio, dur = run_cuda(model, ids, style, 1.0, noise, stages=True,
+                              teacher={"pred_dur": ref["pred_dur"], "F0": ref["stages"]["F0"], "N": ref["stages"]["N"]})
+        assert np.array_equal(dur, ref["pred_dur"])
+        worst = {s: rel_l2(ref["stages"][s], model.debug_stage(s)) for s in STAGES}
+        print("stream_bf16 stage errors:", {k: round(v, 5) for k, v in worst.items() if k.startswith("gen") or k == "conv_post"},
+              "audio", rel_l2(ref["audio"], audio))
+        bad = {k: v for k, v in worst.items() if not v < 3e-2}
+        assert not bad, bad
+        assert rel_l2(ref["audio"], audio) < 3e-2
+        assert np.abs(ref["audio"] - audio).max() < 0.15
+        if n_tokens == 50:
+            model.debug_enable(False)
+            model.set_noise(None)
+            cases = [synth_case(n, s, 300 + s) for n, s in ((40, 1), (200, 2), (90, 3))]
+            singles = [model.infer_batch([c[0]], [c[1]], [1.0])[0].copy() for c in cases]
+            outs = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], [1.0] * 3)
+            assert all(np.array_equal(a, b) for a, b in zip(outs, singles))
+    finally:
+        model.set_option("stream_bf16", 0)
+        model.set_option("precision", 0)
+
+
 @pytest.mark.parametrize("opts", [{"attention_umma": 1}, {"split_f16": 1}, {"attention_umma": 1, "split_f16": 1}])
 @pytest.mark.parametrize("n_tokens,seed,speed", [(50, 0, 1.0), (300, 4, 1.3), (510, 1, 1.0), (510, 1000, 1.0)])
 def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, seed, speed):

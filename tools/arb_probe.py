@@ -77,6 +77,39 @@ def run_case(lib, Cc, k, dil, lens, in_bf16, want_bf16, use_res, oscale, accumul
     return out, ref, sums, ref_sums
 
 
+def run_case_stream(lib, Cc, k, dil, lens, use_res, want_bf16, oscale, accumulate, seed=0):
+    """The bf16-residual-stream variants (kkx_test_arb_conv_stream): x and the residual are bf16; conv1 (no residual)
+    writes bf16, conv2 writes the next bf16 x (want_bf16) or the fp32 block output."""
+    rng = np.random.default_rng(seed)
+    n = int(sum(lens))
+    B = len(lens)
+    x = rng.standard_normal((n, Cc)).astype(np.float32)
+    sc = (1.0 + 0.3 * rng.standard_normal((B, Cc))).astype(np.float32)
+    sh = (0.3 * rng.standard_normal((B, Cc))).astype(np.float32)
+    al = (0.5 + rng.random(Cc)).astype(np.float32)
+    w = (rng.standard_normal((Cc, k, Cc)) / np.sqrt(Cc * k)).astype(np.float32)
+    bias = rng.standard_normal(Cc).astype(np.float32)
+    res = rng.standard_normal((n, Cc)).astype(np.float32) if use_res else None
+    prev = rng.standard_normal((n, Cc)).astype(np.float32)
+    out = prev.copy()
+    sums = np.zeros((B, 2, Cc), np.float32)
+    fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+    li = np.asarray(lens, np.int32)
+    rc = lib.kkx_test_arb_conv_stream(0, fp(x), B, li.ctypes.data_as(C.POINTER(C.c_int)), Cc, fp(sc), fp(sh), fp(al),
+                                      fp(w), fp(bias), k, dil, fp(res), C.c_float(oscale), int(accumulate),
+                                      int(want_bf16), fp(out), fp(sums))
+    assert rc == 0, lib.kkx_test_last_error()
+    y = reference(x, lens, sc, sh, al, w, bias, k, dil, None if res is None else bf16_round(res), 1)
+    ref = y.copy() if want_bf16 else y * oscale + (prev if accumulate else 0.0)
+    ref_sums = np.zeros((B, 2, Cc))
+    o = 0
+    for b, L in enumerate(lens):
+        ref_sums[b, 0] = y[o:o + L].sum(0)
+        ref_sums[b, 1] = (y[o:o + L] ** 2).sum(0)
+        o += L
+    return out, ref, sums, ref_sums
+
+
 def main():
     from kokorox_b200.onn import load_library
     lib = load_library()
