@@ -270,13 +270,20 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         mbar_wait(bfull_bar(j), (uint32_t)(ch / 3) & 1u);
         tc_fence_after();
         TCT(0);
+        if (BN == 64) {      // one TMEM round trip per chain (the latency path: small problems run 64-wide tiles)
+          uint32_t v[64];
+          tmem_ld64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j)), v);
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-          if (TC_DBG(a, 4)) continue;                   // perf experiment: chains are not drained
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
+          for (int e = 0; e < 64; e++) racc[MODE ? (e < BN ? e : 0) : 0] += __uint_as_float(v[e]);
+        } else {
 #pragma unroll
-          for (int e = 0; e < 32; e++) racc[(MODE ? c : 0) + (MODE ? e : 0)] += __uint_as_float(v[e]);
+          for (int c = 0; c < BN; c += 32) {
+            if (TC_DBG(a, 4)) continue;                   // perf experiment: chains are not drained
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
+#pragma unroll
+            for (int e = 0; e < 32; e++) racc[(MODE ? c : 0) + (MODE ? e : 0)] += __uint_as_float(v[e]);
+          }
         }
         tc_fence_before();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
@@ -560,7 +567,8 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
 // neither overlapped with anything at one CTA per SM.  Here the epilogue pulls the small-terms accumulator
 // into registers right after the last chain, hands all of TMEM back, and finishes (smem transpose, bias,
 // activation, residual, stores) from registers while the next tile's operands stream in and its MMAs run.
-__global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__ CUtensorMap tmA,
+constexpr int kGemm32pThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps
+__global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB,
                                                          const __grid_constant__ CUtensorMap tmA2,
                                                          const __grid_constant__ CUtensorMap tmB2,
@@ -570,12 +578,10 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
   const int KE = f16 ? 64 : 32;                // K elements per 128-byte span
   const int cs = f16 ? 0 : 1;                  // log2(stages per hi*hi chain): a chain is 64 K-elements either way
   constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-  constexpr int PITCH = 36;
-  constexpr uint32_t STG_BYTES = 128 * PITCH * 4;
+  constexpr int NEPI = (kGemm32pThreads - 64) / 32;     // epilogue warps: 8 = two column halves x four TMEM lane quadrants
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg_base = base + STAGES * STAGE_BYTES;
-  const uint32_t bar_base = stg_base + STG_BYTES;       // full[3], empty[3], bfull[3], bempty[3], sfull, sfree
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;       // full[3], empty[3], bfull[3], bempty[3], sfull, sfree
   const uint32_t tmem_slot = bar_base + 14 * 8;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
@@ -596,8 +602,8 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 4); }
-    mbar_init(sfull_bar, 1); mbar_init(sfree_bar, 4);
+    for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), NEPI); }
+    mbar_init(sfull_bar, 1); mbar_init(sfree_bar, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -686,29 +692,33 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
       }
     }
   } else {
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+    // ---- epilogue: 8 warps.  Warp w owns TMEM lane quadrant q = w & 3 (its 32 accumulator rows) and column half
+    // hh = (w - 2) >> 2 (64 of the tile's 128 columns); a thread holds ONE row x 64 columns in registers.
+    // Round 1 ran this with 4 warps x 128 columns and four sequential 32-column tcgen05.ld + wait round trips per
+    // chain: at ~3 000 cycles per drained chain the epilogue warps -- not the tensor pipe, not L2 -- set the pace of
+    // every large split-precision GEMM (the per-chain time was the same for K = 768 and K = 2048, for tf32 and for
+    // fp16 planes).  Two column halves and one 64-column load per chain cut the drain to one TMEM round trip.
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int et = q * 32 + lane;           // accumulator row held by this thread
-    const int t128 = threadIdx.x - 64;
-    const int c4 = (t128 & 7) << 2;
-    float* const buf = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
     int gc = 0, ti = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
       int b, m0, n0;
       decode(t, b, m0, n0);
       const int mlen = a.m_len[b];
-      float racc[BN];
+      float racc[64];
 #pragma unroll
-      for (int e = 0; e < BN; e++) racc[e] = 0.f;
+      for (int e = 0; e < 64; e++) racc[e] = 0.f;
       for (int ch = 0; ch < nchains; ch++) {
         const int G = gc + ch, j = G % 3;
         mbar_wait(bfull_bar(j), (uint32_t)(G / 3) & 1u);
         tc_fence_after();
+        {
+          uint32_t v[64];
+          tmem_ld64(tq + (uint32_t)(BN * (1 + j)), v);
 #pragma unroll
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN * (1 + j) + c), v);
-#pragma unroll
-          for (int e = 0; e < 32; e++) racc[c + e] += __uint_as_float(v[e]);
+          for (int e = 0; e < 64; e++) racc[e] += __uint_as_float(v[e]);
         }
         tc_fence_before();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
@@ -716,67 +726,52 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
       gc += nchains;
       mbar_wait(sfull_bar, (uint32_t)ti & 1u);
       tc_fence_after();
+      {
+        uint32_t v[64];
+        tmem_ld64(tq, v);
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-#pragma unroll
-        for (int e = 0; e < 32; e++) racc[c + e] = __uint_as_float(v[e]) + racc[c + e];   // same order as the single-tile kernel
+        for (int e = 0; e < 64; e++) racc[e] = __uint_as_float(v[e]) + racc[e];   // same order as the single-tile kernel
       }
       tc_fence_before();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sfree_bar) : "memory");   // TMEM is free again
 
-      // ---- the rest runs from registers while the next tile's pipeline is already going
-      const int out_off = a.out_off[b];
-      const int res_off = a.res ? a.res_off[b] : 0;
+      // ---- the rest runs from registers while the next tile's pipeline is already going: bias, activation,
+      // residual, scale and the stores of this thread's row segment (64 consecutive floats = two full 128-byte lines)
+      const int mm = m0 + et;
+      if (mm < mlen) {
+        const int orow = mm * a.ors + a.oro;
+        float* const orow_p = a.out + ((size_t)(a.out_off[b] + orow) * a.ldo + a.ocol);
+        const float* const rrow_p = a.res ? a.res + ((size_t)(a.res_off[b] + (orow >> a.res_shift)) * a.ldr + a.rcol) : nullptr;
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        const int n = n0 + c + c4;
-        const bool vec = a.vec4 && (n + 3 < a.Co);
-        float4 rv[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {           // residual operand of this chunk (in flight across the two barriers)
-          const int mm = m0 + (t128 >> 3) + 16 * i;
-          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.res && n < a.Co && mm < mlen) {
-            const int orow = mm * a.ors + a.oro;
-            const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
-            if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
-            else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer drained by the previous chunk
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(buf + et * PITCH + j) = make_float4(racc[c + j], racc[c + j + 1], racc[c + j + 2], racc[c + j + 3]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (n < a.Co) {
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 64; c += 4) {
+          const int n = n0 + hh * 64 + c;
+          if (n >= a.Co) break;
+          const bool vec = a.vec4 && (n + 3 < a.Co);
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rv = bb;
           if (a.bias) {
             if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
             else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
           }
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int row = (t128 >> 3) + 16 * i;
-            const int mm = m0 + row;
-            if (mm >= mlen) continue;
-            float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
-            o.x = fmaf(o.x, a.wscale, bb.x); o.y = fmaf(o.y, a.wscale, bb.y); o.z = fmaf(o.z, a.wscale, bb.z); o.w = fmaf(o.w, a.wscale, bb.w);
-            if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
-            o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
-            o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-            float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
-            if (vec) {
-              if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
-              *reinterpret_cast<float4*>(op) = o;
-            } else {
-              if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
-              op[0] = o.x;
-              if (n + 1 < a.Co) op[1] = o.y;
-              if (n + 2 < a.Co) op[2] = o.z;
-              if (n + 3 < a.Co) op[3] = o.w;
-            }
+          if (rrow_p) {
+            if (vec) rv = *reinterpret_cast<const float4*>(rrow_p + n);
+            else { rv.x = rrow_p[n]; if (n + 1 < a.Co) rv.y = rrow_p[n + 1]; if (n + 2 < a.Co) rv.z = rrow_p[n + 2]; if (n + 3 < a.Co) rv.w = rrow_p[n + 3]; }
+          }
+          float4 o;
+          o.x = fmaf(racc[c], a.wscale, bb.x); o.y = fmaf(racc[c + 1], a.wscale, bb.y);
+          o.z = fmaf(racc[c + 2], a.wscale, bb.z); o.w = fmaf(racc[c + 3], a.wscale, bb.w);
+          if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+          o.x = (o.x + rv.x) * a.oscale; o.y = (o.y + rv.y) * a.oscale;
+          o.z = (o.z + rv.z) * a.oscale; o.w = (o.w + rv.w) * a.oscale;
+          float* op = orow_p + n;
+          if (vec) {
+            if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+            *reinterpret_cast<float4*>(op) = o;
+          } else {
+            if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+            op[0] = o.x;
+            if (n + 1 < a.Co) op[1] = o.y;
+            if (n + 2 < a.Co) op[2] = o.z;
+            if (n + 3 < a.Co) op[3] = o.w;
           }
         }
       }
@@ -791,7 +786,7 @@ __global__ void __launch_bounds__(192, 1) gemm32p_kernel(const __grid_constant__
 }
 
 static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
-  constexpr int smem = 3 * 4 * 128 * 128 + 128 * 36 * 4 + 14 * 8 + 16 + 1024;
+  constexpr int smem = 3 * 4 * 128 * 128 + 14 * 8 + 16 + 1024;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -806,7 +801,7 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
   if (gm < 8) gm = 8;
   if (gm > a.ntiles_m) gm = a.ntiles_m;
   b.group_m = (int)gm;
-  gemm32p_kernel<<<grid, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB),
+  gemm32p_kernel<<<grid, kGemm32pThreads, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB),
                                           *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2), b);
 }
 

@@ -384,10 +384,10 @@ def test_fused_arb_conv_bf16_residual_stream(lib, Cc, k, dil, lens, variant):
     lib.kkx_test_arb_conv_stream.restype = C.c_int
     if variant == "conv1_bf16_in":
         out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 0, 1, 1.0, 0)
-        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=1e-3)
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=3e-3)
     elif variant == "conv2_bf16_stream":
         out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 1, 1, 1.0, 0)
-        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=1e-3)
+        np.testing.assert_allclose(out, ref, rtol=2 ** -7, atol=3e-3)
     else:
         out, ref, sums, rs = run_case_stream(lib, Cc, k, dil, lens, 1, 0, 1.0 / 3.0, 1)
         np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-3)
