@@ -257,13 +257,10 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       tc_fence_after();
       float sc[64];
       {
-        uint32_t v[32];
-        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s, v);
+        uint32_t v[64];
+        tmem_ld64(tq + kColS0 + 64u * (uint32_t)s, v);      // one TMEM round trip for the 64 keys of the tile
 #pragma unroll
-        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(v[e]);
-        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s + 32u, v);
-#pragma unroll
-        for (int e = 0; e < 32; e++) sc[32 + e] = __uint_as_float(v[e]);
+        for (int e = 0; e < 64; e++) sc[e] = __uint_as_float(v[e]);
       }
       tc_fence_before();
       __syncwarp();
@@ -306,13 +303,10 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       mbar_wait(o_full, (uint32_t)j & 1u);
       tc_fence_after();
       {
-        uint32_t v[32];
-        tmem_ld32(tq + kColO, v);
+        uint32_t v[64];
+        tmem_ld64(tq + kColO, v);
 #pragma unroll
-        for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]);
-        tmem_ld32(tq + kColO + 32u, v);
-#pragma unroll
-        for (int e = 0; e < 32; e++) o[32 + e] += __uint_as_float(v[e]);
+        for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]);
       }
       tc_fence_before();
     }

@@ -638,13 +638,16 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       int g = 0;
+      TCT_DECL(2);
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int b, m0, n0;
         decode(t, b, m0, n0);
         const int row0 = a.in_off[b] + m0 - a.pad;
         for (int it = 0; it < num_k; it++, g++) {
           const int s = g % STAGES;
+          TCT(1);
           mbar_wait(empty_bar(s), (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          TCT(0);
           const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
           const uint32_t sa = base + s * STAGE_BYTES;
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
@@ -654,18 +657,23 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
           tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
         }
       }
+      TCT_FLUSH(0, 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = f16 ? umma_idesc_f16(128, BN) : umma_idesc_tf32(128, BN);
       int g = 0, gc = 0, ti = 0;
+      TCT_DECL(4);
       for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
         // the small-terms accumulator of the previous tile must have been pulled into registers
+        TCT(2);
         if (ti > 0) { mbar_wait(sfree_bar, (uint32_t)(ti - 1) & 1u); tc_fence_after(); }
+        TCT(3);
         for (int it = 0; it < num_k; it++, g++) {
           const int s = g % STAGES;
           mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
           tc_fence_after();
+          TCT(0);
           const uint32_t sa = base + s * STAGE_BYTES;
           const int G = gc + (it >> cs), j = G % 3;
           const bool chain_start = (it & cs) == 0;
@@ -673,6 +681,7 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
             mbar_wait(bempty_bar(j), (uint32_t)(G / 3 - 1) & 1u);
             tc_fence_after();
           }
+          TCT(1);
           const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + A_BYTES);
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES), bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES);
           const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
@@ -686,10 +695,12 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
           }
           if ((it & cs) == cs || it == num_k - 1) umma_commit(bfull_bar(j));  // chain complete
           umma_commit(empty_bar(s));
+          TCT(2);
         }
         umma_commit(sfull_bar);
         gc += nchains;
       }
+      TCT_FLUSH(4, 4);
     }
   } else {
     // ---- epilogue: 8 warps.  Warp w owns TMEM lane quadrant q = w & 3 (its 32 accumulator rows) and column half
@@ -703,6 +714,10 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
     const int et = q * 32 + lane;           // accumulator row held by this thread
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
     int gc = 0, ti = 0;
+#ifdef KKX_TC_TIMING
+    long long tct_acc[4] = {0}; long long tct_last = clock64();
+    const bool tct_on = a.timing && blockIdx.x == gridDim.x - 2 && threadIdx.x == 64;
+#endif
     for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
       int b, m0, n0;
       decode(t, b, m0, n0);
@@ -714,6 +729,7 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
         const int G = gc + ch, j = G % 3;
         mbar_wait(bfull_bar(j), (uint32_t)(G / 3) & 1u);
         tc_fence_after();
+        TCT(0);
         {
           uint32_t v[64];
           tmem_ld64(tq + (uint32_t)(BN * (1 + j)), v);
@@ -722,10 +738,12 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
         }
         tc_fence_before();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bempty_bar(j)) : "memory");
+        TCT(1);
       }
       gc += nchains;
       mbar_wait(sfull_bar, (uint32_t)ti & 1u);
       tc_fence_after();
+      TCT(2);
       {
         uint32_t v[64];
         tmem_ld64(tq, v);
@@ -775,7 +793,9 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
           }
         }
       }
+      TCT(3);
     }
+    TCT_FLUSH(8, 4);
   }
   tc_fence_before();
   __syncthreads();

@@ -427,12 +427,13 @@ def test_bf16_residual_stream_parity(model, oracle, n_tokens, seed):
         model.set_option("precision", 0)
 
 
-@pytest.mark.parametrize("opts", [{"attention_umma": 1}, {"split_f16": 1}, {"attention_umma": 1, "split_f16": 1}])
+@pytest.mark.parametrize("opts", [{"attention_umma": 0, "split_f16": 0}, {"attention_umma": 1, "split_f16": 0},
+                                  {"attention_umma": 0, "split_f16": 1}, {"attention_umma": 1, "split_f16": 1}])
 @pytest.mark.parametrize("n_tokens,seed,speed", [(50, 0, 1.0), (300, 4, 1.3), (510, 1, 1.0), (510, 1000, 1.0)])
 def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, seed, speed):
-    """The tcgen05 attention kernel and the split-FP16 GEMMs replace fp32-grade kernels on the path that decides
-    the integer durations: every seeded case must still match the oracle bit for bit, with dur_float as close as the
-    round-1 kernels get it."""
+    """The tcgen05 attention kernel and the split-FP16 GEMMs (both on by default) replace fp32-grade kernels on the
+    path that decides the integer durations: every combination with their round-1 counterparts (mma.sync attention,
+    split-TF32 planes) must match the oracle bit for bit, with dur_float as close as the round-1 kernels get it."""
     ids, style = synth_case(n_tokens, seed, 100 + seed)
     noise = make_noise(12 * len(ids) if n_tokens > 60 else 50 * len(ids))
     ref = oracle.forward(ids, style, speed, noise=noise, stages=True)
@@ -449,7 +450,7 @@ def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, 
         assert audio.shape == ref["audio"].shape and np.isfinite(audio).all()
     finally:
         for k in opts:
-            model.set_option(k, 0)
+            model.set_option(k, 1)          # the library defaults
         model.set_option("precision", 0)
 
 
