@@ -18,8 +18,10 @@
 //                  operand of the second MMA; then the O tile is drained and folded into the fp32 running output with
 //                  the flash rescaling (each 64-key chain is added in fp32 RN -- the tensor core truncates per
 //                  accumulate, the same chain splitting the split-TF32 GEMMs use).
-//   S_{j+1} is issued before the softmax of tile j starts, so the tensor pipe works under the exponentials.
-// TMEM columns: S0 0..63, S1 64..127, P_hi 128..191, P_lo 192..255, O 256..319.
+//   S, P and O are all double-buffered in TMEM: S_{j+1} is issued before the softmax of tile j starts and O_j = P_j V_j
+//   runs while the softmax warps are already on tile j+1 (they fold O_j in after writing P_{j+1}; the order of the
+//   floating-point operations is unchanged), so the tensor pipe works under the exponentials.
+// TMEM columns: S0 0..63, S1 64..127, P_hi/P_lo buffer 0 128..255, buffer 1 256..383, O0 384..447, O1 448..511.
 #include "kernels.h"
 #include <cuda.h>
 #include "tc_ptx.cuh"
@@ -119,7 +121,7 @@ constexpr uint32_t kQPlane = 2 * 128 * 128;            // one Q plane: two K-chu
 constexpr uint32_t kTilePlane = 2 * 64 * 128;          // one K / V^T plane of a 64-key tile: two chunks of [64 x 32] = 16 KB
 constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 64 KB
 constexpr int kAttnSmem = 2 * kQPlane + 2 * kStage + 16 * 8 + 16 + 1024;
-constexpr uint32_t kColS0 = 0, kColPH = 128, kColPL = 192, kColO = 256;
+constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 384;   // P buffer pb: hi at kColP + 128 pb, lo 64 columns further
 
 __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
                                                            const __grid_constant__ CUtensorMap tmQl,
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
   auto sfull_bar = [&](int i) { return bar_base + (5 + i) * 8; };
   auto sfree_bar = [&](int i) { return bar_base + (7 + i) * 8; };
-  const uint32_t p_full = bar_base + 9 * 8, o_full = bar_base + 10 * 8;
+  auto pfull_bar = [&](int i) { return bar_base + (9 + i) * 8; };
+  auto ofull_bar = [&](int i) { return bar_base + (11 + i) * 8; };
+  auto ofree_bar = [&](int i) { return bar_base + (13 + i) * 8; };
   const uint32_t tmem_slot = bar_base + 16 * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -155,8 +159,8 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     for (int s = 0; s < 2; s++) {
       mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
       mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 4);
+      mbar_init(pfull_bar(s), 4); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 4);
     }
-    mbar_init(p_full, 4); mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -224,11 +228,16 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       issue_s(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
-        const int s = j & 1;
-        mbar_wait(p_full, (uint32_t)j & 1u);           // P_j is in TMEM (and O_{j-1} has been drained)
+        const int s = j & 1;                           // stage, P buffer and O buffer of tile j
+        mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);   // P_j is in TMEM
         tc_fence_after();
+        if (j >= 2) {                                  // O_{j-2} has been read out of this O buffer
+          mbar_wait(ofree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
+          tc_fence_after();
+        }
         const uint32_t sa = st0 + s * kStage;
-        const uint32_t t_o = tmem_base + kColO, t_ph = tmem_base + kColPH, t_pl = tmem_base + kColPL;
+        const uint32_t t_o = tmem_base + kColO + 64u * (uint32_t)s;
+        const uint32_t t_ph = tmem_base + kColP + 128u * (uint32_t)s, t_pl = t_ph + 64u;
 #pragma unroll
         for (int kk = 0; kk < 8; kk++) {               // 8 keys per UMMA
           const int c = kk >> 2;
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           umma_tf32_ts(t_o, t_ph + 8u * kk, vl, idesc, 1u);
           umma_tf32_ts(t_o, t_ph + 8u * kk, vh, idesc, 1u);
         }
-        umma_commit(o_full);
+        umma_commit(ofull_bar(s));
         umma_commit(empty_bar(s));                     // K_j and V^T_j are consumed
       }
     }
@@ -280,8 +289,8 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       for (int e = 0; e < 64; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
       l = l * corr + ps;
       m = mn;
-      // P_j -> TMEM as tf32 hi / lo (A operand of the second MMA).  MMA_{j-1} has finished reading the previous P:
-      // this thread waited for o_full(j-1) below.
+      // P_j -> TMEM as tf32 hi / lo (A operand of the second MMA).  MMA_{j-2} has finished reading this P buffer:
+      // this thread waited for its O tile in the previous iteration.
 #pragma unroll
       for (int half = 0; half < 2; half++) {
         uint32_t ph[32], pl[32];
@@ -291,24 +300,39 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           ph[e] = to_tf32(p);
           pl[e] = to_tf32(p - __uint_as_float(ph[e]));
         }
-        tmem_st32(tq + kColPH + 32u * half, ph);
-        tmem_st32(tq + kColPL + 32u * half, pl);
+        tmem_st32(tq + kColP + 128u * (uint32_t)s + 32u * half, ph);
+        tmem_st32(tq + kColP + 128u * (uint32_t)s + 64u + 32u * half, pl);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-#pragma unroll
-      for (int e = 0; e < 64; e++) o[e] *= corr;       // under the second MMA
-      mbar_wait(o_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      {
+      if (lane == 0) mbar_arrive(pfull_bar(s));
+      // fold in O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new running maximum: the same
+      // operations in the same order as add-after-rescale inside one iteration
+      if (j >= 1) {
+        const int so = (j - 1) & 1;
+        mbar_wait(ofull_bar(so), ((uint32_t)((j - 1) >> 1)) & 1u);
+        tc_fence_after();
         uint32_t v[64];
-        tmem_ld64(tq + kColO, v);
+        tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ofree_bar(so));
 #pragma unroll
         for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]);
       }
+#pragma unroll
+      for (int e = 0; e < 64; e++) o[e] *= corr;
+    }
+    {
+      const int so = (nt - 1) & 1;
+      mbar_wait(ofull_bar(so), ((uint32_t)((nt - 1) >> 1)) & 1u);
+      tc_fence_after();
+      uint32_t v[64];
+      tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
       tc_fence_before();
+#pragma unroll
+      for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]);
     }
     if (q0 + row < N) {
       const float inv = 1.0f / l;
