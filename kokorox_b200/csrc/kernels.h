@@ -60,6 +60,13 @@ struct TcConvArgs {
   long long* timing = nullptr;   // diagnostics (-DKKX_TC_TIMING builds)
   const int* tile_start = nullptr; int ntiles_m = 0;   // persistent split-TF32 GEMM: prefix sum of ceil(m_len/128) per item
   int group_m = 1;               // (set by the launcher) m-tiles per L2-resident group
+  // Phase-fused ConvTranspose1d (bf16 path, MODE 0): `nphase` two-tap phase convs in ONE launch.  The weights of the
+  // phases are stacked along the weight map's rows (phase p at rows [p*Co, (p+1)*Co)), each phase has its own tap shift
+  // and output row offset, and the phase is the FASTEST grid dimension, so the CTAs that read one activation tile run
+  // together and the re-reads are served from L2 instead of HBM (the phases used to be 10 + 6 separate launches).
+  int nphase = 1;
+  int phase_pad[10] = {0};
+  int phase_oro[10] = {0};
   int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);

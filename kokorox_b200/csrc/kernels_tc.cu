@@ -133,15 +133,23 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 
   const int b = blockIdx.z;
   const int mlen = a.m_len[b];
-  const int m0 = blockIdx.x * 128;
+  // phase-fused launches put (phase, n-tile) on grid.x and the m-tile on grid.y
+  const bool fused = MODE == 0 && CL == 1 && a.nphase > 1;
+  const int bx = fused ? blockIdx.y : blockIdx.x, by = fused ? blockIdx.x : blockIdx.y;
+  const int m0 = bx * 128;
   if (CL == 1) {
     if (m0 >= mlen) return;  // CTA-uniform
   } else {
     if ((int)(blockIdx.x / CL) * CL * 128 >= mlen) return;  // cluster-uniform: a CTA past the end still feeds its peers
   }
+  const int ntn = (a.Co + BN - 1) / BN;
+  const int ph = fused ? by / ntn : 0;
+  const int c_pad = fused ? a.phase_pad[ph] : a.pad;
+  const int c_oro = fused ? a.phase_oro[ph] : a.oro;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-  const int n0 = blockIdx.y * BN;
+  const int n0 = (fused ? by - ph * ntn : by) * BN;
+  const int wrow0 = ph * a.Co + n0;          // row of this tile in the (phase-stacked) weight map
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.Cpad / KE;
   const int num_k = a.ks * kchunks;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 
   if (warp == 0) {
     if (lane == 0) {
-      const int row0 = a.in_off[b] + m0 - a.pad;
+      const int row0 = a.in_off[b] + m0 - c_pad;
       TCT_DECL(2);
       for (int it = 0; it < num_k; it++) {
         const int s = it % STAGES;
@@ -187,8 +195,8 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
         if (MODE && !skipA2) tma_load_2d(sa + A_BYTES, &tmA2, c0, row0 + tap * a.dil, full_bar(s));
         if (CL == 1) {
-          tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
-          if (MODE && !skipB2) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, n0, full_bar(s));
+          tma_load_2d(sa + PLANES * A_BYTES, &tmB, tap * a.Cpad + c0, wrow0, full_bar(s));
+          if (MODE && !skipB2) tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &tmB2, tap * a.Cpad + c0, wrow0, full_bar(s));
         } else {
           // this CTA's 1/CL of the weight rows (tmB / tmB2 have BN/CL-row boxes), multicast to the whole cluster
           constexpr uint32_t SUB = (BN / CL) * 128;
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
         const int mm = m0 + (t >> 3) + 16 * i;
         rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.res && n < a.Co && mm < mlen) {
-          const int orow = mm * a.ors + a.oro;
+          const int orow = mm * a.ors + c_oro;
           const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
           if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
           else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
           if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
           o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
           o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-          float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
+          float* op = a.out + ((size_t)(out_off + mm * a.ors + c_oro) * a.ldo + a.ocol + n);
           if (vec) {
             if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
             *reinterpret_cast<float4*>(op) = o;
@@ -847,6 +855,7 @@ static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
   once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, MODE, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
   const unsigned gx = (unsigned)(((a.max_m + 127) / 128 + CL - 1) / CL * CL);
   dim3 g(gx, (a.Co + BN - 1) / BN, a.B);
+  if (MODE == 0 && CL == 1 && a.nphase > 1) g = dim3((unsigned)(a.nphase * ((a.Co + BN - 1) / BN)), gx, a.B);
   const CUtensorMap* mA = reinterpret_cast<const CUtensorMap*>(a.tmA);
   const CUtensorMap* mB = reinterpret_cast<const CUtensorMap*>(CL > 1 ? a.tmB_c : a.tmB);
   const CUtensorMap* mA2 = reinterpret_cast<const CUtensorMap*>(a.tmA2 ? a.tmA2 : a.tmA);
@@ -875,7 +884,8 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   a.debug = 0;
 #endif
   a.vec4 = ((a.ldo | a.ocol) % 4 == 0) && (!a.res || ((a.ldr | a.rcol) % 4 == 0)) ? 1 : 0;
-  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks;
+  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)a.sum_m * a.Co * a.Ci * a.ks * (a.nphase > 1 ? a.nphase : 1);
+  if (a.nphase > 1 && (a.tf32 || a.nphase > 10 || a.Co % tc_box_n(a.Co) != 0)) throw ArgError("launch_conv_tc: unsupported phase-fused shape");
   if (a.tf32) {
     // split-TF32: 4 operand planes per stage (64 KB at BN=128) -> 3 stages, one CTA per SM
     static const bool bn64 = env_flag("KKX_TC_BN64", false);
@@ -911,7 +921,7 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   // opt-in (KKX_TC_MULTI=1) as the base for the halo-reuse kernel.
   static const bool multi_ok = env_flag("KKX_TC_MULTI", false);
   const long long tiles = (a.sum_m + 127) / 128 * ((a.Co + 127) / 128);
-  if (multi_ok && tiles >= 4 * 2 * 148 && a.Co > 64) {
+  if (multi_ok && a.nphase <= 1 && tiles >= 4 * 2 * 148 && a.Co > 64) {
     if (a.Co > 128) launch_tc_multi<256, 2, 4>(a, st);   // 96 + 37 KB smem, 512 TMEM cols: 1 CTA/SM
     else launch_tc_multi<128, 2, 4>(a, st);              // 64 + 37 KB smem, 256 TMEM cols: 2 CTAs/SM
     if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
@@ -926,7 +936,7 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   else if (a.Co > 64) launch_tc<128, 2, 0>(a, st);   // 65 KB smem -> three CTAs per SM
   else launch_tc<64, 4, 0>(a, st);
   if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {
-    char nm[96]; snprintf(nm, sizeof nm, "conv_tc[ci%d co%d k%d m%lld]", a.Ci, a.Co, a.ks, a.sum_m);
+    char nm[96]; snprintf(nm, sizeof nm, "conv_tc[ci%d co%d k%d%s m%lld]", a.Ci, a.Co, a.ks, a.nphase > 1 ? " phases" : "", a.sum_m);
     post_launch(nm, st);
   } else post_launch("conv_tc", st);
 }

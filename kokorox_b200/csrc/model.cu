@@ -494,9 +494,21 @@ void WeightSet::load(const WeightFile& wf) {
   const int rk[3] = {3, 7, 11};
   for (int i = 0; i < 2; i++)
     for (int j = 0; j < 3; j++) W.res[i * 3 + j] = ARB(G + "resblocks." + std::to_string(i * 3 + j), i == 0 ? 256 : 128, rk[j]);
-  auto UPS = [&](const std::string& n, int Ci, int Co, int k, int s, std::vector<float*>& out, std::vector<TcW>& tout) {
+  auto UPS = [&](const std::string& n, int Ci, int Co, int k, int s, std::vector<float*>& out, std::vector<TcW>& tout,
+                 TcW& tall) {
     const HostTensor& t = wf.get(n);
     expect(t, {Ci, Co, k}, n);
+    {   // all phases stacked along the output-channel axis: row p*Co + o = phase p, channel o
+      std::vector<float> tw((size_t)s * Co * 2 * Ci);
+      for (int r = 0; r < s; r++)
+        for (int o = 0; o < Co; o++)
+          for (int j = 0; j < 2; j++)
+            for (int c = 0; c < Ci; c++)
+              tw[(((size_t)r * Co + o) * 2 + j) * Ci + c] = t.data[((size_t)c * Co + o) * k + r + j * s];
+      tall = make_tc(tw, s * Co, 2, Ci);
+      tall.Co = Co;                                                    // per-phase output channels
+      make_tmap_bf16(tall.tmap, tall.w, (long long)2 * tall.Cpad, (long long)s * Co, (long long)2 * tall.Cpad, tc_box_n(Co));
+    }
     for (int r = 0; r < s; r++) {
       std::vector<float> tw((size_t)Co * 2 * Ci);
       for (int o = 0; o < Co; o++)
@@ -512,8 +524,8 @@ void WeightSet::load(const WeightFile& wf) {
       out.push_back(up(ph));
     }
   };
-  UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0, W.tups0); W.ups0_b = U(G + "ups.0.bias");
-  UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1, W.tups1); W.ups1_b = U(G + "ups.1.bias");
+  UPS(G + "ups.0.weight", 512, 256, 20, 10, W.ups0, W.tups0, W.tups0_all); W.ups0_b = U(G + "ups.0.bias");
+  UPS(G + "ups.1.weight", 256, 128, 12, 6, W.ups1, W.tups1, W.tups1_all); W.ups1_b = U(G + "ups.1.bias");
   W.post_w = CW(G + "conv_post.weight", 22, 128, 7); W.post_b = U(G + "conv_post.bias");
   W.t_post = make_tc(convCoKsCi(wf, G + "conv_post.weight", 22, 128, 7), 22, 7, 128);
   {

@@ -111,6 +111,7 @@ struct Weights {
   ArbW nres[2], res[6];
   std::vector<float*> ups0, ups1;  // per-phase [2][Ci][Co]
   std::vector<TcW> tups0, tups1;   // per-phase bf16 [Co][2][Ci]
+  TcW tups0_all, tups1_all;        // the phases stacked along Co (phase-fused launch): [s*Co][2][Ci]
   TcW t_post, t_nc0, t_nc1, t_asr; // conv_post, noise_convs (nc0 as an im2col GEMM, K = 12*22), asr_res
   float *ups0_b, *ups1_b, *post_w, *post_b;
   TcW t_post_arb; float* post_b128 = nullptr;   // conv_post zero-padded to 128 output channels for the fused kernel
@@ -143,6 +144,8 @@ struct Options {
   // generator res-blocks: keep the residual stream between the three iterations of a block in bf16 (10 instead of
   // 16 bytes per row-channel and iteration; the k = 3 / k = 7 convs are HBM-bound)
   int stream_bf16 = 0;
+  // ConvTranspose1d up-sampling: all phases in one launch (L2 serves the re-reads of the input) instead of s launches
+  int fuse_phases = 0;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32

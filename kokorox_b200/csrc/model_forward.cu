@@ -727,6 +727,19 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     launch_apply_bf16(y, 512, 512, nullptr, nullptr, ACT_LRELU, 0.1f, nullptr, ybf, 512, FR2.rows, FR2.d_off,
                       FR2.d_len, B, FR2.max_len, st);
   }
+  if (opt.precision == 1 && opt.fuse_phases && !dry) {
+    // all 10 phases in one launch: phase p reads rows (m + q0 - tap), writes output row 10 m + q0*10 + p - 5
+    alignas(64) unsigned char tmA[128];
+    make_tmap_bf16(tmA, ybf, W.tups0_all.Cpad, FR2.rows, W.tups0_all.Cpad, 128);
+    TcConvArgs a;
+    a.tmA = tmA; a.tmB = W.tups0_all.tmap;
+    a.Cpad = W.tups0_all.Cpad; a.Ci = W.tups0_all.Ci; a.Co = 256; a.ks = 2; a.dil = -1;
+    a.in_off = FR2.d_off; a.m_len = FR2.d_len; a.max_m = FR2.max_len; a.B = B; a.sum_m = FR2.sum_len;
+    a.bias = W.ups0_b; a.out = x0; a.ldo = 256; a.ocol = 0; a.out_off = G20.d_off; a.ors = 10;
+    a.nphase = 10;
+    for (int ph = 0; ph < 10; ph++) { const int q0 = ph < 5 ? 1 : 0; a.phase_pad[ph] = -q0; a.phase_oro[ph] = q0 * 10 + ph - 5; }
+    launch_conv_tc(a, st);
+  } else
   for (int ph = 0; ph < 10; ph++) {  // ConvTranspose1d(512,256,k20,s10,p5) as 10 two-tap phase convs
     const int q0 = ph < 5 ? 1 : 0;
     if (opt.precision == 1) {
@@ -767,6 +780,18 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     launch_apply_bf16(acc0, 256, 256, nullptr, nullptr, ACT_LRELU, 0.1f, nullptr, abf, 256, G20.rows, G20.d_off,
                       G20.d_len, B, G20.max_len, st);
   }
+  if (opt.precision == 1 && opt.fuse_phases && !dry) {
+    alignas(64) unsigned char tmA[128];
+    make_tmap_bf16(tmA, abf, W.tups1_all.Cpad, G20.rows, W.tups1_all.Cpad, 128);
+    TcConvArgs a;
+    a.tmA = tmA; a.tmB = W.tups1_all.tmap;
+    a.Cpad = W.tups1_all.Cpad; a.Ci = W.tups1_all.Ci; a.Co = 128; a.ks = 2; a.dil = -1;
+    a.in_off = G20.d_off; a.m_len = G20.d_len; a.max_m = G20.max_len; a.B = B; a.sum_m = G20.sum_len;
+    a.bias = W.ups1_b; a.out = x1; a.ldo = 128; a.ocol = 0; a.out_off = G120.d_off; a.ors = 6;
+    a.nphase = 6;
+    for (int ph = 0; ph < 6; ph++) { const int q0 = ph < 3 ? 1 : 0; a.phase_pad[ph] = -q0; a.phase_oro[ph] = q0 * 6 + ph - 3 + 1; }
+    launch_conv_tc(a, st);
+  } else
   for (int ph = 0; ph < 6; ph++) {  // ConvTranspose1d(256,128,k12,s6,p3) + ReflectionPad1d((1,0))
     const int q0 = ph < 3 ? 1 : 0;
     if (opt.precision == 1) {

@@ -454,6 +454,27 @@ def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, 
         model.set_option("precision", 0)
 
 
+def test_phase_fused_upsampling_is_bit_identical(model):
+    """"fuse_phases": the 10 + 6 ConvTranspose1d phase convs of the generator as one launch each (phase = fastest grid
+    dimension, weights stacked along the map's rows).  Same kernel, same accumulation order -> the same bits."""
+    model.set_noise(None)
+    model.debug_enable(False)
+    model.set_option("precision", 1)
+    try:
+        cases = [synth_case(n, 60 + n, 61 + n) for n in (33, 140, 77, 510)]
+        speeds = [1.0, 0.9, 1.2, 1.0]
+        model.set_option("fuse_phases", 0)
+        ref = [o.copy() for o in model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds)]
+        model.set_option("fuse_phases", 1)
+        got = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds)
+        assert all(np.array_equal(x, y) for x, y in zip(ref, got))
+        one = model.infer_one(cases[1][0], cases[1][1], speeds[1])
+        assert np.array_equal(one, ref[1])
+    finally:
+        model.set_option("fuse_phases", 0)
+        model.set_option("precision", 0)
+
+
 def test_call_sequence_and_limits(model):
     """the staged API cannot be driven into a stale state, speed and frame counts are bounded."""
     from kokorox_b200.onn import KkxError
