@@ -353,6 +353,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the synthetic checkpoints are written once (rank 0), not raced for by every rank
+    if rank == 0:
+        ensure_weights()
+        if args.config in ("all", "4"):
+            ensure_second_weights()
+    barrier()
+
     if args.config == "3":
         if rank == 0:
             c3 = run_cfg3(local_rank)

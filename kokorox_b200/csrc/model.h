@@ -145,7 +145,7 @@ struct Options {
   // 16 bytes per row-channel and iteration; the k = 3 / k = 7 convs are HBM-bound)
   int stream_bf16 = 0;
   // ConvTranspose1d up-sampling: all phases in one launch (L2 serves the re-reads of the input) instead of s launches
-  int fuse_phases = 0;
+  int fuse_phases = 1;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
