@@ -388,7 +388,10 @@ def main():
     m = B200Koko.new(ensure_weights(), device=local_rank)
     default_precision = m.get_stat("precision")          # what an unconfigured session runs (stated)
     m.set_option("precision", args.precision)
-    toks, styles, speeds = synth_batch(args.batch, args.tokens, rank)
+    # weak scaling: every rank runs the SAME 64 utterances (per-GPU work fixed; rank-dependent seeds made the ranks'
+    # frame counts differ by ~5 %, which showed up as a scaling loss that was really load imbalance -- VERDICT r1).
+    # The mixed, sharded workload is cfg4.
+    toks, styles, speeds = synth_batch(args.batch, args.tokens, 0)
     sum_n = sum(len(t) for t in toks)
 
     # ---------------- value: inputs resident in HBM, device-timed
@@ -541,7 +544,7 @@ def main():
                        "audio_s_per_step": audio_all, "frame_groups_per_step": groups,
                        "weights": "random-init seed 1234 (no checkpoint, no network)",
                        "precision": args.precision, "library_default_precision": default_precision,
-                       "parallelism": f"request-sharded x{world}, no collective on the data path",
+                       "parallelism": f"one process + one session per GPU x{world}, every rank the same batch, no collective on the data path",
                        "l2": "working set per step (GBs of activations) is larger than the 126 MB L2; no flush needed"},
             "clocks": clocks,
             "e2e": {"value": e2e_audio_all / e2e_step_s, "unit": "audio-s/s", "h2d_bytes_per_step": h2d * world,
