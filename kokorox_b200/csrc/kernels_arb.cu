@@ -214,30 +214,9 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       TileCur cur;
       cur.init(s_ts, B, t_begin);
       const bool resident = KCH * ks <= NB;
-      // L2 prefetch of the activation rows (and the residual rows of conv2) kPf tiles ahead.  ncu on the k = 3 convs:
-      // every unit below 30 %, ~7 warps per issue slot stalled on the long scoreboard -- the producers' and the
-      // epilogue's global loads wait out the full loaded HBM latency with one load group in flight.  A tile's rows
-      // are one contiguous range, so this thread (paced by the tile loop) asks the copy engine to pull them into L2
-      // ahead of time: the loads then see L2 latency, and no registers or shared memory are held meanwhile.
-      constexpr int kPf = 3;
-      TileCur pf = cur;
-      auto prefetch_tile = [&](const TileCur& c) {
-        const int r0 = c.mt * MT;
-        const int rows = min(MT, s_len[c.b] - r0);
-        if (rows <= 0) return;
-        const size_t e0 = (size_t)(s_off[c.b] + r0) * BN;
-        const uint32_t xb = (uint32_t)rows * BN * (XIN_BF ? 2u : 4u);
-        bulk_prefetch_l2(reinterpret_cast<const char*>(a.x) + e0 * (XIN_BF ? 2 : 4), xb);
-        if (CONV2) {
-          const uint32_t rb = (uint32_t)rows * BN * (SB ? 2u : 4u);
-          bulk_prefetch_l2(reinterpret_cast<const char*>(a.res) + e0 * (SB ? 2 : 4), rb);
-        }
-      };
-      for (int i = 0; i < kPf && t_begin + i < t_end; i++) { prefetch_tile(pf); pf.next(s_ts); }
       TIM_DECL(4);
 #pragma unroll 1
       for (int tile = t_begin; tile < t_end; tile++, ti++) {
-        if (tile + kPf < t_end) { prefetch_tile(pf); pf.next(s_ts); }
         const int rem = s_len[cur.b] - cur.mt * MT;         // rows of this item left from the tile start
         (void)rem;
         const int buf = NBUF == 2 ? (ti & 1) : 0;

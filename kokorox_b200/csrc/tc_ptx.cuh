@@ -36,11 +36,6 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
-// L2 prefetch of a contiguous global range (bytes: multiple of 16, address 16-byte aligned): one instruction, no
-// registers or shared memory held while the lines travel from HBM
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
