@@ -123,6 +123,9 @@ struct ArbConvArgs {
                                                        // stream has in_bf16 = 1, conv2 writes out_bf16 (next x) or out_f32
   float* part = nullptr; int nchunk = 0;               // column sums of (y + res): [B][nchunk][2][C], 128-row chunks
   long long* timing = nullptr;                         // diagnostics (-DKKX_ARB_TIMING builds): per-role phase cycle counters
+  int debug = 0;                                       // diagnostics (-DKKX_EXPERIMENTS builds, wrong results): 1 = producers skip
+                                                       // the global loads, 2 = epilogue skips the global stores / residual loads,
+                                                       // 4 = producers skip the transform, 8 = MMA warp issues nothing but commits
   // "post" variant (generator conv_post): operand transform = LeakyReLU(slope) instead of AdaIN + Snake, weights
   // zero-padded to C output channels, fp32 output [rows, ldo] of the first `cout` channels, no statistics
   int post = 0, cout = 0, ldo = 0; float slope = 0.f;

@@ -43,6 +43,13 @@ namespace {
 #define TIM_FLUSH(base, n)
 #endif
 
+// perf-experiment switches (skip loads / stores / math: wrong results, timing only) exist only in -DKKX_EXPERIMENTS builds
+#ifdef KKX_EXPERIMENTS
+#define ARB_DBG(a, bit) ((a).debug & (bit))
+#else
+#define ARB_DBG(a, bit) (0)
+#endif
+
 constexpr int kArbThreads = 512;   // 16 warps: TMA, MMA, 8 epilogue, 6 operand producers (128 regs/thread)
 constexpr int kArbMaxB = 512;
 
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
                 const uint32_t td = tmem_base + (uint32_t)(buf * 256 + s2 * 256);
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                  umma_bf16(td, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idescT, (c | tap | k) ? 1u : 0u);
+                  if (!ARB_DBG(a, 8)) umma_bf16(td, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idescT, (c | tap | k) ? 1u : 0u);
               }
             } else {
 #pragma unroll
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     constexpr int RW = MSUB * 128 / (NEW / 4);   // rows per epilogue warp (row group eg of the tile)
     constexpr int NCHK = RW / 32;            // 32-row chunks per warp and tile (4 or 8)
     auto fetchT = [&](int L, int off, int m0, int ch, float (&rv)[32]) {
-      if (!CONV2) return;
+      if (!CONV2 || ARB_DBG(a, 2)) return;
       const int row = m0 + eg * RW + ch * 32;
       const int left = L - row;
       if (SB) {
@@ -303,7 +310,10 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
         const float* rp = a.res + (size_t)(off + row) * 128 + co;
 #pragma unroll
         for (int j = 0; j < 32; j++)
-          if (j < left) rv[j] = rp[j * 128];
+          if (j < left) {
+            if (ARB_DBG(a, 32)) asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(rv[j]) : "l"(rp + j * 128));
+            else rv[j] = rp[j * 128];
+          }
       }
     };
     int ti = 0;
@@ -335,7 +345,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       auto bodyT = [&](int ch, float (&rv)[32], auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
         const int row = m0 + eg * RW + ch * 32;
-        const int left = L - row;
+        const int left = ARB_DBG(a, 2) ? 0 : L - row;
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + eg * RW + ch * 32), v);
         if (ch == NCHK - 1) {      // last TMEM read of this tile by this warp
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
           s2 = make_float2(0.f, 0.f); q2 = s2;
         }
       };
-      if (L - m0 >= MT) {
+      if (L - m0 >= MT && !ARB_DBG(a, 2)) {
 #pragma unroll
         for (int ch = 0; ch < NCHK; ch += 2) { bodyT(ch, rv0, std::true_type{}); bodyT(ch + 1, rv1, std::true_type{}); }
       } else {
@@ -623,10 +633,16 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       const char* xp = reinterpret_cast<const char*>(a.x) + ((size_t)(s_off[lc.b] + row) * BN + (l_c * 64 + cg * 8)) * XE;
 #pragma unroll
       for (int p = 0; p < GP; p++) {
-        if ((unsigned)(row + p * kProdRows) < (unsigned)L && rloc + p * kProdRows < ra_used) {
+        if ((unsigned)(row + p * kProdRows) < (unsigned)L && rloc + p * kProdRows < ra_used && !ARB_DBG(a, 1)) {
 #pragma unroll
-          for (int v = 0; v < RPP; v++)
-            rb[p][v] = *reinterpret_cast<const Raw*>(xp + (size_t)p * kProdRows * BN * XE + v * 16);
+          for (int v = 0; v < RPP; v++) {
+            const char* gp = xp + (size_t)p * kProdRows * BN * XE + v * 16;
+            if (ARB_DBG(a, 16)) {
+              uint4 t;
+              asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(gp));
+              rb[p][v] = *reinterpret_cast<Raw*>(&t);
+            } else rb[p][v] = *reinterpret_cast<const Raw*>(gp);
+          }
         }
       }
       if (++l_g == ngc) { l_g = 0; if (++l_c == KCH) { l_c = 0; lc.next(s_ts); } }
@@ -687,6 +703,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
             pw[e] = pack_bf16(fmaxf(xv[e].x, lx.x), fmaxf(xv[e].y, lx.y)) & inmask;
             continue;
           }
+          if (ARB_DBG(a, 4)) { pw[e] = pack_bf16(xv[e].x, xv[e].y) & inmask; continue; }
           const float2 u = __ffma2_rn(xv[e], cA[e], cB[e]);
           const float2 sn = make_float2(__sinf(u.x), __sinf(u.y));
           const float2 y = __fmul2_rn(__ffma2_rn(sn, sn, u), cI[e]);
@@ -782,6 +799,10 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
             : (!a.out_bf16 || a.out_f32 || a.accumulate || a.res_bf16))
     throw ArgError("launch_arb_conv: unsupported input/output combination");
   const int variant = arb_variant(a.C, a.ks);
+#ifdef KKX_EXPERIMENTS
+  static const int dbg = env_int("KKX_ARB_DBG", 0);
+  if (dbg && !a.debug) { ArbConvArgs d = a; d.debug = dbg; launch_arb_conv(d, st); return; }
+#endif
   const bool stream_bf = conv2 ? a.res_bf16 != 0 : a.in_bf16 != 0;
   if (stream_bf && !(variant == 1 || a.C == 256)) throw ArgError("launch_arb_conv: the bf16 stream needs the default kernel variants");
   if (g_launch_stats) {

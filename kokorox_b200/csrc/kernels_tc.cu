@@ -589,7 +589,9 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
   constexpr int NEPI = (kGemm32pThreads - 64) / 32;     // epilogue warps: 8 = two column halves x four TMEM lane quadrants
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;       // full[3], empty[3], bfull[3], bempty[3], sfull, sfree
+  const uint32_t scr_base = base + STAGES * STAGE_BYTES;       // 8 epilogue warps x 4 KB transpose scratch
+  float* const scr_f = reinterpret_cast<float*>(smem_raw + (scr_base - smem_u32(smem_raw)));
+  const uint32_t bar_base = scr_base + 8 * 4096;               // full[3], empty[3], bfull[3], bempty[3], sfull, sfree
   const uint32_t tmem_slot = bar_base + 14 * 8;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
@@ -761,44 +763,69 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
       tc_fence_before();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sfree_bar) : "memory");   // TMEM is free again
 
-      // ---- the rest runs from registers while the next tile's pipeline is already going: bias, activation,
-      // residual, scale and the stores of this thread's row segment (64 consecutive floats = two full 128-byte lines)
-      const int mm = m0 + et;
-      if (mm < mlen) {
-        const int orow = mm * a.ors + a.oro;
-        float* const orow_p = a.out + ((size_t)(a.out_off[b] + orow) * a.ldo + a.ocol);
-        const float* const rrow_p = a.res ? a.res + ((size_t)(a.res_off[b] + (orow >> a.res_shift)) * a.ldr + a.rcol) : nullptr;
+      // ---- the rest runs while the next tile's pipeline is already going: bias, activation, residual, scale, stores.
+      // A thread holds one accumulator ROW (64 columns); storing that directly makes every warp-wide store touch 32
+      // different rows (32 x 16 B) and kept the drain warps away from the accumulator ring for ~12 k cycles per tile
+      // (the MMA warp then waits on the ring).  Each warp transposes its 32 x 32 block through a private 4 KB smem
+      // scratch (16-byte chunks XOR-swizzled by row: conflict-free both ways, __syncwarp only): afterwards 8 lanes
+      // cover one 128-byte row segment, so residual loads and stores are full-line and the bias is one float4 per block.
+      {
+        float* const scr = scr_f + (warp - 2) * 1024;
+        const int rq = lane >> 3, cq = lane & 7;
+        const int out_row0 = a.out_off[b];
+        const int res_row0 = a.res ? a.res_off[b] : 0;
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          const int n = n0 + hh * 64 + c;
-          if (n >= a.Co) break;
-          const bool vec = a.vec4 && (n + 3 < a.Co);
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rv = bb;
-          if (a.bias) {
-            if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
-            else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+        for (int blk = 0; blk < 2; blk++) {
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            *reinterpret_cast<float4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_float4(racc[blk * 32 + 4 * j], racc[blk * 32 + 4 * j + 1], racc[blk * 32 + 4 * j + 2], racc[blk * 32 + 4 * j + 3]);
+          __syncwarp();
+          const int n = n0 + hh * 64 + blk * 32 + cq * 4;
+          if (n < a.Co) {
+            const bool vec = a.vec4 && (n + 3 < a.Co);
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias) {
+              if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+              else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+            }
+            float4 rv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int mm = m0 + q * 32 + rq + 4 * i;
+              if (a.res && mm < mlen) {
+                const float* rp = a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n;
+                if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+                else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int r = rq + 4 * i;
+              const int mm = m0 + q * 32 + r;
+              if (mm >= mlen) continue;
+              const float4 v = *reinterpret_cast<const float4*>(scr + r * 32 + ((cq ^ (r & 7)) << 2));
+              float4 o;
+              o.x = fmaf(v.x, a.wscale, bb.x); o.y = fmaf(v.y, a.wscale, bb.y);
+              o.z = fmaf(v.z, a.wscale, bb.z); o.w = fmaf(v.w, a.wscale, bb.w);
+              if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+              o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+              o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+              float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
+              if (vec) {
+                if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+                *reinterpret_cast<float4*>(op) = o;
+              } else {
+                if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+                op[0] = o.x;
+                if (n + 1 < a.Co) op[1] = o.y;
+                if (n + 2 < a.Co) op[2] = o.z;
+                if (n + 3 < a.Co) op[3] = o.w;
+              }
+            }
           }
-          if (rrow_p) {
-            if (vec) rv = *reinterpret_cast<const float4*>(rrow_p + n);
-            else { rv.x = rrow_p[n]; if (n + 1 < a.Co) rv.y = rrow_p[n + 1]; if (n + 2 < a.Co) rv.z = rrow_p[n + 2]; if (n + 3 < a.Co) rv.w = rrow_p[n + 3]; }
-          }
-          float4 o;
-          o.x = fmaf(racc[c], a.wscale, bb.x); o.y = fmaf(racc[c + 1], a.wscale, bb.y);
-          o.z = fmaf(racc[c + 2], a.wscale, bb.z); o.w = fmaf(racc[c + 3], a.wscale, bb.w);
-          if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
-          o.x = (o.x + rv.x) * a.oscale; o.y = (o.y + rv.y) * a.oscale;
-          o.z = (o.z + rv.z) * a.oscale; o.w = (o.w + rv.w) * a.oscale;
-          float* op = orow_p + n;
-          if (vec) {
-            if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
-            *reinterpret_cast<float4*>(op) = o;
-          } else {
-            if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
-            op[0] = o.x;
-            if (n + 1 < a.Co) op[1] = o.y;
-            if (n + 2 < a.Co) op[2] = o.z;
-            if (n + 3 < a.Co) op[3] = o.w;
-          }
+          __syncwarp();
         }
       }
       TCT(3);
@@ -814,7 +841,7 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
 }
 
 static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
-  constexpr int smem = 3 * 4 * 128 * 128 + 14 * 8 + 16 + 1024;
+  constexpr int smem = 3 * 4 * 128 * 128 + 8 * 4096 + 14 * 8 + 16 + 1024;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);

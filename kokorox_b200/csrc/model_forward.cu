@@ -461,6 +461,8 @@ void Model::arb(Run& r, Arena& A, const ArbW& w, const float* x, const Level& L,
     else if (sb && !x_bf16) throw ArgError("arb: a bf16 stream with caller-provided statistics needs the bf16 input too");
     const void* curb = sb ? (x_bf16 ? x_bf16 : xb0) : nullptr;
     long long* tim = arb_timing_buf();
+    static const int tim_ks = env_int("KKX_ARB_TIMING_KS", 0);   // diagnostics: restrict the role counters to one kernel size
+    if (tim_ks && tim_ks != k) tim = nullptr;
     for (int j = 0; j < 3; j++) {
       launch_adain_coef(j == 0 && part_x ? part_x : part, C, L.max_len, L.d_len, sty, sld, w.s1[j], 1e-5f, sc, sh, B, st);
       ArbConvArgs c1 = base;

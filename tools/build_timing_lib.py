@@ -13,7 +13,11 @@ from kokorox_b200 import build as b  # noqa: E402
 OUT = os.path.join(b.OUT_DIR, "libkkx_timing.so")
 OBJ = "/tmp/kkx_timing_objs"
 os.makedirs(OBJ, exist_ok=True)
-flags = b.FLAGS + ["-DKKX_TC_TIMING", "-DKKX_EXPERIMENTS"]
+flags = b.FLAGS + ["-DKKX_EXPERIMENTS"] + (["-DKKX_TC_TIMING", "-DKKX_ARB_TIMING"] if os.environ.get("KKX_NO_COUNTERS") != "1" else [])
+if os.environ.get("KKX_NO_COUNTERS") == "1":
+    OUT = os.path.join(b.OUT_DIR, "libkkx_exp.so")          # experiment switches only (no cycle counters in the kernels)
+    OBJ = "/tmp/kkx_exp_objs"
+    os.makedirs(OBJ, exist_ok=True)
 
 
 def cc(src):
