@@ -70,6 +70,12 @@ KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const 
  * the epilogue); problems with >= 148 output tiles take the persistent kernel, smaller ones the single-tile kernel. */
 KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const float* w, const float* bias,
                                 int Co, int ks, int dil, int pad, int eact, float* out);
+/* The same with the kernel chosen by the caller -- 1 = single-tile, 2 = persistent, 3 = persistent CTA-pair
+ * (tcgen05 cta_group::2) -- plus an optional residual [L, Co] and output scale: out = (conv + bias (+act) + res) * oscale.
+ * The three kernels accumulate every output element in the same order; tests compare them bit for bit. */
+KKX_API int kkx_test_conv_f16x3_k(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                                  int Co, int ks, int dil, int pad, int eact, int kernel, const float* res, float oscale,
+                                  float* out);
 /* Fused generator res-block conv (kernels_arb.cu): out = (conv1d(snake(x*scale_b+shift_b), w, dilation) + bias + res)
  * * oscale (+ out when accumulate); B ragged items packed along rows (x, res, out: [sum lens, C]); C in
  * {128, 256}; w [C][ks][C]; x optionally rounded to bf16 first (in_bf16); result as fp32 or, want_bf16, the

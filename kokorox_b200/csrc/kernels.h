@@ -60,6 +60,8 @@ struct TcConvArgs {
   long long* timing = nullptr;   // diagnostics (-DKKX_TC_TIMING builds)
   const int* tile_start = nullptr; int ntiles_m = 0;   // persistent split-TF32 GEMM: prefix sum of ceil(m_len/128) per item
   int group_m = 1;               // (set by the launcher) m-tiles per L2-resident group
+  int pair = 0;                  // persistent split-FP16 GEMM: CTA pairs (cta_group::2, 256 x 128 tiles) when tmB_c / tmB2_c exist
+  int force_kernel = 0;          // tests: 1 = never take the small-problem (64-wide single-tile) kernel
   // Phase-fused ConvTranspose1d (bf16 path, MODE 0): `nphase` two-tap phase convs in ONE launch.  The weights of the
   // phases are stacked along the weight map's rows (phase p at rows [p*Co, (p+1)*Co)), each phase has its own tap shift
   // and output row offset, and the phase is the FASTEST grid dimension, so the CTAs that read one activation tile run

@@ -566,6 +566,72 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
   }
 }
 
+// Final phase of the persistent split-precision GEMMs (bias, activation, residual, scale, stores) for one epilogue warp:
+// a thread holds one accumulator ROW (64 columns); storing that directly makes every warp-wide store touch 32
+// different rows (32 x 16 B) and kept the drain warps away from the accumulator ring for ~12 k cycles per tile (the MMA
+// warp then waits on the ring).  The warp transposes its 32 x 32 blocks through a private 4 KB smem scratch (16-byte
+// chunks XOR-swizzled by row: conflict-free both ways, __syncwarp only): afterwards 8 lanes cover one 128-byte row
+// segment, so residual loads and stores are full-line and the bias is one float4 per block.
+__device__ __forceinline__ void gemm32_final(const TcConvArgs& a, float* scr, const float (&racc)[64], int b, int m0, int n0,
+                                       int hh, int q, int lane, int mlen) {
+  const int rq = lane >> 3, cq = lane & 7;
+  const int out_row0 = a.out_off[b];
+  const int res_row0 = a.res ? a.res_off[b] : 0;
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      *reinterpret_cast<float4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+          make_float4(racc[blk * 32 + 4 * j], racc[blk * 32 + 4 * j + 1], racc[blk * 32 + 4 * j + 2], racc[blk * 32 + 4 * j + 3]);
+    __syncwarp();
+    const int n = n0 + hh * 64 + blk * 32 + cq * 4;
+    if (n < a.Co) {
+      const bool vec = a.vec4 && (n + 3 < a.Co);
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias) {
+        if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+        else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+      }
+      float4 rv[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int mm = m0 + q * 32 + rq + 4 * i;
+        if (a.res && mm < mlen) {
+          const float* rp = a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n;
+          if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+          else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int r = rq + 4 * i;
+        const int mm = m0 + q * 32 + r;
+        if (mm >= mlen) continue;
+        const float4 v = *reinterpret_cast<const float4*>(scr + r * 32 + ((cq ^ (r & 7)) << 2));
+        float4 o;
+        o.x = fmaf(v.x, a.wscale, bb.x); o.y = fmaf(v.y, a.wscale, bb.y);
+        o.z = fmaf(v.z, a.wscale, bb.z); o.w = fmaf(v.w, a.wscale, bb.w);
+        if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+        o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+        o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+        float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
+        if (vec) {
+          if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+          *reinterpret_cast<float4*>(op) = o;
+        } else {
+          if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+          op[0] = o.x;
+          if (n + 1 < a.Co) op[1] = o.y;
+          if (n + 2 < a.Co) op[2] = o.z;
+          if (n + 3 < a.Co) op[3] = o.w;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Persistent split-TF32 GEMM / conv (BN = 128, 3 stages of 4 x 16 KB operand planes).  One CTA per SM
 // walks tiles t = blockIdx.x + i*gridDim.x of the (n-tile, item, m-tile) space, m fastest.  Same arithmetic
@@ -763,71 +829,8 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
       tc_fence_before();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sfree_bar) : "memory");   // TMEM is free again
 
-      // ---- the rest runs while the next tile's pipeline is already going: bias, activation, residual, scale, stores.
-      // A thread holds one accumulator ROW (64 columns); storing that directly makes every warp-wide store touch 32
-      // different rows (32 x 16 B) and kept the drain warps away from the accumulator ring for ~12 k cycles per tile
-      // (the MMA warp then waits on the ring).  Each warp transposes its 32 x 32 block through a private 4 KB smem
-      // scratch (16-byte chunks XOR-swizzled by row: conflict-free both ways, __syncwarp only): afterwards 8 lanes
-      // cover one 128-byte row segment, so residual loads and stores are full-line and the bias is one float4 per block.
-      {
-        float* const scr = scr_f + (warp - 2) * 1024;
-        const int rq = lane >> 3, cq = lane & 7;
-        const int out_row0 = a.out_off[b];
-        const int res_row0 = a.res ? a.res_off[b] : 0;
-#pragma unroll
-        for (int blk = 0; blk < 2; blk++) {
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            *reinterpret_cast<float4*>(scr + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-                make_float4(racc[blk * 32 + 4 * j], racc[blk * 32 + 4 * j + 1], racc[blk * 32 + 4 * j + 2], racc[blk * 32 + 4 * j + 3]);
-          __syncwarp();
-          const int n = n0 + hh * 64 + blk * 32 + cq * 4;
-          if (n < a.Co) {
-            const bool vec = a.vec4 && (n + 3 < a.Co);
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.bias) {
-              if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
-              else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
-            }
-            float4 rv[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              const int mm = m0 + q * 32 + rq + 4 * i;
-              if (a.res && mm < mlen) {
-                const float* rp = a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n;
-                if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
-                else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int r = rq + 4 * i;
-              const int mm = m0 + q * 32 + r;
-              if (mm >= mlen) continue;
-              const float4 v = *reinterpret_cast<const float4*>(scr + r * 32 + ((cq ^ (r & 7)) << 2));
-              float4 o;
-              o.x = fmaf(v.x, a.wscale, bb.x); o.y = fmaf(v.y, a.wscale, bb.y);
-              o.z = fmaf(v.z, a.wscale, bb.z); o.w = fmaf(v.w, a.wscale, bb.w);
-              if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
-              o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
-              o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-              float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
-              if (vec) {
-                if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
-                *reinterpret_cast<float4*>(op) = o;
-              } else {
-                if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
-                op[0] = o.x;
-                if (n + 1 < a.Co) op[1] = o.y;
-                if (n + 2 < a.Co) op[2] = o.z;
-                if (n + 3 < a.Co) op[3] = o.w;
-              }
-            }
-          }
-          __syncwarp();
-        }
-      }
+      // ---- the rest runs while the next tile's pipeline is already going (see gemm32_final)
+      gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0, hh, q, lane, mlen);
       TCT(3);
     }
     TCT_FLUSH(8, 4);
@@ -858,6 +861,233 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
   b.group_m = (int)gm;
   gemm32p_kernel<<<grid, kGemm32pThreads, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB),
                                           *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2), b);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair version of the persistent split-FP16 GEMM (cta_group::2, clusters of two CTAs along M).
+// Role counters of gemm32p_kernel showed the MMA warp's issue time at ~1270 cycles per 64-K stage against a tensor-pipe
+// floor of 768: a stage moves 64 KB of TMA writes plus 12 x 8 KB of operand reads through the SM's 128 B/clk shared-
+// memory port (160 KB -> 1250 cycles), and the 148 CTAs together pull ~7.5 KB/clk out of L2 -- both above what the
+// hardware gives.  A pair computes a 256 x 128 tile with ONE tcgen05.mma.cta_group::2 per K step: each CTA supplies its
+// own 128 rows of A (hi and lo planes) and only HALF of the weight tile (64 of the 128 rows of B); the tensor cores read
+// the other half from the peer's shared memory.  Per CTA and stage: 48 KB of TMA writes + 12 x 6 KB of operand reads
+// (120 KB, -25 %), 48 instead of 64 KB from L2, and the smaller stage buys a fourth pipeline stage.
+//   * both CTAs run a TMA warp; all loads of a stage count their bytes on the LEADER's full barrier (cta_group::2 TMA);
+//   * only the leader issues MMAs; its commits arrive on the barriers of both CTAs (multicast);
+//   * each CTA drains / finishes its own 128 accumulator rows exactly like gemm32p_kernel (same arithmetic, same order:
+//     bit-identical results); "ring slot drained" / "small accumulator pulled" arrivals of both CTAs go to the leader.
+// The two m-tiles of a pair are consecutive entries of the m-tile list (they may belong to different items); an odd
+// list ends with a pair whose second CTA recomputes the last tile and stores nothing.
+constexpr int kG2Stages = 4;
+constexpr uint32_t kG2A = 128 * 128, kG2Bh = 64 * 128, kG2Stage = 2 * (kG2A + kG2Bh);
+constexpr int kG2Smem = kG2Stages * (int)kG2Stage + 8 * 4096 + 16 * 8 + 16 + 1024;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm32pThreads, 1)
+gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, TcConvArgs a) {
+  constexpr int BN = 128, STAGES = kG2Stages;
+  constexpr int KE = 64;                                   // K elements per 128-byte span (fp16 planes); one chain per stage
+  constexpr int NEPI = (kGemm32pThreads - 64) / 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t scr_base = base + STAGES * kG2Stage;
+  float* const scr_f = reinterpret_cast<float*>(smem_raw + (scr_base - smem_u32(smem_raw)));
+  const uint32_t bar_base = scr_base + 8 * 4096;           // full[4], empty[4], bfull[3], bempty[3], sfull, sfree
+  const uint32_t tmem_slot = bar_base + 16 * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (4 + s) * 8; };
+  auto bfull_bar = [&](int j) { return bar_base + (8 + j) * 8; };
+  auto bempty_bar = [&](int j) { return bar_base + (11 + j) * 8; };
+  const uint32_t sfull_bar = bar_base + 14 * 8, sfree_bar = bar_base + 15 * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int kchunks = a.Cpad / KE;
+  const int num_k = a.ks * kchunks;                        // stages = chains per tile
+  const int ntm = a.ntiles_m, ntm2 = (ntm + 1) >> 1;
+  const int NT = (a.Co + BN - 1) / BN;
+  const int total = ntm2 * NT;
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2h) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 2 * NEPI); }
+    mbar_init(sfull_bar, 1); mbar_init(sfree_bar, 2 * NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // the same warp of both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barriers of both CTAs initialised, TMEM of both allocated, before any cross-CTA traffic
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // pair-tile -> (n-tile, this CTA's m-tile); groups of gm2 consecutive m-tile PAIRS stay L2-resident while all their
+  // n-tiles are computed (same idea as gemm32p_kernel)
+  const int gm2 = a.group_m > 1 ? (a.group_m >> 1) : 1;
+  auto decode = [&](int t, int& b, int& m0, int& n0, bool& valid) {
+    const int g = t / (gm2 * NT), r = t - g * gm2 * NT;
+    const int gsz = min(gm2, ntm2 - g * gm2);
+    const int nt = r / gsz;
+    int mg = 2 * (g * gm2 + (r - nt * gsz)) + (int)rank;
+    valid = mg < ntm;
+    if (!valid) mg = ntm - 1;
+    int lo = 0, hi = a.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.tile_start[mid] <= mg) lo = mid; else hi = mid;
+    }
+    b = lo; m0 = (mg - a.tile_start[lo]) * 128; n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      TCT_DECL(2);
+      for (int t = pair; t < total; t += npairs) {
+        int b, m0, n0; bool valid;
+        decode(t, b, m0, n0, valid);
+        const int row0 = a.in_off[b] + m0 - a.pad;
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          TCT(1);
+          mbar_wait(empty_bar(s), (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          TCT(0);
+          const int tap = it / kchunks, c0 = (it - tap * kchunks) * KE;
+          const uint32_t sa = base + s * kG2Stage;
+          const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * kG2Stage);      // the bytes of both CTAs
+          tma_load_2d_pair(sa, &tmA, c0, row0 + tap * a.dil, lead_full);
+          tma_load_2d_pair(sa + kG2A, &tmA2, c0, row0 + tap * a.dil, lead_full);
+          tma_load_2d_pair(sa + 2 * kG2A, &tmBh, tap * a.Cpad + c0, n0 + (int)rank * 64, lead_full);
+          tma_load_2d_pair(sa + 2 * kG2A + kG2Bh, &tmB2h, tap * a.Cpad + c0, n0 + (int)rank * 64, lead_full);
+        }
+      }
+      TCT_FLUSH(0, 2);
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(256, BN);
+      int g = 0, gc = 0, ti = 0;
+      TCT_DECL(4);
+      for (int t = pair; t < total; t += npairs, ti++) {
+        TCT(2);
+        if (ti > 0) { mbar_wait(sfree_bar, (uint32_t)(ti - 1) & 1u); tc_fence_after(); }
+        TCT(3);
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
+          tc_fence_after();
+          TCT(0);
+          const uint32_t sa = base + s * kG2Stage;
+          const int G = gc + it, j = G % 3;
+          if (G >= 3) {                          // ring slot j must have been drained by the epilogues of both CTAs
+            mbar_wait(bempty_bar(j), (uint32_t)(G / 3 - 1) & 1u);
+            tc_fence_after();
+          }
+          TCT(1);
+          const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + kG2A);
+          const uint64_t bh = umma_desc_sw128(sa + 2 * kG2A), bl = umma_desc_sw128(sa + 2 * kG2A + kG2Bh);
+          const uint32_t t_small = tmem_base, t_big = tmem_base + (uint32_t)(BN * (1 + j));
+#pragma unroll
+          for (int k = 0; k < 4; k++) {          // 4 x 16 fp16 of K; same products, same order as gemm32p_kernel
+            const uint64_t o = (uint64_t)(2 * k);
+            umma_f16_pair(t_small, al + o, bh + o, idesc, (it | k) ? 1u : 0u);
+            umma_f16_pair(t_small, ah + o, bl + o, idesc, 1u);
+            umma_f16_pair(t_big, ah + o, bh + o, idesc, k == 0 ? 0u : 1u);
+          }
+          umma_commit_pair(bfull_bar(j));        // chain complete (both CTAs)
+          umma_commit_pair(empty_bar(s));        // stage free (both CTAs)
+          TCT(2);
+        }
+        umma_commit_pair(sfull_bar);
+        gc += num_k;
+      }
+      TCT_FLUSH(4, 4);
+    }
+  } else {
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
+    const uint32_t lead_bars = mapa_u32(bar_base, 0);          // the leader's barrier block (same offsets)
+    const uint32_t lead_sfree = lead_bars + 15 * 8;
+    int gc = 0, ti = 0;
+#ifdef KKX_TC_TIMING
+    long long tct_acc[4] = {0}; long long tct_last = clock64();
+    const bool tct_on = a.timing && blockIdx.x == gridDim.x - 2 && threadIdx.x == 64;
+#endif
+    for (int t = pair; t < total; t += npairs, ti++) {
+      int b, m0, n0; bool valid;
+      decode(t, b, m0, n0, valid);
+      const int mlen = valid ? a.m_len[b] : 0;           // the duplicate tile of an odd list stores nothing
+      float racc[64];
+#pragma unroll
+      for (int e = 0; e < 64; e++) racc[e] = 0.f;
+      for (int ch = 0; ch < num_k; ch++) {
+        const int G = gc + ch, j = G % 3;
+        mbar_wait(bfull_bar(j), (uint32_t)(G / 3) & 1u);
+        tc_fence_after();
+        TCT(0);
+        {
+          uint32_t v[64];
+          tmem_ld64(tq + (uint32_t)(BN * (1 + j)), v);
+#pragma unroll
+          for (int e = 0; e < 64; e++) racc[e] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        if (lane == 0) mbar_arrive_cluster(lead_bars + (uint32_t)(11 + j) * 8);
+        TCT(1);
+      }
+      gc += num_k;
+      mbar_wait(sfull_bar, (uint32_t)ti & 1u);
+      tc_fence_after();
+      TCT(2);
+      {
+        uint32_t v[64];
+        tmem_ld64(tq, v);
+#pragma unroll
+        for (int e = 0; e < 64; e++) racc[e] = __uint_as_float(v[e]) + racc[e];
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_cluster(lead_sfree);
+      gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0, hh, q, lane, mlen);
+      TCT(3);
+    }
+    TCT_FLUSH(8, 4);
+  }
+  tc_fence_before();
+  cluster_sync_all();      // nobody leaves (or frees TMEM) while the peer may still signal it or the pair-MMAs read its smem
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
+  static DevOnce once;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(gemm32p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem)); });
+  const int nsm = device_sm_count(dev);
+  const int total = ((a.ntiles_m + 1) / 2) * ((a.Co + 127) / 128);
+  int npairs = nsm / 2;
+  if (npairs > total) npairs = total;
+  TcConvArgs b = a;
+  static const int l2mb = env_int("KKX_TC_GROUP_MB", 24);
+  const long long per_tile = 128LL * a.Cpad * 4;                      // bytes of the hi + lo planes of one m-tile
+  long long gm = (long long)l2mb * 1000000LL / (per_tile > 0 ? per_tile : 1);
+  if (gm < 8) gm = 8;
+  if (gm > a.ntiles_m) gm = a.ntiles_m;
+  b.group_m = (int)gm;
+  gemm32p2_kernel<<<2 * npairs, kGemm32pThreads, kG2Smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c),
+                                                         *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2_c), b);
 }
 
 template <int BN, int STAGES, int TPC>
@@ -924,11 +1154,15 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
     cudaGetDevice(&cur_dev);
     const int nsm = device_sm_count(cur_dev);
     const long long tiles128 = (long long)(a.ntiles_m > 0 ? a.ntiles_m : (a.sum_m + 127) / 128) * ((a.Co + 127) / 128);
-    const bool small = tiles128 < nsm && a.tmB_c && a.tmB2_c && a.cluster < 2;
+    const bool small = tiles128 < nsm && a.tmB_c && a.tmB2_c && a.cluster < 2 && a.force_kernel == 0;
     if (a.Co > 64 && small) {
       TcConvArgs b = a; b.tmB = a.tmB_c; b.tmB2 = a.tmB2_c;
       launch_tc<64, 4, 1>(b, st);
-    } else if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) launch_gemm32p(a, st);
+    } else if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) {
+      // CTA pairs (cta_group::2) for the split-FP16 planes when the weight maps with 64-row boxes exist
+      if (a.pair && a.f16 && a.nprod == 3 && a.tmB_c && a.tmB2_c && a.ntiles_m >= 2) launch_gemm32p2(a, st);
+      else launch_gemm32p(a, st);
+    }
     else if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);
     else if (a.Co > 64 && !(bn64 && a.tmB_c)) launch_tc<128, 3, 1>(a, st);
     else if (a.Co > 64) {   // experiment: 64-wide tiles (4 stages of 48 KB) with the half-height weight boxes

@@ -146,6 +146,8 @@ struct Options {
   int stream_bf16 = 0;
   // ConvTranspose1d up-sampling: all phases in one launch (L2 serves the re-reads of the input) instead of s launches
   int fuse_phases = 1;
+  // persistent split-FP16 GEMMs: CTA pairs (tcgen05 cta_group::2, 256 x 128 tiles, half the weight tile per CTA)
+  int gemm_pair = 1;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32

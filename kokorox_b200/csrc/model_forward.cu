@@ -88,7 +88,7 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
       make_tmap_f16(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
       a.tmB = w32->tm16_hi; a.tmB2 = w32->tm16_lo; a.f16 = 1;
       a.wscale = w32->wscale16 / kSplitF16Scale;
-      if (w32->has_c) { a.tmB_c = w32->tm16_hi_c; a.tmB2_c = w32->tm16_lo_c; }
+      if (w32->has_c) { a.tmB_c = w32->tm16_hi_c; a.tmB2_c = w32->tm16_lo_c; a.pair = opt.gemm_pair; }
     } else {
       launch_apply_tf32(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
                         Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
@@ -154,7 +154,7 @@ void Model::token_phase(Run& r) {
   // captured once (on the second call with that count) and replayed afterwards -- ~190 launches become one.
   const bool graph_ok = opt.latency_graphs && B_ == 1 && !debug_ && !stats.profile && !stats.check_each && inj_dur_.empty();
   if (graph_ok) {
-    const GraphKey key{tok_len_[0], opt.precision * 4 + opt.attention_umma * 2 + opt.split_f16, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
+    const GraphKey key{tok_len_[0], opt.precision * 8 + opt.attention_umma * 4 + opt.split_f16 * 2 + opt.gemm_pair, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
     auto it = graphs_.find(key);
     if (it != graphs_.end() && it->second.exec) {
       r = it->second.run;

@@ -178,8 +178,9 @@ KKX_API int kkx_test_conv_tf32(int device, const float* x, int L, int Ci, const 
   });
 }
 
-KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const float* w, const float* bias,
-                                int Co, int ks, int dil, int pad, int eact, float* out) {
+// kernel: 0 = the launcher's own choice, 1 = single-tile kernel, 2 = persistent kernel, 3 = persistent CTA-pair kernel
+static int conv_f16x3_impl(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                           int Co, int ks, int dil, int pad, int eact, int kernel, const float* res, float oscale, float* out) {
   return run(device, [&] {
     const int Cpad = (Ci + 63) & ~63;
     const int off = kGapRows, rows_total = (off + L + kGapRows + 7) & ~7;
@@ -222,10 +223,27 @@ KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const
     a.bias = bias ? db.as<float>() : nullptr;
     a.out = dout.as<float>(); a.ldo = Co; a.ocol = 0; a.out_off = dm.as<int>() + 2; a.ors = 1; a.oro = 0;
     a.tile_start = dt.as<int>(); a.ntiles_m = nt;
+    DevBuf dres(res, res ? (size_t)L * Co * 4 : 0);
+    if (res) { a.res = dres.as<float>(); a.ldr = Co; a.rcol = 0; a.res_off = dm.as<int>() + 2; a.res_shift = 0; }
+    a.oscale = oscale;
+    if (kernel) a.force_kernel = 1;
+    if (kernel == 1) { a.tile_start = nullptr; a.ntiles_m = 0; }
+    a.pair = (kernel == 0 || kernel == 3) ? 1 : 0;
     launch_conv_tc(a, 0);
     KKX_CUDA(cudaDeviceSynchronize());
     KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)L * Co * 4, cudaMemcpyDeviceToHost));
   });
+}
+
+KKX_API int kkx_test_conv_f16x3(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                                int Co, int ks, int dil, int pad, int eact, float* out) {
+  return conv_f16x3_impl(device, x, L, Ci, w, bias, Co, ks, dil, pad, eact, 0, nullptr, 1.f, out);
+}
+
+KKX_API int kkx_test_conv_f16x3_k(int device, const float* x, int L, int Ci, const float* w, const float* bias,
+                                  int Co, int ks, int dil, int pad, int eact, int kernel, const float* res, float oscale,
+                                  float* out) {
+  return conv_f16x3_impl(device, x, L, Ci, w, bias, Co, ks, dil, pad, eact, kernel, res, oscale, out);
 }
 
 KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int N, float* out) {

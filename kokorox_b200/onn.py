@@ -89,6 +89,8 @@ def load_library(path: Optional[str] = None):
         lib.kkx_test_tensor_specs.restype = i64
         lib.kkx_test_conv_f16x3.argtypes = [C.c_int, P(f32), C.c_int, C.c_int, P(f32), P(f32), C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, P(f32)]
+        lib.kkx_test_conv_f16x3_k.argtypes = [C.c_int, P(f32), C.c_int, C.c_int, P(f32), P(f32), C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.c_int, P(f32), f32, P(f32)]
         lib.kkx_test_arb_conv_stream.argtypes = [C.c_int, P(f32), C.c_int, P(i32), C.c_int, P(f32), P(f32), P(f32), P(f32),
                                                  P(f32), C.c_int, C.c_int, P(f32), f32, C.c_int, C.c_int, P(f32), P(f32)]
         lib.kkx_test_attention_batch.argtypes = [C.c_int, P(f32), C.c_int, P(i32), P(i32), C.c_int, C.c_int, P(f32)]

@@ -334,6 +334,40 @@ def test_split_fp16_gemm_is_fp32_grade(lib, L, Ci, Co, k):
     assert e_tc < 4e-6 and rms_tc < 8 * max(rms_32, 1e-9)
 
 
+@pytest.mark.parametrize("L,Ci,Co,k,eact,use_res", [(20000, 768, 768, 1, 0, True), (128 * 151 + 5, 768, 2304, 1, 0, False),
+                                                     (128 * 37, 2048, 768, 1, 0, True), (9000, 512, 512, 3, 0, False),
+                                                     (128 * 75 + 1, 768, 2048, 1, 3, False), (300, 640, 2048, 1, 0, True)])
+def test_split_fp16_gemm_kernels_are_bit_identical(lib, L, Ci, Co, k, eact, use_res):
+    """The single-tile kernel, the persistent kernel and the persistent CTA-pair kernel (tcgen05 cta_group::2: 256 x 128
+    tiles, each CTA holds half of the weight tile) accumulate every output element in the same order: identical bits,
+    for odd and even m-tile counts (an odd count ends with a pair whose second CTA stores nothing), ragged tails,
+    residual + scale and the GELU epilogue.  Which kernel runs depends on the batch, so this is what keeps results
+    independent of the batch composition."""
+    x = rnd(L, Ci, seed=L + Ci)
+    w = rnd(Co, Ci, k, seed=L + Co, scale=0.5 / np.sqrt(Ci * k))
+    b = rnd(Co, seed=3)
+    res = rnd(L, Co, seed=5) if use_res else None
+    pad = (k - 1) // 2
+    outs = []
+    for kernel in (1, 2, 3):
+        out = np.full((L, Co), np.nan, np.float32)
+        rc = lib.kkx_test_conv_f16x3_k(0, fp(x), L, Ci, fp(np.ascontiguousarray(w.transpose(0, 2, 1))), fp(b), Co, k, 1, pad,
+                                       eact, kernel, fp(res) if use_res else None, 0.5 if use_res else 1.0, fp(out))
+        assert rc == 0, lib.kkx_test_last_error()
+        assert np.isfinite(out).all()
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1]), "persistent kernel differs from the single-tile kernel"
+    assert np.array_equal(outs[0], outs[2]), "CTA-pair kernel differs from the single-tile kernel"
+    tx, tw, tb = torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b)
+    ref = F.conv1d(tx.double().T[None], tw.double(), tb.double(), padding=pad)[0].T
+    if eact == 3:
+        ref = 0.5 * ref * (1.0 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
+    ref = ref.numpy()
+    if use_res:
+        ref = (ref + res) * 0.5
+    assert np.abs(outs[2] - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("Cc,k,dil", [(128, 3, 1), (128, 11, 5), (256, 7, 3)])
 def test_tc_conv_multi_tile_kernel(lib, Cc, k, dil):
     # large enough (>= 1184 tiles) to take the multi-tile / double-buffered-TMEM kernel, with a ragged

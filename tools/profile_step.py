@@ -20,12 +20,16 @@ def main():
     ap.add_argument("--precision", type=int, default=1)
     ap.add_argument("--runs", type=int, default=2)
     ap.add_argument("--max-frames", type=int, default=0, help="frame budget per frame-phase group (0 = library default)")
+    ap.add_argument("--set", action="append", default=[], metavar="OPTION=VALUE", help="session option (kkx_set_option), repeatable")
     a = ap.parse_args()
     from kokorox_b200.onn import B200Koko
     m = B200Koko.new(ensure_weights())
     m.set_option("precision", a.precision)
     if a.max_frames:
         m.set_option("max_frames", a.max_frames)
+    for kv in a.set:
+        k, v = kv.split("=")
+        m.set_option(k, int(v))
     toks, styles, speeds = synth_batch(a.batch, a.tokens)
     m.stage(toks, styles, speeds)
     m.profile_enable(True)
