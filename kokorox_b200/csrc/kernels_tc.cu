@@ -871,33 +871,41 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
 // hardware gives.  A pair computes a 256 x 128 tile with ONE tcgen05.mma.cta_group::2 per K step: each CTA supplies its
 // own 128 rows of A (hi and lo planes) and only HALF of the weight tile (64 of the 128 rows of B); the tensor cores read
 // the other half from the peer's shared memory.  Per CTA and stage: 48 KB of TMA writes + 12 x 6 KB of operand reads
-// (120 KB, -25 %), 48 instead of 64 KB from L2, and the smaller stage buys a fourth pipeline stage.
+// (120 KB, -25 %) and 48 instead of 64 KB from L2.
 //   * both CTAs run a TMA warp; all loads of a stage count their bytes on the LEADER's full barrier (cta_group::2 TMA);
 //   * only the leader issues MMAs; its commits arrive on the barriers of both CTAs (multicast);
 //   * each CTA drains / finishes its own 128 accumulator rows exactly like gemm32p_kernel (same arithmetic, same order:
 //     bit-identical results); "ring slot drained" / "small accumulator pulled" arrivals of both CTAs go to the leader.
 // The two m-tiles of a pair are consecutive entries of the m-tile list (they may belong to different items); an odd
 // list ends with a pair whose second CTA recomputes the last tile and stores nothing.
-constexpr int kG2Stages = 4;
+//   * the finished tile leaves through shared memory: the 8 drain warps only accumulate chains (registers) and drop the
+//     128 x 128 fp32 result into a 64 KB staging tile; 4 "final" warps apply bias / activation / residual / scale and
+//     store whole 512-byte rows while the drain warps are already on the next tile.  (With the final phase on the drain
+//     warps the accumulator ring was not drained for ~8 k cycles per tile and the MMA warp spent 13 of its 36 Mcycles
+//     per step waiting for a ring slot.)
+constexpr int kG2Stages = 3;
+constexpr int kG2Threads = 448;    // TMA warp, MMA warp, 8 drain warps, 4 final warps
 constexpr uint32_t kG2A = 128 * 128, kG2Bh = 64 * 128, kG2Stage = 2 * (kG2A + kG2Bh);
-constexpr int kG2Smem = kG2Stages * (int)kG2Stage + 8 * 4096 + 16 * 8 + 16 + 1024;
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm32pThreads, 1)
+constexpr uint32_t kG2Stg = 128 * 128 * 4;
+constexpr int kG2Smem = kG2Stages * (int)kG2Stage + (int)kG2Stg + 20 * 8 + 16 + 1024;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, TcConvArgs a) {
   constexpr int BN = 128, STAGES = kG2Stages;
   constexpr int KE = 64;                                   // K elements per 128-byte span (fp16 planes); one chain per stage
-  constexpr int NEPI = (kGemm32pThreads - 64) / 32;
+  constexpr int NEPI = 8, NFIN = 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t scr_base = base + STAGES * kG2Stage;
-  float* const scr_f = reinterpret_cast<float*>(smem_raw + (scr_base - smem_u32(smem_raw)));
-  const uint32_t bar_base = scr_base + 8 * 4096;           // full[4], empty[4], bfull[3], bempty[3], sfull, sfree
-  const uint32_t tmem_slot = bar_base + 16 * 8;
+  const uint32_t stg_base = base + STAGES * kG2Stage;      // finished tile, fp32 [128][128], 16-byte chunks XOR-swizzled by row
+  float* const stg_f = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+  const uint32_t bar_base = stg_base + kG2Stg;             // full[4], empty[4], bfull[3], bempty[3], sfull, sfree, gfull, gfree
+  const uint32_t tmem_slot = bar_base + 20 * 8;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
   auto empty_bar = [&](int s) { return bar_base + (4 + s) * 8; };
   auto bfull_bar = [&](int j) { return bar_base + (8 + j) * 8; };
   auto bempty_bar = [&](int j) { return bar_base + (11 + j) * 8; };
   const uint32_t sfull_bar = bar_base + 14 * 8, sfree_bar = bar_base + 15 * 8;
+  const uint32_t gfull_bar = bar_base + 16 * 8, gfree_bar = bar_base + 17 * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -916,6 +924,7 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int j = 0; j < 3; j++) { mbar_init(bfull_bar(j), 1); mbar_init(bempty_bar(j), 2 * NEPI); }
     mbar_init(sfull_bar, 1); mbar_init(sfree_bar, 2 * NEPI);
+    mbar_init(gfull_bar, NEPI); mbar_init(gfree_bar, NFIN);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1012,9 +1021,12 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       TCT_FLUSH(4, 4);
     }
-  } else {
+  } else if (warp < 2 + NEPI) {
+    // ---- drain warps: warp w owns TMEM lane quadrant q = w & 3 and column half hh; a thread accumulates one row x 64
+    // columns over the tile's chains (two 32-column loads per chain keep this role inside its register budget)
     const int q = warp & 3;
     const int hh = (warp - 2) >> 2;
+    const int et = q * 32 + lane;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
     const uint32_t lead_bars = mapa_u32(bar_base, 0);          // the leader's barrier block (same offsets)
     const uint32_t lead_sfree = lead_bars + 15 * 8;
@@ -1024,9 +1036,6 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool tct_on = a.timing && blockIdx.x == gridDim.x - 2 && threadIdx.x == 64;
 #endif
     for (int t = pair; t < total; t += npairs, ti++) {
-      int b, m0, n0; bool valid;
-      decode(t, b, m0, n0, valid);
-      const int mlen = valid ? a.m_len[b] : 0;           // the duplicate tile of an odd list stores nothing
       float racc[64];
 #pragma unroll
       for (int e = 0; e < 64; e++) racc[e] = 0.f;
@@ -1035,11 +1044,12 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bfull_bar(j), (uint32_t)(G / 3) & 1u);
         tc_fence_after();
         TCT(0);
-        {
-          uint32_t v[64];
-          tmem_ld64(tq + (uint32_t)(BN * (1 + j)), v);
 #pragma unroll
-          for (int e = 0; e < 64; e++) racc[e] += __uint_as_float(v[e]);
+        for (int h2 = 0; h2 < 2; h2++) {
+          uint32_t v[32];
+          tmem_ld32(tq + (uint32_t)(BN * (1 + j) + h2 * 32), v);
+#pragma unroll
+          for (int e = 0; e < 32; e++) racc[h2 * 32 + e] += __uint_as_float(v[e]);
         }
         tc_fence_before();
         if (lane == 0) mbar_arrive_cluster(lead_bars + (uint32_t)(11 + j) * 8);
@@ -1049,18 +1059,102 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(sfull_bar, (uint32_t)ti & 1u);
       tc_fence_after();
       TCT(2);
-      {
-        uint32_t v[64];
-        tmem_ld64(tq, v);
 #pragma unroll
-        for (int e = 0; e < 64; e++) racc[e] = __uint_as_float(v[e]) + racc[e];
+      for (int h2 = 0; h2 < 2; h2++) {
+        uint32_t v[32];
+        tmem_ld32(tq + (uint32_t)(h2 * 32), v);
+#pragma unroll
+        for (int e = 0; e < 32; e++) racc[h2 * 32 + e] = __uint_as_float(v[e]) + racc[h2 * 32 + e];   // same order as the single-tile kernel
       }
       tc_fence_before();
-      if (lane == 0) mbar_arrive_cluster(lead_sfree);
-      gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0, hh, q, lane, mlen);
+      if (lane == 0) mbar_arrive_cluster(lead_sfree);        // TMEM is free again
+      // hand the finished rows to the final warps
+      if (ti > 0) mbar_wait(gfree_bar, (uint32_t)(ti - 1) & 1u);
+      float* const srow = stg_f + et * 128;
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const int chunk = hh * 16 + c;                         // 16-byte chunk of the row; swizzle inside groups of 8 chunks
+        *reinterpret_cast<float4*>(srow + (((chunk & ~7) | ((chunk ^ et) & 7)) << 2)) =
+            make_float4(racc[4 * c], racc[4 * c + 1], racc[4 * c + 2], racc[4 * c + 3]);
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gfull_bar) : "memory");
       TCT(3);
     }
     TCT_FLUSH(8, 4);
+  } else {
+    // ---- final warps: bias, activation, residual, scale and the stores, one 512-byte row per warp instruction (lane l
+    // owns columns 4l .. 4l+3), rows fw, fw + 4, ... of the staged tile
+    const int fw = warp - (2 + NEPI);
+    int ti = 0;
+    for (int t = pair; t < total; t += npairs, ti++) {
+      int b, m0, n0; bool valid;
+      decode(t, b, m0, n0, valid);
+      const int mlen = valid ? a.m_len[b] : 0;                 // the duplicate tile of an odd list stores nothing
+      const int n = n0 + lane * 4;
+      const bool ncol = n < a.Co;
+      const bool vec = a.vec4 && (n + 3 < a.Co);
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias && ncol) {
+        if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
+        else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+      }
+      const int out_row0 = a.out_off[b];
+      const int res_row0 = a.res ? a.res_off[b] : 0;
+      constexpr int RB = 8;                                    // rows per batch: residual loads of a batch are issued together
+      auto res_ptr = [&](int mm) { return a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n; };
+      auto load_res = [&](int i0, float4 (&rv)[RB]) {
+#pragma unroll
+        for (int i = 0; i < RB; i++) {
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int mm = m0 + fw + 4 * (i0 + i);
+          if (a.res && ncol && mm < mlen) {
+            const float* rp = res_ptr(mm);
+            if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
+            else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
+          }
+        }
+      };
+      float4 rv[RB];
+      load_res(0, rv);                                         // overlaps the wait for the tile
+      mbar_wait(gfull_bar, (uint32_t)ti & 1u);
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += RB) {
+        float4 v[RB];
+#pragma unroll
+        for (int i = 0; i < RB; i++) {
+          const int r = fw + 4 * (i0 + i);
+          v[i] = *reinterpret_cast<const float4*>(stg_f + r * 128 + (((lane & ~7) | ((lane ^ r) & 7)) << 2));
+        }
+        if (i0 + RB >= 32) {                                   // last read of the staged tile
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gfree_bar) : "memory");
+        }
+#pragma unroll
+        for (int i = 0; i < RB; i++) {
+          const int mm = m0 + fw + 4 * (i0 + i);
+          if (mm >= mlen || !ncol) continue;
+          float4 o;
+          o.x = fmaf(v[i].x, a.wscale, bb.x); o.y = fmaf(v[i].y, a.wscale, bb.y);
+          o.z = fmaf(v[i].z, a.wscale, bb.z); o.w = fmaf(v[i].w, a.wscale, bb.w);
+          if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
+          o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
+          o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
+          float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
+          if (vec) {
+            if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
+            *reinterpret_cast<float4*>(op) = o;
+          } else {
+            if (a.accumulate) { o.x += op[0]; if (n + 1 < a.Co) o.y += op[1]; if (n + 2 < a.Co) o.z += op[2]; if (n + 3 < a.Co) o.w += op[3]; }
+            op[0] = o.x;
+            if (n + 1 < a.Co) op[1] = o.y;
+            if (n + 2 < a.Co) op[2] = o.z;
+            if (n + 3 < a.Co) op[3] = o.w;
+          }
+        }
+        if (i0 + RB < 32) load_res(i0 + RB, rv);
+      }
+    }
   }
   tc_fence_before();
   cluster_sync_all();      // nobody leaves (or frees TMEM) while the peer may still signal it or the pair-MMAs read its smem
@@ -1086,7 +1180,7 @@ static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
   if (gm < 8) gm = 8;
   if (gm > a.ntiles_m) gm = a.ntiles_m;
   b.group_m = (int)gm;
-  gemm32p2_kernel<<<2 * npairs, kGemm32pThreads, kG2Smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c),
+  gemm32p2_kernel<<<2 * npairs, kG2Threads, kG2Smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c),
                                                          *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2_c), b);
 }
 
