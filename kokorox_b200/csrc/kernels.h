@@ -60,6 +60,9 @@ struct TcConvArgs {
   long long* timing = nullptr;   // diagnostics (-DKKX_TC_TIMING builds)
   const int* tile_start = nullptr; int ntiles_m = 0;   // persistent split-TF32 GEMM: prefix sum of ceil(m_len/128) per item
   int group_m = 1;               // (set by the launcher) m-tiles per L2-resident group
+  // persistent CTA-pair kernel only: also (or, with out == nullptr, only) write the result as split-FP16 operand planes
+  // [rows, out_pl_ld] (hi / lo halves of 16 * value, like launch_apply_f16x2) for the GEMM that consumes it next
+  void* out_hi = nullptr; void* out_lo = nullptr; int out_pl_ld = 0;
   int pair = 0;                  // persistent split-FP16 GEMM: CTA pairs (cta_group::2, 256 x 128 tiles) when tmB_c / tmB2_c exist
   int force_kernel = 0;          // tests: 1 = never take the small-problem (64-wide single-tile) kernel
   // Phase-fused ConvTranspose1d (bf16 path, MODE 0): `nphase` two-tap phase convs in ONE launch.  The weights of the
@@ -72,6 +75,8 @@ struct TcConvArgs {
   int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);
+// true when launch_conv_tc will run the CTA-pair kernel for these arguments (the only kernel that honours out_hi / out_lo)
+bool conv_tc_takes_pair(const TcConvArgs& a);
 // out_map: 128-byte CUtensorMap storage (64-byte aligned).  bf16 [outer, inner], box [box_outer, 64].
 void make_tmap_bf16(void* out_map, const void* ptr, long long inner, long long outer,
                     long long pitch_elems, int box_outer);
@@ -145,6 +150,9 @@ struct LnArgs {
   float eps = 1e-5f; float slope = 1.f;                        // slope != 1 -> LeakyReLU
   float* out = nullptr; int ldo = 0; int ocol = 0;
   const int* off = nullptr; const int* len = nullptr; int B = 1; int max_len = 0; int C = 0;
+  // optional second output: the result as split-FP16 operand planes [rows, pl_ld] (hi / lo halves of 16 * value, the
+  // arithmetic of launch_apply_f16x2) for the GEMM that reads it next
+  void* pl_hi = nullptr; void* pl_lo = nullptr; int pl_ld = 0;
 };
 void launch_layernorm(const LnArgs& a, cudaStream_t st);
 

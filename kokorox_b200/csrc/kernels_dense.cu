@@ -3,6 +3,7 @@
 // integer frame durations must match the oracle bit for bit, and serve as the fp32 reference
 // configuration ("precision"=0) for the decoder/generator.
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace kkx {
@@ -168,6 +169,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
     if (ada) v = (1.0f + ada[c]) * v + ada[C + c];
     if (a.slope != 1.f) v = v > 0.f ? v : v * a.slope;
     o[c] = v;
+    if (a.pl_hi) {   // operand planes for the next split-FP16 GEMM (same arithmetic as apply_f16x2_kernel)
+      const float sv = fminf(fmaxf(v * kSplitF16Scale, -65504.f), 65504.f);
+      const __half hi = __float2half_rn(sv);
+      static_cast<__half*>(a.pl_hi)[row * a.pl_ld + c] = hi;
+      static_cast<__half*>(a.pl_lo)[row * a.pl_ld + c] = __float2half_rn(sv - __half2float(hi));
+    }
   }
 }
 

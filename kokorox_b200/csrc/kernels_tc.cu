@@ -1140,7 +1140,22 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
           o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
           o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-          float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
+          const size_t orow = (size_t)(out_row0 + mm * a.ors + a.oro);
+          if (a.out_hi) {      // operand planes for the next GEMM (host guarantees Co % 4 == 0, no accumulate)
+            const float e4[4] = {o.x, o.y, o.z, o.w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float sv = fminf(fmaxf(e4[e] * kSplitF16Scale, -65504.f), 65504.f);
+              const __half hi = __float2half_rn(sv);
+              hw[e] = __half_as_ushort(hi);
+              lw[e] = __half_as_ushort(__float2half_rn(sv - __half2float(hi)));
+            }
+            *reinterpret_cast<uint2*>(static_cast<__half*>(a.out_hi) + orow * a.out_pl_ld + n) = make_uint2(hw[0] | (hw[1] << 16), hw[2] | (hw[3] << 16));
+            *reinterpret_cast<uint2*>(static_cast<__half*>(a.out_lo) + orow * a.out_pl_ld + n) = make_uint2(lw[0] | (lw[1] << 16), lw[2] | (lw[3] << 16));
+            if (!a.out) continue;
+          }
+          float* op = a.out + (orow * a.ldo + a.ocol) + n;
           if (vec) {
             if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
             *reinterpret_cast<float4*>(op) = o;
@@ -1224,6 +1239,19 @@ static void launch_tc(const TcConvArgs& a, cudaStream_t st) {
   }
 }
 
+bool conv_tc_takes_pair(const TcConvArgs& a) {
+  if (!(a.tf32 && a.f16 && a.pair && a.nprod == 3 && a.tmA2 && a.tmB2 && a.tmB_c && a.tmB2_c)) return false;
+  if (!(a.Co > 64 && a.cluster < 2 && a.tile_start && a.ntiles_m >= 2)) return false;
+  if (!env_flag("KKX_TC_PERSIST", true)) return false;
+  if (a.force_kernel == 0) {   // small problems take the 64-wide single-tile kernel (see launch_conv_tc)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const long long tiles128 = (long long)a.ntiles_m * ((a.Co + 127) / 128);
+    if (tiles128 < device_sm_count(dev)) return false;
+  }
+  return true;
+}
+
 void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   if (g_dry_run) return;
   if (a0.max_m <= 0 || a0.B <= 0) return;
@@ -1254,7 +1282,7 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
       launch_tc<64, 4, 1>(b, st);
     } else if (a.Co > 64 && persist && a.cluster < 2 && a.tile_start && a.ntiles_m > 0 && a.tmA2 && a.tmB2) {
       // CTA pairs (cta_group::2) for the split-FP16 planes when the weight maps with 64-row boxes exist
-      if (a.pair && a.f16 && a.nprod == 3 && a.tmB_c && a.tmB2_c && a.ntiles_m >= 2) launch_gemm32p2(a, st);
+      if (conv_tc_takes_pair(a)) launch_gemm32p2(a, st);
       else launch_gemm32p(a, st);
     }
     else if (a.Co > 64 && a.cluster == 2 && a.tmB_c && a.tmB2_c) launch_tc<128, 3, 1, 2>(a, st);

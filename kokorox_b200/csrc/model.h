@@ -148,6 +148,9 @@ struct Options {
   int fuse_phases = 1;
   // persistent split-FP16 GEMMs: CTA pairs (tcgen05 cta_group::2, 256 x 128 tiles, half the weight tile per CTA)
   int gemm_pair = 1;
+  // ALBERT: LayerNorm and the FFN GEMM leave their results as split-FP16 operand planes for the next GEMM (no separate
+  // fp32 -> planes pass; the FFN activation never exists in fp32)
+  int fuse_planes = 1;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32
@@ -233,11 +236,22 @@ class Model {
   };
   // Linear / Conv1d on the precision-critical path: split-TF32 tensor cores when precision==1 and
   // the weight has a TcW32, fp32 SIMT otherwise.
+  // Operand planes handed from producer to consumer without the fp32 round trip (split-FP16 path only):
+  //   in_hi / in_lo   the input already exists as fp16 hi / lo planes [Lin.rows, Cpad of the weight] (written by the
+  //                   LayerNorm before, or by the GEMM before): no apply pass;
+  //   out_hi / out_lo ask the GEMM to leave its result as planes [rows, out_ld] for the next GEMM INSTEAD of the fp32
+  //                   output; honoured only by the CTA-pair kernel -- `out_done` tells the caller whether it happened
+  //                   (otherwise the fp32 output was written as usual).
+  struct GemmPlanes {
+    const void* in_hi = nullptr; const void* in_lo = nullptr;
+    void* out_hi = nullptr; void* out_lo = nullptr; int out_ld = 0; bool out_done = false;
+  };
   void gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
             const float* bias, int N, float* out, int ldo, int ocol, int eact = ACT_NONE, int ks = 1,
             int pad = 0, const float* pscale = nullptr, const float* pshift = nullptr, int pact = ACT_NONE,
             float pslope = 0.f, const float* res = nullptr, int ldr = 0, const Level* Lres = nullptr,
-            int res_shift = 0, float oscale = 1.f);
+            int res_shift = 0, float oscale = 1.f, GemmPlanes* pl = nullptr);
+  bool planes_ok() const { return opt.precision == 1 && opt.split_f16 && opt.fuse_planes; }
   float* split_hi_ = nullptr; float* split_lo_ = nullptr; size_t split_cap_ = 0;  // scratch planes (floats) of the current lane
   // Two execution lanes: lane 0 = stream_, lane 1 = stream2_ (forked branches of small batches).  cur_ is the stream
   // every launcher of the forward pass uses; each lane has its own split-TF32 scratch planes.

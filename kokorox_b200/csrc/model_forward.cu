@@ -73,19 +73,22 @@ void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, in
 void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
                  const float* bias, int N, float* out, int ldo, int ocol, int eact, int ks, int pad,
                  const float* pscale, const float* pshift, int pact, float pslope, const float* res, int ldr,
-                 const Level* Lres, int res_shift, float oscale) {
+                 const Level* Lres, int res_shift, float oscale, GemmPlanes* pl) {
   cudaStream_t st = cur_;
+  if (pl) pl->out_done = false;
   if (opt.precision == 1 && w32 && w32->hi && split_hi_ && (size_t)Lin.rows * w32->Cpad <= split_cap_) {
     if (g_dry_run) return;
     const bool f16 = opt.split_f16 && w32->h_hi;
     alignas(64) unsigned char tA[128], tA2[128];
     TcConvArgs a;
     if (f16) {
+      const bool planes_in = pl && pl->in_hi && pl->in_lo && !pscale && pact == ACT_NONE && ks == 1;
       // the scratch planes hold 2-byte elements in this mode (half of the fp32-sized buffers is used)
-      launch_apply_f16x2(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
-                         Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
-      make_tmap_f16(tA, split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
-      make_tmap_f16(tA2, split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      if (!planes_in)
+        launch_apply_f16x2(in, ldi, K, pscale, pshift, pact, pslope, split_hi_, split_lo_, w32->Cpad, Lin.rows,
+                           Lin.d_off, Lin.d_len, Lin.B, Lin.max_len, st);
+      make_tmap_f16(tA, planes_in ? pl->in_hi : split_hi_, w32->Cpad, Lin.rows, w32->Cpad, 128);
+      make_tmap_f16(tA2, planes_in ? pl->in_lo : split_lo_, w32->Cpad, Lin.rows, w32->Cpad, 128);
       a.tmB = w32->tm16_hi; a.tmB2 = w32->tm16_lo; a.f16 = 1;
       a.wscale = w32->wscale16 / kSplitF16Scale;
       if (w32->has_c) { a.tmB_c = w32->tm16_hi_c; a.tmB2_c = w32->tm16_lo_c; a.pair = opt.gemm_pair; }
@@ -107,6 +110,10 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
     a.res = res; a.ldr = ldr; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift; a.oscale = oscale;
     if (long long* tim = arb_timing_buf()) a.timing = tim + 100;   // diagnostics: slots 100..111
     a.tile_start = Lm.d_tiles128; a.ntiles_m = Lm.ntiles128;
+    if (pl && pl->out_hi && pl->out_lo && f16 && N % 4 == 0 && pl->out_ld >= N && ocol == 0 && conv_tc_takes_pair(a)) {
+      a.out_hi = pl->out_hi; a.out_lo = pl->out_lo; a.out_pl_ld = pl->out_ld; a.out = nullptr;
+      pl->out_done = true;
+    }
     launch_conv_tc(a, st);
     return;
   }
@@ -122,7 +129,7 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
 // Token phase: everything at phoneme-token rate, for the whole batch.
 size_t Model::token_arena_bytes() const {
   const size_t R = (size_t)tokL_.rows;
-  return R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048 + 2048 + 2 * 512) * sizeof(float) +
+  return R * (128 + 768 * 4 + 2304 + 2048 + 2048 + 640 * 2 + 512 * 6 + 64 + 16 + 2 * 2048 + 2048 + 2 * 512 + (768 + 2048)) * sizeof(float) +
          (size_t)B_ * (W.sty_pro_n + W.sty_dec_n + 1024) * sizeof(float) + (4 << 20) +
          (opt.attention_umma ? attention_umma_scratch_floats((int)R, B_) * sizeof(float) + 1024 : 0);
 }
@@ -154,7 +161,7 @@ void Model::token_phase(Run& r) {
   // captured once (on the second call with that count) and replayed afterwards -- ~190 launches become one.
   const bool graph_ok = opt.latency_graphs && B_ == 1 && !debug_ && !stats.profile && !stats.check_each && inj_dur_.empty();
   if (graph_ok) {
-    const GraphKey key{tok_len_[0], opt.precision * 8 + opt.attention_umma * 4 + opt.split_f16 * 2 + opt.gemm_pair, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
+    const GraphKey key{tok_len_[0], opt.precision * 16 + opt.attention_umma * 8 + opt.split_f16 * 4 + opt.gemm_pair * 2 + opt.fuse_planes, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
     auto it = graphs_.find(key);
     if (it != graphs_.end() && it->second.exec) {
       r = it->second.run;
@@ -263,11 +270,21 @@ void Model::token_issue(Run& r) {
   float* qkv = A.alloc<float>(R * 2304);
   float* ff = A.alloc<float>(R * 2048);
   float* att_scratch = opt.attention_umma ? A.alloc<float>(attention_umma_scratch_floats((int)R, B)) : nullptr;
+  // operand planes passed between LayerNorm / FFN and the next GEMM (fp16 hi + lo: R x C x 2 x 2 bytes = one float each)
+  const bool pl_ok = planes_ok();
+  void* p768h = pl_ok ? A.alloc_bytes(R * 768 * 2) : nullptr;
+  void* p768l = pl_ok ? A.alloc_bytes(R * 768 * 2) : nullptr;
+  void* p2048h = pl_ok ? A.alloc_bytes(R * 2048 * 2) : nullptr;
+  void* p2048l = pl_ok ? A.alloc_bytes(R * 2048 * 2) : nullptr;
+  bool h_planes = false;      // p768 holds the planes of h
   launch_albert_embed(d_ids_, W.word, W.pos, W.type, W.emb_lnw, W.emb_lnb, e, L.d_off, L.d_len, B,
                       L.max_len, st);
   gemm(L, L, e, 128, 128, W.map_w, &W.t_map, W.map_b, 768, h, 768, 0);
   for (int layer = 0; layer < 12; layer++) {
-    gemm(L, L, h, 768, 768, W.qkv_w, &W.t_qkv, W.qkv_b, 2304, qkv, 2304, 0);
+    GemmPlanes gq;
+    if (h_planes) { gq.in_hi = p768h; gq.in_lo = p768l; }
+    gemm(L, L, h, 768, 768, W.qkv_w, &W.t_qkv, W.qkv_b, 2304, qkv, 2304, 0, ACT_NONE, 1, 0, nullptr, nullptr, ACT_NONE, 0.f,
+         nullptr, 0, nullptr, 0, 1.f, &gq);
     if (att_scratch) launch_attention_umma(qkv, att_scratch, ctx, L.d_off, L.d_len, B, L.max_len, L.rows, st);
     else launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
     gemm(L, L, ctx, 768, 768, W.dense_w, &W.t_dense, W.dense_b, 768, tmp, 768, 0);
@@ -275,11 +292,19 @@ void Model::token_issue(Run& r) {
     ln.x = h; ln.ldx = 768; ln.res = tmp; ln.ldr = 768; ln.w = W.attn_lnw; ln.b = W.attn_lnb;
     ln.eps = 1e-12f; ln.out = h1; ln.ldo = 768; ln.off = L.d_off; ln.len = L.d_len; ln.B = B;
     ln.max_len = L.max_len; ln.C = 768;
+    if (pl_ok) { ln.pl_hi = p768h; ln.pl_lo = p768l; ln.pl_ld = 768; }      // h1 as planes for the FFN GEMM
     launch_layernorm(ln, st);
-    gemm(L, L, h1, 768, 768, W.ffn_w, &W.t_ffn, W.ffn_b, 2048, ff, 2048, 0, ACT_GELU_NEW);
-    gemm(L, L, ff, 2048, 2048, W.ffo_w, &W.t_ffo, W.ffo_b, 768, tmp, 768, 0);
+    GemmPlanes gf;
+    if (pl_ok) { gf.in_hi = p768h; gf.in_lo = p768l; gf.out_hi = p2048h; gf.out_lo = p2048l; gf.out_ld = 2048; }
+    gemm(L, L, h1, 768, 768, W.ffn_w, &W.t_ffn, W.ffn_b, 2048, ff, 2048, 0, ACT_GELU_NEW, 1, 0, nullptr, nullptr, ACT_NONE, 0.f,
+         nullptr, 0, nullptr, 0, 1.f, &gf);
+    GemmPlanes go;
+    if (gf.out_done) { go.in_hi = p2048h; go.in_lo = p2048l; }              // gelu(ffn) exists only as planes
+    gemm(L, L, ff, 2048, 2048, W.ffo_w, &W.t_ffo, W.ffo_b, 768, tmp, 768, 0, ACT_NONE, 1, 0, nullptr, nullptr, ACT_NONE, 0.f,
+         nullptr, 0, nullptr, 0, 1.f, &go);
     ln.x = tmp; ln.res = h1; ln.w = W.full_lnw; ln.b = W.full_lnb; ln.out = h;
-    launch_layernorm(ln, st);
+    launch_layernorm(ln, st);                                                 // h (+ its planes for the next QKV / bert_encoder)
+    h_planes = pl_ok;
   }
   capture("bert", h, 768, 0, 768, L, 0);
 
@@ -288,7 +313,12 @@ void Model::token_issue(Run& r) {
   float* xb = A.alloc<float>(R * 640);
   float* xp = A.alloc<float>(R * 2048);
   float* lo = A.alloc<float>(R * 512);
-  gemm(L, L, h, 768, 768, W.benc_w, &W.t_benc, W.benc_b, 512, xa, 640, 0);
+  {
+    GemmPlanes gb;
+    if (h_planes) { gb.in_hi = p768h; gb.in_lo = p768l; }
+    gemm(L, L, h, 768, 768, W.benc_w, &W.t_benc, W.benc_b, 512, xa, 640, 0, ACT_NONE, 1, 0, nullptr, nullptr, ACT_NONE, 0.f,
+         nullptr, 0, nullptr, 0, 1.f, &gb);
+  }
   capture("d_en", xa, 640, 0, 512, L, 0);
   launch_bcast_cols(d_styles_, 256, 128, 128, xa, 640, 512, L.d_off, L.d_len, B, L.max_len, st);
   launch_bcast_cols(d_styles_, 256, 128, 128, xb, 640, 512, L.d_off, L.d_len, B, L.max_len, st);

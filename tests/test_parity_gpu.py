@@ -454,6 +454,39 @@ def test_round2_kernels_keep_durations_bit_exact(model, oracle, opts, n_tokens, 
         model.set_option("precision", 0)
 
 
+def test_pair_gemm_and_plane_fusion_are_bit_identical(model):
+    """Round-2 GEMM path of the big-batch case: CTA-pair kernel (tcgen05 cta_group::2, "gemm_pair") and operand planes
+    handed from LayerNorm / the FFN GEMM straight to the next GEMM ("fuse_planes").  Both only change WHERE the same
+    arithmetic happens, so a batch large enough to take the pair kernel (>= 148 output tiles per GEMM) must produce the
+    same bits with either switched off -- and each utterance the same bits as when it is run alone (single-tile
+    kernels, no pair, planes from LayerNorm only)."""
+    model.set_noise(None)
+    model.debug_enable(False)
+    model.set_option("precision", 1)
+    try:
+        cases = [synth_case(510 if i % 3 else 200 + 7 * i, 700 + i, 800 + i) for i in range(36)]
+        toks, styles = [c[0] for c in cases], [c[1] for c in cases]
+        speeds = [1.0 + 0.01 * (i % 5) for i in range(36)]
+        outs = {}
+        for pair, planes in ((1, 1), (0, 0), (1, 0), (0, 1)):
+            model.set_option("gemm_pair", pair)
+            model.set_option("fuse_planes", planes)
+            outs[(pair, planes)] = [o.copy() for o in model.infer_batch(toks, styles, speeds)]
+        ref = outs[(0, 0)]
+        for key, got in outs.items():
+            assert len(got) == len(ref)
+            assert all(np.array_equal(x, y) for x, y in zip(ref, got)), f"gemm_pair, fuse_planes = {key} changed the result"
+        model.set_option("gemm_pair", 1)
+        model.set_option("fuse_planes", 1)
+        for i in (0, 1, 17):
+            one = model.infer_one(toks[i], styles[i], speeds[i])
+            assert np.array_equal(one, ref[i]), f"utterance {i} alone differs from the batch"
+    finally:
+        model.set_option("gemm_pair", 1)
+        model.set_option("fuse_planes", 1)
+        model.set_option("precision", 0)
+
+
 def test_phase_fused_upsampling_is_bit_identical(model):
     """"fuse_phases": the 10 + 6 ConvTranspose1d phase convs of the generator as one launch each (phase = fastest grid
     dimension, weights stacked along the map's rows).  Same kernel, same accumulation order -> the same bits."""
