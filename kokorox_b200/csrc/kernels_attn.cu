@@ -355,8 +355,14 @@ size_t attention_umma_scratch_floats(int rows_total, int B) {
   return (size_t)4 * rows_total * 768 + (size_t)2 * B * 768 * kVtPitch;
 }
 
+void attention_umma_planes(float* scratch, int rows_total, int B, float* (&pl)[6]) {
+  const size_t plane = (size_t)rows_total * 768;
+  pl[0] = scratch; pl[1] = pl[0] + plane; pl[2] = pl[1] + plane; pl[3] = pl[2] + plane;
+  pl[4] = pl[3] + plane; pl[5] = pl[4] + (size_t)B * 768 * kVtPitch;
+}
+
 void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
-                           int max_len, int rows_total, cudaStream_t st) {
+                           int max_len, int rows_total, cudaStream_t st, bool planes_ready) {
   if (g_dry_run) return;
   if (max_len > kVtPitch) throw ArgError("launch_attention_umma: more than 512 tokens");
   const size_t plane = (size_t)rows_total * 768;
@@ -366,9 +372,11 @@ void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const i
   int dev = 0;
   cudaGetDevice(&dev);
   once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem)); });
-  dim3 gp((((max_len + 63) & ~63) + 31) / 32, 12, B);
-  attn_prep_kernel<<<gp, 256, 0, st>>>(qkv, qh, ql, kh, kl, vth, vtl, off, len);
-  post_launch("attn_prep", st);
+  if (!planes_ready) {
+    dim3 gp((((max_len + 63) & ~63) + 31) / 32, 12, B);
+    attn_prep_kernel<<<gp, 256, 0, st>>>(qkv, qh, ql, kh, kl, vth, vtl, off, len);
+    post_launch("attn_prep", st);
+  }
   alignas(64) CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl;
   make_tmap_f32(&mQh, qh, 768, rows_total, 768, 128);
   make_tmap_f32(&mQl, ql, 768, rows_total, 768, 128);

@@ -1118,6 +1118,37 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float4 rv[RB];
       load_res(0, rv);                                         // overlaps the wait for the tile
       mbar_wait(gfull_bar, (uint32_t)ti & 1u);
+      if (a.attn_pl[0] && n0 >= 1536) {
+        // QKV projection, V columns: the attention kernel wants V TRANSPOSED per head ([(item, head, d), key], pitch 512,
+        // tf32 hi / lo, zero-filled to a multiple of 64 keys).  The staged tile is read by columns instead: warp fw takes
+        // the tile's dims 32 fw .. 32 fw + 31, a lane one token, so every store covers 32 consecutive keys (128 bytes).
+        const int NR = (mlen + 63) & ~63;
+#pragma unroll 1
+        for (int dl = 0; dl < 32; dl++) {
+          const int cl = fw * 32 + dl;                         // column inside the tile
+          const int cv = n0 - 1536 + cl;                       // V column: head * 64 + d
+          const float bias_c = a.bias ? a.bias[n0 + cl] : 0.f;
+          float* const vh = a.attn_pl[4] + ((size_t)b * 768 + cv) * 512 + m0;
+          float* const vl = a.attn_pl[5] + ((size_t)b * 768 + cv) * 512 + m0;
+          const int chunk = cl >> 2, e4 = cl & 3;
+#pragma unroll
+          for (int tg = 0; tg < 4; tg++) {
+            const int r = tg * 32 + lane;                      // token inside the tile
+            if (m0 + r < NR) {
+              const float raw = stg_f[r * 128 + (((chunk & ~7) | ((chunk ^ r) & 7)) << 2) + e4];
+              const float val = m0 + r < mlen ? fmaf(raw, a.wscale, bias_c) : 0.f;
+              uint32_t hi, lo;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(val));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(val - __uint_as_float(hi)));
+              vh[r] = __uint_as_float(hi);
+              vl[r] = __uint_as_float(lo);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gfree_bar) : "memory");
+        continue;
+      }
 #pragma unroll 1
       for (int i0 = 0; i0 < 32; i0 += RB) {
         float4 v[RB];
@@ -1141,6 +1172,23 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
           o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
           const size_t orow = (size_t)(out_row0 + mm * a.ors + a.oro);
+          if (a.attn_pl[0]) {   // QKV projection, Q (scaled by 1/8 = 1/sqrt(64), exact) and K columns: tf32 hi / lo planes
+            const bool isq = n0 < 768;
+            const float e4[4] = {o.x, o.y, o.z, o.w};
+            float hi4[4], lo4[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float val = isq ? e4[e] * 0.125f : e4[e];
+              uint32_t hi, lo;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(val));
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(val - __uint_as_float(hi)));
+              hi4[e] = __uint_as_float(hi); lo4[e] = __uint_as_float(lo);
+            }
+            const size_t pidx = orow * 768 + (size_t)(isq ? n : n - 768);
+            *reinterpret_cast<float4*>(a.attn_pl[isq ? 0 : 2] + pidx) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+            *reinterpret_cast<float4*>(a.attn_pl[isq ? 1 : 3] + pidx) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            continue;
+          }
           if (a.out_hi) {      // operand planes for the next GEMM (host guarantees Co % 4 == 0, no accumulate)
             const float e4[4] = {o.x, o.y, o.z, o.w};
             uint32_t hw[4], lw[4];

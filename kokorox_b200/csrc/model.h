@@ -241,10 +241,12 @@ class Model {
   //                   LayerNorm before, or by the GEMM before): no apply pass;
   //   out_hi / out_lo ask the GEMM to leave its result as planes [rows, out_ld] for the next GEMM INSTEAD of the fp32
   //                   output; honoured only by the CTA-pair kernel -- `out_done` tells the caller whether it happened
-  //                   (otherwise the fp32 output was written as usual).
+  //                   (otherwise the fp32 output was written as usual);
+  //   attn_scratch    the same for the QKV projection and the planes of launch_attention_umma.
   struct GemmPlanes {
     const void* in_hi = nullptr; const void* in_lo = nullptr;
     void* out_hi = nullptr; void* out_lo = nullptr; int out_ld = 0; bool out_done = false;
+    float* attn_scratch = nullptr;   // QKV projection: leave the result as the attention kernel's operand planes (same rule)
   };
   void gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, int K, const float* w, const TcW32* w32,
             const float* bias, int N, float* out, int ldo, int ocol, int eact = ACT_NONE, int ks = 1,

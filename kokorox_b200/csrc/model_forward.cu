@@ -113,6 +113,10 @@ void Model::gemm(const Level& Lin, const Level& Lm, const float* in, int ldi, in
     if (pl && pl->out_hi && pl->out_lo && f16 && N % 4 == 0 && pl->out_ld >= N && ocol == 0 && conv_tc_takes_pair(a)) {
       a.out_hi = pl->out_hi; a.out_lo = pl->out_lo; a.out_pl_ld = pl->out_ld; a.out = nullptr;
       pl->out_done = true;
+    } else if (pl && pl->attn_scratch && f16 && N == 2304 && eact == ACT_NONE && !res && oscale == 1.f && conv_tc_takes_pair(a)) {
+      attention_umma_planes(pl->attn_scratch, Lm.rows, Lm.B, a.attn_pl);
+      a.out = nullptr;
+      pl->out_done = true;
     }
     launch_conv_tc(a, st);
     return;
@@ -283,9 +287,10 @@ void Model::token_issue(Run& r) {
   for (int layer = 0; layer < 12; layer++) {
     GemmPlanes gq;
     if (h_planes) { gq.in_hi = p768h; gq.in_lo = p768l; }
+    if (pl_ok && att_scratch) gq.attn_scratch = att_scratch;   // Q/8, K, V^T planes straight from the GEMM's final warps
     gemm(L, L, h, 768, 768, W.qkv_w, &W.t_qkv, W.qkv_b, 2304, qkv, 2304, 0, ACT_NONE, 1, 0, nullptr, nullptr, ACT_NONE, 0.f,
          nullptr, 0, nullptr, 0, 1.f, &gq);
-    if (att_scratch) launch_attention_umma(qkv, att_scratch, ctx, L.d_off, L.d_len, B, L.max_len, L.rows, st);
+    if (att_scratch) launch_attention_umma(qkv, att_scratch, ctx, L.d_off, L.d_len, B, L.max_len, L.rows, st, gq.out_done);
     else launch_attention(qkv, ctx, L.d_off, L.d_len, B, L.max_len, st);
     gemm(L, L, ctx, 768, 768, W.dense_w, &W.t_dense, W.dense_b, 768, tmp, 768, 0);
     LnArgs ln;
