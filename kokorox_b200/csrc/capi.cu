@@ -743,6 +743,7 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "fuse_phases") o.fuse_phases = value ? 1 : 0;
     else if (k == "gemm_pair") o.gemm_pair = value ? 1 : 0;
     else if (k == "fuse_planes") o.fuse_planes = value ? 1 : 0;
+    else if (k == "conv_pair") o.conv_pair = value ? 1 : 0;
     else if (k == "fork_max_batch") { if (value < 0 || value > 512) throw ArgError("fork_max_batch must be in 0..512"); o.fork_max_batch = (int)value; }
     else if (k == "max_tokens") { if (value < 512) throw ArgError("max_tokens must be >= 512"); ctx->max_tokens = value; }
     else if (k == "coalesce") {

@@ -1247,6 +1247,183 @@ static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
                                                          *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2_c), b);
 }
 
+// ------------------------------------------------------------------------------------------
+// CTA-pair version of the bf16 implicit-GEMM conv (MODE 0) for the decoder's wide convs (Co a multiple of 256).
+// The single-tile kernel pulls 48 KB per 64-channel K step and CTA out of L2 (A 16 KB, B 32 KB at BN = 256), two CTAs
+// per SM: ~190 B/clk/SM against the ~42 B/clk/SM the L2 delivers chip-wide -- measured 30-45 % of the tensor floor.
+// Here a pair of CTAs computes a 256 x 256 tile with tcgen05.mma.cta_group::2: each CTA loads its own 128 activation
+// rows and HALF of the weight tile (32 KB per K step for twice the rows: a third of the L2 traffic per output row), the
+// kernel is persistent (5-stage ring running across tiles, the same m-tile-pair scheduling as gemm32p2_kernel) and the
+// two 256-column accumulators in TMEM alternate, so a tile's epilogue (per-warp smem transposes, full-line residual
+// loads and stores: gemm32_final) runs under the next tile's MMAs.  Same accumulation order per output element as the
+// single-tile kernel: identical bits.
+constexpr int kCpStages = 5;
+constexpr uint32_t kCpA = 128 * 128, kCpBh = 128 * 128, kCpStage = kCpA + kCpBh;
+constexpr int kCpThreads = 320;    // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kCpSmem = kCpStages * (int)kCpStage + 8 * 4096 + 16 * 8 + 16 + 1024;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCpThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, TcConvArgs a) {
+  constexpr int BN = 256, STAGES = kCpStages, NEPI = 8;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t scr_base = base + STAGES * kCpStage;       // 8 epilogue warps x 4 KB transpose scratch
+  float* const scr_f = reinterpret_cast<float*>(smem_raw + (scr_base - smem_u32(smem_raw)));
+  const uint32_t bar_base = scr_base + 8 * 4096;            // full[5], empty[5], tfull[2], tempty[2]
+  const uint32_t tmem_slot = bar_base + 16 * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (5 + s) * 8; };
+  auto tfull_bar = [&](int j) { return bar_base + (10 + j) * 8; };
+  auto tempty_bar = [&](int j) { return bar_base + (12 + j) * 8; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int kchunks = a.Cpad >> 6;
+  const int num_k = a.ks * kchunks;
+  const int ntm = a.ntiles_m, ntm2 = (ntm + 1) >> 1;
+  const int NT = a.Co / BN;
+  const int total = ntm2 * NT;
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int j = 0; j < 2; j++) { mbar_init(tfull_bar(j), 1); mbar_init(tempty_bar(j), 2 * NEPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int gm2 = a.group_m > 1 ? (a.group_m >> 1) : 1;
+  auto decode = [&](int t, int& b, int& m0, int& n0, bool& valid) {
+    const int g = t / (gm2 * NT), r = t - g * gm2 * NT;
+    const int gsz = min(gm2, ntm2 - g * gm2);
+    const int nt = r / gsz;
+    int mg = 2 * (g * gm2 + (r - nt * gsz)) + (int)rank;
+    valid = mg < ntm;
+    if (!valid) mg = ntm - 1;
+    int lo = 0, hi = a.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.tile_start[mid] <= mg) lo = mid; else hi = mid;
+    }
+    b = lo; m0 = (mg - a.tile_start[lo]) * 128; n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = pair; t < total; t += npairs) {
+        int b, m0, n0; bool valid;
+        decode(t, b, m0, n0, valid);
+        const int row0 = a.in_off[b] + m0 - a.pad;
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          mbar_wait(empty_bar(s), (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
+          const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+          const uint32_t sa = base + s * kCpStage;
+          const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * kCpStage);
+          tma_load_2d_pair(sa, &tmA, c0, row0 + tap * a.dil, lead_full);
+          tma_load_2d_pair(sa + kCpA, &tmBh, tap * a.Cpad + c0, n0 + (int)rank * 128, lead_full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      int g = 0, ti = 0;
+      for (int t = pair; t < total; t += npairs, ti++) {
+        const int buf = ti & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)(ti >> 1)) & 1u) ^ 1u);   // both CTAs' epilogues are done with this accumulator
+        tc_fence_after();
+        const uint32_t td = tmem_base + (uint32_t)(buf * BN);
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
+          tc_fence_after();
+          const uint32_t sa = base + s * kCpStage;
+          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kCpA);
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_f16_pair(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          umma_commit_pair(empty_bar(s));
+        }
+        umma_commit_pair(tfull_bar(buf));
+      }
+    }
+  } else {
+    // epilogue: warp w owns TMEM lane quadrant q = w & 3 (32 rows) and column half hh (128 of the 256 columns)
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
+    const uint32_t lead_bars = mapa_u32(bar_base, 0);
+    int ti = 0;
+    for (int t = pair; t < total; t += npairs, ti++) {
+      int b, m0, n0; bool valid;
+      decode(t, b, m0, n0, valid);
+      const int mlen = valid ? a.m_len[b] : 0;
+      const int buf = ti & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)(ti >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hh * 128);
+#pragma unroll 1
+      for (int h2 = 0; h2 < 2; h2++) {
+        float racc[64];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          uint32_t v[32];
+          tmem_ld32(tq + (uint32_t)(h2 * 64 + c * 32), v);
+#pragma unroll
+          for (int e = 0; e < 32; e++) racc[c * 32 + e] = __uint_as_float(v[e]);
+        }
+        if (h2 == 1) {      // last TMEM read of this tile by this warp: hand the accumulator back
+          tc_fence_before();
+          if (lane == 0) mbar_arrive_cluster(lead_bars + (uint32_t)(12 + buf) * 8);
+        }
+        gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0 + hh * 128 + h2 * 64, 0, q, lane, mlen);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// true when launch_conv_tc runs the bf16 CTA-pair kernel for these arguments
+static bool conv_tc_takes_pair_bf16(const TcConvArgs& a, int nsm) {
+  if (a.tf32 || !a.pair || !a.tmB_c || a.nphase > 1 || a.cluster > 1) return false;
+  if (a.Co < 256 || a.Co % 256 != 0 || !a.tile_start || a.ntiles_m < 2) return false;
+  return (long long)((a.ntiles_m + 1) / 2) * (a.Co / 256) >= nsm / 2;     // at least one tile per pair
+}
+
+static void launch_conv_pair(const TcConvArgs& a, cudaStream_t st) {
+  static DevOnce once;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpSmem)); });
+  const int nsm = device_sm_count(dev);
+  const int total = ((a.ntiles_m + 1) / 2) * (a.Co / 256);
+  int npairs = nsm / 2;
+  if (npairs > total) npairs = total;
+  TcConvArgs b = a;
+  const long long per_tile = 128LL * a.Cpad * 2 * a.ks;               // activation bytes one m-tile pulls through L2
+  long long gm = 24LL * 1000000LL / (per_tile > 0 ? per_tile : 1);
+  if (gm < 8) gm = 8;
+  if (gm > a.ntiles_m) gm = a.ntiles_m;
+  b.group_m = (int)gm;
+  conv_pair_kernel<<<2 * npairs, kCpThreads, kCpSmem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c), b);
+}
+
 template <int BN, int STAGES, int TPC>
 static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (128 * 128 + BN * 128) + 2 * 128 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -1363,7 +1540,10 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   }
   // smem per CTA ~97 KB in every configuration -> two CTAs per SM, so one tile's epilogue overlaps
   // the other's TMA/MMA main loop (TMEM: 2 x 256 columns = the whole 512-column file)
-  if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
+  int pdev = 0;
+  cudaGetDevice(&pdev);
+  if (conv_tc_takes_pair_bf16(a, device_sm_count(pdev))) launch_conv_pair(a, st);   // wide convs of big batches: CTA pairs
+  else if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
   else if (a.Co > 64) launch_tc<128, 2, 0>(a, st);   // 65 KB smem -> three CTAs per SM
   else launch_tc<64, 4, 0>(a, st);
   if (g_launch_stats && g_launch_stats->profile && g_launch_stats->detail) {

@@ -53,6 +53,8 @@ std::vector<std::pair<std::string, std::vector<int>>> kokoro_tensor_specs();
 struct TcW {
   void* w = nullptr;
   alignas(64) unsigned char tmap[128];
+  alignas(64) unsigned char tmap_h[128];     // 128-row boxes: one CTA's half of a 256-wide weight tile (CTA-pair conv)
+  bool has_h = false;
   int Cpad = 0, Ci = 0, Co = 0, ks = 0;
 };
 // split-TF32 weight: tf32-exact hi / lo fp32 planes [Co][ks][Cpad] + TMA descriptors
@@ -151,6 +153,8 @@ struct Options {
   // ALBERT: LayerNorm and the FFN GEMM leave their results as split-FP16 operand planes for the next GEMM (no separate
   // fp32 -> planes pass; the FFN activation never exists in fp32)
   int fuse_planes = 1;
+  // bf16 decoder convs with Co % 256 == 0: CTA pairs (256 x 256 tiles, half the weight tile per CTA, persistent)
+  int conv_pair = 1;
 };
 
 // Device-resident weights of one checkpoint on one GPU: every layout the kernels read (fp32 SIMT, bf16 / split-TF32

@@ -67,6 +67,9 @@ void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, in
   a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lout.d_off; a.ors = ors; a.oro = oro;
   a.res = res; a.ldr = ldr; a.rcol = 0; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift;
   a.oscale = oscale; a.accumulate = accumulate ? 1 : 0;
+  if (w.has_h && opt.conv_pair) {      // CTA-pair kernel for the wide convs (taken when the batch gives every pair a tile)
+    a.tmB_c = w.tmap_h; a.pair = 1; a.tile_start = Lm.d_tiles128; a.ntiles_m = Lm.ntiles128;
+  }
   launch_conv_tc(a, cur_);
 }
 

@@ -468,22 +468,25 @@ def test_pair_gemm_and_plane_fusion_are_bit_identical(model):
         toks, styles = [c[0] for c in cases], [c[1] for c in cases]
         speeds = [1.0 + 0.01 * (i % 5) for i in range(36)]
         outs = {}
-        for pair, planes in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        for pair, planes, cpair in ((1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 0), (1, 1, 0)):
             model.set_option("gemm_pair", pair)
             model.set_option("fuse_planes", planes)
-            outs[(pair, planes)] = [o.copy() for o in model.infer_batch(toks, styles, speeds)]
-        ref = outs[(0, 0)]
+            model.set_option("conv_pair", cpair)       # bf16 decoder convs on CTA pairs (256 x 256 tiles)
+            outs[(pair, planes, cpair)] = [o.copy() for o in model.infer_batch(toks, styles, speeds)]
+        ref = outs[(0, 0, 0)]
         for key, got in outs.items():
             assert len(got) == len(ref)
-            assert all(np.array_equal(x, y) for x, y in zip(ref, got)), f"gemm_pair, fuse_planes = {key} changed the result"
+            assert all(np.array_equal(x, y) for x, y in zip(ref, got)), f"gemm_pair, fuse_planes, conv_pair = {key} changed the result"
         model.set_option("gemm_pair", 1)
         model.set_option("fuse_planes", 1)
+        model.set_option("conv_pair", 1)
         for i in (0, 1, 17):
             one = model.infer_one(toks[i], styles[i], speeds[i])
             assert np.array_equal(one, ref[i]), f"utterance {i} alone differs from the batch"
     finally:
         model.set_option("gemm_pair", 1)
         model.set_option("fuse_planes", 1)
+        model.set_option("conv_pair", 1)
         model.set_option("precision", 0)
 
 
