@@ -879,21 +879,24 @@ static void launch_gemm32p(const TcConvArgs& a, cudaStream_t st) {
 // The two m-tiles of a pair are consecutive entries of the m-tile list (they may belong to different items); an odd
 // list ends with a pair whose second CTA recomputes the last tile and stores nothing.
 //   * the finished tile leaves through shared memory: the 8 drain warps only accumulate chains (registers) and drop the
-//     128 x 128 fp32 result into a 64 KB staging tile; 4 "final" warps apply bias / activation / residual / scale and
+//     128 x 128 fp32 result into a 64 KB staging tile; 6 "final" warps apply bias / activation / residual / scale and
 //     store whole 512-byte rows while the drain warps are already on the next tile.  (With the final phase on the drain
 //     warps the accumulator ring was not drained for ~8 k cycles per tile and the MMA warp spent 13 of its 36 Mcycles
 //     per step waiting for a ring slot.)
 constexpr int kG2Stages = 3;
-constexpr int kG2Threads = 448;    // TMA warp, MMA warp, 8 drain warps, 4 final warps
+// threads: TMA warp, MMA warp, 8 drain warps, NFIN final warps (6: 16 warps x 128 registers fill the register file --
+// registers are granted in steps of 32 per thread, so 18 warps would get 96; 4 is kept for A/B runs in experiment builds)
+constexpr int g2_threads(int nfin) { return (2 + 8 + nfin) * 32; }
 constexpr uint32_t kG2A = 128 * 128, kG2Bh = 64 * 128, kG2Stage = 2 * (kG2A + kG2Bh);
 constexpr uint32_t kG2Stg = 128 * 128 * 4;
 constexpr int kG2Smem = kG2Stages * (int)kG2Stage + (int)kG2Stg + 20 * 8 + 16 + 1024;
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
+template <int NFIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(NFIN), 1)
 gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2h, TcConvArgs a) {
   constexpr int BN = 128, STAGES = kG2Stages;
   constexpr int KE = 64;                                   // K elements per 128-byte span (fp16 planes); one chain per stage
-  constexpr int NEPI = 8, NFIN = 4;
+  constexpr int NEPI = 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + STAGES * kG2Stage;      // finished tile, fp32 [128][128], 16-byte chunks XOR-swizzled by row
@@ -1084,7 +1087,7 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     TCT_FLUSH(8, 4);
   } else {
     // ---- final warps: bias, activation, residual, scale and the stores, one 512-byte row per warp instruction (lane l
-    // owns columns 4l .. 4l+3), rows fw, fw + 4, ... of the staged tile
+    // owns columns 4l .. 4l+3), rows fw, fw + NFIN, ... of the staged tile
     const int fw = warp - (2 + NEPI);
     int ti = 0;
     for (int t = pair; t < total; t += npairs, ti++) {
@@ -1101,14 +1104,14 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       const int out_row0 = a.out_off[b];
       const int res_row0 = a.res ? a.res_off[b] : 0;
-      constexpr int RB = 8;                                    // rows per batch: residual loads of a batch are issued together
+      constexpr int RB = 4;                                    // rows per batch: residual loads of a batch are issued together
       auto res_ptr = [&](int mm) { return a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n; };
       auto load_res = [&](int i0, float4 (&rv)[RB]) {
 #pragma unroll
         for (int i = 0; i < RB; i++) {
           rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int mm = m0 + fw + 4 * (i0 + i);
-          if (a.res && ncol && mm < mlen) {
+          const int mm = m0 + fw + NFIN * (i0 + i);
+          if (a.res && ncol && mm < mlen && fw + NFIN * (i0 + i) < 128) {
             const float* rp = res_ptr(mm);
             if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
             else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
@@ -1121,11 +1124,10 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (a.attn_pl[0] && n0 >= 1536) {
         // QKV projection, V columns: the attention kernel wants V TRANSPOSED per head ([(item, head, d), key], pitch 512,
         // tf32 hi / lo, zero-filled to a multiple of 64 keys).  The staged tile is read by columns instead: warp fw takes
-        // the tile's dims 32 fw .. 32 fw + 31, a lane one token, so every store covers 32 consecutive keys (128 bytes).
+        // every NFIN-th dim of the tile, a lane one token, so every store covers 32 consecutive keys (128 bytes).
         const int NR = (mlen + 63) & ~63;
 #pragma unroll 1
-        for (int dl = 0; dl < 32; dl++) {
-          const int cl = fw * 32 + dl;                         // column inside the tile
+        for (int cl = fw; cl < 128; cl += NFIN) {                // column inside the tile
           const int cv = n0 - 1536 + cl;                       // V column: head * 64 + d
           const float bias_c = a.bias ? a.bias[n0 + cl] : 0.f;
           float* const vh = a.attn_pl[4] + ((size_t)b * 768 + cv) * 512 + m0;
@@ -1150,21 +1152,21 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         continue;
       }
 #pragma unroll 1
-      for (int i0 = 0; i0 < 32; i0 += RB) {
+      for (int i0 = 0; i0 < (128 + NFIN - 1) / NFIN; i0 += RB) {
         float4 v[RB];
 #pragma unroll
         for (int i = 0; i < RB; i++) {
-          const int r = fw + 4 * (i0 + i);
+          const int r = min(fw + NFIN * (i0 + i), 127);        // (rows past the tile are skipped below)
           v[i] = *reinterpret_cast<const float4*>(stg_f + r * 128 + (((lane & ~7) | ((lane ^ r) & 7)) << 2));
         }
-        if (i0 + RB >= 32) {                                   // last read of the staged tile
+        if (i0 + RB >= (128 + NFIN - 1) / NFIN) {             // last read of the staged tile
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gfree_bar) : "memory");
         }
 #pragma unroll
         for (int i = 0; i < RB; i++) {
-          const int mm = m0 + fw + 4 * (i0 + i);
-          if (mm >= mlen || !ncol) continue;
+          const int mm = m0 + fw + NFIN * (i0 + i);
+          if (mm >= mlen || !ncol || fw + NFIN * (i0 + i) >= 128) continue;
           float4 o;
           o.x = fmaf(v[i].x, a.wscale, bb.x); o.y = fmaf(v[i].y, a.wscale, bb.y);
           o.z = fmaf(v[i].z, a.wscale, bb.z); o.w = fmaf(v[i].w, a.wscale, bb.w);
@@ -1215,7 +1217,7 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (n + 3 < a.Co) op[3] = o.w;
           }
         }
-        if (i0 + RB < 32) load_res(i0 + RB, rv);
+        if (i0 + RB < (128 + NFIN - 1) / NFIN) load_res(i0 + RB, rv);
       }
     }
   }
@@ -1227,11 +1229,12 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
+template <int NFIN>
+static void launch_gemm32p2_t(const TcConvArgs& a, cudaStream_t st) {
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(gemm32p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem)); });
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(gemm32p2_kernel<NFIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem)); });
   const int nsm = device_sm_count(dev);
   const int total = ((a.ntiles_m + 1) / 2) * ((a.Co + 127) / 128);
   int npairs = nsm / 2;
@@ -1243,8 +1246,15 @@ static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
   if (gm < 8) gm = 8;
   if (gm > a.ntiles_m) gm = a.ntiles_m;
   b.group_m = (int)gm;
-  gemm32p2_kernel<<<2 * npairs, kG2Threads, kG2Smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c),
-                                                         *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2_c), b);
+  gemm32p2_kernel<NFIN><<<2 * npairs, g2_threads(NFIN), kG2Smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c),
+                                                                 *reinterpret_cast<const CUtensorMap*>(a.tmA2), *reinterpret_cast<const CUtensorMap*>(a.tmB2_c), b);
+}
+static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
+  // 6 final warps: with 4, the GELU + plane split of the FFN GEMM (128 tanh per lane and tile) and the transposed V
+  // pass of the QKV GEMM took longer than the tile's MMAs (ncu: tensor pipe 29 % / 38 % active against 52 % for the
+  // plain GEMMs)
+  static const bool fin4 = env_flag("KKX_G2_FIN4", false);
+  if (fin4) launch_gemm32p2_t<4>(a, st); else launch_gemm32p2_t<6>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------
