@@ -188,6 +188,13 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *                 count (default 1; captured on the second call with a given count)
  *   "fork_max_batch" largest batch whose independent branches (text encoder | ALBERT, F0 | N, harmonic source |
  *                 decoder) run on two streams (default 4; 0 = never).  Results do not depend on either option.
+ *   kernel selection, all default 1 and none of them changes a bit of the result (each names the round-2 kernel it
+ *   switches on; 0 selects the kernel it replaced -- for A/B measurements and the bit-identity tests):
+ *   "attention_umma" (tcgen05 attention), "split_f16" (fp16 instead of tf32 operand planes; fp32-grade either way, but
+ *   not the same bits), "gemm_pair" (split-precision GEMMs on CTA pairs, tcgen05 cta_group::2), "conv_pair" (the
+ *   decoder's wide bf16 convs on CTA pairs), "fuse_planes" (LayerNorm / FFN / QKV GEMM write the next kernel's operand
+ *   planes directly), "fuse_phases" (ConvTranspose1d phases in one launch); "stream_bf16" (default 0) keeps the
+ *   res-block residual stream in bf16.
  * kkx_get_stat keys: "launches", "last_frames", "gpu_us", "precision", "coalesced_batches",
  * "coalesced_requests", "coalesced_largest", "async_batches", "async_requests", "frame_groups",
  * "group_first:<g>" (first item of frame group g of the last run), "weights_sessions" (sessions sharing this

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
 // chunks XOR-swizzled by row: conflict-free both ways, __syncwarp only): afterwards 8 lanes cover one 128-byte row
 // segment, so residual loads and stores are full-line and the bias is one float4 per block.
 __device__ __forceinline__ void gemm32_final(const TcConvArgs& a, float* scr, const float (&racc)[64], int b, int m0, int n0,
-                                       int hh, int q, int lane, int mlen) {
+                                       int hh, int q, int lane, int mlen, int oro, const float* bias) {
   const int rq = lane >> 3, cq = lane & 7;
   const int out_row0 = a.out_off[b];
   const int res_row0 = a.res ? a.res_off[b] : 0;
@@ -588,9 +588,9 @@ __device__ __forceinline__ void gemm32_final(const TcConvArgs& a, float* scr, co
     if (n < a.Co) {
       const bool vec = a.vec4 && (n + 3 < a.Co);
       float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.bias) {
-        if (vec) bb = *reinterpret_cast<const float4*>(a.bias + n);
-        else { bb.x = a.bias[n]; if (n + 1 < a.Co) bb.y = a.bias[n + 1]; if (n + 2 < a.Co) bb.z = a.bias[n + 2]; if (n + 3 < a.Co) bb.w = a.bias[n + 3]; }
+      if (bias) {
+        if (vec) bb = *reinterpret_cast<const float4*>(bias + n);
+        else { bb.x = bias[n]; if (n + 1 < a.Co) bb.y = bias[n + 1]; if (n + 2 < a.Co) bb.z = bias[n + 2]; if (n + 3 < a.Co) bb.w = bias[n + 3]; }
       }
       float4 rv[8];
 #pragma unroll
@@ -598,7 +598,7 @@ __device__ __forceinline__ void gemm32_final(const TcConvArgs& a, float* scr, co
         rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int mm = m0 + q * 32 + rq + 4 * i;
         if (a.res && mm < mlen) {
-          const float* rp = a.res + ((size_t)(res_row0 + ((mm * a.ors + a.oro) >> a.res_shift)) * a.ldr + a.rcol) + n;
+          const float* rp = a.res + ((size_t)(res_row0 + ((mm * a.ors + oro) >> a.res_shift)) * a.ldr + a.rcol) + n;
           if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
           else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
         }
@@ -615,7 +615,7 @@ __device__ __forceinline__ void gemm32_final(const TcConvArgs& a, float* scr, co
         if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
         o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
         o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-        float* op = a.out + ((size_t)(out_row0 + mm * a.ors + a.oro) * a.ldo + a.ocol) + n;
+        float* op = a.out + ((size_t)(out_row0 + mm * a.ors + oro) * a.ldo + a.ocol) + n;
         if (vec) {
           if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
           *reinterpret_cast<float4*>(op) = o;
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kGemm32pThreads, 1) gemm32p_kernel(const __gri
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sfree_bar) : "memory");   // TMEM is free again
 
       // ---- the rest runs while the next tile's pipeline is already going (see gemm32_final)
-      gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0, hh, q, lane, mlen);
+      gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0, hh, q, lane, mlen, a.oro, a.bias);
       TCT(3);
     }
     TCT_FLUSH(8, 4);
@@ -1267,30 +1267,41 @@ static void launch_gemm32p2(const TcConvArgs& a, cudaStream_t st) {
 // two 256-column accumulators in TMEM alternate, so a tile's epilogue (per-warp smem transposes, full-line residual
 // loads and stores: gemm32_final) runs under the next tile's MMAs.  Same accumulation order per output element as the
 // single-tile kernel: identical bits.
-constexpr int kCpStages = 5;
-constexpr uint32_t kCpA = 128 * 128, kCpBh = 128 * 128, kCpStage = kCpA + kCpBh;
+// Phase-fused ConvTranspose1d launches (nphase > 1) are n-tiles like any other: tile (phase, n-tile, m-tile pair) reads
+// the stacked weight rows of its phase, with the phase's tap shift and output row offset.
+// BN is a template parameter, but only 256 is used: 128-wide pair tiles (Co = 128: the noise convs, the stage-1
+// up-sampling) were measured SLOWER than the single-tile kernel (2.40 vs 1.72 ms and 2.06 vs 1.29 ms at 5.75 M output
+// rows, profiles/r2_conv_pair_bn128_v30.txt) -- those convs have K = 64 ... 512 and are bound by the epilogue's stores,
+// where three co-resident single-tile CTAs bring 12 epilogue warps per SM against 8 here.
+template <int BN> struct CpCfg {
+  static constexpr int STAGES = BN == 256 ? 5 : 7;
+  static constexpr uint32_t A = 128 * 128, Bh = (BN / 2) * 128, STAGE = A + Bh;
+  static constexpr int SMEM = STAGES * (int)STAGE + 8 * 4096 + 20 * 8 + 16 + 1024;
+};
 constexpr int kCpThreads = 320;    // TMA warp, MMA warp, 8 epilogue warps
-constexpr int kCpSmem = kCpStages * (int)kCpStage + 8 * 4096 + 16 * 8 + 16 + 1024;
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCpThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, TcConvArgs a) {
-  constexpr int BN = 256, STAGES = kCpStages, NEPI = 8;
+  using Cfg = CpCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, NEPI = 8;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t scr_base = base + STAGES * kCpStage;       // 8 epilogue warps x 4 KB transpose scratch
+  const uint32_t scr_base = base + STAGES * Cfg::STAGE;     // 8 epilogue warps x 4 KB transpose scratch
   float* const scr_f = reinterpret_cast<float*>(smem_raw + (scr_base - smem_u32(smem_raw)));
-  const uint32_t bar_base = scr_base + 8 * 4096;            // full[5], empty[5], tfull[2], tempty[2]
-  const uint32_t tmem_slot = bar_base + 16 * 8;
+  const uint32_t bar_base = scr_base + 8 * 4096;            // full[S], empty[S], tfull[2], tempty[2]
+  const uint32_t tmem_slot = bar_base + 20 * 8;
   auto full_bar = [&](int s) { return bar_base + s * 8; };
-  auto empty_bar = [&](int s) { return bar_base + (5 + s) * 8; };
-  auto tfull_bar = [&](int j) { return bar_base + (10 + j) * 8; };
-  auto tempty_bar = [&](int j) { return bar_base + (12 + j) * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
+  auto tfull_bar = [&](int j) { return bar_base + (2 * STAGES + j) * 8; };
+  auto tempty_bar = [&](int j) { return bar_base + (2 * STAGES + 2 + j) * 8; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int kchunks = a.Cpad >> 6;
   const int num_k = a.ks * kchunks;
   const int ntm = a.ntiles_m, ntm2 = (ntm + 1) >> 1;
-  const int NT = a.Co / BN;
+  const int ntn = a.Co / BN;                                // n-tiles per phase
+  const int NT = ntn * (a.nphase > 1 ? a.nphase : 1);
   const int total = ntm2 * NT;
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
@@ -1313,7 +1324,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int gm2 = a.group_m > 1 ? (a.group_m >> 1) : 1;
-  auto decode = [&](int t, int& b, int& m0, int& n0, bool& valid) {
+  // tile -> (item, m-tile of this CTA, phase, first output channel); n-tiles (all phases) are the outer loop inside a
+  // group of m-tile pairs, so a group's activation tiles are served from L2 for every phase and n-tile
+  auto decode = [&](int t, int& b, int& m0, int& ph, int& n0, bool& valid) {
     const int g = t / (gm2 * NT), r = t - g * gm2 * NT;
     const int gsz = min(gm2, ntm2 - g * gm2);
     const int nt = r / gsz;
@@ -1325,25 +1338,28 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int mid = (lo + hi) >> 1;
       if (a.tile_start[mid] <= mg) lo = mid; else hi = mid;
     }
-    b = lo; m0 = (mg - a.tile_start[lo]) * 128; n0 = nt * BN;
+    b = lo; m0 = (mg - a.tile_start[lo]) * 128;
+    ph = nt / ntn; n0 = (nt - ph * ntn) * BN;
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int g = 0;
       for (int t = pair; t < total; t += npairs) {
-        int b, m0, n0; bool valid;
-        decode(t, b, m0, n0, valid);
-        const int row0 = a.in_off[b] + m0 - a.pad;
+        int b, m0, ph, n0; bool valid;
+        decode(t, b, m0, ph, n0, valid);
+        const int c_pad = a.nphase > 1 ? a.phase_pad[ph] : a.pad;
+        const int row0 = a.in_off[b] + m0 - c_pad;
+        const int wrow = ph * a.Co + n0 + (int)rank * (BN / 2);         // this CTA's half of the (phase-stacked) weight tile
         for (int it = 0; it < num_k; it++, g++) {
           const int s = g % STAGES;
           mbar_wait(empty_bar(s), (((uint32_t)(g / STAGES)) & 1u) ^ 1u);
           const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
-          const uint32_t sa = base + s * kCpStage;
+          const uint32_t sa = base + s * Cfg::STAGE;
           const uint32_t lead_full = mapa_u32(full_bar(s), 0);
-          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * kCpStage);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE);
           tma_load_2d_pair(sa, &tmA, c0, row0 + tap * a.dil, lead_full);
-          tma_load_2d_pair(sa + kCpA, &tmBh, tap * a.Cpad + c0, n0 + (int)rank * 128, lead_full);
+          tma_load_2d_pair(sa + Cfg::A, &tmBh, tap * a.Cpad + c0, wrow, lead_full);
         }
       }
     }
@@ -1360,8 +1376,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = g % STAGES;
           mbar_wait(full_bar(s), ((uint32_t)(g / STAGES)) & 1u);
           tc_fence_after();
-          const uint32_t sa = base + s * kCpStage;
-          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + kCpA);
+          const uint32_t sa = base + s * Cfg::STAGE;
+          const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + Cfg::A);
 #pragma unroll
           for (int k = 0; k < 4; k++) umma_f16_pair(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
           umma_commit_pair(empty_bar(s));
@@ -1370,21 +1386,22 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // epilogue: warp w owns TMEM lane quadrant q = w & 3 (32 rows) and column half hh (128 of the 256 columns)
+    // epilogue: warp w owns TMEM lane quadrant q = w & 3 (32 rows) and column half hh (BN / 2 columns)
     const int q = warp & 3;
     const int hh = (warp - 2) >> 2;
     const uint32_t lead_bars = mapa_u32(bar_base, 0);
     int ti = 0;
     for (int t = pair; t < total; t += npairs, ti++) {
-      int b, m0, n0; bool valid;
-      decode(t, b, m0, n0, valid);
+      int b, m0, ph, n0; bool valid;
+      decode(t, b, m0, ph, n0, valid);
       const int mlen = valid ? a.m_len[b] : 0;
+      const int c_oro = a.nphase > 1 ? a.phase_oro[ph] : a.oro;
       const int buf = ti & 1;
       mbar_wait(tfull_bar(buf), ((uint32_t)(ti >> 1)) & 1u);
       tc_fence_after();
-      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hh * 128);
+      const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + hh * (BN / 2));
 #pragma unroll 1
-      for (int h2 = 0; h2 < 2; h2++) {
+      for (int h2 = 0; h2 < BN / 128; h2++) {
         float racc[64];
 #pragma unroll
         for (int c = 0; c < 2; c++) {
@@ -1393,11 +1410,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 32; e++) racc[c * 32 + e] = __uint_as_float(v[e]);
         }
-        if (h2 == 1) {      // last TMEM read of this tile by this warp: hand the accumulator back
+        if (h2 == BN / 128 - 1) {      // last TMEM read of this tile by this warp: hand the accumulator back
           tc_fence_before();
-          if (lane == 0) mbar_arrive_cluster(lead_bars + (uint32_t)(12 + buf) * 8);
+          if (lane == 0) mbar_arrive_cluster(lead_bars + (uint32_t)(2 * STAGES + 2 + buf) * 8);
         }
-        gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0 + hh * 128 + h2 * 64, 0, q, lane, mlen);
+        gemm32_final(a, scr_f + (warp - 2) * 1024, racc, b, m0, n0 + hh * (BN / 2) + h2 * 64, 0, q, lane, mlen, c_oro, a.bias);
       }
     }
   }
@@ -1409,30 +1426,32 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-// true when launch_conv_tc runs the bf16 CTA-pair kernel for these arguments
+// true when launch_conv_tc runs the bf16 CTA-pair kernel for these arguments (tmB_c: the weight map with 128-row boxes)
 static bool conv_tc_takes_pair_bf16(const TcConvArgs& a, int nsm) {
-  if (a.tf32 || !a.pair || !a.tmB_c || a.nphase > 1 || a.cluster > 1) return false;
+  if (a.tf32 || !a.pair || !a.tmB_c || a.cluster > 1) return false;
   if (a.Co < 256 || a.Co % 256 != 0 || !a.tile_start || a.ntiles_m < 2) return false;
-  return (long long)((a.ntiles_m + 1) / 2) * (a.Co / 256) >= nsm / 2;     // at least one tile per pair
+  return (long long)((a.ntiles_m + 1) / 2) * (a.Co / 256) * (a.nphase > 1 ? a.nphase : 1) >= nsm / 2;     // at least one tile per pair
 }
 
-static void launch_conv_pair(const TcConvArgs& a, cudaStream_t st) {
+template <int BN>
+static void launch_conv_pair_t(const TcConvArgs& a, cudaStream_t st) {
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpSmem)); });
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CpCfg<BN>::SMEM)); });
   const int nsm = device_sm_count(dev);
-  const int total = ((a.ntiles_m + 1) / 2) * (a.Co / 256);
+  const int total = ((a.ntiles_m + 1) / 2) * (a.Co / BN) * (a.nphase > 1 ? a.nphase : 1);
   int npairs = nsm / 2;
   if (npairs > total) npairs = total;
   TcConvArgs b = a;
-  const long long per_tile = 128LL * a.Cpad * 2 * a.ks;               // activation bytes one m-tile pulls through L2
+  const long long per_tile = 128LL * a.Cpad * 2;                      // activation bytes of one m-tile
   long long gm = 24LL * 1000000LL / (per_tile > 0 ? per_tile : 1);
   if (gm < 8) gm = 8;
   if (gm > a.ntiles_m) gm = a.ntiles_m;
   b.group_m = (int)gm;
-  conv_pair_kernel<<<2 * npairs, kCpThreads, kCpSmem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c), b);
+  conv_pair_kernel<BN><<<2 * npairs, kCpThreads, CpCfg<BN>::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA), *reinterpret_cast<const CUtensorMap*>(a.tmB_c), b);
 }
+static void launch_conv_pair(const TcConvArgs& a, cudaStream_t st) { launch_conv_pair_t<256>(a, st); }
 
 template <int BN, int STAGES, int TPC>
 static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {

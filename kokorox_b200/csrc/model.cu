@@ -273,7 +273,7 @@ TcW WeightSet::make_tc(const std::vector<float>& w, int Co, int ks, int Ci) {
   device_bytes += h.size() * 2;
   KKX_CUDA(cudaMemcpy(t.w, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
   make_tmap_bf16(t.tmap, t.w, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, tc_box_n(Co));
-  if (Co >= 256 && Co % 256 == 0) {
+  if (Co >= 128 && Co % 128 == 0) {
     make_tmap_bf16(t.tmap_h, t.w, (long long)ks * t.Cpad, Co, (long long)ks * t.Cpad, 128);
     t.has_h = true;
   }

@@ -53,8 +53,11 @@ std::vector<std::pair<std::string, std::vector<int>>> kokoro_tensor_specs();
 struct TcW {
   void* w = nullptr;
   alignas(64) unsigned char tmap[128];
-  alignas(64) unsigned char tmap_h[128];     // 128-row boxes: one CTA's half of a 256-wide weight tile (CTA-pair conv)
+  // one CTA's half (128-row boxes) of a 256-wide weight tile for the CTA-pair conv; exists when the map's row count
+  // (phase-stacked weights: all phases) is a multiple of 128
+  alignas(64) unsigned char tmap_h[128];
   bool has_h = false;
+  const void* pair_map(int co_tile) const { return co_tile >= 256 && co_tile % 256 == 0 && has_h ? tmap_h : nullptr; }
   int Cpad = 0, Ci = 0, Co = 0, ks = 0;
 };
 // split-TF32 weight: tf32-exact hi / lo fp32 planes [Co][ks][Cpad] + TMA descriptors

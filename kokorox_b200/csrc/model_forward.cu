@@ -67,8 +67,8 @@ void Model::tc_conv(Arena& A, const void* abuf, int rows_total, const TcW& w, in
   a.bias = bias; a.out = out; a.ldo = ldo; a.ocol = ocol; a.out_off = Lout.d_off; a.ors = ors; a.oro = oro;
   a.res = res; a.ldr = ldr; a.rcol = 0; a.res_off = Lres ? Lres->d_off : nullptr; a.res_shift = res_shift;
   a.oscale = oscale; a.accumulate = accumulate ? 1 : 0;
-  if (w.has_h && opt.conv_pair) {      // CTA-pair kernel for the wide convs (taken when the batch gives every pair a tile)
-    a.tmB_c = w.tmap_h; a.pair = 1; a.tile_start = Lm.d_tiles128; a.ntiles_m = Lm.ntiles128;
+  if (opt.conv_pair && w.pair_map(w.Co)) {      // CTA-pair kernel (taken when the batch gives every pair a tile)
+    a.tmB_c = w.pair_map(w.Co); a.pair = 1; a.tile_start = Lm.d_tiles128; a.ntiles_m = Lm.ntiles128;
   }
   launch_conv_tc(a, cur_);
 }
@@ -778,6 +778,9 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     a.bias = W.ups0_b; a.out = x0; a.ldo = 256; a.ocol = 0; a.out_off = G20.d_off; a.ors = 10;
     a.nphase = 10;
     for (int ph = 0; ph < 10; ph++) { const int q0 = ph < 5 ? 1 : 0; a.phase_pad[ph] = -q0; a.phase_oro[ph] = q0 * 10 + ph - 5; }
+    if (opt.conv_pair && W.tups0_all.pair_map(256)) {
+      a.tmB_c = W.tups0_all.pair_map(256); a.pair = 1; a.tile_start = FR2.d_tiles128; a.ntiles_m = FR2.ntiles128;
+    }
     launch_conv_tc(a, st);
   } else
   for (int ph = 0; ph < 10; ph++) {  // ConvTranspose1d(512,256,k20,s10,p5) as 10 two-tap phase convs
