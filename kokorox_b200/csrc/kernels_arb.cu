@@ -115,9 +115,10 @@ struct TileCur {
 // iteration moves 10 B: conv1 reads bf16 x (SB = 1), conv2 reads the bf16 residual and writes either the next bf16 x
 // (SB = 1) or -- last iteration -- the fp32 block output (SB = 2).  The AdaIN statistics still come from the fp32
 // accumulator, before any rounding.
-template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0>
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0, bool PB = false>
 __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_constant__ CUtensorMap tmB, ArbConvArgs a) {
   static_assert(SB == 0 || (!POST && (CONV2 || SB == 1)), "stream-bf16 variants: conv1 SB=1, conv2 SB=1 (bf16 out) / SB=2 (fp32 out)");
+  static_assert(!PB || (T && !CONV2 && !POST && SB == 0 && MSUB == 2), "balanced-producer variant: conv1, transposed accumulator, fp32 input");
   constexpr bool XIN_BF = CONV2 || SB != 0;          // element type of the operand the producers read
   constexpr bool OUT_BF = !CONV2 || SB == 1;         // epilogue writes bf16 (conv1 always; conv2 when the stream stays bf16)
   static_assert(!T || (BN == 128 && (MSUB == 2 || MSUB == 4)), "transposed mode: C = 128, 256- or 512-row tiles");
@@ -132,10 +133,13 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   // conv1 in transposed mode (trivial epilogue, producer-bound) was measured: no gain (1.14 / 1.35 / 1.61 ms vs
   // 1.20 / 1.29 / 1.63 ms at k = 3 / 7 / 11) -- the producers are limited by the shared-memory port they share
   // with the tensor pipe's operand reads, not by their thread count.
-  constexpr int NEW = 8;                                    // epilogue warps (4 is supported by the transposed epilogue)
-  constexpr int NPW = 14 - NEW;                             // producer warps
+  // conv1 in transposed mode (trivial epilogue, producer-bound) can run 4 epilogue + 8 producer warps (+ 2 idle) so that
+  // every scheduler carries two producer warps (with 8 + 6, schedulers 2 and 3 carry two producer warps each and a third
+  // of the Snake sines: MUFU-bound).  Selected per launch by the PB template flag.
+  constexpr int NEW = PB ? 4 : 8;                           // epilogue warps (4 is supported by the transposed epilogue)
+  constexpr int NPW = PB ? 8 : 14 - NEW;                    // producer warps
   constexpr int kProdThreads = NPW * 32;
-  constexpr int kProdRows = kProdThreads / 8;               // rows per producer pass (24 or 40: multiples of 8)
+  constexpr int kProdRows = kProdThreads / 8;               // rows per producer pass (24 or 32: multiples of 8)
   using Cfg = ArbCfg<BN, MSUB, T>;
   constexpr int KCH = Cfg::KCH, NA = Cfg::NA, NB = Cfg::NB, PITCH = Cfg::PITCH;
   constexpr int MT = MSUB * 128;
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
       }
     }
     TIM_FLUSH(8, 9);
-  } else {
+  } else if (warp < 2 + NEW + NPW) {
     // ------------------------------------------------------------------ operand producers
     // y = snake(x*sc + sh) = ial * (u + sin(u)^2), u = x*(al*sc) + al*sh: three per-channel coefficients,
     // cached in smem per item.  Loads run one group (4 passes of 24 rows) ahead of the transform through
@@ -604,8 +608,8 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     const int pt = threadIdx.x - (2 + NEW) * 32;   // 0..kProdThreads-1
     const int cg = pt & 7;                  // 8-channel group inside the 64-channel chunk
     const int rl = pt >> 3;                 // row lane 0..23
-    constexpr int GP = 4;
-    constexpr int GR = GP * kProdRows;      // rows per load group (96 or 160: multiples of 8 -> constant swizzle phase)
+    constexpr int GP = PB ? 3 : 4;
+    constexpr int GR = GP * kProdRows;      // rows per load group (96: a multiple of 8 -> constant swizzle phase)
     const int ra_used = MT + 2 * pad;       // <= Cfg::RA
     const int ngc = (ra_used + GR - 1) / GR;                 // load groups per chunk
     float* const coef = reinterpret_cast<float*>(gbase + (coef_base - base));   // [3][BN]: al*sc, al*sh, 1/al
@@ -748,16 +752,16 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
   }
 }
 
-template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0>
+template <int BN, int MSUB, bool CONV2, bool T, bool POST = false, int SB = 0, bool PB = false>
 void launch_arb_t(const ArbConvArgs& a, cudaStream_t st) {
   using Cfg = ArbCfg<BN, MSUB, T>;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); });
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); });
   const int nsm = device_sm_count(dev);
   const int grid = a.total_tiles < nsm ? a.total_tiles : nsm;
-  arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  arb_conv_kernel<BN, MSUB, CONV2, T, POST, SB, PB><<<grid, kArbThreads, Cfg::SMEM, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 }  // namespace
@@ -826,7 +830,12 @@ void launch_arb_conv(const ArbConvArgs& a, cudaStream_t st) {
   } else if (variant == 2) {
     if (a.in_bf16) launch_arb_t<128, 4, true, true>(a, st); else launch_arb_t<128, 4, false, true>(a, st);
   } else if (variant == 1) {
-    if (a.in_bf16) launch_arb_t<128, 2, true, true>(a, st); else launch_arb_t<128, 2, false, true>(a, st);
+    // conv1: 4 epilogue + 8 producer warps, two producer warps on every scheduler -- measured against 8 + 6 on one box
+    // (profiles/r2_arb_balanced_producers_v32.txt): k = 3 1.45 -> 1.15 ms, k = 7 1.50 -> 1.25 ms, k = 11 unchanged
+    static const bool pb = env_flag("KKX_ARB_PB", true);
+    if (a.in_bf16) launch_arb_t<128, 2, true, true>(a, st);
+    else if (pb) launch_arb_t<128, 2, false, true, false, 0, true>(a, st);
+    else launch_arb_t<128, 2, false, true>(a, st);
   } else if (a.C == 128) {
     if (a.in_bf16) launch_arb_t<128, 2, true, false>(a, st); else launch_arb_t<128, 2, false, false>(a, st);
   } else {
