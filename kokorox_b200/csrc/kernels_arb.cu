@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kArbThreads, 1) arb_conv_kernel(const __grid_c
     const int pt = threadIdx.x - (2 + NEW) * 32;   // 0..kProdThreads-1
     const int cg = pt & 7;                  // 8-channel group inside the 64-channel chunk
     const int rl = pt >> 3;                 // row lane 0..23
-    constexpr int GP = PB ? 3 : 4;
+    constexpr int GP = PB ? 3 : 4;         // (bf16-input producers with 6 passes per group, 18 instead of 12 KB in flight: no change, v34)
     constexpr int GR = GP * kProdRows;      // rows per load group (96: a multiple of 8 -> constant swizzle phase)
     const int ra_used = MT + 2 * pad;       // <= Cfg::RA
     const int ngc = (ra_used + GR - 1) / GR;                 // load groups per chunk

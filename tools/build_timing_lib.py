@@ -17,6 +17,11 @@ flags = b.FLAGS + ["-DKKX_EXPERIMENTS"] + (["-DKKX_TC_TIMING", "-DKKX_ARB_TIMING
 if os.environ.get("KKX_NO_COUNTERS") == "1":
     OUT = os.path.join(b.OUT_DIR, "libkkx_exp.so")          # experiment switches only (no cycle counters in the kernels)
     OBJ = "/tmp/kkx_exp_objs"
+    extra = os.environ.get("KKX_EXP_DEFS", "").split()        # e.g. KKX_EXP_DEFS="-DKKX_ARB_GP6" -> libkkx_exp2.so
+    if extra:
+        flags += extra
+        OUT = os.path.join(b.OUT_DIR, "libkkx_exp2.so")
+        OBJ = "/tmp/kkx_exp2_objs"
     os.makedirs(OBJ, exist_ok=True)
 
 
