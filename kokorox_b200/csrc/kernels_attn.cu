@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict_
 constexpr uint32_t kQPlane = 2 * 128 * 128;            // one Q plane: two K-chunks of [128 rows x 32 floats] = 32 KB
 constexpr uint32_t kTilePlane = 2 * 64 * 128;          // one K / V^T plane of a 64-key tile: two chunks of [64 x 32] = 16 KB
 constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 64 KB
-constexpr int kAttnSmem = 2 * kQPlane + 2 * kStage + 16 * 8 + 16 + 1024;
+constexpr int kAttnSmem = 2 * kQPlane + 2 * kStage + 20 * 8 + 16 + 1024;
 constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 384;   // P buffer pb: hi at kColP + 128 pb, lo 64 columns further
 
 __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
@@ -141,14 +141,19 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   const uint32_t st0 = base + 2 * kQPlane;
   const uint32_t bar_base = st0 + 2 * kStage;
   const uint32_t q_full = bar_base;
-  auto full_bar = [&](int s) { return bar_base + (1 + s) * 8; };
-  auto empty_bar = [&](int s) { return bar_base + (3 + s) * 8; };
+  // K and V^T of a stage have their own full / empty barriers: K_j is free again as soon as S_j has been computed,
+  // V^T_j only after P_j V_j -- with one barrier pair per stage every reload had less than one tile period to arrive,
+  // and the kernel ran at the latency of a 64 KB TMA stage per tile (tensor pipe 26 % active, softmax not the limit)
+  auto fullk_bar = [&](int s) { return bar_base + (1 + s) * 8; };
+  auto emptyk_bar = [&](int s) { return bar_base + (3 + s) * 8; };
   auto sfull_bar = [&](int i) { return bar_base + (5 + i) * 8; };
   auto sfree_bar = [&](int i) { return bar_base + (7 + i) * 8; };
   auto pfull_bar = [&](int i) { return bar_base + (9 + i) * 8; };
   auto ofull_bar = [&](int i) { return bar_base + (11 + i) * 8; };
   auto ofree_bar = [&](int i) { return bar_base + (13 + i) * 8; };
-  const uint32_t tmem_slot = bar_base + 16 * 8;
+  auto fullv_bar = [&](int s) { return bar_base + (15 + s) * 8; };
+  auto emptyv_bar = [&](int s) { return bar_base + (17 + s) * 8; };
+  const uint32_t tmem_slot = bar_base + 20 * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -157,7 +162,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVh) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; s++) {
-      mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
+      mbar_init(fullk_bar(s), 1); mbar_init(emptyk_bar(s), 1); mbar_init(fullv_bar(s), 1); mbar_init(emptyv_bar(s), 1);
       mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 4);
       mbar_init(pfull_bar(s), 4); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 4);
     }
@@ -182,18 +187,34 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
         tma_load_2d(q_h + c * (kQPlane / 2), &tmQh, h * 64 + 32 * c, qrow, q_full);
         tma_load_2d(q_l + c * (kQPlane / 2), &tmQl, h * 64 + 32 * c, qrow, q_full);
       }
-      for (int j = 0; j < nt; j++) {
+      auto load_k = [&](int j) {
         const int s = j & 1;
-        mbar_wait(empty_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        mbar_wait(emptyk_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
         const uint32_t sa = st0 + s * kStage;
-        mbar_expect_tx(full_bar(s), kStage);
+        mbar_expect_tx(fullk_bar(s), 2 * kTilePlane);
         for (int c = 0; c < 2; c++) {
           const uint32_t co = c * (kTilePlane / 2);
-          tma_load_2d(sa + co, &tmKh, h * 64 + 32 * c, krow0 + j * 64, full_bar(s));
-          tma_load_2d(sa + kTilePlane + co, &tmKl, h * 64 + 32 * c, krow0 + j * 64, full_bar(s));
-          tma_load_2d(sa + 2 * kTilePlane + co, &tmVh, j * 64 + 32 * c, vrow, full_bar(s));
-          tma_load_2d(sa + 3 * kTilePlane + co, &tmVl, j * 64 + 32 * c, vrow, full_bar(s));
+          tma_load_2d(sa + co, &tmKh, h * 64 + 32 * c, krow0 + j * 64, fullk_bar(s));
+          tma_load_2d(sa + kTilePlane + co, &tmKl, h * 64 + 32 * c, krow0 + j * 64, fullk_bar(s));
         }
+      };
+      auto load_v = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(emptyv_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        const uint32_t sa = st0 + s * kStage;
+        mbar_expect_tx(fullv_bar(s), 2 * kTilePlane);
+        for (int c = 0; c < 2; c++) {
+          const uint32_t co = c * (kTilePlane / 2);
+          tma_load_2d(sa + 2 * kTilePlane + co, &tmVh, j * 64 + 32 * c, vrow, fullv_bar(s));
+          tma_load_2d(sa + 3 * kTilePlane + co, &tmVl, j * 64 + 32 * c, vrow, fullv_bar(s));
+        }
+      };
+      // issue order = the order in which the MMA warp frees the buffers (S_0, S_1, PV_0, S_2, PV_1, ...):
+      // K_0, K_1, V_0, K_2, V_1, K_3, V_2, ...
+      load_k(0);
+      for (int j = 0; j < nt; j++) {
+        if (j + 1 < nt) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 1) {
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       tc_fence_after();
       auto issue_s = [&](int j) {                      // S_j = (Q/8) K_j^T, small terms first (as the mma.sync kernel)
         const int s = j & 1;
-        mbar_wait(full_bar(s), ((uint32_t)(j >> 1)) & 1u);
+        mbar_wait(fullk_bar(s), ((uint32_t)(j >> 1)) & 1u);
         tc_fence_after();
         if (j >= 2) {                                  // the softmax warps have read S_{j-2} out of this buffer
           mbar_wait(sfree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
@@ -224,11 +245,13 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           }
         }
         umma_commit(sfull_bar(s));
+        umma_commit(emptyk_bar(s));                    // K_j is consumed
       };
       issue_s(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
         const int s = j & 1;                           // stage, P buffer and O buffer of tile j
+        mbar_wait(fullv_bar(s), ((uint32_t)(j >> 1)) & 1u);   // V^T_j has landed
         mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);   // P_j is in TMEM
         tc_fence_after();
         if (j >= 2) {                                  // O_{j-2} has been read out of this O buffer
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           umma_tf32_ts(t_o, t_ph + 8u * kk, vh, idesc, 1u);
         }
         umma_commit(ofull_bar(s));
-        umma_commit(empty_bar(s));                     // K_j and V^T_j are consumed
+        umma_commit(emptyv_bar(s));                    // V^T_j is consumed
       }
     }
   } else {
