@@ -932,6 +932,7 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
     if (fits(1)) launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st);
     else if (fits(2)) launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st);
     else if (fits(4)) launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st);
+    else if (fits(6)) launch_lstm_cluster<6>(xproj, whhT, out, ldo, ocol, off, len, B, st);     // 40 items (first frame group of B = 64) -> 14 clusters
     else if (fits(8)) launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);
     else if (fits(10)) launch_lstm_cluster<10>(xproj, whhT, out, ldo, ocol, off, len, B, st);   // 64 items -> 14 clusters
     else if (fits(12)) launch_lstm_cluster<12>(xproj, whhT, out, ldo, ocol, off, len, B, st);
