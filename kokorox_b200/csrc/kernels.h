@@ -189,6 +189,7 @@ void launch_attention(const float* qkv, float* ctx, const int* off, const int* l
 // operand of the second MMA.  scratch: attention_umma_scratch_floats(rows_total, B) floats (tf32 hi/lo planes of
 // Q/8, K and the transposed V); rows_total = rows of the packed qkv / ctx matrices (Level.rows).
 size_t attention_umma_scratch_floats(int rows_total, int B);
+void attention_timing_dump();   // diagnostics (-DKKX_TC_TIMING builds): role cycle counters of attn_umma_kernel; no-op otherwise
 // planes_ready: the QKV GEMM already wrote the operand planes into `scratch` (TcConvArgs::attn_pl); qkv is not read.
 void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
                            int max_len, int rows_total, cudaStream_t st, bool planes_ready = false);

@@ -23,10 +23,24 @@
 //   floating-point operations is unchanged), so the tensor pipe works under the exponentials.
 // TMEM columns: S0 0..63, S1 64..127, P_hi/P_lo buffer 0 128..255, buffer 1 256..383, O0 384..447, O1 448..511.
 #include "kernels.h"
+#include <cstdio>
 #include <cuda.h>
 #include "tc_ptx.cuh"
 
 namespace kkx {
+
+// Optional per-role phase timing (-DKKX_TC_TIMING, diagnostics only): the MMA thread and one softmax thread of CTA
+// (0, 0, 0) of every launch attribute the cycles between consecutive ticks to a slot of g_attn_tim.
+#ifdef KKX_TC_TIMING
+__device__ unsigned long long g_attn_tim[24];
+#define ATT_DECL(cond) long long att_acc[8] = {0}; long long att_last = clock64(); const bool att_on = (cond) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0
+#define ATT(slot) do { if (att_on) { const long long now_ = clock64(); att_acc[slot] += now_ - att_last; att_last = now_; } } while (0)
+#define ATT_FLUSH(base) do { if (att_on) for (int i_ = 0; i_ < 8; i_++) atomicAdd(g_attn_tim + (base) + i_, (unsigned long long)att_acc[i_]); } while (0)
+#else
+#define ATT_DECL(cond)
+#define ATT(slot)
+#define ATT_FLUSH(base)
+#endif
 
 namespace {
 __device__ __forceinline__ uint32_t to_tf32(float v) {
@@ -220,16 +234,20 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      ATT_DECL(true);
       mbar_wait(q_full, 0u);
       tc_fence_after();
+      ATT(0);
       auto issue_s = [&](int j) {                      // S_j = (Q/8) K_j^T, small terms first (as the mma.sync kernel)
         const int s = j & 1;
         mbar_wait(fullk_bar(s), ((uint32_t)(j >> 1)) & 1u);
         tc_fence_after();
+        ATT(1);
         if (j >= 2) {                                  // the softmax warps have read S_{j-2} out of this buffer
           mbar_wait(sfree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
           tc_fence_after();
         }
+        ATT(2);
         const uint32_t sa = st0 + s * kStage;
         const uint32_t t_s = tmem_base + kColS0 + 64u * (uint32_t)s;
 #pragma unroll
@@ -246,18 +264,22 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
         }
         umma_commit(sfull_bar(s));
         umma_commit(emptyk_bar(s));                    // K_j is consumed
+        ATT(3);
       };
       issue_s(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
         const int s = j & 1;                           // stage, P buffer and O buffer of tile j
         mbar_wait(fullv_bar(s), ((uint32_t)(j >> 1)) & 1u);   // V^T_j has landed
+        ATT(4);
         mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);   // P_j is in TMEM
         tc_fence_after();
+        ATT(5);
         if (j >= 2) {                                  // O_{j-2} has been read out of this O buffer
           mbar_wait(ofree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
           tc_fence_after();
         }
+        ATT(6);
         const uint32_t sa = st0 + s * kStage;
         const uint32_t t_o = tmem_base + kColO + 64u * (uint32_t)s;
         const uint32_t t_ph = tmem_base + kColP + 128u * (uint32_t)s, t_pl = t_ph + 64u;
@@ -273,7 +295,9 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
         }
         umma_commit(ofull_bar(s));
         umma_commit(emptyv_bar(s));                    // V^T_j is consumed
+        ATT(7);
       }
+      ATT_FLUSH(0);
     }
   } else {
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
@@ -283,10 +307,13 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     float o[64];
 #pragma unroll
     for (int e = 0; e < 64; e++) o[e] = 0.f;
+    ATT_DECL(warp == 2 && lane == 0);
     for (int j = 0; j < nt; j++) {
       const int s = j & 1;
+      ATT(7);
       mbar_wait(sfull_bar(s), ((uint32_t)(j >> 1)) & 1u);
       tc_fence_after();
+      ATT(0);
       float sc[64];
       {
         uint32_t v[64];
@@ -297,6 +324,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sfree_bar(s));
+      ATT(1);
       // key-padding mask + online softmax, all in this thread
       const int kbase = j * 64;
       float cm = -INFINITY;
@@ -312,6 +340,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       for (int e = 0; e < 64; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
       l = l * corr + ps;
       m = mn;
+      ATT(2);
       // P_j -> TMEM as tf32 hi / lo (A operand of the second MMA).  MMA_{j-2} has finished reading this P buffer:
       // this thread waited for its O tile in the previous iteration.
 #pragma unroll
@@ -330,12 +359,14 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar(s));
+      ATT(3);
       // fold in O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new running maximum: the same
       // operations in the same order as add-after-rescale inside one iteration
       if (j >= 1) {
         const int so = (j - 1) & 1;
         mbar_wait(ofull_bar(so), ((uint32_t)((j - 1) >> 1)) & 1u);
         tc_fence_after();
+        ATT(4);
         uint32_t v[64];
         tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
         tc_fence_before();
@@ -346,6 +377,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       }
 #pragma unroll
       for (int e = 0; e < 64; e++) o[e] *= corr;
+      ATT(5);
     }
     {
       const int so = (nt - 1) & 1;
@@ -364,6 +396,8 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       for (int e = 0; e < 64; e += 4)
         *reinterpret_cast<float4*>(dst + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
     }
+    ATT(6);
+    ATT_FLUSH(8);
   }
   tc_fence_before();
   __syncthreads();
@@ -373,6 +407,19 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   }
 }
 }  // namespace
+
+void attention_timing_dump() {
+#ifdef KKX_TC_TIMING
+  unsigned long long h[24] = {0};
+  cudaMemcpyFromSymbol(h, g_attn_tim, sizeof h);
+  unsigned long long z[24] = {0};
+  cudaMemcpyToSymbol(g_attn_tim, z, sizeof z);
+  fprintf(stderr, "[attention timing, CTA (0,0,0) of every launch] (kcycles) MMA wait_q %.1f wait_K %.1f wait_sfree %.1f issue_S %.1f wait_V %.1f wait_P %.1f wait_ofree %.1f issue_PV %.1f |"
+          " SOFTMAX wait_S %.1f ld+arrive %.1f mask+exp %.1f split+st_P %.1f wait_O %.1f fold %.1f final %.1f loop %.1f\n",
+          h[0] / 1e3, h[1] / 1e3, h[2] / 1e3, h[3] / 1e3, h[4] / 1e3, h[5] / 1e3, h[6] / 1e3, h[7] / 1e3,
+          h[8] / 1e3, h[9] / 1e3, h[10] / 1e3, h[11] / 1e3, h[12] / 1e3, h[13] / 1e3, h[14] / 1e3, h[15] / 1e3);
+#endif
+}
 
 size_t attention_umma_scratch_floats(int rows_total, int B) {
   return (size_t)4 * rows_total * 768 + (size_t)2 * B * 768 * kVtPitch;

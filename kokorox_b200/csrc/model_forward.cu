@@ -34,6 +34,7 @@ ConvArgs gemm_args(const Level& L, const float* in, int ldi, int K, const float*
 
 void arb_timing_dump() {
   if (!g_arb_timing) return;
+  attention_timing_dump();
   long long h[128];
   cudaDeviceSynchronize();
   cudaMemcpy(h, g_arb_timing, sizeof h, cudaMemcpyDeviceToHost);
