@@ -64,10 +64,10 @@ struct TcConvArgs {
   // [rows, out_pl_ld] (hi / lo halves of 16 * value, like launch_apply_f16x2) for the GEMM that consumes it next
   void* out_hi = nullptr; void* out_lo = nullptr; int out_pl_ld = 0;
   // persistent CTA-pair kernel only, QKV projection of ALBERT (Co = 2304): write the result directly as the attention
-  // kernel's operand planes (kernels_attn.cu: tf32 hi / lo of Q/8 and K, row-major [rows, 768], and of V transposed
-  // per head, [(item, head, d), key] with pitch 512 and zero-filled to a multiple of 64 keys) instead of fp32:
+  // kernel's operand planes (kernels_attn.cu: fp16 hi / lo of 2 q and 16 k, row-major [rows, 768], and of 16 v
+  // transposed per head, [(item, head, d), key] with pitch 512 and zero-filled to a multiple of 64 keys) instead of fp32:
   // attn_pl = {qh, ql, kh, kl, vth, vtl}
-  float* attn_pl[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* attn_pl[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int pair = 0;                  // persistent split-FP16 GEMM: CTA pairs (cta_group::2, 256 x 128 tiles) when tmB_c / tmB2_c exist
   int force_kernel = 0;          // tests: 1 = never take the small-problem (64-wide single-tile) kernel
   // Phase-fused ConvTranspose1d (bf16 path, MODE 0): `nphase` two-tap phase convs in ONE launch.  The weights of the
@@ -194,7 +194,7 @@ void attention_timing_dump();   // diagnostics (-DKKX_TC_TIMING builds): role cy
 void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
                            int max_len, int rows_total, cudaStream_t st, bool planes_ready = false);
 // the six plane pointers inside an attention scratch buffer: qh, ql, kh, kl, vth, vtl
-void attention_umma_planes(float* scratch, int rows_total, int B, float* (&pl)[6]);
+void attention_umma_planes(float* scratch, int rows_total, int B, void* (&pl)[6]);
 
 // Bidirectional LSTM recurrence, H=256.  xproj [rows, 2048] = x W_ih^T + b_ih + b_hh for
 // (fwd i,f,g,o | bwd i,f,g,o); whhT [2][256][1024] (k-major); out [rows, ldo] cols ocol..+512.

@@ -3,25 +3,31 @@
 // north_star: "the ALBERT/PL-BERT encoder ... use tcgen05/TMEM tiles fed by TMA".  Round 1 ran attention on legacy
 // mma.sync fragments (kernels_dense.cu attention_tc_kernel, kept as the fallback); this is the Blackwell-native form.
 // The path feeds the duration predictor, whose integer durations must match the fp32 oracle bit for bit, so every
-// product is split-TF32 ("3xTF32": hi*hi + hi*lo + lo*hi, fp32 accumulation) exactly like the mma.sync kernel.
+// product is split-precision (hi*hi + hi*lo + lo*hi with 11-bit significands, fp32 accumulation) like the mma.sync
+// kernel.  The planes are FP16 ("3xFP16", the same 22 significand bits as the tf32 pair of the first version): role
+// counters showed the MMA thread issuing for 63 % of a CTA's life at ~66 cycles per 128 x 64 x 8 tf32 MMA -- twice the
+// tensor-pipe floor, a per-instruction cost -- and kind::f16 covers K = 16 per instruction, so the same work is half the
+// instructions (and half the operand bytes).  Exact power-of-two scaling keeps the fp16 low parts normal:
+//   Q planes hold 2 q (= 16 * q/8), K planes 16 k  ->  S' = 256 S;   P planes hold 4096 p, V planes 16 v  ->  O' = 65536 O.
 //
 // Two kernels per layer:
-//   attn_prep_kernel   qkv [rows, 2304] fp32 -> tf32 hi/lo planes  Q/8 [rows, 768], K [rows, 768] and the TRANSPOSED
+//   attn_prep_kernel   qkv [rows, 2304] fp32 -> fp16 hi/lo planes  Q [rows, 768], K [rows, 768] and the TRANSPOSED
 //                      V^T [(item, head, d), key] (pitch 512), so that both MMAs take K-major operands straight from
-//                      128B-swizzled TMA boxes (keys beyond the item's length are zero-filled up to a multiple of 64);
+//                      128B-swizzled TMA boxes (keys beyond the item's length are zero-filled up to a multiple of 64).
+//                      (Big batches skip it: the QKV GEMM's final warps write the planes, kernels_tc.cu.)
 //   attn_umma_kernel   one CTA per (item, head, 128 query rows), 6 warps:
-//       warp 0     TMA producer: the Q planes once, then a 2-stage ring of (K, V^T) tiles of 64 keys (64 KB / stage)
-//       warp 1     MMA issuer:  S_j = Q K_j^T (M 128, N 64 keys, K 64: 24 UMMAs) into one of two TMEM S buffers,
-//                               O_j = P_j V_j  (A = P from TENSOR MEMORY, B = V^T tile: 24 UMMAs) into the TMEM O tile
+//       warp 0     TMA producer: the Q planes once, then a 2-stage ring of K and V^T tiles of 64 keys
+//       warp 1     MMA issuer:  S_j = Q K_j^T (M 128, N 64 keys, K 64: 12 UMMAs) into one of two TMEM S buffers,
+//                               O_j = P_j V_j  (A = P from TENSOR MEMORY, B = V^T tile: 12 UMMAs) into a TMEM O tile
 //       warps 2-5  softmax: thread = query row = TMEM lane, so row max / sum are thread-local (no shuffles): tcgen05.ld
-//                  of S_j, mask, online max, exp, split P into tf32 hi/lo and tcgen05.st them back to TMEM as the A
+//                  of S_j, mask, online max, exp, split P into fp16 hi/lo and tcgen05.st them back to TMEM as the A
 //                  operand of the second MMA; then the O tile is drained and folded into the fp32 running output with
 //                  the flash rescaling (each 64-key chain is added in fp32 RN -- the tensor core truncates per
-//                  accumulate, the same chain splitting the split-TF32 GEMMs use).
+//                  accumulate, the same chain splitting the split-precision GEMMs use).
 //   S, P and O are all double-buffered in TMEM: S_{j+1} is issued before the softmax of tile j starts and O_j = P_j V_j
 //   runs while the softmax warps are already on tile j+1 (they fold O_j in after writing P_{j+1}; the order of the
 //   floating-point operations is unchanged), so the tensor pipe works under the exponentials.
-// TMEM columns: S0 0..63, S1 64..127, P_hi/P_lo buffer 0 128..255, buffer 1 256..383, O0 384..447, O1 448..511.
+// TMEM columns: S0 0..63, S1 64..127, P buffer pb at 128 + 64 pb (hi 32 columns = 64 keys, then lo), O0 256..319, O1 320..383.
 #include "kernels.h"
 #include <cstdio>
 #include <cuda.h>
@@ -48,13 +54,24 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
 }
-// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// v (already scaled) -> fp16 hi = rn(v), lo = rn(v - hi); returned as raw 16-bit patterns
+__device__ __forceinline__ void split_h(float v, uint32_t& hi, uint32_t& lo) {
+  const __half h = __float2half_rn(v);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+}
+constexpr float kQScale = 2.0f;          // 16 * (1/8): the 1/sqrt(64) of the scores folded in, exact
+constexpr float kKVScale = 16.0f;
+constexpr float kPScale = 4096.0f;
+constexpr float kSInv = 1.0f / 256.0f;    // S = q.k / 8 = S' / (kQScale * kKVScale * 8)
+constexpr float kOInv = 1.0f / 65536.0f;  // O = O' / (kPScale * kKVScale)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -74,12 +91,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 constexpr int kVtPitch = 512;          // keys per V^T row (ALBERT max_position_embeddings)
 
 // ------------------------------------------------------------------------------------------ operand planes
-__global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict__ qkv, float* __restrict__ qh,
-                                                        float* __restrict__ ql, float* __restrict__ kh,
-                                                        float* __restrict__ kl, float* __restrict__ vth,
-                                                        float* __restrict__ vtl, const int* __restrict__ off,
+__global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict__ qkv, __half* __restrict__ qh,
+                                                        __half* __restrict__ ql, __half* __restrict__ kh,
+                                                        __half* __restrict__ kl, __half* __restrict__ vth,
+                                                        __half* __restrict__ vtl, const int* __restrict__ off,
                                                         const int* __restrict__ len) {
-  __shared__ float s_h[64][33], s_l[64][33];
+  __shared__ unsigned short s_h[64][34], s_l[64][34];
   const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 32;
   const int N = len[b];
   const int NR = (N + 63) & ~63;                       // V^T is consumed in tiles of 64 keys: zero-fill up to there
@@ -99,43 +116,44 @@ __global__ void __launch_bounds__(256) attn_prep_kernel(const float* __restrict_
     q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = a0.w; q[4] = a1.x; q[5] = a1.y; q[6] = a1.z; q[7] = a1.w;
     k[0] = b0.x; k[1] = b0.y; k[2] = b0.z; k[3] = b0.w; k[4] = b1.x; k[5] = b1.y; k[6] = b1.z; k[7] = b1.w;
     v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w;
-    float o[4][8];   // qh ql kh kl
+    uint32_t w[4][8];   // qh ql kh kl
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const float qs = q[e] * 0.125f;                  // 1/sqrt(64), exact
-      o[0][e] = __uint_as_float(to_tf32(qs)); o[1][e] = __uint_as_float(to_tf32(qs - o[0][e]));
-      o[2][e] = __uint_as_float(to_tf32(k[e])); o[3][e] = __uint_as_float(to_tf32(k[e] - o[2][e]));
+      split_h(q[e] * kQScale, w[0][e], w[1][e]);
+      split_h(k[e] * kKVScale, w[2][e], w[3][e]);
     }
-    float* dst[4] = {qh, ql, kh, kl};
+    __half* dst[4] = {qh, ql, kh, kl};
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-      float* d = dst[p] + row * 768 + h * 64 + c8;
-      *reinterpret_cast<float4*>(d) = make_float4(o[p][0], o[p][1], o[p][2], o[p][3]);
-      *reinterpret_cast<float4*>(d + 4) = make_float4(o[p][4], o[p][5], o[p][6], o[p][7]);
-    }
+    for (int p = 0; p < 4; p++)
+      *reinterpret_cast<uint4*>(dst[p] + row * 768 + h * 64 + c8) =
+          make_uint4(w[p][0] | (w[p][1] << 16), w[p][2] | (w[p][3] << 16), w[p][4] | (w[p][5] << 16), w[p][6] | (w[p][7] << 16));
   }
 #pragma unroll
   for (int e = 0; e < 8; e++) {
-    const float hi = __uint_as_float(to_tf32(v[e]));
-    s_h[c8 + e][r] = hi;
-    s_l[c8 + e][r] = __uint_as_float(to_tf32(v[e] - hi));
+    uint32_t hi, lo;
+    split_h(v[e] * kKVScale, hi, lo);
+    s_h[c8 + e][r] = (unsigned short)hi;
+    s_l[c8 + e][r] = (unsigned short)lo;
   }
   __syncthreads();
-  // V^T rows: (item, head, d), 32 keys of this block contiguous
+  // V^T rows: (item, head, d), 32 keys of this block contiguous (64 bytes): 4 threads x 8 keys per d
   const int d = tid >> 2, seg = (tid & 3) << 3;
   const size_t vrow = ((size_t)(b * 12 + h) * 64 + d) * kVtPitch + t0 + seg;
-  *reinterpret_cast<float4*>(vth + vrow) = make_float4(s_h[d][seg], s_h[d][seg + 1], s_h[d][seg + 2], s_h[d][seg + 3]);
-  *reinterpret_cast<float4*>(vth + vrow + 4) = make_float4(s_h[d][seg + 4], s_h[d][seg + 5], s_h[d][seg + 6], s_h[d][seg + 7]);
-  *reinterpret_cast<float4*>(vtl + vrow) = make_float4(s_l[d][seg], s_l[d][seg + 1], s_l[d][seg + 2], s_l[d][seg + 3]);
-  *reinterpret_cast<float4*>(vtl + vrow + 4) = make_float4(s_l[d][seg + 4], s_l[d][seg + 5], s_l[d][seg + 6], s_l[d][seg + 7]);
+  *reinterpret_cast<uint4*>(vth + vrow) =
+      make_uint4(s_h[d][seg] | ((uint32_t)s_h[d][seg + 1] << 16), s_h[d][seg + 2] | ((uint32_t)s_h[d][seg + 3] << 16),
+                 s_h[d][seg + 4] | ((uint32_t)s_h[d][seg + 5] << 16), s_h[d][seg + 6] | ((uint32_t)s_h[d][seg + 7] << 16));
+  *reinterpret_cast<uint4*>(vtl + vrow) =
+      make_uint4(s_l[d][seg] | ((uint32_t)s_l[d][seg + 1] << 16), s_l[d][seg + 2] | ((uint32_t)s_l[d][seg + 3] << 16),
+                 s_l[d][seg + 4] | ((uint32_t)s_l[d][seg + 5] << 16), s_l[d][seg + 6] | ((uint32_t)s_l[d][seg + 7] << 16));
 }
 
 // ------------------------------------------------------------------------------------------ the attention kernel
-constexpr uint32_t kQPlane = 2 * 128 * 128;            // one Q plane: two K-chunks of [128 rows x 32 floats] = 32 KB
-constexpr uint32_t kTilePlane = 2 * 64 * 128;          // one K / V^T plane of a 64-key tile: two chunks of [64 x 32] = 16 KB
-constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 64 KB
-constexpr int kAttnSmem = 2 * kQPlane + 2 * kStage + 20 * 8 + 16 + 1024;
-constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 384;   // P buffer pb: hi at kColP + 128 pb, lo 64 columns further
+constexpr uint32_t kQPlane = 128 * 128;                // one Q plane: [128 rows x 64 fp16] = 16 KB
+constexpr uint32_t kTilePlane = 64 * 128;              // one K / V^T plane of a 64-key tile: [64 x 64 fp16] = 8 KB
+constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 32 KB
+constexpr int kAttnStages = 4;
+constexpr int kAttnSmem = 2 * kQPlane + kAttnStages * kStage + 32 * 8 + 16 + 1024;
+constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 256;   // P buffer pb: hi at kColP + 64 pb (32 columns = 64 keys), lo 32 columns further
 
 __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
                                                            const __grid_constant__ CUtensorMap tmQl,
@@ -145,6 +163,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap tmVl,
                                                            const int* __restrict__ off, const int* __restrict__ len,
                                                            float* __restrict__ ctx) {
+  constexpr int NST = kAttnStages;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
   const int N = len[b];
   if (q0 >= N) return;                                  // (uniform per CTA, before any barrier / TMEM allocation)
@@ -153,21 +172,20 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_h = base, q_l = base + kQPlane;
   const uint32_t st0 = base + 2 * kQPlane;
-  const uint32_t bar_base = st0 + 2 * kStage;
+  const uint32_t bar_base = st0 + NST * kStage;
   const uint32_t q_full = bar_base;
   // K and V^T of a stage have their own full / empty barriers: K_j is free again as soon as S_j has been computed,
-  // V^T_j only after P_j V_j -- with one barrier pair per stage every reload had less than one tile period to arrive,
-  // and the kernel ran at the latency of a 64 KB TMA stage per tile (tensor pipe 26 % active, softmax not the limit)
+  // V^T_j only after P_j V_j; the stage ring (4 deep) is independent of the double-buffered S / P / O in TMEM
   auto fullk_bar = [&](int s) { return bar_base + (1 + s) * 8; };
-  auto emptyk_bar = [&](int s) { return bar_base + (3 + s) * 8; };
-  auto sfull_bar = [&](int i) { return bar_base + (5 + i) * 8; };
-  auto sfree_bar = [&](int i) { return bar_base + (7 + i) * 8; };
-  auto pfull_bar = [&](int i) { return bar_base + (9 + i) * 8; };
-  auto ofull_bar = [&](int i) { return bar_base + (11 + i) * 8; };
-  auto ofree_bar = [&](int i) { return bar_base + (13 + i) * 8; };
-  auto fullv_bar = [&](int s) { return bar_base + (15 + s) * 8; };
-  auto emptyv_bar = [&](int s) { return bar_base + (17 + s) * 8; };
-  const uint32_t tmem_slot = bar_base + 20 * 8;
+  auto emptyk_bar = [&](int s) { return bar_base + (1 + NST + s) * 8; };
+  auto fullv_bar = [&](int s) { return bar_base + (1 + 2 * NST + s) * 8; };
+  auto emptyv_bar = [&](int s) { return bar_base + (1 + 3 * NST + s) * 8; };
+  auto sfull_bar = [&](int i) { return bar_base + (1 + 4 * NST + i) * 8; };
+  auto sfree_bar = [&](int i) { return bar_base + (3 + 4 * NST + i) * 8; };
+  auto pfull_bar = [&](int i) { return bar_base + (5 + 4 * NST + i) * 8; };
+  auto ofull_bar = [&](int i) { return bar_base + (7 + 4 * NST + i) * 8; };
+  auto ofree_bar = [&](int i) { return bar_base + (9 + 4 * NST + i) * 8; };
+  const uint32_t tmem_slot = bar_base + 32 * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -175,8 +193,10 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVh) : "memory");
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < NST; s++) {
       mbar_init(fullk_bar(s), 1); mbar_init(emptyk_bar(s), 1); mbar_init(fullv_bar(s), 1); mbar_init(emptyv_bar(s), 1);
+    }
+    for (int s = 0; s < 2; s++) {
       mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 4);
       mbar_init(pfull_bar(s), 4); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 4);
     }
@@ -197,34 +217,25 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     if (lane == 0) {
       const int qrow = off[b] + q0, krow0 = off[b], vrow = (b * 12 + h) * 64;
       mbar_expect_tx(q_full, 2 * kQPlane);
-      for (int c = 0; c < 2; c++) {
-        tma_load_2d(q_h + c * (kQPlane / 2), &tmQh, h * 64 + 32 * c, qrow, q_full);
-        tma_load_2d(q_l + c * (kQPlane / 2), &tmQl, h * 64 + 32 * c, qrow, q_full);
-      }
+      tma_load_2d(q_h, &tmQh, h * 64, qrow, q_full);
+      tma_load_2d(q_l, &tmQl, h * 64, qrow, q_full);
       auto load_k = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(emptyk_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        const int s = j % NST;
+        mbar_wait(emptyk_bar(s), (((uint32_t)(j / NST)) & 1u) ^ 1u);
         const uint32_t sa = st0 + s * kStage;
         mbar_expect_tx(fullk_bar(s), 2 * kTilePlane);
-        for (int c = 0; c < 2; c++) {
-          const uint32_t co = c * (kTilePlane / 2);
-          tma_load_2d(sa + co, &tmKh, h * 64 + 32 * c, krow0 + j * 64, fullk_bar(s));
-          tma_load_2d(sa + kTilePlane + co, &tmKl, h * 64 + 32 * c, krow0 + j * 64, fullk_bar(s));
-        }
+        tma_load_2d(sa, &tmKh, h * 64, krow0 + j * 64, fullk_bar(s));
+        tma_load_2d(sa + kTilePlane, &tmKl, h * 64, krow0 + j * 64, fullk_bar(s));
       };
       auto load_v = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(emptyv_bar(s), (((uint32_t)(j >> 1)) & 1u) ^ 1u);
+        const int s = j % NST;
+        mbar_wait(emptyv_bar(s), (((uint32_t)(j / NST)) & 1u) ^ 1u);
         const uint32_t sa = st0 + s * kStage;
         mbar_expect_tx(fullv_bar(s), 2 * kTilePlane);
-        for (int c = 0; c < 2; c++) {
-          const uint32_t co = c * (kTilePlane / 2);
-          tma_load_2d(sa + 2 * kTilePlane + co, &tmVh, j * 64 + 32 * c, vrow, fullv_bar(s));
-          tma_load_2d(sa + 3 * kTilePlane + co, &tmVl, j * 64 + 32 * c, vrow, fullv_bar(s));
-        }
+        tma_load_2d(sa + 2 * kTilePlane, &tmVh, j * 64, vrow, fullv_bar(s));
+        tma_load_2d(sa + 3 * kTilePlane, &tmVl, j * 64, vrow, fullv_bar(s));
       };
-      // issue order = the order in which the MMA warp frees the buffers (S_0, S_1, PV_0, S_2, PV_1, ...):
-      // K_0, K_1, V_0, K_2, V_1, K_3, V_2, ...
+      // issue order = the order in which the MMA warp needs (and frees) the buffers: K_0, K_1, V_0, K_2, V_1, ...
       load_k(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) load_k(j + 1);
@@ -233,14 +244,14 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(128, 64);
+      constexpr uint32_t idesc = umma_idesc_f16(128, 64);
       ATT_DECL(true);
       mbar_wait(q_full, 0u);
       tc_fence_after();
       ATT(0);
-      auto issue_s = [&](int j) {                      // S_j = (Q/8) K_j^T, small terms first (as the mma.sync kernel)
-        const int s = j & 1;
-        mbar_wait(fullk_bar(s), ((uint32_t)(j >> 1)) & 1u);
+      auto issue_s = [&](int j) {                      // S'_j = Q' K'_j^T, small terms first (as the mma.sync kernel)
+        const int s = j & 1, st = j % NST;
+        mbar_wait(fullk_bar(st), ((uint32_t)(j / NST)) & 1u);
         tc_fence_after();
         ATT(1);
         if (j >= 2) {                                  // the softmax warps have read S_{j-2} out of this buffer
@@ -248,31 +259,28 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           tc_fence_after();
         }
         ATT(2);
-        const uint32_t sa = st0 + s * kStage;
+        const uint32_t sa = st0 + st * kStage;
         const uint32_t t_s = tmem_base + kColS0 + 64u * (uint32_t)s;
+        const uint64_t ah = umma_desc_sw128(q_h), al = umma_desc_sw128(q_l);
+        const uint64_t bh = umma_desc_sw128(sa), bl = umma_desc_sw128(sa + kTilePlane);
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const uint64_t ah = umma_desc_sw128(q_h + c * (kQPlane / 2)), al = umma_desc_sw128(q_l + c * (kQPlane / 2));
-          const uint64_t bh = umma_desc_sw128(sa + c * (kTilePlane / 2)), bl = umma_desc_sw128(sa + kTilePlane + c * (kTilePlane / 2));
-#pragma unroll
-          for (int k = 0; k < 4; k++) {                // 4 x (K = 8 tf32 = 32 B)
-            const uint64_t o = (uint64_t)(2 * k);
-            umma_tf32(t_s, al + o, bh + o, idesc, (c | k) ? 1u : 0u);
-            umma_tf32(t_s, ah + o, bl + o, idesc, 1u);
-            umma_tf32(t_s, ah + o, bh + o, idesc, 1u);
-          }
+        for (int k = 0; k < 4; k++) {                  // 4 x (K = 16 fp16 = 32 B) = the 64 dims of a head
+          const uint64_t o = (uint64_t)(2 * k);
+          umma_bf16(t_s, al + o, bh + o, idesc, k ? 1u : 0u);      // (kind::f16; the descriptor selects fp16)
+          umma_bf16(t_s, ah + o, bl + o, idesc, 1u);
+          umma_bf16(t_s, ah + o, bh + o, idesc, 1u);
         }
         umma_commit(sfull_bar(s));
-        umma_commit(emptyk_bar(s));                    // K_j is consumed
+        umma_commit(emptyk_bar(st));                   // K_j is consumed
         ATT(3);
       };
       issue_s(0);
       for (int j = 0; j < nt; j++) {
         if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
-        const int s = j & 1;                           // stage, P buffer and O buffer of tile j
-        mbar_wait(fullv_bar(s), ((uint32_t)(j >> 1)) & 1u);   // V^T_j has landed
+        const int s = j & 1, st = j % NST;             // P / O buffer and stage of tile j
+        mbar_wait(fullv_bar(st), ((uint32_t)(j / NST)) & 1u);   // V^T_j has landed
         ATT(4);
-        mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);   // P_j is in TMEM
+        mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);     // P_j is in TMEM
         tc_fence_after();
         ATT(5);
         if (j >= 2) {                                  // O_{j-2} has been read out of this O buffer
@@ -280,21 +288,19 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
           tc_fence_after();
         }
         ATT(6);
-        const uint32_t sa = st0 + s * kStage;
+        const uint32_t sa = st0 + st * kStage;
         const uint32_t t_o = tmem_base + kColO + 64u * (uint32_t)s;
-        const uint32_t t_ph = tmem_base + kColP + 128u * (uint32_t)s, t_pl = t_ph + 64u;
+        const uint32_t t_ph = tmem_base + kColP + 64u * (uint32_t)s, t_pl = t_ph + 32u;
+        const uint64_t vh = umma_desc_sw128(sa + 2 * kTilePlane), vl = umma_desc_sw128(sa + 3 * kTilePlane);
 #pragma unroll
-        for (int kk = 0; kk < 8; kk++) {               // 8 keys per UMMA
-          const int c = kk >> 2;
-          const uint64_t o = (uint64_t)(2 * (kk & 3));
-          const uint64_t vh = umma_desc_sw128(sa + 2 * kTilePlane + c * (kTilePlane / 2)) + o;
-          const uint64_t vl = umma_desc_sw128(sa + 3 * kTilePlane + c * (kTilePlane / 2)) + o;
-          umma_tf32_ts(t_o, t_pl + 8u * kk, vh, idesc, kk ? 1u : 0u);
-          umma_tf32_ts(t_o, t_ph + 8u * kk, vl, idesc, 1u);
-          umma_tf32_ts(t_o, t_ph + 8u * kk, vh, idesc, 1u);
+        for (int kk = 0; kk < 4; kk++) {               // 16 keys (8 TMEM columns of packed fp16 pairs) per UMMA
+          const uint64_t o = (uint64_t)(2 * kk);
+          umma_f16_ts(t_o, t_pl + 8u * kk, vh + o, idesc, kk ? 1u : 0u);
+          umma_f16_ts(t_o, t_ph + 8u * kk, vl + o, idesc, 1u);
+          umma_f16_ts(t_o, t_ph + 8u * kk, vh + o, idesc, 1u);
         }
         umma_commit(ofull_bar(s));
-        umma_commit(emptyv_bar(s));                    // V^T_j is consumed
+        umma_commit(emptyv_bar(st));                   // V^T_j is consumed
         ATT(7);
       }
       ATT_FLUSH(0);
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
         uint32_t v[64];
         tmem_ld64(tq + kColS0 + 64u * (uint32_t)s, v);      // one TMEM round trip for the 64 keys of the tile
 #pragma unroll
-        for (int e = 0; e < 64; e++) sc[e] = __uint_as_float(v[e]);
+        for (int e = 0; e < 64; e++) sc[e] = __uint_as_float(v[e]) * kSInv;     // exact: the planes' power-of-two scaling
       }
       tc_fence_before();
       __syncwarp();
@@ -341,19 +347,20 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       l = l * corr + ps;
       m = mn;
       ATT(2);
-      // P_j -> TMEM as tf32 hi / lo (A operand of the second MMA).  MMA_{j-2} has finished reading this P buffer:
-      // this thread waited for its O tile in the previous iteration.
-#pragma unroll
-      for (int half = 0; half < 2; half++) {
+      // P_j -> TMEM as fp16 hi / lo planes of 4096 p, two keys per 32-bit column (A operand of the second MMA).
+      // MMA_{j-2} has finished reading this P buffer: this thread waited for its O tile in the previous iteration.
+      {
         uint32_t ph[32], pl[32];
 #pragma unroll
         for (int e = 0; e < 32; e++) {
-          const float p = sc[half * 32 + e];
-          ph[e] = to_tf32(p);
-          pl[e] = to_tf32(p - __uint_as_float(ph[e]));
+          uint32_t h0, l0, h1, l1;
+          split_h(sc[2 * e] * kPScale, h0, l0);
+          split_h(sc[2 * e + 1] * kPScale, h1, l1);
+          ph[e] = h0 | (h1 << 16);
+          pl[e] = l0 | (l1 << 16);
         }
-        tmem_st32(tq + kColP + 128u * (uint32_t)s + 32u * half, ph);
-        tmem_st32(tq + kColP + 128u * (uint32_t)s + 64u + 32u * half, pl);
+        tmem_st32(tq + kColP + 64u * (uint32_t)s, ph);
+        tmem_st32(tq + kColP + 64u * (uint32_t)s + 32u, pl);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(ofree_bar(so));
 #pragma unroll
-        for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]);
+        for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]) * kOInv;
       }
 #pragma unroll
       for (int e = 0; e < 64; e++) o[e] *= corr;
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
       tc_fence_before();
 #pragma unroll
-      for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]);
+      for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]) * kOInv;
     }
     if (q0 + row < N) {
       const float inv = 1.0f / l;
@@ -421,23 +428,27 @@ void attention_timing_dump() {
 #endif
 }
 
+// scratch size in floats: six fp16 planes (Q, K: hi / lo [rows, 768]; V^T: hi / lo [B * 768, 512])
 size_t attention_umma_scratch_floats(int rows_total, int B) {
-  return (size_t)4 * rows_total * 768 + (size_t)2 * B * 768 * kVtPitch;
+  return ((size_t)4 * rows_total * 768 + (size_t)2 * B * 768 * kVtPitch) / 2 + 64;
 }
 
-void attention_umma_planes(float* scratch, int rows_total, int B, float* (&pl)[6]) {
+void attention_umma_planes(float* scratch, int rows_total, int B, void* (&pl)[6]) {
   const size_t plane = (size_t)rows_total * 768;
-  pl[0] = scratch; pl[1] = pl[0] + plane; pl[2] = pl[1] + plane; pl[3] = pl[2] + plane;
-  pl[4] = pl[3] + plane; pl[5] = pl[4] + (size_t)B * 768 * kVtPitch;
+  __half* p0 = reinterpret_cast<__half*>(scratch);
+  pl[0] = p0; pl[1] = p0 + plane; pl[2] = p0 + 2 * plane; pl[3] = p0 + 3 * plane;
+  pl[4] = p0 + 4 * plane; pl[5] = p0 + 4 * plane + (size_t)B * 768 * kVtPitch;
 }
 
 void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const int* off, const int* len, int B,
                            int max_len, int rows_total, cudaStream_t st, bool planes_ready) {
   if (g_dry_run) return;
   if (max_len > kVtPitch) throw ArgError("launch_attention_umma: more than 512 tokens");
-  const size_t plane = (size_t)rows_total * 768;
-  float* qh = scratch; float* ql = qh + plane; float* kh = ql + plane; float* kl = kh + plane;
-  float* vth = kl + plane; float* vtl = vth + (size_t)B * 768 * kVtPitch;
+  void* pl[6];
+  attention_umma_planes(scratch, rows_total, B, pl);
+  __half* qh = static_cast<__half*>(pl[0]); __half* ql = static_cast<__half*>(pl[1]);
+  __half* kh = static_cast<__half*>(pl[2]); __half* kl = static_cast<__half*>(pl[3]);
+  __half* vth = static_cast<__half*>(pl[4]); __half* vtl = static_cast<__half*>(pl[5]);
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -448,12 +459,12 @@ void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const i
     post_launch("attn_prep", st);
   }
   alignas(64) CUtensorMap mQh, mQl, mKh, mKl, mVh, mVl;
-  make_tmap_f32(&mQh, qh, 768, rows_total, 768, 128);
-  make_tmap_f32(&mQl, ql, 768, rows_total, 768, 128);
-  make_tmap_f32(&mKh, kh, 768, rows_total, 768, 64);
-  make_tmap_f32(&mKl, kl, 768, rows_total, 768, 64);
-  make_tmap_f32(&mVh, vth, kVtPitch, (long long)B * 768, kVtPitch, 64);
-  make_tmap_f32(&mVl, vtl, kVtPitch, (long long)B * 768, kVtPitch, 64);
+  make_tmap_f16(&mQh, qh, 768, rows_total, 768, 128);
+  make_tmap_f16(&mQl, ql, 768, rows_total, 768, 128);
+  make_tmap_f16(&mKh, kh, 768, rows_total, 768, 64);
+  make_tmap_f16(&mKl, kl, 768, rows_total, 768, 64);
+  make_tmap_f16(&mVh, vth, kVtPitch, (long long)B * 768, kVtPitch, 64);
+  make_tmap_f16(&mVl, vtl, kVtPitch, (long long)B * 768, kVtPitch, 64);
   dim3 g((max_len + 127) / 128, 12, B);
   attn_umma_kernel<<<g, 192, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx);
   post_launch("attention", st);

@@ -1123,27 +1123,27 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(gfull_bar, (uint32_t)ti & 1u);
       if (a.attn_pl[0] && n0 >= 1536) {
         // QKV projection, V columns: the attention kernel wants V TRANSPOSED per head ([(item, head, d), key], pitch 512,
-        // tf32 hi / lo, zero-filled to a multiple of 64 keys).  The staged tile is read by columns instead: warp fw takes
-        // every NFIN-th dim of the tile, a lane one token, so every store covers 32 consecutive keys (128 bytes).
+        // fp16 hi / lo of 16 v, zero-filled to a multiple of 64 keys).  The staged tile is read by columns instead: warp fw
+        // takes every NFIN-th dim of the tile, a lane one token, so every store covers 32 consecutive keys (64 bytes).
         const int NR = (mlen + 63) & ~63;
+        __half* const vth = static_cast<__half*>(a.attn_pl[4]);
+        __half* const vtl = static_cast<__half*>(a.attn_pl[5]);
 #pragma unroll 1
         for (int cl = fw; cl < 128; cl += NFIN) {                // column inside the tile
           const int cv = n0 - 1536 + cl;                       // V column: head * 64 + d
           const float bias_c = a.bias ? a.bias[n0 + cl] : 0.f;
-          float* const vh = a.attn_pl[4] + ((size_t)b * 768 + cv) * 512 + m0;
-          float* const vl = a.attn_pl[5] + ((size_t)b * 768 + cv) * 512 + m0;
+          __half* const vh = vth + ((size_t)b * 768 + cv) * 512 + m0;
+          __half* const vl = vtl + ((size_t)b * 768 + cv) * 512 + m0;
           const int chunk = cl >> 2, e4 = cl & 3;
 #pragma unroll
           for (int tg = 0; tg < 4; tg++) {
             const int r = tg * 32 + lane;                      // token inside the tile
             if (m0 + r < NR) {
               const float raw = stg_f[r * 128 + (((chunk & ~7) | ((chunk ^ r) & 7)) << 2) + e4];
-              const float val = m0 + r < mlen ? fmaf(raw, a.wscale, bias_c) : 0.f;
-              uint32_t hi, lo;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(val));
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(val - __uint_as_float(hi)));
-              vh[r] = __uint_as_float(hi);
-              vl[r] = __uint_as_float(lo);
+              const float sv = (m0 + r < mlen ? fmaf(raw, a.wscale, bias_c) : 0.f) * 16.0f;
+              const __half hi = __float2half_rn(sv);
+              vh[r] = hi;
+              vl[r] = __float2half_rn(sv - __half2float(hi));
             }
           }
         }
@@ -1174,21 +1174,21 @@ gemm32p2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
           o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
           const size_t orow = (size_t)(out_row0 + mm * a.ors + a.oro);
-          if (a.attn_pl[0]) {   // QKV projection, Q (scaled by 1/8 = 1/sqrt(64), exact) and K columns: tf32 hi / lo planes
+          if (a.attn_pl[0]) {   // QKV projection, Q and K columns: fp16 hi / lo planes of 2 q (= 16 q / sqrt(64)) and 16 k
             const bool isq = n0 < 768;
+            const float sc_ = isq ? 2.0f : 16.0f;
             const float e4[4] = {o.x, o.y, o.z, o.w};
-            float hi4[4], lo4[4];
+            uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
-              const float val = isq ? e4[e] * 0.125f : e4[e];
-              uint32_t hi, lo;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(val));
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(val - __uint_as_float(hi)));
-              hi4[e] = __uint_as_float(hi); lo4[e] = __uint_as_float(lo);
+              const float sv = e4[e] * sc_;
+              const __half hi = __float2half_rn(sv);
+              hw[e] = __half_as_ushort(hi);
+              lw[e] = __half_as_ushort(__float2half_rn(sv - __half2float(hi)));
             }
             const size_t pidx = orow * 768 + (size_t)(isq ? n : n - 768);
-            *reinterpret_cast<float4*>(a.attn_pl[isq ? 0 : 2] + pidx) = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
-            *reinterpret_cast<float4*>(a.attn_pl[isq ? 1 : 3] + pidx) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+            *reinterpret_cast<uint2*>(static_cast<__half*>(a.attn_pl[isq ? 0 : 2]) + pidx) = make_uint2(hw[0] | (hw[1] << 16), hw[2] | (hw[3] << 16));
+            *reinterpret_cast<uint2*>(static_cast<__half*>(a.attn_pl[isq ? 1 : 3]) + pidx) = make_uint2(lw[0] | (lw[1] << 16), lw[2] | (lw[3] << 16));
             continue;
           }
           if (a.out_hi) {      // operand planes for the next GEMM (host guarantees Co % 4 == 0, no accumulate)
