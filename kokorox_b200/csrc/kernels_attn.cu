@@ -15,11 +15,12 @@
 //                      V^T [(item, head, d), key] (pitch 512), so that both MMAs take K-major operands straight from
 //                      128B-swizzled TMA boxes (keys beyond the item's length are zero-filled up to a multiple of 64).
 //                      (Big batches skip it: the QKV GEMM's final warps write the planes, kernels_tc.cu.)
-//   attn_umma_kernel   one CTA per (item, head, 128 query rows), 6 warps:
+//   attn_umma_kernel   one CTA per (item, head, 128 query rows), 10 warps:
 //       warp 0     TMA producer: the Q planes once, then a 2-stage ring of K and V^T tiles of 64 keys
 //       warp 1     MMA issuer:  S_j = Q K_j^T (M 128, N 64 keys, K 64: 12 UMMAs) into one of two TMEM S buffers,
 //                               O_j = P_j V_j  (A = P from TENSOR MEMORY, B = V^T tile: 12 UMMAs) into a TMEM O tile
-//       warps 2-5  softmax: thread = query row = TMEM lane, so row max / sum are thread-local (no shuffles): tcgen05.ld
+//       warps 2-9  softmax, two warps per block of 32 query rows (each takes 32 of a tile's 64 keys and 32 of the 64 output
+//                  dims; row maxima exchanged through smem): thread = query row = TMEM lane: tcgen05.ld
 //                  of S_j, mask, online max, exp, split P into fp16 hi/lo and tcgen05.st them back to TMEM as the A
 //                  operand of the second MMA; then the O tile is drained and folded into the fp32 running output with
 //                  the flash rescaling (each 64-key chain is added in fp32 RN -- the tensor core truncates per
@@ -81,6 +82,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
         "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -152,10 +161,11 @@ constexpr uint32_t kQPlane = 128 * 128;                // one Q plane: [128 rows
 constexpr uint32_t kTilePlane = 64 * 128;              // one K / V^T plane of a 64-key tile: [64 x 64 fp16] = 8 KB
 constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 32 KB
 constexpr int kAttnStages = 4;
-constexpr int kAttnSmem = 2 * kQPlane + kAttnStages * kStage + 32 * 8 + 16 + 1024;
+constexpr int kAttnThreads = 320;                      // TMA warp, MMA warp, 8 softmax warps
+constexpr int kAttnSmem = 2 * kQPlane + kAttnStages * kStage + 32 * 8 + 16 + 3072 + 1024;   // + the softmax warps' exchange buffers
 constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 256;   // P buffer pb: hi at kColP + 64 pb (32 columns = 64 keys), lo 32 columns further
 
-__global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
                                                            const __grid_constant__ CUtensorMap tmQl,
                                                            const __grid_constant__ CUtensorMap tmKh,
                                                            const __grid_constant__ CUtensorMap tmKl,
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
   auto ofull_bar = [&](int i) { return bar_base + (7 + 4 * NST + i) * 8; };
   auto ofree_bar = [&](int i) { return bar_base + (9 + 4 * NST + i) * 8; };
   const uint32_t tmem_slot = bar_base + 32 * 8;
+  const uint32_t xch_base = tmem_slot + 16;             // row maxima [2][2][128] + row sums [2][128] (floats)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -197,8 +208,8 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       mbar_init(fullk_bar(s), 1); mbar_init(emptyk_bar(s), 1); mbar_init(fullv_bar(s), 1); mbar_init(emptyv_bar(s), 1);
     }
     for (int s = 0; s < 2; s++) {
-      mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 4);
-      mbar_init(pfull_bar(s), 4); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 4);
+      mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 8);
+      mbar_init(pfull_bar(s), 8); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -306,13 +317,23 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       ATT_FLUSH(0);
     }
   } else {
-    const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    // ---- softmax: 8 warps.  Warp w owns TMEM lane quadrant q = w & 3 (32 query rows, one per thread) and key half
+    // kh = (w - 2) >> 2: the 32 keys [32 kh, 32 kh + 32) of every tile and, for the output, the 32 dims [32 kh, 32 kh + 32).
+    // With fp16 planes the MMA thread needs ~14 k cycles per CTA and one warp per row block needed ~39 k for its
+    // exp / split / fold chain (role counters); two warps per row block halve that chain.  The two warps of a row
+    // exchange their partial row maxima through shared memory once per tile; their partial sums stay separate until
+    // the end (both are scaled to the same running maximum).
+    const int q = warp & 3;
+    const int kh = (warp - 2) >> 2;
     const int row = q * 32 + lane;                     // query row of this thread
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* const xmax = reinterpret_cast<float*>(smem_raw + (xch_base - smem_u32(smem_raw)));   // [2 buffers][2 halves][128 rows]
+    float* const xl = xmax + 512;                                                               // [2 halves][128 rows]
+    const int pair_bar = 1 + q;                        // named barrier of the two warps of this quadrant
     float m = -INFINITY, l = 0.f;
-    float o[64];
+    float o[32];
 #pragma unroll
-    for (int e = 0; e < 64; e++) o[e] = 0.f;
+    for (int e = 0; e < 32; e++) o[e] = 0.f;
     ATT_DECL(warp == 2 && lane == 0);
     for (int j = 0; j < nt; j++) {
       const int s = j & 1;
@@ -320,87 +341,94 @@ __global__ void __launch_bounds__(192, 1) attn_umma_kernel(const __grid_constant
       mbar_wait(sfull_bar(s), ((uint32_t)(j >> 1)) & 1u);
       tc_fence_after();
       ATT(0);
-      float sc[64];
+      float sc[32];
       {
-        uint32_t v[64];
-        tmem_ld64(tq + kColS0 + 64u * (uint32_t)s, v);      // one TMEM round trip for the 64 keys of the tile
+        uint32_t v[32];
+        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s + 32u * (uint32_t)kh, v);
 #pragma unroll
-        for (int e = 0; e < 64; e++) sc[e] = __uint_as_float(v[e]) * kSInv;     // exact: the planes' power-of-two scaling
+        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(v[e]) * kSInv;     // exact: the planes' power-of-two scaling
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sfree_bar(s));
       ATT(1);
-      // key-padding mask + online softmax, all in this thread
-      const int kbase = j * 64;
+      // key-padding mask + online softmax; the row maximum is the maximum over both halves
+      const int kbase = j * 64 + kh * 32;
       float cm = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 64; e++) {
+      for (int e = 0; e < 32; e++) {
         if (kbase + e >= N) sc[e] = -INFINITY;
         cm = fmaxf(cm, sc[e]);
       }
+      xmax[(s * 2 + kh) * 128 + row] = cm;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      cm = fmaxf(cm, xmax[(s * 2 + (kh ^ 1)) * 128 + row]);
       const float mn = fmaxf(m, cm);                   // finite: every tile holds at least one valid key
       const float corr = expf(m - mn);
       float ps = 0.f;
 #pragma unroll
-      for (int e = 0; e < 64; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
+      for (int e = 0; e < 32; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
       l = l * corr + ps;
       m = mn;
       ATT(2);
-      // P_j -> TMEM as fp16 hi / lo planes of 4096 p, two keys per 32-bit column (A operand of the second MMA).
-      // MMA_{j-2} has finished reading this P buffer: this thread waited for its O tile in the previous iteration.
+      // P_j -> TMEM as fp16 hi / lo planes of 4096 p, two keys per 32-bit column (A operand of the second MMA): this
+      // warp's 32 keys are 16 columns of each plane.  MMA_{j-2} has finished reading this P buffer: this thread waited
+      // for its O tile in the previous iteration.
       {
-        uint32_t ph[32], pl[32];
+        uint32_t ph[16], pl[16];
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
+        for (int e = 0; e < 16; e++) {
           uint32_t h0, l0, h1, l1;
           split_h(sc[2 * e] * kPScale, h0, l0);
           split_h(sc[2 * e + 1] * kPScale, h1, l1);
           ph[e] = h0 | (h1 << 16);
           pl[e] = l0 | (l1 << 16);
         }
-        tmem_st32(tq + kColP + 64u * (uint32_t)s, ph);
-        tmem_st32(tq + kColP + 64u * (uint32_t)s + 32u, pl);
+        tmem_st16(tq + kColP + 64u * (uint32_t)s + 16u * (uint32_t)kh, ph);
+        tmem_st16(tq + kColP + 64u * (uint32_t)s + 32u + 16u * (uint32_t)kh, pl);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pfull_bar(s));
       ATT(3);
-      // fold in O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new running maximum: the same
-      // operations in the same order as add-after-rescale inside one iteration
+      // fold in this warp's 32 dims of O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new
+      // running maximum: the same operations in the same order as add-after-rescale inside one iteration
       if (j >= 1) {
         const int so = (j - 1) & 1;
         mbar_wait(ofull_bar(so), ((uint32_t)((j - 1) >> 1)) & 1u);
         tc_fence_after();
         ATT(4);
-        uint32_t v[64];
-        tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
+        uint32_t v[32];
+        tmem_ld32(tq + kColO + 64u * (uint32_t)so + 32u * (uint32_t)kh, v);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(ofree_bar(so));
 #pragma unroll
-        for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]) * kOInv;
+        for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]) * kOInv;
       }
 #pragma unroll
-      for (int e = 0; e < 64; e++) o[e] *= corr;
+      for (int e = 0; e < 32; e++) o[e] *= corr;
       ATT(5);
     }
     {
       const int so = (nt - 1) & 1;
       mbar_wait(ofull_bar(so), ((uint32_t)((nt - 1) >> 1)) & 1u);
       tc_fence_after();
-      uint32_t v[64];
-      tmem_ld64(tq + kColO + 64u * (uint32_t)so, v);
+      uint32_t v[32];
+      tmem_ld32(tq + kColO + 64u * (uint32_t)so + 32u * (uint32_t)kh, v);
       tc_fence_before();
 #pragma unroll
-      for (int e = 0; e < 64; e++) o[e] += __uint_as_float(v[e]) * kOInv;
+      for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]) * kOInv;
     }
+    // the row sum is the sum of the two halves' sums, added in a fixed order
+    xl[kh * 128 + row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     if (q0 + row < N) {
-      const float inv = 1.0f / l;
-      float* dst = ctx + ((size_t)off[b] + q0 + row) * 768 + h * 64;
+      const float inv = 1.0f / (xl[row] + xl[128 + row]);
+      float* dst = ctx + ((size_t)off[b] + q0 + row) * 768 + h * 64 + kh * 32;
 #pragma unroll
-      for (int e = 0; e < 64; e += 4)
+      for (int e = 0; e < 32; e += 4)
         *reinterpret_cast<float4*>(dst + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
     }
     ATT(6);
@@ -466,7 +494,7 @@ void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const i
   make_tmap_f16(&mVh, vth, kVtPitch, (long long)B * 768, kVtPitch, 64);
   make_tmap_f16(&mVl, vtl, kVtPitch, (long long)B * 768, kVtPitch, 64);
   dim3 g((max_len + 127) / 128, 12, B);
-  attn_umma_kernel<<<g, 192, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx);
+  attn_umma_kernel<<<g, kAttnThreads, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx);
   post_launch("attention", st);
 }
 
