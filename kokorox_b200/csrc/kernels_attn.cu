@@ -162,8 +162,26 @@ constexpr uint32_t kTilePlane = 64 * 128;              // one K / V^T plane of a
 constexpr uint32_t kStage = 4 * kTilePlane;            // Kh | Kl | VTh | VTl = 32 KB
 constexpr int kAttnStages = 4;
 constexpr int kAttnThreads = 320;                      // TMA warp, MMA warp, 8 softmax warps
-constexpr int kAttnSmem = 2 * kQPlane + kAttnStages * kStage + 32 * 8 + 16 + 3072 + 1024;   // + the softmax warps' exchange buffers
+constexpr int kAttnSmem = 4 * kQPlane + kAttnStages * kStage + 32 * 8 + 16 + 3072 + 1024;   // 2 Q buffers, K/V ring, barriers, exchange buffers
 constexpr uint32_t kColS0 = 0, kColP = 128, kColO = 256;   // P buffer pb: hi at kColP + 64 pb (32 columns = 64 keys), lo 32 columns further
+
+// Persistent: a CTA walks the work items w = blockIdx.x, blockIdx.x + gridDim.x, ... of the (item, head, query block)
+// space, query block fastest (the CTAs that run together share K / V^T tiles in L2).  With one CTA per work item the
+// start-up (TMEM allocation, Q load: ~4 k cycles) and the tear-down (output rows, ~5 k) were exposed 21 times per SM and
+// launch -- 30 % of a CTA's life; here the TMA warp prefetches the next item's Q into a second buffer, the MMA thread
+// issues the next item's S_0 under the last softmax of the current one, and all barrier phases follow running counters
+// (`g` = key tiles processed so far by this CTA, `it` = work items so far).
+struct AttnItem {
+  int b, h, q0, N, nt;
+};
+__device__ __forceinline__ bool attn_item(int w, int QB, const int* __restrict__ len, AttnItem& a) {
+  const int qb = w % QB, bh = w / QB;
+  a.h = bh % 12; a.b = bh / 12;
+  a.q0 = qb * 128;
+  a.N = len[a.b];
+  a.nt = (a.N + 63) >> 6;
+  return a.q0 < a.N;
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid_constant__ CUtensorMap tmQh,
                                                            const __grid_constant__ CUtensorMap tmQl,
@@ -172,29 +190,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid
                                                            const __grid_constant__ CUtensorMap tmVh,
                                                            const __grid_constant__ CUtensorMap tmVl,
                                                            const int* __restrict__ off, const int* __restrict__ len,
-                                                           float* __restrict__ ctx) {
+                                                           float* __restrict__ ctx, int QB, int W) {
   constexpr int NST = kAttnStages;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
-  const int N = len[b];
-  if (q0 >= N) return;                                  // (uniform per CTA, before any barrier / TMEM allocation)
-  const int nt = (N + 63) >> 6;                         // key tiles
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_h = base, q_l = base + kQPlane;
-  const uint32_t st0 = base + 2 * kQPlane;
+  auto q_h = [&](int qi) { return base + (uint32_t)qi * 2u * kQPlane; };      // Q buffer qi: hi plane, lo plane
+  auto q_l = [&](int qi) { return base + (uint32_t)qi * 2u * kQPlane + kQPlane; };
+  const uint32_t st0 = base + 4 * kQPlane;
   const uint32_t bar_base = st0 + NST * kStage;
-  const uint32_t q_full = bar_base;
   // K and V^T of a stage have their own full / empty barriers: K_j is free again as soon as S_j has been computed,
   // V^T_j only after P_j V_j; the stage ring (4 deep) is independent of the double-buffered S / P / O in TMEM
-  auto fullk_bar = [&](int s) { return bar_base + (1 + s) * 8; };
-  auto emptyk_bar = [&](int s) { return bar_base + (1 + NST + s) * 8; };
-  auto fullv_bar = [&](int s) { return bar_base + (1 + 2 * NST + s) * 8; };
-  auto emptyv_bar = [&](int s) { return bar_base + (1 + 3 * NST + s) * 8; };
-  auto sfull_bar = [&](int i) { return bar_base + (1 + 4 * NST + i) * 8; };
-  auto sfree_bar = [&](int i) { return bar_base + (3 + 4 * NST + i) * 8; };
-  auto pfull_bar = [&](int i) { return bar_base + (5 + 4 * NST + i) * 8; };
-  auto ofull_bar = [&](int i) { return bar_base + (7 + 4 * NST + i) * 8; };
-  auto ofree_bar = [&](int i) { return bar_base + (9 + 4 * NST + i) * 8; };
+  auto fullk_bar = [&](int s) { return bar_base + s * 8; };
+  auto emptyk_bar = [&](int s) { return bar_base + (NST + s) * 8; };
+  auto fullv_bar = [&](int s) { return bar_base + (2 * NST + s) * 8; };
+  auto emptyv_bar = [&](int s) { return bar_base + (3 * NST + s) * 8; };
+  auto sfull_bar = [&](int i) { return bar_base + (4 * NST + i) * 8; };
+  auto sfree_bar = [&](int i) { return bar_base + (4 * NST + 2 + i) * 8; };
+  auto pfull_bar = [&](int i) { return bar_base + (4 * NST + 4 + i) * 8; };
+  auto ofull_bar = [&](int i) { return bar_base + (4 * NST + 6 + i) * 8; };
+  auto ofree_bar = [&](int i) { return bar_base + (4 * NST + 8 + i) * 8; };
+  auto qfull_bar = [&](int i) { return bar_base + (4 * NST + 10 + i) * 8; };
+  auto qfree_bar = [&](int i) { return bar_base + (4 * NST + 12 + i) * 8; };
   const uint32_t tmem_slot = bar_base + 32 * 8;
   const uint32_t xch_base = tmem_slot + 16;             // row maxima [2][2][128] + row sums [2][128] (floats)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,13 +219,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmKh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmVh) : "memory");
-    mbar_init(q_full, 1);
     for (int s = 0; s < NST; s++) {
       mbar_init(fullk_bar(s), 1); mbar_init(emptyk_bar(s), 1); mbar_init(fullv_bar(s), 1); mbar_init(emptyv_bar(s), 1);
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(sfull_bar(s), 1); mbar_init(sfree_bar(s), 8);
       mbar_init(pfull_bar(s), 8); mbar_init(ofull_bar(s), 1); mbar_init(ofree_bar(s), 8);
+      mbar_init(qfull_bar(s), 1); mbar_init(qfree_bar(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -226,53 +242,64 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      const int qrow = off[b] + q0, krow0 = off[b], vrow = (b * 12 + h) * 64;
-      mbar_expect_tx(q_full, 2 * kQPlane);
-      tma_load_2d(q_h, &tmQh, h * 64, qrow, q_full);
-      tma_load_2d(q_l, &tmQl, h * 64, qrow, q_full);
-      auto load_k = [&](int j) {
-        const int s = j % NST;
-        mbar_wait(emptyk_bar(s), (((uint32_t)(j / NST)) & 1u) ^ 1u);
-        const uint32_t sa = st0 + s * kStage;
-        mbar_expect_tx(fullk_bar(s), 2 * kTilePlane);
-        tma_load_2d(sa, &tmKh, h * 64, krow0 + j * 64, fullk_bar(s));
-        tma_load_2d(sa + kTilePlane, &tmKl, h * 64, krow0 + j * 64, fullk_bar(s));
-      };
-      auto load_v = [&](int j) {
-        const int s = j % NST;
-        mbar_wait(emptyv_bar(s), (((uint32_t)(j / NST)) & 1u) ^ 1u);
-        const uint32_t sa = st0 + s * kStage;
-        mbar_expect_tx(fullv_bar(s), 2 * kTilePlane);
-        tma_load_2d(sa + 2 * kTilePlane, &tmVh, j * 64, vrow, fullv_bar(s));
-        tma_load_2d(sa + 3 * kTilePlane, &tmVl, j * 64, vrow, fullv_bar(s));
-      };
-      // issue order = the order in which the MMA warp needs (and frees) the buffers: K_0, K_1, V_0, K_2, V_1, ...
-      load_k(0);
-      for (int j = 0; j < nt; j++) {
-        if (j + 1 < nt) load_k(j + 1);
-        load_v(j);
+      int g = 0, it = 0;                                // key tiles / work items issued so far
+      for (int w = blockIdx.x; w < W; w += gridDim.x) {
+        AttnItem a;
+        if (!attn_item(w, QB, len, a)) continue;
+        const int qi = it & 1;
+        const int qrow = off[a.b] + a.q0, krow0 = off[a.b], vrow = (a.b * 12 + a.h) * 64;
+        mbar_wait(qfree_bar(qi), (((uint32_t)(it >> 1)) & 1u) ^ 1u);     // the S MMAs of item it - 2 are done with this Q buffer
+        mbar_expect_tx(qfull_bar(qi), 2 * kQPlane);
+        tma_load_2d(q_h(qi), &tmQh, a.h * 64, qrow, qfull_bar(qi));
+        tma_load_2d(q_l(qi), &tmQl, a.h * 64, qrow, qfull_bar(qi));
+        auto load_k = [&](int j) {
+          const int s = (g + j) % NST;
+          mbar_wait(emptyk_bar(s), (((uint32_t)((g + j) / NST)) & 1u) ^ 1u);
+          const uint32_t sa = st0 + s * kStage;
+          mbar_expect_tx(fullk_bar(s), 2 * kTilePlane);
+          tma_load_2d(sa, &tmKh, a.h * 64, krow0 + j * 64, fullk_bar(s));
+          tma_load_2d(sa + kTilePlane, &tmKl, a.h * 64, krow0 + j * 64, fullk_bar(s));
+        };
+        auto load_v = [&](int j) {
+          const int s = (g + j) % NST;
+          mbar_wait(emptyv_bar(s), (((uint32_t)((g + j) / NST)) & 1u) ^ 1u);
+          const uint32_t sa = st0 + s * kStage;
+          mbar_expect_tx(fullv_bar(s), 2 * kTilePlane);
+          tma_load_2d(sa + 2 * kTilePlane, &tmVh, j * 64, vrow, fullv_bar(s));
+          tma_load_2d(sa + 3 * kTilePlane, &tmVl, j * 64, vrow, fullv_bar(s));
+        };
+        // issue order = the order in which the MMA warp needs (and frees) the buffers: K_0, K_1, V_0, K_2, V_1, ...
+        load_k(0);
+        for (int j = 0; j < a.nt; j++) {
+          if (j + 1 < a.nt) load_k(j + 1);
+          load_v(j);
+        }
+        g += a.nt; it++;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(128, 64);
       ATT_DECL(true);
-      mbar_wait(q_full, 0u);
-      tc_fence_after();
-      ATT(0);
-      auto issue_s = [&](int j) {                      // S'_j = Q' K'_j^T, small terms first (as the mma.sync kernel)
-        const int s = j & 1, st = j % NST;
-        mbar_wait(fullk_bar(st), ((uint32_t)(j / NST)) & 1u);
+      // S'_j = Q' K'_j^T of key tile j of item `a` (global tile index gt, item counter it_), small terms first
+      auto issue_s = [&](const AttnItem& a, int j, int gt, int it_) {
+        const int s = gt & 1, st = gt % NST, qi = it_ & 1;
+        if (j == 0) {
+          mbar_wait(qfull_bar(qi), ((uint32_t)(it_ >> 1)) & 1u);
+          tc_fence_after();
+        }
+        ATT(0);
+        mbar_wait(fullk_bar(st), ((uint32_t)(gt / NST)) & 1u);
         tc_fence_after();
         ATT(1);
-        if (j >= 2) {                                  // the softmax warps have read S_{j-2} out of this buffer
-          mbar_wait(sfree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
+        if (gt >= 2) {                                 // the softmax warps have read the S tile that used this buffer
+          mbar_wait(sfree_bar(s), ((uint32_t)((gt >> 1) - 1)) & 1u);
           tc_fence_after();
         }
         ATT(2);
         const uint32_t sa = st0 + st * kStage;
         const uint32_t t_s = tmem_base + kColS0 + 64u * (uint32_t)s;
-        const uint64_t ah = umma_desc_sw128(q_h), al = umma_desc_sw128(q_l);
+        const uint64_t ah = umma_desc_sw128(q_h(qi)), al = umma_desc_sw128(q_l(qi));
         const uint64_t bh = umma_desc_sw128(sa), bl = umma_desc_sw128(sa + kTilePlane);
 #pragma unroll
         for (int k = 0; k < 4; k++) {                  // 4 x (K = 16 fp16 = 32 B) = the 64 dims of a head
@@ -283,43 +310,61 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid
         }
         umma_commit(sfull_bar(s));
         umma_commit(emptyk_bar(st));                   // K_j is consumed
+        if (j == a.nt - 1) umma_commit(qfree_bar(qi)); // the item's last S: its Q buffer is free
         ATT(3);
       };
-      issue_s(0);
-      for (int j = 0; j < nt; j++) {
-        if (j + 1 < nt) issue_s(j + 1);                // runs under the softmax of tile j
-        const int s = j & 1, st = j % NST;             // P / O buffer and stage of tile j
-        mbar_wait(fullv_bar(st), ((uint32_t)(j / NST)) & 1u);   // V^T_j has landed
-        ATT(4);
-        mbar_wait(pfull_bar(s), ((uint32_t)(j >> 1)) & 1u);     // P_j is in TMEM
-        tc_fence_after();
-        ATT(5);
-        if (j >= 2) {                                  // O_{j-2} has been read out of this O buffer
-          mbar_wait(ofree_bar(s), ((uint32_t)((j >> 1) - 1)) & 1u);
+      // first valid work item
+      int w = blockIdx.x;
+      AttnItem cur;
+      bool have = false;
+      for (; w < W; w += gridDim.x) if (attn_item(w, QB, len, cur)) { have = true; break; }
+      int g = 0, it = 0;
+      if (have) issue_s(cur, 0, 0, 0);
+      while (have) {
+        // look ahead: the next valid work item (its S_0 is issued under the last softmax of the current item)
+        AttnItem nxt;
+        bool have_n = false;
+        int wn = w + gridDim.x;
+        for (; wn < W; wn += gridDim.x) if (attn_item(wn, QB, len, nxt)) { have_n = true; break; }
+        for (int j = 0; j < cur.nt; j++) {
+          const int gt = g + j;
+          if (j + 1 < cur.nt) issue_s(cur, j + 1, gt + 1, it);      // runs under the softmax of tile j
+          else if (have_n) issue_s(nxt, 0, gt + 1, it + 1);
+          const int s = gt & 1, st = gt % NST;           // P / O buffer and stage of this tile
+          mbar_wait(fullv_bar(st), ((uint32_t)(gt / NST)) & 1u);   // V^T_j has landed
+          ATT(4);
+          mbar_wait(pfull_bar(s), ((uint32_t)(gt >> 1)) & 1u);     // P_j is in TMEM
           tc_fence_after();
-        }
-        ATT(6);
-        const uint32_t sa = st0 + st * kStage;
-        const uint32_t t_o = tmem_base + kColO + 64u * (uint32_t)s;
-        const uint32_t t_ph = tmem_base + kColP + 64u * (uint32_t)s, t_pl = t_ph + 32u;
-        const uint64_t vh = umma_desc_sw128(sa + 2 * kTilePlane), vl = umma_desc_sw128(sa + 3 * kTilePlane);
+          ATT(5);
+          if (gt >= 2) {                                 // the O tile that used this buffer has been read out
+            mbar_wait(ofree_bar(s), ((uint32_t)((gt >> 1) - 1)) & 1u);
+            tc_fence_after();
+          }
+          ATT(6);
+          const uint32_t sa = st0 + st * kStage;
+          const uint32_t t_o = tmem_base + kColO + 64u * (uint32_t)s;
+          const uint32_t t_ph = tmem_base + kColP + 64u * (uint32_t)s, t_pl = t_ph + 32u;
+          const uint64_t vh = umma_desc_sw128(sa + 2 * kTilePlane), vl = umma_desc_sw128(sa + 3 * kTilePlane);
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {               // 16 keys (8 TMEM columns of packed fp16 pairs) per UMMA
-          const uint64_t o = (uint64_t)(2 * kk);
-          umma_f16_ts(t_o, t_pl + 8u * kk, vh + o, idesc, kk ? 1u : 0u);
-          umma_f16_ts(t_o, t_ph + 8u * kk, vl + o, idesc, 1u);
-          umma_f16_ts(t_o, t_ph + 8u * kk, vh + o, idesc, 1u);
+          for (int kk = 0; kk < 4; kk++) {               // 16 keys (8 TMEM columns of packed fp16 pairs) per UMMA
+            const uint64_t o = (uint64_t)(2 * kk);
+            umma_f16_ts(t_o, t_pl + 8u * kk, vh + o, idesc, kk ? 1u : 0u);
+            umma_f16_ts(t_o, t_ph + 8u * kk, vl + o, idesc, 1u);
+            umma_f16_ts(t_o, t_ph + 8u * kk, vh + o, idesc, 1u);
+          }
+          umma_commit(ofull_bar(s));
+          umma_commit(emptyv_bar(st));                   // V^T_j is consumed
+          ATT(7);
         }
-        umma_commit(ofull_bar(s));
-        umma_commit(emptyv_bar(st));                   // V^T_j is consumed
-        ATT(7);
+        g += cur.nt; it++;
+        cur = nxt; have = have_n; w = wn;
       }
       ATT_FLUSH(0);
     }
   } else {
     // ---- softmax: 8 warps.  Warp w owns TMEM lane quadrant q = w & 3 (32 query rows, one per thread) and key half
     // kh = (w - 2) >> 2: the 32 keys [32 kh, 32 kh + 32) of every tile and, for the output, the 32 dims [32 kh, 32 kh + 32).
-    // With fp16 planes the MMA thread needs ~14 k cycles per CTA and one warp per row block needed ~39 k for its
+    // With fp16 planes the MMA thread needs ~14 k cycles per work item and one warp per row block needed ~39 k for its
     // exp / split / fold chain (role counters); two warps per row block halve that chain.  The two warps of a row
     // exchange their partial row maxima through shared memory once per tile; their partial sums stay separate until
     // the end (both are scaled to the same running maximum).
@@ -330,108 +375,119 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_umma_kernel(const __grid
     float* const xmax = reinterpret_cast<float*>(smem_raw + (xch_base - smem_u32(smem_raw)));   // [2 buffers][2 halves][128 rows]
     float* const xl = xmax + 512;                                                               // [2 halves][128 rows]
     const int pair_bar = 1 + q;                        // named barrier of the two warps of this quadrant
-    float m = -INFINITY, l = 0.f;
-    float o[32];
-#pragma unroll
-    for (int e = 0; e < 32; e++) o[e] = 0.f;
     ATT_DECL(warp == 2 && lane == 0);
-    for (int j = 0; j < nt; j++) {
-      const int s = j & 1;
-      ATT(7);
-      mbar_wait(sfull_bar(s), ((uint32_t)(j >> 1)) & 1u);
-      tc_fence_after();
-      ATT(0);
-      float sc[32];
-      {
-        uint32_t v[32];
-        tmem_ld32(tq + kColS0 + 64u * (uint32_t)s + 32u * (uint32_t)kh, v);
+    int g = 0;
+    for (int w = blockIdx.x; w < W; w += gridDim.x) {
+      AttnItem a;
+      if (!attn_item(w, QB, len, a)) continue;
+      const int N = a.N, nt = a.nt;
+      float m = -INFINITY, l = 0.f;
+      float o[32];
 #pragma unroll
-        for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(v[e]) * kSInv;     // exact: the planes' power-of-two scaling
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sfree_bar(s));
-      ATT(1);
-      // key-padding mask + online softmax; the row maximum is the maximum over both halves
-      const int kbase = j * 64 + kh * 32;
-      float cm = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 32; e++) {
-        if (kbase + e >= N) sc[e] = -INFINITY;
-        cm = fmaxf(cm, sc[e]);
-      }
-      xmax[(s * 2 + kh) * 128 + row] = cm;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-      cm = fmaxf(cm, xmax[(s * 2 + (kh ^ 1)) * 128 + row]);
-      const float mn = fmaxf(m, cm);                   // finite: every tile holds at least one valid key
-      const float corr = expf(m - mn);
-      float ps = 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
-      l = l * corr + ps;
-      m = mn;
-      ATT(2);
-      // P_j -> TMEM as fp16 hi / lo planes of 4096 p, two keys per 32-bit column (A operand of the second MMA): this
-      // warp's 32 keys are 16 columns of each plane.  MMA_{j-2} has finished reading this P buffer: this thread waited
-      // for its O tile in the previous iteration.
-      {
-        uint32_t ph[16], pl[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-          uint32_t h0, l0, h1, l1;
-          split_h(sc[2 * e] * kPScale, h0, l0);
-          split_h(sc[2 * e + 1] * kPScale, h1, l1);
-          ph[e] = h0 | (h1 << 16);
-          pl[e] = l0 | (l1 << 16);
-        }
-        tmem_st16(tq + kColP + 64u * (uint32_t)s + 16u * (uint32_t)kh, ph);
-        tmem_st16(tq + kColP + 64u * (uint32_t)s + 32u + 16u * (uint32_t)kh, pl);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pfull_bar(s));
-      ATT(3);
-      // fold in this warp's 32 dims of O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new
-      // running maximum: the same operations in the same order as add-after-rescale inside one iteration
-      if (j >= 1) {
-        const int so = (j - 1) & 1;
-        mbar_wait(ofull_bar(so), ((uint32_t)((j - 1) >> 1)) & 1u);
+      for (int e = 0; e < 32; e++) o[e] = 0.f;
+      for (int j = 0; j < nt; j++) {
+        const int gt = g + j, s = gt & 1;
+        ATT(7);
+        mbar_wait(sfull_bar(s), ((uint32_t)(gt >> 1)) & 1u);
         tc_fence_after();
-        ATT(4);
+        ATT(0);
+        float sc[32];
+        {
+          uint32_t v[32];
+          tmem_ld32(tq + kColS0 + 64u * (uint32_t)s + 32u * (uint32_t)kh, v);
+#pragma unroll
+          for (int e = 0; e < 32; e++) sc[e] = __uint_as_float(v[e]) * kSInv;     // exact: the planes' power-of-two scaling
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree_bar(s));
+        ATT(1);
+        // key-padding mask + online softmax; the row maximum is the maximum over both halves
+        const int kbase = j * 64 + kh * 32;
+        float cm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          if (kbase + e >= N) sc[e] = -INFINITY;
+          cm = fmaxf(cm, sc[e]);
+        }
+        xmax[(s * 2 + kh) * 128 + row] = cm;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        cm = fmaxf(cm, xmax[(s * 2 + (kh ^ 1)) * 128 + row]);
+        const float mn = fmaxf(m, cm);                   // finite: every tile holds at least one valid key
+        const float corr = expf(m - mn);
+        float ps = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e++) { sc[e] = expf(sc[e] - mn); ps += sc[e]; }
+        l = l * corr + ps;
+        m = mn;
+        ATT(2);
+        // P_j -> TMEM as fp16 hi / lo planes of 4096 p, two keys per 32-bit column (A operand of the second MMA): this
+        // warp's 32 keys are 16 columns of each plane.  The MMAs that read this P buffer two tiles ago are complete: this
+        // thread waited for that O tile before it got here.
+        {
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++) {                 // two keys per packed conversion (cvt.rn.f16x2.f32): same rounding
+            const float p0 = sc[2 * e] * kPScale, p1 = sc[2 * e + 1] * kPScale;
+            const __half2 hi = __floats2half2_rn(p0, p1);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+            ph[e] = *reinterpret_cast<const uint32_t*>(&hi);
+            pl[e] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
+          tmem_st16(tq + kColP + 64u * (uint32_t)s + 16u * (uint32_t)kh, ph);
+          tmem_st16(tq + kColP + 64u * (uint32_t)s + 32u + 16u * (uint32_t)kh, pl);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar(s));
+        ATT(3);
+        // fold in this warp's 32 dims of O_{j-1} (its MMAs ran under this tile's softmax), then rescale to the new
+        // running maximum: the same operations in the same order as add-after-rescale inside one iteration
+        if (j >= 1) {
+          const int go = gt - 1, so = go & 1;
+          mbar_wait(ofull_bar(so), ((uint32_t)(go >> 1)) & 1u);
+          tc_fence_after();
+          ATT(4);
+          uint32_t v[32];
+          tmem_ld32(tq + kColO + 64u * (uint32_t)so + 32u * (uint32_t)kh, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ofree_bar(so));
+#pragma unroll
+          for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]) * kOInv;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e++) o[e] *= corr;
+        ATT(5);
+      }
+      {
+        const int go = g + nt - 1, so = go & 1;
+        mbar_wait(ofull_bar(so), ((uint32_t)(go >> 1)) & 1u);
+        tc_fence_after();
         uint32_t v[32];
         tmem_ld32(tq + kColO + 64u * (uint32_t)so + 32u * (uint32_t)kh, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(ofree_bar(so));
+        if (lane == 0) mbar_arrive(ofree_bar(so));       // (the next work item reuses the buffer)
 #pragma unroll
         for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]) * kOInv;
       }
+      // the row sum is the sum of the two halves' sums, added in a fixed order
+      xl[kh * 128 + row] = l;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      if (a.q0 + row < N) {
+        const float inv = 1.0f / (xl[row] + xl[128 + row]);
+        float* dst = ctx + ((size_t)off[a.b] + a.q0 + row) * 768 + a.h * 64 + kh * 32;
 #pragma unroll
-      for (int e = 0; e < 32; e++) o[e] *= corr;
-      ATT(5);
+        for (int e = 0; e < 32; e += 4)
+          *reinterpret_cast<float4*>(dst + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // xl is rewritten by the next work item
+      ATT(6);
+      g += nt;
     }
-    {
-      const int so = (nt - 1) & 1;
-      mbar_wait(ofull_bar(so), ((uint32_t)((nt - 1) >> 1)) & 1u);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tq + kColO + 64u * (uint32_t)so + 32u * (uint32_t)kh, v);
-      tc_fence_before();
-#pragma unroll
-      for (int e = 0; e < 32; e++) o[e] += __uint_as_float(v[e]) * kOInv;
-    }
-    // the row sum is the sum of the two halves' sums, added in a fixed order
-    xl[kh * 128 + row] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-    if (q0 + row < N) {
-      const float inv = 1.0f / (xl[row] + xl[128 + row]);
-      float* dst = ctx + ((size_t)off[b] + q0 + row) * 768 + h * 64 + kh * 32;
-#pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<float4*>(dst + e) = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
-    }
-    ATT(6);
     ATT_FLUSH(8);
   }
   tc_fence_before();
@@ -493,8 +549,9 @@ void launch_attention_umma(const float* qkv, float* scratch, float* ctx, const i
   make_tmap_f16(&mKl, kl, 768, rows_total, 768, 64);
   make_tmap_f16(&mVh, vth, kVtPitch, (long long)B * 768, kVtPitch, 64);
   make_tmap_f16(&mVl, vtl, kVtPitch, (long long)B * 768, kVtPitch, 64);
-  dim3 g((max_len + 127) / 128, 12, B);
-  attn_umma_kernel<<<g, kAttnThreads, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx);
+  const int QB = (max_len + 127) / 128, W = B * 12 * QB;
+  const int nsm = device_sm_count(dev);
+  attn_umma_kernel<<<W < nsm ? W : nsm, kAttnThreads, kAttnSmem, st>>>(mQh, mQl, mKh, mKl, mVh, mVl, off, len, ctx, QB, W);
   post_launch("attention", st);
 }
 
