@@ -45,6 +45,10 @@ KKX_API int kkx_test_lstm(int device, const float* xproj, const float* whhT, int
 /* ragged batch: xproj [rows,2048], items at off[b] with len[b] rows -> out [rows,512] (pre-zeroed) */
 KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whhT, int B, const int* off,
                                 const int* len, int rows, float* out);
+/* the same with an explicit kernel variant (1 = cluster kernel, SFU gate functions; 0 = cluster kernel, libm gate
+   functions; -1 = plain one-CTA-per-item kernel) and the average device time of `reps` further launches */
+KKX_API int kkx_test_lstm_batch_v(int device, const float* xproj, const float* whhT, int B, const int* off,
+                                  const int* len, int rows, int variant, int reps, float* out, float* ms);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* ragged batch through the tcgen05 / TMEM attention kernel (kernels_attn.cu), or the mma.sync kernel (umma = 0):

@@ -198,8 +198,10 @@ void attention_umma_planes(float* scratch, int rows_total, int B, void* (&pl)[6]
 
 // Bidirectional LSTM recurrence, H=256.  xproj [rows, 2048] = x W_ih^T + b_ih + b_hh for
 // (fwd i,f,g,o | bwd i,f,g,o); whhT [2][256][1024] (k-major); out [rows, ldo] cols ocol..+512.
+// variant: 1 = cluster kernel with SFU gate functions (the tensor-core configuration), 0 = cluster kernel with libm
+// gate functions (fp32 configuration), -1 = one CTA per (item, direction) (plain kernel, tests only).
 void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
-                 const int* off, const int* len, int B, cudaStream_t st);
+                 const int* off, const int* len, int B, cudaStream_t st, int variant = 1);
 
 // InstanceNorm statistics -> AdaIN coefficients.
 //   partial sums over row chunks, then scale[b,c] = rstd*(1+gamma), shift[b,c] = beta - mean*scale

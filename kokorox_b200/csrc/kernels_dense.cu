@@ -709,7 +709,18 @@ constexpr int kHItem = 4 * kHQ;         // floats per item in an h buffer
 // the items g = 4i + q; warp w runs the gate non-linearities of the items g = w + 8i.  G = 10 and 12 exist because
 // only 15 clusters of 8 CTAs are co-resident on a B200 (cudaOccupancyMaxActiveClusters): 64 items at G = 8 need
 // 16 clusters, and the one left over used to run as a second wave, doubling the kernel's time.
-template <int G>
+// FAST (the tensor-core configuration): gate non-linearities on the SFU (ex2.approx / rcp.approx, |error| ~ 1e-7) instead
+// of libm's expf / tanhf / IEEE division.  Measured with the phase counters (KKX_LSTM_TIMING): a gate slot -- one warp,
+// one dependent chain through libm's expf, a division, the two-branch tanhf, twice -- took ~ 850 cycles, i.e. 1 940 of
+// the 6 280 cycles of a step at G = 10 (two slots on warps 0 and 1) and 845 of 1 500 at G = 1.
+__device__ __forceinline__ float lstm_sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float lstm_tanh_fast(float x) {
+  const float ax = fabsf(x), x2 = x * x;
+  const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * ax) + 1.0f);                 // |x| >= 0.15: abs error ~ 1e-7
+  const float p = ax * fmaf(x2, fmaf(x2, fmaf(x2, -17.0f / 315.0f, 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);   // next term 8e-10
+  return copysignf(ax < 0.15f ? p : t, x);
+}
+template <int G, bool FAST>
 __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __restrict__ xproj,
                                                               const float* __restrict__ whhT,
                                                               float* __restrict__ out, int ldo, int ocol,
@@ -718,8 +729,10 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
   constexpr int NW = (G + 7) / 8;                      // item slots of a warp (gate phase)
   extern __shared__ float4 lsm4[];
   float* hbuf = reinterpret_cast<float*>(lsm4);        // [2][G][4][68]
-  float* gates = hbuf + 2 * G * kHItem;                // [G][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gates + G * 128);   // [2] h-buffer "full" barriers
+  float* gates2 = hbuf + 2 * G * kHItem;               // [2][G][128], by step parity: ONE block barrier per step --
+  // the dot loop of step s + 1 writes the other buffer, and the buffer of step s is rewritten only behind the barrier
+  // of step s + 1, which every warp reaches after its gate phase of step s
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gates2 + 2 * G * 128);   // [2] h-buffer "full" barriers
   cg::cluster_group cluster = cg::this_cluster();
   const int r = (int)cluster.block_rank();             // 0..7: hidden-unit slice
   const int group = blockIdx.x >> 3, dir = blockIdx.y;
@@ -800,6 +813,7 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bcur), "r"(kStepBytes) : "memory");
     const float* hc = hbuf + (s & 1) * G * kHItem;
     float* hn_local = hbuf + ((s + 1) & 1) * G * kHItem;
+    float* gates = gates2 + (s & 1) * G * 128;
     // input projections were fetched one step ahead (xpn); fetch the next step's now so that the global
     // latency hides behind a whole step
     float2 xp[NQ];
@@ -836,51 +850,66 @@ __global__ void __launch_bounds__(256, 1) lstm_cluster_kernel(const float* __res
     LT(1)
     __syncthreads();
     LT(2)
+    // both slots' arithmetic first, branch-free (a warp without a second item recomputes the last one and drops the
+    // result), so that the two dependent chains interleave; then the stores and the hand-off
+    float hv_[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+      const int g = min(warp + 8 * i, G - 1), j = lane;
+      const float* gp = gates + g * 128;
+      float ig, fg, gg, og;
+      if (FAST) {
+        ig = lstm_sigmoid_fast(gp[j]); fg = lstm_sigmoid_fast(gp[32 + j]);
+        gg = lstm_tanh_fast(gp[64 + j]); og = lstm_sigmoid_fast(gp[96 + j]);
+      } else {
+        ig = 1.0f / (1.0f + expf(-gp[j])); fg = 1.0f / (1.0f + expf(-gp[32 + j]));
+        gg = tanhf(gp[64 + j]); og = 1.0f / (1.0f + expf(-gp[96 + j]));
+      }
+      c[i] = fg * c[i] + ig * gg;
+      hv_[i] = og * (FAST ? lstm_tanh_fast(c[i]) : tanhf(c[i]));
+    }
 #pragma unroll
     for (int i = 0; i < NW; i++) {
       const int g = warp + 8 * i, j = lane;
-      if (g < G) {
-        const float* gp = gates + g * 128;
-        const float ig = 1.0f / (1.0f + expf(-gp[j]));
-        const float fg = 1.0f / (1.0f + expf(-gp[32 + j]));
-        const float gg = tanhf(gp[64 + j]);
-        const float og = 1.0f / (1.0f + expf(-gp[96 + j]));
-        c[i] = fg * c[i] + ig * gg;
-        const float hv = og * tanhf(c[i]);
-        if (s < wlen[i]) {
-          const int t = dir == 0 ? s : wlen[i] - 1 - s;
-          out[(size_t)(woff[i] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
-        }
-        // gather 4 consecutive hidden units into one lane, push 16 bytes to every CTA of the cluster
-        const float h1 = __shfl_down_sync(0xffffffffu, hv, 1);
-        const float h2 = __shfl_down_sync(0xffffffffu, hv, 2);
-        const float h3 = __shfl_down_sync(0xffffffffu, hv, 3);
-        if ((j & 3) == 0 && s + 1 < maxN) {
-          const int u = r * 32 + j;                        // hidden unit -> padded quarter layout
-          const uint32_t dst = lstm_smem_u32(hn_local + g * kHItem + (u >> 6) * kHQ + (u & 63));
-          const uint32_t bnext = (s & 1) ? bar0 : bar1;
+      const float hv = hv_[i];
+      if (g < G && s < wlen[i]) {
+        const int t = dir == 0 ? s : wlen[i] - 1 - s;
+        out[(size_t)(woff[i] + t) * ldo + ocol + dir * 256 + r * 32 + j] = hv;
+      }
+      // gather 4 consecutive hidden units into one lane, push 16 bytes to every CTA of the cluster (spreading the 64
+      // stores of an item over all 32 lanes -- two per lane, eight shuffles -- measured 8 % slower per step)
+      const float h1 = __shfl_down_sync(0xffffffffu, hv, 1);
+      const float h2 = __shfl_down_sync(0xffffffffu, hv, 2);
+      const float h3 = __shfl_down_sync(0xffffffffu, hv, 3);
+      if (g < G && (j & 3) == 0 && s + 1 < maxN) {
+        const int u = r * 32 + j;                        // hidden unit -> padded quarter layout
+        const uint32_t dst = lstm_smem_u32(hn_local + g * kHItem + (u >> 6) * kHQ + (u & 63));
+        const uint32_t bnext = (s & 1) ? bar0 : bar1;
 #pragma unroll
-          for (int d = 0; d < 8; d++) {
-            const uint32_t ra = lstm_mapa(dst, (uint32_t)d), rb = lstm_mapa(bnext, (uint32_t)d);
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
-                         ::"r"(ra), "f"(hv), "f"(h1), "f"(h2), "f"(h3), "r"(rb) : "memory");
-          }
+        for (int d = 0; d < 8; d++) {
+          const uint32_t ra = lstm_mapa(dst, (uint32_t)d), rb = lstm_mapa(bnext, (uint32_t)d);
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                       ::"r"(ra), "f"(hv), "f"(h1), "f"(h2), "f"(h3), "r"(rb) : "memory");
         }
       }
     }
-    __syncthreads();   // gates[] is rewritten by the next step's dot loop
   }
   LT_DUMP
   cluster.sync();      // no CTA may exit while a peer can still write into its shared memory
 }
+
 template <int G>
 static void launch_lstm_cluster(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
-                                const int* off, const int* len, int B, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * G * kHItem + G * 128) * sizeof(float) + 16;
+                                const int* off, const int* len, int B, cudaStream_t st, int fast) {
+  const size_t smem = (size_t)(2 * G * kHItem + 2 * G * 128) * sizeof(float) + 16;
+  auto kern = fast ? lstm_cluster_kernel<G, true> : lstm_cluster_kernel<G, false>;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [smem] { KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+  once.run(dev, [smem] {
+    KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KKX_CUDA(cudaFuncSetAttribute(lstm_cluster_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  });
   const int groups = (B + G - 1) / G;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(8 * groups, 2, 1);
@@ -891,23 +920,17 @@ static void launch_lstm_cluster(const float* xproj, const float* whhT, float* ou
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  static const bool dbg = env_flag("KKX_LSTM_DEBUG", false);
-  if (dbg) {
-    int ncl = -1;
-    cudaOccupancyMaxActiveClusters(&ncl, lstm_cluster_kernel<G>, &cfg);
-    fprintf(stderr, "lstm_cluster<%d>: B=%d clusters=%d max active clusters=%d\n", G, B, 2 * groups, ncl);
-  }
-  KKX_CUDA(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel<G>, xproj, whhT, out, ldo, ocol, off, len, B));
+  KKX_CUDA(cudaLaunchKernelEx(&cfg, kern, xproj, whhT, out, ldo, ocol, off, len, B));
 }
 
 void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int ocol,
-                 const int* off, const int* len, int B, cudaStream_t st) {
+                 const int* off, const int* len, int B, cudaStream_t st, int variant) {
   if (g_dry_run) return;
-  static const bool simple = env_flag("KKX_LSTM_SIMPLE", false);
-  if (simple) {
+  if (variant < 0) {                    // one CTA per (item, direction): the plain reference kernel (tests only)
     dim3 g(B, 2);
     lstm_kernel<<<g, 1024, 0, st>>>(xproj, whhT, out, ldo, ocol, off, len);
   } else {
+    const int pp = variant;               // 1 = SFU gate functions, 0 = libm
     // smallest group size whose clusters are all co-resident: 15 clusters of 8 CTAs fit a B200
     // (cudaOccupancyMaxActiveClusters); one cluster too many runs as a second wave and doubles the time
     static int max_clusters[64] = {0};
@@ -918,25 +941,25 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(8 * 64, 2, 1);
       cfg.blockDim = dim3(256, 1, 1);
-      cfg.dynamicSmemBytes = (size_t)(2 * 8 * kHItem + 8 * 128) * sizeof(float) + 16;
+      cfg.dynamicSmemBytes = (size_t)(2 * 8 * kHItem + 2 * 8 * 128) * sizeof(float) + 16;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8>, &cfg) != cudaSuccess || n <= 0) { n = 15; cudaGetLastError(); }
+      if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8, true>, &cfg) != cudaSuccess || n <= 0) { n = 15; cudaGetLastError(); }
       max_clusters[dev] = n;
     }
     const int kMaxClusters = max_clusters[dev];
     auto fits = [&](int G) { return 2 * ((B + G - 1) / G) <= kMaxClusters; };
-    if (fits(1)) launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-    else if (fits(2)) launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-    else if (fits(4)) launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-    else if (fits(6)) launch_lstm_cluster<6>(xproj, whhT, out, ldo, ocol, off, len, B, st);     // 40 items (first frame group of B = 64) -> 14 clusters
-    else if (fits(8)) launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-    else if (fits(10)) launch_lstm_cluster<10>(xproj, whhT, out, ldo, ocol, off, len, B, st);   // 64 items -> 14 clusters
-    else if (fits(12)) launch_lstm_cluster<12>(xproj, whhT, out, ldo, ocol, off, len, B, st);
-    else launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st);                  // several waves anyway
+    if (fits(1)) launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
+    else if (fits(2)) launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
+    else if (fits(4)) launch_lstm_cluster<4>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
+    else if (fits(6)) launch_lstm_cluster<6>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);     // 40 items (first frame group of B = 64) -> 14 clusters
+    else if (fits(8)) launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
+    else if (fits(10)) launch_lstm_cluster<10>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);   // 64 items -> 14 clusters
+    else if (fits(12)) launch_lstm_cluster<12>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
+    else launch_lstm_cluster<8>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);                  // several waves anyway
   }
   post_launch("lstm", st);
 }

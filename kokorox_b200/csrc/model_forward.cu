@@ -169,7 +169,7 @@ void Model::token_phase(Run& r) {
   // captured once (on the second call with that count) and replayed afterwards -- ~190 launches become one.
   const bool graph_ok = opt.latency_graphs && B_ == 1 && !debug_ && !stats.profile && !stats.check_each && inj_dur_.empty();
   if (graph_ok) {
-    const GraphKey key{tok_len_[0], opt.precision * 16 + opt.attention_umma * 8 + opt.split_f16 * 4 + opt.gemm_pair * 2 + opt.fuse_planes, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
+    const GraphKey key{tok_len_[0], opt.lstm_fast_gates * 32 + opt.precision * 16 + opt.attention_umma * 8 + opt.split_f16 * 4 + opt.gemm_pair * 2 + opt.fuse_planes, tokA_.base(), d_ids_, tokL_.d_off, h_T_, h_pred_dur_};
     auto it = graphs_.find(key);
     if (it != graphs_.end() && it->second.exec) {
       r = it->second.run;
@@ -260,7 +260,7 @@ void Model::token_issue(Run& r) {
       launch_layernorm(ln, ts);
     }
     gemm(L, L, ta, 512, 512, W.te_lstm.wih, &W.te_lstm.t_ih, W.te_lstm.bias, 2048, xp_te, 2048, 0);
-    launch_lstm(xp_te, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, ts);
+    launch_lstm(xp_te, W.te_lstm.whhT, r.t_en, 512, 0, L.d_off, L.d_len, B, ts, opt.precision != 0 && opt.lstm_fast_gates);
   };
   if (fork) {
     fork_lane1();
@@ -334,7 +334,7 @@ void Model::token_issue(Run& r) {
   float* cur = xa; float* nxt = xb;
   for (int i = 0; i < 3; i++) {
     gemm(L, L, cur, 640, 640, W.dur_lstm[i].wih, &W.dur_lstm[i].t_ih, W.dur_lstm[i].bias, 2048, xp, 2048, 0);
-    launch_lstm(xp, W.dur_lstm[i].whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
+    launch_lstm(xp, W.dur_lstm[i].whhT, lo, 512, 0, L.d_off, L.d_len, B, st, opt.precision != 0 && opt.lstm_fast_gates);
     LnArgs ln;
     ln.x = lo; ln.ldx = 512; ln.ada = r.sty_pro; ln.ada_ld = W.sty_pro_n; ln.ada_off = W.dur_ada[i];
     ln.eps = 1e-5f; ln.out = nxt; ln.ldo = 640; ln.ocol = 0; ln.off = L.d_off; ln.len = L.d_len;
@@ -347,7 +347,7 @@ void Model::token_issue(Run& r) {
 
   // ---- duration head (A.1, K4)
   gemm(L, L, r.d, 640, 640, W.pred_lstm.wih, &W.pred_lstm.t_ih, W.pred_lstm.bias, 2048, xp, 2048, 0);
-  launch_lstm(xp, W.pred_lstm.whhT, lo, 512, 0, L.d_off, L.d_len, B, st);
+  launch_lstm(xp, W.pred_lstm.whhT, lo, 512, 0, L.d_off, L.d_len, B, st, opt.precision != 0 && opt.lstm_fast_gates);
   capture("dur_lstm", lo, 512, 0, 512, L, 0);
   float* logits = A.alloc<float>(R * 50);
   gemm(L, L, lo, 512, 512, W.durp_w, &W.t_durp, W.durp_b, 50, logits, 50, 0);
@@ -641,7 +641,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     set_lane_scratch(1, hi1, lo1, cap);
   }
   gemm(FR, FR, en, 640, 640, W.shared_lstm.wih, &W.shared_lstm.t_ih, W.shared_lstm.bias, 2048, xp, 2048, 0);
-  launch_lstm(xp, W.shared_lstm.whhT, shd, 512, 0, FR.d_off, FR.d_len, B, st);
+  launch_lstm(xp, W.shared_lstm.whhT, shd, 512, 0, FR.d_off, FR.d_len, B, st, opt.precision != 0 && opt.lstm_fast_gates);
   capture("shared_lstm", shd, 512, 0, 512, FR, b0);
   float* curves[2];
   if (fork) fork_lane1();

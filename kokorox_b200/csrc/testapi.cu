@@ -268,6 +268,27 @@ KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whh
   });
 }
 
+KKX_API int kkx_test_lstm_batch_v(int device, const float* xproj, const float* whhT, int B, const int* off,
+                                  const int* len, int rows, int variant, int reps, float* out, float* ms) {
+  return run(device, [&] {
+    DevBuf dx(xproj, (size_t)rows * 2048 * 4), dw(whhT, (size_t)2 * 256 * 1024 * 4), dout(out, (size_t)rows * 512 * 4);
+    DevBuf doff(off, B * 4), dlen(len, B * 4);
+    cudaEvent_t e0, e1;
+    KKX_CUDA(cudaEventCreate(&e0)); KKX_CUDA(cudaEventCreate(&e1));
+    launch_lstm(dx.as<float>(), dw.as<float>(), dout.as<float>(), 512, 0, doff.as<int>(), dlen.as<int>(), B, 0, variant);
+    KKX_CUDA(cudaEventRecord(e0, 0));
+    for (int i = 0; i < reps; i++)
+      launch_lstm(dx.as<float>(), dw.as<float>(), dout.as<float>(), 512, 0, doff.as<int>(), dlen.as<int>(), B, 0, variant);
+    KKX_CUDA(cudaEventRecord(e1, 0));
+    KKX_CUDA(cudaDeviceSynchronize());
+    float t = 0.f;
+    KKX_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = reps > 0 ? t / reps : 0.f;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)rows * 512 * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) {
   return run(device, [&] {
     DevBuf dq(qkv, (size_t)N * 2304 * 4), dout(nullptr, (size_t)N * 768 * 4);

@@ -156,6 +156,36 @@ def test_lstm_ragged_batch_groups(lib, B):
     np.testing.assert_allclose(out, ref, atol=2e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,lo,hi", [(2, 1, 90), (9, 200, 300), (40, 60, 90), (64, 500, 512), (100, 1, 40)])
+def test_lstm_kernel_variants_agree(lib, B, lo, hi):
+    """The cluster kernel with SFU gate functions (tensor-core configuration) against the one with libm gate functions
+    (fp32 configuration; same dot products) and the plain one-CTA-per-item kernel (other summation order), over
+    sequences long enough for a recurrent error to build up."""
+    rng = np.random.default_rng(100 + B)
+    lens = rng.integers(lo, hi, B).astype(np.int32)
+    offs = np.zeros(B, np.int32)
+    o = 2
+    for b in range(B):
+        offs[b] = o
+        o += int(lens[b]) + 3
+    rows = o
+    xproj = (rng.standard_normal((rows, 2048)) * 1.5).astype(np.float32)
+    whh = (rng.standard_normal((2, 256, 1024)) * 0.06).astype(np.float32)
+    outs = []
+    for variant in (1, 0, -1):
+        out = np.zeros((rows, 512), np.float32)
+        ms = C.c_float(0)
+        rc = lib.kkx_test_lstm_batch_v(0, fp(xproj), fp(whh), B, offs.ctypes.data_as(C.POINTER(C.c_int)),
+                                       lens.ctypes.data_as(C.POINTER(C.c_int)), rows, variant, 0, fp(out), C.byref(ms))
+        assert rc == 0, lib.kkx_test_last_error()
+        outs.append(out)
+    assert np.abs(outs[0]).max() > 0.05
+    np.testing.assert_allclose(outs[1], outs[2], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(outs[0], outs[1], atol=2e-5, rtol=1e-4)
+    rel = np.sqrt(((outs[0] - outs[1]) ** 2).sum() / (outs[1] ** 2).sum())
+    assert rel < 2e-6, rel
+
+
 @pytest.mark.parametrize("N", [3, 52, 130, 512])
 def test_attention_matches_torch(lib, N):
     qkv = rnd(N, 2304, seed=N)
