@@ -49,6 +49,12 @@ KKX_API int kkx_test_lstm_batch(int device, const float* xproj, const float* whh
    functions; -1 = plain one-CTA-per-item kernel) and the average device time of `reps` further launches */
 KKX_API int kkx_test_lstm_batch_v(int device, const float* xproj, const float* whhT, int B, const int* off,
                                   const int* len, int rows, int variant, int reps, float* out, float* ms);
+/* Conv1d(22, 128, k = 1) fused with the chunk statistics of its output (kernels_signal.cu): x [rows,24] (22 used),
+   w [22][128], items at off[b] (len[b] rows) -> out [rows,128] (pre-filled by the caller), part [B][nchunk][2][128] with
+   nchunk = ceil(max_len / 128); part_ref receives what launch_colstats computes from `out` */
+KKX_API int kkx_test_pointwise_conv_stats(int device, const float* x, const float* w, const float* bias, int B,
+                                          const int* off, const int* len, int rows, int max_len, float* out, float* part,
+                                          float* part_ref);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* ragged batch through the tcgen05 / TMEM attention kernel (kernels_attn.cu), or the mma.sync kernel (umma = 0):

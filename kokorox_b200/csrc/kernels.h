@@ -214,6 +214,11 @@ void launch_colstats(const float* x, int ldx, int C, float* part, const int* off
 // written ONLY as bf16 [rows, C] (statistics still from the fp32 sum) and `out` is left untouched
 void launch_add_rows_stats(const float* a, const float* b, float* out, int C, float* part, const int* off,
                            const int* len, int B, int max_len, cudaStream_t st, void* out_bf16 = nullptr);
+// out[r, co] = bias[co] + sum_ci x[r, ci] * w[ci][co] for Conv1d(22, 128, k = 1) (generator noise_convs[1]) and the chunk
+// statistics of the result (same `part` layout as launch_colstats) in one pass; fp32 SIMT, store-bound
+void launch_pointwise_conv_stats(const float* x, int ldx, int Ci, const float* w, const float* bias, float* out, int Co,
+                                 float* part, const int* off, const int* len, int B, int max_len, long long sum_m,
+                                 cudaStream_t st);
 void launch_adain_coef(const float* part, int C, int max_len, const int* len, const float* sty,
                        int sld, int soff, float eps, float* scale, float* shift, int B,
                        cudaStream_t st);

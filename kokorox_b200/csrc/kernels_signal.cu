@@ -102,6 +102,88 @@ void launch_add_rows_stats(const float* a, const float* b, float* out, int C, fl
   post_launch("add_rows_stats", st);
 }
 
+// Pointwise conv with few input channels, fused with the statistics of its output (generator stage 1: noise_convs[1]
+// = Conv1d(22, 128, k = 1) over the 120T+1 STFT frames, followed by the first AdaIN of noise_res[1]).
+//   out[r, co] = bias[co] + sum_ci x[r, ci] * w[ci][co],   part[b][chunk][2][128] = column sums / sums of squares
+// The op writes 512 B per row for 88 B read and 22 FMA per output: it is a store stream, not a GEMM.  On the tensor-core
+// path it was three passes (x -> bf16 plane padded to 64 channels, a one-k-step implicit GEMM whose single-tile CTAs
+// stored at 2.2 TB/s, and a colstats pass reading the 2.9 GB result back); here one CTA owns one statistics chunk
+// (128 rows): the x rows are staged in shared memory, a warp shares a row (broadcast reads), a thread owns 4 output
+// channels with its 4 x Ci weights in registers, stores are 512 contiguous bytes per warp, and the chunk statistics
+// leave from the same registers in a fixed order.  fp32 FMA in ascending ci: exact operands, no bf16 rounding.
+template <int CI>
+__global__ void __launch_bounds__(256) pointwise_conv_stats_kernel(const float* __restrict__ x, int ldx,
+                                                                   const float* __restrict__ w /*[CI][128]*/,
+                                                                   const float* __restrict__ bias,
+                                                                   float* __restrict__ out, float* __restrict__ part,
+                                                                   int nchunk, const int* off, const int* len) {
+  constexpr int LDS_ = 24;                         // staged row pitch (CI <= 24)
+  static_assert(CI <= LDS_, "pointwise_conv_stats: at most 24 input channels");
+  __shared__ __align__(16) float xs[kStatRows * LDS_];
+  __shared__ float red[2][8][128];
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int L = len[b];
+  const int r0 = ch * kStatRows;
+  if (r0 >= L) return;
+  const int nrows = min(kStatRows, L - r0);
+  const size_t row0 = (size_t)off[b] + r0;
+  const int t = threadIdx.x;
+  if (ldx == LDS_) {                               // contiguous block: 128-bit loads
+    const float4* src = reinterpret_cast<const float4*>(x + row0 * LDS_);
+    for (int i = t; i < kStatRows * LDS_ / 4; i += 256)
+      reinterpret_cast<float4*>(xs)[i] = (i * 4) / LDS_ < nrows ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int i = t; i < kStatRows * LDS_; i += 256) {
+      const int r = i / LDS_, c = i % LDS_;
+      xs[i] = (r < nrows && c < CI) ? x[(row0 + r) * ldx + c] : 0.f;
+    }
+  }
+  const int cq = t & 31, rl = t >> 5;              // channel quad, row lane (= warp)
+  float4 wr[CI];
+#pragma unroll
+  for (int ci = 0; ci < CI; ci++) wr[ci] = *reinterpret_cast<const float4*>(w + ci * 128 + 4 * cq);
+  const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * cq);
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
+  __syncthreads();
+  float* op = out + (row0 + rl) * 128 + 4 * cq;
+#pragma unroll 4
+  for (int r = rl; r < nrows; r += 8, op += 8 * 128) {
+    const float* xr = xs + r * LDS_;
+    float4 a = b4;
+#pragma unroll
+    for (int ci = 0; ci < CI; ci++) {
+      const float h = xr[ci];
+      a.x = fmaf(h, wr[ci].x, a.x); a.y = fmaf(h, wr[ci].y, a.y); a.z = fmaf(h, wr[ci].z, a.z); a.w = fmaf(h, wr[ci].w, a.w);
+    }
+    *reinterpret_cast<float4*>(op) = a;
+    s4.x += a.x; s4.y += a.y; s4.z += a.z; s4.w += a.w;
+    q4.x = fmaf(a.x, a.x, q4.x); q4.y = fmaf(a.y, a.y, q4.y); q4.z = fmaf(a.z, a.z, q4.z); q4.w = fmaf(a.w, a.w, q4.w);
+  }
+  *reinterpret_cast<float4*>(&red[0][rl][4 * cq]) = s4;
+  *reinterpret_cast<float4*>(&red[1][rl][4 * cq]) = q4;
+  __syncthreads();
+  {
+    const int which = t >> 7, c = t & 127;         // threads 0..127: sums, 128..255: sums of squares
+    float acc = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; y++) acc += red[which][y][c];
+    part[((size_t)b * nchunk + ch) * 2 * 128 + which * 128 + c] = acc;
+  }
+}
+void launch_pointwise_conv_stats(const float* x, int ldx, int Ci, const float* w, const float* bias, float* out, int Co,
+                                 float* part, const int* off, const int* len, int B, int max_len, long long sum_m,
+                                 cudaStream_t st) {
+  if (g_dry_run) return;
+  if (Ci != 22 || Co != 128 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w) |
+                                 reinterpret_cast<uintptr_t>(bias)) & 15))
+    throw ArgError("launch_pointwise_conv_stats: built for Conv1d(22, 128, k = 1) on 16-byte aligned tensors");
+  const int nchunk = (max_len + kStatRows - 1) / kStatRows;
+  dim3 g(nchunk, B);
+  pointwise_conv_stats_kernel<22><<<g, 256, 0, st>>>(x, ldx, w, bias, out, part, nchunk, off, len);
+  if (g_launch_stats) g_launch_stats->conv_flops += 2.0 * (double)sum_m * Co * Ci;   // counted like the GEMM path it replaces
+  post_launch("pointwise_conv_stats", st);
+}
+
 // Combine the chunk partials (fp64, fixed order) -> AdaIN coefficients.  Block = 32 channels x 32 chunk
 // slices (1024 threads): the grid is tiny (C/32 x B blocks), so the kernel is pure load latency -- every thread
 // keeps 4 chunks (8 independent loads) in flight; the additions keep a fixed order, so the result depends only

@@ -158,6 +158,9 @@ struct Options {
   int fuse_planes = 1;
   // bf16 decoder convs with Co % 256 == 0: CTA pairs (256 x 256 tiles, half the weight tile per CTA, persistent)
   int conv_pair = 1;
+  // generator stage 1: noise_convs[1] (22 -> 128, k = 1) as one fp32 store-stream pass that also emits the statistics of its
+  // output (kernels_signal.cu pointwise_conv_stats_kernel) instead of bf16 plane + implicit GEMM + statistics pass
+  int fuse_noise_stats = 1;
   // LSTM gate non-linearities on the SFU (ex2 / rcp approximations, |error| ~ 1e-7) in the tensor-core configuration;
   // precision = 0 always uses libm's expf / tanhf and IEEE division
   int lstm_fast_gates = 1;

@@ -730,7 +730,14 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   float* w1 = A.alloc<float>(n120);
   float* t1 = A.alloc<float>(n120);
   float* acc1 = A.alloc<float>(n120);
-  if (opt.precision == 1) {
+  float* pxs1 = nullptr;      // chunk statistics of xs1 when the conv below produced them
+  if (opt.precision == 1 && opt.fuse_noise_stats && !use_stream_bf16(128, W.nres[1].k, B)) {
+    // Conv1d(22, 128, k = 1) is a store stream (22 FMA per output): one fp32 pass that also emits the statistics the
+    // first AdaIN of noise_res[1] needs, instead of bf16 plane + one-k-step implicit GEMM + colstats
+    pxs1 = A.alloc<float>((size_t)B * ((G120.max_len + kStatRows - 1) / kStatRows) * 2 * 128);
+    launch_pointwise_conv_stats(har, 24, 22, W.nc1_w, W.nc1_b, xs1, 128, pxs1, G120.d_off, G120.d_len, B, G120.max_len,
+                                G120.sum_len, st1);
+  } else if (opt.precision == 1) {
     void* hb = A.alloc_bytes((size_t)G120.rows * W.t_nc1.Cpad * 2);
     launch_apply_bf16(har, 24, 22, nullptr, nullptr, ACT_NONE, 0.f, nullptr, hb, W.t_nc1.Cpad, G120.rows, G120.d_off,
                       G120.d_len, B, G120.max_len, st1);
@@ -738,7 +745,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
   } else {
     launch_conv_f32(gemm_args(G120, har, 24, 22, W.nc1_w, W.nc1_b, 128, xs1, 128, 0), st1);
   }
-  arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false);
+  arb(r, A, W.nres[1], xs1, G120, sty_dec, W.sty_dec_n, w1, t1, xs1, 1.f, false, pxs1);
   capture("gen.x_source.1", xs1, 128, 0, 128, G120, b0);
   use_lane(0);
 

@@ -289,6 +289,27 @@ KKX_API int kkx_test_lstm_batch_v(int device, const float* xproj, const float* w
   });
 }
 
+KKX_API int kkx_test_pointwise_conv_stats(int device, const float* x, const float* w, const float* bias, int B,
+                                          const int* off, const int* len, int rows, int max_len, float* out, float* part,
+                                          float* part_ref) {
+  return run(device, [&] {
+    const int nchunk = (max_len + kStatRows - 1) / kStatRows;
+    const size_t np = (size_t)B * nchunk * 2 * 128;
+    DevBuf dx(x, (size_t)rows * 24 * 4), dw(w, (size_t)22 * 128 * 4), db(bias, 128 * 4), dout(out, (size_t)rows * 128 * 4);
+    DevBuf dp(part, np * 4), dpr(part_ref, np * 4), doff(off, B * 4), dlen(len, B * 4);
+    long long sum_m = 0;
+    for (int b = 0; b < B; b++) sum_m += len[b];
+    launch_pointwise_conv_stats(dx.as<float>(), 24, 22, dw.as<float>(), db.as<float>(), dout.as<float>(), 128, dp.as<float>(),
+                                doff.as<int>(), dlen.as<int>(), B, max_len, sum_m, 0);
+    // the statistics pass it replaces, over the tensor just written
+    launch_colstats(dout.as<float>(), 128, 128, dpr.as<float>(), doff.as<int>(), dlen.as<int>(), B, max_len, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)rows * 128 * 4, cudaMemcpyDeviceToHost));
+    KKX_CUDA(cudaMemcpy(part, dp.p, np * 4, cudaMemcpyDeviceToHost));
+    KKX_CUDA(cudaMemcpy(part_ref, dpr.p, np * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) {
   return run(device, [&] {
     DevBuf dq(qkv, (size_t)N * 2304 * 4), dout(nullptr, (size_t)N * 768 * 4);

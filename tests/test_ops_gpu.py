@@ -186,6 +186,46 @@ def test_lstm_kernel_variants_agree(lib, B, lo, hi):
     assert rel < 2e-6, rel
 
 
+@pytest.mark.parametrize("lens", [[1], [127], [128], [129], [1000, 5, 260, 384]])
+def test_pointwise_conv_with_statistics(lib, lens):
+    """noise_convs[1] (22 -> 128, k = 1) as one fp32 pass that also emits the per-128-row column sums: the output
+    against numpy fp64, the statistics against the colstats pass over that output, gap rows untouched."""
+    rng = np.random.default_rng(len(lens) * 1000 + lens[0])
+    B = len(lens)
+    lens_a = np.asarray(lens, np.int32)
+    offs = np.zeros(B, np.int32)
+    o = 32
+    for b in range(B):
+        offs[b] = o
+        o += int(lens_a[b]) + 32
+    rows = o
+    x = rng.standard_normal((rows, 24)).astype(np.float32) * 3
+    x[:, 22:] = np.nan                                   # pad columns must never be read into the result
+    w = (rng.standard_normal((22, 128)) * 0.3).astype(np.float32)
+    bias = rng.standard_normal(128).astype(np.float32)
+    max_len = int(lens_a.max())
+    nchunk = (max_len + 127) // 128
+    out = np.full((rows, 128), 7.5, np.float32)
+    part = np.zeros((B, nchunk, 2, 128), np.float32)
+    part_ref = np.zeros_like(part)
+    rc = lib.kkx_test_pointwise_conv_stats(0, fp(x), fp(w), fp(bias), B, offs.ctypes.data_as(C.POINTER(C.c_int)),
+                                           lens_a.ctypes.data_as(C.POINTER(C.c_int)), rows, max_len, fp(out), fp(part),
+                                           fp(part_ref))
+    assert rc == 0, lib.kkx_test_last_error()
+    ref = x[:, :22].astype(np.float64) @ w.astype(np.float64) + bias
+    touched = np.zeros(rows, bool)
+    for b in range(B):
+        sl = slice(offs[b], offs[b] + lens_a[b])
+        touched[sl] = True
+        np.testing.assert_allclose(out[sl], ref[sl], atol=2e-5, rtol=2e-6)
+        for ch in range((lens_a[b] + 127) // 128):
+            blk = out[offs[b] + ch * 128: offs[b] + min(lens_a[b], ch * 128 + 128)].astype(np.float64)
+            np.testing.assert_allclose(part[b, ch, 0], blk.sum(0), atol=2e-3, rtol=1e-5)
+            np.testing.assert_allclose(part[b, ch, 1], (blk ** 2).sum(0), atol=2e-3, rtol=1e-5)
+            np.testing.assert_allclose(part[b, ch], part_ref[b, ch], atol=2e-3, rtol=1e-5)
+    assert np.all(out[~touched] == 7.5)
+
+
 @pytest.mark.parametrize("N", [3, 52, 130, 512])
 def test_attention_matches_torch(lib, N):
     qkv = rnd(N, 2304, seed=N)
