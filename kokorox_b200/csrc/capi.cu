@@ -740,6 +740,7 @@ KKX_API int kkx_set_option(kkx_ctx* ctx, const char* key, int64_t value) {
     else if (k == "attention_umma") o.attention_umma = value ? 1 : 0;
     else if (k == "lstm_fast_gates") o.lstm_fast_gates = value ? 1 : 0;
     else if (k == "fuse_noise_stats") o.fuse_noise_stats = value ? 1 : 0;
+    else if (k == "ups_phase_loop") o.ups_phase_loop = value < 0 ? 0 : value > 3 ? 3 : (int)value;
     else if (k == "split_f16") o.split_f16 = value ? 1 : 0;
     else if (k == "stream_bf16") o.stream_bf16 = value ? 1 : 0;
     else if (k == "fuse_phases") o.fuse_phases = value ? 1 : 0;

@@ -77,6 +77,7 @@ struct TcConvArgs {
   int nphase = 1;
   int phase_pad[10] = {0};
   int phase_oro[10] = {0};
+  int phase_loop = 0;            // Co = 128 only: one CTA per m-tile loops over the phases (conv_tc_multi_kernel<.., PH>)
   int debug = 0;  // KKX_TC_DEBUG bit mask (perf experiments): 1 skip global stores, 2 skip MMA issue, 4 skip TMEM loads
 };
 void launch_conv_tc(const TcConvArgs& a, cudaStream_t st);

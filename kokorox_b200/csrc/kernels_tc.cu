@@ -392,7 +392,11 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 // pipeline runs straight across tile boundaries and alternates between two TMEM accumulators, so
 // the epilogue of tile i (TMEM -> smem transpose -> global) overlaps the main loop of tile i+1, and
 // barrier init / TMEM allocation / descriptor prefetch are paid once per TPC tiles.
-template <int BN, int STAGES, int TPC>
+// PH (phase-fused ConvTranspose1d, a.nphase two-tap phase convs): the CTA's "tiles" are the PHASES of ONE 128-row m-tile
+// (same activation rows, phase p's weights at rows [p*Co, (p+1)*Co) of the stacked map, output rows m*ors + phase_oro[p]):
+// barrier init / TMEM allocation / descriptor prefetch are paid once per a.nphase tiles, each phase's epilogue runs under
+// the next phase's loads and MMAs, and the activation tile of the later phases comes out of L2.
+template <int BN, int STAGES, int TPC, bool PH = false>
 __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             TcConvArgs a) {
@@ -411,9 +415,9 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
 
   const int b = blockIdx.z;
   const int mlen = a.m_len[b];
-  const int m_base = blockIdx.x * (128 * TPC);
+  const int m_base = PH ? blockIdx.x * 128 : blockIdx.x * (128 * TPC);
   if (m_base >= mlen) return;  // CTA-uniform
-  const int ntiles = min(TPC, (mlen - m_base + 127) >> 7);
+  const int ntiles = PH ? a.nphase : min(TPC, (mlen - m_base + 127) >> 7);
   const int n0 = blockIdx.y * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kchunks = a.Cpad >> 6;
@@ -441,7 +445,8 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
     if (lane == 0) {
       int g = 0;
       for (int ti = 0; ti < ntiles; ti++) {
-        const int row0 = a.in_off[b] + m_base + ti * 128 - a.pad;
+        const int row0 = PH ? a.in_off[b] + m_base - a.phase_pad[ti] : a.in_off[b] + m_base + ti * 128 - a.pad;
+        const int wrow = PH ? ti * a.Co + n0 : n0;
         for (int it = 0; it < num_k; it++, g++) {
           const int s = g % STAGES;
           const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
           const uint32_t sa = base + s * STAGE_BYTES;
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
           tma_load_2d(sa, &tmA, c0, row0 + tap * a.dil, full_bar(s));
-          tma_load_2d(sa + A_BYTES, &tmB, tap * a.Cpad + c0, n0, full_bar(s));
+          tma_load_2d(sa + A_BYTES, &tmB, tap * a.Cpad + c0, wrow, full_bar(s));
         }
       }
     }
@@ -488,7 +493,8 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
     const int c4 = (t & 7) << 2;
     int chunk_ctr = 0;
     for (int ti = 0; ti < ntiles; ti++) {
-      const int m0 = m_base + ti * 128;
+      const int m0 = PH ? m_base : m_base + ti * 128;
+      const int oro = PH ? a.phase_oro[ti] : a.oro;
       const int acc = ti & 1;
       auto fetch = [&](int c, float4* rv) {
         const int n = n0 + c + c4;
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
           const int mm = m0 + (t >> 3) + 16 * i;
           rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.res && n < a.Co && mm < mlen) {
-            const int orow = mm * a.ors + a.oro;
+            const int orow = mm * a.ors + oro;
             const float* rp = a.res + ((size_t)(res_off + (orow >> a.res_shift)) * a.ldr + a.rcol + n);
             if (vec) rv[i] = *reinterpret_cast<const float4*>(rp);
             else { rv[i].x = rp[0]; if (n + 1 < a.Co) rv[i].y = rp[1]; if (n + 2 < a.Co) rv[i].z = rp[2]; if (n + 3 < a.Co) rv[i].w = rp[3]; }
@@ -541,7 +547,7 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
             if (a.eact == ACT_GELU_NEW) { o.x = gelu_new_f(o.x); o.y = gelu_new_f(o.y); o.z = gelu_new_f(o.z); o.w = gelu_new_f(o.w); }
             o.x = (o.x + rv[i].x) * a.oscale; o.y = (o.y + rv[i].y) * a.oscale;
             o.z = (o.z + rv[i].z) * a.oscale; o.w = (o.w + rv[i].w) * a.oscale;
-            float* op = a.out + ((size_t)(out_off + mm * a.ors + a.oro) * a.ldo + a.ocol + n);
+            float* op = a.out + ((size_t)(out_off + mm * a.ors + oro) * a.ldo + a.ocol + n);
             if (vec) {
               if (a.accumulate) { const float4 pvv = *reinterpret_cast<const float4*>(op); o.x += pvv.x; o.y += pvv.y; o.z += pvv.z; o.w += pvv.w; }
               *reinterpret_cast<float4*>(op) = o;
@@ -564,6 +570,185 @@ __global__ void __launch_bounds__(192) conv_tc_multi_kernel(const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
+}
+
+// Weight-resident phase conv (generator stage-1 up-sampling, ConvTranspose1d(256, 128, k = 12, s = 6) as 6 two-tap phase
+// convs).  The kernels above stream the weight tiles with the activations: 8 k-steps x 32 KB per (m-tile, phase), i.e. the
+// whole 768 KB weight set once per 128 input rows -- 11.5 GB through L2 per launch at 5.75 M output rows, which is what
+// the launch took (7 TB/s out of L2; its 2.9 GB of output would stream in 0.5 ms).  Here a persistent CTA owns ONE phase:
+// the phase's weights (2 taps x 4 chunks x 16 KB = 128 KB) are loaded once and stay in shared memory, the CTA walks a
+// contiguous range of the batch's m-tiles, and only activation tiles go through the TMA ring (3 stages of 16 KB).  Two
+// TMEM accumulators alternate, so the epilogue of a tile runs under the MMAs of the next.  Same MMAs in the same order per
+// output element as conv_tc_kernel -> identical bits.  grid = (CTAs per phase, nphase).
+constexpr int kUpsStages = 3;     // 128 KB of weights + 3 x 16 KB activation stages + 36 KB epilogue staging = 212 KB
+__global__ void __launch_bounds__(192) conv_phase_resident_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmB,
+                                                                  TcConvArgs a) {
+  constexpr int BN = 128, STAGES = kUpsStages;
+  constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = BN * 128;
+  constexpr int PITCH = 36;
+  constexpr uint32_t STG_BYTES = 2 * 128 * PITCH * 4;
+  constexpr int MAXK = 8;                               // resident weight tiles (ks * Cpad / 64)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = base;                         // [num_k][B_BYTES]
+  const uint32_t a_base = w_base + MAXK * B_BYTES;      // [STAGES][A_BYTES]
+  const uint32_t stg_base = a_base + STAGES * A_BYTES;
+  const uint32_t bar_base = stg_base + STG_BYTES;       // full[S], empty[S], tfull[2], tempty[2], wfull
+  const uint32_t tmem_slot = bar_base + (2 * STAGES + 5) * 8;
+  auto full_bar = [&](int s) { return bar_base + s * 8; };
+  auto empty_bar = [&](int s) { return bar_base + (STAGES + s) * 8; };
+  auto tfull_bar = [&](int j) { return bar_base + (2 * STAGES + j) * 8; };
+  auto tempty_bar = [&](int j) { return bar_base + (2 * STAGES + 2 + j) * 8; };
+  const uint32_t wfull_bar = bar_base + (2 * STAGES + 4) * 8;
+
+  const int ph = blockIdx.y;
+  const int t_begin = (int)(((long long)a.ntiles_m * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)a.ntiles_m * (blockIdx.x + 1)) / gridDim.x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = a.Cpad >> 6;
+  const int num_k = a.ks * kchunks;
+  auto locate = [&](int tile, int& b, int& m0) {        // tile -> (item, first row); tile_start = prefix sum of ceil(len/128)
+    int lo = 0, hi = a.B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (a.tile_start[mid] <= tile) lo = mid; else hi = mid;
+    }
+    b = lo; m0 = (tile - a.tile_start[lo]) * 128;
+  };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int j = 0; j < 2; j++) { mbar_init(tfull_bar(j), 1); mbar_init(tempty_bar(j), 4); }
+    mbar_init(wfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0 && t_begin < t_end) {
+      mbar_expect_tx(wfull_bar, (uint32_t)num_k * B_BYTES);
+      for (int it = 0; it < num_k; it++) {
+        const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+        tma_load_2d(w_base + it * B_BYTES, &tmB, tap * a.Cpad + c0, ph * a.Co, wfull_bar);
+      }
+      int g = 0;
+      for (int tile = t_begin; tile < t_end; tile++) {
+        int b, m0;
+        locate(tile, b, m0);
+        const int row0 = a.in_off[b] + m0 - a.phase_pad[ph];
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          const uint32_t par = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(empty_bar(s), par ^ 1u);
+          const int tap = it / kchunks, c0 = (it - tap * kchunks) << 6;
+          mbar_expect_tx(full_bar(s), A_BYTES);
+          tma_load_2d(a_base + s * A_BYTES, &tmA, c0, row0 + tap * a.dil, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && t_begin < t_end) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      mbar_wait(wfull_bar, 0);
+      int g = 0, ti = 0;
+      for (int tile = t_begin; tile < t_end; tile++, ti++) {
+        const int acc = ti & 1;
+        mbar_wait(tempty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // accumulator drained?
+        tc_fence_after();
+        const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+        for (int it = 0; it < num_k; it++, g++) {
+          const int s = g % STAGES;
+          const uint32_t par = (uint32_t)(g / STAGES) & 1u;
+          mbar_wait(full_bar(s), par);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(a_base + s * A_BYTES), bd = umma_desc_sw128(w_base + it * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(td, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int et = q * 32 + lane;
+    float* stage_f = reinterpret_cast<float*>(smem_raw + (stg_base - smem_u32(smem_raw)));
+    const int t = threadIdx.x - 64;
+    const int c4 = (t & 7) << 2;
+    const int oro = a.phase_oro[ph];
+    int chunk_ctr = 0, ti = 0;
+    for (int tile = t_begin; tile < t_end; tile++, ti++) {
+      int b, m0;
+      locate(tile, b, m0);
+      const int mlen = a.m_len[b];
+      const int out_off = a.out_off[b];
+      const int acc = ti & 1;
+      mbar_wait(tfull_bar(acc), (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        if (c + 32 >= BN) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
+        }
+        float* buf = stage_f + (chunk_ctr & 1) * (128 * PITCH);
+        chunk_ctr++;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(buf + et * PITCH + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int n = c + c4;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bb = *reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = (t >> 3) + 16 * i;
+          const int mm = m0 + row;
+          if (mm >= mlen) continue;
+          float4 o = *reinterpret_cast<const float4*>(buf + row * PITCH + c4);
+          o.x = fmaf(o.x, a.wscale, bb.x); o.y = fmaf(o.y, a.wscale, bb.y); o.z = fmaf(o.z, a.wscale, bb.z); o.w = fmaf(o.w, a.wscale, bb.w);
+          o.x = (o.x + 0.f) * a.oscale; o.y = (o.y + 0.f) * a.oscale; o.z = (o.z + 0.f) * a.oscale; o.w = (o.w + 0.f) * a.oscale;
+          *reinterpret_cast<float4*>(a.out + ((size_t)(out_off + mm * a.ors + oro) * a.ldo + a.ocol + n)) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+static bool conv_phase_resident_ok(const TcConvArgs& a) {
+  return a.nphase > 1 && a.Co == 128 && !a.tf32 && !a.res && !a.accumulate && a.eact == ACT_NONE && a.tile_start && a.ntiles_m > 0 &&
+         a.ks * (a.Cpad >> 6) <= 8 && a.vec4 && a.ldo % 4 == 0 && a.ocol % 4 == 0;
+}
+static void launch_conv_phase_resident(const TcConvArgs& a, cudaStream_t st) {
+  constexpr int smem = 8 * 128 * 128 + kUpsStages * 128 * 128 + 2 * 128 * 36 * 4 + (2 * kUpsStages + 5) * 8 + 16 + 1024;
+  static DevOnce once;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_phase_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+  const int per_phase = std::max(1, std::min(device_sm_count(dev) / a.nphase, a.ntiles_m));
+  dim3 g(per_phase, a.nphase, 1);
+  conv_phase_resident_kernel<<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
+                                                   *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 // Final phase of the persistent split-precision GEMMs (bias, activation, residual, scale, stores) for one epilogue warp:
@@ -1453,16 +1638,16 @@ static void launch_conv_pair_t(const TcConvArgs& a, cudaStream_t st) {
 }
 static void launch_conv_pair(const TcConvArgs& a, cudaStream_t st) { launch_conv_pair_t<256>(a, st); }
 
-template <int BN, int STAGES, int TPC>
+template <int BN, int STAGES, int TPC, bool PH = false>
 static void launch_tc_multi(const TcConvArgs& a, cudaStream_t st) {
   constexpr int smem = STAGES * (128 * 128 + BN * 128) + 2 * 128 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
   static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel<BN, STAGES, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
-  dim3 g((a.max_m + 128 * TPC - 1) / (128 * TPC), (a.Co + BN - 1) / BN, a.B);
-  conv_tc_multi_kernel<BN, STAGES, TPC><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
-                                                             *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
+  once.run(dev, [] { KKX_CUDA(cudaFuncSetAttribute(conv_tc_multi_kernel<BN, STAGES, TPC, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+  dim3 g(PH ? (a.max_m + 127) / 128 : (a.max_m + 128 * TPC - 1) / (128 * TPC), (a.Co + BN - 1) / BN, a.B);
+  conv_tc_multi_kernel<BN, STAGES, TPC, PH><<<g, 192, smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tmA),
+                                                                 *reinterpret_cast<const CUtensorMap*>(a.tmB), a);
 }
 
 template <int BN, int STAGES, int MODE, int CL = 1>
@@ -1571,7 +1756,14 @@ void launch_conv_tc(const TcConvArgs& a0, cudaStream_t st) {
   // the other's TMA/MMA main loop (TMEM: 2 x 256 columns = the whole 512-column file)
   int pdev = 0;
   cudaGetDevice(&pdev);
-  if (conv_tc_takes_pair_bf16(a, device_sm_count(pdev))) launch_conv_pair(a, st);   // wide convs of big batches: CTA pairs
+  if (a.phase_loop == 3 && conv_phase_resident_ok(a)) {
+    launch_conv_phase_resident(a, st);     // stage-1 up-sampling of a batch: persistent CTAs with one phase's weights resident
+  } else if (a.nphase > 1 && a.Co == 128 && a.phase_loop && !a.res && !a.accumulate) {
+    // one CTA loops over the phases of its m-tile (2 stages: two CTAs per SM; 3: one)
+    if (a.phase_loop == 2) launch_tc_multi<128, 3, 1, true>(a, st);
+    else launch_tc_multi<128, 2, 1, true>(a, st);
+  }
+  else if (conv_tc_takes_pair_bf16(a, device_sm_count(pdev))) launch_conv_pair(a, st);   // wide convs of big batches: CTA pairs
   else if (a.Co > 128) launch_tc<256, 2, 0>(a, st);
   else if (a.Co > 64) launch_tc<128, 2, 0>(a, st);   // 65 KB smem -> three CTAs per SM
   else launch_tc<64, 4, 0>(a, st);

@@ -161,6 +161,10 @@ struct Options {
   // generator stage 1: noise_convs[1] (22 -> 128, k = 1) as one fp32 store-stream pass that also emits the statistics of its
   // output (kernels_signal.cu pointwise_conv_stats_kernel) instead of bf16 plane + implicit GEMM + statistics pass
   int fuse_noise_stats = 1;
+  // stage-1 up-sampling conv (256 -> 128, 6 phases): one CTA per 128-row m-tile loops over the phases with a pipeline that
+  // runs across them (1 = two-stage ring, two CTAs per SM; 2 = three stages, one CTA per SM; 0 = one CTA per (tile, phase));
+  // 3 = persistent CTAs that keep ONE phase's weights resident in shared memory and stream only activation tiles
+  int ups_phase_loop = 3;
   // LSTM gate non-linearities on the SFU (ex2 / rcp approximations, |error| ~ 1e-7) in the tensor-core configuration;
   // precision = 0 always uses libm's expf / tanhf and IEEE division
   int lstm_fast_gates = 1;

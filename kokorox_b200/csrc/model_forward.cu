@@ -839,7 +839,7 @@ void Model::frame_phase(Run& r, int b0, int b1, bool dry) {
     a.Cpad = W.tups1_all.Cpad; a.Ci = W.tups1_all.Ci; a.Co = 128; a.ks = 2; a.dil = -1;
     a.in_off = G20.d_off; a.m_len = G20.d_len; a.max_m = G20.max_len; a.B = B; a.sum_m = G20.sum_len;
     a.bias = W.ups1_b; a.out = x1; a.ldo = 128; a.ocol = 0; a.out_off = G120.d_off; a.ors = 6;
-    a.nphase = 6;
+    a.nphase = 6; a.phase_loop = opt.ups_phase_loop; a.tile_start = G20.d_tiles128; a.ntiles_m = G20.ntiles128;
     for (int ph = 0; ph < 6; ph++) { const int q0 = ph < 3 ? 1 : 0; a.phase_pad[ph] = -q0; a.phase_oro[ph] = q0 * 6 + ph - 3 + 1; }
     launch_conv_tc(a, st);
   } else

@@ -502,12 +502,18 @@ def test_phase_fused_upsampling_is_bit_identical(model):
         model.set_option("fuse_phases", 0)
         ref = [o.copy() for o in model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds)]
         model.set_option("fuse_phases", 1)
-        got = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds)
-        assert all(np.array_equal(x, y) for x, y in zip(ref, got))
+        # "ups_phase_loop": the stage-1 launch as one CTA per m-tile looping over the 6 phases (1: two-stage ring, 2: three
+        # stages), as persistent CTAs with one phase's weights resident (3), or as one CTA per (m-tile, phase) (0) -- the same MMAs in the same order per output element
+        for loop in (0, 1, 2, 3):
+            model.set_option("ups_phase_loop", loop)
+            got = model.infer_batch([c[0] for c in cases], [c[1] for c in cases], speeds)
+            assert all(np.array_equal(x, y) for x, y in zip(ref, got)), f"ups_phase_loop = {loop} changed the result"
+        model.set_option("ups_phase_loop", 3)
         one = model.infer_one(cases[1][0], cases[1][1], speeds[1])
         assert np.array_equal(one, ref[1])
     finally:
-        model.set_option("fuse_phases", 0)
+        model.set_option("fuse_phases", 1)          # the library defaults
+        model.set_option("ups_phase_loop", 3)
         model.set_option("precision", 0)
 
 
