@@ -15,8 +15,8 @@
 //                      V^T [(item, head, d), key] (pitch 512), so that both MMAs take K-major operands straight from
 //                      128B-swizzled TMA boxes (keys beyond the item's length are zero-filled up to a multiple of 64).
 //                      (Big batches skip it: the QKV GEMM's final warps write the planes, kernels_tc.cu.)
-//   attn_umma_kernel   one CTA per (item, head, 128 query rows), 10 warps:
-//       warp 0     TMA producer: the Q planes once, then a 2-stage ring of K and V^T tiles of 64 keys
+//   attn_umma_kernel   persistent CTAs over the (item, head, 128 query rows) work items, 10 warps:
+//       warp 0     TMA producer: the Q planes per work item (prefetched), a 4-stage ring of K and V^T tiles of 64 keys
 //       warp 1     MMA issuer:  S_j = Q K_j^T (M 128, N 64 keys, K 64: 12 UMMAs) into one of two TMEM S buffers,
 //                               O_j = P_j V_j  (A = P from TENSOR MEMORY, B = V^T tile: 12 UMMAs) into a TMEM O tile
 //       warps 2-9  softmax, two warps per block of 32 query rows (each takes 32 of a tile's 64 keys and 32 of the 64 output
