@@ -427,6 +427,32 @@ def test_bf16_residual_stream_parity(model, oracle, n_tokens, seed):
         model.set_option("precision", 0)
 
 
+def test_fused_noise_conv_is_closer_to_the_oracle(model, oracle):
+    """"fuse_noise_stats": the generator's Conv1d(22, 128, k = 1) over the STFT frames in fp32 with the AdaIN statistics of
+    its output from the same pass, against bf16 operands on the tensor cores + a separate statistics pass.  The stage the
+    conv feeds (gen.x_source.1 = noise_res[1] of it) must stay inside the tensor-core bar either way and must not get
+    worse with the fp32 conv; the waveform stays inside 3e-2 / 0.15."""
+    ids, style = synth_case(120, 5, 105)
+    noise = make_noise(50 * len(ids))
+    ref = oracle.forward(ids, style, 1.0, noise=noise, stages=True)
+    teacher = {"pred_dur": ref["pred_dur"], "F0": ref["stages"]["F0"], "N": ref["stages"]["N"]}
+    model.set_option("precision", 1)
+    try:
+        err = {}
+        for fused in (0, 1):
+            model.set_option("fuse_noise_stats", fused)
+            audio, dur = run_cuda(model, ids, style, 1.0, noise, stages=True, teacher=teacher)
+            assert np.array_equal(dur, ref["pred_dur"])
+            err[fused] = (rel_l2(ref["stages"]["gen.x_source.1"], model.debug_stage("gen.x_source.1")), rel_l2(ref["audio"], audio))
+            assert err[fused][0] < 3e-2 and err[fused][1] < 3e-2, err
+            assert np.abs(ref["audio"] - audio).max() < 0.15
+        print("x_source.1 / audio rel-L2, bf16 tensor-core conv vs fp32 fused conv:", err)
+        assert err[1][0] <= err[0][0] * 1.05, err
+    finally:
+        model.set_option("fuse_noise_stats", 1)
+        model.set_option("precision", 0)
+
+
 @pytest.mark.parametrize("opts", [{"attention_umma": 0, "split_f16": 0}, {"attention_umma": 1, "split_f16": 0},
                                   {"attention_umma": 0, "split_f16": 1}, {"attention_umma": 1, "split_f16": 1}])
 @pytest.mark.parametrize("n_tokens,seed,speed", [(50, 0, 1.0), (300, 4, 1.3), (510, 1, 1.0), (510, 1000, 1.0)])
