@@ -55,6 +55,11 @@ KKX_API int kkx_test_lstm_batch_v(int device, const float* xproj, const float* w
 KKX_API int kkx_test_pointwise_conv_stats(int device, const float* x, const float* w, const float* bias, int B,
                                           const int* off, const int* len, int rows, int max_len, float* out, float* part,
                                           float* part_ref);
+/* row LayerNorm of x (+ res) [rows,C] with optional affine w / b [C], per-item AdaLN (ada = gamma [C] then beta [C]),
+   LeakyReLU slope (1 = none); optional fp16 hi / lo operand planes of 16 * result (raw half bits) */
+KKX_API int kkx_test_layernorm(int device, const float* x, const float* res, const float* w, const float* b,
+                               const float* ada, int rows, int C, float eps, float slope, float* out,
+                               unsigned short* pl_hi, unsigned short* pl_lo);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* ragged batch through the tcgen05 / TMEM attention kernel (kernels_attn.cu), or the mma.sync kernel (umma = 0):

@@ -178,11 +178,94 @@ __global__ void __launch_bounds__(256) layernorm_kernel(LnArgs a) {
   }
 }
 
+// The same row normalisation with the row held in registers: one 128-bit load per 4 channels (x and the residual are
+// read ONCE instead of three times), 128-bit stores of the fp32 result and 64-bit stores of the operand planes.  A lane
+// owns channels 4 (lane + 32 i) .. + 3, i < NV = C / 128.  (The scalar kernel above made three passes of 4-byte
+// accesses and 2-byte plane stores: ~3 TB/s on the 32 768 x 768 ALBERT rows.)
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(LnArgs a) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * 8 + warp;
+  if (t >= a.len[b]) return;
+  const size_t row = (size_t)a.off[b] + t;
+  const float4* x4 = reinterpret_cast<const float4*>(a.x + row * a.ldx);
+  const float4* r4 = a.res ? reinterpret_cast<const float4*>(a.res + row * a.ldr) : nullptr;
+  constexpr int C = NV * 128;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    v[i] = x4[lane + 32 * i];
+    if (r4) { const float4 rr = r4[lane + 32 * i]; v[i].x += rr.x; v[i].y += rr.y; v[i].z += rr.z; v[i].w += rr.w; }
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q = fmaf(v[i].x, v[i].x, q); q = fmaf(v[i].y, v[i].y, q); q = fmaf(v[i].z, v[i].z, q); q = fmaf(v[i].w, v[i].w, q);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)C + a.eps);
+  const float* ada = a.ada ? a.ada + (size_t)b * a.ada_ld + a.ada_off : nullptr;
+  float* o = a.out + row * a.ldo + a.ocol;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const int c = 4 * (lane + 32 * i);
+    float e[4] = {v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd};
+    if (a.w) {
+      const float4 w4 = *reinterpret_cast<const float4*>(a.w + c), b4 = *reinterpret_cast<const float4*>(a.b + c);
+      e[0] = e[0] * w4.x + b4.x; e[1] = e[1] * w4.y + b4.y; e[2] = e[2] * w4.z + b4.z; e[3] = e[3] * w4.w + b4.w;
+    }
+    if (ada) {
+      const float4 g4 = *reinterpret_cast<const float4*>(ada + c), h4 = *reinterpret_cast<const float4*>(ada + C + c);
+      e[0] = (1.0f + g4.x) * e[0] + h4.x; e[1] = (1.0f + g4.y) * e[1] + h4.y;
+      e[2] = (1.0f + g4.z) * e[2] + h4.z; e[3] = (1.0f + g4.w) * e[3] + h4.w;
+    }
+    if (a.slope != 1.f) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) e[k] = e[k] > 0.f ? e[k] : e[k] * a.slope;
+    }
+    *reinterpret_cast<float4*>(o + c) = make_float4(e[0], e[1], e[2], e[3]);
+    if (a.pl_hi) {   // operand planes for the next split-FP16 GEMM (same arithmetic as apply_f16x2_kernel)
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float sv = fminf(fmaxf(e[k] * kSplitF16Scale, -65504.f), 65504.f);
+        hi[k] = __float2half_rn(sv);
+        lo[k] = __float2half_rn(sv - __half2float(hi[k]));
+      }
+      const __half2 h01 = __halves2half2(hi[0], hi[1]), h23 = __halves2half2(hi[2], hi[3]);
+      const __half2 l01 = __halves2half2(lo[0], lo[1]), l23 = __halves2half2(lo[2], lo[3]);
+      *reinterpret_cast<uint2*>(static_cast<__half*>(a.pl_hi) + row * a.pl_ld + c) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      *reinterpret_cast<uint2*>(static_cast<__half*>(a.pl_lo) + row * a.pl_ld + c) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+  }
+}
+
 void launch_layernorm(const LnArgs& a, cudaStream_t st) {
   if (g_dry_run) return;
   if (a.max_len <= 0) return;
   dim3 g((a.max_len + 7) / 8, a.B);
-  layernorm_kernel<<<g, 256, 0, st>>>(a);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = a.C % 128 == 0 && a.C <= 1024 && a.ldx % 4 == 0 && a.ldo % 4 == 0 && a.ocol % 4 == 0 && al16(a.x) && al16(a.out) &&
+                   (!a.res || (a.ldr % 4 == 0 && al16(a.res))) && (!a.w || (al16(a.w) && al16(a.b))) &&
+                   (!a.ada || (a.ada_ld % 4 == 0 && a.ada_off % 4 == 0 && al16(a.ada))) &&
+                   (!a.pl_hi || (a.pl_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(a.pl_hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(a.pl_lo) & 7) == 0));
+  // one choice per shape, never per batch: a batch and its single calls take the same kernel
+  if (vec && a.C == 768) layernorm_vec_kernel<6><<<g, 256, 0, st>>>(a);
+  else if (vec && a.C == 512) layernorm_vec_kernel<4><<<g, 256, 0, st>>>(a);
+  else if (vec && a.C == 1024) layernorm_vec_kernel<8><<<g, 256, 0, st>>>(a);
+  else if (vec && a.C == 256) layernorm_vec_kernel<2><<<g, 256, 0, st>>>(a);
+  else if (vec && a.C == 128) layernorm_vec_kernel<1><<<g, 256, 0, st>>>(a);
+  else layernorm_kernel<<<g, 256, 0, st>>>(a);
   post_launch("layernorm", st);
 }
 

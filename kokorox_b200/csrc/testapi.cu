@@ -310,6 +310,33 @@ KKX_API int kkx_test_pointwise_conv_stats(int device, const float* x, const floa
   });
 }
 
+KKX_API int kkx_test_layernorm(int device, const float* x, const float* res, const float* w, const float* b,
+                               const float* ada, int rows, int C, float eps, float slope, float* out,
+                               unsigned short* pl_hi, unsigned short* pl_lo) {
+  return run(device, [&] {
+    const size_t n = (size_t)rows * C;
+    DevBuf dx(x, n * 4), dr(res, res ? n * 4 : 0), dw(w, w ? (size_t)C * 4 : 0), db(b, b ? (size_t)C * 4 : 0);
+    DevBuf da(ada, ada ? (size_t)2 * C * 4 : 0), dout(nullptr, n * 4), dhi(nullptr, pl_hi ? n * 2 : 0), dlo(nullptr, pl_lo ? n * 2 : 0);
+    int meta[2] = {0, rows};
+    DevBuf dm(meta, sizeof meta);
+    LnArgs a;
+    a.x = dx.as<float>(); a.ldx = C;
+    if (res) { a.res = dr.as<float>(); a.ldr = C; }
+    if (w) { a.w = dw.as<float>(); a.b = db.as<float>(); }
+    if (ada) { a.ada = da.as<float>(); a.ada_ld = 2 * C; a.ada_off = 0; }
+    a.eps = eps; a.slope = slope; a.out = dout.as<float>(); a.ldo = C; a.ocol = 0;
+    a.off = dm.as<int>(); a.len = dm.as<int>() + 1; a.B = 1; a.max_len = rows; a.C = C;
+    if (pl_hi) { a.pl_hi = dhi.p; a.pl_lo = dlo.p; a.pl_ld = C; }
+    launch_layernorm(a, 0);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, n * 4, cudaMemcpyDeviceToHost));
+    if (pl_hi) {
+      KKX_CUDA(cudaMemcpy(pl_hi, dhi.p, n * 2, cudaMemcpyDeviceToHost));
+      KKX_CUDA(cudaMemcpy(pl_lo, dlo.p, n * 2, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) {
   return run(device, [&] {
     DevBuf dq(qkv, (size_t)N * 2304 * 4), dout(nullptr, (size_t)N * 768 * 4);

@@ -1,6 +1,7 @@
 """GPU tests (-m gpu): each hand-written kernel in isolation against the matching torch op,
 through the op-level hooks of include/kkx_test.h."""
 import ctypes as C
+import ctypes as C_
 
 import numpy as np
 import pytest
@@ -224,6 +225,45 @@ def test_pointwise_conv_with_statistics(lib, lens):
             np.testing.assert_allclose(part[b, ch, 1], (blk ** 2).sum(0), atol=2e-3, rtol=1e-5)
             np.testing.assert_allclose(part[b, ch], part_ref[b, ch], atol=2e-3, rtol=1e-5)
     assert np.all(out[~touched] == 7.5)
+
+
+@pytest.mark.parametrize("C,rows,res,affine,ada,slope,planes", [
+    (768, 37, True, True, False, 1.0, True),      # ALBERT: LN(x + residual), planes for the next GEMM (vector kernel)
+    (768, 5, False, True, False, 1.0, False),
+    (512, 64, False, False, True, 1.0, False),    # AdaLayerNorm of the duration encoder
+    (512, 9, False, True, False, 0.2, False),     # channel LN + LeakyReLU of the text encoder
+    (128, 20, False, True, False, 1.0, True),
+    (640, 11, True, True, True, 1.0, True),       # no vector instantiation: scalar kernel
+])
+def test_layernorm_kernels(lib, C, rows, res, affine, ada, slope, planes):
+    """layernorm_vec_kernel (row in registers, 128-bit accesses) and the scalar kernel against torch fp64; the operand
+    planes must hold hi + lo = 16 * the fp32 result to fp32 accuracy (what the split-FP16 GEMM reads next)."""
+    rng = np.random.default_rng(C + rows)
+    x = (rng.standard_normal((rows, C)) * 2 + 0.3).astype(np.float32)
+    r = rng.standard_normal((rows, C)).astype(np.float32) if res else None
+    w = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32) if affine else None
+    b = (0.1 * rng.standard_normal(C)).astype(np.float32) if affine else None
+    ad = (0.3 * rng.standard_normal(2 * C)).astype(np.float32) if ada else None
+    out = np.zeros((rows, C), np.float32)
+    hi = np.zeros((rows, C), np.uint16) if planes else None
+    lo = np.zeros((rows, C), np.uint16) if planes else None
+    u16 = lambda a: a.ctypes.data_as(C_.POINTER(C_.c_ushort)) if a is not None else None  # noqa: E731
+    fpn = lambda a: fp(a) if a is not None else None  # noqa: E731
+    rc = lib.kkx_test_layernorm(0, fp(x), fpn(r), fpn(w), fpn(b), fpn(ad), rows, C, C_.c_float(1e-5), C_.c_float(slope),
+                                fp(out), u16(hi), u16(lo))
+    assert rc == 0, lib.kkx_test_last_error()
+    t = torch.from_numpy(x).double() + (torch.from_numpy(r).double() if res else 0)
+    ref = torch.nn.functional.layer_norm(t, (C,), eps=1e-5)
+    if affine:
+        ref = ref * torch.from_numpy(w).double() + torch.from_numpy(b).double()
+    if ada:
+        ref = (1 + torch.from_numpy(ad[:C]).double()) * ref + torch.from_numpy(ad[C:]).double()
+    if slope != 1.0:
+        ref = torch.where(ref > 0, ref, ref * slope)
+    np.testing.assert_allclose(out, ref.numpy(), atol=3e-6, rtol=3e-6)
+    if planes:
+        got = hi.view(np.float16).astype(np.float64) + lo.view(np.float16).astype(np.float64)
+        np.testing.assert_allclose(got, 16.0 * out.astype(np.float64), atol=2e-6, rtol=2e-7)
 
 
 @pytest.mark.parametrize("N", [3, 52, 130, 512])
