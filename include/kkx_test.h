@@ -60,6 +60,12 @@ KKX_API int kkx_test_pointwise_conv_stats(int device, const float* x, const floa
 KKX_API int kkx_test_layernorm(int device, const float* x, const float* res, const float* w, const float* b,
                                const float* ada, int rows, int C, float eps, float slope, float* out,
                                unsigned short* pl_hi, unsigned short* pl_lo);
+/* im2col operand producer of noise_convs[0] (22 of 24 input columns, k = 12, stride 6, pad 3): in [rows_in,24] fp32 with
+   items at in_off[b] (in_len[b] rows) -> out [rows_out,Cpad] bf16 bits (pre-filled by the caller) with items at out_off[b]
+   (out_len[b] rows) and 32 zeroed gap rows around each; generic = 1 forces the element-wise kernel */
+KKX_API int kkx_test_im2col(int device, const float* in, int rows_in, int B, const int* in_off, const int* in_len,
+                            const int* out_off, const int* out_len, int rows_out, int max_out_len, int Cpad, int generic,
+                            unsigned short* out);
 /* qkv [N,2304] -> ctx [N,768] */
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx);
 /* ragged batch through the tcgen05 / TMEM attention kernel (kernels_attn.cu), or the mma.sync kernel (umma = 0):

@@ -109,7 +109,7 @@ void launch_apply_bf16(const float* x, int ldx, int C, const float* scale, const
                        const int* off, const int* len, int B, int max_len, cudaStream_t st);
 void launch_im2col_bf16(const float* in, int ldi, int C, int ks, int stride, int pad, void* out, int Cpad,
                         int rows_total, const int* in_off, const int* in_len, const int* out_off,
-                        const int* out_len, int B, int max_out_len, cudaStream_t st);
+                        const int* out_len, int B, int max_out_len, cudaStream_t st, int force_generic = 0);
 void launch_pool_up_bf16(const float* in, int ldi, const float* scale, const float* shift, float slope,
                          const float* w, const float* bias, int C, void* out, int Cpad, int rows_total,
                          const int* in_off, const int* in_len, const int* out_off, int B, int max_len,

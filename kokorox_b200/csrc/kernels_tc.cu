@@ -1949,14 +1949,72 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const float* __restric
     out[(size_t)r * Cpad + k] = __float2bfloat16_rn(v);
   }
 }
+// The same gather for noise_convs[0] (C = 22 of ldi = 24, k = 12, stride 6, pad 3) with compile-time geometry: the KS input
+// rows of an output row are ONE contiguous window of KS * 24 floats (output column tap * 22 + c <- window index tap * 24 + c),
+// and consecutive output rows' windows overlap by half.  A CTA stages the input rows of its RPB output rows in shared memory
+// with 128-bit loads and every thread writes 8 consecutive bf16 (one 16-byte store).  The generic kernel above did one
+// 4-byte load, two integer divisions and one 2-byte store per element (1.2 TB/s).
+template <int C, int LDI, int KS, int STRIDE, int PAD, int RPB>
+__global__ void __launch_bounds__(256) im2col_bf16_fast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                               int Cpad, int rows_total, const int* in_off, const int* in_len,
+                                                               const int* out_off, const int* out_len) {
+  constexpr int WROWS = (RPB - 1) * STRIDE + KS;        // input rows a CTA touches
+  __shared__ __align__(16) float win[WROWS * LDI];
+  const int b = blockIdx.y;
+  const int Lo = out_len[b], oo = out_off[b], Li = in_len[b], io = in_off[b];
+  const int r_begin = oo - kGapRows;
+  const int r_end = (b == (int)gridDim.y - 1) ? rows_total : oo + Lo + kGapRows;
+  const int rb = r_begin + blockIdx.x * RPB;
+  if (rb >= r_end) return;
+  const int re = min(r_end, rb + RPB);
+  const int m0 = rb - oo;                               // first output row of the CTA relative to the item (may be < 0)
+  const int ir0 = m0 * STRIDE - PAD;                    // first input row of the window
+  for (int i = threadIdx.x; i < WROWS * LDI / 4; i += 256) {
+    const int ir = ir0 + (i * 4) / LDI;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ir >= 0 && ir < Li) v = *reinterpret_cast<const float4*>(in + (size_t)(io + ir) * LDI + (i * 4) % LDI);
+    reinterpret_cast<float4*>(win)[i] = v;
+  }
+  __syncthreads();
+  const int chunks = Cpad >> 3;                         // 16-byte output chunks per row
+  for (int i = threadIdx.x; i < (re - rb) * chunks; i += 256) {
+    const int rl = i / chunks, k0 = (i - rl * chunks) << 3;
+    const int m = m0 + rl;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (m >= 0 && m < Lo) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int k = k0 + e;
+        const int tap = k / C, c = k - tap * C;
+        v[e] = k < KS * C ? win[(rl * STRIDE + tap) * LDI + c] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        w[e] = *reinterpret_cast<const uint32_t*>(&p);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)(rb + rl) * Cpad + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 void launch_im2col_bf16(const float* in, int ldi, int C, int ks, int stride, int pad, void* out, int Cpad,
                         int rows_total, const int* in_off, const int* in_len, const int* out_off,
-                        const int* out_len, int B, int max_out_len, cudaStream_t st) {
+                        const int* out_len, int B, int max_out_len, cudaStream_t st, int force_generic) {
   if (g_dry_run) return;
   const int rows = max_out_len + 2 * kGapRows + 8;
-  dim3 g((rows + 7) / 8, B);
-  im2col_bf16_kernel<<<g, 256, 0, st>>>(in, ldi, C, ks, stride, pad, (__nv_bfloat16*)out, Cpad, rows_total,
-                                        in_off, in_len, out_off, out_len);
+  if (!force_generic && C == 22 && ldi == 24 && ks == 12 && stride == 6 && pad == 3 && Cpad % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    constexpr int RPB = 32;
+    dim3 g((rows + RPB - 1) / RPB, B);
+    im2col_bf16_fast_kernel<22, 24, 12, 6, 3, RPB><<<g, 256, 0, st>>>(in, (__nv_bfloat16*)out, Cpad, rows_total, in_off, in_len,
+                                                                      out_off, out_len);
+  } else {
+    dim3 g((rows + 7) / 8, B);
+    im2col_bf16_kernel<<<g, 256, 0, st>>>(in, ldi, C, ks, stride, pad, (__nv_bfloat16*)out, Cpad, rows_total,
+                                          in_off, in_len, out_off, out_len);
+  }
   post_launch("im2col_bf16", st);
 }
 

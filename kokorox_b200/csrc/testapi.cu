@@ -337,6 +337,19 @@ KKX_API int kkx_test_layernorm(int device, const float* x, const float* res, con
   });
 }
 
+KKX_API int kkx_test_im2col(int device, const float* in, int rows_in, int B, const int* in_off, const int* in_len,
+                            const int* out_off, const int* out_len, int rows_out, int max_out_len, int Cpad, int generic,
+                            unsigned short* out) {
+  return run(device, [&] {
+    DevBuf di(in, (size_t)rows_in * 24 * 4), dout(out, (size_t)rows_out * Cpad * 2);
+    DevBuf dio(in_off, B * 4), dil(in_len, B * 4), doo(out_off, B * 4), dol(out_len, B * 4);
+    launch_im2col_bf16(di.as<float>(), 24, 22, 12, 6, 3, dout.p, Cpad, rows_out, dio.as<int>(), dil.as<int>(), doo.as<int>(),
+                       dol.as<int>(), B, max_out_len, 0, generic);
+    KKX_CUDA(cudaDeviceSynchronize());
+    KKX_CUDA(cudaMemcpy(out, dout.p, (size_t)rows_out * Cpad * 2, cudaMemcpyDeviceToHost));
+  });
+}
+
 KKX_API int kkx_test_attention(int device, const float* qkv, int N, float* ctx) {
   return run(device, [&] {
     DevBuf dq(qkv, (size_t)N * 2304 * 4), dout(nullptr, (size_t)N * 768 * 4);

@@ -266,6 +266,44 @@ def test_layernorm_kernels(lib, C, rows, res, affine, ada, slope, planes):
         np.testing.assert_allclose(got, 16.0 * out.astype(np.float64), atol=2e-6, rtol=2e-7)
 
 
+@pytest.mark.parametrize("frames", [[1], [7, 40], [33, 2, 100]])
+def test_im2col_fast_kernel_is_bit_identical(lib, frames):
+    """noise_convs[0] operand gather (k = 12, stride 6, pad 3 over the 120T+1 STFT frames -> 20T rows of 12 x 22 columns):
+    the shared-memory kernel against the element-wise one, bit for bit, and against numpy."""
+    rng = np.random.default_rng(sum(frames))
+    B = len(frames)
+    out_len = np.asarray([20 * t for t in frames], np.int32)
+    in_len = np.asarray([120 * t + 1 for t in frames], np.int32)
+    in_off = np.zeros(B, np.int32); out_off = np.zeros(B, np.int32)
+    oi, oo = 32, 32
+    for b in range(B):
+        in_off[b], out_off[b] = oi, oo
+        oi += int(in_len[b]) + 32
+        oo += int(out_len[b]) + 32 + 8
+    rows_in, rows_out = oi, oo          # 32 + 8 rows behind the last item: what one launch's grid covers (max_len + 72 rows per item)
+    x = rng.standard_normal((rows_in, 24)).astype(np.float32)
+    Cpad = 320
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))  # noqa: E731
+    outs = []
+    for generic in (1, 0):
+        out = np.full((rows_out, Cpad), 0x7fc0, np.uint16)           # bf16 NaN bits: untouched rows stay visible
+        rc = lib.kkx_test_im2col(0, fp(x), rows_in, B, ip(in_off), ip(in_len), ip(out_off), ip(out_len), rows_out,
+                                 int(out_len.max()), Cpad, generic, out.ctypes.data_as(C.POINTER(C.c_ushort)))
+        assert rc == 0, lib.kkx_test_last_error()
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    got = (outs[1].astype(np.uint32) << 16).view(np.float32)
+    for b in range(B):
+        for m in (0, 1, int(out_len[b]) // 2, int(out_len[b]) - 1):
+            ref = np.zeros(Cpad, np.float32)
+            for tap in range(12):
+                ir = m * 6 + tap - 3
+                if 0 <= ir < in_len[b]:
+                    ref[tap * 22:(tap + 1) * 22] = x[in_off[b] + ir, :22]
+            ref_bf = (torch.from_numpy(ref).to(torch.bfloat16).to(torch.float32)).numpy()
+            assert np.array_equal(got[out_off[b] + m], ref_bf), (b, m)
+
+
 @pytest.mark.parametrize("N", [3, 52, 130, 512])
 def test_attention_matches_torch(lib, N):
     qkv = rnd(N, 2304, seed=N)
