@@ -1016,11 +1016,11 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
     const int pp = variant;               // 1 = SFU gate functions, 0 = libm
     // smallest group size whose clusters are all co-resident: 15 clusters of 8 CTAs fit a B200
     // (cudaOccupancyMaxActiveClusters); one cluster too many runs as a second wave and doubles the time
-    static int max_clusters[64] = {0};
+    static std::atomic<int> max_clusters[64];      // 0 = not asked yet (two threads may both ask: same answer)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 64) dev = 63;
-    if (max_clusters[dev] == 0) {       // depends on how the part's GPCs are populated: ask, do not assume
+    if (max_clusters[dev].load(std::memory_order_relaxed) == 0) {       // depends on how the part's GPCs are populated: ask, do not assume
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(8 * 64, 2, 1);
       cfg.blockDim = dim3(256, 1, 1);
@@ -1031,9 +1031,9 @@ void launch_lstm(const float* xproj, const float* whhT, float* out, int ldo, int
       cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel<8, true>, &cfg) != cudaSuccess || n <= 0) { n = 15; cudaGetLastError(); }
-      max_clusters[dev] = n;
+      max_clusters[dev].store(n, std::memory_order_relaxed);
     }
-    const int kMaxClusters = max_clusters[dev];
+    const int kMaxClusters = max_clusters[dev].load(std::memory_order_relaxed);
     auto fits = [&](int G) { return 2 * ((B + G - 1) / G) <= kMaxClusters; };
     if (fits(1)) launch_lstm_cluster<1>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);
     else if (fits(2)) launch_lstm_cluster<2>(xproj, whhT, out, ldo, ocol, off, len, B, st, pp);

@@ -591,12 +591,12 @@ void launch_sine_source(const float* f0, const int* f0_off, const int* f0_len, c
 __constant__ float c_cos20[20];
 __constant__ float c_sin20[20];
 __constant__ float c_hann20[20];
-static bool g_tables_ready[64] = {false};
-
 static void ensure_tables() {
+  // once per device, and safe when two sessions on two threads reach their first STFT together
+  static DevOnce once;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && g_tables_ready[dev]) return;
+  once.run(dev, [] {
   float cs[20], sn[20], hw[20];
   for (int j = 0; j < 20; j++) {
     cs[j] = (float)cos(2.0 * M_PI * j / 20.0);
@@ -607,7 +607,7 @@ static void ensure_tables() {
   KKX_CUDA(cudaMemcpyToSymbol(c_cos20, cs, sizeof cs));
   KKX_CUDA(cudaMemcpyToSymbol(c_sin20, sn, sizeof sn));
   KKX_CUDA(cudaMemcpyToSymbol(c_hann20, hw, sizeof hw));
-  if (dev < 64) g_tables_ready[dev] = true;
+  });
 }
 
 __global__ void __launch_bounds__(128) stft_kernel(const float* __restrict__ x,
