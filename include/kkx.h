@@ -193,8 +193,12 @@ KKX_API int kkx_fetch_staged(kkx_ctx* ctx, float* dst_audio, int64_t capacity, i
  *   "attention_umma" (tcgen05 attention), "split_f16" (fp16 instead of tf32 operand planes; fp32-grade either way, but
  *   not the same bits), "gemm_pair" (split-precision GEMMs on CTA pairs, tcgen05 cta_group::2), "conv_pair" (the
  *   decoder's wide bf16 convs on CTA pairs), "fuse_planes" (LayerNorm / FFN / QKV GEMM write the next kernel's operand
- *   planes directly), "fuse_phases" (ConvTranspose1d phases in one launch); "stream_bf16" (default 0) keeps the
- *   res-block residual stream in bf16.
+ *   planes directly), "fuse_phases" (ConvTranspose1d phases in one launch), "ups_phase_loop" (default 3: the stage-1
+ *   up-sampling conv on persistent CTAs with resident weights; 1 / 2 = one CTA per row tile looping over the phases,
+ *   0 = one CTA per (tile, phase); same bits); "lstm_fast_gates" (SFU gate functions in the LSTM recurrence of the
+ *   tensor-core configuration; fp32-grade, not the same bits as libm) and "fuse_noise_stats" (the generator's 22 -> 128
+ *   noise conv in fp32 together with the statistics of its output instead of bf16 operands on the tensor cores);
+ *   "stream_bf16" (default 0) keeps the res-block residual stream in bf16.
  * kkx_get_stat keys: "launches", "last_frames", "gpu_us", "precision", "coalesced_batches",
  * "coalesced_requests", "coalesced_largest", "async_batches", "async_requests", "frame_groups",
  * "group_first:<g>" (first item of frame group g of the last run), "weights_sessions" (sessions sharing this
