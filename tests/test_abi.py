@@ -42,6 +42,22 @@ def test_no_torch_types_in_the_abi():
     assert "torch" not in src and "at::" not in src and "std::" not in src
 
 
+def test_every_session_option_is_documented():
+    """Every key kkx_set_option accepts (csrc/capi.cu) is described in the public header and in INTEGRATION.md's option
+    table: a maintainer must be able to find what a switch does without reading the library."""
+    capi = open(os.path.join(ROOT, "kokorox_b200", "csrc", "capi.cu")).read()
+    body = capi[capi.index("KKX_API int kkx_set_option"):]
+    body = body[:body.index("KKX_API", 10)]
+    keys = set(re.findall(r'k == "(\w+)"', body))
+    assert {"precision", "coalesce", "max_frames", "gemm_pair", "lstm_fast_gates", "ups_phase_loop"} <= keys
+    header = open(os.path.join(ROOT, "include", "kkx.h")).read()
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing_h = sorted(k for k in keys if f'"{k}"' not in header)
+    missing_i = sorted(k for k in keys if f"`{k}`" not in integ)
+    assert not missing_h, f"not described in include/kkx.h: {missing_h}"
+    assert not missing_i, f"not in INTEGRATION.md's option table: {missing_i}"
+
+
 def _has_gpu():
     try:
         import torch
